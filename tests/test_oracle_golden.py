@@ -1,0 +1,203 @@
+"""CPU: pin oracle/pcnerf_oracle.py against fixtures produced by executing the reference (oracle/make_golden.py)."""
+import numpy as np
+import torch
+
+import pcnerf_oracle as orc
+from conftest import golden
+
+STRIDE = 17
+BIG = ("layer1.3.weight", "layer1.6.weight", "layer1.9.weight", "layer2.0.weight", "layer2.2.weight",
+       "layer2.4.weight", "layer2.6.weight")
+LAM = (1.0, 1e6, 1e5)
+
+
+def test_aabb_leaf_bit_exact():
+    g = golden("aabb_leaf")
+    o, dirs = g["origin"], g["dirs"]
+    x_min, x_max, y_min, y_max, z_min, z_max = g["parent"]
+    assert np.array_equal(orc.compute_far_bound(o, dirs, x_max, x_min, y_max, y_min, z_max, z_min), g["far_parent"])
+    inside, idx = orc.find_aabb_box(g["centres"], g["child_bounds"], g["points"])
+    assert np.array_equal(inside, g["inside"]) and np.array_equal(idx, g["idx"])
+    bb = g["child_bounds_bigger"]
+    P, D = o[None, None, :], dirs[:, None, :]
+    f, n, r = orc.compute_far_bound0429(P, D, bb[None, :, :3], bb[None, :, 3:])
+    assert np.array_equal(f, g["f0429"]) and np.array_equal(n, g["n0429"]) and np.array_equal(r, g["r0429"])
+    f, n, r = orc.compute_far_bound0606(P, D, bb[None, :, :3], bb[None, :, 3:])
+    assert np.array_equal(f, g["f0606"]) and np.array_equal(n, g["n0606"]) and np.array_equal(r, g["r0606"])
+    n, r = orc.compute_far_bound0406(P, D, bb[None, :, :3], bb[None, :, 3:])
+    assert np.array_equal(n, g["n0406"], equal_nan=True) and np.array_equal(r, g["r0406"], equal_nan=True)
+    pmin, pmax = np.array([x_min, y_min, z_min]), np.array([x_max, y_max, z_max])
+    assert np.array_equal(orc.ray_aabb_distances(o, dirs, pmin, pmax), g["slab"])
+    centre = (g["child_bounds"][:, :3] + g["child_bounds"][:, 3:]) / 2
+    dtr = np.stack([orc.distance_to_ray(o, d, centre) for d in dirs[:64]])
+    assert np.array_equal(dtr, g["dist_to_ray"], equal_nan=True)
+
+
+def test_aabb_pack_and_groups_bit_exact():
+    g = golden("aabb_leaf")
+    for variant in ("maicity", "kitti"):
+        gp = golden("aabb_pack_" + variant)
+        rays, _ = orc.pack_train_rays_from_dirs(g["origin"], g["dirs"], g["dist"], g["points"], g["centres"],
+                                                g["child_bounds"], g["child_bounds_bigger"], tuple(g["parent"]),
+                                                float(gp["surface_expand"]), variant)
+        assert np.array_equal(rays, gp["rays"], equal_nan=True)
+    x_min, x_max, y_min, y_max, z_min, z_max = g["parent"]
+    pmin, pmax = np.array([x_min, y_min, z_min]), np.array([x_max, y_max, z_max])
+    sbl = g["child_bounds"] + np.array([-0.025] * 3 + [0.025] * 3)
+    for method in (2, 1):
+        for grow in (0.005, 0.05):
+            gg = golden("aabb_groups_m%d_g%s" % (method, str(grow).replace(".", "p")))
+            n = int(gg["nray"])
+            rays, ranges, other, _ = orc.build_candidate_groups(g["origin"], g["dirs"][:n], g["dist"][:n],
+                                                                g["child_bounds"], sbl, pmin, pmax, method, grow)
+            assert np.array_equal(rays, gg["rays"]) and np.array_equal(ranges, gg["ranges"])
+            assert np.array_equal(other, gg["other"])
+
+
+def test_head_train_and_sample_pdf():
+    g = golden("head_train")
+    rays = torch.from_numpy(g["rays"])
+    for zk, pk, fk, dk, depk, gk in (("z", "p", "free", "depthloss", "depth", "grad_p"),
+                                     ("zu", "pu", "free_u", "depthloss_u", "depth_u", "grad_pu")):
+        z = torch.from_numpy(g[zk])
+        p = torch.from_numpy(g[pk]).requires_grad_(True)
+        fl, dl, depth, w = orc.train_head(p, z, rays, None, 0.0, 1e-10, 1)
+        np.testing.assert_allclose(fl.item(), g[fk], rtol=1e-6)
+        np.testing.assert_allclose(dl.item(), g[dk], rtol=1e-6)
+        np.testing.assert_allclose(depth.detach().numpy(), g[depk], rtol=1e-6, atol=1e-6)
+        if zk == "z":
+            np.testing.assert_allclose(w.detach().numpy(), g["w"], rtol=1e-6, atol=1e-9)
+            loss = 0.1 * orc.smooth_l1_mean(10 * depth, 10 * rays[:, 14]) + 1e6 * fl + 1e5 * dl
+        else:
+            loss = 1e6 * fl + 1e5 * dl + depth.sum()
+        loss.backward()
+        np.testing.assert_allclose(p.grad.numpy(), g[gk], rtol=2e-4, atol=1e-6 * np.abs(g[gk]).max())
+    z, w = torch.from_numpy(g["z"]), torch.from_numpy(g["w"])
+    mid = .5 * (z[..., 1:] + z[..., :-1])
+    assert np.array_equal(orc.sample_pdf(mid, w[..., 1:-1], 128, det=True).numpy(), g["zs_det"])
+    assert np.array_equal(orc.sample_pdf(mid, w[..., 1:-1], 128, det=False, u=torch.from_numpy(g["u"])).numpy(), g["zs_rnd"])
+
+
+def test_head_search_flags_bit_exact():
+    g = golden("head_search")
+    rays, other = torch.from_numpy(g["rays"]), torch.from_numpy(g["other"])
+    z, p = torch.from_numpy(g["z"]), torch.from_numpy(g["p"])
+    for m in (2, 1):
+        d, w, op, flag = orc.search_head(p, z, other, rays[:, 6:8], 1e-10, m)
+        assert np.array_equal(flag.numpy(), g["flag_m%d" % m])
+        np.testing.assert_allclose(d.numpy(), g["depth_m%d" % m], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(w.numpy(), g["w_m%d" % m], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(op.item(), g["opacity_m%d" % m], rtol=1e-6)
+
+
+def test_gaussian_filter_matches_scipy():
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(0)
+    for n in (7, 19, 64, 192, 777):
+        x = rng.random((5, n)).astype(np.float32)
+        ours = orc.gaussian_filter_reflect(x, 5.0)
+        for i in range(5):
+            assert np.array_equal(ours[i], gaussian_filter(x[i], sigma=5))
+
+
+def _grads(sd):
+    out = {}
+    for k in orc.param_names():
+        gr = sd[k].grad.numpy()
+        out[k] = gr.reshape(-1)[::STRIDE] if k in BIG else gr
+    return out
+
+
+def _leaf_sd(seed):
+    sd = orc.init_state_dict(seed)
+    for k in orc.param_names():
+        sd[k].requires_grad_(True)
+    return sd
+
+
+def _check_train(name, rtol_out=2e-5, rtol_grad=2e-3):
+    g = golden(name)
+    rays = torch.from_numpy(g["rays"])
+    sd_c, sd_f = _leaf_sd(42), _leaf_sd(43)
+    perturb = float(g["perturb"])
+    res = orc.render_rays_train(sd_c, sd_f, rays, int(g["S"]), int(g["Ni"]), perturb, 0, int(g["chunk"]),
+                                int(g["issegmentated"]), float(g["ratio"]), 0, int(g["use_child"]),
+                                U=torch.from_numpy(g["U"]) if perturb > 0 else None,
+                                u_fine=torch.from_numpy(g["u"]) if perturb > 0 else None)
+    for k in ("depth", "depth_fine", "child_free_loss", "child_free_loss_fine", "child_depth_loss",
+              "child_depth_loss_fine"):
+        np.testing.assert_allclose(res[k].detach().numpy(), g["out_" + k], rtol=rtol_out, atol=1e-6, err_msg=k)
+    gt = rays[:, 14]
+    lam = g["lam"]
+    loss = orc.training_loss(res, gt, lam[0], lam[1], lam[2])
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=rtol_out)
+    loss.backward()
+    for tag, sd in (("c", sd_c), ("f", sd_f)):
+        for k, gr in _grads(sd).items():
+            ref = g["grad_%s_%s" % (tag, k)]
+            atol = rtol_grad * np.abs(ref).max() + 1e-12
+            if k.endswith(".bias") and k.split(".")[0] in ("layer1", "layer2") and k != "layer2.7.bias":
+                # Linear biases and BN betas that feed (through a Linear) a train-mode BN have an exactly-zero
+                # gradient in exact arithmetic: both sides are rounding noise -> compare on the net's grad scale.
+                atol = 1e-5 * max(np.abs(g[kk]).max() for kk in g.files if kk.startswith("grad_%s_" % tag))
+            np.testing.assert_allclose(gr, ref, rtol=rtol_grad, atol=atol, err_msg="%s %s" % (tag, k))
+        for k in ("layer1.1.running_mean", "layer1.1.running_var", "layer2.7.running_mean", "layer2.7.running_var"):
+            np.testing.assert_allclose(sd[k].numpy(), g["bn_%s_%s" % (tag, k)], rtol=1e-5, atol=1e-6)
+
+
+def test_train_seg():
+    _check_train("train_seg")
+
+
+def test_train_perturb():
+    _check_train("train_perturb")
+
+
+def test_train_plain():
+    _check_train("train_plain")
+
+
+def test_val_and_legacy():
+    g = golden("val_legacy")
+    rays = torch.from_numpy(g["rays"])
+    S, Ni, chunk = int(g["S"]), int(g["Ni"]), int(g["chunk"])
+    with torch.no_grad():
+        sd_c, sd_f = orc.init_state_dict(42), orc.init_state_dict(43)
+        v = orc.render_rays_val(sd_c, sd_f, rays, S, Ni, 0, 0, chunk)
+        for k in ("depth", "depth_fine"):
+            np.testing.assert_allclose(v[k].numpy(), g["val_" + k], rtol=2e-5, atol=1e-6)
+        leg = orc.render_rays(sd_c, sd_f, rays, S, Ni, False, 0, 0, chunk, False)
+        legd = orc.render_rays(sd_c, sd_f, rays, S, Ni, True, 0, 0, chunk, True)
+    for pre, r in (("leg_", leg), ("legdisp_", legd)):
+        for k in ("depth_fine", "weights", "opacity", "z_vals", "depth", "opacity_fine"):
+            np.testing.assert_allclose(r[k].numpy(), g[pre + k], rtol=5e-5, atol=1e-6, err_msg=pre + k)
+        assert r["depth2"].shape == g[pre + "depth2"].shape
+
+
+def test_view():
+    for m in (2, 1):
+        g = golden("view_m%d" % m)
+        rays, other = torch.from_numpy(g["rays"]), torch.from_numpy(g["other"])
+        with torch.no_grad():
+            sd_c, sd_f = orc.init_state_dict(42), orc.init_state_dict(43)
+            r = orc.render_rays_view(sd_c, sd_f, rays, other, int(g["S"]), int(g["Ni"]), 0, 0, int(g["chunk"]), m)
+        assert np.array_equal(r["rays_effective_flag"].numpy(), g["out_rays_effective_flag"])
+        assert np.array_equal(r["rays_effective_flag_fine"].numpy(), g["out_rays_effective_flag_fine"])
+        for k in ("depth", "depth_fine", "points_inference", "points_inference_fine", "weights", "z_vals"):
+            np.testing.assert_allclose(r[k].numpy(), g["out_" + k], rtol=5e-5, atol=1e-6, err_msg=k)
+
+
+def test_system_step_loss():
+    g = golden("system_step")
+    rays = torch.from_numpy(g["rays"])
+    sd_c, sd_f = _leaf_sd(42), _leaf_sd(43)
+    res = orc.render_rays_train(sd_c, sd_f, rays, 32, 64, 0, 0, 4096, 1, 0.1, 0, 1)
+    loss = orc.training_loss(res, rays[:, 14], 1.0, 1e6, 1e5)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=2e-5)
+    loss.backward()
+    params = [sd_c[k] for k in orc.param_names()] + [sd_f[k] for k in orc.param_names()]
+    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, weight_decay=1e-3)
+    opt.step()
+    for tag, sd in (("c", sd_c), ("f", sd_f)):
+        for k in ("layer1.1.weight", "occ_out.0.weight", "occ_out.0.bias"):
+            np.testing.assert_allclose(sd[k].detach().numpy(), g["after_%s_%s" % (tag, k)], rtol=1e-4, atol=1e-6)
