@@ -1,0 +1,214 @@
+/*
+ * pcnerf_b200 -- C ABI of the B200-native PC-NeRF ray-rendering hot path (libpcnerf_b200.so).
+ *
+ * The reference (biter0088/pc-nerf) has no FFI: its hot path is plain Python/PyTorch.  Each entry point below
+ * replaces the eager-torch / numpy body of the reference function cited next to it (file:line relative to the
+ * reference tree) and is what a binding for that function would call (see INTEGRATION.md for the ctypes stubs).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_` (host, read during the call);
+ *   - tensors are dense row-major; `ld` parameters are row strides in elements;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the device,
+ *     allocates device memory or keeps global mutable state;
+ *   - return value: 0 on success, negative on error; pcnerf_last_error() gives the message (thread local).
+ *   - fp32 "renderer" arithmetic follows the reference's operation order where masks/indices depend on it
+ *     (no FMA contraction in z placement and thresholds); the AABB stage is fp64 like the reference's numpy.
+ */
+#ifndef PCNERF_B200_H
+#define PCNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCNERF_OK 0
+#define PCNERF_ERR_ARG (-1)
+#define PCNERF_ERR_CUDA (-2)
+#define PCNERF_ERR_UNSUPPORTED (-3)
+
+#define PCNERF_ENC_DIM 63      /* 3 + 3*10*2, nof/networks/models.py:27-41 */
+#define PCNERF_ENC_LD 64       /* encodings are stored padded to 64 columns (col 63 == 0) */
+#define PCNERF_HID 256         /* feature_size */
+#define PCNERF_NLIN 9          /* 8 hidden Linear + occ_out */
+#define PCNERF_NBN 8
+
+const char* pcnerf_last_error(void);
+int pcnerf_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1  AABB stage (fp64).  Replaces the numpy / python-scalar leaf functions and the per-ray loops around them.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* compute_far_bound, nof/dataset/ipb2dmapping.py:36-77.  h_parent = {x_max,x_min,y_max,y_min,z_max,z_min}.
+ * out_t[i] = min positive plane parameter, +inf where the reference returns None. */
+int pcnerf_aabb_far_bound(const double* ray_o, const double* ray_d, int64_t n, const double* h_parent,
+                          double* out_t, void* stream);
+
+/* ray_aabb_distances, eval_kitti_render.py:213-235 (slab test; +inf when tmax < tmin). */
+int pcnerf_aabb_slab(const double* ray_o, const double* ray_d, int64_t n, const double* h_min3,
+                     const double* h_max3, double* out_t, void* stream);
+
+/* compute_far_bound0406 / 0606 / 0429 for every (ray, box) pair: ipb2dmapping.py:82-114, :119-172,
+ * eval_kitti_render.py:170-211.  variant = 406 | 606 | 429.  boxes (K,6) = min xyz, max xyz.
+ * out_flag (n,K) u8, out_near/out_far (n,K) f64 (NaN for 0406 with fewer than two hits). */
+int pcnerf_aabb_child_pairs(int variant, const double* ray_o, const double* ray_d, int64_t n, const double* boxes,
+                            int K, uint8_t* out_flag, double* out_near, double* out_far, void* stream);
+
+/* distance_to_ray, eval_kitti_render.py:237-244, for every (ray, centre) pair -> out (n,K) f64. */
+int pcnerf_aabb_dist_to_ray(const double* ray_o, const double* ray_d, int64_t n, const double* centres, int K,
+                            double* out, void* stream);
+
+/* find_aabb_box, ipb2dmapping.py:174-197, batched: first containing box among the knn nearest centres.
+ * out_idx[q] = box index or -1. */
+int pcnerf_aabb_find_box(const double* centres, const double* boxes, int K, const double* points, int64_t q,
+                         int knn, int32_t* out_idx, void* stream);
+
+/* Training ray packing: loop body of ipb2dmapping.py:367-397 (variant 406, MaiCity) / :736-768 (variant 606, KITTI)
+ * + the 15-column record of :447-452.  out_rays (n,15) f32, out_keep (n) u8 (rows with keep==0 are dropped by the
+ * caller, order preserved). */
+int pcnerf_aabb_pack_train(int variant, const double* ray_o, const double* ray_d, const double* dist,
+                           const double* points, int64_t n, const double* centres, const double* boxes,
+                           const double* boxes_bigger, int K, const double* h_parent, double surface_expand,
+                           int knn, float* out_rays, uint8_t* out_keep, void* stream);
+
+/* Candidate-group builder: loop body of eval_kitti_render.py:353-461 (grow_step 0.005) / :681-803 (0.05).
+ * Pass 1 counts candidate rows per ray (0 = ray dropped) and emits the parent far bound;
+ * pass 2 (after an exclusive prefix sum of the counts done by the caller) fills the (N',13) rows, ranges and the
+ * `other_interest_sub_nerf_number` side array, candidates sorted by ascending near. */
+int pcnerf_aabb_groups_count(const double* ray_o, const double* ray_d, int64_t n, const double* boxes,
+                             const double* boxes_larger, int K, const double* h_pmin3, const double* h_pmax3,
+                             int method, double grow_step, double prefilter, int32_t* out_count,
+                             double* out_parent_far, void* stream);
+int pcnerf_aabb_groups_fill(const double* ray_o, const double* ray_d, const double* dist, int64_t n,
+                            const double* boxes, const double* boxes_larger, int K, int method, double grow_step,
+                            double prefilter, const int32_t* count, const int64_t* offset,
+                            const double* parent_far, double* scratch /* (N',2) f64 */, float* out_rays13,
+                            float* out_ranges, int64_t* out_other, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K2  sample placement + positional encoding (fp32).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* nof/render.py:429-458 (+ :565-570 disparity, :622-628 view variant) fused with Embedding.forward
+ * (nof/networks/models.py:27-41).
+ *   rays (n, ld) f32; near/far read from columns near_col/far_col; child near/far from cnear_col/cfar_col.
+ *   steps_a (n_a) = torch.linspace(0,1,n_a) for the parent segment, steps_b (n_b) for the child segment
+ *   (n_b == 0 -> uniform sampling).  S = n_a + n_b.
+ *   U (n,S) = pre-drawn uniform numbers or NULL (perturb == 0).
+ *   out_z (n,S); out_enc (n*S, 64) f32 or NULL; out_enc_bf16 (n*S,64) bf16 or NULL. */
+int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n, int near_col, int far_col, int cnear_col,
+                                int cfar_col, const float* steps_a, int n_a, const float* steps_b, int n_b,
+                                int use_disp, float perturb, const float* U, float* out_z, float* out_enc,
+                                void* out_enc_bf16, void* stream);
+
+/* sample_pdf + merge (nof/render.py:371-412, :463-468) fused with the encoding of the merged samples.
+ *   z (n,S), w (n,S) coarse depths / weights; u: (Ni) shared (u_ld == 0, det) or (n,Ni) (u_ld == Ni).
+ *   out_z (n, S+Ni) ascending. */
+int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, const float* z, const float* w, int S,
+                              const float* u, int u_ld, int Ni, float* out_z, float* out_enc, void* out_enc_bf16,
+                              void* stream);
+
+/* sample_pdf alone (nof/render.py:371-412): bins (n,nb), weights (n,nb-1), u as above -> out (n,Ni), unsorted. */
+int pcnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int nb, const float* u, int u_ld, int Ni,
+                      float* out, void* stream);
+
+/* Embedding.forward alone (nof/networks/models.py:27-41): x (b,3) -> out (b, out_ld) f32, 63 columns written
+ * (+ zero padding up to out_ld). */
+int pcnerf_embed(const float* x, int64_t b, float* out, int out_ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K3  occupancy MLP (NOF / NOF_coarse / NOF_fine / NOF_plusfine, nof/networks/models.py:44-359).
+ * As constructed by the reference every activation is LeakyReLU(negative_slope=1.0) == identity
+ * (models.py:152,172), so the network is Linear->BN x8 -> Linear -> Sigmoid; BN(l) is folded into Linear(l+1).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct pcnerf_mlp_params {
+    const float* W[PCNERF_NLIN];        /* Linear weights (out,in): 63|256|256|256|319|256|256|256 -> 256, 256 -> 1 */
+    const float* b[PCNERF_NLIN];
+    const float* gamma[PCNERF_NBN];
+    const float* beta[PCNERF_NBN];
+    float* running_mean[PCNERF_NBN];    /* updated in place in training mode (momentum, unbiased var) */
+    float* running_var[PCNERF_NBN];
+    int64_t* num_batches_tracked[PCNERF_NBN];
+    float momentum;                     /* 0.1 */
+    float eps;                          /* 1e-5 */
+    int training;                       /* 1: batch statistics of this chunk; 0: running statistics */
+    int precision;                      /* 0: fp32 CUDA-core GEMM (1e-5 gate); 1: bf16 tcgen05 GEMM (1e-3 gate) */
+} pcnerf_mlp_params;
+
+typedef struct pcnerf_mlp_grads {       /* accumulated (+=) by pcnerf_mlp_backward */
+    float* dW[PCNERF_NLIN];
+    float* db[PCNERF_NLIN];
+    float* dgamma[PCNERF_NBN];
+    float* dbeta[PCNERF_NBN];
+} pcnerf_mlp_grads;
+
+/* Bytes of the activation store for one chunk of `rows` samples (saved between forward and backward) and of
+ * the scratch area (reusable across chunks). */
+size_t pcnerf_mlp_saved_bytes(int64_t rows, int precision);
+size_t pcnerf_mlp_scratch_bytes(int64_t rows, int precision);
+
+/* One BN batch (= one `chunk` of nof/render.py:47-49).  enc (rows,64) f32 (precision 0) or bf16 (precision 1).
+ * out_p (rows) = sigmoid(logit).  `saved` receives the pre-BN activations and the batch statistics. */
+int pcnerf_mlp_forward(const pcnerf_mlp_params* h_params, const void* enc, int64_t rows, float* out_p,
+                       void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Backward of the same chunk.  grad_p (rows) = dL/dp.  Needs out_p and `saved` of the forward call.
+ * Destroys `saved`. */
+int pcnerf_mlp_backward(const pcnerf_mlp_params* h_params, const pcnerf_mlp_grads* h_grads, const void* enc,
+                        int64_t rows, const float* out_p, const float* grad_p, void* saved, size_t saved_bytes,
+                        void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K4  compositing + losses (nof/render.py:51-61, :75-161, :13-36, :166-226; train_kitti.py:145-146).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+#define PCNERF_COMP_CHILD_LOSS 1        /* masks + child free / depth losses (use_child_nerf_loss == 1) */
+#define PCNERF_COMP_OPACITY 2           /* opacity regulariser partial sums (render.py:224) */
+
+/* p, z (n,P).  rays (n,ld): child near/far in columns cnear_col/cfar_col, range reading in range_col.
+ * noise (n,P) or NULL is added as noise*noise_std before normalisation.
+ * Outputs: w (n,P); depth (n); per_ray (n,8) f32 = {free_r, dhat_r, sl1_child_r, C_r, lo0, hi0, lo2, hi2};
+ * sums (4) f64 = {sum free_r, sum sl1_child_r, sum opacity terms, unused} (zeroed by the call). */
+int pcnerf_composite_fwd(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
+                         int cnear_col, int cfar_col, int range_col, const float* noise, float noise_std,
+                         float epsilon, int flags, float* w, float* depth, float* per_ray, double* sums,
+                         void* stream);
+
+/* child_free_loss = sums[0]/n; child_depth_loss = (1/n)*0.1*(sums[1]/n)  (render.py:121,155) -> out2 (2) f32 */
+int pcnerf_composite_losses(const double* sums, int64_t n, float* out2, void* stream);
+
+/* Backward.  Upstream gradients (any may be NULL): g_depth (n) for depth; g_free / g_dloss device scalars for the two
+ * losses of pcnerf_composite_losses (n_total = number of rays their means are taken over); g_free_r / g_sl1_r (n) for
+ * per_ray[:,0] / per_ray[:,2] (used by the use_child_nerf_divide == 1 segmented variant, render.py:106-119,135-152).
+ * out grad_p (n,P) = dL/dp. */
+int pcnerf_composite_bwd(const float* p, const float* z, const float* w, const float* rays, int ld, int64_t n,
+                         int P, int range_col, float noise_std, float epsilon, int flags, const float* per_ray,
+                         const float* g_depth, const float* g_free, const float* g_dloss, const float* g_free_r,
+                         const float* g_sl1_r, int64_t n_total, float* grad_p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K5  two-step depth-inference search (nof/render.py:229-368, :674-684).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Per candidate row: normalised weights, strict child mask with expand-until-non-empty (:252-263), fp64 Gaussian
+ * smoothing sigma=5 'reflect' + first-max argmax (:303-308), peak-in-child (:309-313), in-child weight sum
+ * (:314-315), depth by method 1 (:342-343) or 2 (:345-348), opacity partial sum -> sums[0] (f64, zeroed). */
+int pcnerf_search_rows(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
+                       int cnear_col, int cfar_col, float epsilon, int method, float* w, float* depth,
+                       uint8_t* peak_in_child, float* wsum_child, double* sums, void* stream);
+
+/* Group winner selection (:317-340).  other (n) i64: head = followers, followers = 0.  out_flag (n) u8. */
+int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in_child, const float* wsum_child, int64_t n,
+                         uint8_t* out_flag, void* stream);
+
+/* points = o + depth*d (:674-684). */
+int pcnerf_points(const float* rays, int ld, int64_t n, const float* depth, float* out_xyz, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCNERF_B200_H */

@@ -1,0 +1,90 @@
+"""ctypes binding of libpcnerf_b200.so (the C ABI declared in include/pcnerf_b200.h).
+
+There is no fallback: if the library is missing or a kernel fails, the call raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpcnerf_b200.so")
+
+NLIN, NBN = 9, 8
+ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
+
+vp, ci, i64, f32, f64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
+
+
+class MlpParams(ctypes.Structure):
+    _fields_ = [("W", vp * NLIN), ("b", vp * NLIN), ("gamma", vp * NBN), ("beta", vp * NBN),
+                ("running_mean", vp * NBN), ("running_var", vp * NBN), ("num_batches_tracked", vp * NBN),
+                ("momentum", f32), ("eps", f32), ("training", ci), ("precision", ci)]
+
+
+class MlpGrads(ctypes.Structure):
+    _fields_ = [("dW", vp * NLIN), ("db", vp * NLIN), ("dgamma", vp * NBN), ("dbeta", vp * NBN)]
+
+
+PD = ctypes.POINTER(f64)
+
+SIGNATURES = {
+    "pcnerf_version": (ci, []),
+    "pcnerf_last_error": (ctypes.c_char_p, []),
+    "pcnerf_aabb_far_bound": (ci, [vp, vp, i64, PD, vp, vp]),
+    "pcnerf_aabb_slab": (ci, [vp, vp, i64, PD, PD, vp, vp]),
+    "pcnerf_aabb_child_pairs": (ci, [ci, vp, vp, i64, vp, ci, vp, vp, vp, vp]),
+    "pcnerf_aabb_dist_to_ray": (ci, [vp, vp, i64, vp, ci, vp, vp]),
+    "pcnerf_aabb_find_box": (ci, [vp, vp, ci, vp, i64, ci, vp, vp]),
+    "pcnerf_aabb_pack_train": (ci, [ci, vp, vp, vp, vp, i64, vp, vp, vp, ci, PD, f64, ci, vp, vp, vp]),
+    "pcnerf_aabb_groups_count": (ci, [vp, vp, i64, vp, vp, ci, PD, PD, ci, f64, f64, vp, vp, vp]),
+    "pcnerf_aabb_groups_fill": (ci, [vp, vp, vp, i64, vp, vp, ci, ci, f64, f64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pcnerf_sample_encode_coarse": (ci, [vp, ci, i64, ci, ci, ci, ci, vp, ci, vp, ci, ci, f32, vp, vp, vp, vp, vp]),
+    "pcnerf_sample_encode_fine": (ci, [vp, ci, i64, vp, vp, ci, vp, ci, ci, vp, vp, vp, vp]),
+    "pcnerf_sample_pdf": (ci, [vp, vp, i64, ci, vp, ci, ci, vp, vp]),
+    "pcnerf_embed": (ci, [vp, i64, vp, ci, vp]),
+    "pcnerf_mlp_saved_bytes": (sz, [i64, ci]),
+    "pcnerf_mlp_scratch_bytes": (sz, [i64, ci]),
+    "pcnerf_mlp_forward": (ci, [ctypes.POINTER(MlpParams), vp, i64, vp, vp, sz, vp, sz, vp]),
+    "pcnerf_mlp_backward": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, i64, vp, vp, vp, sz, vp, sz, vp]),
+    "pcnerf_composite_fwd": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, ci, vp, f32, f32, ci, vp, vp, vp, vp, vp]),
+    "pcnerf_composite_losses": (ci, [vp, i64, vp, vp]),
+    "pcnerf_composite_bwd": (ci, [vp, vp, vp, vp, ci, i64, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
+    "pcnerf_search_rows": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, f32, ci, vp, vp, vp, vp, vp, vp]),
+    "pcnerf_search_select": (ci, [vp, vp, vp, i64, vp, vp]),
+    "pcnerf_points": (ci, [vp, ci, i64, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def header_symbols():
+    """Entry points declared in include/pcnerf_b200.h (parsed, so tests can check header <-> library <-> binding)."""
+    import re
+    hdr = os.path.join(os.path.dirname(HERE), "include", "pcnerf_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(pcnerf_[a-z0-9_]+)\s*\(", txt)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libpcnerf_b200.so is not built (%s missing): run `python -m pcnerf_b200.build`; "
+                               "there is no CPU fallback" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = lib().pcnerf_last_error().decode("utf-8", "replace")
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,59 @@
+// Shared helpers for the pcnerf_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/pcnerf_b200.h"
+
+#define PCN_SM_COUNT 148
+
+void pcn_set_error(const char* fmt, ...);
+
+#define PCN_CHECK_ARG(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            pcn_set_error(__VA_ARGS__);          \
+            return PCNERF_ERR_ARG;               \
+        }                                        \
+    } while (0)
+
+#define PCN_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            pcn_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PCNERF_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+#define PCN_LAUNCH_CHECK()                                                                    \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            pcn_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PCNERF_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+static inline int64_t pcn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}

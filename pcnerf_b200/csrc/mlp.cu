@@ -1,0 +1,547 @@
+// K3 (fp32 path): the occupancy MLP of nof/networks/models.py:125-203 as actually constructed --
+//   Linear(63,256) BN  [Linear(256,256) BN]x3  cat(x, .)  Linear(319,256) BN  [Linear(256,256) BN]x3  Linear(256,1) Sigmoid
+// with every LeakyReLU(negative_slope=True==1.0) an identity (models.py:152,172).
+//
+// Design: BN(l) is an affine map y = a*h + s per feature, so it is folded into Linear(l+1):
+//   h_{l+1} = (W_{l+1} diag(a_l)) h_l + (b_{l+1} + W_{l+1} s_l).
+// Training mode needs the batch statistics of h_l first: each layer is one GEMM whose epilogue accumulates the
+// per-feature sum / sum of squares (fp32 per tile, fp64 across tiles), followed by a tiny fold kernel.
+// Only the pre-BN activations h_1..h_8 are stored (backward needs them); normalised activations, the identity
+// "activation" copies and the skip concat of the eager reference never touch HBM.
+//
+// This file is the CUDA-core fp32 path (precision 0, the 1e-5 parity gate).  mlp_tc.cu holds the bf16 tcgen05 path.
+#include "common.cuh"
+#include "mlp_layout.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 GEMM  C[m,n] = sum_k A(m,k) B(n,k)   (128x64x16 tiles, 8x4 micro-tiles, register-prefetched double buffer)
+// ---------------------------------------------------------------------------------------------------------------
+
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_SPLITK = 2 };
+
+struct GemmArgs {
+    const float* A1; int lda1; int K1;     // A segment 1 covers k in [0,K1); non-transposed A only
+    const float* A2; int lda2;             // A segment 2 covers k in [K1,K)
+    const float* B; int ldb;
+    float* C; int ldc;
+    int M, N, K;
+    const float* bias;                     // EPI_FWD: + bias[n]
+    const float* E; int lde;               // EPI_DGRAD: second statistic is sum_m C[m,n]*E[m,n]
+    double* stat0; double* stat1;          // per-column accumulators (EPI_FWD / EPI_DGRAD)
+    int k_per_split;                       // EPI_SPLITK: partial C for split z goes to C + z*M*ldc
+};
+
+#define GBM 128
+#define GBN 64
+#define GBK 16
+#define AS_LD (GBM + 4)
+#define BS_LD (GBN + 4)
+
+template <bool AT, bool BT, int EPI>
+__global__ void __launch_bounds__(256) k_gemm(GemmArgs g) {
+    __shared__ __align__(16) float As[2][GBK][AS_LD];
+    __shared__ __align__(16) float Bs[2][GBK][BS_LD];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+    int kbeg = 0, kend = g.K;
+    if (EPI == EPI_SPLITK) {
+        kbeg = blockIdx.z * g.k_per_split;
+        kend = min(g.K, kbeg + g.k_per_split);
+    }
+    float4 ra[2], rb;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    auto load_tile = [&](int k0) {
+        if (AT) {
+            // A(m,k) = A1[k*lda + m]: 16 k-rows x 128 m, float4 along m
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = k0 + (tid >> 5) + h * 8, m = m0 + (tid & 31) * 4;
+                ra[h] = (k < kend) ? *reinterpret_cast<const float4*>(g.A1 + (size_t)k * g.lda1 + m)
+                                   : make_float4(0, 0, 0, 0);
+            }
+        } else {
+            const float* Ap = g.A1; int lda = g.lda1; int kk = k0;
+            if (k0 >= g.K1) { Ap = g.A2; lda = g.lda2; kk = k0 - g.K1; }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = m0 + (tid >> 2) + h * 64, kq = (tid & 3) * 4;
+                ra[h] = (m < g.M) ? *reinterpret_cast<const float4*>(Ap + (size_t)m * lda + kk + kq)
+                                  : make_float4(0, 0, 0, 0);
+            }
+        }
+        if (BT) {
+            // B(n,k) = B[k*ldb + n]: 16 k-rows x 64 n
+            const int k = k0 + (tid >> 4), n = n0 + (tid & 15) * 4;
+            rb = (k < kend) ? *reinterpret_cast<const float4*>(g.B + (size_t)k * g.ldb + n) : make_float4(0, 0, 0, 0);
+        } else {
+            const int n = n0 + (tid >> 2), kq = (tid & 3) * 4;
+            rb = *reinterpret_cast<const float4*>(g.B + (size_t)n * g.ldb + k0 + kq);
+        }
+    };
+    auto store_tile = [&](int buf) {
+        if (AT) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                *reinterpret_cast<float4*>(&As[buf][(tid >> 5) + h * 8][(tid & 31) * 4]) = ra[h];
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = (tid >> 2) + h * 64, kq = (tid & 3) * 4;
+                As[buf][kq + 0][m] = ra[h].x; As[buf][kq + 1][m] = ra[h].y;
+                As[buf][kq + 2][m] = ra[h].z; As[buf][kq + 3][m] = ra[h].w;
+            }
+        }
+        if (BT) {
+            *reinterpret_cast<float4*>(&Bs[buf][tid >> 4][(tid & 15) * 4]) = rb;
+        } else {
+            const int n = tid >> 2, kq = (tid & 3) * 4;
+            Bs[buf][kq + 0][n] = rb.x; Bs[buf][kq + 1][n] = rb.y; Bs[buf][kq + 2][n] = rb.z; Bs[buf][kq + 3][n] = rb.w;
+        }
+    };
+
+    int buf = 0;
+    if (kbeg < kend) {
+        load_tile(kbeg);
+        store_tile(0);
+    }
+    __syncthreads();
+    for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+        const bool more = k0 + GBK < kend;
+        if (more) load_tile(k0 + GBK);
+#pragma unroll
+        for (int kk = 0; kk < GBK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) store_tile(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    // ---- epilogue
+    const int n = n0 + tx * 4;
+    if (EPI == EPI_SPLITK) {
+        float* Cp = g.C + (size_t)blockIdx.z * g.M * g.ldc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ty * 8 + i;
+            if (m < g.M)
+                *reinterpret_cast<float4*>(Cp + (size_t)m * g.ldc + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        return;
+    }
+    float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    float bv[4] = {0, 0, 0, 0};
+    if (EPI == EPI_FWD) { bv[0] = g.bias[n]; bv[1] = g.bias[n + 1]; bv[2] = g.bias[n + 2]; bv[3] = g.bias[n + 3]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m < g.M) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
+            *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+            float e[4] = {v[0], v[1], v[2], v[3]};
+            if (EPI == EPI_DGRAD) {
+                const float4 ev = *reinterpret_cast<const float4*>(g.E + (size_t)m * g.lde + n);
+                e[0] = ev.x; e[1] = ev.y; e[2] = ev.z; e[3] = ev.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s0[j] += v[j]; s1[j] = fmaf(v[j], e[j], s1[j]); }
+        }
+    }
+    // reduce the 16 ty-partials per column through shared memory, then one fp64 atomic per column per CTA
+    float* red0 = &As[0][0][0];            // 16 x 64
+    float* red1 = red0 + 16 * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red0[ty * 64 + tx * 4 + j] = s0[j]; red1[ty * 64 + tx * 4 + j] = s1[j]; }
+    __syncthreads();
+    if (tid < 128) {
+        const int c = tid & 63;
+        const float* rp = tid < 64 ? red0 : red1;
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t += (double)rp[k * 64 + c];
+        atomicAdd((tid < 64 ? g.stat0 : g.stat1) + n0 + c, t);
+    }
+}
+
+template <bool AT, bool BT, int EPI>
+static void launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
+    dim3 grid((unsigned)pcn_cdiv(g.M, GBM), (unsigned)(g.N / GBN), (unsigned)splits);
+    k_gemm<AT, BT, EPI><<<grid, 256, 0, st>>>(g);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+struct PrepArgs {
+    const float* W[8];
+    float* Wp[8];
+};
+
+// Padded copies of the hidden Linear weights: layer 0 -> [256,64] (col 63 = 0); layer 4 -> [256,320]
+// ([0,63) encoding cols, col 63 = 0, [64,320) hidden cols); others [256,256].
+__global__ void k_prep_weights(PrepArgs a) {
+    const int l = blockIdx.y;
+    const int kin = mlp_kin(l), kpad = mlp_kpad(l);
+    const int total = 256 * kpad;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int o = idx / kpad, c = idx - o * kpad;
+        float v = 0.f;
+        if (l == 0) { if (c < 63) v = a.W[0][o * kin + c]; }
+        else if (l == 4) { if (c < 63) v = a.W[4][o * kin + c]; else if (c >= 64) v = a.W[4][o * kin + c - 1]; }
+        else v = a.W[l][o * kin + c];
+        a.Wp[l][idx] = v;
+    }
+}
+
+// BN(l) statistics -> (mean, invstd, a, s) and fold into layer l+1 (or the output layer when l == 7).
+// grid: 256 blocks (output feature o of the next layer) x 256 threads (hidden input feature i); l == 7: 1 block.
+__global__ void __launch_bounds__(256) k_bn_fold(int l, int training, int64_t rows, const double* __restrict__ sum,
+                                                 const double* __restrict__ sumsq, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                 float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                                                 float momentum, float eps, float* __restrict__ stats /* [4][256] */,
+                                                 const float* __restrict__ Wp_next, const float* __restrict__ b_next,
+                                                 float* __restrict__ Wf_next, float* __restrict__ bf_next) {
+    __shared__ float red[8];
+    const int i = threadIdx.x, o = blockIdx.x;
+    float mean, var;
+    if (training) {
+        const double m = sum[i] / (double)rows;
+        double v = sumsq[i] / (double)rows - m * m;
+        if (v < 0) v = 0;
+        mean = (float)m;
+        var = (float)v;
+    } else {
+        mean = running_mean[i];
+        var = running_var[i];
+    }
+    const float invstd = 1.f / sqrtf(var + eps);
+    const float a = gamma[i] * invstd;
+    const float s = beta[i] - mean * a;
+    if (o == 0) {
+        stats[i] = mean; stats[256 + i] = invstd; stats[512 + i] = a; stats[768 + i] = s;
+        if (training) {
+            const float unbiased = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+            running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * mean;
+            running_var[i] = (1.f - momentum) * running_var[i] + momentum * unbiased;
+            if (i == 0 && nbt) *nbt += 1;
+        }
+    }
+    const int nl = l + 1;
+    float part;
+    if (nl < 8) {
+        const int kpad = mlp_kpad(nl), off = nl == 4 ? 64 : 0;
+        const float w = Wp_next[o * kpad + off + i];
+        Wf_next[o * kpad + off + i] = w * a;
+        if (nl == 4 && i < 64) Wf_next[o * kpad + i] = Wp_next[o * kpad + i];
+        part = w * s;
+    } else {
+        const float w = Wp_next[i];            // occ_out weight (1,256)
+        Wf_next[i] = w * a;
+        part = w * s;
+    }
+    part = warp_sum(part);
+    if ((i & 31) == 0) red[i >> 5] = part;
+    __syncthreads();
+    if (i == 0) {
+        float t = 0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        bf_next[o] = b_next[o] + t;
+    }
+}
+
+// p = sigmoid(h8 . wout_f + bout_f): one warp per row
+__global__ void k_logit_sigmoid(const float* __restrict__ H, int64_t rows, const float* __restrict__ wf,
+                                const float* __restrict__ bf, float* __restrict__ out_p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = wf[lane * 8 + j];
+    const float b = bf[0];
+    for (int64_t r = warp; r < rows; r += nw) {
+        const float4 h0 = *reinterpret_cast<const float4*>(H + r * 256 + lane * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(H + r * 256 + lane * 8 + 4);
+        float t = h0.x * wv[0] + h0.y * wv[1] + h0.z * wv[2] + h0.w * wv[3] + h1.x * wv[4] + h1.y * wv[5] +
+                  h1.z * wv[6] + h1.w * wv[7];
+        t = warp_sum(t);
+        if (lane == 0) out_p[r] = 1.f / (1.f + expf(-(t + b)));
+    }
+}
+
+#define STRIP 64
+
+// g = dL/dp * p(1-p);  acc[j] += sum_r g_r H8[r,j];  acc[256] += sum_r g_r
+__global__ void __launch_bounds__(256) k_out_bwd_reduce(const float* __restrict__ grad_p, const float* __restrict__ p,
+                                                        const float* __restrict__ H, int64_t rows,
+                                                        float* __restrict__ gvec, double* __restrict__ acc) {
+    const int j = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * STRIP;
+    float a = 0.f, sg = 0.f;
+    for (int k = 0; k < STRIP; ++k) {
+        const int64_t r = r0 + k;
+        if (r >= rows) break;
+        const float pv = p[r];
+        const float gr = grad_p[r] * pv * (1.f - pv);
+        a = fmaf(gr, H[r * 256 + j], a);
+        sg += gr;
+        if (j == 0) gvec[r] = gr;
+    }
+    atomicAdd(acc + j, (double)a);
+    if (j == 0) atomicAdd(acc + 256, (double)sg);
+}
+
+// Output-layer parameter grads, BN(7) grads and the coefficient vectors of
+//   DH8[r,j] = g_r*u[j] - c1[j] - (H8[r,j] - mean[j])*c2[j]
+__global__ void __launch_bounds__(256) k_out_bwd_finalize(const double* __restrict__ acc, int64_t rows,
+                                                          const float* __restrict__ w_out,
+                                                          const float* __restrict__ stats, float* __restrict__ dw_out,
+                                                          float* __restrict__ db_out, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, float* __restrict__ coef) {
+    const int j = threadIdx.x;
+    const float q = (float)acc[j], sg = (float)acc[256];
+    const float mean = stats[j], invstd = stats[256 + j], a = stats[512 + j], s = stats[768 + j];
+    const float w = w_out[j];
+    dw_out[j] += a * q + s * sg;
+    if (j == 0) db_out[0] += sg;
+    const float db = w * sg;
+    const float dg = w * invstd * (q - mean * sg);
+    dgamma[j] += dg;
+    dbeta[j] += db;
+    const float B = (float)rows;
+    coef[j] = a * w;                       // u
+    coef[256 + j] = a * db / B;            // c1
+    coef[512 + j] = a * invstd * dg / B;   // c2
+}
+
+// LAST: DH = g (x) u - c1 - (H - mean) c2     (Gy never materialised for the last BN)
+// else: DH = Gy*a - c1 - (H - mean) c2        in place on Gy
+// plus column sums of DH (the Linear bias gradient; zero in exact arithmetic)
+template <bool LAST>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ gvec, float* __restrict__ G,
+                                                      const float* __restrict__ H, int64_t rows,
+                                                      const float* __restrict__ coef, const float* __restrict__ stats,
+                                                      double* __restrict__ colsum) {
+    const int j = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * STRIP;
+    const float c0 = coef[j], c1 = coef[256 + j], c2 = coef[512 + j], mean = stats[j];
+    float cs = 0.f;
+    for (int k = 0; k < STRIP; ++k) {
+        const int64_t r = r0 + k;
+        if (r >= rows) break;
+        const float up = LAST ? gvec[r] : G[r * 256 + j];
+        const float dh = up * c0 - c1 - (H[r * 256 + j] - mean) * c2;
+        G[r * 256 + j] = dh;
+        cs += dh;
+    }
+    atomicAdd(colsum + j, (double)cs);
+}
+
+// BN(l) backward coefficients from the dgrad epilogue sums: st0 = sum Gy, st1 = sum Gy*H
+__global__ void __launch_bounds__(256) k_bn_bwd_coef(const double* __restrict__ st0, const double* __restrict__ st1,
+                                                     int64_t rows, const float* __restrict__ stats,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     float* __restrict__ coef) {
+    const int j = threadIdx.x;
+    const float mean = stats[j], invstd = stats[256 + j], a = stats[512 + j];
+    const float db = (float)st0[j];
+    const float dg = invstd * (float)(st1[j] - (double)mean * st0[j]);
+    dgamma[j] += dg;
+    dbeta[j] += db;
+    const float B = (float)rows;
+    coef[j] = a;
+    coef[256 + j] = a * db / B;
+    coef[512 + j] = a * invstd * dg / B;
+}
+
+// dW_l[o, real col] += (sum_splits partial[o, c]) * a_prev[c] + dbias[o] * s_prev[c];  db_l[o] += dbias[o]
+// partial is [splits][256][kpad].  prev_stats == NULL for encoding columns (a = 1, s = 0).
+__global__ void k_wgrad_finalize(int l, const float* __restrict__ partial, int splits,
+                                 const double* __restrict__ colsum, const float* __restrict__ prev_stats,
+                                 float* __restrict__ dW, float* __restrict__ db) {
+    const int kin = mlp_kin(l), kpad = mlp_kpad(l);
+    const int total = 256 * kpad;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int o = idx / kpad, c = idx - o * kpad;
+        int real = c, hid = c;
+        bool is_hidden = true;
+        if (l == 0) { is_hidden = false; if (c >= 63) continue; }
+        else if (l == 4) {
+            if (c < 64) { is_hidden = false; if (c == 63) continue; }
+            else { real = c - 1; hid = c - 64; }
+        }
+        double t = 0;
+        for (int s = 0; s < splits; ++s) t += (double)partial[(size_t)s * total + idx];
+        float v = (float)t;
+        const float dbias = (float)colsum[o];
+        if (is_hidden) v = v * prev_stats[512 + hid] + dbias * prev_stats[768 + hid];
+        dW[o * kin + real] += v;
+        if (c == 0) db[o] += dbias;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------------------
+
+static int check_common(const pcnerf_mlp_params* P, const void* enc, int64_t rows, const char* who) {
+    PCN_CHECK_ARG(P && enc, "%s: null params / enc", who);
+    PCN_CHECK_ARG(rows >= 1, "%s: rows must be >= 1", who);
+    PCN_CHECK_ARG(rows < (1ll << 31) / 320, "%s: chunk of %lld rows is too large (use a smaller chunk)", who, (long long)rows);
+    if (P->training && rows == 1) {
+        pcn_set_error("Expected more than 1 value per channel when training, got input size [1, 256]");
+        return PCNERF_ERR_ARG;
+    }
+    return 0;
+}
+
+int mlp_tc_forward(const pcnerf_mlp_params*, const void*, int64_t, float*, void*, size_t, void*, size_t, cudaStream_t);
+int mlp_tc_backward(const pcnerf_mlp_params*, const pcnerf_mlp_grads*, const void*, int64_t, const float*, const float*,
+                    void*, size_t, void*, size_t, cudaStream_t);
+
+extern "C" size_t pcnerf_mlp_saved_bytes(int64_t rows, int precision) { return MlpLayout(rows, precision).saved_bytes; }
+extern "C" size_t pcnerf_mlp_scratch_bytes(int64_t rows, int precision) { return MlpLayout(rows, precision).scratch_bytes; }
+
+static void prep_weights(const pcnerf_mlp_params* P, const MlpLayout& L, char* scratch, cudaStream_t st) {
+    PrepArgs pa;
+    for (int l = 0; l < 8; ++l) { pa.W[l] = P->W[l]; pa.Wp[l] = L.Wp(scratch, l); }
+    k_prep_weights<<<dim3(64, 8), 256, 0, st>>>(pa);
+}
+
+extern "C" int pcnerf_mlp_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, float* out_p, void* saved,
+                                  size_t saved_bytes, void* scratch_v, size_t scratch_bytes, void* stream) {
+    int rc = check_common(P, enc, rows, "mlp_forward");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const MlpLayout L(rows, P->precision);
+    PCN_CHECK_ARG(saved && saved_bytes >= L.saved_bytes, "mlp_forward: saved buffer too small (%zu < %zu)", saved_bytes, L.saved_bytes);
+    PCN_CHECK_ARG(scratch_v && scratch_bytes >= L.scratch_bytes, "mlp_forward: scratch too small (%zu < %zu)", scratch_bytes, L.scratch_bytes);
+    if (P->precision == 1) return mlp_tc_forward(P, enc, rows, out_p, saved, saved_bytes, scratch_v, scratch_bytes, st);
+    PCN_CHECK_ARG(P->precision == 0, "mlp_forward: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
+    char* scratch = (char*)scratch_v;
+    char* sv = (char*)saved;
+    PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
+    prep_weights(P, L, scratch, st);
+    const float* encf = (const float*)enc;
+    for (int l = 0; l < 8; ++l) {
+        GemmArgs g = {};
+        float* Hl = L.H(sv, l);
+        if (l == 0) { g.A1 = encf; g.lda1 = 64; g.K1 = 64; g.K = 64; }
+        else if (l == 4) { g.A1 = encf; g.lda1 = 64; g.K1 = 64; g.A2 = L.H(sv, 3); g.lda2 = 256; g.K = 320; }
+        else { g.A1 = L.H(sv, l - 1); g.lda1 = 256; g.K1 = 256; g.K = 256; }
+        g.B = l == 0 ? L.Wp(scratch, 0) : L.Wf(scratch, l);
+        g.ldb = mlp_kpad(l);
+        g.bias = l == 0 ? P->b[0] : L.bf(scratch, l);
+        g.C = Hl; g.ldc = 256; g.M = (int)rows; g.N = 256;
+        g.stat0 = L.dstat(scratch, l); g.stat1 = g.stat0 + 256;
+        launch_gemm<false, false, EPI_FWD>(g, 1, st);
+        const bool last = l == 7;
+        k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
+            l, P->training, rows, g.stat0, g.stat1, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],
+            P->num_batches_tracked[l], P->momentum, P->eps, L.stats(sv, l), last ? P->W[8] : L.Wp(scratch, l + 1),
+            last ? P->b[8] : P->b[l + 1], last ? L.wout_f(scratch) : L.Wf(scratch, l + 1),
+            last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1));
+    }
+    int64_t blocks = pcn_cdiv(rows, 8);
+    if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
+    k_logit_sigmoid<<<(int)blocks, 256, 0, st>>>(L.H(sv, 7), rows, L.wout_f(scratch), L.wout_f(scratch) + 256, out_p);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const void* enc, int64_t rows,
+                                   const float* out_p, const float* grad_p, void* saved, size_t saved_bytes,
+                                   void* scratch_v, size_t scratch_bytes, void* stream) {
+    int rc = check_common(P, enc, rows, "mlp_backward");
+    if (rc) return rc;
+    PCN_CHECK_ARG(G && out_p && grad_p, "mlp_backward: null grads / out_p / grad_p");
+    PCN_CHECK_ARG(P->training, "mlp_backward: only training-mode (batch-statistics) backward is implemented");
+    cudaStream_t st = (cudaStream_t)stream;
+    const MlpLayout L(rows, P->precision);
+    PCN_CHECK_ARG(saved && saved_bytes >= L.saved_bytes, "mlp_backward: saved buffer too small");
+    PCN_CHECK_ARG(scratch_v && scratch_bytes >= L.scratch_bytes, "mlp_backward: scratch too small");
+    if (P->precision == 1)
+        return mlp_tc_backward(P, G, enc, rows, out_p, grad_p, saved, saved_bytes, scratch_v, scratch_bytes, st);
+    PCN_CHECK_ARG(P->precision == 0, "mlp_backward: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
+    char* scratch = (char*)scratch_v;
+    char* sv = (char*)saved;
+    const float* encf = (const float*)enc;
+    PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * L.n_dstat, st));
+    prep_weights(P, L, scratch, st);
+    double* acc_out = L.dstat(scratch, 8);            // 257 (+pad) doubles
+    float* gvec = L.gvec(scratch);
+    float* coef = L.coef(scratch);
+    float* Gb[2] = {L.G(scratch, 0), L.G(scratch, 1)};
+    const int strips = (int)pcn_cdiv(rows, STRIP);
+
+    k_out_bwd_reduce<<<strips, 256, 0, st>>>(grad_p, out_p, L.H(sv, 7), rows, gvec, acc_out);
+    k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
+                                          G->dbeta[7], coef);
+    int cur = 0;
+    k_bn_bwd_apply<true><<<strips, 256, 0, st>>>(gvec, Gb[cur], L.H(sv, 7), rows, coef, L.stats(sv, 7),
+                                                 L.colsum(scratch, 7));
+    // split-K factor for the weight-gradient GEMMs
+    int splits = (int)pcn_cdiv(rows, 2048);
+    if (splits > MLP_MAX_SPLITS) splits = MLP_MAX_SPLITS;
+    if (splits < 1) splits = 1;
+    int kps = (int)pcn_cdiv(pcn_cdiv(rows, splits), GBK) * GBK;
+    splits = (int)pcn_cdiv(rows, kps);
+    for (int l = 7; l >= 0; --l) {
+        const float* DH = Gb[cur];
+        const int kpad = mlp_kpad(l);
+        float* part = L.partial(scratch);
+        // ---- weight gradient  dWraw[o, c] = sum_r DH[r,o] * U[r,c]
+        {
+            GemmArgs g = {};
+            g.A1 = DH; g.lda1 = 256; g.M = 256; g.K = (int)rows; g.k_per_split = kps;
+            g.C = part; g.ldc = kpad;
+            if (l == 0 || l == 4) {           // encoding columns
+                g.B = encf; g.ldb = 64; g.N = 64;
+                launch_gemm<true, true, EPI_SPLITK>(g, splits, st);
+            }
+            if (l != 0) {                     // hidden columns
+                g.B = L.H(sv, l - 1); g.ldb = 256; g.N = 256;
+                g.C = part + (l == 4 ? 64 : 0);
+                launch_gemm<true, true, EPI_SPLITK>(g, splits, st);
+            }
+            k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, splits, L.colsum(scratch, l),
+                                                   l == 0 ? nullptr : L.stats(sv, l - 1), G->dW[l], G->db[l]);
+        }
+        if (l == 0) break;
+        // ---- data gradient  Gy_{l-1} = DH_l . W_l[:, hidden cols], with the BN(l-1) reductions in the epilogue
+        {
+            GemmArgs g = {};
+            g.A1 = DH; g.lda1 = 256; g.K1 = 256; g.K = 256; g.M = (int)rows; g.N = 256;
+            g.B = L.Wp(scratch, l) + (l == 4 ? 64 : 0); g.ldb = kpad;
+            g.C = Gb[cur ^ 1]; g.ldc = 256;
+            g.E = L.H(sv, l - 1); g.lde = 256;
+            g.stat0 = L.dstat(scratch, 9 + (l - 1)); g.stat1 = g.stat0 + 256;
+            launch_gemm<false, true, EPI_DGRAD>(g, 1, st);
+            k_bn_bwd_coef<<<1, 256, 0, st>>>(g.stat0, g.stat1, rows, L.stats(sv, l - 1), G->dgamma[l - 1],
+                                             G->dbeta[l - 1], coef);
+            cur ^= 1;
+            k_bn_bwd_apply<false><<<strips, 256, 0, st>>>(nullptr, Gb[cur], L.H(sv, l - 1), rows, coef,
+                                                          L.stats(sv, l - 1), L.colsum(scratch, l - 1));
+        }
+    }
+    PCN_LAUNCH_CHECK();
+    return 0;
+}

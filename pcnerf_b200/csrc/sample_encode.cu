@@ -1,0 +1,353 @@
+// K2 / K2': sample placement along each segment, hierarchical resampling and the 63-d positional encoding, fused.
+//
+// Mapping: one warp per ray.  The ray's depths live in shared memory; z placement uses explicit
+// round-to-nearest mul/add (no FMA contraction) in the reference's operation order so that every later
+// mask decision sees bit-identical z.  The encoding of one sample is produced by 30 lanes (one sincosf each, accurate
+// range reduction: arguments reach 512*60 rad), staged in shared memory and written as one coalesced row
+// (256 B fp32 / 128 B bf16) -- the fp32 (rows,64) layout is the MLP's A operand, column 63 is zero padding.
+#include "common.cuh"
+
+#define SE_MAX_SMEM (200 * 1024)
+
+__device__ __forceinline__ float lerp_rn(float a, float b, float s) {
+    // near * (1 - s) + far * s, nof/render.py:432
+    return __fadd_rn(__fmul_rn(a, __fsub_rn(1.f, s)), __fmul_rn(b, s));
+}
+
+// Encode P samples of one ray (depths in shared `zs`) into rows [row0, row0+P).
+__device__ __forceinline__ void encode_ray(const float o0, const float o1, const float o2, const float d0,
+                                           const float d1, const float d2, const float* zs, int P, int64_t row0,
+                                           float* __restrict__ out_enc, __nv_bfloat16* __restrict__ out_bf,
+                                           float* stage, int lane) {
+    const int k = lane / 3, c = lane - 3 * k;
+    const float freq = (float)(1 << (k < 10 ? k : 0));
+    for (int j = 0; j < P; ++j) {
+        float* st = stage + (j & 1) * 64;
+        const float z = zs[j];
+        // rays_o + rays_d * z, nof/render.py:458 (mul then add, no FMA)
+        const float x0 = __fadd_rn(o0, __fmul_rn(d0, z));
+        const float x1 = __fadd_rn(o1, __fmul_rn(d1, z));
+        const float x2 = __fadd_rn(o2, __fmul_rn(d2, z));
+        if (lane < 30) {
+            const float x = c == 0 ? x0 : (c == 1 ? x1 : x2);
+            float s, cs;
+            sincosf(freq * x, &s, &cs);      // freq is a power of two: freq*x is exact (models.py:23,38)
+            st[3 + 6 * k + c] = s;
+            st[6 + 6 * k + c] = cs;
+        } else if (lane == 30) {
+            st[0] = x0; st[1] = x1; st[2] = x2; st[63] = 0.f;
+        }
+        __syncwarp();
+        const int64_t row = row0 + j;
+        if (out_enc) {
+            out_enc[row * 64 + lane] = st[lane];
+            out_enc[row * 64 + 32 + lane] = st[32 + lane];
+        }
+        if (out_bf) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(st[2 * lane], st[2 * lane + 1]);
+            reinterpret_cast<__nv_bfloat162*>(out_bf + row * 64)[lane] = v;
+        }
+        // the other half of `stage` is used by the next iteration; one __syncwarp per sample is enough
+    }
+    __syncwarp();
+}
+
+// stable merge of two ascending lists a (na) and b (nb) into out (na+nb); ties: a first (torch.sort of cat([a,b]))
+__device__ __forceinline__ void rank_merge(const float* a, int na, const float* b, int nb, float* out, int lane) {
+    for (int i = lane; i < na; i += 32) {
+        const float v = a[i];
+        int lo = 0, hi = nb;                  // count of b < v
+        while (lo < hi) { int m = (lo + hi) >> 1; if (b[m] < v) lo = m + 1; else hi = m; }
+        out[i + lo] = v;
+    }
+    for (int j = lane; j < nb; j += 32) {
+        const float v = b[j];
+        int lo = 0, hi = na;                  // count of a <= v
+        while (lo < hi) { int m = (lo + hi) >> 1; if (a[m] <= v) lo = m + 1; else hi = m; }
+        out[j + lo] = v;
+    }
+}
+
+__device__ __forceinline__ void bitonic_sort(float* s, int npad, int lane) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < npad; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float a = s[i], b = s[ixj];
+                    const bool asc = (i & k) == 0;
+                    if ((a > b) == asc) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// sample_pdf body (render.py:371-410) for one ray: `wts` are the nb-1 raw weights, bins/cdf are nb-long shared arrays.
+__device__ __forceinline__ void inverse_cdf(const float* bins, float* cdf, const float* __restrict__ wts, int nb,
+                                            const float* __restrict__ u, int Ni, int NiPad, float* zs, int lane) {
+    const int nw = nb - 1;
+    float part = 0.f;
+    for (int i = lane; i < nw; i += 32) part += __fadd_rn(wts[i], 1e-5f);     // weights + 1e-5 (:373)
+    const float total = warp_sum(part);
+    // cdf = [0, cumsum(pdf)]  -- warp scan in rounds of 32
+    float carry = 0.f;
+    if (lane == 0) cdf[0] = 0.f;
+    for (int base = 0; base < nw; base += 32) {
+        const int i = base + lane;
+        float v = i < nw ? __fdiv_rn(__fadd_rn(wts[i], 1e-5f), total) : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(FULL_MASK, v, o);
+            if (lane >= o) v += t;
+        }
+        v += carry;
+        if (i < nw) cdf[i + 1] = v;
+        carry = __shfl_sync(FULL_MASK, v, 31);
+    }
+    __syncwarp();
+    for (int j = lane; j < NiPad; j += 32) {
+        float out = INFINITY;
+        if (j < Ni) {
+            const float uu = u[j];
+            int lo = 0, hi = nb;            // searchsorted(cdf, u, right=True)
+            while (lo < hi) { int m = (lo + hi) >> 1; if (cdf[m] <= uu) lo = m + 1; else hi = m; }
+            const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+            float denom = __fsub_rn(cdf[above], cdf[below]);
+            if (denom < 1e-5f) denom = 1.f;
+            const float t = __fdiv_rn(__fsub_rn(uu, cdf[below]), denom);
+            out = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+        }
+        zs[j] = out;
+    }
+    __syncwarp();
+}
+
+__global__ void k_sample_pdf(const float* __restrict__ bins_g, const float* __restrict__ wts, int64_t n, int nb,
+                             const float* __restrict__ u, int u_ld, int Ni, float* __restrict__ out) {
+    extern __shared__ float smf[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* bins = smf + (size_t)wib * (2 * nb + Ni);
+    float* cdf = bins + nb;
+    float* zs = cdf + nb;
+    for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
+        for (int i = lane; i < nb; i += 32) bins[i] = bins_g[r * nb + i];
+        __syncwarp();
+        inverse_cdf(bins, cdf, wts + r * (nb - 1), nb, u + (u_ld ? r * (int64_t)u_ld : 0), Ni, Ni, zs, lane);
+        for (int j = lane; j < Ni; j += 32) out[r * Ni + j] = zs[j];
+        __syncwarp();
+    }
+}
+
+__global__ void k_sample_encode_coarse(const float* __restrict__ rays, int ld, int64_t n, int near_col, int far_col,
+                                       int cnear_col, int cfar_col, const float* __restrict__ steps_a, int n_a,
+                                       const float* __restrict__ steps_b, int n_b, int use_disp, float perturb,
+                                       const float* __restrict__ U, float* __restrict__ out_z,
+                                       float* __restrict__ out_enc, __nv_bfloat16* __restrict__ out_bf) {
+    extern __shared__ float smf[];
+    const int S = n_a + n_b;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* za = smf + (size_t)wib * (2 * S + 128);
+    float* tmp = za + S;
+    float* stage = tmp + S;
+    for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
+        const float* ray = rays + r * ld;
+        const float near = ray[near_col], far = ray[far_col];
+        // ---- z placement (render.py:430-442, :565-570)
+        const bool asc_a = !(far < near);
+        for (int i = lane; i < n_a; i += 32) {
+            const float s = steps_a[i];
+            float v;
+            if (use_disp) {
+                const float inv = __fadd_rn(__fmul_rn(__fdiv_rn(1.f, near), __fsub_rn(1.f, s)),
+                                            __fmul_rn(__fdiv_rn(1.f, far), s));
+                v = __fdiv_rn(1.f, inv);
+            } else {
+                v = lerp_rn(near, far, s);
+            }
+            tmp[(asc_a || n_b == 0) ? i : n_a - 1 - i] = v;
+        }
+        if (n_b > 0) {
+            const float cn = ray[cnear_col], cf = ray[cfar_col];
+            const bool asc_b = !(cf < cn);
+            for (int i = lane; i < n_b; i += 32) tmp[n_a + (asc_b ? i : n_b - 1 - i)] = lerp_rn(cn, cf, steps_b[i]);
+        }
+        __syncwarp();
+        if (n_b > 0) rank_merge(tmp, n_a, tmp + n_a, n_b, za, lane);
+        else for (int i = lane; i < S; i += 32) za[i] = tmp[i];
+        __syncwarp();
+        // ---- stratified jitter (render.py:449-454)
+        if (perturb > 0.f) {
+            for (int i = lane; i < S; i += 32) {
+                const float zi = za[i];
+                const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(za[i - 1], zi)) : zi;
+                const float upper = i < S - 1 ? __fmul_rn(0.5f, __fadd_rn(zi, za[i + 1])) : zi;
+                const float pr = __fmul_rn(perturb, U[r * S + i]);
+                tmp[i] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), pr));
+            }
+            __syncwarp();
+            for (int i = lane; i < S; i += 32) za[i] = tmp[i];
+            __syncwarp();
+        }
+        for (int i = lane; i < S; i += 32) out_z[r * S + i] = za[i];
+        if (out_enc || out_bf)
+            encode_ray(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], za, S, r * S, out_enc, out_bf, stage, lane);
+        __syncwarp();
+    }
+}
+
+__global__ void k_sample_encode_fine(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ z,
+                                     const float* __restrict__ w, int S, const float* __restrict__ u, int u_ld, int Ni,
+                                     int NiPad, float* __restrict__ out_z, float* __restrict__ out_enc,
+                                     __nv_bfloat16* __restrict__ out_bf) {
+    extern __shared__ float smf[];
+    const int F = S + Ni;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = (size_t)S + 2 * (S - 1) + NiPad + F + 128;
+    float* zc = smf + wib * per_warp;
+    float* bins = zc + S;
+    float* cdf = bins + (S - 1);
+    float* zs = cdf + (S - 1);
+    float* zo = zs + NiPad;
+    float* stage = zo + F;
+    const int nb = S - 1;                      // len(bins) == len(cdf)
+    for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
+        for (int i = lane; i < S; i += 32) zc[i] = z[r * S + i];
+        __syncwarp();
+        // bins = .5 * (z[1:] + z[:-1])  (render.py:463);  weights = w[1:-1] (render.py:464)
+        for (int i = lane; i < nb; i += 32) bins[i] = __fmul_rn(0.5f, __fadd_rn(zc[i + 1], zc[i]));
+        inverse_cdf(bins, cdf, w + r * S + 1, nb, u + (u_ld ? r * (int64_t)u_ld : 0), Ni, NiPad, zs, lane);
+        // torch.sort(cat([z, z_samples])) (render.py:467): sort the new samples only if they are not already
+        // ascending, then merge with the (ascending) coarse depths.
+        int unsorted = 0;
+        for (int j = lane; j + 1 < Ni; j += 32) unsorted |= (zs[j] > zs[j + 1]);
+        if (__any_sync(FULL_MASK, unsorted)) bitonic_sort(zs, NiPad, lane);
+        rank_merge(zc, S, zs, Ni, zo, lane);
+        __syncwarp();
+        for (int i = lane; i < F; i += 32) out_z[r * F + i] = zo[i];
+        const float* ray = rays + r * ld;
+        if (out_enc || out_bf)
+            encode_ray(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], zo, F, r * F, out_enc, out_bf, stage, lane);
+        __syncwarp();
+    }
+}
+
+// Embedding.forward alone (models.py:27-41): one warp per point.
+__global__ void k_embed(const float* __restrict__ x, int64_t b, float* __restrict__ out, int out_ld) {
+    __shared__ float stage_all[8 * 64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* st = stage_all + wib * 64;
+    const int k = lane / 3, c = lane - 3 * k;
+    const float freq = (float)(1 << (k < 10 ? k : 0));
+    for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < b; r += (int64_t)gridDim.x * wpb) {
+        const float x0 = x[3 * r], x1 = x[3 * r + 1], x2 = x[3 * r + 2];
+        if (lane < 30) {
+            const float xv = c == 0 ? x0 : (c == 1 ? x1 : x2);
+            float s, cs;
+            sincosf(freq * xv, &s, &cs);
+            st[3 + 6 * k + c] = s;
+            st[6 + 6 * k + c] = cs;
+        } else if (lane == 30) {
+            st[0] = x0; st[1] = x1; st[2] = x2; st[63] = 0.f;
+        }
+        __syncwarp();
+        for (int col = lane; col < out_ld; col += 32) out[r * out_ld + col] = col < 63 ? st[col] : 0.f;
+        __syncwarp();
+    }
+}
+
+static int pick_warps(size_t per_warp_bytes, const char* what, int* wpb) {
+    int w = (int)(SE_MAX_SMEM / per_warp_bytes);
+    if (w < 1) {
+        pcn_set_error("%s: %zu bytes of shared memory per ray exceed the %d-byte budget", what, per_warp_bytes,
+                      SE_MAX_SMEM);
+        return PCNERF_ERR_UNSUPPORTED;
+    }
+    *wpb = w > 8 ? 8 : w;
+    return 0;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n, int near_col, int far_col,
+                                           int cnear_col, int cfar_col, const float* steps_a, int n_a,
+                                           const float* steps_b, int n_b, int use_disp, float perturb, const float* U,
+                                           float* out_z, float* out_enc, void* out_enc_bf16, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && ld >= 8 && n_a >= 1 && n_b >= 0, "sample_encode_coarse: bad sizes");
+    PCN_CHECK_ARG(steps_a && (n_b == 0 || steps_b), "sample_encode_coarse: linspace tables missing");
+    PCN_CHECK_ARG(!(perturb > 0.f) || U, "sample_encode_coarse: perturb > 0 needs pre-drawn U");
+    PCN_CHECK_ARG(near_col < ld && far_col < ld && (n_b == 0 || (cnear_col < ld && cfar_col < ld)),
+                  "sample_encode_coarse: column index out of range");
+    if (n == 0) return 0;
+    const int S = n_a + n_b;
+    const size_t per_warp = (size_t)(2 * S + 128) * sizeof(float);
+    int wpb;
+    int rc = pick_warps(per_warp, "sample_encode_coarse", &wpb);
+    if (rc) return rc;
+    const size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024)
+        PCN_CUDA(cudaFuncSetAttribute(k_sample_encode_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = pcn_cdiv(n, wpb);
+    const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
+    if (grid > cap) grid = cap;
+    k_sample_encode_coarse<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+        rays, ld, n, near_col, far_col, cnear_col, cfar_col, steps_a, n_a, steps_b, n_b, use_disp, perturb, U, out_z,
+        out_enc, (__nv_bfloat16*)out_enc_bf16);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, const float* z, const float* w, int S,
+                                         const float* u, int u_ld, int Ni, float* out_z, float* out_enc,
+                                         void* out_enc_bf16, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && ld >= 6 && S >= 3 && Ni >= 1, "sample_encode_fine: bad sizes (need S >= 3, Ni >= 1)");
+    PCN_CHECK_ARG(u && (u_ld == 0 || u_ld == Ni), "sample_encode_fine: u must be (Ni) with u_ld 0 or (n,Ni) with u_ld Ni");
+    if (n == 0) return 0;
+    const int NiPad = next_pow2(Ni);
+    const size_t per_warp = ((size_t)S + 2 * (S - 1) + NiPad + (S + Ni) + 128) * sizeof(float);
+    int wpb;
+    int rc = pick_warps(per_warp, "sample_encode_fine", &wpb);
+    if (rc) return rc;
+    const size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024)
+        PCN_CUDA(cudaFuncSetAttribute(k_sample_encode_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = pcn_cdiv(n, wpb);
+    const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
+    if (grid > cap) grid = cap;
+    k_sample_encode_fine<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+        rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__nv_bfloat16*)out_enc_bf16);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int nb, const float* u, int u_ld,
+                                 int Ni, float* out, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && nb >= 2 && Ni >= 1, "sample_pdf: bad sizes");
+    PCN_CHECK_ARG(u && (u_ld == 0 || u_ld == Ni), "sample_pdf: u must be (Ni) with u_ld 0 or (n,Ni) with u_ld Ni");
+    if (n == 0) return 0;
+    const size_t per_warp = ((size_t)2 * nb + Ni) * sizeof(float);
+    int wpb;
+    int rc = pick_warps(per_warp, "sample_pdf", &wpb);
+    if (rc) return rc;
+    const size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024)
+        PCN_CUDA(cudaFuncSetAttribute(k_sample_pdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = pcn_cdiv(n, wpb);
+    const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
+    if (grid > cap) grid = cap;
+    k_sample_pdf<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(bins, weights, n, nb, u, u_ld, Ni, out);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_embed(const float* x, int64_t b, float* out, int out_ld, void* stream) {
+    PCN_CHECK_ARG(b >= 0 && out_ld >= 63, "embed: out_ld must be >= 63");
+    if (b == 0) return 0;
+    int64_t grid = pcn_cdiv(b, 8);
+    const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
+    if (grid > cap) grid = cap;
+    k_embed<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, b, out, out_ld);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}

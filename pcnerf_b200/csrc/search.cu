@@ -1,0 +1,247 @@
+// K5: parent-then-child depth-inference search (nof/render.py:229-368) and the output points (:674-684).
+//
+// Per candidate row (one warp per row): normalised weights, strict child mask with expand-until-non-empty,
+// Gaussian smoothing of the weights (scipy.ndimage.gaussian_filter sigma=5: radius 20, 'reflect', fp64 accumulation in
+// NI_Correlate1D's symmetric order, rounded to fp32) + first-max argmax, peak-in-child flag, in-child weight sum,
+// depth by method 1 or 2.  A second kernel picks one winner per candidate group.  The fp64 smoothing is compiled
+// with explicit __dmul_rn/__dadd_rn so that the argmax is bit-identical to SciPy's.
+#include "common.cuh"
+
+#define SRCH_MAX_SMEM (200 * 1024)
+#define GAUSS_R 20
+
+struct GaussK { double k[GAUSS_R + 1]; };   // k[j] = weight at offset j-GAUSS_R (j = 0..R), symmetric
+
+struct MaskBounds { float lo, hi; };
+
+__device__ __forceinline__ MaskBounds strict_bounds(const float* zs, int P, float cn, float cf, int lane) {
+    double g = 0.01;                          // render.py:253
+    MaskBounds b;
+    for (int it = 0; it < 1000000; ++it) {
+        b.lo = __fsub_rn(cn, (float)g);
+        b.hi = __fadd_rn(cf, (float)g);
+        int any = 0;
+        for (int i = lane; i < P; i += 32) { const float z = zs[i]; any |= (b.lo < z && z < b.hi); }
+        if (__any_sync(FULL_MASK, any)) break;
+        g = g + 0.01;
+    }
+    return b;
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // scipy 'reflect' (d c b a | a b c d | d c b a), valid for any extension length
+    const int per = 2 * n;
+    int m = i % per;
+    if (m < 0) m += per;
+    return m >= n ? per - 1 - m : m;
+}
+
+__global__ void k_search_rows(const float* __restrict__ p, const float* __restrict__ z, const float* __restrict__ rays,
+                              int ld, int64_t n, int P, int cnear_col, int cfar_col, float epsilon, int method,
+                              GaussK gk, float* __restrict__ w, float* __restrict__ depth,
+                              uint8_t* __restrict__ peak_in, float* __restrict__ wsum_child,
+                              double* __restrict__ sums) {
+    extern __shared__ float smf[];
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* sz = smf + (size_t)wib * 2 * P;
+    float* sw = sz + P;
+    double acc_op = 0;
+    for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
+        for (int i = lane; i < P; i += 32) sz[i] = z[r * P + i];
+        // weights (render.py:241-246)
+        float carry = 1.f, sumv = 0.f, op = 0.f;
+        for (int base = 0; base < P; base += 32) {
+            const int i = base + lane;
+            const float pi = i < P ? p[r * P + i] : 0.f;
+            const float fr = __fsub_rn(1.f, pi);
+            float incl = fr;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl *= t;
+            }
+            float excl = __shfl_up_sync(FULL_MASK, incl, 1);
+            if (lane == 0) excl = 1.f;
+            const float v = carry * excl * pi;
+            carry = carry * __shfl_sync(FULL_MASK, incl, 31);
+            if (i < P) {
+                sw[i] = v;
+                sumv += v;
+                op += __fadd_rn(__fadd_rn(logf(__fadd_rn(0.1f, pi)), logf(__fadd_rn(0.1f, fr))), 2.20727f);
+            }
+        }
+        const float denom = __fadd_rn(warp_sum(sumv), epsilon);
+        acc_op += (double)warp_sum(op);
+        for (int i = lane; i < P; i += 32) {
+            const float wi = __fdiv_rn(sw[i], denom);
+            sw[i] = wi;
+            w[r * P + i] = wi;
+        }
+        __syncwarp();
+        const float cn = rays[r * ld + cnear_col], cf = rays[r * ld + cfar_col];
+        const MaskBounds b = strict_bounds(sz, P, cn, cf, lane);
+        // Gaussian smoothing + first-max argmax (render.py:303-308)
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int i = lane; i < P; i += 32) {
+            double t = __dmul_rn((double)sw[i], gk.k[GAUSS_R]);
+            for (int j = -GAUSS_R; j < 0; ++j) {
+                const double a = (double)sw[reflect_idx(i + j, P)];
+                const double c = (double)sw[reflect_idx(i - j, P)];
+                t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gk.k[j + GAUSS_R]));
+            }
+            const float s = (float)t;
+            if (s > best) { best = s; besti = i; }   // ascending i per lane -> keeps the first maximum
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(FULL_MASK, best, o);
+            const int oi = __shfl_xor_sync(FULL_MASK, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        // NaN rows: torch.argmax returns the first NaN; not reproduced (weights are finite for finite inputs)
+        if (besti == 0x7fffffff) besti = 0;
+        float ws = 0.f, dsum = 0.f;
+        for (int i = lane; i < P; i += 32) {
+            const float zi = sz[i];
+            const float m = (b.lo < zi && zi < b.hi) ? 1.f : 0.f;
+            ws += sw[i] * m;
+            if (method != 2) dsum += sw[i] * zi;
+        }
+        ws = warp_sum(ws);
+        if (method == 2) {
+            // render.py:345-348
+            const float cden = __fadd_rn(ws, epsilon);
+            for (int i = lane; i < P; i += 32) {
+                const float zi = sz[i];
+                const float m = (b.lo < zi && zi < b.hi) ? 1.f : 0.f;
+                dsum += __fdiv_rn(sw[i] * m, cden) * zi;
+            }
+        }
+        dsum = warp_sum(dsum);
+        if (lane == 0) {
+            const float zp = sz[besti];
+            peak_in[r] = (b.lo < zp && zp < b.hi) ? 1 : 0;
+            wsum_child[r] = ws;
+            depth[r] = dsum;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) red[wib] = acc_op;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < wpb; ++k) t += red[k];
+        atomicAdd(&sums[0], t);
+    }
+}
+
+// Group winner (render.py:317-340).  The reference walks the rows sequentially, jumping over the followers of each
+// head.  Parallel form for well-formed input (a head row carries its follower count > 0, a singleton 0, follower
+// rows 0): (A) every head marks its followers as covered (bit 2); (B) every uncovered row acts as head / singleton
+// and sets bit 1 on the winner; (C) the cover bit is cleared.
+__global__ void k_select_cover(const int64_t* __restrict__ other, int64_t n, uint8_t* __restrict__ flag) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t oi = other[i];
+    for (int64_t j = 1; j <= oi && i + j < n; ++j) flag[i + j] = 2;
+}
+
+__global__ void k_select_winner(const int64_t* __restrict__ other, const uint8_t* __restrict__ peak_in,
+                                const float* __restrict__ wsum, int64_t n, volatile uint8_t* flag) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i] & 2) return;                   // follower: decided by its head
+    const int64_t oi = other[i];
+    if (oi < 0) return;
+    int64_t k = oi;
+    if (i + k >= n) k = n - 1 - i;             // the reference would raise IndexError on a truncated group
+    int64_t win = i;
+    if (k > 0 && !peak_in[i]) {
+        bool found = false;
+        for (int64_t j = 1; j <= k; ++j)
+            if (peak_in[i + j]) { win = i + j; found = true; break; }
+        if (!found)
+            for (int64_t j = 1; j <= k; ++j)
+                if (wsum[i + j] > wsum[win]) win = i + j;
+    }
+    flag[win] = (win == i) ? 1 : 3;            // single writer per byte: rows i+1..i+k belong to this head only
+}
+
+__global__ void k_select_clear(int64_t n, uint8_t* __restrict__ flag) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] &= 1;
+}
+
+__global__ void k_points(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ depth,
+                         float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rays + i * ld;
+    const float d = depth[i];
+    out[3 * i + 0] = __fadd_rn(r[0], __fmul_rn(d, r[3]));
+    out[3 * i + 1] = __fadd_rn(r[1], __fmul_rn(d, r[4]));
+    out[3 * i + 2] = __fadd_rn(r[2], __fmul_rn(d, r[5]));
+}
+
+extern "C" int pcnerf_search_rows(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
+                                  int cnear_col, int cfar_col, float epsilon, int method, float* w, float* depth,
+                                  uint8_t* peak_in_child, float* wsum_child, double* sums, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && P >= 1 && cnear_col < ld && cfar_col < ld && sums, "search_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCN_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), st));
+    if (n == 0) return 0;
+    // scipy.ndimage._filters._gaussian_kernel1d(sigma=5, order=0, radius=int(4*5+0.5)=20): the 21 leading weights
+    // (offsets -20..0) as produced by numpy (exp, pairwise sum, divide) -- hex literals so that no host libm
+    // difference can change a bit; tests/test_oracle_golden.py::test_gaussian_filter_matches_scipy pins the oracle
+    // restatement against SciPy and tests/test_gpu_search.py pins this table against the oracle.
+    static const double kGauss[GAUSS_R + 1] = {
+        0x1.c113e67a34f9ap-16, 0x1.e9d347af7ba2cp-15, 0x1.00a91aed84201p-13, 0x1.026ceaaef5d9cp-12,
+        0x1.f3ffe5366298dp-12, 0x1.d0bb4c23b8d53p-11, 0x1.9f03a798bae24p-10, 0x1.64156b94ff939p-9,
+        0x1.258a96c00a508p-8,  0x1.d0fdc1a91a71bp-8,  0x1.61d971cc0d07ep-7,  0x1.02b6d98acd25ap-6,
+        0x1.6b7adf708e81bp-6,  0x1.eaa58a4ba7224p-6,  0x1.3e2acd55166dap-5,  0x1.8c75f2fc165cbp-5,
+        0x1.daa6517492b60p-5,  0x1.10fd11517a7f6p-4,  0x1.2db2f1c27e704p-4,  0x1.405ae2f8a8257p-4,
+        0x1.46d39dcd3d08cp-4};
+    GaussK gk;
+    for (int j = 0; j <= GAUSS_R; ++j) gk.k[j] = kGauss[j];
+    const size_t per_warp = (size_t)2 * P * sizeof(float);
+    int wpb = (int)(SRCH_MAX_SMEM / per_warp);
+    if (wpb < 1) {
+        pcn_set_error("search_rows: %d samples per row exceed the shared-memory budget", P);
+        return PCNERF_ERR_UNSUPPORTED;
+    }
+    if (wpb > 8) wpb = 8;
+    const size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024)
+        PCN_CUDA(cudaFuncSetAttribute(k_search_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = pcn_cdiv(n, wpb);
+    const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
+    if (grid > cap) grid = cap;
+    k_search_rows<<<(int)grid, wpb * 32, smem, st>>>(p, z, rays, ld, n, P, cnear_col, cfar_col, epsilon, method, gk, w,
+                                                    depth, peak_in_child, wsum_child, sums);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in_child, const float* wsum_child,
+                                    int64_t n, uint8_t* out_flag, void* stream) {
+    PCN_CHECK_ARG(n >= 0, "search_select: bad size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    PCN_CUDA(cudaMemsetAsync(out_flag, 0, (size_t)n, st));
+    const int g = (int)pcn_cdiv(n, 256);
+    k_select_cover<<<g, 256, 0, st>>>(other, n, out_flag);
+    k_select_winner<<<g, 256, 0, st>>>(other, peak_in_child, wsum_child, n, out_flag);
+    k_select_clear<<<g, 256, 0, st>>>(n, out_flag);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_points(const float* rays, int ld, int64_t n, const float* depth, float* out_xyz, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && ld >= 6, "points: bad arguments");
+    if (n == 0) return 0;
+    k_points<<<(int)pcn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(rays, ld, n, depth, out_xyz);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}

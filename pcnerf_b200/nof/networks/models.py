@@ -1,0 +1,137 @@
+"""Drop-in for nof/networks/models.py: same classes, constructor arguments, parameter / buffer names and state-dict
+keys (so reference checkpoints and `load_ckpt` work unchanged); `forward` runs the sm_100a kernels.
+
+Reference facts preserved (verified against the reference by tests/golden):
+  * every `nn.LeakyReLU(True)` has negative_slope == True == 1.0 -> identity (models.py:152,172,232,252);
+  * the activations meant for layer2 were appended to layer1 (models.py:172) -> layer2 is Linear+BN only;
+  * BatchNorm1d uses the batch statistics of the rows it is called with when the module is in train mode.
+The module tree below is built the same way so that `state_dict()` keys are identical
+(layer1.{0,1,3,4,6,7,9,10}.*, layer2.{0..7}.*, occ_out.0.*).
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+_DEFAULT_PRECISION = {"value": 0}
+
+
+def set_default_mlp_precision(p):
+    """'fp32' (CUDA-core GEMM, 1e-5 parity gate) or 'bf16' (tcgen05 tensor-core GEMM, 1e-3 gate)."""
+    _DEFAULT_PRECISION["value"] = {"fp32": 0, "bf16": 1, 0: 0, 1: 1}[p]
+
+
+class Embedding(nn.Module):
+    """nof/networks/models.py:4-41: x -> (x, sin(2^k x), cos(2^k x))_{k<N_freq}."""
+
+    def __init__(self, in_channels, N_freq, logscale=True):
+        super(Embedding, self).__init__()
+        self.N_freq = N_freq
+        self.in_channels = in_channels
+        self.funcs = [torch.sin, torch.cos]
+        if logscale:
+            self.freq_bands = 2 ** torch.linspace(0, N_freq - 1, N_freq)
+        else:
+            self.freq_bands = torch.linspace(1, 3 ** (N_freq - 1), N_freq)
+        self.logscale = logscale
+
+    def forward(self, x):
+        if not (self.in_channels == 3 and self.N_freq == 10 and self.logscale):
+            raise NotImplementedError("pcnerf_b200.Embedding: only in_channels=3, N_freq=10, logscale=True "
+                                      "(the PC-NeRF configuration) has a kernel")
+        return ops.embed(x.reshape(-1, 3), 63)
+
+
+class NOF(nn.Module):
+    """nof/networks/models.py:44-123 (NOF_coarse :125-203, NOF_fine :205-282, NOF_plusfine :284-359 are identical)."""
+
+    def __init__(self, feature_size=256, in_channels_xy=63, use_skip=True):
+        super(NOF, self).__init__()
+        self.feature_size = feature_size
+        self.in_channels_xy = in_channels_xy
+        self.use_skip = use_skip
+        layer1 = []
+        for i in range(4):
+            layer1.append(nn.Linear(in_channels_xy if i == 0 else feature_size, feature_size))
+            layer1.append(nn.BatchNorm1d(num_features=feature_size))
+            layer1.append(nn.LeakyReLU(True))
+        layer2 = []
+        for i in range(4):
+            if i == 0:
+                layer2.append(nn.Linear(in_channels_xy + feature_size if use_skip else feature_size, feature_size))
+            else:
+                layer2.append(nn.Linear(feature_size, feature_size))
+            layer2.append(nn.BatchNorm1d(num_features=feature_size))
+            layer1.append(nn.LeakyReLU(True))          # sic: the reference appends these to layer1
+        self.layer1 = nn.Sequential(*layer1)
+        self.layer2 = nn.Sequential(*layer2)
+        self.occ_out = nn.Sequential(nn.Linear(feature_size, 1), nn.Sigmoid())
+        self.precision = None                          # None -> module default (set_default_mlp_precision)
+
+    # ---- kernel-facing views of the module state
+    def _linears(self):
+        return [self.layer1[0], self.layer1[3], self.layer1[6], self.layer1[9],
+                self.layer2[0], self.layer2[2], self.layer2[4], self.layer2[6], self.occ_out[0]]
+
+    def _bns(self):
+        return [self.layer1[1], self.layer1[4], self.layer1[7], self.layer1[10],
+                self.layer2[1], self.layer2[3], self.layer2[5], self.layer2[7]]
+
+    def kernel_params(self):
+        """34 tensors in the order of ops.GRAD_SIZES: (W,b) x 9 then (gamma,beta) x 8."""
+        out = []
+        for lin in self._linears():
+            out += [lin.weight, lin.bias]
+        for bn in self._bns():
+            out += [bn.weight, bn.bias]
+        return out
+
+    def _buffers3(self):
+        bns = self._bns()
+        return ([b.running_mean for b in bns], [b.running_var for b in bns], [b.num_batches_tracked for b in bns])
+
+    def _check_supported(self):
+        if not (self.feature_size == 256 and self.in_channels_xy == 63 and self.use_skip):
+            raise NotImplementedError("pcnerf_b200.NOF: kernels exist for feature_size=256, in_channels_xy=63, "
+                                      "use_skip=True (the PC-NeRF configuration)")
+        for bn in self._bns():
+            if bn.momentum != 0.1 or bn.eps != 1e-5 or not bn.affine or not bn.track_running_stats:
+                raise NotImplementedError("pcnerf_b200.NOF: BatchNorm1d must keep its default configuration")
+        for m in list(self.layer1) + list(self.layer2):
+            if isinstance(m, nn.LeakyReLU) and float(m.negative_slope) != 1.0:
+                raise NotImplementedError("pcnerf_b200.NOF: negative_slope != 1 (the reference builds LeakyReLU(True))")
+
+    def mlp_precision(self):
+        return _DEFAULT_PRECISION["value"] if self.precision is None else {"fp32": 0, "bf16": 1, 0: 0, 1: 1}[self.precision]
+
+    def forward_encoded(self, enc, chunk=None):
+        """enc: (rows, 64) encodings padded with a zero column (fp32, or bf16 for the tensor-core path).
+        One BN batch per `chunk` rows.  Returns p_occ (rows,)."""
+        self._check_supported()
+        prec = self.mlp_precision()
+        want = torch.bfloat16 if prec == 1 else torch.float32
+        if enc.dtype != want:
+            enc = enc.to(want)
+        rows = enc.shape[0]
+        chunk = rows if chunk is None else int(chunk)
+        return ops.MLPFunction.apply(enc.contiguous(), max(chunk, 1), self.training, prec, self._buffers3(),
+                                     *self.kernel_params())
+
+    def forward(self, x):
+        """x: (B, 63) embedded positions -> p_occ (B, 1)   (models.py:183-203)."""
+        if x.dim() != 2 or x.shape[1] != 63:
+            raise ValueError("NOF.forward expects (B, 63) encodings")
+        enc = torch.nn.functional.pad(x, (0, 1))
+        return self.forward_encoded(enc).view(-1, 1)
+
+
+class NOF_coarse(NOF):
+    pass
+
+
+class NOF_fine(NOF):
+    pass
+
+
+class NOF_plusfine(NOF):
+    pass

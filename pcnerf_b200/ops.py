@@ -1,0 +1,448 @@
+"""Tensor-level wrappers over the C ABI (include/pcnerf_b200.h) + the autograd glue.
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every computation on the path is a
+kernel of libpcnerf_b200.so.  All tensors must be CUDA tensors; there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MlpGrads, MlpParams, check, lib
+
+COMP_CHILD_LOSS, COMP_OPACITY = 1, 2
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+LAUNCHES = {"count": 0}          # number of C-ABI compute calls (each enqueues >= 1 kernel); bench reports it
+
+
+def _count(n=1):
+    LAUNCHES["count"] += n
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("pcnerf_b200: %s must be a CUDA tensor (the B200 path has no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("pcnerf_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _h3(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    return a, a.ctypes.data_as(_f64p)
+
+
+_LINSPACE = {}
+
+
+def linspace01(n, device):
+    """torch.linspace(0, 1, n) evaluated on the CPU (the values the reference's CPU path and the golden fixtures see),
+    cached on the device."""
+    key = (int(n), str(device))
+    t = _LINSPACE.get(key)
+    if t is None:
+        t = torch.linspace(0, 1, int(n)).to(device)
+        _LINSPACE[key] = t
+    return t
+
+
+# ----------------------------------------------------------------------------------------------------------- K1 AABB
+
+
+def _f64(t, device="cuda"):
+    if isinstance(t, torch.Tensor):
+        return t.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.asarray(t, dtype=np.float64), device=device).contiguous()
+
+
+def _rays_od(ray_o, ray_d):
+    d = _f64(ray_d).reshape(-1, 3)
+    o = _f64(ray_o).reshape(-1, 3)
+    if o.shape[0] == 1 and d.shape[0] != 1:
+        o = o.expand(d.shape[0], 3).contiguous()
+    return o, d
+
+
+def aabb_far_bound(ray_o, ray_d, x_max, x_min, y_max, y_min, z_max, z_min):
+    o, d = _rays_od(ray_o, ray_d)
+    out = torch.empty(d.shape[0], dtype=torch.float64, device=d.device)
+    keep, hp = _h3([x_max, x_min, y_max, y_min, z_max, z_min])
+    check(lib().pcnerf_aabb_far_bound(_p(o), _p(d), d.shape[0], hp, _p(out), _stream()))
+    _count()
+    return out
+
+
+def aabb_slab(ray_o, ray_d, aabb_min, aabb_max):
+    o, d = _rays_od(ray_o, ray_d)
+    out = torch.empty(d.shape[0], dtype=torch.float64, device=d.device)
+    k1, pmin = _h3(aabb_min)
+    k2, pmax = _h3(aabb_max)
+    check(lib().pcnerf_aabb_slab(_p(o), _p(d), d.shape[0], pmin, pmax, _p(out), _stream()))
+    _count()
+    return out
+
+
+def aabb_child_pairs(variant, ray_o, ray_d, boxes):
+    o, d = _rays_od(ray_o, ray_d)
+    b = _f64(boxes).reshape(-1, 6)
+    n, K = d.shape[0], b.shape[0]
+    flag = torch.empty((n, K), dtype=torch.uint8, device=d.device)
+    near = torch.empty((n, K), dtype=torch.float64, device=d.device)
+    far = torch.empty((n, K), dtype=torch.float64, device=d.device)
+    check(lib().pcnerf_aabb_child_pairs(int(variant), _p(o), _p(d), n, _p(b), K, _p(flag), _p(near), _p(far), _stream()))
+    _count()
+    return flag.bool(), near, far
+
+
+def aabb_dist_to_ray(ray_o, ray_d, centres):
+    o, d = _rays_od(ray_o, ray_d)
+    c = _f64(centres).reshape(-1, 3)
+    out = torch.empty((d.shape[0], c.shape[0]), dtype=torch.float64, device=d.device)
+    check(lib().pcnerf_aabb_dist_to_ray(_p(o), _p(d), d.shape[0], _p(c), c.shape[0], _p(out), _stream()))
+    _count()
+    return out
+
+
+def aabb_find_box(centres, boxes, points, knn=10):
+    c = _f64(centres).reshape(-1, 3)
+    b = _f64(boxes).reshape(-1, 6)
+    q = _f64(points).reshape(-1, 3)
+    out = torch.empty(q.shape[0], dtype=torch.int32, device=q.device)
+    check(lib().pcnerf_aabb_find_box(_p(c), _p(b), c.shape[0], _p(q), q.shape[0], int(knn), _p(out), _stream()))
+    _count()
+    return out
+
+
+def aabb_pack_train(variant, ray_o, ray_d, dist, points, centres, boxes, boxes_bigger, parent, surface_expand, knn=10):
+    """parent = (x_min, x_max, y_min, y_max, z_min, z_max).  Returns (rays (N,15) f32, keep mask) compacted in order."""
+    o, d = _rays_od(ray_o, ray_d)
+    dist = _f64(dist).reshape(-1)
+    pts = _f64(points).reshape(-1, 3)
+    c, b, bb = _f64(centres).reshape(-1, 3), _f64(boxes).reshape(-1, 6), _f64(boxes_bigger).reshape(-1, 6)
+    n = d.shape[0]
+    rays = torch.empty((n, 15), dtype=torch.float32, device=d.device)
+    keep = torch.empty(n, dtype=torch.uint8, device=d.device)
+    x_min, x_max, y_min, y_max, z_min, z_max = parent
+    k, hp = _h3([x_max, x_min, y_max, y_min, z_max, z_min])
+    check(lib().pcnerf_aabb_pack_train(int(variant), _p(o), _p(d), _p(dist), _p(pts), n, _p(c), _p(b), _p(bb), c.shape[0],
+                                       hp, float(surface_expand), int(knn), _p(rays), _p(keep), _stream()))
+    _count()
+    keep = keep.bool()
+    return rays[keep], keep
+
+
+def aabb_build_groups(ray_o, ray_d, dist, boxes, boxes_larger, parent_min, parent_max, depth_inference_method=2,
+                      grow_step=0.005, prefilter=0.65):
+    """Returns (rays (N',13) f32, ranges (N',1) f32, other (N',1) i64, kept ray mask (N,))."""
+    o, d = _rays_od(ray_o, ray_d)
+    dist = _f64(dist).reshape(-1)
+    b, bl = _f64(boxes).reshape(-1, 6), _f64(boxes_larger).reshape(-1, 6)
+    n, K = d.shape[0], b.shape[0]
+    count = torch.empty(n, dtype=torch.int32, device=d.device)
+    pfar = torch.empty(n, dtype=torch.float64, device=d.device)
+    k1, pmin = _h3(parent_min)
+    k2, pmax = _h3(parent_max)
+    check(lib().pcnerf_aabb_groups_count(_p(o), _p(d), n, _p(b), _p(bl), K, pmin, pmax, int(depth_inference_method),
+                                         float(grow_step), float(prefilter), _p(count), _p(pfar), _stream()))
+    csum = torch.cumsum(count.to(torch.int64), 0)
+    total = int(csum[-1].item()) if n > 0 else 0        # output size is data dependent: one host sync
+    offset = (csum - count).contiguous()
+    rays = torch.empty((total, 13), dtype=torch.float32, device=d.device)
+    ranges = torch.empty((total, 1), dtype=torch.float32, device=d.device)
+    other = torch.empty((total, 1), dtype=torch.int64, device=d.device)
+    scratch = torch.empty((max(total, 1), 2), dtype=torch.float64, device=d.device)
+    check(lib().pcnerf_aabb_groups_fill(_p(o), _p(d), _p(dist), n, _p(b), _p(bl), K, int(depth_inference_method),
+                                        float(grow_step), float(prefilter), _p(count), _p(offset), _p(pfar), _p(scratch),
+                                        _p(rays), _p(ranges), _p(other), _stream()))
+    _count(2)
+    return rays, ranges, other, count > 0
+
+
+# ----------------------------------------------------------------------------------------------- K2 sample + encode
+
+
+def sample_encode_coarse(rays, n_a, n_b=0, near_col=6, far_col=7, cnear_col=10, cfar_col=11, use_disp=False,
+                         perturb=0.0, U=None, want_enc=True, bf16=False):
+    rays = _cuda_f32(rays, "rays")
+    n, ld = rays.shape
+    S = n_a + n_b
+    sa = linspace01(n_a, rays.device)
+    sb = linspace01(n_b, rays.device) if n_b > 0 else None
+    if perturb > 0:
+        if U is None:
+            U = torch.rand((n, S), device=rays.device)
+        U = _cuda_f32(U, "U")
+    z = torch.empty((n, S), dtype=torch.float32, device=rays.device)
+    enc = enc_bf = None
+    if want_enc:
+        if bf16:
+            enc_bf = torch.empty((n * S, 64), dtype=torch.bfloat16, device=rays.device)
+        else:
+            enc = torch.empty((n * S, 64), dtype=torch.float32, device=rays.device)
+    check(lib().pcnerf_sample_encode_coarse(_p(rays), ld, n, near_col, far_col, cnear_col, cfar_col, _p(sa), n_a, _p(sb),
+                                            n_b, int(bool(use_disp)), float(perturb), _p(U) if perturb > 0 else None,
+                                            _p(z), _p(enc), _p(enc_bf), _stream()))
+    _count()
+    return z, (enc_bf if bf16 else enc)
+
+
+def sample_encode_fine(rays, z, w, Ni, u=None, det=True, want_enc=True, bf16=False):
+    rays = _cuda_f32(rays, "rays")
+    z = _cuda_f32(z, "z")
+    w = _cuda_f32(w.detach(), "w")
+    n, S = z.shape
+    if det:
+        u = linspace01(Ni, rays.device)
+        u_ld = 0
+    else:
+        u = _cuda_f32(u, "u")
+        u_ld = Ni
+    zf = torch.empty((n, S + Ni), dtype=torch.float32, device=rays.device)
+    enc = enc_bf = None
+    if want_enc:
+        if bf16:
+            enc_bf = torch.empty((n * (S + Ni), 64), dtype=torch.bfloat16, device=rays.device)
+        else:
+            enc = torch.empty((n * (S + Ni), 64), dtype=torch.float32, device=rays.device)
+    check(lib().pcnerf_sample_encode_fine(_p(rays), rays.shape[1], n, _p(z), _p(w), S, _p(u), u_ld, Ni, _p(zf), _p(enc),
+                                          _p(enc_bf), _stream()))
+    _count()
+    return zf, (enc_bf if bf16 else enc)
+
+
+def sample_pdf(bins, weights, Ni, u=None, det=False):
+    bins = _cuda_f32(bins, "bins")
+    weights = _cuda_f32(weights, "weights")
+    n, nb = bins.shape
+    if weights.shape != (n, nb - 1):
+        raise ValueError("sample_pdf: weights must be (N, len(bins)-1)")
+    if det:
+        u, u_ld = linspace01(Ni, bins.device), 0
+    else:
+        u, u_ld = _cuda_f32(u, "u"), Ni
+    out = torch.empty((n, Ni), dtype=torch.float32, device=bins.device)
+    check(lib().pcnerf_sample_pdf(_p(bins), _p(weights), n, nb, _p(u), u_ld, Ni, _p(out), _stream()))
+    _count()
+    return out
+
+
+def embed(x, out_ld=63):
+    x = _cuda_f32(x, "x")
+    if x.dim() != 2 or x.shape[1] != 3:
+        raise ValueError("embed: x must be (B,3)")
+    out = torch.empty((x.shape[0], out_ld), dtype=torch.float32, device=x.device)
+    check(lib().pcnerf_embed(_p(x), x.shape[0], _p(out), out_ld, _stream()))
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------- K3 MLP
+
+_SCRATCH = {}
+
+
+def _scratch(rows, precision, device):
+    need = lib().pcnerf_mlp_scratch_bytes(rows, precision)
+    key = (str(device), precision)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf
+
+
+def _mlp_params(tensors, buffers, training, precision, momentum=0.1, eps=1e-5):
+    """tensors: 34 parameter tensors in mlp_param_order; buffers: (running_mean[8], running_var[8], nbt[8])."""
+    P = MlpParams()
+    for l in range(9):
+        P.W[l] = tensors[2 * l].data_ptr()
+        P.b[l] = tensors[2 * l + 1].data_ptr()
+    for l in range(8):
+        P.gamma[l] = tensors[18 + 2 * l].data_ptr()
+        P.beta[l] = tensors[19 + 2 * l].data_ptr()
+        P.running_mean[l] = buffers[0][l].data_ptr()
+        P.running_var[l] = buffers[1][l].data_ptr()
+        P.num_batches_tracked[l] = buffers[2][l].data_ptr()
+    P.momentum, P.eps, P.training, P.precision = momentum, eps, int(training), int(precision)
+    return P
+
+
+GRAD_SIZES = [256 * 63, 256] + [256 * 256, 256] * 3 + [256 * 319, 256] + [256 * 256, 256] * 3 + [256, 1] + [256, 256] * 8
+
+
+class MLPFunction(torch.autograd.Function):
+    """p = NOF(enc) evaluated chunk by chunk (one BN batch per chunk, nof/render.py:47-49)."""
+
+    @staticmethod
+    def forward(ctx, enc, chunk, training, precision, buffers, *params):
+        rows = enc.shape[0]
+        dev = enc.device
+        P = _mlp_params(params, buffers, training, precision)
+        out = torch.empty(rows, dtype=torch.float32, device=dev)
+        need_grad = training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        saved = []
+        scratch = _scratch(min(chunk, rows), precision, dev)
+        shared = None
+        esz = 2 if precision == 1 else 4
+        for i in range(0, rows, chunk):
+            r = min(chunk, rows - i)
+            nbytes = lib().pcnerf_mlp_saved_bytes(r, precision)
+            if need_grad:
+                sv = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                saved.append(sv)
+            else:
+                if shared is None or shared.numel() < nbytes:
+                    shared = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                sv = shared
+            check(lib().pcnerf_mlp_forward(ctypes.byref(P), ctypes.c_void_p(enc.data_ptr() + i * 64 * esz), r,
+                                           ctypes.c_void_p(out.data_ptr() + i * 4), _p(sv), sv.numel(), _p(scratch),
+                                           scratch.numel(), _stream()))
+            _count(18)
+        ctx.saved_chunks = saved
+        ctx.meta = (chunk, precision, buffers, rows)
+        ctx.save_for_backward(enc, out, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gp):
+        chunk, precision, buffers, rows = ctx.meta
+        enc, out, *params = ctx.saved_tensors
+        dev = enc.device
+        gp = gp.contiguous()
+        P = _mlp_params(params, buffers, True, precision)
+        flat = torch.zeros(sum(GRAD_SIZES), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for sz_, p in zip(GRAD_SIZES, params):
+            views.append(flat[o:o + sz_].view_as(p))
+            o += sz_
+        G = MlpGrads()
+        for l in range(9):
+            G.dW[l] = views[2 * l].data_ptr()
+            G.db[l] = views[2 * l + 1].data_ptr()
+        for l in range(8):
+            G.dgamma[l] = views[18 + 2 * l].data_ptr()
+            G.dbeta[l] = views[19 + 2 * l].data_ptr()
+        scratch = _scratch(min(chunk, rows), precision, dev)
+        esz = 2 if precision == 1 else 4
+        for ci_, i in enumerate(range(0, rows, chunk)):
+            r = min(chunk, rows - i)
+            sv = ctx.saved_chunks[ci_]
+            check(lib().pcnerf_mlp_backward(ctypes.byref(P), ctypes.byref(G), ctypes.c_void_p(enc.data_ptr() + i * 64 * esz),
+                                            r, ctypes.c_void_p(out.data_ptr() + i * 4),
+                                            ctypes.c_void_p(gp.data_ptr() + i * 4), _p(sv), sv.numel(), _p(scratch),
+                                            scratch.numel(), _stream()))
+            _count(45)
+        ctx.saved_chunks = None
+        return (None, None, None, None, None) + tuple(views)
+
+
+# -------------------------------------------------------------------------------------------- K4 composite + losses
+
+
+class CompositeFunction(torch.autograd.Function):
+    """(w, depth, child_free_loss, child_depth_loss, free_r, sl1_r, opacity) = composite(p, z, rays)."""
+
+    @staticmethod
+    def forward(ctx, p, z, rays, cols, noise, noise_std, epsilon, flags, want_per_ray=False):
+        p = _cuda_f32(p, "p")
+        z = _cuda_f32(z, "z")
+        n, P_ = z.shape
+        dev = z.device
+        child = bool(flags & COMP_CHILD_LOSS)
+        if rays is not None:
+            rays = _cuda_f32(rays, "rays")
+        ld = rays.shape[1] if rays is not None else 0
+        cn, cf, rc = cols
+        w = torch.empty((n, P_), dtype=torch.float32, device=dev)
+        depth = torch.empty(n, dtype=torch.float32, device=dev)
+        per_ray = torch.empty((n, 8), dtype=torch.float32, device=dev) if child else None
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        if noise is not None:
+            noise = _cuda_f32(noise, "noise")
+        check(lib().pcnerf_composite_fwd(_p(p), _p(z), _p(rays), ld, n, P_, cn, cf, rc, _p(noise), float(noise_std),
+                                         float(epsilon), int(flags), _p(w), _p(depth), _p(per_ray), _p(sums), _stream()))
+        _count()
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        if child and n > 0:
+            check(lib().pcnerf_composite_losses(_p(sums), n, _p(losses), _stream()))
+            _count()
+        if flags & COMP_OPACITY:
+            opacity = (sums[2] / max(n * P_, 1)).to(torch.float32)
+        else:
+            opacity = torch.zeros((), dtype=torch.float32, device=dev)
+        ctx.save_for_backward(p, z, w, rays, per_ray)
+        ctx.meta = (rc, float(noise_std), float(epsilon), int(flags), n, P_, ld)
+        ctx.set_materialize_grads(False)
+        free_r = per_ray[:, 0].contiguous() if (child and want_per_ray) else None
+        sl1_r = per_ray[:, 2].contiguous() if (child and want_per_ray) else None
+        ctx.mark_non_differentiable(w, opacity)
+        return w, depth, losses[0].clone(), losses[1].clone(), free_r, sl1_r, opacity
+
+    @staticmethod
+    def backward(ctx, g_w, g_depth, g_free, g_dl, g_free_r, g_sl1_r, g_op):
+        p, z, w, rays, per_ray = ctx.saved_tensors
+        rc, noise_std, epsilon, flags, n, P_, ld = ctx.meta
+        if g_w is not None or g_op is not None:
+            raise NotImplementedError("pcnerf_b200: gradients through `weights` / `opacity` outputs are not supported "
+                                      "(the reference never back-propagates through them)")
+        gp = torch.empty((n, P_), dtype=torch.float32, device=p.device)
+
+        def c(t):
+            return None if t is None else t.contiguous().to(torch.float32)
+
+        g_depth, g_free, g_dl, g_free_r, g_sl1_r = c(g_depth), c(g_free), c(g_dl), c(g_free_r), c(g_sl1_r)
+        check(lib().pcnerf_composite_bwd(_p(p), _p(z), _p(w), _p(rays), ld, n, P_, rc, noise_std, epsilon, flags,
+                                         _p(per_ray), _p(g_depth), _p(g_free), _p(g_dl), _p(g_free_r), _p(g_sl1_r), n,
+                                         _p(gp), _stream()))
+        _count()
+        return gp, None, None, None, None, None, None, None, None
+
+
+def composite(p, z, rays=None, cols=(10, 11, 14), noise=None, noise_std=0.0, epsilon=1e-10, flags=0, want_per_ray=False):
+    return CompositeFunction.apply(p, z, rays, cols, noise, noise_std, epsilon, flags, want_per_ray)
+
+
+# -------------------------------------------------------------------------------------------------------- K5 search
+
+
+def search_rows(p, z, rays, cnear_col=6, cfar_col=7, epsilon=1e-10, method=0):
+    p, z, rays = _cuda_f32(p, "p"), _cuda_f32(z, "z"), _cuda_f32(rays, "rays")
+    n, P_ = z.shape
+    dev = z.device
+    w = torch.empty((n, P_), dtype=torch.float32, device=dev)
+    depth = torch.empty(n, dtype=torch.float32, device=dev)
+    peak = torch.empty(n, dtype=torch.uint8, device=dev)
+    wsum = torch.empty(n, dtype=torch.float32, device=dev)
+    sums = torch.empty(4, dtype=torch.float64, device=dev)
+    check(lib().pcnerf_search_rows(_p(p), _p(z), _p(rays), rays.shape[1], n, P_, cnear_col, cfar_col, float(epsilon),
+                                   int(method), _p(w), _p(depth), _p(peak), _p(wsum), _p(sums), _stream()))
+    _count()
+    opacity = (sums[0] / max(n * P_, 1)).to(torch.float32)
+    return depth, w, opacity, peak, wsum
+
+
+def search_select(other, peak, wsum):
+    other = other.reshape(-1).to(torch.int64).contiguous()
+    n = other.shape[0]
+    flag = torch.empty(n, dtype=torch.uint8, device=other.device)
+    check(lib().pcnerf_search_select(_p(other), _p(peak), _p(wsum), n, _p(flag), _stream()))
+    _count(3)
+    return flag.bool().reshape(-1, 1)
+
+
+def points(rays, depth):
+    rays, depth = _cuda_f32(rays, "rays"), _cuda_f32(depth, "depth")
+    out = torch.empty((rays.shape[0], 3), dtype=torch.float32, device=rays.device)
+    check(lib().pcnerf_points(_p(rays), rays.shape[1], rays.shape[0], _p(depth), _p(out), _stream()))
+    _count()
+    return out
