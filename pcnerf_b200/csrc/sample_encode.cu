@@ -88,22 +88,24 @@ __device__ __forceinline__ void bitonic_sort(float* s, int npad, int lane) {
 __device__ __forceinline__ void inverse_cdf(const float* bins, float* cdf, const float* __restrict__ wts, int nb,
                                             const float* __restrict__ u, int Ni, int NiPad, float* zs, int lane) {
     const int nw = nb - 1;
-    float part = 0.f;
-    for (int i = lane; i < nw; i += 32) part += __fadd_rn(wts[i], 1e-5f);     // weights + 1e-5 (:373)
-    const float total = warp_sum(part);
-    // cdf = [0, cumsum(pdf)]  -- warp scan in rounds of 32
-    float carry = 0.f;
+    // torch.sum (:374) has no portable summation order (vector width dependent); the correctly rounded sum is used.
+    double part = 0.0;
+    for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(wts[i], 1e-5f);     // weights + 1e-5 (:373)
+    const float total = (float)warp_sum_d(part);
+    // cdf = [0, cumsum(pdf)] (:375-376): torch's CPU cumsum accumulates float inputs in double and rounds every
+    // prefix to float -- reproduced with a double warp scan in rounds of 32 (bit-exact against the fixtures).
+    double carry = 0.0;
     if (lane == 0) cdf[0] = 0.f;
     for (int base = 0; base < nw; base += 32) {
         const int i = base + lane;
-        float v = i < nw ? __fdiv_rn(__fadd_rn(wts[i], 1e-5f), total) : 0.f;
+        double v = i < nw ? (double)__fdiv_rn(__fadd_rn(wts[i], 1e-5f), total) : 0.0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const float t = __shfl_up_sync(FULL_MASK, v, o);
+            const double t = __shfl_up_sync(FULL_MASK, v, o);
             if (lane >= o) v += t;
         }
         v += carry;
-        if (i < nw) cdf[i + 1] = v;
+        if (i < nw) cdf[i + 1] = (float)v;
         carry = __shfl_sync(FULL_MASK, v, 31);
     }
     __syncwarp();
@@ -344,6 +346,7 @@ extern "C" int pcnerf_sample_pdf(const float* bins, const float* weights, int64_
 extern "C" int pcnerf_embed(const float* x, int64_t b, float* out, int out_ld, void* stream) {
     PCN_CHECK_ARG(b >= 0 && out_ld >= 63, "embed: out_ld must be >= 63");
     if (b == 0) return 0;
+    PCN_CHECK_ARG(x && out, "embed: null x / out");
     int64_t grid = pcn_cdiv(b, 8);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;

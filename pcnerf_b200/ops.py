@@ -289,7 +289,7 @@ class MLPFunction(torch.autograd.Function):
         dev = enc.device
         P = _mlp_params(params, buffers, training, precision)
         out = torch.empty(rows, dtype=torch.float32, device=dev)
-        need_grad = training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = training and any(ctx.needs_input_grad[5:])
         saved = []
         scratch = _scratch(min(chunk, rows), precision, dev)
         shared = None
