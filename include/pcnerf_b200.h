@@ -38,6 +38,17 @@ extern "C" {
 const char* pcnerf_last_error(void);
 int pcnerf_version(void);
 
+/* Instrumentation (no reference counterpart; used by bench.py for `gpu_launches` and the roofline figures).
+ * pcnerf_launch_count: kernels launched by this library since the last reset (always counted).
+ * pcnerf_prof_enable(1): from now on every launch is bracketed by CUDA events on its own stream, grouped in
+ * pcnerf_prof_classes() kernel classes; pcnerf_prof_read synchronises those events and returns the summed device
+ * time (ms), launches and algorithmic work (FLOPs for the MLP GEMM classes, bytes for the others) of one class. */
+long long pcnerf_launch_count(int reset);
+void pcnerf_prof_enable(int on);
+int pcnerf_prof_classes(void);
+const char* pcnerf_prof_name(int id);
+int pcnerf_prof_read(int id, double* out_ms, long long* out_launches, double* out_work);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K1  AABB stage (fp64).  Replaces the numpy / python-scalar leaf functions and the per-ray loops around them.
  * ---------------------------------------------------------------------------------------------------------- */

@@ -29,6 +29,11 @@ PD = ctypes.POINTER(f64)
 SIGNATURES = {
     "pcnerf_version": (ci, []),
     "pcnerf_last_error": (ctypes.c_char_p, []),
+    "pcnerf_launch_count": (ctypes.c_longlong, [ci]),
+    "pcnerf_prof_enable": (None, [ci]),
+    "pcnerf_prof_classes": (ci, []),
+    "pcnerf_prof_name": (ctypes.c_char_p, [ci]),
+    "pcnerf_prof_read": (ci, [ci, ctypes.POINTER(f64), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(f64)]),
     "pcnerf_aabb_far_bound": (ci, [vp, vp, i64, PD, vp, vp]),
     "pcnerf_aabb_slab": (ci, [vp, vp, i64, PD, PD, vp, vp]),
     "pcnerf_aabb_child_pairs": (ci, [ci, vp, vp, i64, vp, ci, vp, vp, vp, vp]),

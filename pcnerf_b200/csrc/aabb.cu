@@ -406,6 +406,7 @@ extern "C" int pcnerf_aabb_far_bound(const double* ray_o, const double* ray_d, i
     if (n == 0) return 0;
     Six pl;
     for (int i = 0; i < 6; ++i) pl.v[i] = h_parent[i];
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)(n * 56.0));
     k_far_bound<<<grid_for(n), AABB_THREADS, 0, (cudaStream_t)stream>>>(ray_o, ray_d, n, pl, out_t);
     PCN_LAUNCH_CHECK();
     return 0;
@@ -417,6 +418,7 @@ extern "C" int pcnerf_aabb_slab(const double* ray_o, const double* ray_d, int64_
     if (n == 0) return 0;
     Six b;
     for (int i = 0; i < 3; ++i) { b.v[i] = h_min3[i]; b.v[3 + i] = h_max3[i]; }
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)(n * 56.0));
     k_slab<<<grid_for(n), AABB_THREADS, 0, (cudaStream_t)stream>>>(ray_o, ray_d, n, b, out_t);
     PCN_LAUNCH_CHECK();
     return 0;
@@ -437,6 +439,7 @@ extern "C" int pcnerf_aabb_child_pairs(int variant, const double* ray_o, const d
         k_child_pairs<V><<<grid_for(n), AABB_THREADS, smem, st>>>(ray_o, ray_d, n, boxes, K, use_smem,    \
                                                                    out_flag, out_near, out_far);          \
     }
+    PcnScope ps(PCN_K_AABB, st, (double)n * (48.0 + 17.0 * K) + K * 48.0);
     if (variant == 429) LAUNCH_PAIRS(429) else if (variant == 606) LAUNCH_PAIRS(606) else LAUNCH_PAIRS(406)
 #undef LAUNCH_PAIRS
     PCN_LAUNCH_CHECK();
@@ -447,6 +450,7 @@ extern "C" int pcnerf_aabb_dist_to_ray(const double* ray_o, const double* ray_d,
                                        int K, double* out, void* stream) {
     PCN_CHECK_ARG(n >= 0 && K >= 0, "aabb_dist_to_ray: bad sizes");
     if (n == 0 || K == 0) return 0;
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)(n * (48.0 + 8.0 * K)));
     k_dist_to_ray<<<grid_for(n), AABB_THREADS, 0, (cudaStream_t)stream>>>(ray_o, ray_d, n, centres, K, out);
     PCN_LAUNCH_CHECK();
     return 0;
@@ -460,6 +464,7 @@ extern "C" int pcnerf_aabb_find_box(const double* centres, const double* boxes, 
     int use_smem; size_t smem;
     int rc = prep_smem(k_find_box, (size_t)K * 72, &use_smem, &smem);
     if (rc) return rc;
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)(q * 28.0 + K * 72.0));
     k_find_box<<<grid_for(q), AABB_THREADS, smem, (cudaStream_t)stream>>>(centres, boxes, K, points, q, knn, use_smem,
                                                                            out_idx);
     PCN_LAUNCH_CHECK();
@@ -479,6 +484,7 @@ extern "C" int pcnerf_aabb_pack_train(int variant, const double* ray_o, const do
     for (int i = 0; i < 6; ++i) pl.v[i] = h_parent[i];
     int use_smem; size_t smem;
     cudaStream_t st = (cudaStream_t)stream;
+    PcnScope ps(PCN_K_AABB, st, (double)n * (80.0 + 61.0) + K * 120.0);
     if (variant == 406) {
         int rc = prep_smem(k_pack_train<406>, (size_t)K * 72, &use_smem, &smem);
         if (rc) return rc;
@@ -508,6 +514,7 @@ extern "C" int pcnerf_aabb_groups_count(const double* ray_o, const double* ray_d
     int use_smem; size_t smem;
     int rc = prep_smem(k_groups_count, (size_t)K * 96, &use_smem, &smem);
     if (rc) return rc;
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)(n * 60.0 + K * 96.0));
     k_groups_count<<<grid_for(n), AABB_THREADS, smem, (cudaStream_t)stream>>>(
         ray_o, ray_d, n, boxes, boxes_larger, K, b, method, grow_step, prefilter, use_smem, out_count, out_parent_far);
     PCN_LAUNCH_CHECK();
@@ -525,6 +532,7 @@ extern "C" int pcnerf_aabb_groups_fill(const double* ray_o, const double* ray_d,
     int use_smem; size_t smem;
     int rc = prep_smem(k_groups_fill, (size_t)K * 96, &use_smem, &smem);
     if (rc) return rc;
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)(n * 230.0 + K * 96.0));
     k_groups_fill<<<grid_for(n), AABB_THREADS, smem, (cudaStream_t)stream>>>(
         ray_o, ray_d, dist, n, boxes, boxes_larger, K, method, grow_step, prefilter, use_smem, count, offset,
         parent_far, scratch, out_rays13, out_ranges, out_other);

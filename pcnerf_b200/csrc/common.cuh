@@ -38,6 +38,29 @@ void pcn_set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
+// kernel classes of the built-in profiler (pcnerf_prof_*); `work` is algorithmic FLOPs (GEMMs) or bytes (the rest)
+enum {
+    PCN_K_GEMM_FWD = 0, PCN_K_GEMM_DGRAD, PCN_K_GEMM_WGRAD, PCN_K_MLP_SMALL, PCN_K_SAMPLE_ENCODE, PCN_K_COMPOSITE_FWD,
+    PCN_K_COMPOSITE_BWD, PCN_K_AABB, PCN_K_SEARCH, PCN_K_COUNT
+};
+
+// Counts kernel launches (always) and, when pcnerf_prof_enable(1) is active, brackets them with CUDA events on the
+// launching stream.  Declare one in the scope of the launch(es) it covers.
+struct PcnScope {
+    int id;
+    cudaStream_t st;
+    cudaEvent_t a, b;
+    bool on;
+    PcnScope(int id, cudaStream_t st, double work = 0.0, int nlaunch = 1);
+    ~PcnScope();
+};
+
+#define PCN_TIMED(id, st, work, ...)       \
+    do {                                   \
+        PcnScope _ps((id), (st), (work));  \
+        __VA_ARGS__;                       \
+    } while (0)
+
 static inline int64_t pcn_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #define FULL_MASK 0xffffffffu

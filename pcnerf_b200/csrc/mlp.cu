@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(256) k_gemm(GemmArgs g) {
 template <bool AT, bool BT, int EPI>
 static void launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
     dim3 grid((unsigned)pcn_cdiv(g.M, GBM), (unsigned)(g.N / GBN), (unsigned)splits);
+    PcnScope ps(EPI == EPI_FWD ? PCN_K_GEMM_FWD : (EPI == EPI_DGRAD ? PCN_K_GEMM_DGRAD : PCN_K_GEMM_WGRAD), st,
+                2.0 * (double)g.M * (double)g.N * (double)g.K);
     k_gemm<AT, BT, EPI><<<grid, 256, 0, st>>>(g);
 }
 
@@ -423,7 +425,7 @@ extern "C" size_t pcnerf_mlp_scratch_bytes(int64_t rows, int precision) { return
 static void prep_weights(const pcnerf_mlp_params* P, const MlpLayout& L, char* scratch, cudaStream_t st) {
     PrepArgs pa;
     for (int l = 0; l < 8; ++l) { pa.W[l] = P->W[l]; pa.Wp[l] = L.Wp(scratch, l); }
-    k_prep_weights<<<dim3(64, 8), 256, 0, st>>>(pa);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_prep_weights<<<dim3(64, 8), 256, 0, st>>>(pa));
 }
 
 extern "C" int pcnerf_mlp_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, float* out_p, void* saved,
@@ -454,15 +456,15 @@ extern "C" int pcnerf_mlp_forward(const pcnerf_mlp_params* P, const void* enc, i
         g.stat0 = L.dstat(scratch, l); g.stat1 = g.stat0 + 256;
         launch_gemm<false, false, EPI_FWD>(g, 1, st);
         const bool last = l == 7;
-        k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
             l, P->training, rows, g.stat0, g.stat1, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],
             P->num_batches_tracked[l], P->momentum, P->eps, L.stats(sv, l), last ? P->W[8] : L.Wp(scratch, l + 1),
             last ? P->b[8] : P->b[l + 1], last ? L.wout_f(scratch) : L.Wf(scratch, l + 1),
-            last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1));
+            last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1)));
     }
     int64_t blocks = pcn_cdiv(rows, 8);
     if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
-    k_logit_sigmoid<<<(int)blocks, 256, 0, st>>>(L.H(sv, 7), rows, L.wout_f(scratch), L.wout_f(scratch) + 256, out_p);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_logit_sigmoid<<<(int)blocks, 256, 0, st>>>(L.H(sv, 7), rows, L.wout_f(scratch), L.wout_f(scratch) + 256, out_p));
     PCN_LAUNCH_CHECK();
     return 0;
 }
@@ -492,12 +494,12 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
     float* Gb[2] = {L.G(scratch, 0), L.G(scratch, 1)};
     const int strips = (int)pcn_cdiv(rows, STRIP);
 
-    k_out_bwd_reduce<<<strips, 256, 0, st>>>(grad_p, out_p, L.H(sv, 7), rows, gvec, acc_out);
-    k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
-                                          G->dbeta[7], coef);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<<<strips, 256, 0, st>>>(grad_p, out_p, L.H(sv, 7), rows, gvec, acc_out));
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
+                                          G->dbeta[7], coef));
     int cur = 0;
-    k_bn_bwd_apply<true><<<strips, 256, 0, st>>>(gvec, Gb[cur], L.H(sv, 7), rows, coef, L.stats(sv, 7),
-                                                 L.colsum(scratch, 7));
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_apply<true><<<strips, 256, 0, st>>>(gvec, Gb[cur], L.H(sv, 7), rows, coef, L.stats(sv, 7),
+                                                 L.colsum(scratch, 7)));
     // split-K factor for the weight-gradient GEMMs
     int splits = (int)pcn_cdiv(rows, 2048);
     if (splits > MLP_MAX_SPLITS) splits = MLP_MAX_SPLITS;
@@ -522,8 +524,8 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
                 g.C = part + (l == 4 ? 64 : 0);
                 launch_gemm<true, true, EPI_SPLITK>(g, splits, st);
             }
-            k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, splits, L.colsum(scratch, l),
-                                                   l == 0 ? nullptr : L.stats(sv, l - 1), G->dW[l], G->db[l]);
+            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, splits, L.colsum(scratch, l),
+                                                   l == 0 ? nullptr : L.stats(sv, l - 1), G->dW[l], G->db[l]));
         }
         if (l == 0) break;
         // ---- data gradient  Gy_{l-1} = DH_l . W_l[:, hidden cols], with the BN(l-1) reductions in the epilogue
@@ -535,11 +537,11 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
             g.E = L.H(sv, l - 1); g.lde = 256;
             g.stat0 = L.dstat(scratch, 9 + (l - 1)); g.stat1 = g.stat0 + 256;
             launch_gemm<false, true, EPI_DGRAD>(g, 1, st);
-            k_bn_bwd_coef<<<1, 256, 0, st>>>(g.stat0, g.stat1, rows, L.stats(sv, l - 1), G->dgamma[l - 1],
-                                             G->dbeta[l - 1], coef);
+            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_coef<<<1, 256, 0, st>>>(g.stat0, g.stat1, rows, L.stats(sv, l - 1), G->dgamma[l - 1],
+                                             G->dbeta[l - 1], coef));
             cur ^= 1;
-            k_bn_bwd_apply<false><<<strips, 256, 0, st>>>(nullptr, Gb[cur], L.H(sv, l - 1), rows, coef,
-                                                          L.stats(sv, l - 1), L.colsum(scratch, l - 1));
+            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_apply<false><<<strips, 256, 0, st>>>(nullptr, Gb[cur], L.H(sv, l - 1), rows, coef,
+                                                          L.stats(sv, l - 1), L.colsum(scratch, l - 1)));
         }
     }
     PCN_LAUNCH_CHECK();

@@ -293,6 +293,8 @@ extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n,
     int64_t grid = pcn_cdiv(n, wpb);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
+    PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
+                (double)n * (60.0 + S * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_bf16 ? 128.0 : 0.0))));
     k_sample_encode_coarse<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
         rays, ld, n, near_col, far_col, cnear_col, cfar_col, steps_a, n_a, steps_b, n_b, use_disp, perturb, U, out_z,
         out_enc, (__nv_bfloat16*)out_enc_bf16);
@@ -317,6 +319,8 @@ extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, c
     int64_t grid = pcn_cdiv(n, wpb);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
+    PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
+                (double)n * (60.0 + 8.0 * S + (S + Ni) * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_bf16 ? 128.0 : 0.0))));
     k_sample_encode_fine<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
         rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__nv_bfloat16*)out_enc_bf16);
     PCN_LAUNCH_CHECK();
@@ -338,6 +342,7 @@ extern "C" int pcnerf_sample_pdf(const float* bins, const float* weights, int64_
     int64_t grid = pcn_cdiv(n, wpb);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
+    PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream, (double)n * (8.0 * nb + 4.0 * Ni));
     k_sample_pdf<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(bins, weights, n, nb, u, u_ld, Ni, out);
     PCN_LAUNCH_CHECK();
     return 0;
@@ -350,6 +355,7 @@ extern "C" int pcnerf_embed(const float* x, int64_t b, float* out, int out_ld, v
     int64_t grid = pcn_cdiv(b, 8);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
+    PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream, (double)b * (12.0 + 4.0 * out_ld));
     k_embed<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, b, out, out_ld);
     PCN_LAUNCH_CHECK();
     return 0;

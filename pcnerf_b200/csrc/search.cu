@@ -218,6 +218,7 @@ extern "C" int pcnerf_search_rows(const float* p, const float* z, const float* r
     int64_t grid = pcn_cdiv(n, wpb);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
+    PcnScope ps(PCN_K_SEARCH, st, (double)n * (8.0 + 12.0 * P + 13.0));
     k_search_rows<<<(int)grid, wpb * 32, smem, st>>>(p, z, rays, ld, n, P, cnear_col, cfar_col, epsilon, method, gk, w,
                                                     depth, peak_in_child, wsum_child, sums);
     PCN_LAUNCH_CHECK();
@@ -231,6 +232,7 @@ extern "C" int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in
     if (n == 0) return 0;
     PCN_CUDA(cudaMemsetAsync(out_flag, 0, (size_t)n, st));
     const int g = (int)pcn_cdiv(n, 256);
+    PcnScope ps(PCN_K_SEARCH, st, (double)n * 15.0, 3);
     k_select_cover<<<g, 256, 0, st>>>(other, n, out_flag);
     k_select_winner<<<g, 256, 0, st>>>(other, peak_in_child, wsum_child, n, out_flag);
     k_select_clear<<<g, 256, 0, st>>>(n, out_flag);
@@ -241,6 +243,7 @@ extern "C" int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in
 extern "C" int pcnerf_points(const float* rays, int ld, int64_t n, const float* depth, float* out_xyz, void* stream) {
     PCN_CHECK_ARG(n >= 0 && ld >= 6, "points: bad arguments");
     if (n == 0) return 0;
+    PcnScope ps(PCN_K_SEARCH, (cudaStream_t)stream, (double)n * 40.0);
     k_points<<<(int)pcn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(rays, ld, n, depth, out_xyz);
     PCN_LAUNCH_CHECK();
     return 0;

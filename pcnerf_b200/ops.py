@@ -14,11 +14,28 @@ from ._lib import MlpGrads, MlpParams, check, lib
 COMP_CHILD_LOSS, COMP_OPACITY = 1, 2
 _f64p = ctypes.POINTER(ctypes.c_double)
 
-LAUNCHES = {"count": 0}          # number of C-ABI compute calls (each enqueues >= 1 kernel); bench reports it
+def launch_count(reset=False):
+    """Kernels launched by libpcnerf_b200.so since the last reset (counted inside the library at every launch site)."""
+    return int(lib().pcnerf_launch_count(1 if reset else 0))
+
+
+def profile(enable):
+    """Switch the library's per-kernel-class CUDA-event timers on (resetting them) or off."""
+    lib().pcnerf_prof_enable(1 if enable else 0)
+
+
+def profile_read():
+    """{class name: (device ms, launches, algorithmic work)} for every kernel class (synchronises the events)."""
+    out = {}
+    for i in range(lib().pcnerf_prof_classes()):
+        ms, n, work = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        check(lib().pcnerf_prof_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(work)))
+        out[lib().pcnerf_prof_name(i).decode()] = (ms.value, n.value, work.value)
+    return out
 
 
 def _count(n=1):
-    LAUNCHES["count"] += n
+    pass
 
 
 def _p(t):
