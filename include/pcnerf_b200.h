@@ -109,17 +109,17 @@ int pcnerf_aabb_groups_fill(const double* ray_o, const double* ray_d, const doub
  *   steps_a (n_a) = torch.linspace(0,1,n_a) for the parent segment, steps_b (n_b) for the child segment
  *   (n_b == 0 -> uniform sampling).  S = n_a + n_b.
  *   U (n,S) = pre-drawn uniform numbers or NULL (perturb == 0).
- *   out_z (n,S); out_enc (n*S, 64) f32 or NULL; out_enc_bf16 (n*S,64) bf16 or NULL. */
+ *   out_z (n,S); out_enc (n*S, 64) f32 or NULL; out_enc_f16 (n*S,64) fp16 or NULL (the tensor-core MLP's operand). */
 int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n, int near_col, int far_col, int cnear_col,
                                 int cfar_col, const float* steps_a, int n_a, const float* steps_b, int n_b,
                                 int use_disp, float perturb, const float* U, float* out_z, float* out_enc,
-                                void* out_enc_bf16, void* stream);
+                                void* out_enc_f16, void* stream);
 
 /* sample_pdf + merge (nof/render.py:371-412, :463-468) fused with the encoding of the merged samples.
  *   z (n,S), w (n,S) coarse depths / weights; u: (Ni) shared (u_ld == 0, det) or (n,Ni) (u_ld == Ni).
  *   out_z (n, S+Ni) ascending. */
 int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, const float* z, const float* w, int S,
-                              const float* u, int u_ld, int Ni, float* out_z, float* out_enc, void* out_enc_bf16,
+                              const float* u, int u_ld, int Ni, float* out_z, float* out_enc, void* out_enc_f16,
                               void* stream);
 
 /* sample_pdf alone (nof/render.py:371-412): bins (n,nb), weights (n,nb-1), u as above -> out (n,Ni), unsorted. */
@@ -147,7 +147,8 @@ typedef struct pcnerf_mlp_params {
     float momentum;                     /* 0.1 */
     float eps;                          /* 1e-5 */
     int training;                       /* 1: batch statistics of this chunk; 0: running statistics */
-    int precision;                      /* 0: fp32 CUDA-core GEMM (1e-5 gate); 1: bf16 tcgen05 GEMM (1e-3 gate) */
+    int precision;                      /* 0: fp32 CUDA-core GEMM (1e-5 gate); 1: tcgen05 GEMM, fp16 operands forward /
+                                           bf16 gradients, fp32 accumulation (1e-3 gate) */
 } pcnerf_mlp_params;
 
 typedef struct pcnerf_mlp_grads {       /* accumulated (+=) by pcnerf_mlp_backward */
@@ -162,7 +163,7 @@ typedef struct pcnerf_mlp_grads {       /* accumulated (+=) by pcnerf_mlp_backwa
 size_t pcnerf_mlp_saved_bytes(int64_t rows, int precision);
 size_t pcnerf_mlp_scratch_bytes(int64_t rows, int precision);
 
-/* One BN batch (= one `chunk` of nof/render.py:47-49).  enc (rows,64) f32 (precision 0) or bf16 (precision 1).
+/* One BN batch (= one `chunk` of nof/render.py:47-49).  enc (rows,64) f32 (precision 0) or fp16 (precision 1).
  * out_p (rows) = sigmoid(logit).  `saved` receives the pre-BN activations and the batch statistics. */
 int pcnerf_mlp_forward(const pcnerf_mlp_params* h_params, const void* enc, int64_t rows, float* out_p,
                        void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
@@ -172,6 +173,19 @@ int pcnerf_mlp_forward(const pcnerf_mlp_params* h_params, const void* enc, int64
 int pcnerf_mlp_backward(const pcnerf_mlp_params* h_params, const pcnerf_mlp_grads* h_grads, const void* enc,
                         int64_t rows, const float* out_p, const float* grad_p, void* saved, size_t saved_bytes,
                         void* scratch, size_t scratch_bytes, void* stream);
+
+/* Building blocks of the precision-1 path (TMA + tcgen05 + TMEM), exported for unit tests and reuse.
+ * pcnerf_tc_rowgemm: out[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T.  mode 0: A, B, out fp16, + bias[256],
+ *   stats (2,256) f64 = column sums of out and out^2 (zeroed by the call).  mode 1: A, B, out bf16, no bias,
+ *   stats = column sums of out and of out*E with E (rows,256) fp16.  k0, k1 multiples of 64, k0 + k1 <= 320.
+ * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T (bf16) * X[rows, 0:ncols] (fp16 or
+ *   bf16, row stride ldx); ncols 64 or 256; accumulated with atomics (zero `out` first).
+ * pcnerf_tc_last_fault: non-zero if a tensor-core kernel aborted on a pipeline time-out (diagnostic). */
+int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B, const float* bias,
+                      const void* E, int64_t rows, void* out, double* stats, void* stream);
+int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows, float* out, int ldo,
+                    int col_off, void* stream);
+int pcnerf_tc_last_fault(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K4  compositing + losses (nof/render.py:51-61, :75-161, :13-36, :166-226; train_kitti.py:145-146).

@@ -187,218 +187,7 @@ static void launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
     k_gemm<AT, BT, EPI><<<grid, 256, 0, st>>>(g);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// small kernels
-// ---------------------------------------------------------------------------------------------------------------
-
-struct PrepArgs {
-    const float* W[8];
-    float* Wp[8];
-};
-
-// Padded copies of the hidden Linear weights: layer 0 -> [256,64] (col 63 = 0); layer 4 -> [256,320]
-// ([0,63) encoding cols, col 63 = 0, [64,320) hidden cols); others [256,256].
-__global__ void k_prep_weights(PrepArgs a) {
-    const int l = blockIdx.y;
-    const int kin = mlp_kin(l), kpad = mlp_kpad(l);
-    const int total = 256 * kpad;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int o = idx / kpad, c = idx - o * kpad;
-        float v = 0.f;
-        if (l == 0) { if (c < 63) v = a.W[0][o * kin + c]; }
-        else if (l == 4) { if (c < 63) v = a.W[4][o * kin + c]; else if (c >= 64) v = a.W[4][o * kin + c - 1]; }
-        else v = a.W[l][o * kin + c];
-        a.Wp[l][idx] = v;
-    }
-}
-
-// BN(l) statistics -> (mean, invstd, a, s) and fold into layer l+1 (or the output layer when l == 7).
-// grid: 256 blocks (output feature o of the next layer) x 256 threads (hidden input feature i); l == 7: 1 block.
-__global__ void __launch_bounds__(256) k_bn_fold(int l, int training, int64_t rows, const double* __restrict__ sum,
-                                                 const double* __restrict__ sumsq, const float* __restrict__ gamma,
-                                                 const float* __restrict__ beta, float* __restrict__ running_mean,
-                                                 float* __restrict__ running_var, int64_t* __restrict__ nbt,
-                                                 float momentum, float eps, float* __restrict__ stats /* [4][256] */,
-                                                 const float* __restrict__ Wp_next, const float* __restrict__ b_next,
-                                                 float* __restrict__ Wf_next, float* __restrict__ bf_next) {
-    __shared__ float red[8];
-    const int i = threadIdx.x, o = blockIdx.x;
-    float mean, var;
-    if (training) {
-        const double m = sum[i] / (double)rows;
-        double v = sumsq[i] / (double)rows - m * m;
-        if (v < 0) v = 0;
-        mean = (float)m;
-        var = (float)v;
-    } else {
-        mean = running_mean[i];
-        var = running_var[i];
-    }
-    const float invstd = 1.f / sqrtf(var + eps);
-    const float a = gamma[i] * invstd;
-    const float s = beta[i] - mean * a;
-    if (o == 0) {
-        stats[i] = mean; stats[256 + i] = invstd; stats[512 + i] = a; stats[768 + i] = s;
-        if (training) {
-            const float unbiased = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
-            running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * mean;
-            running_var[i] = (1.f - momentum) * running_var[i] + momentum * unbiased;
-            if (i == 0 && nbt) *nbt += 1;
-        }
-    }
-    const int nl = l + 1;
-    float part;
-    if (nl < 8) {
-        const int kpad = mlp_kpad(nl), off = nl == 4 ? 64 : 0;
-        const float w = Wp_next[o * kpad + off + i];
-        Wf_next[o * kpad + off + i] = w * a;
-        if (nl == 4 && i < 64) Wf_next[o * kpad + i] = Wp_next[o * kpad + i];
-        part = w * s;
-    } else {
-        const float w = Wp_next[i];            // occ_out weight (1,256)
-        Wf_next[i] = w * a;
-        part = w * s;
-    }
-    part = warp_sum(part);
-    if ((i & 31) == 0) red[i >> 5] = part;
-    __syncthreads();
-    if (i == 0) {
-        float t = 0;
-        for (int k = 0; k < 8; ++k) t += red[k];
-        bf_next[o] = b_next[o] + t;
-    }
-}
-
-// p = sigmoid(h8 . wout_f + bout_f): one warp per row
-__global__ void k_logit_sigmoid(const float* __restrict__ H, int64_t rows, const float* __restrict__ wf,
-                                const float* __restrict__ bf, float* __restrict__ out_p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float wv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wv[j] = wf[lane * 8 + j];
-    const float b = bf[0];
-    for (int64_t r = warp; r < rows; r += nw) {
-        const float4 h0 = *reinterpret_cast<const float4*>(H + r * 256 + lane * 8);
-        const float4 h1 = *reinterpret_cast<const float4*>(H + r * 256 + lane * 8 + 4);
-        float t = h0.x * wv[0] + h0.y * wv[1] + h0.z * wv[2] + h0.w * wv[3] + h1.x * wv[4] + h1.y * wv[5] +
-                  h1.z * wv[6] + h1.w * wv[7];
-        t = warp_sum(t);
-        if (lane == 0) out_p[r] = 1.f / (1.f + expf(-(t + b)));
-    }
-}
-
-#define STRIP 64
-
-// g = dL/dp * p(1-p);  acc[j] += sum_r g_r H8[r,j];  acc[256] += sum_r g_r
-__global__ void __launch_bounds__(256) k_out_bwd_reduce(const float* __restrict__ grad_p, const float* __restrict__ p,
-                                                        const float* __restrict__ H, int64_t rows,
-                                                        float* __restrict__ gvec, double* __restrict__ acc) {
-    const int j = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * STRIP;
-    float a = 0.f, sg = 0.f;
-    for (int k = 0; k < STRIP; ++k) {
-        const int64_t r = r0 + k;
-        if (r >= rows) break;
-        const float pv = p[r];
-        const float gr = grad_p[r] * pv * (1.f - pv);
-        a = fmaf(gr, H[r * 256 + j], a);
-        sg += gr;
-        if (j == 0) gvec[r] = gr;
-    }
-    atomicAdd(acc + j, (double)a);
-    if (j == 0) atomicAdd(acc + 256, (double)sg);
-}
-
-// Output-layer parameter grads, BN(7) grads and the coefficient vectors of
-//   DH8[r,j] = g_r*u[j] - c1[j] - (H8[r,j] - mean[j])*c2[j]
-__global__ void __launch_bounds__(256) k_out_bwd_finalize(const double* __restrict__ acc, int64_t rows,
-                                                          const float* __restrict__ w_out,
-                                                          const float* __restrict__ stats, float* __restrict__ dw_out,
-                                                          float* __restrict__ db_out, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta, float* __restrict__ coef) {
-    const int j = threadIdx.x;
-    const float q = (float)acc[j], sg = (float)acc[256];
-    const float mean = stats[j], invstd = stats[256 + j], a = stats[512 + j], s = stats[768 + j];
-    const float w = w_out[j];
-    dw_out[j] += a * q + s * sg;
-    if (j == 0) db_out[0] += sg;
-    const float db = w * sg;
-    const float dg = w * invstd * (q - mean * sg);
-    dgamma[j] += dg;
-    dbeta[j] += db;
-    const float B = (float)rows;
-    coef[j] = a * w;                       // u
-    coef[256 + j] = a * db / B;            // c1
-    coef[512 + j] = a * invstd * dg / B;   // c2
-}
-
-// LAST: DH = g (x) u - c1 - (H - mean) c2     (Gy never materialised for the last BN)
-// else: DH = Gy*a - c1 - (H - mean) c2        in place on Gy
-// plus column sums of DH (the Linear bias gradient; zero in exact arithmetic)
-template <bool LAST>
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ gvec, float* __restrict__ G,
-                                                      const float* __restrict__ H, int64_t rows,
-                                                      const float* __restrict__ coef, const float* __restrict__ stats,
-                                                      double* __restrict__ colsum) {
-    const int j = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * STRIP;
-    const float c0 = coef[j], c1 = coef[256 + j], c2 = coef[512 + j], mean = stats[j];
-    float cs = 0.f;
-    for (int k = 0; k < STRIP; ++k) {
-        const int64_t r = r0 + k;
-        if (r >= rows) break;
-        const float up = LAST ? gvec[r] : G[r * 256 + j];
-        const float dh = up * c0 - c1 - (H[r * 256 + j] - mean) * c2;
-        G[r * 256 + j] = dh;
-        cs += dh;
-    }
-    atomicAdd(colsum + j, (double)cs);
-}
-
-// BN(l) backward coefficients from the dgrad epilogue sums: st0 = sum Gy, st1 = sum Gy*H
-__global__ void __launch_bounds__(256) k_bn_bwd_coef(const double* __restrict__ st0, const double* __restrict__ st1,
-                                                     int64_t rows, const float* __restrict__ stats,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     float* __restrict__ coef) {
-    const int j = threadIdx.x;
-    const float mean = stats[j], invstd = stats[256 + j], a = stats[512 + j];
-    const float db = (float)st0[j];
-    const float dg = invstd * (float)(st1[j] - (double)mean * st0[j]);
-    dgamma[j] += dg;
-    dbeta[j] += db;
-    const float B = (float)rows;
-    coef[j] = a;
-    coef[256 + j] = a * db / B;
-    coef[512 + j] = a * invstd * dg / B;
-}
-
-// dW_l[o, real col] += (sum_splits partial[o, c]) * a_prev[c] + dbias[o] * s_prev[c];  db_l[o] += dbias[o]
-// partial is [splits][256][kpad].  prev_stats == NULL for encoding columns (a = 1, s = 0).
-__global__ void k_wgrad_finalize(int l, const float* __restrict__ partial, int splits,
-                                 const double* __restrict__ colsum, const float* __restrict__ prev_stats,
-                                 float* __restrict__ dW, float* __restrict__ db) {
-    const int kin = mlp_kin(l), kpad = mlp_kpad(l);
-    const int total = 256 * kpad;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int o = idx / kpad, c = idx - o * kpad;
-        int real = c, hid = c;
-        bool is_hidden = true;
-        if (l == 0) { is_hidden = false; if (c >= 63) continue; }
-        else if (l == 4) {
-            if (c < 64) { is_hidden = false; if (c == 63) continue; }
-            else { real = c - 1; hid = c - 64; }
-        }
-        double t = 0;
-        for (int s = 0; s < splits; ++s) t += (double)partial[(size_t)s * total + idx];
-        float v = (float)t;
-        const float dbias = (float)colsum[o];
-        if (is_hidden) v = v * prev_stats[512 + hid] + dbias * prev_stats[768 + hid];
-        dW[o * kin + real] += v;
-        if (c == 0) db[o] += dbias;
-    }
-}
+#include "mlp_small.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // host orchestration
@@ -460,11 +249,11 @@ extern "C" int pcnerf_mlp_forward(const pcnerf_mlp_params* P, const void* enc, i
             l, P->training, rows, g.stat0, g.stat1, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],
             P->num_batches_tracked[l], P->momentum, P->eps, L.stats(sv, l), last ? P->W[8] : L.Wp(scratch, l + 1),
             last ? P->b[8] : P->b[l + 1], last ? L.wout_f(scratch) : L.Wf(scratch, l + 1),
-            last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1)));
+            last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1), nullptr));
     }
     int64_t blocks = pcn_cdiv(rows, 8);
     if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
-    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_logit_sigmoid<<<(int)blocks, 256, 0, st>>>(L.H(sv, 7), rows, L.wout_f(scratch), L.wout_f(scratch) + 256, out_p));
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_logit_sigmoid<float><<<(int)blocks, 256, 0, st>>>(L.H(sv, 7), rows, L.wout_f(scratch), L.wout_f(scratch) + 256, out_p));
     PCN_LAUNCH_CHECK();
     return 0;
 }
@@ -494,11 +283,11 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
     float* Gb[2] = {L.G(scratch, 0), L.G(scratch, 1)};
     const int strips = (int)pcn_cdiv(rows, STRIP);
 
-    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<<<strips, 256, 0, st>>>(grad_p, out_p, L.H(sv, 7), rows, gvec, acc_out));
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<float><<<strips, 256, 0, st>>>(grad_p, out_p, L.H(sv, 7), rows, gvec, acc_out));
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
                                           G->dbeta[7], coef));
     int cur = 0;
-    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_apply<true><<<strips, 256, 0, st>>>(gvec, Gb[cur], L.H(sv, 7), rows, coef, L.stats(sv, 7),
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_apply<true, float, float><<<strips, 256, 0, st>>>(gvec, Gb[cur], L.H(sv, 7), rows, coef, L.stats(sv, 7),
                                                  L.colsum(scratch, 7)));
     // split-K factor for the weight-gradient GEMMs
     int splits = (int)pcn_cdiv(rows, 2048);
@@ -540,7 +329,7 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
             PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_coef<<<1, 256, 0, st>>>(g.stat0, g.stat1, rows, L.stats(sv, l - 1), G->dgamma[l - 1],
                                              G->dbeta[l - 1], coef));
             cur ^= 1;
-            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_apply<false><<<strips, 256, 0, st>>>(nullptr, Gb[cur], L.H(sv, l - 1), rows, coef,
+            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_bn_bwd_apply<false, float, float><<<strips, 256, 0, st>>>(nullptr, Gb[cur], L.H(sv, l - 1), rows, coef,
                                                           L.stats(sv, l - 1), L.colsum(scratch, l - 1)));
         }
     }

@@ -1,13 +1,693 @@
-// K3 (bf16 tensor-core path) -- placeholder until the tcgen05 kernels land.
+// K3 (tensor-core path, precision 1): the occupancy MLP of nof/networks/models.py:125-203 on tcgen05 / TMEM / TMA.
+//
+// Same algebra as mlp.cu (BN(l) folded into Linear(l+1), batch statistics from the GEMM epilogue), different engine:
+//   * every Linear is one persistent, warp-specialised kernel: warp 0 issues TMA loads (SWIZZLE_128B tiles), warp 1
+//     issues tcgen05.mma (kind::f16, M=128 x N=256 x K=16 per instruction, fp32 accumulators in TMEM, two 256-column
+//     accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1), warps 2..9 are the epilogue
+//     (tcgen05.ld -> bias -> 16-bit store -> per-column batch statistics by a shuffle transpose-reduce);
+//   * the layer's weights (256 x K, up to 160 KB) stay resident in shared memory for the life of the CTA, only
+//     the activations stream through a 3-4 stage ring;
+//   * weight gradients are a split-K GEMM over the rows with both operands MN-major (read straight from the row-major
+//     activation / gradient matrices), 256x256 fp32 accumulators = all 512 TMEM columns, reduced with vector atomics.
+// Number formats (DESIGN.md "precision"): forward operands fp16 (10-bit mantissa: bf16 storage misses the 1e-3 depth
+// gate, measured 3-5e-3), gradients bf16 (range), accumulation and statistics fp32 / fp64.
 #include "common.cuh"
 #include "mlp_layout.h"
+#include "mlp_small.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
-int mlp_tc_forward(const pcnerf_mlp_params*, const void*, int64_t, float*, void*, size_t, void*, size_t, cudaStream_t) {
-    pcn_set_error("mlp: precision 1 (bf16 tcgen05) is not built yet");
-    return PCNERF_ERR_UNSUPPORTED;
+#define TC_THREADS 320           // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: epilogue
+#define TC_A_BYTES (128 * 128)   // one A k-block: 128 rows x 64 x 2 B
+#define TC_B_BYTES (256 * 128)   // one B k-block: 256 rows x 64 x 2 B
+#define TC_WG_STAGE (64 * 1024)  // wgrad stage: A 4 boxes (32 KB) + B up to 4 boxes (32 KB)
+#define TC_TIMEOUT_CYCLES 6000000000LL
+
+__device__ int g_tc_err;         // set (before a trap) when a pipeline wait times out: a bug, never a valid state
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int mlp_tc_backward(const pcnerf_mlp_params*, const pcnerf_mlp_grads*, const void*, int64_t, const float*, const float*,
-                    void*, size_t, void*, size_t, cudaStream_t) {
-    pcn_set_error("mlp: precision 1 (bf16 tcgen05) is not built yet");
-    return PCNERF_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
+            atomicExch(&g_tc_err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (quadrant*32 + t), registers = columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (Blackwell).
+//   K-major operand  (rows of 128 B = 64 elements along K): LBO unused (1), SBO = 1024 B between 8-row groups.
+//   MN-major operand (rows of 128 B = 64 elements along M/N, one row per k): LBO = bytes between 64-element M/N
+//   blocks, SBO = 1024 B between groups of 8 k.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor for kind::f16: D = fp32; formats 0 = f16, 1 = bf16; major 0 = K, 1 = MN
+__host__ __device__ constexpr uint32_t make_idesc(int afmt, int bfmt, int amaj, int bmaj, int M, int N) {
+    return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)amaj << 15) | ((uint32_t)bmaj << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// lane L ends up with the sum over the warp of v[L] (31 shuffles for 32 columns)
+__device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float a = v[i], b = v[i + off];
+            const float send = up ? a : b;
+            const float keep = up ? b : a;
+            v[i] = keep + __shfl_xor_sync(FULL_MASK, send, off);
+        }
+    }
+    return v[0];
+}
+
+enum { TC_FWD = 0, TC_DGRAD = 1 };
+
+struct RowGemmArgs {
+    int rows;
+    int kb0, kb_total;          // 64-wide k-blocks taken from A0 / in total (A1 supplies the rest)
+    int nstage;
+    void* out;                  // [rows][256], fp16 (FWD) or bf16 (DGRAD)
+    const float* bias;          // FWD: [256]
+    const __half* E;            // DGRAD: H_{l-1} [rows][256]; second statistic is sum_r C[r,n] * E[r,n]
+    double* stat0;
+    double* stat1;              // [256] each, accumulated atomically
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// C[rows,256] = A[rows,K] * B[256,K]^T     (A, B K-major; FWD: fp16 x fp16 -> fp16; DGRAD: bf16 x bf16 -> bf16)
+// ---------------------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmB, const RowGemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nstage = g.nstage, KB = g.kb_total;
+    uint8_t* sB = smem;                                   // KB x 32 KB, resident
+    uint8_t* sA = sB + (size_t)KB * TC_B_BYTES;           // nstage x 16 KB ring
+    uint64_t* bars = (uint64_t*)(sA + (size_t)nstage * TC_A_BYTES);
+    // bars: full[8] | empty[8] | bfull | tfull[2] | tempty[2]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
+    const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 21);
+    float* bias_s = (float*)(bars + 22);                  // 256 floats
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_bfull, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 8); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (EPI == TC_FWD) {
+        if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = g.bias[threadIdx.x - 64];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ntiles = (g.rows + 127) >> 7;
+
+    if (warp == 0) {
+        // ===== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(bar_bfull, (uint32_t)KB * TC_B_BYTES);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sB + (size_t)kb * TC_B_BYTES), &tmB, bar_bfull, kb * 64, 0);
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
+                if (lane == 0) {
+                    mbar_expect_tx(bar_full + 8 * s, TC_A_BYTES);
+                    if (kb < g.kb0) tma_load_2d(smem_u32(sA + (size_t)s * TC_A_BYTES), &tmA0, bar_full + 8 * s, kb * 64, tile * 128);
+                    else tma_load_2d(smem_u32(sA + (size_t)s * TC_A_BYTES), &tmA1, bar_full + 8 * s, (kb - g.kb0) * 64, tile * 128);
+                }
+                __syncwarp();
+                if (++s == nstage) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        constexpr uint32_t idesc = (EPI == TC_FWD) ? make_idesc(0, 0, 0, 0, 128, 256) : make_idesc(1, 1, 0, 0, 128, 256);
+        mbar_wait(bar_bfull, 0, 2);
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(bar_tempty + 8 * as, aph ^ 1, 3);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)as * 256;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bar_full + 8 * s, ph, 4);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = smem_u32(sA + (size_t)s * TC_A_BYTES), b0 = smem_u32(sB + (size_t)kb * TC_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(dcol, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                 (uint32_t)((kb | k) != 0));
+                    umma_commit(bar_empty + 8 * s);
+                    if (kb == KB - 1) umma_commit(bar_tfull + 8 * as);
+                }
+                __syncwarp();
+                if (++s == nstage) { s = 0; ph ^= 1; }
+            }
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+    } else {
+        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, column half (warp-2)/4
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        int as = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(bar_tfull + 8 * as, aph, 5);
+            tc_fence_after();
+            const int row = tile * 128 + q * 32 + lane;
+            const bool valid = row < g.rows;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = (half * 4 + c) * 32;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + col0), r);
+                float v[32], w2[32];
+                if (EPI == TC_FWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = valid ? __uint_as_float(r[j]) + bias_s[col0 + j] : 0.f;
+                        w2[j] = v[j] * v[j];
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>((__half*)g.out + (size_t)row * 256 + col0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const __half2 h2 = __floats2half2_rn(v[j4 * 8 + 2 * t], v[j4 * 8 + 2 * t + 1]);
+                                pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            dst[j4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                } else {
+                    uint4 ev[4];
+                    if (valid) {
+                        const uint4* src = reinterpret_cast<const uint4*>(g.E + (size_t)row * 256 + col0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) ev[j4] = src[j4];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const __half2* h = reinterpret_cast<const __half2*>(&ev[j4]);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 e = valid ? __half22float2(h[t]) : make_float2(0.f, 0.f);
+                            w2[j4 * 8 + 2 * t] = v[j4 * 8 + 2 * t] * e.x;
+                            w2[j4 * 8 + 2 * t + 1] = v[j4 * 8 + 2 * t + 1] * e.y;
+                        }
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)g.out + (size_t)row * 256 + col0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j4 * 8 + 2 * t], v[j4 * 8 + 2 * t + 1]);
+                                pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
+                            }
+                            dst[j4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
+                acc0[c] += (double)warp_transpose_sum(v, lane);
+                acc1[c] += (double)warp_transpose_sum(w2, lane);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = (half * 4 + c) * 32 + lane;
+            atomicAdd(g.stat0 + col, acc0[c]);
+            atomicAdd(g.stat1 + col, acc1[c]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// out[256, ldo] (+)= sum_r DH[r, 0:256]^T X[r, 0:N]      (split-K over the rows; DH bf16, X fp16, both MN-major)
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+    int rows;
+    int N;                      // 256 or 64 columns of X
+    int kb_per_cta;             // 64-row k-blocks per CTA
+    float* out;                 // [256][ldo] fp32, accumulated with vector atomics
+    int ldo, col_off;
+    int b_is_bf16;              // format of X (0 = fp16)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NST = 3;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)NST * TC_WG_STAGE);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4), bar_tfull = smem_u32(bars + 8);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+    const int nkb = (g.rows + 63) >> 6;
+    const int kb_beg = blockIdx.x * g.kb_per_cta;
+    const int kb_end = min(nkb, kb_beg + g.kb_per_cta);
+    const int N = g.N, nboxB = N >> 6;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (kb_beg < kb_end) {
+        if (warp == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = kb_beg; kb < kb_end; ++kb) {
+                mbar_wait(bar_empty + 8 * s, ph ^ 1, 11);
+                if (lane == 0) {
+                    uint8_t* st = smem + (size_t)s * TC_WG_STAGE;
+                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)(4 + nboxB) * 8192);
+                    for (int j = 0; j < 4; ++j) tma_load_2d(smem_u32(st + j * 8192), &tmA, bar_full + 8 * s, j * 64, kb * 64);
+                    for (int j = 0; j < nboxB; ++j)
+                        tma_load_2d(smem_u32(st + 32768 + j * 8192), &tmB, bar_full + 8 * s, j * 64, kb * 64);
+                }
+                __syncwarp();
+                if (++s == NST) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 1) {
+            const uint32_t idesc = make_idesc(1, g.b_is_bf16 ? 1 : 0, 1, 1, 128, N);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = kb_beg; kb < kb_end; ++kb) {
+                mbar_wait(bar_full + 8 * s, ph, 12);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = smem_u32(smem + (size_t)s * TC_WG_STAGE), b0 = a0 + 32768;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t bd = make_desc(b0 + k * 2048, 8192, 1024);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            umma_f16(tmem_base + (uint32_t)(h * N), make_desc(a0 + h * 16384 + k * 2048, 8192, 1024), bd, idesc,
+                                     (uint32_t)((kb != kb_beg) | (k != 0)));
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                    if (kb == kb_end - 1) umma_commit(bar_tfull);
+                }
+                __syncwarp();
+                if (++s == NST) { s = 0; ph ^= 1; }
+            }
+        } else {
+            const int q = warp & 3, half = (warp - 2) >> 2;
+            mbar_wait(bar_tfull, 0, 13);
+            tc_fence_after();
+            for (int h = 0; h < 2; ++h) {
+                const int m = h * 128 + q * 32 + lane;
+                for (int c = half; c < (N >> 5); c += 2) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * N + c * 32), r);
+                    float* dst = g.out + (size_t)m * g.ldo + g.col_off + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                                     "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                                     "f"(__uint_as_float(r[j + 3]))
+                                     : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 16-bit weight copies
+// ---------------------------------------------------------------------------------------------------------------
+// Wh0[256][64] = fp16(Wp0)
+__global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict__ Wh0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 256 * 64) Wh0[i] = __float2half_rn(Wp0[i]);
+}
+struct PrepTArgs {
+    const float* Wp[8];
+    __nv_bfloat16* WT[8];
+};
+// WT_l[in][out] = bf16(Wp_l[out][hidden col in]) for l = 1..7 (the B operand of the data-gradient GEMM)
+__global__ void k_tc_prep_bwd(PrepTArgs a) {
+    __shared__ float t[32][33];
+    const int l = blockIdx.z + 1;
+    const int kpad = mlp_kpad(l), off = l == 4 ? 64 : 0;
+    const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = a.Wp[l][(size_t)(o0 + r) * kpad + off + i0 + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+        a.WT[l][(size_t)(i0 + r) * 256 + o0 + threadIdx.x] = __float2bfloat16_rn(t[threadIdx.x][r]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D map over a row-major 16-bit matrix [rows][ld] exposing `cols` columns; box = box_rows x 64 columns, SWIZZLE_128B
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { pcn_set_error("cuTensorMapEncodeTiled is not available from this driver"); return PCNERF_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pcn_set_error("cuTensorMapEncodeTiled failed (%d) for [%lld][%d] ld %d", (int)r, (long long)rows, cols, ld); return PCNERF_ERR_CUDA; }
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = PCN_SM_COUNT;
+    }
+    return n;
+}
+
+// mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias);  TC_DGRAD: A bf16, B bf16 -> out bf16, E = fp16 H
+int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
+                   const float* bias, const __half* E, int64_t rows, void* out, double* stat0, double* stat1,
+                   cudaStream_t st) {
+    PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && (k0 + k1) <= 320, "tc rowgemm: K must be 64..320 in 64s");
+    CUtensorMap mA0, mA1, mB;
+    int rc = make_map(&mA0, A0, rows, k0, lda0, 128);
+    if (rc) return rc;
+    rc = k1 ? make_map(&mA1, A1, rows, k1, lda1, 128) : make_map(&mA1, A0, rows, k0, lda0, 128);
+    if (rc) return rc;
+    rc = make_map(&mB, B, 256, k0 + k1, ldb, 256);
+    if (rc) return rc;
+    RowGemmArgs g;
+    g.rows = (int)rows; g.kb0 = k0 / 64; g.kb_total = (k0 + k1) / 64;
+    g.nstage = g.kb_total >= 5 ? 3 : 4;
+    g.out = out; g.bias = bias; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
+    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 22 * 8 + 1024 + 64;
+    const int ntiles = (int)pcn_cdiv(rows, 128);
+    const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
+    if (mode == TC_FWD) {
+        PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PcnScope ps(PCN_K_GEMM_FWD, st, flops);
+        k_tc_rowgemm<TC_FWD><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB, g);
+    } else {
+        PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<TC_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PcnScope ps(PCN_K_GEMM_DGRAD, st, flops);
+        k_tc_rowgemm<TC_DGRAD><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB, g);
+    }
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, int64_t rows, float* out, int ldo,
+                 int col_off, cudaStream_t st) {
+    PCN_CHECK_ARG(N == 256 || N == 64, "tc wgrad: N must be 64 or 256");
+    CUtensorMap mA, mB;
+    int rc = make_map(&mA, DH, rows, 256, 256, 64);
+    if (rc) return rc;
+    rc = make_map(&mB, X, rows, N, ldx, 64);
+    if (rc) return rc;
+    WgradArgs g;
+    g.rows = (int)rows; g.N = N; g.out = out; g.ldo = ldo; g.col_off = col_off; g.b_is_bf16 = x_is_bf16;
+    const int nkb = (int)pcn_cdiv(rows, 64);
+    g.kb_per_cta = (int)pcn_cdiv(nkb, sm_count());
+    const int grid = (int)pcn_cdiv(nkb, g.kb_per_cta);
+    const size_t smem = 1024 + 3 * (size_t)TC_WG_STAGE + 16 * 8 + 64;
+    PCN_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PcnScope ps(PCN_K_GEMM_WGRAD, st, 2.0 * (double)rows * 256.0 * (double)N);
+    k_tc_wgrad<<<grid, TC_THREADS, smem, st>>>(mA, mB, g);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// fp32 padded weight copies (same kernel as the fp32 path; defined in mlp_small.cuh)
+static void tc_prep_weights(const pcnerf_mlp_params* P, const MlpLayout& L, char* scratch, cudaStream_t st) {
+    PrepArgs pa;
+    for (int l = 0; l < 8; ++l) { pa.W[l] = P->W[l]; pa.Wp[l] = L.Wp(scratch, l); }
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_prep_weights<<<dim3(64, 8), 256, 0, st>>>(pa));
+}
+
+// layout of the 16-bit weight area (MlpLayout::off_tc): Wh[8] fp16 [256][320] | WT[8] bf16 [256][256]
+static __half* tc_Wh(const MlpLayout& L, char* scratch, int l) { return (__half*)L.tc(scratch) + (size_t)l * 256 * 320; }
+static __nv_bfloat16* tc_WT(const MlpLayout& L, char* scratch, int l) {
+    return (__nv_bfloat16*)(L.tc(scratch) + (size_t)8 * 256 * 320 * 2) + (size_t)l * 256 * 256;
+}
+
+int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, float* out_p, void* saved, size_t,
+                   void* scratch_v, size_t, cudaStream_t st) {
+    const MlpLayout L(rows, 1);
+    char* scratch = (char*)scratch_v;
+    char* sv = (char*)saved;
+    const __half* ench = (const __half*)enc;
+    PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
+    tc_prep_weights(P, L, scratch, st);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
+    for (int l = 0; l < 8; ++l) {
+        __half* Hl = (__half*)L.Hraw(sv, l);
+        double* s0 = L.dstat(scratch, l);
+        const float* bias = l == 0 ? P->b[0] : L.bf(scratch, l);
+        int rc;
+        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hl, s0, s0 + 256, st);
+        else if (l == 4)
+            rc = launch_rowgemm(TC_FWD, ench, 64, 64, L.Hraw(sv, 3), 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hl, s0, s0 + 256, st);
+        else rc = launch_rowgemm(TC_FWD, L.Hraw(sv, l - 1), 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hl, s0, s0 + 256, st);
+        if (rc) return rc;
+        const bool last = l == 7;
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                  k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
+                      l, P->training, rows, s0, s0 + 256, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],
+                      P->num_batches_tracked[l], P->momentum, P->eps, L.stats(sv, l), last ? P->W[8] : L.Wp(scratch, l + 1),
+                      last ? P->b[8] : P->b[l + 1], last ? L.wout_f(scratch) : L.Wf(scratch, l + 1),
+                      last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1), last ? nullptr : tc_Wh(L, scratch, l + 1)));
+    }
+    int64_t blocks = pcn_cdiv(rows, 8);
+    if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+              k_logit_sigmoid<__half><<<(int)blocks, 256, 0, st>>>((const __half*)L.Hraw(sv, 7), rows, L.wout_f(scratch),
+                                                                  L.wout_f(scratch) + 256, out_p));
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const void* enc, int64_t rows,
+                    const float* out_p, const float* grad_p, void* saved, size_t, void* scratch_v, size_t,
+                    cudaStream_t st) {
+    const MlpLayout L(rows, 1);
+    char* scratch = (char*)scratch_v;
+    char* sv = (char*)saved;
+    const __half* ench = (const __half*)enc;
+    PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * L.n_dstat, st));
+    tc_prep_weights(P, L, scratch, st);
+    {
+        PrepTArgs pa;
+        for (int l = 0; l < 8; ++l) { pa.Wp[l] = L.Wp(scratch, l); pa.WT[l] = tc_WT(L, scratch, l); }
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_bwd<<<dim3(8, 8, 7), dim3(32, 8), 0, st>>>(pa));
+    }
+    double* acc_out = L.dstat(scratch, 8);
+    float* gvec = L.gvec(scratch);
+    float* coef = L.coef(scratch);
+    __nv_bfloat16* Gb[2] = {(__nv_bfloat16*)L.Graw(scratch, 0), (__nv_bfloat16*)L.Graw(scratch, 1)};
+    const int strips = (int)pcn_cdiv(rows, STRIP);
+    const __half* H7 = (const __half*)L.Hraw(sv, 7);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__half><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+              k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
+                                                    G->dbeta[7], coef));
+    int cur = 0;
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+              k_bn_bwd_apply<true, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef, L.stats(sv, 7),
+                                                                                  L.colsum(scratch, 7)));
+    float* part = L.partial(scratch);
+    for (int l = 7; l >= 0; --l) {
+        const __nv_bfloat16* DH = Gb[cur];
+        const int kpad = mlp_kpad(l);
+        PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
+        int rc = 0;
+        if (l == 0 || l == 4) rc = launch_wgrad(DH, ench, 64, 64, 0, rows, part, kpad, 0, st);
+        if (rc) return rc;
+        if (l != 0) rc = launch_wgrad(DH, L.Hraw(sv, l - 1), 256, 256, 0, rows, part, kpad, l == 4 ? 64 : 0, st);
+        if (rc) return rc;
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                  k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, 1, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
+                                                         G->dW[l], G->db[l]));
+        if (l == 0) break;
+        double* s0 = L.dstat(scratch, 9 + (l - 1));
+        rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, nullptr,
+                            (const __half*)L.Hraw(sv, l - 1), rows, Gb[cur ^ 1], s0, s0 + 256, st);
+        if (rc) return rc;
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                  k_bn_bwd_coef<<<1, 256, 0, st>>>(s0, s0 + 256, rows, L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
+        cur ^= 1;
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                  k_bn_bwd_apply<false, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(
+                      nullptr, Gb[cur], (const __half*)L.Hraw(sv, l - 1), rows, coef, L.stats(sv, l - 1), L.colsum(scratch, l - 1)));
+    }
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Building-block entry points (unit-tested against torch.matmul; also usable on their own)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B,
+                                 const float* bias, const void* E, int64_t rows, void* out, double* stats,
+                                 void* stream) {
+    PCN_CHECK_ARG(mode == 0 || mode == 1, "tc_rowgemm: mode must be 0 (fp16 forward) or 1 (bf16 data gradient)");
+    PCN_CHECK_ARG(A0 && B && out && stats && rows >= 1, "tc_rowgemm: null argument");
+    PCN_CHECK_ARG(mode == 1 || bias, "tc_rowgemm: forward mode needs a bias");
+    PCN_CHECK_ARG(mode == 0 || E, "tc_rowgemm: data-gradient mode needs E");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
+    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, bias, (const __half*)E, rows, out, stats, stats + 256, st);
+}
+
+extern "C" int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows,
+                               float* out, int ldo, int col_off, void* stream) {
+    PCN_CHECK_ARG(DH && X && out && rows >= 1, "tc_wgrad: null argument");
+    PCN_CHECK_ARG(ldo >= col_off + ncols && (ldo % 4) == 0 && (col_off % 4) == 0, "tc_wgrad: bad output window");
+    return launch_wgrad(DH, X, ldx, ncols, x_is_bf16, rows, out, ldo, col_off, (cudaStream_t)stream);
+}
+
+extern "C" int pcnerf_tc_last_fault(void) {
+    int v = 0;
+    cudaMemcpyFromSymbol(&v, g_tc_err, sizeof(int));
+    return v;
 }

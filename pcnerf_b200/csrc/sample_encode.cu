@@ -4,8 +4,9 @@
 // round-to-nearest mul/add (no FMA contraction) in the reference's operation order so that every later
 // mask decision sees bit-identical z.  The encoding of one sample is produced by 30 lanes (one sincosf each, accurate
 // range reduction: arguments reach 512*60 rad), staged in shared memory and written as one coalesced row
-// (256 B fp32 / 128 B bf16) -- the fp32 (rows,64) layout is the MLP's A operand, column 63 is zero padding.
+// (256 B fp32 / 128 B fp16) -- the fp32 (rows,64) layout is the MLP's A operand, column 63 is zero padding.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 #define SE_MAX_SMEM (200 * 1024)
 
@@ -17,7 +18,7 @@ __device__ __forceinline__ float lerp_rn(float a, float b, float s) {
 // Encode P samples of one ray (depths in shared `zs`) into rows [row0, row0+P).
 __device__ __forceinline__ void encode_ray(const float o0, const float o1, const float o2, const float d0,
                                            const float d1, const float d2, const float* zs, int P, int64_t row0,
-                                           float* __restrict__ out_enc, __nv_bfloat16* __restrict__ out_bf,
+                                           float* __restrict__ out_enc, __half* __restrict__ out_bf,
                                            float* stage, int lane) {
     const int k = lane / 3, c = lane - 3 * k;
     const float freq = (float)(1 << (k < 10 ? k : 0));
@@ -44,8 +45,8 @@ __device__ __forceinline__ void encode_ray(const float o0, const float o1, const
             out_enc[row * 64 + 32 + lane] = st[32 + lane];
         }
         if (out_bf) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(st[2 * lane], st[2 * lane + 1]);
-            reinterpret_cast<__nv_bfloat162*>(out_bf + row * 64)[lane] = v;
+            const __half2 v = __floats2half2_rn(st[2 * lane], st[2 * lane + 1]);
+            reinterpret_cast<__half2*>(out_bf + row * 64)[lane] = v;
         }
         // the other half of `stage` is used by the next iteration; one __syncwarp per sample is enough
     }
@@ -146,7 +147,7 @@ __global__ void k_sample_encode_coarse(const float* __restrict__ rays, int ld, i
                                        int cnear_col, int cfar_col, const float* __restrict__ steps_a, int n_a,
                                        const float* __restrict__ steps_b, int n_b, int use_disp, float perturb,
                                        const float* __restrict__ U, float* __restrict__ out_z,
-                                       float* __restrict__ out_enc, __nv_bfloat16* __restrict__ out_bf) {
+                                       float* __restrict__ out_enc, __half* __restrict__ out_bf) {
     extern __shared__ float smf[];
     const int S = n_a + n_b;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -202,7 +203,7 @@ __global__ void k_sample_encode_coarse(const float* __restrict__ rays, int ld, i
 __global__ void k_sample_encode_fine(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ z,
                                      const float* __restrict__ w, int S, const float* __restrict__ u, int u_ld, int Ni,
                                      int NiPad, float* __restrict__ out_z, float* __restrict__ out_enc,
-                                     __nv_bfloat16* __restrict__ out_bf) {
+                                     __half* __restrict__ out_bf) {
     extern __shared__ float smf[];
     const int F = S + Ni;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -275,7 +276,7 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n, int near_col, int far_col,
                                            int cnear_col, int cfar_col, const float* steps_a, int n_a,
                                            const float* steps_b, int n_b, int use_disp, float perturb, const float* U,
-                                           float* out_z, float* out_enc, void* out_enc_bf16, void* stream) {
+                                           float* out_z, float* out_enc, void* out_enc_f16, void* stream) {
     PCN_CHECK_ARG(n >= 0 && ld >= 8 && n_a >= 1 && n_b >= 0, "sample_encode_coarse: bad sizes");
     PCN_CHECK_ARG(steps_a && (n_b == 0 || steps_b), "sample_encode_coarse: linspace tables missing");
     PCN_CHECK_ARG(!(perturb > 0.f) || U, "sample_encode_coarse: perturb > 0 needs pre-drawn U");
@@ -294,17 +295,17 @@ extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n,
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
     PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
-                (double)n * (60.0 + S * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_bf16 ? 128.0 : 0.0))));
+                (double)n * (60.0 + S * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_f16 ? 128.0 : 0.0))));
     k_sample_encode_coarse<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
         rays, ld, n, near_col, far_col, cnear_col, cfar_col, steps_a, n_a, steps_b, n_b, use_disp, perturb, U, out_z,
-        out_enc, (__nv_bfloat16*)out_enc_bf16);
+        out_enc, (__half*)out_enc_f16);
     PCN_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, const float* z, const float* w, int S,
                                          const float* u, int u_ld, int Ni, float* out_z, float* out_enc,
-                                         void* out_enc_bf16, void* stream) {
+                                         void* out_enc_f16, void* stream) {
     PCN_CHECK_ARG(n >= 0 && ld >= 6 && S >= 3 && Ni >= 1, "sample_encode_fine: bad sizes (need S >= 3, Ni >= 1)");
     PCN_CHECK_ARG(u && (u_ld == 0 || u_ld == Ni), "sample_encode_fine: u must be (Ni) with u_ld 0 or (n,Ni) with u_ld Ni");
     if (n == 0) return 0;
@@ -320,9 +321,9 @@ extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, c
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
     PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
-                (double)n * (60.0 + 8.0 * S + (S + Ni) * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_bf16 ? 128.0 : 0.0))));
+                (double)n * (60.0 + 8.0 * S + (S + Ni) * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_f16 ? 128.0 : 0.0))));
     k_sample_encode_fine<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
-        rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__nv_bfloat16*)out_enc_bf16);
+        rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__half*)out_enc_f16);
     PCN_LAUNCH_CHECK();
     return 0;
 }

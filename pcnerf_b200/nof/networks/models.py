@@ -14,11 +14,13 @@ import torch.nn as nn
 from ... import ops
 
 _DEFAULT_PRECISION = {"value": 0}
+_PREC = {"fp32": 0, "tc": 1, "bf16": 1, "f16": 1, 0: 0, 1: 1}
 
 
 def set_default_mlp_precision(p):
-    """'fp32' (CUDA-core GEMM, 1e-5 parity gate) or 'bf16' (tcgen05 tensor-core GEMM, 1e-3 gate)."""
-    _DEFAULT_PRECISION["value"] = {"fp32": 0, "bf16": 1, 0: 0, 1: 1}[p]
+    """'fp32' (CUDA-core GEMM, 1e-5 parity gate) or 'tc' (tcgen05 tensor-core GEMM: fp16 operands forward, bf16
+    gradients, fp32 accumulation; 1e-3 gate).  'bf16' is accepted as an alias of 'tc' (BASELINE.json's name)."""
+    _DEFAULT_PRECISION["value"] = _PREC[p]
 
 
 class Embedding(nn.Module):
@@ -102,14 +104,14 @@ class NOF(nn.Module):
                 raise NotImplementedError("pcnerf_b200.NOF: negative_slope != 1 (the reference builds LeakyReLU(True))")
 
     def mlp_precision(self):
-        return _DEFAULT_PRECISION["value"] if self.precision is None else {"fp32": 0, "bf16": 1, 0: 0, 1: 1}[self.precision]
+        return _DEFAULT_PRECISION["value"] if self.precision is None else _PREC[self.precision]
 
     def forward_encoded(self, enc, chunk=None):
-        """enc: (rows, 64) encodings padded with a zero column (fp32, or bf16 for the tensor-core path).
+        """enc: (rows, 64) encodings padded with a zero column (fp32, or fp16 for the tensor-core path).
         One BN batch per `chunk` rows.  Returns p_occ (rows,)."""
         self._check_supported()
         prec = self.mlp_precision()
-        want = torch.bfloat16 if prec == 1 else torch.float32
+        want = torch.float16 if prec == 1 else torch.float32
         if enc.dtype != want:
             enc = enc.to(want)
         rows = enc.shape[0]

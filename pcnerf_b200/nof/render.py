@@ -19,7 +19,7 @@ __all__ = ['render_rays']
 RNG_ON_CPU = False      # True: draw sample_pdf's u with the CPU generator like nof/render.py:383 (slow: H2D each call)
 
 
-def _bf16(model):
+def _tc(model):
     return model.mlp_precision() == 1
 
 
@@ -42,9 +42,9 @@ def _segments(N_samples, issegmentated, childnerf_ratio):
     return n_parent, N_samples - n_parent
 
 
-def _embed_samples(samples_xy, bf16):
+def _embed_samples(samples_xy, f16):
     enc = ops.embed(samples_xy.reshape(-1, 3).contiguous(), 64)
-    return enc.to(torch.bfloat16) if bf16 else enc
+    return enc.to(torch.float16) if f16 else enc
 
 
 # ----------------------------------------------------------------------------------------------------- inference_*
@@ -55,7 +55,7 @@ def inference_val(model, embedding_xy, samples_xy, rays, z_vals, near_far_child,
                   noise=None, _enc=None):
     """nof/render.py:13-36."""
     N_rays, N_samples = z_vals.shape
-    enc = _enc if _enc is not None else _embed_samples(samples_xy, _bf16(model))
+    enc = _enc if _enc is not None else _embed_samples(samples_xy, _tc(model))
     p = model.forward_encoded(enc, chunk).view(N_rays, N_samples)
     nz = _noise(z_vals.shape, z_vals.device, noise_std, noise)
     w, depth, _, _, _, _, _ = ops.composite(p, z_vals, None, (0, 0, 0), nz, noise_std, epsilon, 0)
@@ -68,7 +68,7 @@ def inference_train(model, embedding_xy, samples_xy, rays, z_vals, near_far_chil
     """nof/render.py:38-163.  `near_far_child` / `range_readings` are read from `rays` columns 10:12 / -1 exactly as
     the reference's caller packs them (render.py:424-427)."""
     N_rays, N_samples = z_vals.shape
-    enc = _enc if _enc is not None else _embed_samples(samples_xy, _bf16(model))
+    enc = _enc if _enc is not None else _embed_samples(samples_xy, _tc(model))
     p = model.forward_encoded(enc, chunk).view(N_rays, N_samples)
     nz = _noise(z_vals.shape, z_vals.device, noise_std, noise)
     ld = rays.shape[1]
@@ -98,7 +98,7 @@ def inference(model, embedding_xy, samples_xy, z_vals, chunk=1024 * 32, noise_st
               noise=None, _enc=None):
     """nof/render.py:166-226."""
     N_rays, N_samples = z_vals.shape
-    enc = _enc if _enc is not None else _embed_samples(samples_xy, _bf16(model))
+    enc = _enc if _enc is not None else _embed_samples(samples_xy, _tc(model))
     p = model.forward_encoded(enc, chunk).view(N_rays, N_samples)
     nz = _noise(z_vals.shape, z_vals.device, noise_std, noise)
     if isval is not False:
@@ -114,7 +114,7 @@ def inference_0525_2(model, embedding_xy, samples_xy, z_vals, other_interest_sub
                      _enc=None):
     """nof/render.py:229-368."""
     N_rays, N_samples = z_vals.shape
-    enc = _enc if _enc is not None else _embed_samples(samples_xy, _bf16(model))
+    enc = _enc if _enc is not None else _embed_samples(samples_xy, _tc(model))
     p = model.forward_encoded(enc, chunk).view(N_rays, N_samples)
     nfc = near_far_child.contiguous().to(torch.float32)
     depth, w, opacity, peak, wsum = ops.search_rows(p, z_vals, nfc, 0, 1, epsilon, depth_inference_method)
@@ -135,14 +135,14 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
 
 def _two_pass(model, model_fine, rays, n_a, n_b, N_importance, use_disp, perturb, U, u, near_col, far_col, head):
     """Shared skeleton of the four render_* entry points: coarse sample+encode -> head -> resample+encode -> head."""
-    bf = _bf16(model)
-    z, enc = ops.sample_encode_coarse(rays, n_a, n_b, near_col, far_col, 10, 11, use_disp, float(perturb), U, True, bf)
+    tc = _tc(model)
+    z, enc = ops.sample_encode_coarse(rays, n_a, n_b, near_col, far_col, 10, 11, use_disp, float(perturb), U, True, tc)
     out_c = head(model, enc, z, 0)
     w = out_c["w"]
     det = (perturb == 0.)
     if not det and u is None:
         u = _draw_u(rays.shape[0], N_importance, rays.device)
-    zf, encf = ops.sample_encode_fine(rays, z, w, N_importance, u, det, True, _bf16(model_fine))
+    zf, encf = ops.sample_encode_fine(rays, z, w, N_importance, u, det, True, _tc(model_fine))
     out_f = head(model_fine, encf, zf, 1)
     return z, zf, out_c, out_f
 

@@ -189,7 +189,7 @@ def aabb_build_groups(ray_o, ray_d, dist, boxes, boxes_larger, parent_min, paren
 
 
 def sample_encode_coarse(rays, n_a, n_b=0, near_col=6, far_col=7, cnear_col=10, cfar_col=11, use_disp=False,
-                         perturb=0.0, U=None, want_enc=True, bf16=False):
+                         perturb=0.0, U=None, want_enc=True, f16=False):
     rays = _cuda_f32(rays, "rays")
     n, ld = rays.shape
     S = n_a + n_b
@@ -202,18 +202,18 @@ def sample_encode_coarse(rays, n_a, n_b=0, near_col=6, far_col=7, cnear_col=10, 
     z = torch.empty((n, S), dtype=torch.float32, device=rays.device)
     enc = enc_bf = None
     if want_enc:
-        if bf16:
-            enc_bf = torch.empty((n * S, 64), dtype=torch.bfloat16, device=rays.device)
+        if f16:
+            enc_bf = torch.empty((n * S, 64), dtype=torch.float16, device=rays.device)
         else:
             enc = torch.empty((n * S, 64), dtype=torch.float32, device=rays.device)
     check(lib().pcnerf_sample_encode_coarse(_p(rays), ld, n, near_col, far_col, cnear_col, cfar_col, _p(sa), n_a, _p(sb),
                                             n_b, int(bool(use_disp)), float(perturb), _p(U) if perturb > 0 else None,
                                             _p(z), _p(enc), _p(enc_bf), _stream()))
     _count()
-    return z, (enc_bf if bf16 else enc)
+    return z, (enc_bf if f16 else enc)
 
 
-def sample_encode_fine(rays, z, w, Ni, u=None, det=True, want_enc=True, bf16=False):
+def sample_encode_fine(rays, z, w, Ni, u=None, det=True, want_enc=True, f16=False):
     rays = _cuda_f32(rays, "rays")
     z = _cuda_f32(z, "z")
     w = _cuda_f32(w.detach(), "w")
@@ -227,14 +227,14 @@ def sample_encode_fine(rays, z, w, Ni, u=None, det=True, want_enc=True, bf16=Fal
     zf = torch.empty((n, S + Ni), dtype=torch.float32, device=rays.device)
     enc = enc_bf = None
     if want_enc:
-        if bf16:
-            enc_bf = torch.empty((n * (S + Ni), 64), dtype=torch.bfloat16, device=rays.device)
+        if f16:
+            enc_bf = torch.empty((n * (S + Ni), 64), dtype=torch.float16, device=rays.device)
         else:
             enc = torch.empty((n * (S + Ni), 64), dtype=torch.float32, device=rays.device)
     check(lib().pcnerf_sample_encode_fine(_p(rays), rays.shape[1], n, _p(z), _p(w), S, _p(u), u_ld, Ni, _p(zf), _p(enc),
                                           _p(enc_bf), _stream()))
     _count()
-    return zf, (enc_bf if bf16 else enc)
+    return zf, (enc_bf if f16 else enc)
 
 
 def sample_pdf(bins, weights, Ni, u=None, det=False):
@@ -462,4 +462,34 @@ def points(rays, depth):
     out = torch.empty((rays.shape[0], 3), dtype=torch.float32, device=rays.device)
     check(lib().pcnerf_points(_p(rays), rays.shape[1], rays.shape[0], _p(depth), _p(out), _stream()))
     _count()
+    return out
+
+
+# ------------------------------------------------------------------------------- tensor-core building blocks (tests)
+
+
+def tc_rowgemm(mode, A0, B, A1=None, bias=None, E=None):
+    """out (rows,256) = [A0 | A1] @ B.T (+ bias) on tcgen05; mode 0: fp16 in/out, mode 1: bf16 in/out with E fp16.
+    Returns (out, stats (2,256) f64)."""
+    dt = torch.float16 if mode == 0 else torch.bfloat16
+    for t in (A0, B) + ((A1,) if A1 is not None else ()):
+        if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise TypeError("tc_rowgemm: operands must be contiguous CUDA %s tensors" % dt)
+    rows, k0 = A0.shape
+    k1 = 0 if A1 is None else A1.shape[1]
+    out = torch.empty((rows, 256), dtype=dt, device=A0.device)
+    stats = torch.empty((2, 256), dtype=torch.float64, device=A0.device)
+    check(lib().pcnerf_tc_rowgemm(int(mode), _p(A0), k0, _p(A1), k1, _p(B), _p(bias), _p(E), rows, _p(out), _p(stats),
+                                  _stream()))
+    return out, stats
+
+
+def tc_wgrad(DH, X, ncols, out, col_off=0):
+    """out[256, ldo] window [col_off, col_off+ncols) += DH.T @ X[:, :ncols] on tcgen05 (DH bf16, X fp16 or bf16)."""
+    if not (DH.is_cuda and DH.dtype == torch.bfloat16 and DH.is_contiguous() and DH.shape[1] == 256):
+        raise TypeError("tc_wgrad: DH must be a contiguous CUDA bf16 (rows,256) tensor")
+    if X.dtype not in (torch.float16, torch.bfloat16) or not X.is_contiguous():
+        raise TypeError("tc_wgrad: X must be contiguous fp16 / bf16")
+    check(lib().pcnerf_tc_wgrad(_p(DH), _p(X), X.shape[1], int(ncols), int(X.dtype == torch.bfloat16), DH.shape[0], _p(out),
+                                out.shape[1], int(col_off), _stream()))
     return out

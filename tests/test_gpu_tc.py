@@ -1,0 +1,130 @@
+"""GPU: the precision-1 (TMA + tcgen05 + TMEM) path.  First the GEMM building blocks against torch.matmul on the same
+16-bit operands (fp32 accumulation on both sides: agreement to fp32 summation order), then the MLP forward/backward
+against the oracle, then the render path at the 1e-3 gate BASELINE.json states for the tensor-core MLP path."""
+import numpy as np
+import pytest
+import torch
+
+import pcnerf_oracle as orc
+from conftest import golden
+from gpu_util import dev, make_nets
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, dt, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dt).to(dev())
+
+
+@pytest.mark.parametrize("rows,k0,k1", [(128, 64, 0), (128, 256, 0), (1000, 256, 0), (4096 + 77, 64, 256), (40000, 256, 0)])
+def test_rowgemm_forward_fp16(rows, k0, k1):
+    from pcnerf_b200 import ops
+    A0 = _rand((rows, k0), torch.float16, 1)
+    A1 = _rand((rows, k1), torch.float16, 2) if k1 else None
+    B = _rand((256, k0 + k1), torch.float16, 3, 0.1)
+    bias = _rand((256,), torch.float32, 4)
+    out, stats = ops.tc_rowgemm(0, A0, B, A1, bias)
+    A = A0 if A1 is None else torch.cat([A0, A1], 1)
+    ref = A.float() @ B.float().t() + bias
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=2e-3, atol=2e-3)   # fp16 output rounding
+    np.testing.assert_allclose(stats[0].cpu().numpy(), ref.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[1].cpu().numpy(), (ref.double() ** 2).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows", [128, 300, 20000])
+def test_rowgemm_dgrad_bf16(rows):
+    from pcnerf_b200 import ops
+    A = _rand((rows, 256), torch.bfloat16, 5)
+    B = _rand((256, 256), torch.bfloat16, 6, 0.1)
+    E = _rand((rows, 256), torch.float16, 7)
+    out, stats = ops.tc_rowgemm(1, A, B, None, None, E)
+    ref = A.float() @ B.float().t()
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=1e-2)    # bf16 output rounding
+    np.testing.assert_allclose(stats[0].cpu().numpy(), ref.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[1].cpu().numpy(), (ref.double() * E.double()).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows,ncols,xdt", [(64, 256, torch.bfloat16), (64, 256, torch.float16), (1000, 256, torch.float16),
+                                            (30000, 64, torch.float16), (70000, 256, torch.float16)])
+def test_wgrad_mn_major(rows, ncols, xdt):
+    from pcnerf_b200 import ops
+    DH = _rand((rows, 256), torch.bfloat16, 8)
+    X = _rand((rows, ncols), xdt, 9)
+    out = torch.zeros((256, 320), dtype=torch.float32, device=dev())
+    ops.tc_wgrad(DH, X, ncols, out, 64 if ncols == 256 else 0)
+    ref = DH.double().t() @ X.double()
+    off = 64 if ncols == 256 else 0
+    got = out[:, off:off + ncols].double()
+    scale = float(ref.abs().max())
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+    rest = out.clone()
+    rest[:, off:off + ncols] = 0
+    assert float(rest.abs().max()) == 0.0
+
+
+def _enc(rows, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x = (torch.rand(rows, 3, generator=gen) - 0.5) * 60.0
+    return orc.embedding(x)
+
+
+@pytest.mark.parametrize("rows,chunk", [(4096, 4096), (5000, 2048), (130, 130)])
+def test_mlp_forward_tc(rows, chunk):
+    enc = _enc(rows, rows)
+    sd = orc.init_state_dict(42)
+    p_ref = torch.cat([orc.nof_forward(sd, enc[i:i + chunk], True) for i in range(0, rows, chunk)]).reshape(-1)
+    mc, _, _ = make_nets(42, 43, True, "tc")
+    p = mc.forward_encoded(torch.nn.functional.pad(enc, (0, 1)).to(dev()), chunk)
+    err = (p.detach().cpu() - p_ref).abs() / p_ref
+    assert float(err.max()) < 6e-3 and float(err.mean()) < 1e-3, (float(err.max()), float(err.mean()))
+    got = mc.state_dict()
+    for k in ("layer1.1.running_mean", "layer1.1.running_var", "layer2.7.running_mean", "layer2.7.running_var"):
+        np.testing.assert_allclose(got[k].cpu().numpy(), sd[k].numpy(), rtol=5e-3, atol=5e-3, err_msg=k)
+
+
+@pytest.mark.parametrize("rows,chunk", [(4096, 4096), (3000, 1024)])
+def test_mlp_backward_tc(rows, chunk):
+    enc = _enc(rows, rows + 1)
+    gen = torch.Generator().manual_seed(rows)
+    gp = torch.randn(rows, generator=gen)
+    sd = orc.init_state_dict(42)
+    for k in orc.param_names():
+        sd[k].requires_grad_(True)
+    p_ref = torch.cat([orc.nof_forward(sd, enc[i:i + chunk], True) for i in range(0, rows, chunk)]).reshape(-1)
+    (p_ref * gp).sum().backward()
+    mc, _, _ = make_nets(42, 43, True, "tc")
+    p = mc.forward_encoded(torch.nn.functional.pad(enc, (0, 1)).to(dev()), chunk)
+    (p * gp.to(dev())).sum().backward()
+    scale = max(float(sd[k].grad.abs().max()) for k in orc.param_names())
+    for k, prm in mc.named_parameters():
+        ref = sd[k].grad.numpy()
+        got = prm.grad.cpu().numpy()
+        # 16-bit operands: compare each tensor on its own scale (bf16 gradients: ~1 % of the tensor's max)
+        atol = 2e-2 * np.abs(ref).max() + 1e-12
+        if k.endswith(".bias") and k.split(".")[0] in ("layer1", "layer2") and k != "layer2.7.bias":
+            atol = 1e-3 * scale          # exactly zero in exact arithmetic: rounding noise of the 16-bit path
+        assert np.abs(got - ref).max() <= atol, (k, np.abs(got - ref).max(), atol)
+        if ref.size > 256:
+            cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+            assert cos > 0.999, (k, cos)
+
+
+@pytest.mark.parametrize("name", ["train_seg", "train_plain"])
+def test_train_coarse_pass_tc_gate_1e3(name):
+    """BASELINE.json: rendered depth and losses within 1e-3 relative for the tensor-core MLP path (coarse pass; the
+    fine pass inherits the resampling conditioning documented in tests/test_gpu_render.py)."""
+    from pcnerf_b200.nof import render
+    g = golden(name)
+    rays = torch.from_numpy(g["rays"]).to(dev())
+    mc, mf, emb = make_nets(42, 43, True, "tc")
+    res = render.render_rays_train(mc, mf, emb, rays, N_samples=int(g["S"]), N_importance=int(g["Ni"]), perturb=0,
+                                   noise_std=0, chunk=int(g["chunk"]), issegmentated=int(g["issegmentated"]),
+                                   childnerf_ratio=float(g["ratio"]), use_child_nerf_divide=0,
+                                   use_child_nerf_loss=int(g["use_child"]))
+    np.testing.assert_allclose(res["depth"].detach().cpu().numpy(), g["out_depth"], rtol=1e-3, atol=1e-6)
+    if int(g["use_child"]):
+        np.testing.assert_allclose(float(res["child_free_loss"]), g["out_child_free_loss"], rtol=1e-3)
+        np.testing.assert_allclose(float(res["child_depth_loss"]), g["out_child_depth_loss"], rtol=1e-3)
+    np.testing.assert_allclose(res["depth_fine"].detach().cpu().numpy(), g["out_depth_fine"], rtol=5e-3, atol=1e-6)
