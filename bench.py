@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- train rays/s (fwd + bwd + Adam) of the PC-NeRF ray-rendering hot path on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision tc|fp32]
 
 One "step" = one pass of the hot path over one batch of synthetic LiDAR returns:
     K1 AABB stage (point -> child box, child near/far, parent far, 15-column ray records)
@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PCNERF_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("PCNERF_PRECISION", "tc"), choices=["fp32", "tc"],
+                    help="MLP engine: tc = TMA + tcgen05 + TMEM (fp16 operands forward, bf16 gradients, fp32 "
+                         "accumulation; 1e-3 parity gate), fp32 = CUDA-core SGEMM (1e-5 gate)")
     ap.add_argument("--rays", type=int, default=32768, help="rays per GPU per step")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -284,7 +286,7 @@ def run_b200(a):
 
     out = {"metric": METRIC, "value": rays_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f16 fwd / bf16 bwd operands, f32 accumulate", "data": "synthetic",
            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "N_samples": S, "N_importance": NI, "chunk": CHUNK,
                       "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam(fused)",
                       "parallelism": "dp%d (rays sharded, one flat NCCL all-reduce of 3.98 MB grads)" % world,

@@ -20,6 +20,7 @@ struct MlpLayout {
     size_t h_bytes;             // one activation matrix
     size_t off_stats, saved_bytes;
     size_t off_wp[8], off_wf[8], off_bf, off_wout, off_coef, off_gvec, off_g[2], off_partial, off_dstat, off_tc;
+    size_t off_hb, off_encb;    // precision 1: bf16 copies of H_{l-1} / enc (B operand of the weight-gradient GEMM)
     size_t n_dstat, scratch_bytes;
 
     MlpLayout(int64_t rows_, int precision_) : rows(rows_), precision(precision_) {
@@ -40,6 +41,10 @@ struct MlpLayout {
         off_dstat = o; o += al256(n_dstat * sizeof(double));
         off_tc = o;              // bf16 copies of the weights etc. for the tensor-core path
         o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
+        off_hb = o;
+        if (precision == 1) o += al256((size_t)rows * 256 * 2);
+        off_encb = o;
+        if (precision == 1) o += al256((size_t)rows * 64 * 2);
         scratch_bytes = o;
     }
     float* H(char* sv, int l) const { return (float*)(sv + (size_t)l * h_bytes); }
@@ -57,4 +62,6 @@ struct MlpLayout {
     double* dstat(char* sc, int slot) const { return (double*)(sc + off_dstat) + (size_t)slot * 512; }
     double* colsum(char* sc, int l) const { return (double*)(sc + off_dstat) + 16 * 512 + (size_t)l * 256; }
     char* tc(char* sc) const { return sc + off_tc; }
+    void* hb(char* sc) const { return (void*)(sc + off_hb); }
+    void* encb(char* sc) const { return (void*)(sc + off_encb); }
 };

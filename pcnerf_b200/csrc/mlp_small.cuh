@@ -188,7 +188,8 @@ template <bool LAST, class TH, class TG>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ gvec, TG* __restrict__ G,
                                                       const TH* __restrict__ H, int64_t rows,
                                                       const float* __restrict__ coef, const float* __restrict__ stats,
-                                                      double* __restrict__ colsum) {
+                                                      double* __restrict__ colsum,
+                                                      __nv_bfloat16* __restrict__ Hb = nullptr /* bf16 copy of H */) {
     const int j = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * STRIP;
     const float c0 = coef[j], c1 = coef[256 + j], c2 = coef[512 + j], mean = stats[j];
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
         const int64_t r = r0 + k;
         if (r >= rows) break;
         const float up = LAST ? gvec[r] : ldf(G + r * 256 + j);
-        const float dh = up * c0 - c1 - (ldf(H + r * 256 + j) - mean) * c2;
+        const float hv = ldf(H + r * 256 + j);
+        if (Hb) Hb[r * 256 + j] = __float2bfloat16_rn(hv);
+        const float dh = up * c0 - c1 - (hv - mean) * c2;
         stf(G + r * 256 + j, dh);
         cs += dh;
     }

@@ -442,6 +442,11 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 256 * 64) Wh0[i] = __float2half_rn(Wp0[i]);
 }
+// bf16 copy of the fp16 encodings (B operand of the layer-0 / layer-4 weight-gradient GEMMs)
+__global__ void k_tc_f16_to_bf16(const __half2* __restrict__ src, __nv_bfloat162* __restrict__ dst, int64_t n2) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __float22bfloat162_rn(__half22float2(src[i]));
+}
 struct PrepTArgs {
     const float* Wp[8];
     __nv_bfloat16* WT[8];
@@ -636,29 +641,42 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
               k_bn_bwd_apply<true, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef, L.stats(sv, 7),
                                                                                   L.colsum(scratch, 7)));
     float* part = L.partial(scratch);
+    __nv_bfloat16* Hb = (__nv_bfloat16*)L.hb(scratch);
+    __nv_bfloat16* encb = (__nv_bfloat16*)L.encb(scratch);
+    {
+        int64_t blocks = pcn_cdiv(rows * 32, 256);
+        if (blocks > PCN_SM_COUNT * 8) blocks = PCN_SM_COUNT * 8;
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                  k_tc_f16_to_bf16<<<(int)blocks, 256, 0, st>>>((const __half2*)ench, (__nv_bfloat162*)encb, rows * 32));
+    }
+    // tcgen05 kind::f16 needs A and B in the same 16-bit format (mixing bf16 gradients with fp16 activations is an
+    // illegal instruction on sm_100a), so the BN-backward pass of layer l-1, which reads H_{l-1} anyway, also
+    // leaves a bf16 copy of it for the weight-gradient GEMM of layer l.
     for (int l = 7; l >= 0; --l) {
         const __nv_bfloat16* DH = Gb[cur];
         const int kpad = mlp_kpad(l);
-        PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
         int rc = 0;
-        if (l == 0 || l == 4) rc = launch_wgrad(DH, ench, 64, 64, 0, rows, part, kpad, 0, st);
+        if (l > 0) {
+            double* s0 = L.dstat(scratch, 9 + (l - 1));
+            rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, nullptr,
+                                (const __half*)L.Hraw(sv, l - 1), rows, Gb[cur ^ 1], s0, s0 + 256, st);
+            if (rc) return rc;
+            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                      k_bn_bwd_coef<<<1, 256, 0, st>>>(s0, s0 + 256, rows, L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
+            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                      k_bn_bwd_apply<false, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(
+                          nullptr, Gb[cur ^ 1], (const __half*)L.Hraw(sv, l - 1), rows, coef, L.stats(sv, l - 1),
+                          L.colsum(scratch, l - 1), Hb));
+        }
+        PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
+        if (l == 0 || l == 4) rc = launch_wgrad(DH, encb, 64, 64, 1, rows, part, kpad, 0, st);
         if (rc) return rc;
-        if (l != 0) rc = launch_wgrad(DH, L.Hraw(sv, l - 1), 256, 256, 0, rows, part, kpad, l == 4 ? 64 : 0, st);
+        if (l != 0) rc = launch_wgrad(DH, Hb, 256, 256, 1, rows, part, kpad, l == 4 ? 64 : 0, st);
         if (rc) return rc;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, 1, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
                                                          G->dW[l], G->db[l]));
-        if (l == 0) break;
-        double* s0 = L.dstat(scratch, 9 + (l - 1));
-        rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, nullptr,
-                            (const __half*)L.Hraw(sv, l - 1), rows, Gb[cur ^ 1], s0, s0 + 256, st);
-        if (rc) return rc;
-        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_bn_bwd_coef<<<1, 256, 0, st>>>(s0, s0 + 256, rows, L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
         cur ^= 1;
-        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_bn_bwd_apply<false, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(
-                      nullptr, Gb[cur], (const __half*)L.Hraw(sv, l - 1), rows, coef, L.stats(sv, l - 1), L.colsum(scratch, l - 1)));
     }
     PCN_LAUNCH_CHECK();
     return 0;
@@ -683,6 +701,10 @@ extern "C" int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols
                                float* out, int ldo, int col_off, void* stream) {
     PCN_CHECK_ARG(DH && X && out && rows >= 1, "tc_wgrad: null argument");
     PCN_CHECK_ARG(ldo >= col_off + ncols && (ldo % 4) == 0 && (col_off % 4) == 0, "tc_wgrad: bad output window");
+    if (!x_is_bf16) {
+        pcn_set_error("tc_wgrad: X must be bf16 like DH (tcgen05 kind::f16 cannot mix fp16 and bf16 operands)");
+        return PCNERF_ERR_UNSUPPORTED;
+    }
     return launch_wgrad(DH, X, ldx, ncols, x_is_bf16, rows, out, ldo, col_off, (cudaStream_t)stream);
 }
 

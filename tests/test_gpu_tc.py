@@ -46,10 +46,18 @@ def test_rowgemm_dgrad_bf16(rows):
     np.testing.assert_allclose(stats[1].cpu().numpy(), (ref.double() * E.double()).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
 
 
-@pytest.mark.parametrize("rows,ncols,xdt", [(64, 256, torch.bfloat16), (64, 256, torch.float16), (1000, 256, torch.float16),
-                                            (30000, 64, torch.float16), (70000, 256, torch.float16)])
-def test_wgrad_mn_major(rows, ncols, xdt):
+def test_wgrad_rejects_mixed_formats():
+    """fp16 x bf16 operands in one tcgen05.mma kind::f16 are an illegal instruction on sm_100a (measured): refused."""
     from pcnerf_b200 import ops
+    out = torch.zeros((256, 256), dtype=torch.float32, device=dev())
+    with pytest.raises(NotImplementedError):
+        ops.tc_wgrad(_rand((64, 256), torch.bfloat16, 1), _rand((64, 256), torch.float16, 2), 256, out, 0)
+
+
+@pytest.mark.parametrize("rows,ncols", [(64, 256), (1000, 256), (30000, 64), (70000, 256)])
+def test_wgrad_mn_major(rows, ncols):
+    from pcnerf_b200 import ops
+    xdt = torch.bfloat16
     DH = _rand((rows, 256), torch.bfloat16, 8)
     X = _rand((rows, ncols), xdt, 9)
     out = torch.zeros((256, 320), dtype=torch.float32, device=dev())
