@@ -175,14 +175,16 @@ int pcnerf_mlp_backward(const pcnerf_mlp_params* h_params, const pcnerf_mlp_grad
                         void* scratch, size_t scratch_bytes, void* stream);
 
 /* Building blocks of the precision-1 path (TMA + tcgen05 + TMEM), exported for unit tests and reuse.
- * pcnerf_tc_rowgemm: out[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T.  mode 0: A, B, out fp16, + bias[256],
- *   stats (2,256) f64 = column sums of out and out^2 (zeroed by the call).  mode 1: A, B, out bf16, no bias,
- *   stats = column sums of out and of out*E with E (rows,256) fp16.  k0, k1 multiples of 64, k0 + k1 <= 320.
- * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T (bf16) * X[rows, 0:ncols] (fp16 or
- *   bf16, row stride ldx); ncols 64 or 256; accumulated with atomics (zero `out` first).
+ * pcnerf_tc_rowgemm: C[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T, k0, k1 multiples of 64, k0 + k1 <= 320.
+ *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 = bf16 copy or NULL;
+ *     stats (2,256) f64 = column sums of (C + bias) and (C + bias)^2 (zeroed by the call).
+ *   mode 1 (data gradient with the BatchNorm backward fused): A, B bf16; E (rows,256) bf16; vec = c0|c1|c2|mean [4][256];
+ *     out = bf16(c0*C - c1 - (E - mean)*c2); stats[0] = column sums of out.
+ * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T * X[rows, 0:ncols] (both bf16,
+ *   X row stride ldx); ncols 64 or 256; accumulated with atomics (zero `out` first).
  * pcnerf_tc_last_fault: non-zero if a tensor-core kernel aborted on a pipeline time-out (diagnostic). */
-int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B, const float* bias,
-                      const void* E, int64_t rows, void* out, double* stats, void* stream);
+int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B, const float* vec,
+                      const void* E, int64_t rows, void* out, void* out2, double* stats, void* stream);
 int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows, float* out, int ldo,
                     int col_off, void* stream);
 int pcnerf_tc_last_fault(void);

@@ -10,7 +10,7 @@ __host__ __device__ inline int mlp_kpad(int l) { return l == 0 ? 64 : (l == 4 ? 
 
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// saved  : H[0..7] (rows x 256, fp32 or bf16)  |  stats[8][4][256] fp32 = {mean, invstd, a = gamma*invstd, s = beta - mean*a}
+// saved  : H[0..7] (rows x 256, fp32 (precision 0) or bf16 (precision 1))  |  stats[8][4][256] fp32 = {mean, invstd, a = gamma*invstd, s = beta - mean*a}
 // scratch: Wp[8] | Wf[8] | bf[8][256] | wout_f[256]+bout_f | coef[3][256] | gvec[rows] | G[2][rows x 256] |
 //          partial[MAX_SPLITS][256][320] | dstat (fp64) : 16 x 512 stat slots + colsum[8][256]
 struct MlpLayout {
@@ -20,7 +20,7 @@ struct MlpLayout {
     size_t h_bytes;             // one activation matrix
     size_t off_stats, saved_bytes;
     size_t off_wp[8], off_wf[8], off_bf, off_wout, off_coef, off_gvec, off_g[2], off_partial, off_dstat, off_tc;
-    size_t off_hb, off_encb;    // precision 1: bf16 copies of H_{l-1} / enc (B operand of the weight-gradient GEMM)
+    size_t off_hf[2], off_encb; // precision 1: fp16 ping-pong activations of the forward pass; bf16 copy of enc
     size_t n_dstat, scratch_bytes;
 
     MlpLayout(int64_t rows_, int precision_) : rows(rows_), precision(precision_) {
@@ -33,7 +33,7 @@ struct MlpLayout {
         for (int l = 0; l < 8; ++l) { off_wf[l] = o; o += al256((size_t)256 * mlp_kpad(l) * 4); }
         off_bf = o; o += al256(8 * 256 * 4);
         off_wout = o; o += al256(512 * 4);
-        off_coef = o; o += al256(3 * 256 * 4);
+        off_coef = o; o += al256(4 * 256 * 4);
         off_gvec = o; o += al256((size_t)rows * 4);
         for (int i = 0; i < 2; ++i) { off_g[i] = o; o += al256((size_t)rows * 256 * esz); }
         off_partial = o; o += al256((size_t)MLP_MAX_SPLITS * 256 * 320 * 4);
@@ -41,8 +41,10 @@ struct MlpLayout {
         off_dstat = o; o += al256(n_dstat * sizeof(double));
         off_tc = o;              // bf16 copies of the weights etc. for the tensor-core path
         o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
-        off_hb = o;
-        if (precision == 1) o += al256((size_t)rows * 256 * 2);
+        for (int i = 0; i < 2; ++i) {
+            off_hf[i] = o;
+            if (precision == 1) o += al256((size_t)rows * 256 * 2);
+        }
         off_encb = o;
         if (precision == 1) o += al256((size_t)rows * 64 * 2);
         scratch_bytes = o;
@@ -62,6 +64,6 @@ struct MlpLayout {
     double* dstat(char* sc, int slot) const { return (double*)(sc + off_dstat) + (size_t)slot * 512; }
     double* colsum(char* sc, int l) const { return (double*)(sc + off_dstat) + 16 * 512 + (size_t)l * 256; }
     char* tc(char* sc) const { return sc + off_tc; }
-    void* hb(char* sc) const { return (void*)(sc + off_hb); }
+    void* hf(char* sc, int i) const { return (void*)(sc + off_hf[i]); }
     void* encb(char* sc) const { return (void*)(sc + off_encb); }
 };

@@ -115,6 +115,27 @@ __device__ __forceinline__ void ld8<__half>(const __half* p, float* o) {
     for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
 }
 
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 template <class TH>
 __global__ void k_logit_sigmoid(const TH* __restrict__ H, int64_t rows, const float* __restrict__ wf,
                                 const float* __restrict__ bf, float* __restrict__ out_p) {
@@ -137,25 +158,42 @@ __global__ void k_logit_sigmoid(const TH* __restrict__ H, int64_t rows, const fl
 
 #define STRIP 64
 
-// g = dL/dp * p(1-p);  acc[j] += sum_r g_r H8[r,j];  acc[256] += sum_r g_r
+// g = dL/dp * p(1-p);  acc[j] += sum_r g_r H8[r,j];  acc[256] += sum_r g_r.
+// One warp per row (lane = 8 consecutive columns, 16/32-byte loads), STRIP rows per block, block reduction in shared
+// memory, one fp64 atomic per column per block.
 template <class TH>
 __global__ void __launch_bounds__(256) k_out_bwd_reduce(const float* __restrict__ grad_p, const float* __restrict__ p,
                                                         const TH* __restrict__ H, int64_t rows,
                                                         float* __restrict__ gvec, double* __restrict__ acc) {
-    const int j = threadIdx.x;
+    __shared__ float red[8][257];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * STRIP;
-    float a = 0.f, sg = 0.f;
-    for (int k = 0; k < STRIP; ++k) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sg = 0.f;
+    for (int k = w; k < STRIP; k += 8) {
         const int64_t r = r0 + k;
         if (r >= rows) break;
         const float pv = p[r];
         const float gr = grad_p[r] * pv * (1.f - pv);
-        a = fmaf(gr, ldf(H + r * 256 + j), a);
+        float hv[8];
+        ld8<TH>(H + r * 256 + lane * 8, hv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(gr, hv[i], a[i]);
         sg += gr;
-        if (j == 0) gvec[r] = gr;
+        if (lane == 0) gvec[r] = gr;
     }
-    atomicAdd(acc + j, (double)a);
-    if (j == 0) atomicAdd(acc + 256, (double)sg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = a[i];
+    if (lane == 0) red[w][256] = sg;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    atomicAdd(acc + threadIdx.x, (double)t);
+    if (threadIdx.x == 0) {
+        float ts = 0.f;
+        for (int k = 0; k < 8; ++k) ts += red[k][256];
+        atomicAdd(acc + 256, (double)ts);
+    }
 }
 
 // Output-layer parameter grads, BN(7) grads and the coefficient vectors of
@@ -183,28 +221,48 @@ static __global__ void __launch_bounds__(256) k_out_bwd_finalize(const double* _
 
 // LAST: DH = g (x) u - c1 - (H - mean) c2     (Gy never materialised for the last BN)
 // else: DH = Gy*a - c1 - (H - mean) c2        in place on Gy
-// plus column sums of DH (the Linear bias gradient; zero in exact arithmetic)
+// plus column sums of DH (the Linear bias gradient; zero in exact arithmetic).
+// One warp per row, lane = 8 consecutive columns.
 template <bool LAST, class TH, class TG>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ gvec, TG* __restrict__ G,
                                                       const TH* __restrict__ H, int64_t rows,
                                                       const float* __restrict__ coef, const float* __restrict__ stats,
-                                                      double* __restrict__ colsum,
-                                                      __nv_bfloat16* __restrict__ Hb = nullptr /* bf16 copy of H */) {
-    const int j = threadIdx.x;
+                                                      double* __restrict__ colsum) {
+    __shared__ float red[8][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * STRIP;
-    const float c0 = coef[j], c1 = coef[256 + j], c2 = coef[512 + j], mean = stats[j];
-    float cs = 0.f;
-    for (int k = 0; k < STRIP; ++k) {
+    float c0[8], c1[8], c2[8], mean[8], cs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = lane * 8 + i;
+        c0[i] = coef[j]; c1[i] = coef[256 + j]; c2[i] = coef[512 + j]; mean[i] = stats[j]; cs[i] = 0.f;
+    }
+    for (int k = w; k < STRIP; k += 8) {
         const int64_t r = r0 + k;
         if (r >= rows) break;
-        const float up = LAST ? gvec[r] : ldf(G + r * 256 + j);
-        const float hv = ldf(H + r * 256 + j);
-        if (Hb) Hb[r * 256 + j] = __float2bfloat16_rn(hv);
-        const float dh = up * c0 - c1 - (hv - mean) * c2;
-        stf(G + r * 256 + j, dh);
-        cs += dh;
+        float hv[8], up[8], dh[8];
+        ld8<TH>(H + r * 256 + lane * 8, hv);
+        if (LAST) {
+            const float gr = gvec[r];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) up[i] = gr;
+        } else {
+            ld8<TG>(G + r * 256 + lane * 8, up);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dh[i] = up[i] * c0[i] - c1[i] - (hv[i] - mean[i]) * c2[i];
+            cs[i] += dh[i];
+        }
+        st8(G + r * 256 + lane * 8, dh);
     }
-    atomicAdd(colsum + j, (double)cs);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = cs[i];
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    atomicAdd(colsum + threadIdx.x, (double)t);
 }
 
 // BN(l) backward coefficients from the dgrad epilogue sums: st0 = sum Gy, st1 = sum Gy*H

@@ -127,54 +127,102 @@ __host__ __device__ constexpr uint32_t make_idesc(int afmt, int bfmt, int amaj, 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// lane L ends up with the sum over the warp of v[L] (31 shuffles for 32 columns)
-__device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float a = v[i], b = v[i + off];
-            const float send = up ? a : b;
-            const float keep = up ? b : a;
-            v[i] = keep + __shfl_xor_sync(FULL_MASK, send, off);
-        }
-    }
-    return v[0];
-}
-
 enum { TC_FWD = 0, TC_DGRAD = 1 };
 
 struct RowGemmArgs {
     int rows;
     int kb0, kb_total;          // 64-wide k-blocks taken from A0 / in total (A1 supplies the rest)
     int nstage;
-    void* out;                  // [rows][256], fp16 (FWD) or bf16 (DGRAD)
-    const float* bias;          // FWD: [256]
-    const __half* E;            // DGRAD: H_{l-1} [rows][256]; second statistic is sum_r C[r,n] * E[r,n]
-    double* stat0;
-    double* stat1;              // [256] each, accumulated atomically
+    void* out;                  // [rows][256]: fp16 (FWD) or bf16 (DGRAD)
+    __nv_bfloat16* out2;        // FWD: optional bf16 copy of `out` (what the backward pass reads)
+    const float* vec;           // FWD: bias[256];  DGRAD: c0 | c1 | c2 | mean, [4][256]
+    const __nv_bfloat16* E;     // DGRAD: H_{l-1} [rows][256] (bf16)
+    double* stat0;              // [256] column sums of the fp32 result, accumulated atomically
+    double* stat1;              // FWD: [256] column sums of squares
 };
 
+#define TC_STAGE_BYTES 2560     // per epilogue warp: 32 rows x 80 B (64 B payload + 16 B pad) or 32 x 17 floats
+
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Column sums over the warp's 32 rows of v[0..31] (and of v^2 when SQ), 16 columns at a time through the warp's
+// staging buffer ([32][17] floats, conflict-free both ways).  Lanes l and l^16 end up with column (hc*16 + l%16).
+template <bool SQ>
+__device__ __forceinline__ void stage_col_sums(float* stg, const float* v, int lane, double* acc0, double* acc1) {
+#pragma unroll
+    for (int hc = 0; hc < 2; ++hc) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[hc * 16 + j];
+        __syncwarp();
+        const int cj = lane & 15, rb = (lane >> 4) * 16;
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float x = stg[(rb + r) * 17 + cj];
+            s += x;
+            if (SQ) q = fmaf(x, x, q);
+        }
+        s += __shfl_xor_sync(FULL_MASK, s, 16);
+        acc0[hc] += (double)s;
+        if (SQ) {
+            q += __shfl_xor_sync(FULL_MASK, q, 16);
+            acc1[hc] += (double)q;
+        }
+    }
+}
+
+// Write the warp's 32 x 32 chunk of 16-bit values (pk[16] = this thread's row, 64 B) to dst[row][col0..col0+31] through
+// the staging buffer so that each store instruction covers 8 rows x 64 contiguous bytes (full sectors).
+__device__ __forceinline__ void stage_store_rows(uint8_t* stg, const uint32_t* pk, int lane, uint16_t* dst_tile_row0,
+                                                 int rows_left /* valid rows of this warp's 32 */) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<uint4*>(stg + lane * 80 + k * 16) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+    __syncwarp();
+    const int seg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = (lane >> 2) + 8 * i;
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 80 + seg * 16);
+        if (row < rows_left) *reinterpret_cast<uint4*>(dst_tile_row0 + (size_t)row * 256 + seg * 8) = val;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// C[rows,256] = A[rows,K] * B[256,K]^T     (A, B K-major; FWD: fp16 x fp16 -> fp16; DGRAD: bf16 x bf16 -> bf16)
+// C[rows,256] = A[rows,K] * B[256,K]^T     (A, B K-major)
+//   FWD  : fp16 x fp16; out = fp16(C + bias), out2 = bf16(C + bias); stats = column sums of (C+bias), (C+bias)^2
+//   DGRAD: bf16 x bf16; out = bf16(c0*C - c1 - (E - mean)*c2)  (BN backward fused); stat0 = column sums of out
 // ---------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB, const RowGemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[24];            // full[8] | empty[8] | bfull | tfull[2] | tempty[2]
+    __shared__ uint32_t tmem_slot;
+    __shared__ float cvec[(EPI == TC_FWD ? 1 : 4) * 256];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nstage = g.nstage, KB = g.kb_total;
     uint8_t* sB = smem;                                   // KB x 32 KB, resident
     uint8_t* sA = sB + (size_t)KB * TC_B_BYTES;           // nstage x 16 KB ring
-    uint64_t* bars = (uint64_t*)(sA + (size_t)nstage * TC_A_BYTES);
-    // bars: full[8] | empty[8] | bfull | tfull[2] | tempty[2]
+    uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 x TC_STAGE_BYTES
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
     const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
-    uint32_t* tmem_slot = (uint32_t*)(bars + 21);
-    float* bias_s = (float*)(bars + 22);                  // 256 floats
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -185,14 +233,12 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tma_prefetch_desc(&tmA1);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-    if (EPI == TC_FWD) {
-        if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = g.bias[threadIdx.x - 64];
-    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+    for (int i = threadIdx.x; i < (EPI == TC_FWD ? 1 : 4) * 256; i += TC_THREADS) cvec[i] = g.vec[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = tmem_slot;
     const int ntiles = (g.rows + 127) >> 7;
 
     if (warp == 0) {
@@ -243,87 +289,98 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             if (++as == 2) { as = 0; aph ^= 1; }
         }
     } else {
-        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, column half (warp-2)/4
+        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, column half (warp-2)/4, four 32-column chunks
         const int q = warp & 3, half = (warp - 2) >> 2;
-        double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        uint8_t* stg8 = sStage + (size_t)(warp - 2) * TC_STAGE_BYTES;
+        float* stgf = reinterpret_cast<float*>(stg8);
+        double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(bar_tfull + 8 * as, aph, 5);
             tc_fence_after();
-            const int row = tile * 128 + q * 32 + lane;
-            const bool valid = row < g.rows;
+            const int row0 = tile * 128 + q * 32;
+            const bool valid = row0 + lane < g.rows;
+            const int rows_left = g.rows - row0;          // rows of this warp's 32 that exist (may be <= 0 or >= 32)
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + half * 128);
+            uint32_t rbuf[2][32];
+            tmem_ld32_issue(tbase, rbuf[0]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int col0 = (half * 4 + c) * 32;
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + col0), r);
-                float v[32], w2[32];
+                tmem_ld_wait();
+                if (c < 3) {
+                    tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);
+                } else {
+                    // every accumulator value of this stage is in registers: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+                }
+                const uint32_t* r = rbuf[c & 1];
+                float v[32];
                 if (EPI == TC_FWD) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = valid ? __uint_as_float(r[j]) + bias_s[col0 + j] : 0.f;
-                        w2[j] = v[j] * v[j];
-                    }
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>((__half*)g.out + (size_t)row * 256 + col0);
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const __half2 h2 = __floats2half2_rn(v[j4 * 8 + 2 * t], v[j4 * 8 + 2 * t + 1]);
-                                pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
-                            }
-                            dst[j4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) + cvec[col0 + j] : 0.f;
                 } else {
-                    uint4 ev[4];
-                    if (valid) {
-                        const uint4* src = reinterpret_cast<const uint4*>(g.E + (size_t)row * 256 + col0);
+                    // this thread's row of H_{l-1}: fetched 8 rows x 64 B per instruction, re-read row-wise
+                    __syncwarp();
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) ev[j4] = src[j4];
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = (lane >> 2) + 8 * i;
+                        uint4 hv = make_uint4(0, 0, 0, 0);
+                        if (row < rows_left)
+                            hv = *reinterpret_cast<const uint4*>(g.E + (size_t)(row0 + row) * 256 + col0 + (lane & 3) * 8);
+                        *reinterpret_cast<uint4*>(stg8 + row * 80 + (lane & 3) * 16) = hv;
                     }
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const __half2* h = reinterpret_cast<const __half2*>(&ev[j4]);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 hv = *reinterpret_cast<const uint4*>(stg8 + lane * 80 + k * 16);
+                        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
-                            const float2 e = valid ? __half22float2(h[t]) : make_float2(0.f, 0.f);
-                            w2[j4 * 8 + 2 * t] = v[j4 * 8 + 2 * t] * e.x;
-                            w2[j4 * 8 + 2 * t + 1] = v[j4 * 8 + 2 * t + 1] * e.y;
-                        }
-                    }
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)g.out + (size_t)row * 256 + col0);
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j4 * 8 + 2 * t], v[j4 * 8 + 2 * t + 1]);
-                                pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
-                            }
-                            dst[j4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            const float2 h2 = __bfloat1622float2(hb[t]);
+                            const int j = k * 8 + 2 * t;
+                            const float g0 = __uint_as_float(r[j]), g1 = __uint_as_float(r[j + 1]);
+                            v[j] = valid ? cvec[col0 + j] * g0 - cvec[256 + col0 + j] - (h2.x - cvec[768 + col0 + j]) * cvec[512 + col0 + j] : 0.f;
+                            v[j + 1] = valid ? cvec[col0 + j + 1] * g1 - cvec[256 + col0 + j + 1] -
+                                                   (h2.y - cvec[768 + col0 + j + 1]) * cvec[512 + col0 + j + 1]
+                                             : 0.f;
                         }
                     }
                 }
-                acc0[c] += (double)warp_transpose_sum(v, lane);
-                acc1[c] += (double)warp_transpose_sum(w2, lane);
+                stage_col_sums<EPI == TC_FWD>(stgf, v, lane, acc0 + 2 * c, acc1 + 2 * c);
+                uint32_t pk[16];
+                if (EPI == TC_FWD) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const __half2 h2 = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+                        pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                    stage_store_rows(stg8, pk, lane, (uint16_t*)g.out + (size_t)row0 * 256 + col0, rows_left);
+                }
+                if (EPI == TC_DGRAD || g.out2) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+                        pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    uint16_t* dst = EPI == TC_DGRAD ? (uint16_t*)g.out : (uint16_t*)g.out2;
+                    stage_store_rows(stg8, pk, lane, dst + (size_t)row0 * 256 + col0, rows_left);
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (lane < 16) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int col = (half * 4 + c) * 32 + lane;
-            atomicAdd(g.stat0 + col, acc0[c]);
-            atomicAdd(g.stat1 + col, acc1[c]);
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    const int col = (half * 4 + c) * 32 + hc * 16 + lane;
+                    atomicAdd(g.stat0 + col, acc0[2 * c + hc]);
+                    if (EPI == TC_FWD) atomicAdd(g.stat1 + col, acc1[2 * c + hc]);
+                }
         }
     }
     tc_fence_before();
@@ -442,6 +499,34 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 256 * 64) Wh0[i] = __float2half_rn(Wp0[i]);
 }
+// BN(l-1) backward coefficients WITHOUT a pass over the data-gradient G = DH_l W_l:
+//   sum_r G[r,n]             = sum_o colsum_l[o] W_l[o,n]                 (colsum_l = column sums of DH_l)
+//   sum_r G[r,n] H_{l-1}[r,n] = sum_o W_l[o,n] (DH_l^T H_{l-1})[o,n]        (the raw weight gradient of layer l)
+// so the data-gradient GEMM can apply the BN backward in its own epilogue.  One block of 256 threads (n).
+__global__ void __launch_bounds__(256) k_tc_bn_bwd_coef2(const float* __restrict__ Wp, int kpad, int off,
+                                                         const float* __restrict__ part, const double* __restrict__ colsum,
+                                                         int64_t rows, const float* __restrict__ stats,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ coef /* c0 | c1 | c2 | mean */) {
+    const int n = threadIdx.x;
+    double st0 = 0.0, st1 = 0.0;
+    for (int o = 0; o < 256; ++o) {
+        const float w = Wp[(size_t)o * kpad + off + n];
+        st0 += colsum[o] * (double)w;
+        st1 += (double)w * (double)part[(size_t)o * kpad + off + n];
+    }
+    const float mean = stats[n], invstd = stats[256 + n], a = stats[512 + n];
+    const float db = (float)st0;
+    const float dg = invstd * (float)(st1 - (double)mean * st0);
+    dgamma[n] += dg;
+    dbeta[n] += db;
+    const float B = (float)rows;
+    coef[n] = a;
+    coef[256 + n] = a * db / B;
+    coef[512 + n] = a * invstd * dg / B;
+    coef[768 + n] = mean;
+}
+
 // bf16 copy of the fp16 encodings (B operand of the layer-0 / layer-4 weight-gradient GEMMs)
 __global__ void k_tc_f16_to_bf16(const __half2* __restrict__ src, __nv_bfloat162* __restrict__ dst, int64_t n2) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
@@ -507,10 +592,11 @@ int sm_count() {
     return n;
 }
 
-// mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias);  TC_DGRAD: A bf16, B bf16 -> out bf16, E = fp16 H
+// mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias), out2 bf16 copy;  TC_DGRAD: A bf16, B bf16 -> out bf16 (BN backward
+// fused: vec = c0|c1|c2|mean, E = bf16 H)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
-                   const float* bias, const __half* E, int64_t rows, void* out, double* stat0, double* stat1,
-                   cudaStream_t st) {
+                   const float* vec, const __nv_bfloat16* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
+                   double* stat1, cudaStream_t st) {
     PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && (k0 + k1) <= 320, "tc rowgemm: K must be 64..320 in 64s");
     CUtensorMap mA0, mA1, mB;
     int rc = make_map(&mA0, A0, rows, k0, lda0, 128);
@@ -521,9 +607,9 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     RowGemmArgs g;
     g.rows = (int)rows; g.kb0 = k0 / 64; g.kb_total = (k0 + k1) / 64;
-    g.nstage = g.kb_total >= 5 ? 3 : 4;
-    g.out = out; g.bias = bias; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
-    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 22 * 8 + 1024 + 64;
+    g.nstage = g.kb_total >= 5 ? 2 : 4;
+    g.out = out; g.out2 = out2; g.vec = vec; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
+    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * TC_STAGE_BYTES;
     const int ntiles = (int)pcn_cdiv(rows, 128);
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
     const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
@@ -585,15 +671,18 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
     tc_prep_weights(P, L, scratch, st);
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
+    // H_l leaves each layer twice: fp16 into a ping-pong buffer (the next layer's operand: 10-bit mantissa for the 1e-3
+    // gate) and bf16 into the saved store (what the backward pass reads; same format as the gradients, see k_tc_wgrad)
     for (int l = 0; l < 8; ++l) {
-        __half* Hl = (__half*)L.Hraw(sv, l);
+        __half* Hout = (__half*)L.hf(scratch, l & 1);
+        const __half* Hin = (const __half*)L.hf(scratch, (l - 1) & 1);
+        __nv_bfloat16* Hsave = (__nv_bfloat16*)L.Hraw(sv, l);
         double* s0 = L.dstat(scratch, l);
         const float* bias = l == 0 ? P->b[0] : L.bf(scratch, l);
         int rc;
-        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hl, s0, s0 + 256, st);
-        else if (l == 4)
-            rc = launch_rowgemm(TC_FWD, ench, 64, 64, L.Hraw(sv, 3), 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hl, s0, s0 + 256, st);
-        else rc = launch_rowgemm(TC_FWD, L.Hraw(sv, l - 1), 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hl, s0, s0 + 256, st);
+        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, st);
+        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, st);
+        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, st);
         if (rc) return rc;
         const bool last = l == 7;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
@@ -606,7 +695,7 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     int64_t blocks = pcn_cdiv(rows, 8);
     if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-              k_logit_sigmoid<__half><<<(int)blocks, 256, 0, st>>>((const __half*)L.Hraw(sv, 7), rows, L.wout_f(scratch),
+              k_logit_sigmoid<__half><<<(int)blocks, 256, 0, st>>>((const __half*)L.hf(scratch, 1), rows, L.wout_f(scratch),
                                                                   L.wout_f(scratch) + 256, out_p));
     PCN_LAUNCH_CHECK();
     return 0;
@@ -631,17 +720,16 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     float* coef = L.coef(scratch);
     __nv_bfloat16* Gb[2] = {(__nv_bfloat16*)L.Graw(scratch, 0), (__nv_bfloat16*)L.Graw(scratch, 1)};
     const int strips = (int)pcn_cdiv(rows, STRIP);
-    const __half* H7 = (const __half*)L.Hraw(sv, 7);
-    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__half><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
+    const __nv_bfloat16* H7 = (const __nv_bfloat16*)L.Hraw(sv, 7);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__nv_bfloat16><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
               k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
                                                     G->dbeta[7], coef));
     int cur = 0;
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-              k_bn_bwd_apply<true, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef, L.stats(sv, 7),
-                                                                                  L.colsum(scratch, 7)));
+              k_bn_bwd_apply<true, __nv_bfloat16, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef,
+                                                                                         L.stats(sv, 7), L.colsum(scratch, 7)));
     float* part = L.partial(scratch);
-    __nv_bfloat16* Hb = (__nv_bfloat16*)L.hb(scratch);
     __nv_bfloat16* encb = (__nv_bfloat16*)L.encb(scratch);
     {
         int64_t blocks = pcn_cdiv(rows * 32, 256);
@@ -649,33 +737,30 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_tc_f16_to_bf16<<<(int)blocks, 256, 0, st>>>((const __half2*)ench, (__nv_bfloat162*)encb, rows * 32));
     }
-    // tcgen05 kind::f16 needs A and B in the same 16-bit format (mixing bf16 gradients with fp16 activations is an
-    // illegal instruction on sm_100a), so the BN-backward pass of layer l-1, which reads H_{l-1} anyway, also
-    // leaves a bf16 copy of it for the weight-gradient GEMM of layer l.
+    // Per layer: weight gradient first (its raw result also yields the BN(l-1) backward coefficients, see
+    // k_tc_bn_bwd_coef2), then the data-gradient GEMM whose epilogue applies the BN backward and emits DH_{l-1} directly.
+    // tcgen05 kind::f16 needs A and B in the same 16-bit format (bf16 x fp16 is an illegal instruction on sm_100a):
+    // gradients, saved activations and the encoding copy are all bf16 here.
     for (int l = 7; l >= 0; --l) {
         const __nv_bfloat16* DH = Gb[cur];
-        const int kpad = mlp_kpad(l);
-        int rc = 0;
-        if (l > 0) {
-            double* s0 = L.dstat(scratch, 9 + (l - 1));
-            rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, nullptr,
-                                (const __half*)L.Hraw(sv, l - 1), rows, Gb[cur ^ 1], s0, s0 + 256, st);
-            if (rc) return rc;
-            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                      k_bn_bwd_coef<<<1, 256, 0, st>>>(s0, s0 + 256, rows, L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
-            PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                      k_bn_bwd_apply<false, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(
-                          nullptr, Gb[cur ^ 1], (const __half*)L.Hraw(sv, l - 1), rows, coef, L.stats(sv, l - 1),
-                          L.colsum(scratch, l - 1), Hb));
-        }
+        const int kpad = mlp_kpad(l), off = l == 4 ? 64 : 0;
+        const __nv_bfloat16* Hprev = l > 0 ? (const __nv_bfloat16*)L.Hraw(sv, l - 1) : nullptr;
         PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
+        int rc = 0;
         if (l == 0 || l == 4) rc = launch_wgrad(DH, encb, 64, 64, 1, rows, part, kpad, 0, st);
         if (rc) return rc;
-        if (l != 0) rc = launch_wgrad(DH, Hb, 256, 256, 1, rows, part, kpad, l == 4 ? 64 : 0, st);
+        if (l != 0) rc = launch_wgrad(DH, Hprev, 256, 256, 1, rows, part, kpad, off, st);
         if (rc) return rc;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, 1, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
                                                          G->dW[l], G->db[l]));
+        if (l == 0) break;
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                  k_tc_bn_bwd_coef2<<<1, 256, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
+                                                       L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
+        rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
+                            nullptr, L.colsum(scratch, l - 1), nullptr, st);
+        if (rc) return rc;
         cur ^= 1;
     }
     PCN_LAUNCH_CHECK();
@@ -686,15 +771,15 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
 // Building-block entry points (unit-tested against torch.matmul; also usable on their own)
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B,
-                                 const float* bias, const void* E, int64_t rows, void* out, double* stats,
+                                 const float* vec, const void* E, int64_t rows, void* out, void* out2, double* stats,
                                  void* stream) {
     PCN_CHECK_ARG(mode == 0 || mode == 1, "tc_rowgemm: mode must be 0 (fp16 forward) or 1 (bf16 data gradient)");
-    PCN_CHECK_ARG(A0 && B && out && stats && rows >= 1, "tc_rowgemm: null argument");
-    PCN_CHECK_ARG(mode == 1 || bias, "tc_rowgemm: forward mode needs a bias");
+    PCN_CHECK_ARG(A0 && B && out && stats && vec && rows >= 1, "tc_rowgemm: null argument");
     PCN_CHECK_ARG(mode == 0 || E, "tc_rowgemm: data-gradient mode needs E");
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
-    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, bias, (const __half*)E, rows, out, stats, stats + 256, st);
+    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __nv_bfloat16*)E, rows, out,
+                          mode == 0 ? (__nv_bfloat16*)out2 : nullptr, stats, stats + 256, st);
 }
 
 extern "C" int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows,

@@ -468,20 +468,23 @@ def points(rays, depth):
 # ------------------------------------------------------------------------------- tensor-core building blocks (tests)
 
 
-def tc_rowgemm(mode, A0, B, A1=None, bias=None, E=None):
-    """out (rows,256) = [A0 | A1] @ B.T (+ bias) on tcgen05; mode 0: fp16 in/out, mode 1: bf16 in/out with E fp16.
-    Returns (out, stats (2,256) f64)."""
+def tc_rowgemm(mode, A0, B, A1=None, vec=None, E=None, want_bf16_copy=True):
+    """C (rows,256) = [A0 | A1] @ B.T on tcgen05.
+    mode 0: fp16 operands; returns (fp16(C + vec), bf16 copy or None, stats (2,256) f64 = col sums of C+vec and its square).
+    mode 1: bf16 operands, E bf16, vec = (4,256) [c0, c1, c2, mean]; returns (bf16(c0*C - c1 - (E-mean)*c2), None, stats)."""
     dt = torch.float16 if mode == 0 else torch.bfloat16
     for t in (A0, B) + ((A1,) if A1 is not None else ()):
         if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
             raise TypeError("tc_rowgemm: operands must be contiguous CUDA %s tensors" % dt)
+    vec = _cuda_f32(vec, "vec")
     rows, k0 = A0.shape
     k1 = 0 if A1 is None else A1.shape[1]
     out = torch.empty((rows, 256), dtype=dt, device=A0.device)
+    out2 = torch.empty((rows, 256), dtype=torch.bfloat16, device=A0.device) if (mode == 0 and want_bf16_copy) else None
     stats = torch.empty((2, 256), dtype=torch.float64, device=A0.device)
-    check(lib().pcnerf_tc_rowgemm(int(mode), _p(A0), k0, _p(A1), k1, _p(B), _p(bias), _p(E), rows, _p(out), _p(stats),
-                                  _stream()))
-    return out, stats
+    check(lib().pcnerf_tc_rowgemm(int(mode), _p(A0), k0, _p(A1), k1, _p(B), _p(vec), _p(E), rows, _p(out), _p(out2),
+                                  _p(stats), _stream()))
+    return out, out2, stats
 
 
 def tc_wgrad(DH, X, ncols, out, col_off=0):

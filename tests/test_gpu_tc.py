@@ -24,26 +24,28 @@ def test_rowgemm_forward_fp16(rows, k0, k1):
     A1 = _rand((rows, k1), torch.float16, 2) if k1 else None
     B = _rand((256, k0 + k1), torch.float16, 3, 0.1)
     bias = _rand((256,), torch.float32, 4)
-    out, stats = ops.tc_rowgemm(0, A0, B, A1, bias)
+    out, out2, stats = ops.tc_rowgemm(0, A0, B, A1, bias)
     A = A0 if A1 is None else torch.cat([A0, A1], 1)
     ref = A.float() @ B.float().t() + bias
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=2e-3, atol=2e-3)   # fp16 output rounding
+    np.testing.assert_allclose(out2.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=1e-2)  # bf16 copy
     np.testing.assert_allclose(stats[0].cpu().numpy(), ref.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(stats[1].cpu().numpy(), (ref.double() ** 2).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("rows", [128, 300, 20000])
-def test_rowgemm_dgrad_bf16(rows):
+def test_rowgemm_dgrad_bf16_fused_bn_backward(rows):
     from pcnerf_b200 import ops
     A = _rand((rows, 256), torch.bfloat16, 5)
     B = _rand((256, 256), torch.bfloat16, 6, 0.1)
-    E = _rand((rows, 256), torch.float16, 7)
-    out, stats = ops.tc_rowgemm(1, A, B, None, None, E)
-    ref = A.float() @ B.float().t()
-    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=1e-2)    # bf16 output rounding
-    np.testing.assert_allclose(stats[0].cpu().numpy(), ref.double().sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
-    np.testing.assert_allclose(stats[1].cpu().numpy(), (ref.double() * E.double()).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    E = _rand((rows, 256), torch.bfloat16, 7)
+    vec = _rand((4, 256), torch.float32, 8)
+    out, _, stats = ops.tc_rowgemm(1, A, B, None, vec, E)
+    C = A.float() @ B.float().t()
+    ref = vec[0] * C - vec[1] - (E.float() - vec[3]) * vec[2]
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=2e-2)    # bf16 output rounding
+    np.testing.assert_allclose(stats[0].cpu().numpy(), ref.double().sum(0).cpu().numpy(), rtol=1e-5, atol=2e-3)
 
 
 def test_wgrad_rejects_mixed_formats():
