@@ -46,10 +46,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u) /* suspend-time hint: the warp may sleep until the phase completes */
         : "memory");
     return ok != 0;
 }
@@ -157,24 +157,43 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// explicit shared-space accesses (32-bit shared addresses): keeps the staging traffic on LDS/STS instead of generic LD/ST
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
 // Column sums over the warp's 32 rows of v[0..31] (and of v^2 when SQ), 16 columns at a time through the warp's
 // staging buffer ([32][17] floats, conflict-free both ways).  Lanes l and l^16 end up with column (hc*16 + l%16).
 template <bool SQ>
-__device__ __forceinline__ void stage_col_sums(float* stg, const float* v, int lane, double* acc0, double* acc1) {
+__device__ __forceinline__ void stage_col_sums(uint32_t stg, const float* v, int lane, double* acc0, double* acc1) {
 #pragma unroll
     for (int hc = 0; hc < 2; ++hc) {
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[hc * 16 + j];
+        for (int j = 0; j < 16; ++j) sts32(stg + (uint32_t)(lane * 17 + j) * 4, v[hc * 16 + j]);
         __syncwarp();
         const int cj = lane & 15, rb = (lane >> 4) * 16;
-        float s = 0.f, q = 0.f;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const float x = stg[(rb + r) * 17 + cj];
-            s += x;
-            if (SQ) q = fmaf(x, x, q);
+        for (int r = 0; r < 16; r += 2) {
+            const float x = lds32(stg + (uint32_t)((rb + r) * 17 + cj) * 4);
+            const float y = lds32(stg + (uint32_t)((rb + r + 1) * 17 + cj) * 4);
+            s0 += x;
+            s1 += y;
+            if (SQ) { q0 = fmaf(x, x, q0); q1 = fmaf(y, y, q1); }
         }
+        float s = s0 + s1, q = q0 + q1;
         s += __shfl_xor_sync(FULL_MASK, s, 16);
         acc0[hc] += (double)s;
         if (SQ) {
@@ -186,18 +205,18 @@ __device__ __forceinline__ void stage_col_sums(float* stg, const float* v, int l
 
 // Write the warp's 32 x 32 chunk of 16-bit values (pk[16] = this thread's row, 64 B) to dst[row][col0..col0+31] through
 // the staging buffer so that each store instruction covers 8 rows x 64 contiguous bytes (full sectors).
-__device__ __forceinline__ void stage_store_rows(uint8_t* stg, const uint32_t* pk, int lane, uint16_t* dst_tile_row0,
+__device__ __forceinline__ void stage_store_rows(uint32_t stg, const uint32_t* pk, int lane, uint16_t* dst_tile_row0,
                                                  int rows_left /* valid rows of this warp's 32 */) {
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<uint4*>(stg + lane * 80 + k * 16) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        sts128(stg + (uint32_t)(lane * 80 + k * 16), make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
     __syncwarp();
     const int seg = lane & 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = (lane >> 2) + 8 * i;
-        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 80 + seg * 16);
+        const uint4 val = lds128(stg + (uint32_t)(row * 80 + seg * 16));
         if (row < rows_left) *reinterpret_cast<uint4*>(dst_tile_row0 + (size_t)row * 256 + seg * 8) = val;
     }
 }
@@ -214,7 +233,8 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[24];            // full[8] | empty[8] | bfull | tfull[2] | tempty[2]
     __shared__ uint32_t tmem_slot;
-    __shared__ float cvec[(EPI == TC_FWD ? 1 : 4) * 256];
+    // FWD: bias[256].  DGRAD: c0 | c2 | k, k = c2*mean - c1, so that DH = c0*G - c2*H + k (two FMAs per element)
+    __shared__ __align__(16) float cvec[(EPI == TC_FWD ? 1 : 3) * 256];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nstage = g.nstage, KB = g.kb_total;
@@ -234,7 +254,16 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tma_prefetch_desc(&tmB);
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
-    for (int i = threadIdx.x; i < (EPI == TC_FWD ? 1 : 4) * 256; i += TC_THREADS) cvec[i] = g.vec[i];
+    if (EPI == TC_FWD) {
+        for (int i = threadIdx.x; i < 256; i += TC_THREADS) cvec[i] = g.vec[i];
+    } else {
+        for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+            const float c0 = g.vec[i], c1 = g.vec[256 + i], c2 = g.vec[512 + i], mean = g.vec[768 + i];
+            cvec[i] = c0;
+            cvec[256 + i] = c2;
+            cvec[512 + i] = c2 * mean - c1;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -291,8 +320,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     } else {
         // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, column half (warp-2)/4, four 32-column chunks
         const int q = warp & 3, half = (warp - 2) >> 2;
-        uint8_t* stg8 = sStage + (size_t)(warp - 2) * TC_STAGE_BYTES;
-        float* stgf = reinterpret_cast<float*>(stg8);
+        const uint32_t stg = smem_u32(sStage) + (uint32_t)(warp - 2) * TC_STAGE_BYTES;
         double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
@@ -321,7 +349,13 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 float v[32];
                 if (EPI == TC_FWD) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = valid ? __uint_as_float(r[j]) + cvec[col0 + j] : 0.f;
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&cvec[col0 + 4 * j4]);
+                        v[4 * j4 + 0] = valid ? __uint_as_float(r[4 * j4 + 0]) + b4.x : 0.f;
+                        v[4 * j4 + 1] = valid ? __uint_as_float(r[4 * j4 + 1]) + b4.y : 0.f;
+                        v[4 * j4 + 2] = valid ? __uint_as_float(r[4 * j4 + 2]) + b4.z : 0.f;
+                        v[4 * j4 + 3] = valid ? __uint_as_float(r[4 * j4 + 3]) + b4.w : 0.f;
+                    }
                 } else {
                     // this thread's row of H_{l-1}: fetched 8 rows x 64 B per instruction, re-read row-wise
                     __syncwarp();
@@ -331,26 +365,34 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         uint4 hv = make_uint4(0, 0, 0, 0);
                         if (row < rows_left)
                             hv = *reinterpret_cast<const uint4*>(g.E + (size_t)(row0 + row) * 256 + col0 + (lane & 3) * 8);
-                        *reinterpret_cast<uint4*>(stg8 + row * 80 + (lane & 3) * 16) = hv;
+                        sts128(stg + (uint32_t)(row * 80 + (lane & 3) * 16), hv);
                     }
                     __syncwarp();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint4 hv = *reinterpret_cast<const uint4*>(stg8 + lane * 80 + k * 16);
+                        const uint4 hv = lds128(stg + (uint32_t)(lane * 80 + k * 16));
                         const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
+                        float hf[8];
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const float2 h2 = __bfloat1622float2(hb[t]);
-                            const int j = k * 8 + 2 * t;
-                            const float g0 = __uint_as_float(r[j]), g1 = __uint_as_float(r[j + 1]);
-                            v[j] = valid ? cvec[col0 + j] * g0 - cvec[256 + col0 + j] - (h2.x - cvec[768 + col0 + j]) * cvec[512 + col0 + j] : 0.f;
-                            v[j + 1] = valid ? cvec[col0 + j + 1] * g1 - cvec[256 + col0 + j + 1] -
-                                                   (h2.y - cvec[768 + col0 + j + 1]) * cvec[512 + col0 + j + 1]
-                                             : 0.f;
+                            hf[2 * t] = h2.x;
+                            hf[2 * t + 1] = h2.y;
+                        }
+#pragma unroll
+                        for (int t4 = 0; t4 < 2; ++t4) {
+                            const int j = k * 8 + t4 * 4;
+                            const float4 a0 = *reinterpret_cast<const float4*>(&cvec[col0 + j]);
+                            const float4 a2 = *reinterpret_cast<const float4*>(&cvec[256 + col0 + j]);
+                            const float4 ak = *reinterpret_cast<const float4*>(&cvec[512 + col0 + j]);
+                            v[j + 0] = valid ? fmaf(a0.x, __uint_as_float(r[j + 0]), fmaf(-a2.x, hf[t4 * 4 + 0], ak.x)) : 0.f;
+                            v[j + 1] = valid ? fmaf(a0.y, __uint_as_float(r[j + 1]), fmaf(-a2.y, hf[t4 * 4 + 1], ak.y)) : 0.f;
+                            v[j + 2] = valid ? fmaf(a0.z, __uint_as_float(r[j + 2]), fmaf(-a2.z, hf[t4 * 4 + 2], ak.z)) : 0.f;
+                            v[j + 3] = valid ? fmaf(a0.w, __uint_as_float(r[j + 3]), fmaf(-a2.w, hf[t4 * 4 + 3], ak.w)) : 0.f;
                         }
                     }
                 }
-                stage_col_sums<EPI == TC_FWD>(stgf, v, lane, acc0 + 2 * c, acc1 + 2 * c);
+                stage_col_sums<EPI == TC_FWD>(stg, v, lane, acc0 + 2 * c, acc1 + 2 * c);
                 uint32_t pk[16];
                 if (EPI == TC_FWD) {
 #pragma unroll
@@ -358,7 +400,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         const __half2 h2 = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
                         pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
                     }
-                    stage_store_rows(stg8, pk, lane, (uint16_t*)g.out + (size_t)row0 * 256 + col0, rows_left);
+                    stage_store_rows(stg, pk, lane, (uint16_t*)g.out + (size_t)row0 * 256 + col0, rows_left);
                 }
                 if (EPI == TC_DGRAD || g.out2) {
 #pragma unroll
@@ -367,7 +409,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
                     }
                     uint16_t* dst = EPI == TC_DGRAD ? (uint16_t*)g.out : (uint16_t*)g.out2;
-                    stage_store_rows(stg8, pk, lane, dst + (size_t)row0 * 256 + col0, rows_left);
+                    stage_store_rows(stg, pk, lane, dst + (size_t)row0 * 256 + col0, rows_left);
                 }
             }
             if (++as == 2) { as = 0; aph ^= 1; }
@@ -503,18 +545,26 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
 //   sum_r G[r,n]             = sum_o colsum_l[o] W_l[o,n]                 (colsum_l = column sums of DH_l)
 //   sum_r G[r,n] H_{l-1}[r,n] = sum_o W_l[o,n] (DH_l^T H_{l-1})[o,n]        (the raw weight gradient of layer l)
 // so the data-gradient GEMM can apply the BN backward in its own epilogue.  One block of 256 threads (n).
-__global__ void __launch_bounds__(256) k_tc_bn_bwd_coef2(const float* __restrict__ Wp, int kpad, int off,
-                                                         const float* __restrict__ part, const double* __restrict__ colsum,
-                                                         int64_t rows, const float* __restrict__ stats,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                         float* __restrict__ coef /* c0 | c1 | c2 | mean */) {
-    const int n = threadIdx.x;
+__global__ void __launch_bounds__(1024) k_tc_bn_bwd_coef2(const float* __restrict__ Wp, int kpad, int off,
+                                                          const float* __restrict__ part, const double* __restrict__ colsum,
+                                                          int64_t rows, const float* __restrict__ stats,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                          float* __restrict__ coef /* c0 | c1 | c2 | mean */) {
+    __shared__ double r0[4][256], r1[4][256];
+    const int n = threadIdx.x & 255, og = threadIdx.x >> 8;      // 4 groups of 64 output rows
     double st0 = 0.0, st1 = 0.0;
-    for (int o = 0; o < 256; ++o) {
+#pragma unroll 8
+    for (int o = og * 64; o < og * 64 + 64; ++o) {
         const float w = Wp[(size_t)o * kpad + off + n];
         st0 += colsum[o] * (double)w;
         st1 += (double)w * (double)part[(size_t)o * kpad + off + n];
     }
+    r0[og][n] = st0;
+    r1[og][n] = st1;
+    __syncthreads();
+    if (og != 0) return;
+    st0 = r0[0][n] + r0[1][n] + r0[2][n] + r0[3][n];
+    st1 = r1[0][n] + r1[1][n] + r1[2][n] + r1[3][n];
     const float mean = stats[n], invstd = stats[256 + n], a = stats[512 + n];
     const float db = (float)st0;
     const float dg = invstd * (float)(st1 - (double)mean * st0);
@@ -756,7 +806,7 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
                                                          G->dW[l], G->db[l]));
         if (l == 0) break;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_tc_bn_bwd_coef2<<<1, 256, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
+                  k_tc_bn_bwd_coef2<<<1, 1024, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
                                                        L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
         rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
                             nullptr, L.colsum(scratch, l - 1), nullptr, st);
