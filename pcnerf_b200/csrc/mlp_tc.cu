@@ -74,6 +74,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -141,7 +153,8 @@ struct RowGemmArgs {
     double* stat1;              // FWD: [256] column sums of squares
 };
 
-#define TC_STAGE_BYTES 2560     // per epilogue warp: 32 rows x 80 B (64 B payload + 16 B pad) or 32 x 17 floats
+#define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
+#define TC_NBUF 2               // staging buffers per epilogue warp
 
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -158,10 +171,9 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // explicit shared-space accesses (32-bit shared addresses): keeps the staging traffic on LDS/STS instead of generic LD/ST
-__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ float lds32(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
@@ -173,63 +185,58 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
     return v;
 }
 
-// Column sums over the warp's 32 rows of v[0..31] (and of v^2 when SQ), 16 columns at a time through the warp's
-// staging buffer ([32][17] floats, conflict-free both ways).  Lanes l and l^16 end up with column (hc*16 + l%16).
-template <bool SQ>
-__device__ __forceinline__ void stage_col_sums(uint32_t stg, const float* v, int lane, double* acc0, double* acc1) {
-#pragma unroll
-    for (int hc = 0; hc < 2; ++hc) {
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sts32(stg + (uint32_t)(lane * 17 + j) * 4, v[hc * 16 + j]);
-        __syncwarp();
-        const int cj = lane & 15, rb = (lane >> 4) * 16;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-        for (int r = 0; r < 16; r += 2) {
-            const float x = lds32(stg + (uint32_t)((rb + r) * 17 + cj) * 4);
-            const float y = lds32(stg + (uint32_t)((rb + r + 1) * 17 + cj) * 4);
-            s0 += x;
-            s1 += y;
-            if (SQ) { q0 = fmaf(x, x, q0); q1 = fmaf(y, y, q1); }
-        }
-        float s = s0 + s1, q = q0 + q1;
-        s += __shfl_xor_sync(FULL_MASK, s, 16);
-        acc0[hc] += (double)s;
-        if (SQ) {
-            q += __shfl_xor_sync(FULL_MASK, q, 16);
-            acc1[hc] += (double)q;
-        }
-    }
+// Staging buffer layout = the SWIZZLE_64B layout of a {32 columns x 32 rows} 16-bit TMA box: row r at r*64 B, its 16-byte
+// chunk k at position k ^ ((r >> 1) & 3).  Row-per-thread 16-byte accesses and the column walks below are conflict-free.
+__device__ __forceinline__ uint32_t stage_addr(uint32_t buf, int row, int chunk) {
+    return buf + (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
-
-// Write the warp's 32 x 32 chunk of 16-bit values (pk[16] = this thread's row, 64 B) to dst[row][col0..col0+31] through
-// the staging buffer so that each store instruction covers 8 rows x 64 contiguous bytes (full sectors).
-__device__ __forceinline__ void stage_store_rows(uint32_t stg, const uint32_t* pk, int lane, uint16_t* dst_tile_row0,
-                                                 int rows_left /* valid rows of this warp's 32 */) {
-    __syncwarp();
+// this thread's row (pk[16] = 32 packed 16-bit values) -> staging buffer
+__device__ __forceinline__ void stage_put_row(uint32_t buf, const uint32_t* pk, int lane) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        sts128(stg + (uint32_t)(lane * 80 + k * 16), make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
-    __syncwarp();
-    const int seg = lane & 3;
+    for (int k = 0; k < 4; ++k) sts128(stage_addr(buf, lane, k), make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+}
+// Column sums (and sums of squares) over the 32 rows of a staged 32 x 32 chunk of 16-bit values.  Lane l walks the
+// 32-bit word (l % 16) = columns 2(l%16), 2(l%16)+1 of the even rows (l < 16) or the odd rows (l >= 16): 32 distinct banks
+// per access.  After the xor-16 shuffle lanes l and l^16 both hold the totals of their two columns.
+template <bool HALF, bool SQ>
+__device__ __forceinline__ void stage_col_sums(uint32_t buf, int lane, double* acc0, double* acc1) {
+    const int w = lane & 15, par = lane >> 4;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = (lane >> 2) + 8 * i;
-        const uint4 val = lds128(stg + (uint32_t)(row * 80 + seg * 16));
-        if (row < rows_left) *reinterpret_cast<uint4*>(dst_tile_row0 + (size_t)row * 256 + seg * 8) = val;
+    for (int i = 0; i < 16; ++i) {
+        const int row = 2 * i + par;
+        const uint32_t u = lds32u(stage_addr(buf, row, w >> 2) + (uint32_t)((w & 3) << 2));
+        float2 f;
+        if (HALF) f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        s0 += f.x;
+        s1 += f.y;
+        if (SQ) { q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1); }
+    }
+    s0 += __shfl_xor_sync(FULL_MASK, s0, 16);
+    s1 += __shfl_xor_sync(FULL_MASK, s1, 16);
+    acc0[0] += (double)s0;
+    acc0[1] += (double)s1;
+    if (SQ) {
+        q0 += __shfl_xor_sync(FULL_MASK, q0, 16);
+        q1 += __shfl_xor_sync(FULL_MASK, q1, 16);
+        acc1[0] += (double)q0;
+        acc1[1] += (double)q1;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // C[rows,256] = A[rows,K] * B[256,K]^T     (A, B K-major)
-//   FWD  : fp16 x fp16; out = fp16(C + bias), out2 = bf16(C + bias); stats = column sums of (C+bias), (C+bias)^2
+//   FWD  : fp16 x fp16; out = fp16(C + bias), out2 = bf16(C + bias); stats = column sums of out and out^2 (the fp16
+//          values the next layer consumes)
 //   DGRAD: bf16 x bf16; out = bf16(c0*C - c1 - (E - mean)*c2)  (BN backward fused); stat0 = column sums of out
+// Outputs leave through per-warp TMA stores of {32 x 32} boxes; rows beyond `rows` are clipped by the tensor map.
 // ---------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-             const __grid_constant__ CUtensorMap tmB, const RowGemmArgs g) {
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+             const __grid_constant__ CUtensorMap tmO2, const RowGemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[24];            // full[8] | empty[8] | bfull | tfull[2] | tempty[2]
     __shared__ uint32_t tmem_slot;
@@ -240,7 +247,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const int nstage = g.nstage, KB = g.kb_total;
     uint8_t* sB = smem;                                   // KB x 32 KB, resident
     uint8_t* sA = sB + (size_t)KB * TC_B_BYTES;           // nstage x 16 KB ring
-    uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 x TC_STAGE_BYTES
+    uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 warps x TC_NBUF x TC_STAGE_BYTES
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
     const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
 
@@ -252,6 +259,8 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmA1);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmO2);
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
     if (EPI == TC_FWD) {
@@ -320,16 +329,29 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     } else {
         // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, column half (warp-2)/4, four 32-column chunks
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const uint32_t stg = smem_u32(sStage) + (uint32_t)(warp - 2) * TC_STAGE_BYTES;
+        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF * TC_STAGE_BYTES);
+        const uint32_t buf1 = buf0 + TC_STAGE_BYTES;
         double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
+        // DGRAD: this warp's 32 x 64 B piece of H_{l-1} for the NEXT chunk is always in flight (8 rows x 64 B per load
+        // instruction) while the current chunk is processed
+        uint4 e[4];
+        auto load_e = [&](int tile_, int c_) {
+            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_, c0_ = (half * 4 + c_) * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = (lane >> 2) + 8 * i;
+                e[i] = make_uint4(0, 0, 0, 0);
+                if (row < left_) e[i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + c0_ + (lane & 3) * 8);
+            }
+        };
+        if (EPI == TC_DGRAD && (int)blockIdx.x < ntiles) load_e(blockIdx.x, 0);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(bar_tfull + 8 * as, aph, 5);
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
             const bool valid = row0 + lane < g.rows;
-            const int rows_left = g.rows - row0;          // rows of this warp's 32 that exist (may be <= 0 or >= 32)
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + half * 128);
             uint32_t rbuf[2][32];
             tmem_ld32_issue(tbase, rbuf[0]);
@@ -347,6 +369,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 }
                 const uint32_t* r = rbuf[c & 1];
                 float v[32];
+                uint32_t pk[16];
                 if (EPI == TC_FWD) {
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -356,21 +379,46 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         v[4 * j4 + 2] = valid ? __uint_as_float(r[4 * j4 + 2]) + b4.z : 0.f;
                         v[4 * j4 + 3] = valid ? __uint_as_float(r[4 * j4 + 3]) + b4.w : 0.f;
                     }
-                } else {
-                    // this thread's row of H_{l-1}: fetched 8 rows x 64 B per instruction, re-read row-wise
-                    __syncwarp();
+                    // fp16 tile -> buf0 -> TMA store; its column statistics are read back from the same staging buffer
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = (lane >> 2) + 8 * i;
-                        uint4 hv = make_uint4(0, 0, 0, 0);
-                        if (row < rows_left)
-                            hv = *reinterpret_cast<const uint4*>(g.E + (size_t)(row0 + row) * 256 + col0 + (lane & 3) * 8);
-                        sts128(stg + (uint32_t)(row * 80 + (lane & 3) * 16), hv);
+                    for (int t = 0; t < 16; ++t) {
+                        const __half2 h2 = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+                        pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                    if (lane == 0) {                              // buf0's previous store has been read out
+                        if (g.out2) tma_store_wait_read<1>();
+                        else tma_store_wait_read<0>();
                     }
                     __syncwarp();
+                    stage_put_row(buf0, pk, lane);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmO, buf0, col0, row0);
+                    stage_col_sums<true, true>(buf0, lane, acc0 + 2 * c, acc1 + 2 * c);
+                    if (g.out2) {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+                            pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
+                        }
+                        if (lane == 0) tma_store_wait_read<1>();  // buf1's previous store has been read out
+                        __syncwarp();
+                        stage_put_row(buf1, pk, lane);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&tmO2, buf1, col0, row0);
+                    }
+                } else {
+                    // this thread's row of H_{l-1}: staged through buf0 (8 rows x 64 B per load), re-read row-wise
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sts128(stage_addr(buf0, (lane >> 2) + 8 * i, lane & 3), e[i]);
+                    __syncwarp();
+                    if (c < 3) load_e(tile, c + 1);
+                    else if (tile + (int)gridDim.x < ntiles) load_e(tile + gridDim.x, 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint4 hv = lds128(stg + (uint32_t)(lane * 80 + k * 16));
+                        const uint4 hv = lds128(stage_addr(buf0, lane, k));
                         const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
                         float hf[8];
 #pragma unroll
@@ -391,37 +439,31 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                             v[j + 3] = valid ? fmaf(a0.w, __uint_as_float(r[j + 3]), fmaf(-a2.w, hf[t4 * 4 + 3], ak.w)) : 0.f;
                         }
                     }
-                }
-                stage_col_sums<EPI == TC_FWD>(stg, v, lane, acc0 + 2 * c, acc1 + 2 * c);
-                uint32_t pk[16];
-                if (EPI == TC_FWD) {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const __half2 h2 = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-                        pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                    stage_store_rows(stg, pk, lane, (uint16_t*)g.out + (size_t)row0 * 256 + col0, rows_left);
-                }
-                if (EPI == TC_DGRAD || g.out2) {
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
                         const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
                         pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
                     }
-                    uint16_t* dst = EPI == TC_DGRAD ? (uint16_t*)g.out : (uint16_t*)g.out2;
-                    stage_store_rows(stg, pk, lane, dst + (size_t)row0 * 256 + col0, rows_left);
+                    if (lane == 0) tma_store_wait_read<0>();      // buf1's previous store has been read out
+                    __syncwarp();
+                    stage_put_row(buf1, pk, lane);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmO, buf1, col0, row0);
+                    stage_col_sums<false, false>(buf1, lane, acc0 + 2 * c, acc1 + 2 * c);
                 }
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (lane == 0) tma_store_wait_all();
         if (lane < 16) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int hc = 0; hc < 2; ++hc) {
-                    const int col = (half * 4 + c) * 32 + hc * 16 + lane;
-                    atomicAdd(g.stat0 + col, acc0[2 * c + hc]);
-                    if (EPI == TC_FWD) atomicAdd(g.stat1 + col, acc1[2 * c + hc]);
+                for (int j = 0; j < 2; ++j) {
+                    const int col = (half * 4 + c) * 32 + 2 * lane + j;
+                    atomicAdd(g.stat0 + col, acc0[2 * c + j]);
+                    if (EPI == TC_FWD) atomicAdd(g.stat1 + col, acc1[2 * c + j]);
                 }
         }
     }
@@ -617,16 +659,18 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D map over a row-major 16-bit matrix [rows][ld] exposing `cols` columns; box = box_rows x 64 columns, SWIZZLE_128B
-int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int ld, int box_rows) {
+// 2-D map over a row-major 16-bit matrix [rows][ld] exposing `cols` columns; box = box_rows x box_cols columns with the
+// swizzle that matches a box row (64 columns = 128 B -> SWIZZLE_128B, 32 columns = 64 B -> SWIZZLE_64B)
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols = 64) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { pcn_set_error("cuTensorMapEncodeTiled is not available from this driver"); return PCNERF_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { pcn_set_error("cuTensorMapEncodeTiled failed (%d) for [%lld][%d] ld %d", (int)r, (long long)rows, cols, ld); return PCNERF_ERR_CUDA; }
     return 0;
@@ -655,22 +699,27 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     rc = make_map(&mB, B, 256, k0 + k1, ldb, 256);
     if (rc) return rc;
+    CUtensorMap mO, mO2;
+    rc = make_map(&mO, out, rows, 256, 256, 32, 32);
+    if (rc) return rc;
+    rc = make_map(&mO2, out2 ? (void*)out2 : out, rows, 256, 256, 32, 32);
+    if (rc) return rc;
     RowGemmArgs g;
     g.rows = (int)rows; g.kb0 = k0 / 64; g.kb_total = (k0 + k1) / 64;
-    g.nstage = g.kb_total >= 5 ? 2 : 4;
+    g.nstage = g.kb_total >= 5 ? 2 : (mode == TC_FWD ? 4 : 3);
     g.out = out; g.out2 = out2; g.vec = vec; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
-    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * TC_STAGE_BYTES;
+    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * TC_NBUF * TC_STAGE_BYTES;
     const int ntiles = (int)pcn_cdiv(rows, 128);
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
     const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
     if (mode == TC_FWD) {
         PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PcnScope ps(PCN_K_GEMM_FWD, st, flops);
-        k_tc_rowgemm<TC_FWD><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB, g);
+        k_tc_rowgemm<TC_FWD><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB, mO, mO2, g);
     } else {
         PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<TC_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PcnScope ps(PCN_K_GEMM_DGRAD, st, flops);
-        k_tc_rowgemm<TC_DGRAD><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB, g);
+        k_tc_rowgemm<TC_DGRAD><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB, mO, mO2, g);
     }
     PCN_LAUNCH_CHECK();
     return 0;
