@@ -278,11 +278,26 @@ def run_b200(a):
         except (OSError, ValueError):
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-        roofline = {"kernel": "mlp_gemm (fwd+dgrad+wgrad, %s)" % a.precision, "bound": "tensor", "achieved": achieved,
-                    "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                    "share_of_step": g_ms / max(sum(v[0] for v in prof.values()), 1e-9)}
+        # dominant kernel = the forward row GEMM (k_tc_rowgemm<FWD> / k_gemm<fwd>): FLOPs per launch / mean launch time
+        f_ms, f_n, f_fl = prof["mlp_gemm_fwd"]
+        achieved = f_fl / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if a.precision == "tc" and CHUNK == tr["rows"]:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]      # one ncu --set full capture, per launch
+        except (OSError, ValueError, KeyError):
+            pass
+        all_ms = max(sum(v[0] for v in prof.values()), 1e-9)
+        roofline = {"kernel": "mlp forward row GEMM (%s)" % ("k_tc_rowgemm<FWD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32"),
+                    "bound": "tensor", "achieved": achieved, "peak": peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "launches_per_step": f_n / psteps, "us_per_launch": 1e3 * f_ms / max(f_n, 1),
+                    "gflop_per_launch": f_fl / max(f_n, 1) / 1e9, "share_of_step": f_ms / all_ms,
+                    "all_mlp_gemms": {"achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
+                                      "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms > 0 else 0.0,
+                                      "share_of_step": g_ms / all_ms}}
 
     out = {"metric": METRIC, "value": rays_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",

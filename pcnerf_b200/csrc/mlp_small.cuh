@@ -169,17 +169,30 @@ __global__ void __launch_bounds__(256) k_out_bwd_reduce(const float* __restrict_
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * STRIP;
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sg = 0.f;
-    for (int k = w; k < STRIP; k += 8) {
-        const int64_t r = r0 + k;
-        if (r >= rows) break;
-        const float pv = p[r];
-        const float gr = grad_p[r] * pv * (1.f - pv);
-        float hv[8];
-        ld8<TH>(H + r * 256 + lane * 8, hv);
+    // warp w owns rows r0 + w*8 .. + 7; four independent row loads in flight per lane
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = fmaf(gr, hv[i], a[i]);
-        sg += gr;
-        if (lane == 0) gvec[r] = gr;
+    for (int b = 0; b < STRIP / 8; b += 4) {
+        float hv[4][8], gr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + w * (STRIP / 8) + b + u;
+            gr[u] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hv[u][i] = 0.f;
+            if (r < rows) {
+                const float pv = p[r];
+                gr[u] = grad_p[r] * pv * (1.f - pv);
+                ld8<TH>(H + r * 256 + lane * 8, hv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + w * (STRIP / 8) + b + u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(gr[u], hv[u][i], a[i]);
+            sg += gr[u];
+            if (lane == 0 && r < rows) gvec[r] = gr[u];
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = a[i];
@@ -237,24 +250,37 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
         const int j = lane * 8 + i;
         c0[i] = coef[j]; c1[i] = coef[256 + j]; c2[i] = coef[512 + j]; mean[i] = stats[j]; cs[i] = 0.f;
     }
-    for (int k = w; k < STRIP; k += 8) {
-        const int64_t r = r0 + k;
-        if (r >= rows) break;
-        float hv[8], up[8], dh[8];
-        ld8<TH>(H + r * 256 + lane * 8, hv);
-        if (LAST) {
-            const float gr = gvec[r];
+    // warp w owns rows r0 + w*8 .. + 7; four independent row loads in flight per lane
 #pragma unroll
-            for (int i = 0; i < 8; ++i) up[i] = gr;
-        } else {
-            ld8<TG>(G + r * 256 + lane * 8, up);
+    for (int b = 0; b < STRIP / 8; b += 4) {
+        float hv[4][8], up[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + w * (STRIP / 8) + b + u;
+            if (r < rows) {
+                ld8<TH>(H + r * 256 + lane * 8, hv[u]);
+                if (LAST) {
+                    const float gr = gvec[r];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) up[u][i] = gr;
+                } else {
+                    ld8<TG>(G + r * 256 + lane * 8, up[u]);
+                }
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dh[i] = up[i] * c0[i] - c1[i] - (hv[i] - mean[i]) * c2[i];
-            cs[i] += dh[i];
+        for (int u = 0; u < 4; ++u) {
+            const int64_t r = r0 + w * (STRIP / 8) + b + u;
+            if (r < rows) {
+                float dh[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    dh[i] = up[u][i] * c0[i] - c1[i] - (hv[u][i] - mean[i]) * c2[i];
+                    cs[i] += dh[i];
+                }
+                st8(G + r * 256 + lane * 8, dh);
+            }
         }
-        st8(G + r * 256 + lane * 8, dh);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = cs[i];
