@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PCNERF_PRECISION", "tc"), choices=["fp32", "tc"],
+    ap.add_argument("--precision", default=os.environ.get("PCNERF_PRECISION", "tc"), choices=["fp32", "tc", "affine"],
                     help="MLP engine: tc = TMA + tcgen05 + TMEM (fp16 operands forward, bf16 gradients, fp32 "
                          "accumulation; 1e-3 parity gate), fp32 = CUDA-core SGEMM (1e-5 gate)")
     ap.add_argument("--rays", type=int, default=32768, help="rays per GPU per step")
@@ -301,7 +301,7 @@ def run_b200(a):
 
     out = {"metric": METRIC, "value": rays_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f16 fwd / bf16 bwd operands, f32 accumulate", "data": "synthetic",
+           "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16 fwd / bf16 bwd operands, f32 accumulate", "affine": "f32 data kernels, f64 closed-form algebra"}[a.precision], "data": "synthetic",
            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "N_samples": S, "N_importance": NI, "chunk": CHUNK,
                       "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam(fused)",
                       "parallelism": "dp%d (rays sharded, one flat NCCL all-reduce of 3.98 MB grads)" % world,

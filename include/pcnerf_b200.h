@@ -174,6 +174,21 @@ int pcnerf_mlp_backward(const pcnerf_mlp_params* h_params, const pcnerf_mlp_grad
                         int64_t rows, const float* out_p, const float* grad_p, void* saved, size_t saved_bytes,
                         void* scratch, size_t scratch_bytes, void* stream);
 
+/* K3' closed form ("affine" mode): for one BatchNorm batch the logit of the network AS THE REFERENCE BUILDS IT (identity
+ * activations, models.py:152,172) is exactly alpha . x + c, with (alpha, c) a function of the parameters and of the
+ * batch's first two moments.  These are the three data-sized kernels; the parameter-sized algebra lives in the host
+ * mirror.  enc (rows,64) f32; chunks are consecutive ranges of `chunk` rows (nchunk = ceil(rows/chunk)).
+ * pcnerf_affine_moments: out_part [nchunk][P][65][64] f64, P = pcnerf_affine_parts(): partial sums over the chunk's rows
+ *   of (x-s)(x-s)^T (rows 0..63) and (x-s) (row 64), s = the chunk's first row.
+ * pcnerf_affine_apply: out_p[r] = sigmoid(alpha[chunk(r)] . x_r + c[chunk(r)]); alpha (nchunk,64), c (nchunk) f32.
+ * pcnerf_affine_grad: out_part [nchunk][P][65] f64: partial sums of g_r x_r (0..63) and g_r (64), g = grad_p * p (1-p). */
+int pcnerf_affine_parts(void);
+int pcnerf_affine_moments(const float* enc, int64_t rows, int64_t chunk, double* out_part, void* stream);
+int pcnerf_affine_apply(const float* enc, int64_t rows, int64_t chunk, const float* alpha, const float* c, float* out_p,
+                        void* stream);
+int pcnerf_affine_grad(const float* enc, const float* p, const float* grad_p, int64_t rows, int64_t chunk,
+                       double* out_part, void* stream);
+
 /* Building blocks of the precision-1 path (TMA + tcgen05 + TMEM), exported for unit tests and reuse.
  * pcnerf_tc_rowgemm: C[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T, k0, k1 multiples of 64, k0 + k1 <= 320.
  *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 = bf16 copy or NULL;

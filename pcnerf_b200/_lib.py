@@ -50,6 +50,10 @@ SIGNATURES = {
     "pcnerf_mlp_scratch_bytes": (sz, [i64, ci]),
     "pcnerf_mlp_forward": (ci, [ctypes.POINTER(MlpParams), vp, i64, vp, vp, sz, vp, sz, vp]),
     "pcnerf_mlp_backward": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, i64, vp, vp, vp, sz, vp, sz, vp]),
+    "pcnerf_affine_parts": (ci, []),
+    "pcnerf_affine_moments": (ci, [vp, i64, i64, vp, vp]),
+    "pcnerf_affine_apply": (ci, [vp, i64, i64, vp, vp, vp, vp]),
+    "pcnerf_affine_grad": (ci, [vp, vp, vp, i64, i64, vp, vp]),
     "pcnerf_tc_rowgemm": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, i64, vp, vp, vp, vp]),
     "pcnerf_tc_wgrad": (ci, [vp, vp, ci, ci, ci, i64, vp, ci, ci, vp]),
     "pcnerf_tc_last_fault": (ci, []),

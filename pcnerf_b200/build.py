@@ -23,6 +23,7 @@ SOURCES = {
     "search.cu": [],
     "mlp.cu": [],
     "mlp_tc.cu": [],
+    "affine.cu": [],
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
           "-Xcompiler", "-fPIC"]

@@ -41,7 +41,7 @@ void pcn_set_error(const char* fmt, ...);
 // kernel classes of the built-in profiler (pcnerf_prof_*); `work` is algorithmic FLOPs (GEMMs) or bytes (the rest)
 enum {
     PCN_K_GEMM_FWD = 0, PCN_K_GEMM_DGRAD, PCN_K_GEMM_WGRAD, PCN_K_MLP_SMALL, PCN_K_SAMPLE_ENCODE, PCN_K_COMPOSITE_FWD,
-    PCN_K_COMPOSITE_BWD, PCN_K_AABB, PCN_K_SEARCH, PCN_K_COUNT
+    PCN_K_COMPOSITE_BWD, PCN_K_AABB, PCN_K_SEARCH, PCN_K_AFFINE, PCN_K_COUNT
 };
 
 // Counts kernel launches (always) and, when pcnerf_prof_enable(1) is active, brackets them with CUDA events on the

@@ -14,12 +14,14 @@ import torch.nn as nn
 from ... import ops
 
 _DEFAULT_PRECISION = {"value": 0}
-_PREC = {"fp32": 0, "tc": 1, "bf16": 1, "f16": 1, 0: 0, 1: 1}
+_PREC = {"fp32": 0, "tc": 1, "bf16": 1, "f16": 1, "affine": 2, 0: 0, 1: 1, 2: 2}
 
 
 def set_default_mlp_precision(p):
     """'fp32' (CUDA-core GEMM, 1e-5 parity gate) or 'tc' (tcgen05 tensor-core GEMM: fp16 operands forward, bf16
-    gradients, fp32 accumulation; 1e-3 gate).  'bf16' is accepted as an alias of 'tc' (BASELINE.json's name)."""
+    gradients, fp32 accumulation; 1e-3 gate).  'bf16' is accepted as an alias of 'tc' (BASELINE.json's name).
+    'affine': the closed form of the network as the reference builds it (identity activations): per BN batch the logit
+    is exactly alpha . x + c (csrc/affine.cu); opt-in fast mode, gated at 1e-5 like 'fp32'."""
     _DEFAULT_PRECISION["value"] = _PREC[p]
 
 
@@ -106,6 +108,70 @@ class NOF(nn.Module):
     def mlp_precision(self):
         return _DEFAULT_PRECISION["value"] if self.precision is None else _PREC[self.precision]
 
+    # ---- closed form ("affine" mode): parameter-sized algebra in float64, batched over the BN chunks
+    def _affine_coeffs(self, m, C, cnt):
+        """(m (nc,64), C (nc,64,64), cnt (nc,)) float64 batch moments of the encodings -> alpha (nc,64), c (nc,) such that
+        logit = alpha . x + c reproduces Linear->BN x8 ->Linear of models.py:183-203 with train-mode batch statistics
+        (m is None: eval mode, running statistics).  Updates the BN running statistics in train mode."""
+        lins, bns = self._linears(), self._bns()
+        f64 = torch.float64
+        train = m is not None
+        if train:
+            m63, C63 = m[:, :63], C[:, :63, :63]
+            nc = m.shape[0]
+        else:
+            nc = 1
+        A = d = None
+        eps, mom = bns[0].eps, bns[0].momentum
+        for l in range(8):
+            W, b = lins[l].weight.to(f64), lins[l].bias.to(f64)
+            if l == 0:
+                A, d = W.unsqueeze(0).expand(nc, -1, -1), b.unsqueeze(0).expand(nc, -1)
+            elif l == 4:
+                A = W[:, :63].unsqueeze(0) + torch.matmul(W[:, 63:], Ab)
+                d = torch.matmul(db, W[:, 63:].t()) + b
+            else:
+                A = torch.matmul(W, Ab)
+                d = torch.matmul(db, W.t()) + b
+            bn = bns[l]
+            if train:
+                mean = torch.matmul(A, m63.unsqueeze(-1)).squeeze(-1) + d
+                var = (torch.matmul(A, C63) * A).sum(-1).clamp_min(0.0)
+                with torch.no_grad():
+                    # one running-statistics update per chunk, in chunk order (momentum recurrence in closed form)
+                    k = torch.arange(nc - 1, -1, -1, device=mean.device, dtype=f64)
+                    wts = mom * (1.0 - mom) ** k
+                    unb = var * (cnt / (cnt - 1.0)).unsqueeze(-1)
+                    keep = (1.0 - mom) ** nc
+                    bn.running_mean.copy_((keep * bn.running_mean.to(f64) + (wts[:, None] * mean).sum(0)).to(bn.running_mean.dtype))
+                    bn.running_var.copy_((keep * bn.running_var.to(f64) + (wts[:, None] * unb).sum(0)).to(bn.running_var.dtype))
+                    bn.num_batches_tracked += nc
+            else:
+                mean = bn.running_mean.to(f64).unsqueeze(0)
+                var = bn.running_var.to(f64).unsqueeze(0)
+            a = bn.weight.to(f64) / torch.sqrt(var + eps)
+            s_ = bn.bias.to(f64) - mean * a
+            Ab = a.unsqueeze(-1) * A
+            db = a * d + s_
+        wo, bo = self.occ_out[0].weight.to(f64)[0], self.occ_out[0].bias.to(f64)[0]
+        alpha = torch.matmul(wo.unsqueeze(0).unsqueeze(0), Ab).squeeze(1)            # (nc,63)
+        c = (db * wo).sum(-1) + bo
+        alpha = torch.nn.functional.pad(alpha, (0, 1))
+        return alpha, c
+
+    def _forward_affine(self, enc, chunk):
+        rows = enc.shape[0]
+        if self.training:
+            last = rows - (-(-rows // chunk) - 1) * chunk
+            if last == 1 or chunk == 1:
+                raise ValueError("Expected more than 1 value per channel when training, got input size [1, 256]")
+            with torch.no_grad():
+                m, C, cnt = ops.affine_moments(enc, chunk)
+            alpha, c = self._affine_coeffs(m, C, cnt)
+            return ops.AffineApplyFunction.apply(enc, alpha.to(torch.float32), c.to(torch.float32), chunk)
+        alpha, c = self._affine_coeffs(None, None, None)
+        return ops.AffineApplyFunction.apply(enc, alpha.to(torch.float32), c.to(torch.float32), rows)
+
     def forward_encoded(self, enc, chunk=None):
         """enc: (rows, 64) encodings padded with a zero column (fp32, or fp16 for the tensor-core path).
         One BN batch per `chunk` rows.  Returns p_occ (rows,)."""
@@ -116,6 +182,8 @@ class NOF(nn.Module):
             enc = enc.to(want)
         rows = enc.shape[0]
         chunk = rows if chunk is None else int(chunk)
+        if prec == 2:
+            return self._forward_affine(enc.contiguous(), max(chunk, 1))
         return ops.MLPFunction.apply(enc.contiguous(), max(chunk, 1), self.training, prec, self._buffers3(),
                                      *self.kernel_params())
 

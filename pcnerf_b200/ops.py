@@ -363,6 +363,54 @@ class MLPFunction(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(views)
 
 
+# ------------------------------------------------------------------------------------ K3' closed-form ("affine") MLP
+
+
+def affine_moments(enc, chunk):
+    """Per-chunk first and second moments of the (rows,64) fp32 encodings.
+    Returns (m (nc,64) f64, C (nc,64,64) f64 covariance, counts (nc,) f64)."""
+    enc = _cuda_f32(enc, "enc")
+    rows = enc.shape[0]
+    nc = -(-rows // chunk)
+    P = lib().pcnerf_affine_parts()
+    part = torch.empty((nc, P, 65, 64), dtype=torch.float64, device=enc.device)
+    check(lib().pcnerf_affine_moments(_p(enc), rows, int(chunk), _p(part), _stream()))
+    tot = part.sum(1)
+    cnt = torch.full((nc,), float(chunk), dtype=torch.float64, device=enc.device)
+    cnt[-1] = float(rows - (nc - 1) * chunk)
+    shift = enc[::chunk].to(torch.float64)
+    m1 = tot[:, 64, :] / cnt[:, None]
+    C = tot[:, :64, :] / cnt[:, None, None] - m1[:, :, None] * m1[:, None, :]
+    return shift + m1, C, cnt
+
+
+class AffineApplyFunction(torch.autograd.Function):
+    """p_r = sigmoid(alpha[chunk(r)] . x_r + c[chunk(r)]); backward returns sum_r g_r x_r and sum_r g_r per chunk."""
+
+    @staticmethod
+    def forward(ctx, enc, alpha, c, chunk):
+        enc = _cuda_f32(enc, "enc")
+        alpha = _cuda_f32(alpha, "alpha")
+        c = _cuda_f32(c, "c")
+        rows = enc.shape[0]
+        p = torch.empty(rows, dtype=torch.float32, device=enc.device)
+        check(lib().pcnerf_affine_apply(_p(enc), rows, int(chunk), _p(alpha), _p(c), _p(p), _stream()))
+        ctx.save_for_backward(enc, p)
+        ctx.chunk = int(chunk)
+        ctx.nc = alpha.shape[0]
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        enc, p = ctx.saved_tensors
+        gp = gp.contiguous()
+        P = lib().pcnerf_affine_parts()
+        part = torch.empty((ctx.nc, P, 65), dtype=torch.float64, device=enc.device)
+        check(lib().pcnerf_affine_grad(_p(enc), _p(p), _p(gp), enc.shape[0], ctx.chunk, _p(part), _stream()))
+        g = part.sum(1)
+        return None, g[:, :64].to(torch.float32), g[:, 64].to(torch.float32), None
+
+
 # -------------------------------------------------------------------------------------------- K4 composite + losses
 
 

@@ -1,0 +1,130 @@
+"""GPU: the closed-form ("affine") MLP mode -- csrc/affine.cu + the float64 parameter-sized algebra in
+nof/networks/models.py.  It is exact algebra for the network as the reference builds it (identity activations), so it
+is held to the fp32 gate: p / depth / losses 1e-5-class tolerances against the oracle and the reference fixtures,
+parameter gradients 1e-4 of each tensor's scale."""
+import numpy as np
+import pytest
+import torch
+
+import pcnerf_oracle as orc
+from conftest import golden
+from gpu_util import assert_grads_match, dev, make_nets
+
+pytestmark = pytest.mark.gpu
+
+
+def _enc(rows, seed, spread=60.0):
+    gen = torch.Generator().manual_seed(seed)
+    x = (torch.rand(rows, 3, generator=gen) - 0.5) * spread
+    return orc.embedding(x)
+
+
+def test_moments_kernel_vs_float64():
+    from pcnerf_b200 import ops
+    enc = torch.nn.functional.pad(_enc(10000, 1), (0, 1))
+    m, C, cnt = ops.affine_moments(enc.to(dev()), 4096)
+    e = enc.double()
+    for k, i in enumerate(range(0, 10000, 4096)):
+        blk = e[i:i + 4096]
+        mr = blk.mean(0)
+        Cr = blk.t() @ blk / blk.shape[0] - mr[:, None] * mr[None, :]
+        assert float(cnt[k]) == blk.shape[0]
+        np.testing.assert_allclose(m[k].cpu().numpy(), mr.numpy(), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(C[k].cpu().numpy(), Cr.numpy(), rtol=0, atol=1e-7 * float(Cr.abs().max()))
+
+
+@pytest.mark.parametrize("rows,chunk", [(4096, 4096), (5000, 2048), (130, 130), (70000, 16384)])
+def test_forward_train_and_running_stats(rows, chunk):
+    enc = _enc(rows, rows)
+    sd = orc.init_state_dict(42)
+    p_ref = torch.cat([orc.nof_forward(sd, enc[i:i + chunk], True) for i in range(0, rows, chunk)]).reshape(-1)
+    mc, _, _ = make_nets(42, 43, True, "affine")
+    p = mc.forward_encoded(torch.nn.functional.pad(enc, (0, 1)).to(dev()), chunk)
+    np.testing.assert_allclose(p.detach().cpu().numpy(), p_ref.numpy(), rtol=2e-5, atol=1e-7)
+    got = mc.state_dict()
+    for k in ("layer1.1.running_mean", "layer1.1.running_var", "layer2.1.running_mean", "layer2.7.running_mean",
+              "layer2.7.running_var"):
+        np.testing.assert_allclose(got[k].cpu().numpy(), sd[k].numpy(), rtol=2e-5, atol=1e-6, err_msg=k)
+    assert int(got["layer2.7.num_batches_tracked"]) == int(sd["layer2.7.num_batches_tracked"])
+
+
+def test_forward_eval_and_errors():
+    enc = _enc(3000, 7)
+    sd = orc.init_state_dict(42)
+    p_ref = orc.nof_forward(sd, enc, False).reshape(-1)
+    mc, _, _ = make_nets(42, 43, False, "affine")
+    with torch.no_grad():
+        p = mc(enc.to(dev())).reshape(-1)
+    np.testing.assert_allclose(p.cpu().numpy(), p_ref.numpy(), rtol=2e-5, atol=1e-7)
+    mc.train()
+    with pytest.raises(ValueError):
+        mc(torch.zeros(1, 63, device=dev()))
+
+
+@pytest.mark.parametrize("rows,chunk", [(4096, 4096), (3000, 1024)])
+def test_backward_param_grads(rows, chunk):
+    enc = _enc(rows, rows + 1)
+    gen = torch.Generator().manual_seed(rows)
+    gp = torch.randn(rows, generator=gen)
+    sd = orc.init_state_dict(42)
+    for k in orc.param_names():
+        sd[k].requires_grad_(True)
+    p_ref = torch.cat([orc.nof_forward(sd, enc[i:i + chunk], True) for i in range(0, rows, chunk)]).reshape(-1)
+    (p_ref * gp).sum().backward()
+    mc, _, _ = make_nets(42, 43, True, "affine")
+    p = mc.forward_encoded(torch.nn.functional.pad(enc, (0, 1)).to(dev()), chunk)
+    (p * gp.to(dev())).sum().backward()
+    scale = max(float(sd[k].grad.abs().max()) for k in orc.param_names())
+    for k, prm in mc.named_parameters():
+        ref = sd[k].grad.numpy()
+        atol = 1e-4 * np.abs(ref).max() + 1e-12
+        if k.endswith(".bias") and k.split(".")[0] in ("layer1", "layer2") and k != "layer2.7.bias":
+            atol = 1e-5 * scale          # exactly zero in exact arithmetic: the reference's value is rounding noise
+        np.testing.assert_allclose(prm.grad.cpu().numpy(), ref, rtol=1e-4, atol=atol, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["train_seg", "train_perturb", "train_plain"])
+def test_render_rays_train_vs_reference(name):
+    """Same gates as tests/test_gpu_render.py::_train for the fp32 engine (coarse 3e-5, fine end-to-end 2e-3)."""
+    from pcnerf_b200.nof import render
+    g = golden(name)
+    rays = torch.from_numpy(g["rays"]).to(dev())
+    perturb = float(g["perturb"])
+    mc, mf, emb = make_nets(42, 43, True, "affine")
+    kw = {}
+    if perturb > 0:
+        kw = dict(U=torch.from_numpy(g["U"]).to(dev()), u=torch.from_numpy(g["u"]).to(dev()))
+    res = render.render_rays_train(mc, mf, emb, rays, N_samples=int(g["S"]), N_importance=int(g["Ni"]), perturb=perturb,
+                                   noise_std=0, chunk=int(g["chunk"]), issegmentated=int(g["issegmentated"]),
+                                   childnerf_ratio=float(g["ratio"]), use_child_nerf_divide=0,
+                                   use_child_nerf_loss=int(g["use_child"]), **kw)
+    for k in ("depth", "child_free_loss", "child_depth_loss"):
+        np.testing.assert_allclose(res[k].detach().cpu().numpy(), g["out_" + k], rtol=3e-5, atol=1e-6, err_msg=k)
+    for k in ("depth_fine", "child_free_loss_fine", "child_depth_loss_fine"):
+        np.testing.assert_allclose(res[k].detach().cpu().numpy(), g["out_" + k], rtol=2e-3, atol=1e-6, err_msg=k)
+    gt = rays[:, 14]
+    lam = g["lam"]
+    sl1 = torch.nn.SmoothL1Loss(reduction="mean")
+    loss = 0.1 * lam[0] * sl1(10 * res["depth"], 10 * gt) + 0.1 * lam[0] * sl1(10 * res["depth_fine"], 10 * gt)
+    for k, l in (("child_free_loss_fine", lam[1]), ("child_free_loss", lam[1]), ("child_depth_loss_fine", lam[2]),
+                 ("child_depth_loss", lam[2])):
+        loss = loss + float(l) * res[k].to(loss.device)
+    loss.backward()
+    assert_grads_match("c", mc, g, 2e-3)
+    assert_grads_match("f", mf, g, 1e-2)
+
+
+def test_view_two_step_flags_bit_exact():
+    from pcnerf_b200.nof import render
+    for m in (2, 1):
+        g = golden("view_m%d" % m)
+        rays, other = torch.from_numpy(g["rays"]).to(dev()), torch.from_numpy(g["other"]).to(dev())
+        mc, mf, emb = make_nets(42, 43, False, "affine")
+        with torch.no_grad():
+            r = render.render_rays_view_0525_2_2(mc, mf, emb, rays, other, N_samples=int(g["S"]),
+                                                 N_importance=int(g["Ni"]), perturb=0, noise_std=0,
+                                                 chunk=int(g["chunk"]), depth_inference_method=m)
+        assert np.array_equal(r["rays_effective_flag"].cpu().numpy(), g["out_rays_effective_flag"])
+        assert np.array_equal(r["rays_effective_flag_fine"].cpu().numpy(), g["out_rays_effective_flag_fine"])
+        for k in ("depth", "depth_fine", "points_inference", "points_inference_fine"):
+            np.testing.assert_allclose(r[k].cpu().numpy(), g["out_" + k], rtol=5e-5, atol=1e-6, err_msg=k)
