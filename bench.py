@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay each step as one CUDA graph (pcnerf_b200.graphed.GraphedStep); auto = fall back to eager "
+                         "launches if capture fails")
     return ap.parse_args()
 
 
@@ -200,17 +203,16 @@ def run_b200(a):
     emb = Embedding(3, 10)
     params = list(mc.parameters()) + list(mf.parameters())
     bucket = parallel.GradBucket(params)
-    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, weight_decay=1e-3, fused=True)
+    use_graph = a.graph != "off"
+    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, weight_decay=1e-3, fused=True, capturable=use_graph)
     sl1 = torch.nn.SmoothL1Loss(reduction="mean")
     dscale = parallel.depth_loss_scale()
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    staged = [torch.empty_like(r) for r in resident]          # device landing buffers of the e2e graph
 
-    def step(from_host):
-        if from_host:
-            d_, r_, p_ = [h.to(dev, non_blocking=True) for h in host]
-        else:
-            d_, r_, p_ = resident
-        rays, _ = ops.aabb_pack_train(606, origin, d_, r_, p_, centres, boxes, boxes_big, scene.parent, 0.05, 10)
+    def core(d_, r_, p_, compact):
+        rays, keep = ops.aabb_pack_train(606, origin, d_, r_, p_, centres, boxes, boxes_big, scene.parent, 0.05, 10,
+                                         compact=compact)
         res = render.render_rays_train(mc, mf, emb, rays, N_samples=S, N_importance=NI, perturb=1.0, noise_std=0,
                                        chunk=CHUNK, issegmentated=1, childnerf_ratio=0.1, use_child_nerf_divide=0,
                                        use_child_nerf_loss=1)
@@ -222,10 +224,58 @@ def run_b200(a):
         loss.backward()
         bucket.allreduce_mean()
         opt.step()
+        return loss.detach().reshape(1), rays.shape[0], keep
+
+    def step(from_host):
+        """One eager step (every kernel launched from the host)."""
         if from_host:
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            d_, r_, p_ = [h.to(dev, non_blocking=True) for h in host]
+        else:
+            d_, r_, p_ = resident
+        loss, nrays, _ = core(d_, r_, p_, True)
+        if from_host:
+            loss_host.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
-        return rays.shape[0]
+        return nrays
+
+    graphs = {}
+    graph_note = "off"
+    if use_graph:
+        try:
+            from pcnerf_b200.graphed import GraphedStep
+            _, _, keep = core(*resident, True)
+            if not bool(keep.all()):
+                raise RuntimeError("the AABB stage drops rays of this batch: data-dependent shape, not capturable")
+            ops.launch_count(reset=True)
+
+            def g_resident():
+                core(*resident, False)
+
+            def g_host():
+                for s_, h_ in zip(staged, host):
+                    s_.copy_(h_, non_blocking=True)
+                loss, _, _ = core(*staged, False)
+                loss_host.copy_(loss, non_blocking=True)
+
+            graphs["resident"] = GraphedStep(g_resident, warmup=2)
+            graphs["host"] = GraphedStep(g_host, warmup=1)
+            graph_note = "on"
+        except Exception as exc:                               # noqa: BLE001 - any capture failure -> eager launches
+            if a.graph == "on":
+                raise
+            sys.stderr.write("bench.py: CUDA-graph capture failed (%s: %s); falling back to eager launches\n"
+                             % (type(exc).__name__, exc))
+            graphs = {}
+            graph_note = "capture failed, eager"
+            torch.cuda.synchronize()
+
+    def run(from_host):
+        if graphs:
+            graphs["host" if from_host else "resident"]()
+            if from_host:
+                torch.cuda.current_stream().synchronize()
+            return n
+        return step(from_host)
 
     def barrier():
         if world > 1:
@@ -239,7 +289,7 @@ def run_b200(a):
         e0.record()
         rays_done = 0
         for _ in range(steps):
-            rays_done += step(from_host)
+            rays_done += run(from_host)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -249,12 +299,17 @@ def run_b200(a):
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         return float(ms.item()), float(tot.item()), ops.launch_count()
 
+    # kernels launched by one step (a graph replay re-issues exactly the launches recorded at capture)
+    ops.launch_count(reset=True)
+    step(False)
+    launches_per_step = ops.launch_count()
     for _ in range(max(a.warmup, 3)):
-        step(False)
-    step(True)
+        run(False)
+    run(True)
     clocks = ClockSampler(local)
     clocks.start()
-    ms, rays_total, launches = timed(False, a.steps)
+    ms, rays_total, _ = timed(False, a.steps)
+    launches = launches_per_step * a.steps
     ms_e2e, rays_e2e, _ = timed(True, a.steps)
     clk = clocks.stop()
 
@@ -303,7 +358,7 @@ def run_b200(a):
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16 fwd / bf16 bwd operands, f32 accumulate", "affine": "f32 data kernels, f64 closed-form algebra"}[a.precision], "data": "synthetic",
            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "N_samples": S, "N_importance": NI, "chunk": CHUNK,
-                      "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam(fused)",
+                      "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam(fused)", "cuda_graph": graph_note,
                       "parallelism": "dp%d (rays sharded, one flat NCCL all-reduce of 3.98 MB grads)" % world,
                       "l2": "per-step working set (>2 GB encodings, >30 GB activations) exceeds the 126 MB L2"},
            "clocks": clk,

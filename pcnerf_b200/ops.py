@@ -140,8 +140,11 @@ def aabb_find_box(centres, boxes, points, knn=10):
     return out
 
 
-def aabb_pack_train(variant, ray_o, ray_d, dist, points, centres, boxes, boxes_bigger, parent, surface_expand, knn=10):
-    """parent = (x_min, x_max, y_min, y_max, z_min, z_max).  Returns (rays (N,15) f32, keep mask) compacted in order."""
+def aabb_pack_train(variant, ray_o, ray_d, dist, points, centres, boxes, boxes_bigger, parent, surface_expand, knn=10,
+                    compact=True):
+    """parent = (x_min, x_max, y_min, y_max, z_min, z_max).  Returns (rays (N,15) f32, keep mask) compacted in order.
+    compact=False returns all N rows (rows with keep == 0 are undefined): no data-dependent shape, so the call can be
+    captured in a CUDA graph when the caller knows every ray is kept."""
     o, d = _rays_od(ray_o, ray_d)
     dist = _f64(dist).reshape(-1)
     pts = _f64(points).reshape(-1, 3)
@@ -155,7 +158,7 @@ def aabb_pack_train(variant, ray_o, ray_d, dist, points, centres, boxes, boxes_b
                                        hp, float(surface_expand), int(knn), _p(rays), _p(keep), _stream()))
     _count()
     keep = keep.bool()
-    return rays[keep], keep
+    return (rays[keep] if compact else rays), keep
 
 
 def aabb_build_groups(ray_o, ray_d, dist, boxes, boxes_larger, parent_min, parent_max, depth_inference_method=2,
