@@ -182,7 +182,16 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
 
     n = a.rays
-    scene, pts, dirs, dist_v = make_inputs(rank, n)
+    # Synthetic returns: draw 3 % more than needed and keep the first n that the AABB stage itself accepts (a fraction of a
+    # percent of random points misses every child box and would be dropped, ipb2dmapping.py:372-376), so that every timed
+    # step packs exactly n rays -- a fixed shape, which is what makes the step capturable as one CUDA graph.
+    scene, pts, dirs, dist_v = make_inputs(rank, n + n // 32 + 64)
+    _, keep0 = ops.aabb_pack_train(606, scene.origin, dirs, dist_v, pts, scene.centres, scene.child_bounds,
+                                   scene.child_bounds_bigger, scene.parent, 0.05, 10, compact=False)
+    sel = np.nonzero(keep0.cpu().numpy())[0][:n]
+    if sel.shape[0] < n:
+        raise SystemExit("synthetic scene produced only %d usable returns" % sel.shape[0])
+    pts, dirs, dist_v = pts[sel], dirs[sel], dist_v[sel]
     # scene constants live on the device; the per-step inputs (the LiDAR returns of this batch) exist twice:
     # pinned host buffers (e2e) and device-resident copies (value)
     f64 = dict(dtype=torch.float64, device=dev)

@@ -18,7 +18,7 @@
 
 #define AFF_PARTS 16            // CTAs (partial results) per chunk
 #define AFF_SUB 32              // rows per shared-memory sub-tile
-#define AFF_FLUSH 1024          // rows accumulated in fp32 before being folded into the fp64 accumulators
+#define AFF_FLUSH 256           // rows accumulated in fp32 before being folded into the fp64 accumulators
 
 // out partial layout per (chunk, part): [65][64] doubles: rows 0..63 = sum (x-s)(x-s)^T, row 64 = sum (x-s)
 __global__ void __launch_bounds__(256) k_affine_moments(const float* __restrict__ enc, int64_t rows, int64_t chunk,
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) k_affine_moments(const float* __restrict_
     if (tid < 64) shift[tid] = enc[c_beg * 64 + tid];
     __syncthreads();
     double acc[4][4], acc1 = 0.0;
-    float f[4][4], f1 = 0.f;
+    float f[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -62,9 +62,11 @@ __global__ void __launch_bounds__(256) k_affine_moments(const float* __restrict_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) f[i][j] = fmaf(av[i], bv[j], f[i][j]);
         }
-        if (tid < 64) {
+        if (tid < 64) {                      // first moment: fp32 over one sub-tile only, then fp64
+            float t1 = 0.f;
 #pragma unroll 8
-            for (int rr = 0; rr < AFF_SUB; ++rr) f1 += xs[rr][tid];
+            for (int rr = 0; rr < AFF_SUB; ++rr) t1 += xs[rr][tid];
+            acc1 += (double)t1;
         }
         __syncthreads();
         since += AFF_SUB;
@@ -73,8 +75,6 @@ __global__ void __launch_bounds__(256) k_affine_moments(const float* __restrict_
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { acc[i][j] += (double)f[i][j]; f[i][j] = 0.f; }
-            acc1 += (double)f1;
-            f1 = 0.f;
             since = 0;
         }
     }
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_affine_moments(const float* __restrict_
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * 64 + tx * 4 + j] = acc[i][j] + (double)f[i][j];
-    if (tid < 64) out[64 * 64 + tid] = acc1 + (double)f1;
+    if (tid < 64) out[64 * 64 + tid] = acc1;
 }
 
 // half-warp per row: lane holds 4 consecutive columns
