@@ -8,6 +8,8 @@ Reference facts preserved (verified against the reference by test
 The module tree below is built the same way so that `state_dict()` keys are identical
 (layer1.{0,1,3,4,6,7,9,10}.*, layer2.{0..7}.*, occ_out.0.*).
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -140,7 +142,7 @@ class NOF(nn.Module):
                 with torch.no_grad():
                     # one running-statistics update per chunk, in chunk order (momentum recurrence in closed form)
                     k = torch.arange(nc - 1, -1, -1, device=mean.device, dtype=f64)
-                    wts = mom * (1.0 - mom) ** k
+                    wts = mom * torch.exp(k * math.log(1.0 - mom))      # (1-mom)^k without a host scalar tensor
                     unb = var * (cnt / (cnt - 1.0)).unsqueeze(-1)
                     keep = (1.0 - mom) ** nc
                     bn.running_mean.copy_((keep * bn.running_mean.to(f64) + (wts[:, None] * mean).sum(0)).to(bn.running_mean.dtype))

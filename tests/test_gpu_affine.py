@@ -31,7 +31,7 @@ def test_moments_kernel_vs_float64():
         assert float(cnt[k]) == blk.shape[0]
         # (x - s) is formed in fp32 (|x| up to 30 m): 1e-7-class relative errors, then fp64 accumulation
         np.testing.assert_allclose(m[k].cpu().numpy(), mr.numpy(), rtol=0, atol=3e-8 * 30.0)
-        np.testing.assert_allclose(C[k].cpu().numpy(), Cr.numpy(), rtol=0, atol=1e-7 * float(Cr.abs().max()))
+        np.testing.assert_allclose(C[k].cpu().numpy(), Cr.numpy(), rtol=0, atol=5e-7 * float(Cr.abs().max()))   # fp32 products of (x - s), fp64 sums
 
 
 @pytest.mark.parametrize("rows,chunk", [(4096, 4096), (5000, 2048), (130, 130), (70000, 16384)])
