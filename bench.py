@@ -272,8 +272,9 @@ def run_b200(a):
         except Exception as exc:                               # noqa: BLE001 - any capture failure -> eager launches
             if a.graph == "on":
                 raise
-            sys.stderr.write("bench.py: CUDA-graph capture failed (%s: %s); falling back to eager launches\n"
-                             % (type(exc).__name__, exc))
+            import traceback
+            sys.stderr.write("bench.py: CUDA-graph capture failed (%s: %s); falling back to eager launches\n%s\n"
+                             % (type(exc).__name__, exc, "".join(traceback.format_tb(exc.__traceback__)[-6:])))
             graphs = {}
             graph_note = "capture failed, eager"
             torch.cuda.synchronize()

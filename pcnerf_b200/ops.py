@@ -380,7 +380,7 @@ def affine_moments(enc, chunk):
     check(lib().pcnerf_affine_moments(_p(enc), rows, int(chunk), _p(part), _stream()))
     tot = part.sum(1)
     cnt = torch.full((nc,), float(chunk), dtype=torch.float64, device=enc.device)
-    cnt[-1] = float(rows - (nc - 1) * chunk)
+    cnt[-1:].fill_(float(rows - (nc - 1) * chunk))           # (fill_, not setitem: no host scalar tensor -> graph-safe)
     shift = enc[::chunk].to(torch.float64)
     m1 = tot[:, 64, :] / cnt[:, None]
     C = tot[:, :64, :] / cnt[:, None, None] - m1[:, :, None] * m1[:, None, :]
