@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the depth-inference (C3) block")
+    ap.add_argument("--infer-rays", type=int, default=131072, help="physical LiDAR rays of the inference frame per GPU")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step as one CUDA graph (pcnerf_b200.graphed.GraphedStep); auto = fall back to eager "
                          "launches if capture fails")
@@ -378,6 +380,8 @@ def run_b200(a):
     if roofline:
         out["roofline"] = roofline
         out["kernels"] = kernels
+    if not a.no_inference:
+        out["inference"] = time_inference(a, rank, world, dev, mc, mf, emb)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, ms_cpu = time_cpu(a.cpu_rays, 2, 1)
         out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
@@ -387,6 +391,51 @@ def run_b200(a):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_inference(a, rank, world, dev, mc, mf, emb):
+    """BASELINE.json configs[2]: one full 64-beam frame (131,072 physical rays/GPU, every rank renders its own frame =
+    rays sharded with no communication), two-step parent-then-child search, ~2.9 candidate rows per ray with the shipped
+    group-size histogram, 64 + 128 samples, eval-mode BN, through pcnerf_b200.eval_kitti_render.render_frame.
+    rays/s counts PHYSICAL rays.  Timed with the candidate rows already resident in HBM."""
+    import torch.distributed as dist
+    from pcnerf_b200 import eval_kitti_render as ev
+    from pcnerf_b200 import synth
+    base_phys = 4096
+    rows, other, _ = synth.synth_infer_rows(500 + rank, base_phys)
+    reps = max(1, a.infer_rays // base_phys)
+    rows = np.tile(rows, (reps, 1))
+    other = np.tile(other, reps)
+    n_phys = base_phys * reps
+    rays_d = torch.from_numpy(rows).to(dev)
+    other_d = torch.from_numpy(other).to(dev)
+    mc.eval()
+    mf.eval()
+
+    def frame():
+        return ev.render_frame(mc, mf, emb, rays_d, other_d, S, NI, 184320, depth_inference_method=2, batch_size_set=18432)
+
+    pts = frame()
+    assert pts.shape[0] == n_phys, (pts.shape, n_phys)          # exactly one rendered point per physical ray
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps_t = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps_t):
+        frame()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps_t], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    mc.train()
+    mf.train()
+    return {"metric": "depth-inference rays/s (physical rays, two-step search)", "value": world * n_phys / (float(ms.item()) * 1e-3),
+            "unit": "rays/s", "ms_per_frame": float(ms.item()), "physical_rays_per_gpu": n_phys,
+            "candidate_rows_per_gpu": int(rows.shape[0]), "N_samples": S, "N_importance": NI, "batch_rows": 18432,
+            "precision": a.precision}
 
 
 def run_reference(a):

@@ -149,3 +149,40 @@ def test_cpu_tensor_is_rejected():
     from pcnerf_b200 import ops
     with pytest.raises(RuntimeError):
         ops.embed(torch.zeros(4, 3), 63)
+
+
+def test_child_nerf_divide_variant_vs_oracle():
+    """use_child_nerf_divide == 1 (nof/render.py:106-119,135-152; train_kitti.py:129-143): per-child means keyed by the
+    child id in column 9 -- a segmented reduction built on the kernel's per-ray outputs."""
+    from pcnerf_b200 import synth
+    from pcnerf_b200.nof import render
+
+    class Given(torch.nn.Module):          # a stand-in model that returns given occupancies (the head is what is tested)
+        def __init__(self, p):
+            super().__init__()
+            self.p = torch.nn.Parameter(p.clone())
+
+        def mlp_precision(self):
+            return 0
+
+        def forward_encoded(self, enc, chunk=None):
+            return self.p.reshape(-1)
+
+    N, P, K = 300, 64, 8
+    rays = torch.from_numpy(synth.synth_train_rays(77, N, K=K))
+    gen = torch.Generator().manual_seed(9)
+    z = orc.sample_z(rays, P, 1, 0.1, 0, None)
+    p0 = torch.sigmoid(torch.randn(N, P, generator=gen) * 2 - 2 + 6 * torch.exp(-0.5 * ((z - rays[:, 14:15]) / 0.3) ** 2))
+    p_ref = p0.clone().requires_grad_(True)
+    fl, dl, depth, w = orc.train_head(p_ref, z, rays, None, 0.0, 1e-10, 1, 1, K)
+    (1e6 * fl + 1e5 * dl + depth.sum()).sum().backward()
+    net = Given(p0).to(dev())
+    rays_d = rays.to(dev())
+    flg, dlg, dg, wg = render.inference_train(net, None, None, rays_d, z.to(dev()), None, None, None, None, chunk=1 << 20,
+                                              noise_std=0, epsilon=1e-10, sub_nerf_test_num=K, use_child_nerf_divide=1,
+                                              use_child_nerf_loss=1, _enc=torch.zeros(1, device=dev()))
+    np.testing.assert_allclose(flg.item(), fl.item(), rtol=1e-5)
+    np.testing.assert_allclose(dlg.item(), dl.item(), rtol=1e-5)
+    (1e6 * flg + 1e5 * dlg + dg.sum()).sum().backward()
+    gr = p_ref.grad.numpy()
+    np.testing.assert_allclose(net.p.grad.cpu().numpy(), gr, rtol=5e-4, atol=2e-6 * np.abs(gr).max())

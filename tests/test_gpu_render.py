@@ -227,3 +227,23 @@ def test_bn_single_row_chunk_raises():
     mc, _, _ = make_nets(42, 43, True)
     with pytest.raises(ValueError):
         mc(torch.zeros(1, 63, device=dev()))
+
+
+def test_render_frame_driver_vs_oracle():
+    """eval_kitti_render.py:979-1030: group-aligned batches, render, keep the rows flagged by the fine pass."""
+    from pcnerf_b200 import eval_kitti_render as ev
+    from pcnerf_b200 import synth
+    rows, other, _ = synth.synth_infer_rows(33, 90)
+    mc, mf, emb = make_nets(42, 43, False)
+    rays, oth = _t(rows), _t(other)
+    pts = ev.render_frame(mc, mf, emb, rays, oth, 32, 64, 8192, depth_inference_method=2, batch_size_set=64)
+    sd_c, sd_f = orc.init_state_dict(42), orc.init_state_dict(43)
+    ref = []
+    with torch.no_grad():
+        for a, b in orc.eval_batches(rows, 64):
+            r = orc.render_rays_view(sd_c, sd_f, torch.from_numpy(rows[a:b]), torch.from_numpy(other[a:b]), 32, 64, 0, 0, 8192, 2)
+            keep = r["rays_effective_flag_fine"].reshape(-1).bool()
+            ref.append(r["points_inference_fine"][keep])
+    ref = torch.cat(ref, 0).numpy()
+    assert pts.shape == ref.shape and ref.shape[0] == 90          # one winner per physical ray
+    np.testing.assert_allclose(pts.cpu().numpy(), ref, rtol=5e-5, atol=1e-5)

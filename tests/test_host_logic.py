@@ -1,0 +1,45 @@
+"""CPU: host-side logic of the boundary that needs no device -- the group-aligned batch driver of the depth-inference
+entry point (eval_kitti_render.py:979-1005) against the oracle's restatement, and the mirror's public surface."""
+import inspect
+
+import numpy as np
+
+import pcnerf_oracle as orc
+from pcnerf_b200 import eval_kitti_render as ev
+from pcnerf_b200 import synth
+
+
+def test_eval_batches_never_split_a_group():
+    rows, other, _ = synth.synth_infer_rows(5, 400)
+    for bs in (64, 100, 257, 5000):
+        got = ev.eval_batches(rows[:, -1], bs)
+        assert got == orc.eval_batches(rows, bs)
+        for a, b in got:
+            assert rows[a, -1] >= 0                       # every batch starts at a group head
+        assert got[0][0] == 0 and all(got[i][1] == got[i + 1][0] for i in range(len(got) - 1))
+
+
+def test_mirror_signatures_match_reference_names():
+    """Parameter names / defaults of the reference's public entry points (nof/render.py:13-15, :38-40, :166-167, :229-231,
+    :371, :416-418, :485-486, :538-539, :614-616) as recorded in SURVEY.md section 8b."""
+    from pcnerf_b200.nof import render
+    want = {
+        "render_rays_train": ["model", "model_fine", "embedding_xy", "rays", "sub_nerf_test_num", "N_samples", "N_importance",
+                              "use_disp", "perturb", "noise_std", "chunk", "isval", "issegmentated", "childnerf_ratio",
+                              "use_child_nerf_divide", "use_child_nerf_loss"],
+        "render_rays_val": ["model", "model_fine", "embedding_xy", "rays", "sub_nerf_test_num", "N_samples", "N_importance",
+                            "use_disp", "perturb", "noise_std", "chunk", "isval"],
+        "render_rays": ["model", "model_fine", "embedding_xy", "rays", "N_samples", "N_importance", "use_disp", "perturb",
+                        "noise_std", "chunk", "isval"],
+        "render_rays_view_0525_2_2": ["model", "model_fine", "embedding_xy", "rays", "other_interest_sub_nerf_number",
+                                      "N_samples", "N_importance", "use_disp", "perturb", "noise_std", "chunk", "isval",
+                                      "depth_inference_method"],
+        "sample_pdf": ["bins", "weights", "N_samples", "det", "pytest"],
+    }
+    for name, params in want.items():
+        sig = inspect.signature(getattr(render, name))
+        positional = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert positional == params, name
+    d = {k: v.default for k, v in inspect.signature(render.render_rays_train).parameters.items()}
+    assert (d["N_samples"], d["N_importance"], d["chunk"], d["noise_std"], d["childnerf_ratio"]) == (64, 128, 1024 * 3, 1, 0.5)
+    assert render.__all__ == ["render_rays"]
