@@ -138,14 +138,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples that arrived in [t0, t1] (the timed region); all samples if none fall inside."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]
+        if not rows:
+            rows = [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -233,9 +237,13 @@ def run_b200(a):
             + LAM[2] * dscale * (res["child_depth_loss_fine"] + res["child_depth_loss"])
         bucket.zero()
         loss.backward()
+        return loss.detach().reshape(1), rays.shape[0], keep
+
+    def finish():
+        """Gradient all-reduce (N > 1) + Adam.  Kept OUT of the captured graph when N > 1: NCCL collectives replayed from a
+        CUDA graph hung the process at teardown on this stack (profiles/README.md), and the step has exactly one."""
         bucket.allreduce_mean()
         opt.step()
-        return loss.detach().reshape(1), rays.shape[0], keep
 
     def step(from_host):
         """One eager step (every kernel launched from the host)."""
@@ -244,6 +252,7 @@ def run_b200(a):
         else:
             d_, r_, p_ = resident
         loss, nrays, _ = core(d_, r_, p_, True)
+        finish()
         if from_host:
             loss_host.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
@@ -255,17 +264,22 @@ def run_b200(a):
         try:
             from pcnerf_b200.graphed import GraphedStep
             _, _, keep = core(*resident, True)
+            finish()
             if not bool(keep.all()):
                 raise RuntimeError("the AABB stage drops rays of this batch: data-dependent shape, not capturable")
             ops.launch_count(reset=True)
 
             def g_resident():
                 core(*resident, False)
+                if world == 1:
+                    finish()
 
             def g_host():
                 for s_, h_ in zip(staged, host):
                     s_.copy_(h_, non_blocking=True)
                 loss, _, _ = core(*staged, False)
+                if world == 1:
+                    finish()
                 loss_host.copy_(loss, non_blocking=True)
 
             graphs["resident"] = GraphedStep(g_resident, warmup=2)
@@ -284,6 +298,8 @@ def run_b200(a):
     def run(from_host):
         if graphs:
             graphs["host" if from_host else "resident"]()
+            if world > 1:
+                finish()
             if from_host:
                 torch.cuda.current_stream().synchronize()
             return n
@@ -311,6 +327,8 @@ def run_b200(a):
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         return float(ms.item()), float(tot.item()), ops.launch_count()
 
+    clocks = ClockSampler(local)                     # started before the warm-up: nvidia-smi needs ~1 s to come up
+    clocks.start()
     # kernels launched by one step (a graph replay re-issues exactly the launches recorded at capture)
     ops.launch_count(reset=True)
     step(False)
@@ -318,12 +336,11 @@ def run_b200(a):
     for _ in range(max(a.warmup, 3)):
         run(False)
     run(True)
-    clocks = ClockSampler(local)
-    clocks.start()
+    t_wall0 = time.time()
     ms, rays_total, _ = timed(False, a.steps)
     launches = launches_per_step * a.steps
     ms_e2e, rays_e2e, _ = timed(True, a.steps)
-    clk = clocks.stop()
+    clk = clocks.stop(t_wall0, time.time())
 
     # ---- per-kernel-class device time (separate pass so the event pairs do not perturb the numbers above)
     roofline, kernels = None, None
@@ -388,9 +405,13 @@ def run_b200(a):
                                "sample": "%d rays of the same workload (oracle port, fp32, same S/Ni/chunk/flags), "
                                          "1 warm-up + 2 timed steps, %.0f ms/step" % (a.cpu_rays, ms_cpu)}
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)          # skip interpreter teardown of NCCL + CUDA-graph state (a hang here cost a 15-minute box)
 
 
 def time_inference(a, rank, world, dev, mc, mf, emb):
