@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-inference", action="store_true", help="skip the depth-inference (C3) block")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra closed-form (affine) measurement")
     ap.add_argument("--infer-rays", type=int, default=131072, help="physical LiDAR rays of the inference frame per GPU")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step as one CUDA graph (pcnerf_b200.graphed.GraphedStep); auto = fall back to eager "
@@ -258,16 +259,16 @@ def run_b200(a):
             torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
         return nrays
 
-    graphs = {}
-    graph_note = "off"
-    if use_graph:
+    def build_graphs():
+        """Capture the resident-input and the host-input step as CUDA graphs; ({}, note) when graphs are off or fail."""
+        if not use_graph:
+            return {}, "off"
         try:
             from pcnerf_b200.graphed import GraphedStep
             _, _, keep = core(*resident, True)
             finish()
             if not bool(keep.all()):
                 raise RuntimeError("the AABB stage drops rays of this batch: data-dependent shape, not capturable")
-            ops.launch_count(reset=True)
 
             def g_resident():
                 core(*resident, False)
@@ -282,18 +283,17 @@ def run_b200(a):
                     finish()
                 loss_host.copy_(loss, non_blocking=True)
 
-            graphs["resident"] = GraphedStep(g_resident, warmup=2)
-            graphs["host"] = GraphedStep(g_host, warmup=1)
-            graph_note = "on"
+            return {"resident": GraphedStep(g_resident, warmup=2), "host": GraphedStep(g_host, warmup=1)}, "on"
         except Exception as exc:                               # noqa: BLE001 - any capture failure -> eager launches
             if a.graph == "on":
                 raise
             import traceback
             sys.stderr.write("bench.py: CUDA-graph capture failed (%s: %s); falling back to eager launches\n%s\n"
                              % (type(exc).__name__, exc, "".join(traceback.format_tb(exc.__traceback__)[-6:])))
-            graphs = {}
-            graph_note = "capture failed, eager"
             torch.cuda.synchronize()
+            return {}, "capture failed, eager"
+
+    graphs, graph_note = build_graphs()
 
     def run(from_host):
         if graphs:
@@ -399,6 +399,27 @@ def run_b200(a):
         out["kernels"] = kernels
     if not a.no_inference:
         out["inference"] = time_inference(a, rank, world, dev, mc, mf, emb)
+    if a.precision != "affine" and not a.no_fast_mode:
+        # The same step with the MLP engine switched to the closed form (precision 2): reported beside
+        # the headline, never instead of it.
+        graphs.clear()
+        torch.cuda.empty_cache()
+        mc.precision = mf.precision = "affine"
+        g2, note2 = build_graphs()
+        graphs.update(g2)
+        for _ in range(3):
+            run(False)
+        run(True)
+        ms_f, rays_f, _ = timed(False, a.steps)
+        ms_fe, rays_fe, _ = timed(True, a.steps)
+        fast = {"precision": "affine (closed form of the identity-activation network, 1e-5 parity gate: "
+                             "tests/test_gpu_affine.py)", "value": rays_f / (ms_f * 1e-3), "unit": "rays/s",
+                "ms_per_step": ms_f / a.steps, "e2e": rays_fe / (ms_fe * 1e-3), "cuda_graph": note2}
+        if not a.no_inference:
+            fast["inference"] = time_inference(a, rank, world, dev, mc, mf, emb)["value"]
+        out["fast_mode"] = fast
+        graphs.clear()
+        mc.precision = mf.precision = a.precision
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, ms_cpu = time_cpu(a.cpu_rays, 2, 1)
         out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",

@@ -623,27 +623,26 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
 // BN(l-1) backward coefficients WITHOUT a pass over the data-gradient G = DH_l W_l:
 //   sum_r G[r,n]             = sum_o colsum_l[o] W_l[o,n]                 (colsum_l = column sums of DH_l)
 //   sum_r G[r,n] H_{l-1}[r,n] = sum_o W_l[o,n] (DH_l^T H_{l-1})[o,n]        (the raw weight gradient of layer l)
-// so the data-gradient GEMM can apply the BN backward in its own epilogue.  One block of 256 threads (n).
-__global__ void __launch_bounds__(1024) k_tc_bn_bwd_coef2(const float* __restrict__ Wp, int kpad, int off,
-                                                          const float* __restrict__ part, const double* __restrict__ colsum,
-                                                          int64_t rows, const float* __restrict__ stats,
-                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                          float* __restrict__ coef /* c0 | c1 | c2 | mean */) {
-    __shared__ double r0[4][256], r1[4][256];
-    const int n = threadIdx.x & 255, og = threadIdx.x >> 8;      // 4 groups of 64 output rows
-    double st0 = 0.0, st1 = 0.0;
-#pragma unroll 8
-    for (int o = og * 64; o < og * 64 + 64; ++o) {
-        const float w = Wp[(size_t)o * kpad + off + n];
-        st0 += colsum[o] * (double)w;
-        st1 += (double)w * (double)part[(size_t)o * kpad + off + n];
-    }
-    r0[og][n] = st0;
-    r1[og][n] = st1;
+// so the data-gradient GEMM can apply the BN backward in its own epilogue.
+__global__ void __launch_bounds__(256) k_tc_bn_bwd_coef2(const float* __restrict__ Wp, int kpad, int off,
+                                                         const float* __restrict__ part, const double* __restrict__ colsum,
+                                                         int64_t rows, const float* __restrict__ stats,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ coef /* c0 | c1 | c2 | mean */) {
+    // one block per column n, one thread per output row o
+    __shared__ double r0[8], r1[8];
+    const int n = blockIdx.x, o = threadIdx.x;
+    const float w = Wp[(size_t)o * kpad + off + n];
+    double st0 = colsum[o] * (double)w;
+    double st1 = (double)w * (double)part[(size_t)o * kpad + off + n];
+    st0 = warp_sum_d(st0);
+    st1 = warp_sum_d(st1);
+    if ((o & 31) == 0) { r0[o >> 5] = st0; r1[o >> 5] = st1; }
     __syncthreads();
-    if (og != 0) return;
-    st0 = r0[0][n] + r0[1][n] + r0[2][n] + r0[3][n];
-    st1 = r1[0][n] + r1[1][n] + r1[2][n] + r1[3][n];
+    if (o != 0) return;
+    st0 = 0.0;
+    st1 = 0.0;
+    for (int k = 0; k < 8; ++k) { st0 += r0[k]; st1 += r1[k]; }
     const float mean = stats[n], invstd = stats[256 + n], a = stats[512 + n];
     const float db = (float)st0;
     const float dg = invstd * (float)(st1 - (double)mean * st0);
@@ -892,7 +891,7 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
                                                          G->dW[l], G->db[l]));
         if (l == 0) break;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_tc_bn_bwd_coef2<<<1, 1024, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
+                  k_tc_bn_bwd_coef2<<<256, 256, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
                                                        L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
         rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
                             nullptr, L.colsum(scratch, l - 1), nullptr, st);
