@@ -193,10 +193,11 @@ int pcnerf_affine_grad(const float* enc, const float* p, const float* grad_p, in
  * pcnerf_tc_rowgemm: C[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T, k0, k1 multiples of 64, k0 + k1 <= 320.
  *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 = bf16 copy or NULL;
  *     stats (2,256) f64 = column sums of (C + bias) and (C + bias)^2 (zeroed by the call).
- *   mode 1 (data gradient with the BatchNorm backward fused): A, B bf16; E (rows,256) bf16; vec = c0|c1|c2|mean [4][256];
+ *   mode 1 (data gradient with the BatchNorm backward fused): A, B bf16; E (rows,256) fp16; vec = c0|c1|c2|mean [4][256];
  *     out = bf16(c0*C - c1 - (E - mean)*c2); stats[0] = column sums of out.
- * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T * X[rows, 0:ncols] (both bf16,
- *   X row stride ldx); ncols 64 or 256; accumulated with atomics (zero `out` first).
+ * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T (bf16) * X[rows, 0:ncols] (bf16, or
+ *   fp16 converted to bf16 tile by tile in shared memory; row stride ldx); ncols 64 or 256; accumulated with atomics
+ *   (zero `out` first).
  * pcnerf_tc_last_fault: non-zero if a tensor-core kernel aborted on a pipeline time-out (diagnostic). */
 int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B, const float* vec,
                       const void* E, int64_t rows, void* out, void* out2, double* stats, void* stream);

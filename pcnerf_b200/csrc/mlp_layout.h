@@ -10,7 +10,7 @@ __host__ __device__ inline int mlp_kpad(int l) { return l == 0 ? 64 : (l == 4 ? 
 
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// saved  : H[0..7] (rows x 256, fp32 (precision 0) or bf16 (precision 1))  |  stats[8][4][256] fp32 = {mean, invstd, a = gamma*invstd, s = beta - mean*a}
+// saved  : H[0..7] (rows x 256, fp32 (precision 0) or fp16 (precision 1))  |  stats[8][4][256] fp32 = {mean, invstd, a = gamma*invstd, s = beta - mean*a}
 // scratch: Wp[8] | Wf[8] | bf[8][256] | wout_f[256]+bout_f | coef[3][256] | gvec[rows] | G[2][rows x 256] |
 //          partial[MAX_SPLITS][256][320] | dstat (fp64) : 16 x 512 stat slots + colsum[8][256]
 struct MlpLayout {
@@ -41,12 +41,7 @@ struct MlpLayout {
         off_dstat = o; o += al256(n_dstat * sizeof(double));
         off_tc = o;              // bf16 copies of the weights etc. for the tensor-core path
         o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
-        for (int i = 0; i < 2; ++i) {
-            off_hf[i] = o;
-            if (precision == 1) o += al256((size_t)rows * 256 * 2);
-        }
-        off_encb = o;
-        if (precision == 1) o += al256((size_t)rows * 64 * 2);
+        off_hf[0] = off_hf[1] = off_encb = o;      // (unused since the weight-gradient kernel converts in shared memory)
         scratch_bytes = o;
     }
     float* H(char* sv, int l) const { return (float*)(sv + (size_t)l * h_bytes); }

@@ -175,7 +175,7 @@ struct RowGemmArgs {
     void* out;                  // [rows][256]: fp16 (FWD) or bf16 (DGRAD)
     __nv_bfloat16* out2;        // FWD: optional bf16 copy of `out` (what the backward pass reads)
     const float* vec;           // FWD: bias[256];  DGRAD: c0 | c1 | c2 | mean, [4][256]
-    const __nv_bfloat16* E;     // DGRAD: H_{l-1} [rows][256] (bf16)
+    const __half* E;            // DGRAD: H_{l-1} [rows][256] (fp16, as the forward pass stored it)
     double* stat0;              // [256] column sums of the fp32 result, accumulated atomically
     double* stat1;              // FWD: [256] column sums of squares
 };
@@ -256,7 +256,7 @@ __device__ __forceinline__ void stage_col_sums(uint32_t buf, int lane, double* a
 // C[rows,256] = A[rows,K] * B[256,K]^T     (A, B K-major)
 //   FWD  : fp16 x fp16; out = fp16(C + bias), out2 = bf16(C + bias); stats = column sums of out and out^2 (the fp16
 //          values the next layer consumes)
-//   DGRAD: bf16 x bf16; out = bf16(c0*C - c1 - (E - mean)*c2)  (BN backward fused); stat0 = column sums of out
+//   DGRAD: bf16 x bf16; out = bf16(c0*C - c1 - (E - mean)*c2)  (BN backward fused, E fp16); stat0 = column sums of out
 // Outputs leave through per-warp TMA stores of {32 x 32} boxes; rows beyond `rows` are clipped by the tensor map.
 // ---------------------------------------------------------------------------------------------------------------
 template <int EPI>
@@ -422,16 +422,16 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         const __half2 h2 = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
                         pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
                     }
-                    if (lane == 0) {                              // buf0's previous store has been read out
-                        if (g.out2) tma_store_wait_read<1>();
-                        else tma_store_wait_read<0>();
-                    }
+                    // with a single output the two staging buffers alternate chunk by chunk; either way the store that
+                    // last read this buffer is at least two bulk groups old
+                    const uint32_t bufc = (g.out2 || !(c & 1)) ? buf0 : buf1;
+                    if (lane == 0) tma_store_wait_read<1>();
                     __syncwarp();
-                    stage_put_row(buf0, pk, lane);
+                    stage_put_row(bufc, pk, lane);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmO, buf0, col0, row0);
-                    stage_col_sums<true, true>(buf0, lane, acc0 + 2 * c, acc1 + 2 * c);
+                    if (lane == 0) tma_store_2d(&tmO, bufc, col0, row0);
+                    stage_col_sums<true, true>(bufc, lane, acc0 + 2 * c, acc1 + 2 * c);
                     if (g.out2) {
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
@@ -456,11 +456,11 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint4 hv = lds128(stage_addr(buf0, lane, k));
-                        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
+                        const __half2* hb = reinterpret_cast<const __half2*>(&hv);
                         float hf[8];
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
-                            const float2 h2 = __bfloat1622float2(hb[t]);
+                            const float2 h2 = __half22float2(hb[t]);
                             hf[2 * t] = h2.x;
                             hf[2 * t + 1] = h2.y;
                         }
@@ -518,7 +518,7 @@ struct WgradArgs {
     int kb_per_cta;             // 64-row k-blocks per CTA
     float* out;                 // [256][ldo] fp32, accumulated with vector atomics
     int ldo, col_off;
-    int b_is_bf16;              // format of X (0 = fp16)
+    int convert_b;              // X is fp16: the idle epilogue warps convert each B tile to bf16 in shared memory
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -529,6 +529,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     constexpr int NST = 3;
     uint64_t* bars = (uint64_t*)(smem + (size_t)NST * TC_WG_STAGE);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4), bar_tfull = smem_u32(bars + 8);
+    const uint32_t bar_conv = smem_u32(bars + 10);
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
     const int nkb = (g.rows + 63) >> 6;
     const int kb_beg = blockIdx.x * g.kb_per_cta;
@@ -536,7 +537,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const int N = g.N, nboxB = N >> 6;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 8);
+        }
         mbar_init(bar_tfull, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -565,11 +570,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 if (++s == NST) { s = 0; ph ^= 1; }
             }
         } else if (warp == 1) {
-            const uint32_t idesc = make_idesc(1, g.b_is_bf16 ? 1 : 0, 1, 1, 128, N);
+            const uint32_t idesc = make_idesc(1, 1, 1, 1, 128, N);
             int s = 0;
             uint32_t ph = 0;
             for (int kb = kb_beg; kb < kb_end; ++kb) {
-                mbar_wait(bar_full + 8 * s, ph, 12);
+                mbar_wait((g.convert_b ? bar_conv : bar_full) + 8 * s, ph, 12);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a0 = smem_u32(smem + (size_t)s * TC_WG_STAGE), b0 = a0 + 32768;
@@ -589,6 +594,33 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
         } else {
             const int q = warp & 3, half = (warp - 2) >> 2;
+            if (g.convert_b) {
+                // tcgen05 kind::f16 cannot mix fp16 and bf16 operands, and the gradients need bf16's range: while the
+                // mainloop runs these eight warps have nothing else to do, so they rewrite every freshly landed fp16
+                // B tile as bf16 in place (same size, same swizzled position) before the MMA warp may touch it.
+                const int t256 = threadIdx.x - 64, nch = N * 8;          // 16-byte chunks of the B tile
+                int s = 0;
+                uint32_t ph = 0;
+                for (int kb = kb_beg; kb < kb_end; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph, 14);
+                    const uint32_t b0 = smem_u32(smem + (size_t)s * TC_WG_STAGE) + 32768;
+                    for (int i = t256; i < nch; i += 256) {
+                        uint4 v = lds128(b0 + (uint32_t)i * 16);
+                        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(f.x, f.y);
+                            w[t] = *reinterpret_cast<const uint32_t*>(&b2);
+                        }
+                        sts128(b0 + (uint32_t)i * 16, v);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                    if (++s == NST) { s = 0; ph ^= 1; }
+                }
+            }
             mbar_wait(bar_tfull, 0, 13);
             tc_fence_after();
             for (int h = 0; h < 2; ++h) {
@@ -655,11 +687,6 @@ __global__ void __launch_bounds__(256) k_tc_bn_bwd_coef2(const float* __restrict
     coef[768 + n] = mean;
 }
 
-// bf16 copy of the fp16 encodings (B operand of the layer-0 / layer-4 weight-gradient GEMMs)
-__global__ void k_tc_f16_to_bf16(const __half2* __restrict__ src, __nv_bfloat162* __restrict__ dst, int64_t n2) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = __float22bfloat162_rn(__half22float2(src[i]));
-}
 struct PrepTArgs {
     const float* Wp[8];
     __nv_bfloat16* WT[8];
@@ -723,9 +750,9 @@ int sm_count() {
 }
 
 // mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias), out2 bf16 copy;  TC_DGRAD: A bf16, B bf16 -> out bf16 (BN backward
-// fused: vec = c0|c1|c2|mean, E = bf16 H)
+// fused: vec = c0|c1|c2|mean, E = fp16 H)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
-                   const float* vec, const __nv_bfloat16* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
+                   const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
                    double* stat1, cudaStream_t st) {
     PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && (k0 + k1) <= 320, "tc rowgemm: K must be 64..320 in 64s");
     CUtensorMap mA0, mA1, mB;
@@ -770,11 +797,11 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
     rc = make_map(&mB, X, rows, N, ldx, 64);
     if (rc) return rc;
     WgradArgs g;
-    g.rows = (int)rows; g.N = N; g.out = out; g.ldo = ldo; g.col_off = col_off; g.b_is_bf16 = x_is_bf16;
+    g.rows = (int)rows; g.N = N; g.out = out; g.ldo = ldo; g.col_off = col_off; g.convert_b = x_is_bf16 ? 0 : 1;
     const int nkb = (int)pcn_cdiv(rows, 64);
     g.kb_per_cta = (int)pcn_cdiv(nkb, sm_count());
     const int grid = (int)pcn_cdiv(nkb, g.kb_per_cta);
-    const size_t smem = 1024 + 3 * (size_t)TC_WG_STAGE + 16 * 8 + 64;
+    const size_t smem = 1024 + 3 * (size_t)TC_WG_STAGE + 16 * 8 + 64;      // 13 barriers + the TMEM slot
     PCN_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PcnScope ps(PCN_K_GEMM_WGRAD, st, 2.0 * (double)rows * 256.0 * (double)N);
     k_tc_wgrad<<<grid, TC_THREADS, smem, st>>>(mA, mB, g);
@@ -806,12 +833,12 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
     tc_prep_weights(P, L, scratch, st);
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
-    // H_l leaves each layer twice: fp16 into a ping-pong buffer (the next layer's operand: 10-bit mantissa for the 1e-3
-    // gate) and bf16 into the saved store (what the backward pass reads; same format as the gradients, see k_tc_wgrad)
+    // H_l is stored once, fp16 (10-bit mantissa for the 1e-3 gate): it is the next layer's operand and what the backward
+    // pass re-reads (the weight-gradient kernel converts its tiles to bf16 in shared memory)
     for (int l = 0; l < 8; ++l) {
-        __half* Hout = (__half*)L.hf(scratch, l & 1);
-        const __half* Hin = (const __half*)L.hf(scratch, (l - 1) & 1);
-        __nv_bfloat16* Hsave = (__nv_bfloat16*)L.Hraw(sv, l);
+        __half* Hout = (__half*)L.Hraw(sv, l);
+        const __half* Hin = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;
+        __nv_bfloat16* Hsave = nullptr;
         double* s0 = L.dstat(scratch, l);
         const float* bias = l == 0 ? P->b[0] : L.bf(scratch, l);
         int rc;
@@ -830,7 +857,7 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     int64_t blocks = pcn_cdiv(rows, 8);
     if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-              k_logit_sigmoid<__half><<<(int)blocks, 256, 0, st>>>((const __half*)L.hf(scratch, 1), rows, L.wout_f(scratch),
+              k_logit_sigmoid<__half><<<(int)blocks, 256, 0, st>>>((const __half*)L.Hraw(sv, 7), rows, L.wout_f(scratch),
                                                                   L.wout_f(scratch) + 256, out_p));
     PCN_LAUNCH_CHECK();
     return 0;
@@ -855,36 +882,29 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     float* coef = L.coef(scratch);
     __nv_bfloat16* Gb[2] = {(__nv_bfloat16*)L.Graw(scratch, 0), (__nv_bfloat16*)L.Graw(scratch, 1)};
     const int strips = (int)pcn_cdiv(rows, STRIP);
-    const __nv_bfloat16* H7 = (const __nv_bfloat16*)L.Hraw(sv, 7);
-    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__nv_bfloat16><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
+    const __half* H7 = (const __half*)L.Hraw(sv, 7);
+    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__half><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
               k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
                                                     G->dbeta[7], coef));
     int cur = 0;
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-              k_bn_bwd_apply<true, __nv_bfloat16, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef,
-                                                                                         L.stats(sv, 7), L.colsum(scratch, 7)));
+              k_bn_bwd_apply<true, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef, L.stats(sv, 7),
+                                                                                  L.colsum(scratch, 7)));
     float* part = L.partial(scratch);
-    __nv_bfloat16* encb = (__nv_bfloat16*)L.encb(scratch);
-    {
-        int64_t blocks = pcn_cdiv(rows * 32, 256);
-        if (blocks > PCN_SM_COUNT * 8) blocks = PCN_SM_COUNT * 8;
-        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_tc_f16_to_bf16<<<(int)blocks, 256, 0, st>>>((const __half2*)ench, (__nv_bfloat162*)encb, rows * 32));
-    }
     // Per layer: weight gradient first (its raw result also yields the BN(l-1) backward coefficients, see
     // k_tc_bn_bwd_coef2), then the data-gradient GEMM whose epilogue applies the BN backward and emits DH_{l-1} directly.
-    // tcgen05 kind::f16 needs A and B in the same 16-bit format (bf16 x fp16 is an illegal instruction on sm_100a):
-    // gradients, saved activations and the encoding copy are all bf16 here.
+    // tcgen05 kind::f16 needs A and B in the same 16-bit format (bf16 x fp16 is an illegal instruction on sm_100a): the
+    // weight-gradient kernel converts the fp16 activation / encoding tiles to bf16 in shared memory.
     for (int l = 7; l >= 0; --l) {
         const __nv_bfloat16* DH = Gb[cur];
         const int kpad = mlp_kpad(l), off = l == 4 ? 64 : 0;
-        const __nv_bfloat16* Hprev = l > 0 ? (const __nv_bfloat16*)L.Hraw(sv, l - 1) : nullptr;
+        const __half* Hprev = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;
         PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
         int rc = 0;
-        if (l == 0 || l == 4) rc = launch_wgrad(DH, encb, 64, 64, 1, rows, part, kpad, 0, st);
+        if (l == 0 || l == 4) rc = launch_wgrad(DH, ench, 64, 64, 0, rows, part, kpad, 0, st);
         if (rc) return rc;
-        if (l != 0) rc = launch_wgrad(DH, Hprev, 256, 256, 1, rows, part, kpad, off, st);
+        if (l != 0) rc = launch_wgrad(DH, Hprev, 256, 256, 0, rows, part, kpad, off, st);
         if (rc) return rc;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, 1, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
@@ -913,7 +933,7 @@ extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A
     PCN_CHECK_ARG(mode == 0 || E, "tc_rowgemm: data-gradient mode needs E");
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
-    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __nv_bfloat16*)E, rows, out,
+    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __half*)E, rows, out,
                           mode == 0 ? (__nv_bfloat16*)out2 : nullptr, stats, stats + 256, st);
 }
 
@@ -921,10 +941,7 @@ extern "C" int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols
                                float* out, int ldo, int col_off, void* stream) {
     PCN_CHECK_ARG(DH && X && out && rows >= 1, "tc_wgrad: null argument");
     PCN_CHECK_ARG(ldo >= col_off + ncols && (ldo % 4) == 0 && (col_off % 4) == 0, "tc_wgrad: bad output window");
-    if (!x_is_bf16) {
-        pcn_set_error("tc_wgrad: X must be bf16 like DH (tcgen05 kind::f16 cannot mix fp16 and bf16 operands)");
-        return PCNERF_ERR_UNSUPPORTED;
-    }
+
     return launch_wgrad(DH, X, ldx, ncols, x_is_bf16, rows, out, ldo, col_off, (cudaStream_t)stream);
 }
 

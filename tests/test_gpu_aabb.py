@@ -112,3 +112,25 @@ def test_empty_inputs():
     assert ops.aabb_find_box(np.zeros((12, 3)), scene_boxes, z3, 10).shape[0] == 0
     r, rg, o, _ = ops.aabb_build_groups(np.zeros(3), z3, np.zeros(0), scene_boxes, scene_boxes, np.zeros(3), np.ones(3))
     assert r.shape == (0, 13) and o.shape == (0, 1)
+
+
+def test_real_scale_box_count_bit_exact_vs_oracle():
+    """K = 3,000 child boxes: more than fits the shared-memory staging (the shipped KITTI scene has 15,333), so the
+    kernels read the boxes through L2 instead -- results must not change."""
+    from pcnerf_b200 import ops, synth
+    K, n = 3000, 300
+    scene = synth.make_scene(4242, K, synth.KITTI_PARENT)
+    pts = synth.make_points(scene, 6, n)
+    dirs, dist = synth.rays_from_points(scene.origin, pts)
+    ref, _ = orc.pack_train_rays_from_dirs(scene.origin, dirs, dist, pts, scene.centres, scene.child_bounds,
+                                           scene.child_bounds_bigger, scene.parent, 0.05, "kitti")
+    got, _ = ops.aabb_pack_train(606, scene.origin, dirs, dist, pts, scene.centres, scene.child_bounds,
+                                 scene.child_bounds_bigger, scene.parent, 0.05, 10)
+    assert np.array_equal(_np(got), ref, equal_nan=True)
+    sbl = scene.child_bounds + np.array([-0.025] * 3 + [0.025] * 3)
+    m = 120
+    r_ref, rg_ref, o_ref, _ = orc.build_candidate_groups(scene.origin, dirs[:m], dist[:m], scene.child_bounds, sbl,
+                                                         scene.parent_min, scene.parent_max, 2, 0.05)
+    r, rg, o, _ = ops.aabb_build_groups(scene.origin, dirs[:m], dist[:m], scene.child_bounds, sbl, scene.parent_min,
+                                        scene.parent_max, 2, 0.05, 0.65)
+    assert np.array_equal(_np(r), r_ref) and np.array_equal(_np(rg), rg_ref) and np.array_equal(_np(o), o_ref)

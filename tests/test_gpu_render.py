@@ -247,3 +247,41 @@ def test_render_frame_driver_vs_oracle():
     ref = torch.cat(ref, 0).numpy()
     assert pts.shape == ref.shape and ref.shape[0] == 90          # one winner per physical ray
     np.testing.assert_allclose(pts.cpu().numpy(), ref, rtol=5e-5, atol=1e-5)
+
+
+def test_shipped_eval_sizes_one_group():
+    """The shipped evaluation flags (shells/pretraining/KITTI00_pcnerf_eval.bash:12): N_samples 4096, N_importance 8192,
+    chunk 184320 -- the largest per-ray sizes the kernels are asked for (12,288 samples per ray)."""
+    from pcnerf_b200.nof import render
+    from pcnerf_b200 import synth
+    rows, other, _ = synth.synth_infer_rows(71, 3)
+    rows, other = rows[:7], other[:7]
+    n_head = int(other[0]) + 1
+    rows, other = rows[:n_head], other[:n_head]          # one complete candidate group
+    mc, mf, emb = make_nets(42, 43, False)
+    with torch.no_grad():
+        r = render.render_rays_view_0525_2_2(mc, mf, emb, _t(rows), _t(other), N_samples=4096, N_importance=8192,
+                                             perturb=0, noise_std=0, chunk=184320, depth_inference_method=2)
+        sd_c, sd_f = orc.init_state_dict(42), orc.init_state_dict(43)
+        ref = orc.render_rays_view(sd_c, sd_f, torch.from_numpy(rows), torch.from_numpy(other), 4096, 8192, 0, 0, 184320, 2)
+    assert np.array_equal(r["rays_effective_flag"].cpu().numpy(), ref["rays_effective_flag"].numpy())
+    np.testing.assert_allclose(r["depth"].cpu().numpy(), ref["depth"].numpy(), rtol=5e-5, atol=1e-6)
+    assert int(r["rays_effective_flag_fine"].sum()) == 1
+    np.testing.assert_allclose(r["depth_fine"].cpu().numpy(), ref["depth_fine"].numpy(), rtol=2e-3, atol=1e-5)
+
+
+def test_c4_sample_counts_train_step():
+    """BASELINE configs[3] per-ray sizes: 128 coarse + 256 importance samples (nof_utils.py:121-124 defaults)."""
+    from pcnerf_b200.nof import render
+    from pcnerf_b200 import synth
+    rays_cpu = torch.from_numpy(synth.synth_train_rays(41, 24, K=8))
+    sd_c, sd_f = orc.init_state_dict(42), orc.init_state_dict(43)
+    with torch.no_grad():
+        ref = orc.render_rays_train(sd_c, sd_f, rays_cpu, 128, 256, 0, 0, 4096, 1, 0.1, 0, 1)
+    mc, mf, emb = make_nets(42, 43, True)
+    res = render.render_rays_train(mc, mf, emb, rays_cpu.to(dev()), N_samples=128, N_importance=256, perturb=0, noise_std=0,
+                                   chunk=4096, issegmentated=1, childnerf_ratio=0.1, use_child_nerf_divide=0,
+                                   use_child_nerf_loss=1)
+    for k in ("depth", "child_free_loss", "child_depth_loss"):
+        np.testing.assert_allclose(res[k].detach().cpu().numpy(), ref[k].numpy(), rtol=3e-5, atol=1e-6, err_msg=k)
+    np.testing.assert_allclose(res["depth_fine"].detach().cpu().numpy(), ref["depth_fine"].numpy(), rtol=FINE_E2E_RTOL, atol=1e-6)

@@ -43,7 +43,7 @@ def test_rowgemm_dgrad_bf16_fused_bn_backward(rows):
     from pcnerf_b200 import ops
     A = _rand((rows, 256), torch.bfloat16, 5)
     B = _rand((256, 256), torch.bfloat16, 6, 0.1)
-    E = _rand((rows, 256), torch.bfloat16, 7)
+    E = _rand((rows, 256), torch.float16, 7)
     vec = _rand((4, 256), torch.float32, 8)
     out, _, stats = ops.tc_rowgemm(1, A, B, None, vec, E)
     C = A.float() @ B.float().t()
@@ -52,23 +52,18 @@ def test_rowgemm_dgrad_bf16_fused_bn_backward(rows):
     np.testing.assert_allclose(stats[0].cpu().numpy(), out.double().sum(0).cpu().numpy(), rtol=1e-5, atol=2e-3)
 
 
-def test_wgrad_rejects_mixed_formats():
-    """fp16 x bf16 operands in one tcgen05.mma kind::f16 are an illegal instruction on sm_100a (measured): refused."""
+@pytest.mark.parametrize("rows,ncols,xdt", [(64, 256, torch.bfloat16), (64, 256, torch.float16), (1000, 256, torch.float16),
+                                            (30000, 64, torch.float16), (70000, 256, torch.float16)])
+def test_wgrad_mn_major(rows, ncols, xdt):
+    """DH^T X with both operands MN-major.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands (measured: illegal
+    instruction), so an fp16 X is rewritten as bf16 tile by tile in shared memory by the kernel's idle epilogue warps:
+    the reference result for fp16 X is therefore computed from bf16(X)."""
     from pcnerf_b200 import ops
-    out = torch.zeros((256, 256), dtype=torch.float32, device=dev())
-    with pytest.raises(NotImplementedError):
-        ops.tc_wgrad(_rand((64, 256), torch.bfloat16, 1), _rand((64, 256), torch.float16, 2), 256, out, 0)
-
-
-@pytest.mark.parametrize("rows,ncols", [(64, 256), (1000, 256), (30000, 64), (70000, 256)])
-def test_wgrad_mn_major(rows, ncols):
-    from pcnerf_b200 import ops
-    xdt = torch.bfloat16
     DH = _rand((rows, 256), torch.bfloat16, 8)
     X = _rand((rows, ncols), xdt, 9)
     out = torch.zeros((256, 320), dtype=torch.float32, device=dev())
     ops.tc_wgrad(DH, X, ncols, out, 64 if ncols == 256 else 0)
-    ref = DH.double().t() @ X.double()
+    ref = DH.double().t() @ X.to(torch.bfloat16).double()
     off = 64 if ncols == 256 else 0
     got = out[:, off:off + ncols].double()
     scale = float(ref.abs().max())
