@@ -17,10 +17,12 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #define TC_THREADS 320           // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: epilogue
 #define TC_A_BYTES (128 * 128)   // one A k-block: 128 rows x 64 x 2 B
-#define TC_B_BYTES (256 * 128)   // one B k-block: 256 rows x 64 x 2 B
+#define TC_NCTA 128              // output columns per CTA of the row GEMM (two CTAs share a row tile, see k_tc_rowgemm)
+#define TC_B_BYTES (TC_NCTA * 128)   // one B k-block: 128 weight rows x 64 x 2 B
 #define TC_WG_STAGE (64 * 1024)  // wgrad stage: A 4 boxes (32 KB) + B up to 4 boxes (32 KB)
 #define TC_TIMEOUT_CYCLES 6000000000LL
 
@@ -178,6 +180,7 @@ struct RowGemmArgs {
     const __half* E;            // DGRAD: H_{l-1} [rows][256] (fp16, as the forward pass stored it)
     double* stat0;              // [256] column sums of the fp32 result, accumulated atomically
     double* stat1;              // FWD: [256] column sums of squares
+    int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores
 };
 
 #define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
@@ -258,6 +261,10 @@ __device__ __forceinline__ void stage_col_sums(uint32_t buf, int lane, double* a
 //          values the next layer consumes)
 //   DGRAD: bf16 x bf16; out = bf16(c0*C - c1 - (E - mean)*c2)  (BN backward fused, E fp16); stat0 = column sums of out
 // Outputs leave through per-warp TMA stores of {32 x 32} boxes; rows beyond `rows` are clipped by the tensor map.
+// Work split: CTA b owns the column half (b & 1) of row tiles (b >> 1), (b >> 1) + gridDim.x/2, ...  Its 128 x K slice of
+// the weights (<= 80 KB) stays resident, which leaves room for an 7-8 stage ring of A tiles: the kernel is bound by bytes
+// in flight (measured: a one-tile ring sustained 2.5 TB/s regardless of the epilogue), and the twin CTA's read of the same
+// A tile hits L2.
 // ---------------------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -305,12 +312,15 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const int ntiles = (g.rows + 127) >> 7;
+    const int nhalf = blockIdx.x & 1;                     // which 128 output columns this CTA owns
+    const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
 
     if (warp == 0) {
         // ===== TMA producer
         if (lane == 0) {
             mbar_expect_tx(bar_bfull, (uint32_t)KB * TC_B_BYTES);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sB + (size_t)kb * TC_B_BYTES), &tmB, bar_bfull, kb * 64, 0);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(smem_u32(sB + (size_t)kb * TC_B_BYTES), &tmB, bar_bfull, kb * 64, nhalf * TC_NCTA);
         }
         // The smem ring holds at most one tile of A; the tiles this CTA will need after that are pulled into L2 two
         // tiles ahead, so the ring refills at L2 latency and HBM always has ~128 KB per SM in flight.
@@ -324,7 +334,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         (void)prefetch_tile;      // measured: L2 prefetch two tiles ahead made the kernel 10 % slower (profiles/README.md)
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < ntiles; tile += tstep) {
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
                 if (lane == 0) {
@@ -338,14 +348,14 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
     } else if (warp == 1) {
         // ===== MMA issuer
-        constexpr uint32_t idesc = (EPI == TC_FWD) ? make_idesc(0, 0, 0, 0, 128, 256) : make_idesc(1, 1, 0, 0, 128, 256);
+        constexpr uint32_t idesc = (EPI == TC_FWD) ? make_idesc(0, 0, 0, 0, 128, TC_NCTA) : make_idesc(1, 1, 0, 0, 128, TC_NCTA);
         mbar_wait(bar_bfull, 0, 2);
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < ntiles; tile += tstep) {
             mbar_wait_spin(bar_tempty + 8 * as, aph ^ 1, 3);
             tc_fence_after();
-            const uint32_t dcol = tmem_base + (uint32_t)as * 256;
+            const uint32_t dcol = tmem_base + (uint32_t)as * TC_NCTA;
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait_spin(bar_full + 8 * s, ph, 4);
                 tc_fence_after();
@@ -364,18 +374,20 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             if (++as == 2) { as = 0; aph ^= 1; }
         }
     } else {
-        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, column half (warp-2)/4, four 32-column chunks
+        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, 64-column half (warp-2)/4 of the CTA's 128 columns,
+        // two 32-column chunks
         const int q = warp & 3, half = (warp - 2) >> 2;
+        const int colb = nhalf * TC_NCTA + half * 64;     // first output column of this warp
         const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF * TC_STAGE_BYTES);
         const uint32_t buf1 = buf0 + TC_STAGE_BYTES;
-        double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
         // DGRAD: this warp's 32 x 64 B piece of H_{l-1} for the NEXT chunk is always in flight (8 rows x 64 B per load
         // instruction) while the current chunk is processed
         uint4 e[4];
         auto load_e = [&](int tile_, int c_) {
-            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_, c0_ = (half * 4 + c_) * 32;
+            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_, c0_ = colb + c_ * 32;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = (lane >> 2) + 8 * i;
@@ -383,20 +395,20 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 if (row < left_) e[i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + c0_ + (lane & 3) * 8);
             }
         };
-        if (EPI == TC_DGRAD && (int)blockIdx.x < ntiles) load_e(blockIdx.x, 0);
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (EPI == TC_DGRAD && tile0 < ntiles) load_e(tile0, 0);
+        for (int tile = tile0; tile < ntiles; tile += tstep) {
             mbar_wait_spin(bar_tfull + 8 * as, aph, 5);
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
             const bool valid = row0 + lane < g.rows;
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + half * 128);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_NCTA + half * 64);
             uint32_t rbuf[2][32];
             tmem_ld32_issue(tbase, rbuf[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = (half * 4 + c) * 32;
+            for (int c = 0; c < 2; ++c) {
+                const int col0 = colb + c * 32;
                 tmem_ld_wait();
-                if (c < 3) {
+                if (c < 1) {
                     tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);
                 } else {
                     // every accumulator value of this stage is in registers: hand the TMEM stage back to the MMA warp
@@ -430,8 +442,8 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     stage_put_row(bufc, pk, lane);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmO, bufc, col0, row0);
-                    stage_col_sums<true, true>(bufc, lane, acc0 + 2 * c, acc1 + 2 * c);
+                    if (lane == 0 && !(g.debug & 2)) tma_store_2d(&tmO, bufc, col0, row0);
+                    if (!(g.debug & 1)) stage_col_sums<true, true>(bufc, lane, acc0 + 2 * c, acc1 + 2 * c);
                     if (g.out2) {
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
@@ -451,8 +463,8 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; ++i) sts128(stage_addr(buf0, (lane >> 2) + 8 * i, lane & 3), e[i]);
                     __syncwarp();
-                    if (c < 3) load_e(tile, c + 1);
-                    else if (tile + (int)gridDim.x < ntiles) load_e(tile + gridDim.x, 0);
+                    if (c < 1) load_e(tile, c + 1);
+                    else if (tile + tstep < ntiles) load_e(tile + tstep, 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint4 hv = lds128(stage_addr(buf0, lane, k));
@@ -495,10 +507,10 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         if (lane == 0) tma_store_wait_all();
         if (lane < 16) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int col = (half * 4 + c) * 32 + 2 * lane + j;
+                    const int col = colb + c * 32 + 2 * lane + j;
                     atomicAdd(g.stat0 + col, acc0[2 * c + j]);
                     if (EPI == TC_FWD) atomicAdd(g.stat1 + col, acc1[2 * c + j]);
                 }
@@ -760,7 +772,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     rc = k1 ? make_map(&mA1, A1, rows, k1, lda1, 128) : make_map(&mA1, A0, rows, k0, lda0, 128);
     if (rc) return rc;
-    rc = make_map(&mB, B, 256, k0 + k1, ldb, 256);
+    rc = make_map(&mB, B, 256, k0 + k1, ldb, TC_NCTA);
     if (rc) return rc;
     CUtensorMap mO, mO2;
     rc = make_map(&mO, out, rows, 256, 256, 32, 32);
@@ -769,11 +781,21 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     RowGemmArgs g;
     g.rows = (int)rows; g.kb0 = k0 / 64; g.kb_total = (k0 + k1) / 64;
-    g.nstage = g.kb_total >= 5 ? 2 : (mode == TC_FWD ? 4 : 3);
+    {
+        // everything that is left of the 227 KB after the resident weights and the staging buffers becomes A ring
+        const size_t fixed = 1024 + (size_t)g.kb_total * TC_B_BYTES + 8 * TC_NBUF * TC_STAGE_BYTES + 4096 /* static */;
+        int ns = (int)((232448 - fixed) / TC_A_BYTES);
+        g.nstage = ns > 8 ? 8 : ns;
+    }
     g.out = out; g.out2 = out2; g.vec = vec; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+        g.debug = dbg;
+    }
     const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * TC_NBUF * TC_STAGE_BYTES;
     const int ntiles = (int)pcn_cdiv(rows, 128);
-    const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    const int grid = 2 * ntiles < sm_count() ? 2 * ntiles : (sm_count() & ~1);
     const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
     if (mode == TC_FWD) {
         PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
