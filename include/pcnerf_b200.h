@@ -191,8 +191,8 @@ int pcnerf_affine_grad(const float* enc, const float* p, const float* grad_p, in
 
 /* Building blocks of the precision-1 path (TMA + tcgen05 + TMEM), exported for unit tests and reuse.
  * pcnerf_tc_rowgemm: C[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T, k0, k1 multiples of 64, k0 + k1 <= 320.
- *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 = bf16 copy or NULL;
- *     stats (2,256) f64 = column sums of (C + bias) and (C + bias)^2 (zeroed by the call).
+ *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 reserved (NULL);
+ *     stats (2,256) f64 = column sums of out and out^2 (the fp16 values; zeroed by the call).
  *   mode 1 (data gradient with the BatchNorm backward fused): A, B bf16; E (rows,256) fp16; vec = c0|c1|c2|mean [4][256];
  *     out = bf16(c0*C - c1 - (E - mean)*c2); stats[0] = column sums of out.
  * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T (bf16) * X[rows, 0:ncols] (bf16, or

@@ -99,12 +99,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+__device__ __forceinline__ void tma_store_2d_nocommit(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1)
                  : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -374,100 +374,78 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             if (++as == 2) { as = 0; aph ^= 1; }
         }
     } else {
-        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, 64-column half (warp-2)/4 of the CTA's 128 columns,
-        // two 32-column chunks
+        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4, 64-column half (warp-2)/4 of the CTA's 128 columns.
+        // Both 32-column chunks of a tile are handled together: one TMEM wait (after which the accumulator stage goes
+        // straight back to the MMA warp), one staging round trip, one bulk-store group per tile.
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int colb = nhalf * TC_NCTA + half * 64;     // first output column of this warp
         const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF * TC_STAGE_BYTES);
-        const uint32_t buf1 = buf0 + TC_STAGE_BYTES;
+        const uint32_t bufs[2] = {buf0, buf0 + TC_STAGE_BYTES};
         double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
-        // DGRAD: this warp's 32 x 64 B piece of H_{l-1} for the NEXT chunk is always in flight (8 rows x 64 B per load
-        // instruction) while the current chunk is processed
-        uint4 e[4];
-        auto load_e = [&](int tile_, int c_) {
-            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_, c0_ = colb + c_ * 32;
+        // DGRAD: this warp's 32 rows x 128 B piece of H_{l-1} for the NEXT tile is in flight (8 rows x 64 B per load
+        // instruction) while the current tile is processed
+        uint4 e[2][4];
+        auto load_e = [&](int tile_) {
+            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = (lane >> 2) + 8 * i;
-                e[i] = make_uint4(0, 0, 0, 0);
-                if (row < left_) e[i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + c0_ + (lane & 3) * 8);
-            }
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (lane >> 2) + 8 * i;
+                    e[c][i] = make_uint4(0, 0, 0, 0);
+                    if (row < left_)
+                        e[c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + colb + c * 32 + (lane & 3) * 8);
+                }
         };
-        if (EPI == TC_DGRAD && tile0 < ntiles) load_e(tile0, 0);
+        if (EPI == TC_DGRAD && tile0 < ntiles) load_e(tile0);
         for (int tile = tile0; tile < ntiles; tile += tstep) {
             mbar_wait_spin(bar_tfull + 8 * as, aph, 5);
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
             const bool valid = row0 + lane < g.rows;
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_NCTA + half * 64);
-            uint32_t rbuf[2][32];
-            tmem_ld32_issue(tbase, rbuf[0]);
+            uint32_t r[2][32];
+            tmem_ld32_issue(tbase, r[0]);
+            tmem_ld32_issue(tbase + 32, r[1]);
+            tmem_ld_wait();
+            // every accumulator value of this stage is in registers: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_tempty + 8 * as);
+                tma_store_wait_read<0>();                 // last tile's stores have read both staging buffers
+            }
+            __syncwarp();
+            uint32_t pk[2][16];
+            if (EPI == TC_FWD) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int col0 = colb + c * 32;
-                tmem_ld_wait();
-                if (c < 1) {
-                    tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), rbuf[(c + 1) & 1]);
-                } else {
-                    // every accumulator value of this stage is in registers: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-                }
-                const uint32_t* r = rbuf[c & 1];
-                float v[32];
-                uint32_t pk[16];
-                if (EPI == TC_FWD) {
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(&cvec[col0 + 4 * j4]);
-                        v[4 * j4 + 0] = valid ? __uint_as_float(r[4 * j4 + 0]) + b4.x : 0.f;
-                        v[4 * j4 + 1] = valid ? __uint_as_float(r[4 * j4 + 1]) + b4.y : 0.f;
-                        v[4 * j4 + 2] = valid ? __uint_as_float(r[4 * j4 + 2]) + b4.z : 0.f;
-                        v[4 * j4 + 3] = valid ? __uint_as_float(r[4 * j4 + 3]) + b4.w : 0.f;
+                        const float4 b4 = *reinterpret_cast<const float4*>(&cvec[colb + c * 32 + 4 * j4]);
+                        const float v0 = valid ? __uint_as_float(r[c][4 * j4 + 0]) + b4.x : 0.f;
+                        const float v1 = valid ? __uint_as_float(r[c][4 * j4 + 1]) + b4.y : 0.f;
+                        const float v2 = valid ? __uint_as_float(r[c][4 * j4 + 2]) + b4.z : 0.f;
+                        const float v3 = valid ? __uint_as_float(r[c][4 * j4 + 3]) + b4.w : 0.f;
+                        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                        pk[c][2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
+                        pk[c][2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
                     }
-                    // fp16 tile -> buf0 -> TMA store; its column statistics are read back from the same staging buffer
+            } else {
+                // this thread's row of H_{l-1}: staged through the (currently idle) output buffers, re-read row-wise
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const __half2 h2 = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-                        pk[t] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                    // with a single output the two staging buffers alternate chunk by chunk; either way the store that
-                    // last read this buffer is at least two bulk groups old
-                    const uint32_t bufc = (g.out2 || !(c & 1)) ? buf0 : buf1;
-                    if (lane == 0) tma_store_wait_read<1>();
-                    __syncwarp();
-                    stage_put_row(bufc, pk, lane);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0 && !(g.debug & 2)) tma_store_2d(&tmO, bufc, col0, row0);
-                    if (!(g.debug & 1)) stage_col_sums<true, true>(bufc, lane, acc0 + 2 * c, acc1 + 2 * c);
-                    if (g.out2) {
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
-                            pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
-                        }
-                        if (lane == 0) tma_store_wait_read<1>();  // buf1's previous store has been read out
-                        __syncwarp();
-                        stage_put_row(buf1, pk, lane);
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) tma_store_2d(&tmO2, buf1, col0, row0);
-                    }
-                } else {
-                    // this thread's row of H_{l-1}: staged through buf0 (8 rows x 64 B per load), re-read row-wise
-                    __syncwarp();
+                    for (int i = 0; i < 4; ++i) sts128(stage_addr(bufs[c], (lane >> 2) + 8 * i, lane & 3), e[c][i]);
+                __syncwarp();
+                if (tile + tstep < ntiles) load_e(tile + tstep);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) sts128(stage_addr(buf0, (lane >> 2) + 8 * i, lane & 3), e[i]);
-                    __syncwarp();
-                    if (c < 1) load_e(tile, c + 1);
-                    else if (tile + tstep < ntiles) load_e(tile + tstep, 0);
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint4 hv = lds128(stage_addr(buf0, lane, k));
+                        const uint4 hv = lds128(stage_addr(bufs[c], lane, k));
                         const __half2* hb = reinterpret_cast<const __half2*>(&hv);
                         float hf[8];
 #pragma unroll
@@ -478,28 +456,37 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         }
 #pragma unroll
                         for (int t4 = 0; t4 < 2; ++t4) {
-                            const int j = k * 8 + t4 * 4;
-                            const float4 a0 = *reinterpret_cast<const float4*>(&cvec[col0 + j]);
-                            const float4 a2 = *reinterpret_cast<const float4*>(&cvec[256 + col0 + j]);
-                            const float4 ak = *reinterpret_cast<const float4*>(&cvec[512 + col0 + j]);
-                            v[j + 0] = valid ? fmaf(a0.x, __uint_as_float(r[j + 0]), fmaf(-a2.x, hf[t4 * 4 + 0], ak.x)) : 0.f;
-                            v[j + 1] = valid ? fmaf(a0.y, __uint_as_float(r[j + 1]), fmaf(-a2.y, hf[t4 * 4 + 1], ak.y)) : 0.f;
-                            v[j + 2] = valid ? fmaf(a0.z, __uint_as_float(r[j + 2]), fmaf(-a2.z, hf[t4 * 4 + 2], ak.z)) : 0.f;
-                            v[j + 3] = valid ? fmaf(a0.w, __uint_as_float(r[j + 3]), fmaf(-a2.w, hf[t4 * 4 + 3], ak.w)) : 0.f;
+                            const int j = k * 8 + t4 * 4, col = colb + c * 32 + j;
+                            const float4 a0 = *reinterpret_cast<const float4*>(&cvec[col]);
+                            const float4 a2 = *reinterpret_cast<const float4*>(&cvec[256 + col]);
+                            const float4 ak = *reinterpret_cast<const float4*>(&cvec[512 + col]);
+                            const float v0 = valid ? fmaf(a0.x, __uint_as_float(r[c][j + 0]), fmaf(-a2.x, hf[t4 * 4 + 0], ak.x)) : 0.f;
+                            const float v1 = valid ? fmaf(a0.y, __uint_as_float(r[c][j + 1]), fmaf(-a2.y, hf[t4 * 4 + 1], ak.y)) : 0.f;
+                            const float v2 = valid ? fmaf(a0.z, __uint_as_float(r[c][j + 2]), fmaf(-a2.z, hf[t4 * 4 + 2], ak.z)) : 0.f;
+                            const float v3 = valid ? fmaf(a0.w, __uint_as_float(r[c][j + 3]), fmaf(-a2.w, hf[t4 * 4 + 3], ak.w)) : 0.f;
+                            const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+                            pk[c][k * 4 + t4 * 2] = *reinterpret_cast<const uint32_t*>(&b01);
+                            pk[c][k * 4 + t4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
                         }
                     }
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
-                        pk[t] = *reinterpret_cast<const uint32_t*>(&b2);
-                    }
-                    if (lane == 0) tma_store_wait_read<0>();      // buf1's previous store has been read out
-                    __syncwarp();
-                    stage_put_row(buf1, pk, lane);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmO, buf1, col0, row0);
-                    stage_col_sums<false, false>(buf1, lane, acc0 + 2 * c, acc1 + 2 * c);
+                __syncwarp();                              // every lane has read its row of E: the buffers can be rewritten
+            }
+            stage_put_row(bufs[0], pk[0], lane);
+            stage_put_row(bufs[1], pk[1], lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(g.debug & 2)) {
+                tma_store_2d_nocommit(&tmO, bufs[0], colb, row0);
+                tma_store_2d_nocommit(&tmO, bufs[1], colb + 32, row0);
+                tma_store_commit();
+            }
+            if (!(g.debug & 1)) {
+                if (EPI == TC_FWD) {
+                    stage_col_sums<true, true>(bufs[0], lane, acc0, acc1);
+                    stage_col_sums<true, true>(bufs[1], lane, acc0 + 2, acc1 + 2);
+                } else {
+                    stage_col_sums<false, false>(bufs[0], lane, acc0, acc1);
+                    stage_col_sums<false, false>(bufs[1], lane, acc0 + 2, acc1 + 2);
                 }
             }
             if (++as == 2) { as = 0; aph ^= 1; }
@@ -953,6 +940,7 @@ extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A
     PCN_CHECK_ARG(mode == 0 || mode == 1, "tc_rowgemm: mode must be 0 (fp16 forward) or 1 (bf16 data gradient)");
     PCN_CHECK_ARG(A0 && B && out && stats && vec && rows >= 1, "tc_rowgemm: null argument");
     PCN_CHECK_ARG(mode == 0 || E, "tc_rowgemm: data-gradient mode needs E");
+    PCN_CHECK_ARG(out2 == nullptr, "tc_rowgemm: out2 is reserved and must be NULL (activations are stored once, fp16)");
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
     return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __half*)E, rows, out,

@@ -519,10 +519,10 @@ def points(rays, depth):
 # ------------------------------------------------------------------------------- tensor-core building blocks (tests)
 
 
-def tc_rowgemm(mode, A0, B, A1=None, vec=None, E=None, want_bf16_copy=True):
+def tc_rowgemm(mode, A0, B, A1=None, vec=None, E=None, want_bf16_copy=False):
     """C (rows,256) = [A0 | A1] @ B.T on tcgen05.
-    mode 0: fp16 operands; returns (fp16(C + vec), bf16 copy or None, stats (2,256) f64 = col sums of C+vec and its square).
-    mode 1: bf16 operands, E bf16, vec = (4,256) [c0, c1, c2, mean]; returns (bf16(c0*C - c1 - (E-mean)*c2), None, stats)."""
+    mode 0: fp16 operands; returns (out = fp16(C + vec), None, stats (2,256) f64 = col sums of out and out^2).
+    mode 1: bf16 operands, E fp16, vec = (4,256) [c0, c1, c2, mean]; returns (bf16(c0*C - c1 - (E-mean)*c2), None, stats)."""
     dt = torch.float16 if mode == 0 else torch.bfloat16
     for t in (A0, B) + ((A1,) if A1 is not None else ()):
         if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):

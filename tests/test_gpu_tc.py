@@ -29,13 +29,11 @@ def test_rowgemm_forward_fp16(rows, k0, k1):
     ref = A.float() @ B.float().t() + bias
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=2e-3, atol=2e-3)   # fp16 output rounding
-    np.testing.assert_allclose(out2.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=1e-2)  # bf16 copy
     # the statistics are those of the fp16 values the next layer consumes
     o64 = out.double()
     np.testing.assert_allclose(stats[0].cpu().numpy(), o64.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(stats[1].cpu().numpy(), (o64 ** 2).sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
-    out_only, none2, _ = ops.tc_rowgemm(0, A0, B, A1, bias, want_bf16_copy=False)
-    assert none2 is None and torch.equal(out_only, out)
+    assert out2 is None
 
 
 @pytest.mark.parametrize("rows", [128, 300, 20000])
