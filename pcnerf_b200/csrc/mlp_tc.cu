@@ -518,6 +518,7 @@ struct WgradArgs {
     float* out;                 // [256][ldo] fp32, accumulated with vector atomics
     int ldo, col_off;
     int convert_b;              // X is fp16: the idle epilogue warps convert each B tile to bf16 in shared memory
+    int debug;                  // timing experiments only (PCNERF_TC_DEBUG & 4: skip the atomic reduction)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -622,7 +623,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
             mbar_wait(bar_tfull, 0, 13);
             tc_fence_after();
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < ((g.debug & 4) ? 0 : 2); ++h) {
                 const int m = h * 128 + q * 32 + lane;
                 for (int c = half; c < (N >> 5); c += 2) {
                     uint32_t r[32];
@@ -807,6 +808,11 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
     if (rc) return rc;
     WgradArgs g;
     g.rows = (int)rows; g.N = N; g.out = out; g.ldo = ldo; g.col_off = col_off; g.convert_b = x_is_bf16 ? 0 : 1;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+        g.debug = dbg;
+    }
     const int nkb = (int)pcn_cdiv(rows, 64);
     g.kb_per_cta = (int)pcn_cdiv(nkb, sm_count());
     const int grid = (int)pcn_cdiv(nkb, g.kb_per_cta);
