@@ -198,9 +198,11 @@ int pcnerf_affine_grad(const float* enc, const float* p, const float* grad_p, in
  * pcnerf_tc_wgrad: out[256, ldo] window [col_off, col_off+ncols) += DH[rows,256]^T (bf16) * X[rows, 0:ncols] (bf16, or
  *   fp16 converted to bf16 tile by tile in shared memory; row stride ldx); ncols 64 or 256; accumulated with atomics
  *   (zero `out` first).
- * pcnerf_tc_last_fault: non-zero if a tensor-core kernel aborted on a pipeline time-out (diagnostic). */
+ * pcnerf_tc_last_fault: non-zero if a tensor-core kernel aborted on a pipeline time-out (diagnostic).
+ * work: pcnerf_tc_rowgemm_work_bytes() of device scratch (CTA counter + per-CTA statistic partials). */
+size_t pcnerf_tc_rowgemm_work_bytes(void);
 int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B, const float* vec,
-                      const void* E, int64_t rows, void* out, void* out2, double* stats, void* stream);
+                      const void* E, int64_t rows, void* out, void* out2, double* stats, void* work, void* stream);
 int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows, float* out, int ldo,
                     int col_off, void* stream);
 int pcnerf_tc_last_fault(void);

@@ -54,7 +54,8 @@ SIGNATURES = {
     "pcnerf_affine_moments": (ci, [vp, i64, i64, vp, vp]),
     "pcnerf_affine_apply": (ci, [vp, i64, i64, vp, vp, vp, vp]),
     "pcnerf_affine_grad": (ci, [vp, vp, vp, i64, i64, vp, vp]),
-    "pcnerf_tc_rowgemm": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, i64, vp, vp, vp, vp]),
+    "pcnerf_tc_rowgemm_work_bytes": (sz, []),
+    "pcnerf_tc_rowgemm": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     "pcnerf_tc_wgrad": (ci, [vp, vp, ci, ci, ci, i64, vp, ci, ci, vp]),
     "pcnerf_tc_last_fault": (ci, []),
     "pcnerf_composite_fwd": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, ci, vp, f32, f32, ci, vp, vp, vp, vp, vp]),

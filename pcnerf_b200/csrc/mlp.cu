@@ -281,7 +281,7 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
     float* gvec = L.gvec(scratch);
     float* coef = L.coef(scratch);
     float* Gb[2] = {L.G(scratch, 0), L.G(scratch, 1)};
-    const int strips = (int)pcn_cdiv(rows, STRIP);
+    const int strips = (int)(pcn_cdiv(rows, STRIP) < 4 * PCN_SM_COUNT ? pcn_cdiv(rows, STRIP) : 4 * PCN_SM_COUNT);
 
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<float><<<strips, 256, 0, st>>>(grad_p, out_p, L.H(sv, 7), rows, gvec, acc_out));
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],

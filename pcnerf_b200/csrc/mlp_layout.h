@@ -20,7 +20,7 @@ struct MlpLayout {
     size_t h_bytes;             // one activation matrix
     size_t off_stats, saved_bytes;
     size_t off_wp[8], off_wf[8], off_bf, off_wout, off_coef, off_gvec, off_g[2], off_partial, off_dstat, off_tc;
-    size_t off_hf[2], off_encb; // precision 1: fp16 ping-pong activations of the forward pass; bf16 copy of enc
+    size_t off_hf[2], off_encb, off_rgwork;
     size_t n_dstat, scratch_bytes;
 
     MlpLayout(int64_t rows_, int precision_) : rows(rows_), precision(precision_) {
@@ -42,6 +42,8 @@ struct MlpLayout {
         off_tc = o;              // bf16 copies of the weights etc. for the tensor-core path
         o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
         off_hf[0] = off_hf[1] = off_encb = o;      // (unused since the weight-gradient kernel converts in shared memory)
+        off_rgwork = o;                            // row-GEMM CTA counter + per-CTA statistic partials (precision 1)
+        if (precision == 1) o += al256(256 + 160 * 2 * 128 * 8);
         scratch_bytes = o;
     }
     float* H(char* sv, int l) const { return (float*)(sv + (size_t)l * h_bytes); }
@@ -60,5 +62,6 @@ struct MlpLayout {
     double* colsum(char* sc, int l) const { return (double*)(sc + off_dstat) + 16 * 512 + (size_t)l * 256; }
     char* tc(char* sc) const { return sc + off_tc; }
     void* hf(char* sc, int i) const { return (void*)(sc + off_hf[i]); }
+    void* rgwork(char* sc) const { return (void*)(sc + off_rgwork); }
     void* encb(char* sc) const { return (void*)(sc + off_encb); }
 };

@@ -167,9 +167,11 @@ __global__ void __launch_bounds__(256) k_out_bwd_reduce(const float* __restrict_
                                                         float* __restrict__ gvec, double* __restrict__ acc) {
     __shared__ float red[8][257];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t r0 = (int64_t)blockIdx.x * STRIP;
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sg = 0.f;
-    // warp w owns rows r0 + w*8 .. + 7; four independent row loads in flight per lane
+    // Grid-stride over strips of STRIP rows (the launch caps the grid at a few CTAs per SM: every CTA ends with one fp64
+    // atomic per column, and thousands of same-address atomics serialise in L2 -- 58 us for 4096 CTAs, measured).
+    // Within a strip warp w owns rows r0 + w*8 .. + 7; four independent row loads in flight per lane.
+    for (int64_t r0 = (int64_t)blockIdx.x * STRIP; r0 < rows; r0 += (int64_t)gridDim.x * STRIP)
 #pragma unroll
     for (int b = 0; b < STRIP / 8; b += 4) {
         float hv[4][8], gr[4];
@@ -243,14 +245,14 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       double* __restrict__ colsum) {
     __shared__ float red[8][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t r0 = (int64_t)blockIdx.x * STRIP;
     float c0[8], c1[8], c2[8], mean[8], cs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int j = lane * 8 + i;
         c0[i] = coef[j]; c1[i] = coef[256 + j]; c2[i] = coef[512 + j]; mean[i] = stats[j]; cs[i] = 0.f;
     }
-    // warp w owns rows r0 + w*8 .. + 7; four independent row loads in flight per lane
+    // grid-stride over strips (see k_out_bwd_reduce); warp w owns rows r0 + w*8 .. + 7, four row loads in flight per lane
+    for (int64_t r0 = (int64_t)blockIdx.x * STRIP; r0 < rows; r0 += (int64_t)gridDim.x * STRIP)
 #pragma unroll
     for (int b = 0; b < STRIP / 8; b += 4) {
         float hv[4][8], up[4][8];

@@ -178,8 +178,11 @@ struct RowGemmArgs {
     __nv_bfloat16* out2;        // FWD: optional bf16 copy of `out` (what the backward pass reads)
     const float* vec;           // FWD: bias[256];  DGRAD: c0 | c1 | c2 | mean, [4][256]
     const __half* E;            // DGRAD: H_{l-1} [rows][256] (fp16, as the forward pass stored it)
-    double* stat0;              // [256] column sums of the fp32 result, accumulated atomically
+    double* stat0;              // [256] column sums of `out` (written once, by the last CTA to finish)
     double* stat1;              // FWD: [256] column sums of squares
+    double* partials;           // [gridDim.x][2][128] per-CTA column sums (no same-address atomics: with 296 adds per
+                                // address at kernel exit the L2 atomic unit serialised ~19 us per launch)
+    unsigned int* counter;      // zeroed by the caller; counts finished CTAs
     int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores
 };
 
@@ -492,15 +495,43 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             if (++as == 2) { as = 0; aph ^= 1; }
         }
         if (lane == 0) tma_store_wait_all();
+        // ---- column statistics: quadrant warps -> CTA partial (staging memory is free now) -> global per-CTA slot;
+        //      the last CTA to arrive adds the slots up.  No two CTAs ever touch the same address atomically.
+        double* sred = reinterpret_cast<double*>(sStage);              // [2 stats][4 quadrants][128 columns]
+        asm volatile("bar.sync 1, 256;" ::: "memory");                  // every warp's bulk stores have read the staging
         if (lane < 16) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int col = colb + c * 32 + 2 * lane + j;
-                    atomicAdd(g.stat0 + col, acc0[2 * c + j]);
-                    if (EPI == TC_FWD) atomicAdd(g.stat1 + col, acc1[2 * c + j]);
+                    const int cl = half * 64 + c * 32 + 2 * lane + j;   // column within this CTA's 128
+                    sred[(0 * 4 + q) * 128 + cl] = acc0[2 * c + j];
+                    sred[(1 * 4 + q) * 128 + cl] = acc1[2 * c + j];
                 }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int t = threadIdx.x - 64;                                 // 0..255
+        {
+            const int st = t >> 7, cl = t & 127;
+            const double v = sred[(st * 4 + 0) * 128 + cl] + sred[(st * 4 + 1) * 128 + cl] + sred[(st * 4 + 2) * 128 + cl] +
+                             sred[(st * 4 + 3) * 128 + cl];
+            g.partials[((size_t)blockIdx.x * 2 + st) * 128 + cl] = v;
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __shared__ unsigned int s_last;
+        if (t == 0) s_last = atomicAdd(g.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (s_last) {
+            __threadfence();
+            const int col = t, hsel = col >> 7, cl = col & 127;         // CTAs with (blockIdx & 1) == hsel own this column
+            double a0 = 0.0, a1 = 0.0;
+            for (int b = hsel; b < (int)gridDim.x; b += 2) {
+                a0 += g.partials[((size_t)b * 2 + 0) * 128 + cl];
+                if (EPI == TC_FWD) a1 += g.partials[((size_t)b * 2 + 1) * 128 + cl];
+            }
+            g.stat0[col] = a0;
+            if (EPI == TC_FWD) g.stat1[col] = a1;
         }
     }
     tc_fence_before();
@@ -751,9 +782,11 @@ int sm_count() {
 
 // mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias), out2 bf16 copy;  TC_DGRAD: A bf16, B bf16 -> out bf16 (BN backward
 // fused: vec = c0|c1|c2|mean, E = fp16 H)
+// `work` = >= TC_ROWGEMM_WORK_BYTES of device memory: [0,4) CTA counter (zeroed here), then the per-CTA partials
+#define TC_ROWGEMM_WORK_BYTES (256 + 160 * 2 * 128 * 8)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
                    const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
-                   double* stat1, cudaStream_t st) {
+                   double* stat1, void* work, cudaStream_t st) {
     PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && (k0 + k1) <= 320, "tc rowgemm: K must be 64..320 in 64s");
     CUtensorMap mA0, mA1, mB;
     int rc = make_map(&mA0, A0, rows, k0, lda0, 128);
@@ -776,6 +809,9 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         g.nstage = ns > 8 ? 8 : ns;
     }
     g.out = out; g.out2 = out2; g.vec = vec; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
+    g.counter = (unsigned int*)work;
+    g.partials = (double*)((char*)work + 256);
+    PCN_CUDA(cudaMemsetAsync(work, 0, 4, st));
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -857,9 +893,9 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
         double* s0 = L.dstat(scratch, l);
         const float* bias = l == 0 ? P->b[0] : L.bf(scratch, l);
         int rc;
-        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, st);
-        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, st);
-        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, st);
+        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), st);
+        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), st);
+        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), st);
         if (rc) return rc;
         const bool last = l == 7;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
@@ -896,7 +932,7 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     float* gvec = L.gvec(scratch);
     float* coef = L.coef(scratch);
     __nv_bfloat16* Gb[2] = {(__nv_bfloat16*)L.Graw(scratch, 0), (__nv_bfloat16*)L.Graw(scratch, 1)};
-    const int strips = (int)pcn_cdiv(rows, STRIP);
+    const int strips = (int)(pcn_cdiv(rows, STRIP) < 4 * PCN_SM_COUNT ? pcn_cdiv(rows, STRIP) : 4 * PCN_SM_COUNT);
     const __half* H7 = (const __half*)L.Hraw(sv, 7);
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__half><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
@@ -929,7 +965,7 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
                   k_tc_bn_bwd_coef2<<<256, 256, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
                                                        L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
         rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
-                            nullptr, L.colsum(scratch, l - 1), nullptr, st);
+                            nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), st);
         if (rc) return rc;
         cur ^= 1;
     }
@@ -940,17 +976,19 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
 // ---------------------------------------------------------------------------------------------------------------
 // Building-block entry points (unit-tested against torch.matmul; also usable on their own)
 // ---------------------------------------------------------------------------------------------------------------
+extern "C" size_t pcnerf_tc_rowgemm_work_bytes(void) { return TC_ROWGEMM_WORK_BYTES; }
+
 extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, const void* B,
                                  const float* vec, const void* E, int64_t rows, void* out, void* out2, double* stats,
-                                 void* stream) {
+                                 void* work, void* stream) {
     PCN_CHECK_ARG(mode == 0 || mode == 1, "tc_rowgemm: mode must be 0 (fp16 forward) or 1 (bf16 data gradient)");
-    PCN_CHECK_ARG(A0 && B && out && stats && vec && rows >= 1, "tc_rowgemm: null argument");
+    PCN_CHECK_ARG(A0 && B && out && stats && vec && work && rows >= 1, "tc_rowgemm: null argument");
     PCN_CHECK_ARG(mode == 0 || E, "tc_rowgemm: data-gradient mode needs E");
     PCN_CHECK_ARG(out2 == nullptr, "tc_rowgemm: out2 is reserved and must be NULL (activations are stored once, fp16)");
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
-    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __half*)E, rows, out,
-                          mode == 0 ? (__nv_bfloat16*)out2 : nullptr, stats, stats + 256, st);
+    return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __half*)E, rows, out, nullptr, stats,
+                          stats + 256, work, st);
 }
 
 extern "C" int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows,

@@ -533,8 +533,9 @@ def tc_rowgemm(mode, A0, B, A1=None, vec=None, E=None, want_bf16_copy=False):
     out = torch.empty((rows, 256), dtype=dt, device=A0.device)
     out2 = torch.empty((rows, 256), dtype=torch.bfloat16, device=A0.device) if (mode == 0 and want_bf16_copy) else None
     stats = torch.empty((2, 256), dtype=torch.float64, device=A0.device)
+    work = torch.empty(lib().pcnerf_tc_rowgemm_work_bytes(), dtype=torch.uint8, device=A0.device)
     check(lib().pcnerf_tc_rowgemm(int(mode), _p(A0), k0, _p(A1), k1, _p(B), _p(vec), _p(E), rows, _p(out), _p(out2),
-                                  _p(stats), _stream()))
+                                  _p(stats), _p(work), _stream()))
     return out, out2, stats
 
 
