@@ -180,8 +180,8 @@ struct RowGemmArgs {
     const __half* E;            // DGRAD: H_{l-1} [rows][256] (fp16, as the forward pass stored it)
     double* stat0;              // [256] column sums of `out` (written once, by the last CTA to finish)
     double* stat1;              // FWD: [256] column sums of squares
-    double* partials;           // [gridDim.x][2][128] per-CTA column sums (no same-address atomics: with 296 adds per
-                                // address at kernel exit the L2 atomic unit serialised ~19 us per launch)
+    double* partials;           // [gridDim.x][2][128] per-CTA column sums: no same-address fp64 atomics (296 adds per
+                                // address at kernel exit serialise in the L2 atomic unit)
     unsigned int* counter;      // zeroed by the caller; counts finished CTAs
     int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores
 };
