@@ -149,6 +149,9 @@ typedef struct pcnerf_mlp_params {
     int training;                       /* 1: batch statistics of this chunk; 0: running statistics */
     int precision;                      /* 0: fp32 CUDA-core GEMM (1e-5 gate); 1: tcgen05 GEMM, fp16 operands forward /
                                            bf16 gradients, fp32 accumulation (1e-3 gate) */
+    int prepared;                       /* 1: `scratch` still holds the padded / transposed weight copies written by the
+                                           previous call with these same weights (next chunk of the same pass): skip
+                                           re-deriving them.  0 is always safe. */
 } pcnerf_mlp_params;
 
 typedef struct pcnerf_mlp_grads {       /* accumulated (+=) by pcnerf_mlp_backward */

@@ -17,7 +17,7 @@ vp, ci, i64, f32, f64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctype
 class MlpParams(ctypes.Structure):
     _fields_ = [("W", vp * NLIN), ("b", vp * NLIN), ("gamma", vp * NBN), ("beta", vp * NBN),
                 ("running_mean", vp * NBN), ("running_var", vp * NBN), ("num_batches_tracked", vp * NBN),
-                ("momentum", f32), ("eps", f32), ("training", ci), ("precision", ci)]
+                ("momentum", f32), ("eps", f32), ("training", ci), ("precision", ci), ("prepared", ci)]
 
 
 class MlpGrads(ctypes.Structure):

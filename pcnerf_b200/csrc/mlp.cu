@@ -230,7 +230,7 @@ extern "C" int pcnerf_mlp_forward(const pcnerf_mlp_params* P, const void* enc, i
     char* scratch = (char*)scratch_v;
     char* sv = (char*)saved;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
-    prep_weights(P, L, scratch, st);
+    if (!P->prepared) prep_weights(P, L, scratch, st);
     const float* encf = (const float*)enc;
     for (int l = 0; l < 8; ++l) {
         GemmArgs g = {};
@@ -276,7 +276,7 @@ extern "C" int pcnerf_mlp_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_
     char* sv = (char*)saved;
     const float* encf = (const float*)enc;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * L.n_dstat, st));
-    prep_weights(P, L, scratch, st);
+    if (!P->prepared) prep_weights(P, L, scratch, st);
     double* acc_out = L.dstat(scratch, 8);            // 257 (+pad) doubles
     float* gvec = L.gvec(scratch);
     float* coef = L.coef(scratch);

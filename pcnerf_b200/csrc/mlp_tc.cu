@@ -718,6 +718,50 @@ __global__ void __launch_bounds__(256) k_tc_bn_bwd_coef2(const float* __restrict
     coef[768 + n] = mean;
 }
 
+// Per layer, after the weight-gradient GEMM: dW_l / db_l from the raw product (x a_{l-1}, + db (x) s_{l-1}) AND the BN(l-1)
+// backward coefficients (see above) in one pass over `part`.  One block per padded input column, one thread per output row.
+__global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __restrict__ part, const double* __restrict__ colsum,
+                                                         const float* __restrict__ prev_stats, const float* __restrict__ Wp,
+                                                         int64_t rows, float* __restrict__ dW, float* __restrict__ db,
+                                                         float* __restrict__ dgamma_prev, float* __restrict__ dbeta_prev,
+                                                         float* __restrict__ coef) {
+    __shared__ double r0[8], r1[8];
+    const int kin = mlp_kin(l), kpad = mlp_kpad(l);
+    const int c = blockIdx.x, o = threadIdx.x;
+    int real = c, hid = c;
+    bool is_hidden = true, live = true;
+    if (l == 0) { is_hidden = false; live = c < 63; }
+    else if (l == 4) {
+        if (c < 64) { is_hidden = false; live = c != 63; }
+        else { real = c - 1; hid = c - 64; }
+    }
+    const float v = part[(size_t)o * kpad + c];
+    const double cs = colsum[o];
+    const float dbias = (float)cs;
+    if (live) dW[o * kin + real] += is_hidden ? v * prev_stats[512 + hid] + dbias * prev_stats[768 + hid] : v;
+    if (c == 0) db[o] += dbias;
+    if (!is_hidden) return;                              // (whole block: uniform)
+    const float w = Wp[(size_t)o * kpad + c];
+    double st0 = warp_sum_d(cs * (double)w), st1 = warp_sum_d((double)w * (double)v);
+    if ((o & 31) == 0) { r0[o >> 5] = st0; r1[o >> 5] = st1; }
+    __syncthreads();
+    if (o != 0) return;
+    st0 = 0.0;
+    st1 = 0.0;
+    for (int k = 0; k < 8; ++k) { st0 += r0[k]; st1 += r1[k]; }
+    const int n = hid;
+    const float mean = prev_stats[n], invstd = prev_stats[256 + n], a = prev_stats[512 + n];
+    const float dbt = (float)st0;
+    const float dg = invstd * (float)(st1 - (double)mean * st0);
+    dgamma_prev[n] += dg;
+    dbeta_prev[n] += dbt;
+    const float B = (float)rows;
+    coef[n] = a;
+    coef[256 + n] = a * dbt / B;
+    coef[512 + n] = a * invstd * dg / B;
+    coef[768 + n] = mean;
+}
+
 struct PrepTArgs {
     const float* Wp[8];
     __nv_bfloat16* WT[8];
@@ -882,8 +926,10 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     char* sv = (char*)saved;
     const __half* ench = (const __half*)enc;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
-    tc_prep_weights(P, L, scratch, st);
-    PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
+    if (!P->prepared) {
+        tc_prep_weights(P, L, scratch, st);
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
+    }
     // H_l is stored once, fp16 (10-bit mantissa for the 1e-3 gate): it is the next layer's operand and what the backward
     // pass re-reads (the weight-gradient kernel converts its tiles to bf16 in shared memory)
     for (int l = 0; l < 8; ++l) {
@@ -922,8 +968,8 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     char* sv = (char*)saved;
     const __half* ench = (const __half*)enc;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * L.n_dstat, st));
-    tc_prep_weights(P, L, scratch, st);
-    {
+    if (!P->prepared) {
+        tc_prep_weights(P, L, scratch, st);
         PrepTArgs pa;
         for (int l = 0; l < 8; ++l) { pa.Wp[l] = L.Wp(scratch, l); pa.WT[l] = tc_WT(L, scratch, l); }
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_bwd<<<dim3(8, 8, 7), dim3(32, 8), 0, st>>>(pa));
@@ -958,12 +1004,11 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
         if (l != 0) rc = launch_wgrad(DH, Hprev, 256, 256, 0, rows, part, kpad, off, st);
         if (rc) return rc;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_wgrad_finalize<<<128, 256, 0, st>>>(l, part, 1, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
-                                                         G->dW[l], G->db[l]));
+                  k_tc_wgrad_finish<<<kpad, 256, 0, st>>>(l, part, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
+                                                          L.Wp(scratch, l), rows, G->dW[l], G->db[l],
+                                                          l == 0 ? nullptr : G->dgamma[l - 1], l == 0 ? nullptr : G->dbeta[l - 1],
+                                                          coef));
         if (l == 0) break;
-        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
-                  k_tc_bn_bwd_coef2<<<256, 256, 0, st>>>(L.Wp(scratch, l), kpad, off, part, L.colsum(scratch, l), rows,
-                                                       L.stats(sv, l - 1), G->dgamma[l - 1], G->dbeta[l - 1], coef));
         rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
                             nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), st);
         if (rc) return rc;

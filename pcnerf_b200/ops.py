@@ -294,6 +294,7 @@ def _mlp_params(tensors, buffers, training, precision, momentum=0.1, eps=1e-5):
         P.running_var[l] = buffers[1][l].data_ptr()
         P.num_batches_tracked[l] = buffers[2][l].data_ptr()
     P.momentum, P.eps, P.training, P.precision = momentum, eps, int(training), int(precision)
+    P.prepared = 0
     return P
 
 
@@ -327,6 +328,7 @@ class MLPFunction(torch.autograd.Function):
             check(lib().pcnerf_mlp_forward(ctypes.byref(P), ctypes.c_void_p(enc.data_ptr() + i * 64 * esz), r,
                                            ctypes.c_void_p(out.data_ptr() + i * 4), _p(sv), sv.numel(), _p(scratch),
                                            scratch.numel(), _stream()))
+            P.prepared = 1              # later chunks of this pass reuse the weight copies in `scratch`
             _count(18)
         ctx.saved_chunks = saved
         ctx.meta = (chunk, precision, buffers, rows)
@@ -361,6 +363,7 @@ class MLPFunction(torch.autograd.Function):
                                             r, ctypes.c_void_p(out.data_ptr() + i * 4),
                                             ctypes.c_void_p(gp.data_ptr() + i * 4), _p(sv), sv.numel(), _p(scratch),
                                             scratch.numel(), _stream()))
+            P.prepared = 1
             _count(45)
         ctx.saved_chunks = None
         return (None, None, None, None, None) + tuple(views)
