@@ -34,16 +34,18 @@ struct MlpLayout {
         off_bf = o; o += al256(8 * 256 * 4);
         off_wout = o; o += al256(512 * 4);
         off_coef = o; o += al256(4 * 256 * 4);
-        off_gvec = o; o += al256((size_t)rows * 4);
-        for (int i = 0; i < 2; ++i) { off_g[i] = o; o += al256((size_t)rows * 256 * esz); }
+        // rows-independent regions first, so that their offsets are the same for every chunk of a pass (the weight
+        // copies written for the first chunk are reused by the following, possibly shorter, ones: params.prepared)
         off_partial = o; o += al256((size_t)MLP_MAX_SPLITS * 256 * 320 * 4);
         n_dstat = 16 * 512 + 8 * 256;
         off_dstat = o; o += al256(n_dstat * sizeof(double));
-        off_tc = o;              // bf16 copies of the weights etc. for the tensor-core path
+        off_tc = o;              // 16-bit copies of the weights for the tensor-core path
         o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
         off_hf[0] = off_hf[1] = off_encb = o;      // (unused since the weight-gradient kernel converts in shared memory)
         off_rgwork = o;                            // row-GEMM CTA counter + per-CTA statistic partials (precision 1)
         if (precision == 1) o += al256(256 + 160 * 2 * 128 * 8);
+        off_gvec = o; o += al256((size_t)rows * 4);
+        for (int i = 0; i < 2; ++i) { off_g[i] = o; o += al256((size_t)rows * 256 * esz); }
         scratch_bytes = o;
     }
     float* H(char* sv, int l) const { return (float*)(sv + (size_t)l * h_bytes); }
