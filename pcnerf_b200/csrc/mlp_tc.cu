@@ -111,10 +111,6 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// pull a box into L2 without touching shared memory (deepens the load pipeline beyond the smem ring)
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -325,16 +321,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(smem_u32(sB + (size_t)kb * TC_B_BYTES), &tmB, bar_bfull, kb * 64, nhalf * TC_NCTA);
         }
-        // The smem ring holds at most one tile of A; the tiles this CTA will need after that are pulled into L2 two
-        // tiles ahead, so the ring refills at L2 latency and HBM always has ~128 KB per SM in flight.
-        auto prefetch_tile = [&](int t) {
-            if (t < ntiles)
-                for (int kb = 0; kb < KB; ++kb) {
-                    if (kb < g.kb0) tma_prefetch_l2_2d(&tmA0, kb * 64, t * 128);
-                    else tma_prefetch_l2_2d(&tmA1, (kb - g.kb0) * 64, t * 128);
-                }
-        };
-        (void)prefetch_tile;      // measured: L2 prefetch two tiles ahead made the kernel 10 % slower (profiles/README.md)
+        // (an extra `cp.async.bulk.prefetch.tensor` of the tiles after the ring into L2 was measured 10 % slower)
         int s = 0;
         uint32_t ph = 0;
         for (int tile = tile0; tile < ntiles; tile += tstep) {
@@ -687,37 +674,7 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
 //   sum_r G[r,n]             = sum_o colsum_l[o] W_l[o,n]                 (colsum_l = column sums of DH_l)
 //   sum_r G[r,n] H_{l-1}[r,n] = sum_o W_l[o,n] (DH_l^T H_{l-1})[o,n]        (the raw weight gradient of layer l)
 // so the data-gradient GEMM can apply the BN backward in its own epilogue.
-__global__ void __launch_bounds__(256) k_tc_bn_bwd_coef2(const float* __restrict__ Wp, int kpad, int off,
-                                                         const float* __restrict__ part, const double* __restrict__ colsum,
-                                                         int64_t rows, const float* __restrict__ stats,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                         float* __restrict__ coef /* c0 | c1 | c2 | mean */) {
-    // one block per column n, one thread per output row o
-    __shared__ double r0[8], r1[8];
-    const int n = blockIdx.x, o = threadIdx.x;
-    const float w = Wp[(size_t)o * kpad + off + n];
-    double st0 = colsum[o] * (double)w;
-    double st1 = (double)w * (double)part[(size_t)o * kpad + off + n];
-    st0 = warp_sum_d(st0);
-    st1 = warp_sum_d(st1);
-    if ((o & 31) == 0) { r0[o >> 5] = st0; r1[o >> 5] = st1; }
-    __syncthreads();
-    if (o != 0) return;
-    st0 = 0.0;
-    st1 = 0.0;
-    for (int k = 0; k < 8; ++k) { st0 += r0[k]; st1 += r1[k]; }
-    const float mean = stats[n], invstd = stats[256 + n], a = stats[512 + n];
-    const float db = (float)st0;
-    const float dg = invstd * (float)(st1 - (double)mean * st0);
-    dgamma[n] += dg;
-    dbeta[n] += db;
-    const float B = (float)rows;
-    coef[n] = a;
-    coef[256 + n] = a * db / B;
-    coef[512 + n] = a * invstd * dg / B;
-    coef[768 + n] = mean;
-}
-
+//
 // Per layer, after the weight-gradient GEMM: dW_l / db_l from the raw product (x a_{l-1}, + db (x) s_{l-1}) AND the BN(l-1)
 // backward coefficients (see above) in one pass over `part`.  One block per padded input column, one thread per output row.
 __global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __restrict__ part, const double* __restrict__ colsum,
