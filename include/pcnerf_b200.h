@@ -256,6 +256,17 @@ int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in_child, con
 /* points = o + depth*d (:674-684). */
 int pcnerf_points(const float* rays, int ld, int64_t n, const float* depth, float* out_xyz, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K6  point-cloud metrics (nof/criteria/pointcloud_metrics.py:5-49, nof/criteria/metrics.py:24-32).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* nn_correspondance (pointcloud_metrics.py:5-33): for each vertex of verts2 (n2,3) f64 the exact nearest vertex of verts1
+ * (n1,3) f64 -> out_idx (n2) i32, out_dist (n2) f64 = sqrt of the squared L2 distance.  n1 == 0 or n2 == 0: no output. */
+int pcnerf_nn_correspondance(const double* verts1, int64_t n1, const double* verts2, int64_t n2, int32_t* out_idx,
+                             double* out_dist, void* stream);
+/* sums2 = {sum dist, count(dist < threshold)} (the ingredients of eval_pts, pointcloud_metrics.py:39-49). */
+int pcnerf_dist_stats(const double* dist, int64_t n, double threshold, double* sums2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -699,3 +699,33 @@ def eval_batches(rays, batch_size_set):
             out.append((i, n))
             i = n
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Point-cloud metrics.  Parity note: nn_correspondance needs Open3D (KDTreeFlann, not
+# installed here; no pinned version in the reference), so this row is anchored on the algorithm it runs --
+# FLANN's exact kd-tree 1-NN search (SearchParams checks = -1, eps = 0) in float64 -- restated with SciPy's
+# exact cKDTree, not on executed reference output.
+# --------------------------------------------------------------------------------------------------
+
+
+def nn_correspondance(verts1, verts2):
+    """nof/criteria/pointcloud_metrics.py:5-33 -> (indices, distances) as numpy arrays."""
+    from scipy.spatial import cKDTree
+    verts1 = np.asarray(verts1, dtype=np.float64).reshape(-1, 3)
+    verts2 = np.asarray(verts2, dtype=np.float64).reshape(-1, 3)
+    if len(verts1) == 0 or len(verts2) == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0)
+    dist, idx = cKDTree(verts1).query(verts2, k=1)
+    return idx, dist
+
+
+def eval_pts(pts1, pts2, threshold=0.2):
+    """nof/criteria/pointcloud_metrics.py:39-49."""
+    _, dist1 = nn_correspondance(pts1, pts2)
+    _, dist2 = nn_correspondance(pts2, pts1)
+    precision = np.mean((dist1 < threshold).astype('float'))
+    recall = np.mean((dist2 < threshold).astype('float'))
+    fscore = 2 * precision * recall / (precision + recall)
+    cd = np.mean(dist1) + np.mean(dist2)
+    return cd, fscore

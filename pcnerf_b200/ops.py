@@ -551,3 +551,24 @@ def tc_wgrad(DH, X, ncols, out, col_off=0):
     check(lib().pcnerf_tc_wgrad(_p(DH), _p(X), X.shape[1], int(ncols), int(X.dtype == torch.bfloat16), DH.shape[0], _p(out),
                                 out.shape[1], int(col_off), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------- K6 point-cloud metrics
+
+
+def nn_correspondance(verts1, verts2):
+    """For each vertex of verts2 the exact nearest vertex of verts1 -> (indices (n2,) i32, distances (n2,) f64)."""
+    v1 = _f64(verts1).reshape(-1, 3)
+    v2 = _f64(verts2).reshape(-1, 3)
+    idx = torch.empty(v2.shape[0], dtype=torch.int32, device=v2.device)
+    dist = torch.empty(v2.shape[0], dtype=torch.float64, device=v2.device)
+    check(lib().pcnerf_nn_correspondance(_p(v1), v1.shape[0], _p(v2), v2.shape[0], _p(idx), _p(dist), _stream()))
+    return idx, dist
+
+
+def dist_stats(dist, threshold):
+    """(sum of distances, number below threshold) as a (2,) f64 device tensor."""
+    dist = dist.contiguous()
+    out = torch.empty(2, dtype=torch.float64, device=dist.device)
+    check(lib().pcnerf_dist_stats(_p(dist), dist.shape[0], float(threshold), _p(out), _stream()))
+    return out
