@@ -444,7 +444,7 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
     from pcnerf_b200 import eval_kitti_render as ev
     from pcnerf_b200 import synth
     base_phys = 4096
-    rows, other, _ = synth.synth_infer_rows(500 + rank, base_phys)
+    rows, other, true_range = synth.synth_infer_rows(500 + rank, base_phys)
     reps = max(1, a.infer_rays // base_phys)
     rows = np.tile(rows, (reps, 1))
     other = np.tile(other, reps)
@@ -472,9 +472,20 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
     ms = torch.tensor([e0.elapsed_time(e1) / reps_t], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # downstream step: Chamfer distance / F-score of the rendered cloud against the returns
+    from pcnerf_b200.nof.criteria.metrics import eval_points
+    heads = np.nonzero(rows[:base_phys * 40, 12] >= 0)[0][:base_phys]
+    gt = torch.from_numpy(np.tile(rows[heads, :3] + rows[heads, 3:6] * true_range[:, None].astype(np.float32), (reps, 1))).to(dev)
+    eval_points(pts, gt)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cd, fscore = eval_points(pts, gt)
+    torch.cuda.synchronize()
+    metrics_ms = (time.perf_counter() - t0) * 1e3
     mc.train()
     mf.train()
-    return {"metric": "depth-inference rays/s (physical rays, two-step search)", "value": world * n_phys / (float(ms.item()) * 1e-3),
+    return {"metric": "depth-inference rays/s (physical rays, two-step search)", "eval_pts_ms": metrics_ms,
+            "chamfer_untrained_net": cd, "value": world * n_phys / (float(ms.item()) * 1e-3),
             "unit": "rays/s", "ms_per_frame": float(ms.item()), "physical_rays_per_gpu": n_phys,
             "candidate_rows_per_gpu": int(rows.shape[0]), "N_samples": S, "N_importance": NI, "batch_rows": 18432,
             "precision": a.precision}
