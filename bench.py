@@ -373,12 +373,23 @@ def run_b200(a):
         except (OSError, ValueError, KeyError):
             pass
         all_ms = max(sum(v[0] for v in prof.values()), 1e-9)
+        # mean algorithmic bytes of one forward row GEMM of this workload: 7 of 8 layers read (rows,256) and write
+        # (rows,256) 16-bit activations, layer 0 reads the (rows,64) encoding, layer 4 reads both
+        esz = 2 if a.precision == "tc" else 4
+        alg_bytes = CHUNK * esz * (7 * 256 + 2 * 64 + 8 * 256) / 8.0 if a.precision in ("tc", "fp32") else 0
         roofline = {"kernel": "mlp forward row GEMM (%s)" % ("k_tc_rowgemm<FWD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32"),
                     "bound": "tensor", "achieved": achieved, "peak": peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "launches_per_step": f_n / psteps, "us_per_launch": 1e3 * f_ms / max(f_n, 1),
                     "gflop_per_launch": f_fl / max(f_n, 1) / 1e9, "share_of_step": f_ms / all_ms,
+                    # the layered GEMM moves one activation matrix in and one out per layer (train-mode BN needs a
+                    # chunk-wide reduction between layers): its arithmetic intensity caps it below the tensor peak
+                    "hbm": ({"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes * f_n / (f_ms * 1e-3) / 1e9,
+                             "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)),
+                             "frac": alg_bytes * f_n / (f_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
+                             "attainable_tflops": (f_fl / max(f_n, 1)) / alg_bytes * float(peaks.get("hbm_gbs", 6650.0)) / 1e3}
+                            if alg_bytes else None),
                     "all_mlp_gemms": {"achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
                                       "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms > 0 else 0.0,
                                       "share_of_step": g_ms / all_ms}}
