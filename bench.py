@@ -453,6 +453,7 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
     rays/s counts PHYSICAL rays.  Timed with the candidate rows already resident in HBM."""
     import torch.distributed as dist
     from pcnerf_b200 import eval_kitti_render as ev
+    from pcnerf_b200 import ops as ops_mod
     from pcnerf_b200 import synth
     base_phys = 4096
     rows, other, true_range = synth.synth_infer_rows(500 + rank, base_phys)
@@ -493,9 +494,25 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
     cd, fscore = eval_points(pts, gt)
     torch.cuda.synchronize()
     metrics_ms = (time.perf_counter() - t0) * 1e3
+    # upstream step (K1, eval_kitti_render.py:353-461): candidate-group construction for one frame of raw rays against
+    # ~200 child AABBs (parent slab test, 0.65 m prefilter, exactly-two-hits intersection, grow-until-hit fallback, sort)
+    scene = synth.make_scene(900 + rank, K_BOXES, synth.KITTI_PARENT)
+    fp = synth.make_points(scene, 5 + rank, n_phys)
+    fd, fr = synth.rays_from_points(scene.origin, fp)
+    sbl = scene.child_bounds + np.array([-0.025] * 3 + [0.025] * 3)
+    f64 = dict(dtype=torch.float64, device=dev)
+    g_args = (torch.tensor(scene.origin, **f64), torch.tensor(fd, **f64), torch.tensor(fr, **f64),
+              torch.tensor(scene.child_bounds, **f64), torch.tensor(sbl, **f64), scene.parent_min, scene.parent_max, 2, 0.05, 0.65)
+    g_rows = ops_mod.aabb_build_groups(*g_args)[0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ops_mod.aabb_build_groups(*g_args)
+    torch.cuda.synchronize()
+    groups_ms = (time.perf_counter() - t0) * 1e3
     mc.train()
     mf.train()
     return {"metric": "depth-inference rays/s (physical rays, two-step search)", "eval_pts_ms": metrics_ms,
+            "aabb_groups_ms": groups_ms, "aabb_groups_rows": int(g_rows.shape[0]),
             "chamfer_untrained_net": cd, "value": world * n_phys / (float(ms.item()) * 1e-3),
             "unit": "rays/s", "ms_per_frame": float(ms.item()), "physical_rays_per_gpu": n_phys,
             "candidate_rows_per_gpu": int(rows.shape[0]), "N_samples": S, "N_importance": NI, "batch_rows": 18432,

@@ -16,7 +16,7 @@
 //   pcnerf_affine_grad    : per chunk, partial sums of g_r x_r and g_r,  g_r = dL/dp_r * p_r (1 - p_r)
 #include "common.cuh"
 
-#define AFF_PARTS 16            // CTAs (partial results) per chunk
+#define AFF_PARTS 64            // CTAs (partial results) per chunk: enough CTAs to fill the machine several times over
 #define AFF_SUB 32              // rows per shared-memory sub-tile
 #define AFF_FLUSH 256           // rows accumulated in fp32 before being folded into the fp64 accumulators
 
