@@ -361,6 +361,12 @@ def run_b200(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except (OSError, ValueError):
             pass
+        # HBM-bound kernel classes: algorithmic bytes (counted by the library per launch) / device time
+        for k in ("sample_encode", "composite_fwd", "composite_bwd", "aabb", "search"):
+            if k in kernels and prof[k][0] > 0 and prof[k][2] > 0:
+                gbs = prof[k][2] / (prof[k][0] * 1e-3) / 1e9
+                kernels[k]["algorithmic_gbs"] = gbs
+                kernels[k]["hbm_frac"] = gbs / float(peaks.get("hbm_gbs", 6650.0))
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         # dominant kernel = the forward row GEMM (k_tc_rowgemm<FWD> / k_gemm<fwd>): FLOPs per launch / mean launch time
         f_ms, f_n, f_fl = prof["mlp_gemm_fwd"]

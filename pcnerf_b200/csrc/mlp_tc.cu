@@ -99,6 +99,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// same, with an L2 eviction-priority hint (policy constants as CUTLASS's CacheHintSm90 encodes them)
+#define TC_L2_EVICT_FIRST 0x12F0000000000000ull
+#define TC_L2_EVICT_LAST 0x14F0000000000000ull
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d_nocommit(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1)
@@ -180,7 +189,29 @@ struct RowGemmArgs {
                                 // address at kernel exit serialise in the L2 atomic unit)
     unsigned int* counter;      // zeroed by the caller; counts finished CTAs
     int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores
+    int sched;                  // row-tile order of a CTA pair: 0 interleaved (pair, pair + npairs, ...), 1 contiguous slab
+                                // walked upwards, 2 contiguous slab walked downwards (see tile_plan)
+    int hint;                   // 1: the A tiles are not read again soon -> L2 evict_first, so that the freshly WRITTEN
+                                // output matrix is what stays in the 126 MB L2 for the next kernel
 };
+
+// Which row tiles a CTA pair processes, in which order.  Consecutive kernels of a chunk walk their slabs in opposite
+// directions (forward layer l reads what layer l-1 wrote last first; the data-gradient GEMM re-reads DH_l / H_{l-1} in the
+// reverse of the weight-gradient kernel's order), so the tail of the previous kernel's traffic is still in L2.
+struct TilePlan { int first, step, count; };
+__device__ __forceinline__ TilePlan tile_plan(int sched, int ntiles, int pair, int npairs) {
+    TilePlan p;
+    if (sched == 0) {
+        p.first = pair; p.step = npairs; p.count = pair < ntiles ? (ntiles - 1 - pair) / npairs + 1 : 0;
+    } else {
+        const int per = (ntiles + npairs - 1) / npairs;
+        const int lo = pair * per, hi = min(ntiles, lo + per);
+        p.count = hi > lo ? hi - lo : 0;
+        if (sched == 1) { p.first = lo; p.step = 1; }
+        else { p.first = hi - 1; p.step = -1; }
+    }
+    return p;
+}
 
 #define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
 #define TC_NBUF 2               // staging buffers per epilogue warp
@@ -312,7 +343,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const uint32_t tmem_base = tmem_slot;
     const int ntiles = (g.rows + 127) >> 7;
     const int nhalf = blockIdx.x & 1;                     // which 128 output columns this CTA owns
-    const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;
+    const TilePlan tp = tile_plan(g.sched, ntiles, blockIdx.x >> 1, gridDim.x >> 1);
 
     if (warp == 0) {
         // ===== TMA producer
@@ -324,13 +355,16 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         // (an extra `cp.async.bulk.prefetch.tensor` of the tiles after the ring into L2 was measured 10 % slower)
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = tile0; tile < ntiles; tile += tstep) {
+        for (int it = 0; it < tp.count; ++it) {
+            const int tile = tp.first + it * tp.step;
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
                 if (lane == 0) {
                     mbar_expect_tx(bar_full + 8 * s, TC_A_BYTES);
-                    if (kb < g.kb0) tma_load_2d(smem_u32(sA + (size_t)s * TC_A_BYTES), &tmA0, bar_full + 8 * s, kb * 64, tile * 128);
-                    else tma_load_2d(smem_u32(sA + (size_t)s * TC_A_BYTES), &tmA1, bar_full + 8 * s, (kb - g.kb0) * 64, tile * 128);
+                    const CUtensorMap* m = kb < g.kb0 ? &tmA0 : &tmA1;
+                    const int c0 = (kb < g.kb0 ? kb : kb - g.kb0) * 64;
+                    if (g.hint) tma_load_2d_hint(smem_u32(sA + (size_t)s * TC_A_BYTES), m, bar_full + 8 * s, c0, tile * 128, TC_L2_EVICT_FIRST);
+                    else tma_load_2d(smem_u32(sA + (size_t)s * TC_A_BYTES), m, bar_full + 8 * s, c0, tile * 128);
                 }
                 __syncwarp();
                 if (++s == nstage) { s = 0; ph ^= 1; }
@@ -342,7 +376,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         mbar_wait(bar_bfull, 0, 2);
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
-        for (int tile = tile0; tile < ntiles; tile += tstep) {
+        for (int it = 0; it < tp.count; ++it) {
             mbar_wait_spin(bar_tempty + 8 * as, aph ^ 1, 3);
             tc_fence_after();
             const uint32_t dcol = tmem_base + (uint32_t)as * TC_NCTA;
@@ -385,12 +419,15 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 for (int i = 0; i < 4; ++i) {
                     const int row = (lane >> 2) + 8 * i;
                     e[c][i] = make_uint4(0, 0, 0, 0);
-                    if (row < left_)
-                        e[c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + colb + c * 32 + (lane & 3) * 8);
+                    if (row < left_) {
+                        const uint4* src = reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + colb + c * 32 + (lane & 3) * 8);
+                        e[c][i] = g.hint ? __ldcs(src) : *src;      // last use of H_{l-1} in this pass
+                    }
                 }
         };
-        if (EPI == TC_DGRAD && tile0 < ntiles) load_e(tile0);
-        for (int tile = tile0; tile < ntiles; tile += tstep) {
+        if (EPI == TC_DGRAD && tp.count > 0) load_e(tp.first);
+        for (int it = 0; it < tp.count; ++it) {
+            const int tile = tp.first + it * tp.step;
             mbar_wait_spin(bar_tfull + 8 * as, aph, 5);
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
@@ -430,7 +467,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; ++i) sts128(stage_addr(bufs[c], (lane >> 2) + 8 * i, lane & 3), e[c][i]);
                 __syncwarp();
-                if (tile + tstep < ntiles) load_e(tile + tstep);
+                if (it + 1 < tp.count) load_e(tile + tp.step);
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -519,6 +556,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             }
             g.stat0[col] = a0;
             if (EPI == TC_FWD) g.stat1[col] = a1;
+            if (t == 0) *g.counter = 0;                                 // ready for the next launch on this stream
         }
     }
     tc_fence_before();
@@ -677,7 +715,7 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
 //
 // Per layer, after the weight-gradient GEMM: dW_l / db_l from the raw product (x a_{l-1}, + db (x) s_{l-1}) AND the BN(l-1)
 // backward coefficients (see above) in one pass over `part`.  One block per padded input column, one thread per output row.
-__global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __restrict__ part, const double* __restrict__ colsum,
+__global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, float* __restrict__ part, const double* __restrict__ colsum,
                                                          const float* __restrict__ prev_stats, const float* __restrict__ Wp,
                                                          int64_t rows, float* __restrict__ dW, float* __restrict__ db,
                                                          float* __restrict__ dgamma_prev, float* __restrict__ dbeta_prev,
@@ -693,6 +731,7 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __r
         else { real = c - 1; hid = c - 64; }
     }
     const float v = part[(size_t)o * kpad + c];
+    part[(size_t)o * kpad + c] = 0.f;                    // the next layer's split-K accumulation starts from zero
     const double cs = colsum[o];
     const float dbias = (float)cs;
     if (live) dW[o * kin + real] += is_hidden ? v * prev_stats[512 + hid] + dbias * prev_stats[768 + hid] : v;
@@ -771,6 +810,12 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int ld, i
     return 0;
 }
 
+int tc_sched_mode() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("PCNERF_TC_SCHED"); m = e ? atoi(e) : 2; if (m < 0 || m > 2) m = 2; }
+    return m;
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -787,7 +832,7 @@ int sm_count() {
 #define TC_ROWGEMM_WORK_BYTES (256 + 160 * 2 * 128 * 8)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
                    const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
-                   double* stat1, void* work, cudaStream_t st) {
+                   double* stat1, void* work, int dir, cudaStream_t st) {
     PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && (k0 + k1) <= 320, "tc rowgemm: K must be 64..320 in 64s");
     CUtensorMap mA0, mA1, mB;
     int rc = make_map(&mA0, A0, rows, k0, lda0, 128);
@@ -810,9 +855,14 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         g.nstage = ns > 8 ? 8 : ns;
     }
     g.out = out; g.out2 = out2; g.vec = vec; g.E = E; g.stat0 = stat0; g.stat1 = stat1;
-    g.counter = (unsigned int*)work;
+    g.counter = (unsigned int*)work;            // zero on entry (the caller clears it once; the last CTA re-arms it)
     g.partials = (double*)((char*)work + 256);
-    PCN_CUDA(cudaMemsetAsync(work, 0, 4, st));
+    {
+        // PCNERF_TC_SCHED: 0 = interleaved row tiles, 1 = serpentine slabs, 2 (default) = serpentine slabs + L2 hints
+        const int m = tc_sched_mode();
+        g.sched = m == 0 ? 0 : (dir ? 2 : 1);
+        g.hint = m == 2 ? 1 : 0;
+    }
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -883,6 +933,7 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     char* sv = (char*)saved;
     const __half* ench = (const __half*)enc;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
+    PCN_CUDA(cudaMemsetAsync(L.rgwork(scratch), 0, 4, st));
     if (!P->prepared) {
         tc_prep_weights(P, L, scratch, st);
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
@@ -896,9 +947,9 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
         double* s0 = L.dstat(scratch, l);
         const float* bias = l == 0 ? P->b[0] : L.bf(scratch, l);
         int rc;
-        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), st);
-        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), st);
-        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), st);
+        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st);
+        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st);
+        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st);
         if (rc) return rc;
         const bool last = l == 7;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
@@ -925,6 +976,9 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     char* sv = (char*)saved;
     const __half* ench = (const __half*)enc;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * L.n_dstat, st));
+    PCN_CUDA(cudaMemsetAsync(L.rgwork(scratch), 0, 4, st));
+    // the split-K accumulator of the weight-gradient GEMM: cleared once, then every k_tc_wgrad_finish zeroes what it read
+    PCN_CUDA(cudaMemsetAsync(L.partial(scratch), 0, (size_t)256 * 320 * sizeof(float), st));
     if (!P->prepared) {
         tc_prep_weights(P, L, scratch, st);
         PrepTArgs pa;
@@ -954,7 +1008,6 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
         const __nv_bfloat16* DH = Gb[cur];
         const int kpad = mlp_kpad(l), off = l == 4 ? 64 : 0;
         const __half* Hprev = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;
-        PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
         int rc = 0;
         if (l == 0 || l == 4) rc = launch_wgrad(DH, ench, 64, 64, 0, rows, part, kpad, 0, st);
         if (rc) return rc;
@@ -967,7 +1020,7 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
                                                           coef));
         if (l == 0) break;
         rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
-                            nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), st);
+                            nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), 1, st);
         if (rc) return rc;
         cur ^= 1;
     }
@@ -989,8 +1042,9 @@ extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A
     PCN_CHECK_ARG(out2 == nullptr, "tc_rowgemm: out2 is reserved and must be NULL (activations are stored once, fp16)");
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
+    PCN_CUDA(cudaMemsetAsync(work, 0, 4, st));
     return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __half*)E, rows, out, nullptr, stats,
-                          stats + 256, work, st);
+                          stats + 256, work, mode, st);
 }
 
 extern "C" int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows,

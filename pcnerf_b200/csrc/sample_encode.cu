@@ -10,47 +10,147 @@
 
 #define SE_MAX_SMEM (200 * 1024)
 
+__host__ __device__ __forceinline__ int al4(int v) { return (v + 3) & ~3; }
+// floats of per-warp row staging: 32 rows x 64 columns, fp32 (256 B rows) if fp32 rows are written, else fp16
+static inline int stage_floats(const void* out_enc, const void* out_f16) { return out_enc ? 2048 : (out_f16 ? 1024 : 0); }
+
 __device__ __forceinline__ float lerp_rn(float a, float b, float s) {
     // near * (1 - s) + far * s, nof/render.py:432
     return __fadd_rn(__fmul_rn(a, __fsub_rn(1.f, s)), __fmul_rn(b, s));
 }
 
-// Encode P samples of one ray (depths in shared `zs`) into rows [row0, row0+P).
+// ---- positional encoding of one ray (models.py:27-41), 32 samples at a time, one sample per lane.
+//
+// The argument of every sin/cos is 2^k * x with x an fp32 value, so the range reduction can be done EXACTLY once per
+// coordinate: t = x / (2 pi) in double (relative error 2^-53), q = round(t * 2^41) as a 64-bit integer, and the
+// fractional part of 2^k * t is a bit field of q -- no per-frequency Cody-Waite reduction.  Two back ends:
+//   * fp32 rows (precision 0 / 2, the 1e-5 gates): the 32-bit fraction goes through sincospif (<= 2 ulp);
+//   * fp16 rows (precision 1): the top 23 fraction bits are spliced into a float and fed to MUFU.SIN / MUFU.COS
+//     (abs error ~5e-7 on a reduced argument, 1000 x below the fp16 rounding of the stored value).
+// Each lane builds its whole 64-column row in registers; rows are transposed through a swizzled shared-memory tile so
+// that the global stores are 512 contiguous bytes per instruction (the 32 rows of a round are contiguous in HBM).
+#define ENC_BIG 8.0e6f          // |x| beyond this (or NaN/Inf): plain sincosf, whose result is what torch computes
+
+__device__ __forceinline__ long long enc_phase(float x) {
+    return __double2ll_rn((double)x * (0.15915494309189535 * 2199023255552.0));        // x / (2 pi) * 2^41
+}
+
+template <bool FAST>
+__device__ __forceinline__ void enc_coord(float x, float* __restrict__ e, int c) {
+    // e: this lane's row; writes columns 3 + 6k + c (sin) and 6 + 6k + c (cos), k = 0..9
+    if (fabsf(x) < ENC_BIG) {
+        const long long q = enc_phase(x);
+        const uint32_t lo = (uint32_t)q, hi = (uint32_t)((unsigned long long)q >> 32);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float sn, cs;
+            if (FAST) {
+                // bits [40-k : 18-k] of q = top 23 bits of frac(2^k t); flipping the top one adds half a turn, so that
+                // f - 1.5 = frac - 1/2 (mod 1) - ... lands in [-0.5, 0.5) with sin/cos of the ORIGINAL angle
+                const uint32_t w = __funnelshift_r(lo, hi, 18 - k);
+                const float f = __uint_as_float((w & 0x7FFFFFu) ^ 0x3FC00000u);
+                const float ang = fmaf(f - 1.5f, 6.2831853071795865f, 3.7450703e-7f);   // + half an lsb (2^-24 turns)
+                sn = __sinf(ang);
+                cs = __cosf(ang);
+            } else {
+                const int fr = (int)__funnelshift_r(lo, hi, 9 - k);                       // frac(2^k t) in 2^-32 turns, signed
+                sincospif((float)fr * 4.656612873077393e-10f, &sn, &cs);                  // * 2^-31: [-1, 1) half-turns
+            }
+            e[3 + 6 * k + c] = sn;
+            e[6 + 6 * k + c] = cs;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float sn, cs;
+            sincosf((float)(1 << k) * x, &sn, &cs);
+            e[3 + 6 * k + c] = sn;
+            e[6 + 6 * k + c] = cs;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t enc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Encode P samples of one ray (depths in shared `zs`) into rows [row0, row0+P).  `stage`: 32 x (F32 ? 256 : 128) bytes.
+template <bool F32, bool F16>
+__device__ __forceinline__ void encode_ray_t(const float o0, const float o1, const float o2, const float d0,
+                                             const float d1, const float d2, const float* zs, int P, int64_t row0,
+                                             float* __restrict__ out_enc, __half* __restrict__ out_bf,
+                                             float* stage, int lane) {
+    const uint32_t sbase = enc_smem_u32(stage);
+    for (int j0 = 0; j0 < P; j0 += 32) {
+        const int j = j0 + lane;
+        const float z = zs[j < P ? j : P - 1];
+        float e[64];
+        // rays_o + rays_d * z, nof/render.py:458 (mul then add, no FMA)
+        e[0] = __fadd_rn(o0, __fmul_rn(d0, z));
+        e[1] = __fadd_rn(o1, __fmul_rn(d1, z));
+        e[2] = __fadd_rn(o2, __fmul_rn(d2, z));
+        e[63] = 0.f;
+        enc_coord<!F32>(e[0], e, 0);
+        enc_coord<!F32>(e[1], e, 1);
+        enc_coord<!F32>(e[2], e, 2);
+        const int nrows = min(32, P - j0);
+        if (F32) {
+            // chunk c (16 B) of lane's 256-byte row at lane*256 + ((c & 8) | ((c ^ lane) & 7)) * 16: conflict-free both ways
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const uint32_t a = sbase + (uint32_t)(lane * 256 + (((c & 8) | ((c ^ lane) & 7)) << 4));
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(e[4 * c]), "f"(e[4 * c + 1]),
+                             "f"(e[4 * c + 2]), "f"(e[4 * c + 3]) : "memory");
+            }
+            __syncwarp();
+            float4* dst = reinterpret_cast<float4*>(out_enc + (row0 + j0) * 64);
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int idx = it * 32 + lane, row = idx >> 4, c = idx & 15;
+                if (row < nrows) {
+                    float4 v;
+                    const uint32_t a = sbase + (uint32_t)(row * 256 + (((c & 8) | ((c ^ row) & 7)) << 4));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+                    __stcs(dst + idx, v);
+                }
+            }
+            __syncwarp();
+        }
+        if (F16) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const __half2 h = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
+                pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t a = sbase + (uint32_t)(lane * 128 + (((c ^ lane) & 7) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                             "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+            }
+            __syncwarp();
+            uint4* dst = reinterpret_cast<uint4*>(out_bf + (row0 + j0) * 64);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int idx = it * 32 + lane, row = idx >> 3, c = idx & 7;
+                if (row < nrows) {
+                    uint4 v;
+                    const uint32_t a = sbase + (uint32_t)(row * 128 + (((c ^ row) & 7) << 4));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+                    dst[idx] = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __device__ __forceinline__ void encode_ray(const float o0, const float o1, const float o2, const float d0,
                                            const float d1, const float d2, const float* zs, int P, int64_t row0,
                                            float* __restrict__ out_enc, __half* __restrict__ out_bf,
                                            float* stage, int lane) {
-    const int k = lane / 3, c = lane - 3 * k;
-    const float freq = (float)(1 << (k < 10 ? k : 0));
-    for (int j = 0; j < P; ++j) {
-        float* st = stage + (j & 1) * 64;
-        const float z = zs[j];
-        // rays_o + rays_d * z, nof/render.py:458 (mul then add, no FMA)
-        const float x0 = __fadd_rn(o0, __fmul_rn(d0, z));
-        const float x1 = __fadd_rn(o1, __fmul_rn(d1, z));
-        const float x2 = __fadd_rn(o2, __fmul_rn(d2, z));
-        if (lane < 30) {
-            const float x = c == 0 ? x0 : (c == 1 ? x1 : x2);
-            float s, cs;
-            sincosf(freq * x, &s, &cs);      // freq is a power of two: freq*x is exact (models.py:23,38)
-            st[3 + 6 * k + c] = s;
-            st[6 + 6 * k + c] = cs;
-        } else if (lane == 30) {
-            st[0] = x0; st[1] = x1; st[2] = x2; st[63] = 0.f;
-        }
-        __syncwarp();
-        const int64_t row = row0 + j;
-        if (out_enc) {
-            out_enc[row * 64 + lane] = st[lane];
-            out_enc[row * 64 + 32 + lane] = st[32 + lane];
-        }
-        if (out_bf) {
-            const __half2 v = __floats2half2_rn(st[2 * lane], st[2 * lane + 1]);
-            reinterpret_cast<__half2*>(out_bf + row * 64)[lane] = v;
-        }
-        // the other half of `stage` is used by the next iteration; one __syncwarp per sample is enough
-    }
-    __syncwarp();
+    if (out_enc && out_bf) encode_ray_t<true, true>(o0, o1, o2, d0, d1, d2, zs, P, row0, out_enc, out_bf, stage, lane);
+    else if (out_enc) encode_ray_t<true, false>(o0, o1, o2, d0, d1, d2, zs, P, row0, out_enc, out_bf, stage, lane);
+    else encode_ray_t<false, true>(o0, o1, o2, d0, d1, d2, zs, P, row0, out_enc, out_bf, stage, lane);
 }
 
 // stable merge of two ascending lists a (na) and b (nb) into out (na+nb); ties: a first (torch.sort of cat([a,b]))
@@ -143,17 +243,17 @@ __global__ void k_sample_pdf(const float* __restrict__ bins_g, const float* __re
     }
 }
 
-__global__ void k_sample_encode_coarse(const float* __restrict__ rays, int ld, int64_t n, int near_col, int far_col,
+__global__ void __launch_bounds__(256, 2) k_sample_encode_coarse(const float* __restrict__ rays, int ld, int64_t n, int near_col, int far_col,
                                        int cnear_col, int cfar_col, const float* __restrict__ steps_a, int n_a,
                                        const float* __restrict__ steps_b, int n_b, int use_disp, float perturb,
                                        const float* __restrict__ U, float* __restrict__ out_z,
-                                       float* __restrict__ out_enc, __half* __restrict__ out_bf) {
-    extern __shared__ float smf[];
+                                       float* __restrict__ out_enc, __half* __restrict__ out_bf, int stage_f) {
+    extern __shared__ __align__(16) float smf[];
     const int S = n_a + n_b;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    float* za = smf + (size_t)wib * (2 * S + 128);
+    float* za = smf + (size_t)wib * (al4(2 * S) + stage_f);
     float* tmp = za + S;
-    float* stage = tmp + S;
+    float* stage = za + al4(2 * S);
     for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
         const float* ray = rays + r * ld;
         const float near = ray[near_col], far = ray[far_col];
@@ -200,20 +300,20 @@ __global__ void k_sample_encode_coarse(const float* __restrict__ rays, int ld, i
     }
 }
 
-__global__ void k_sample_encode_fine(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ z,
+__global__ void __launch_bounds__(256, 2) k_sample_encode_fine(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ z,
                                      const float* __restrict__ w, int S, const float* __restrict__ u, int u_ld, int Ni,
                                      int NiPad, float* __restrict__ out_z, float* __restrict__ out_enc,
-                                     __half* __restrict__ out_bf) {
-    extern __shared__ float smf[];
+                                     __half* __restrict__ out_bf, int stage_f) {
+    extern __shared__ __align__(16) float smf[];
     const int F = S + Ni;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)S + 2 * (S - 1) + NiPad + F + 128;
-    float* zc = smf + wib * per_warp;
+    const size_t arrays = al4(S + 2 * (S - 1) + NiPad + F);
+    float* zc = smf + wib * (arrays + stage_f);
     float* bins = zc + S;
     float* cdf = bins + (S - 1);
     float* zs = cdf + (S - 1);
     float* zo = zs + NiPad;
-    float* stage = zo + F;
+    float* stage = zc + arrays;
     const int nb = S - 1;                      // len(bins) == len(cdf)
     for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
         for (int i = lane; i < S; i += 32) zc[i] = z[r * S + i];
@@ -284,7 +384,8 @@ extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n,
                   "sample_encode_coarse: column index out of range");
     if (n == 0) return 0;
     const int S = n_a + n_b;
-    const size_t per_warp = (size_t)(2 * S + 128) * sizeof(float);
+    const int stage_f = stage_floats(out_enc, out_enc_f16);
+    const size_t per_warp = (size_t)(al4(2 * S) + stage_f) * sizeof(float);
     int wpb;
     int rc = pick_warps(per_warp, "sample_encode_coarse", &wpb);
     if (rc) return rc;
@@ -298,7 +399,7 @@ extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n,
                 (double)n * (60.0 + S * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_f16 ? 128.0 : 0.0))));
     k_sample_encode_coarse<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
         rays, ld, n, near_col, far_col, cnear_col, cfar_col, steps_a, n_a, steps_b, n_b, use_disp, perturb, U, out_z,
-        out_enc, (__half*)out_enc_f16);
+        out_enc, (__half*)out_enc_f16, stage_f);
     PCN_LAUNCH_CHECK();
     return 0;
 }
@@ -310,7 +411,8 @@ extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, c
     PCN_CHECK_ARG(u && (u_ld == 0 || u_ld == Ni), "sample_encode_fine: u must be (Ni) with u_ld 0 or (n,Ni) with u_ld Ni");
     if (n == 0) return 0;
     const int NiPad = next_pow2(Ni);
-    const size_t per_warp = ((size_t)S + 2 * (S - 1) + NiPad + (S + Ni) + 128) * sizeof(float);
+    const int stage_f = stage_floats(out_enc, out_enc_f16);
+    const size_t per_warp = ((size_t)al4(S + 2 * (S - 1) + NiPad + (S + Ni)) + stage_f) * sizeof(float);
     int wpb;
     int rc = pick_warps(per_warp, "sample_encode_fine", &wpb);
     if (rc) return rc;
@@ -323,7 +425,7 @@ extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, c
     PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
                 (double)n * (60.0 + 8.0 * S + (S + Ni) * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_f16 ? 128.0 : 0.0))));
     k_sample_encode_fine<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
-        rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__half*)out_enc_f16);
+        rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__half*)out_enc_f16, stage_f);
     PCN_LAUNCH_CHECK();
     return 0;
 }

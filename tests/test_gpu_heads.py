@@ -186,3 +186,36 @@ def test_child_nerf_divide_variant_vs_oracle():
     (1e6 * flg + 1e5 * dlg + dg.sum()).sum().backward()
     gr = p_ref.grad.numpy()
     np.testing.assert_allclose(net.p.grad.cpu().numpy(), gr, rtol=5e-4, atol=2e-6 * np.abs(gr).max())
+
+
+@pytest.mark.parametrize("S,n", [(64, 257), (37, 64), (5, 3), (192, 33)])
+def test_fused_sample_encode_rows_vs_oracle(S, n):
+    """K2's encoding rows (one lane per sample, exact integer range reduction) against Embedding (models.py:27-41) of
+    o + d*z: fp32 rows within 4e-7 absolute (sincospif on the reduced argument), fp16 rows within one fp16 rounding of the
+    exact value (MUFU.SIN/COS on the reduced argument: 1e-6 absolute before the rounding), pad column zero.  Sample counts
+    that are not multiples of 32 exercise the partial last round of the row transpose."""
+    from pcnerf_b200 import ops
+    gen = torch.Generator().manual_seed(S * 1000 + n)
+    rays = torch.zeros(n, 15)
+    rays[:, 0:3] = (torch.rand(n, 3, generator=gen) - 0.5) * 40.0
+    d = torch.randn(n, 3, generator=gen)
+    rays[:, 3:6] = d / d.norm(dim=1, keepdim=True)
+    rays[:, 6] = torch.rand(n, generator=gen) * 2.0
+    rays[:, 7] = rays[:, 6] + 1.0 + torch.rand(n, generator=gen) * 40.0
+    z, enc = ops.sample_encode_coarse(rays.to(dev()), S, 0, 6, 7, 10, 11, False, 0.0, None, want_enc=True)
+    z16, enc16 = ops.sample_encode_coarse(rays.to(dev()), S, 0, 6, 7, 10, 11, False, 0.0, None, want_enc=True, f16=True)
+    assert torch.equal(z, z16)
+    zc = z.cpu()
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * zc[:, :, None]).reshape(-1, 3)
+    ref = orc.embedding(pts).numpy()
+    got = enc.cpu().numpy()
+    assert got.shape == (n * S, 64)
+    assert np.array_equal(got[:, :3], ref[:, :3]) and not got[:, 63].any()
+    np.testing.assert_allclose(got[:, :63], ref, rtol=0, atol=4e-7)
+    got16 = enc16.float().cpu().numpy()
+    assert not got16[:, 63].any()
+    ref16 = torch.from_numpy(ref).half().float().numpy()
+    # |fp16(v + e) - fp16(v)| <= one fp16 ulp of v when |e| = 1e-6 pushes v across a rounding boundary
+    ulp = np.maximum(np.abs(ref), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(np.abs(got16[:, :63] - ref16) <= ulp + 1.5e-6)
+    assert np.mean(got16[:, 3:63] != ref16[:, 3:]) < 0.05          # and such flips are rare (near-zero values)
