@@ -419,10 +419,8 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 for (int i = 0; i < 4; ++i) {
                     const int row = (lane >> 2) + 8 * i;
                     e[c][i] = make_uint4(0, 0, 0, 0);
-                    if (row < left_) {
-                        const uint4* src = reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + colb + c * 32 + (lane & 3) * 8);
-                        e[c][i] = g.hint ? __ldcs(src) : *src;      // last use of H_{l-1} in this pass
-                    }
+                    if (row < left_)
+                        e[c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + colb + c * 32 + (lane & 3) * 8);
                 }
         };
         if (EPI == TC_DGRAD && tp.count > 0) load_e(tp.first);
@@ -715,7 +713,7 @@ __global__ void k_tc_prep_fwd(const float* __restrict__ Wp0, __half* __restrict_
 //
 // Per layer, after the weight-gradient GEMM: dW_l / db_l from the raw product (x a_{l-1}, + db (x) s_{l-1}) AND the BN(l-1)
 // backward coefficients (see above) in one pass over `part`.  One block per padded input column, one thread per output row.
-__global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, float* __restrict__ part, const double* __restrict__ colsum,
+__global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __restrict__ part, const double* __restrict__ colsum,
                                                          const float* __restrict__ prev_stats, const float* __restrict__ Wp,
                                                          int64_t rows, float* __restrict__ dW, float* __restrict__ db,
                                                          float* __restrict__ dgamma_prev, float* __restrict__ dbeta_prev,
@@ -731,7 +729,6 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, float* __restric
         else { real = c - 1; hid = c - 64; }
     }
     const float v = part[(size_t)o * kpad + c];
-    part[(size_t)o * kpad + c] = 0.f;                    // the next layer's split-K accumulation starts from zero
     const double cs = colsum[o];
     const float dbias = (float)cs;
     if (live) dW[o * kin + real] += is_hidden ? v * prev_stats[512 + hid] + dbias * prev_stats[768 + hid] : v;
@@ -977,8 +974,6 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     const __half* ench = (const __half*)enc;
     PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * L.n_dstat, st));
     PCN_CUDA(cudaMemsetAsync(L.rgwork(scratch), 0, 4, st));
-    // the split-K accumulator of the weight-gradient GEMM: cleared once, then every k_tc_wgrad_finish zeroes what it read
-    PCN_CUDA(cudaMemsetAsync(L.partial(scratch), 0, (size_t)256 * 320 * sizeof(float), st));
     if (!P->prepared) {
         tc_prep_weights(P, L, scratch, st);
         PrepTArgs pa;
@@ -1008,6 +1003,8 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
         const __nv_bfloat16* DH = Gb[cur];
         const int kpad = mlp_kpad(l), off = l == 4 ? 64 : 0;
         const __half* Hprev = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;
+        // (a scattered in-kernel clear by k_tc_wgrad_finish was measured 3 ms/step slower than this memset node)
+        PCN_CUDA(cudaMemsetAsync(part, 0, (size_t)256 * kpad * sizeof(float), st));
         int rc = 0;
         if (l == 0 || l == 4) rc = launch_wgrad(DH, ench, 64, 64, 0, rows, part, kpad, 0, st);
         if (rc) return rc;
