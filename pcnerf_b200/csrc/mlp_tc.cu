@@ -191,6 +191,7 @@ struct RowGemmArgs {
     int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores
     int sched;                  // row-tile order of a CTA pair: 0 interleaved (pair, pair + npairs, ...), 1 contiguous slab
                                 // walked upwards, 2 contiguous slab walked downwards (see tile_plan)
+    int nostat;                 // 1: eval-mode BN (running statistics): the epilogue skips the column sums
     int hint;                   // 1: the A tiles are not read again soon -> L2 evict_first, so that the freshly WRITTEN
                                 // output matrix is what stays in the 126 MB L2 for the next kernel
 };
@@ -505,7 +506,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 tma_store_2d_nocommit(&tmO, bufs[1], colb + 32, row0);
                 tma_store_commit();
             }
-            if (!(g.debug & 1)) {
+            if (!(g.debug & 1) && !g.nostat) {
                 if (EPI == TC_FWD) {
                     stage_col_sums<true, true>(bufs[0], lane, acc0, acc1);
                     stage_col_sums<true, true>(bufs[1], lane, acc0 + 2, acc1 + 2);
@@ -829,7 +830,7 @@ int sm_count() {
 #define TC_ROWGEMM_WORK_BYTES (256 + 160 * 2 * 128 * 8)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
                    const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
-                   double* stat1, void* work, int dir, cudaStream_t st) {
+                   double* stat1, void* work, int dir, cudaStream_t st, int nostat = 0) {
     PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && (k0 + k1) <= 320, "tc rowgemm: K must be 64..320 in 64s");
     CUtensorMap mA0, mA1, mB;
     int rc = make_map(&mA0, A0, rows, k0, lda0, 128);
@@ -860,6 +861,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         g.sched = m == 0 ? 0 : (dir ? 2 : 1);
         g.hint = m == 2 ? 1 : 0;
     }
+    g.nostat = nostat;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -937,6 +939,9 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     }
     // H_l is stored once, fp16 (10-bit mantissa for the 1e-3 gate): it is the next layer's operand and what the backward
     // pass re-reads (the weight-gradient kernel converts its tiles to bf16 in shared memory)
+    // Eval mode (running statistics): every fold is a function of the parameters alone, so the folded fp16 weights of all
+    // layers are derived once per pass (first chunk) and the row GEMMs neither wait for nor compute batch statistics.
+    const int ns = P->training ? 0 : 1;
     for (int l = 0; l < 8; ++l) {
         __half* Hout = (__half*)L.Hraw(sv, l);
         const __half* Hin = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;
@@ -944,11 +949,12 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
         double* s0 = L.dstat(scratch, l);
         const float* bias = l == 0 ? P->b[0] : L.bf(scratch, l);
         int rc;
-        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st);
-        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st);
-        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st);
+        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), 64, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns);
+        else if (l == 4) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, 4), 320, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns);
+        else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), 256, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns);
         if (rc) return rc;
         const bool last = l == 7;
+        if (!P->training && P->prepared) continue;       // folded copies of the first chunk are still in `scratch`
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
                       l, P->training, rows, s0, s0 + 256, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],

@@ -169,7 +169,7 @@ __device__ __forceinline__ void rank_merge(const float* a, int na, const float* 
     }
 }
 
-__device__ __forceinline__ void bitonic_sort(float* s, int npad, int lane) {
+__device__ __forceinline__ void bitonic_sort_smem(float* s, int npad, int lane) {
     for (int k = 2; k <= npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = lane; i < npad; i += 32) {
@@ -182,6 +182,55 @@ __device__ __forceinline__ void bitonic_sort(float* s, int npad, int lane) {
             }
             __syncwarp();
         }
+    }
+}
+
+// The same network with the EPL = npad/32 elements [lane*EPL, lane*EPL + EPL) of every lane in registers: compare-exchanges
+// at distance j < EPL stay inside the lane, the others are one shfl_xor per element (Ni = 128 / 256 -> 4 / 8 registers).
+template <int EPL>
+__device__ __forceinline__ void bitonic_sort_regs(float* s, int lane) {
+    float v[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] = s[lane * EPL + i];
+#pragma unroll
+    for (int k = 2; k <= EPL * 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= EPL) {
+                const int lj = j / EPL;
+                const bool up = ((lane * EPL) & k) == 0, lower = (lane & lj) == 0;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    const float o = __shfl_xor_sync(FULL_MASK, v[i], lj);
+                    v[i] = (lower == up) ? fminf(v[i], o) : fmaxf(v[i], o);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) {
+                    if ((i & j) == 0) {
+                        const bool up = (((lane * EPL) + i) & k) == 0;
+                        const float a = v[i], b = v[i | j];
+                        const float lo = fminf(a, b), hi = fmaxf(a, b);
+                        v[i] = up ? lo : hi;
+                        v[i | j] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) s[lane * EPL + i] = v[i];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void bitonic_sort(float* s, int npad, int lane) {
+    switch (npad) {
+        case 32: bitonic_sort_regs<1>(s, lane); break;
+        case 64: bitonic_sort_regs<2>(s, lane); break;
+        case 128: bitonic_sort_regs<4>(s, lane); break;
+        case 256: bitonic_sort_regs<8>(s, lane); break;
+        case 512: bitonic_sort_regs<16>(s, lane); break;
+        default: bitonic_sort_smem(s, npad, lane);
     }
 }
 

@@ -269,6 +269,7 @@ def embed(x, out_ld=63):
 # ------------------------------------------------------------------------------------------------------- K3 MLP
 
 _SCRATCH = {}
+EVAL_CHUNK_FLOOR = 1 << 20        # rows per launch of the eval-mode tensor-core MLP (tests lower it to cover chunking)
 
 
 def _scratch(rows, precision, device):
@@ -311,6 +312,10 @@ class MLPFunction(torch.autograd.Function):
         P = _mlp_params(params, buffers, training, precision)
         out = torch.empty(rows, dtype=torch.float32, device=dev)
         need_grad = training and any(ctx.needs_input_grad[5:])
+        if not training and precision == 1:
+            # eval-mode BN is row-wise (running statistics): `chunk` (an OOM guard in the reference, nof/render.py:21-24)
+            # does not change any value, and the row GEMMs run closer to their steady-state rate on >= 1 M-row launches
+            chunk = max(int(chunk), EVAL_CHUNK_FLOOR)
         saved = []
         scratch = _scratch(min(chunk, rows), precision, dev)
         shared = None

@@ -135,3 +135,34 @@ def test_train_coarse_pass_tc_gate_1e3(name):
         np.testing.assert_allclose(float(res["child_free_loss"]), g["out_child_free_loss"], rtol=1e-3)
         np.testing.assert_allclose(float(res["child_depth_loss"]), g["out_child_depth_loss"], rtol=1e-3)
     np.testing.assert_allclose(res["depth_fine"].detach().cpu().numpy(), g["out_depth_fine"], rtol=5e-3, atol=1e-6)
+
+
+def test_mlp_eval_tc_chunking_is_invisible():
+    """Eval-mode BN uses running statistics, so `chunk` must not change a single bit: the tensor-core path derives the
+    folded weights once per pass (first chunk), later chunks reuse them and no chunk computes batch statistics.  Checked
+    with non-trivial running statistics (one training pass first) against the fp32 oracle at the 1e-3 gate."""
+    from pcnerf_b200 import ops
+    rows = 3000
+    enc = _enc(rows, 7)
+    mc, _, _ = make_nets(42, 43, True, "tc")
+    encd = torch.nn.functional.pad(enc, (0, 1)).to(dev())
+    mc.forward_encoded(encd, 1024)                       # train-mode pass: running statistics move away from (0, 1)
+    mc.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in mc.state_dict().items()}
+    p_ref = orc.nof_forward(sd, enc, False).reshape(-1)
+    floor = ops.EVAL_CHUNK_FLOOR
+    try:
+        ops.EVAL_CHUNK_FLOOR = 0
+        with torch.no_grad():
+            p_chunks = mc.forward_encoded(encd, 1024).cpu()          # 3 chunks: 1024, 1024, 952 rows
+            p_odd = mc.forward_encoded(encd, 777).cpu()
+        ops.EVAL_CHUNK_FLOOR = floor
+        with torch.no_grad():
+            p_one = mc.forward_encoded(encd, 1024).cpu()             # one launch
+    finally:
+        ops.EVAL_CHUNK_FLOOR = floor
+    assert torch.equal(p_chunks, p_one) and torch.equal(p_odd, p_one)
+    err = (p_one - p_ref).abs() / p_ref
+    assert float(err.max()) < 6e-3 and float(err.mean()) < 1e-3, (float(err.max()), float(err.mean()))
+    for k in ("layer1.1.running_mean", "layer2.7.running_var"):    # eval mode leaves the running statistics alone
+        assert torch.equal(mc.state_dict()[k].cpu(), sd[k])
