@@ -167,7 +167,8 @@ size_t pcnerf_mlp_saved_bytes(int64_t rows, int precision);
 size_t pcnerf_mlp_scratch_bytes(int64_t rows, int precision);
 
 /* One BN batch (= one `chunk` of nof/render.py:47-49).  enc (rows,64) f32 (precision 0) or fp16 (precision 1).
- * out_p (rows) = sigmoid(logit).  `saved` receives the pre-BN activations and the batch statistics. */
+ * out_p (rows) = sigmoid(logit).  `saved` receives the pre-BN activations and the batch statistics; it is not touched
+ * (and may be NULL) for precision 1 with training == 0 while pcnerf_tc_get_fused_eval() is 1. */
 int pcnerf_mlp_forward(const pcnerf_mlp_params* h_params, const void* enc, int64_t rows, float* out_p,
                        void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
 
@@ -209,6 +210,12 @@ int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A1, int k1, 
 int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_bf16, int64_t rows, float* out, int ldo,
                     int col_off, void* stream);
 int pcnerf_tc_last_fault(void);
+
+/* Eval-mode (running-statistics) forward of the precision-1 MLP: 1 (default) = all nine layers in one persistent kernel with
+ * the activations resident in shared memory / TMEM (k_tc_fused_eval, replaces the per-chunk loop of nof/render.py:21-24 for
+ * model.eval()); 0 = the layered row GEMMs (one kernel per Linear, activations through HBM).  Process-wide switch. */
+void pcnerf_tc_set_fused_eval(int on);
+int pcnerf_tc_get_fused_eval(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K4  compositing + losses (nof/render.py:51-61, :75-161, :13-36, :166-226; train_kitti.py:145-146).

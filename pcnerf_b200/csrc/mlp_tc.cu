@@ -700,6 +700,214 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Eval-mode forward, all eight Linear(+folded BN) layers and the output layer in ONE persistent kernel.
+//
+// With running statistics every fold is known before the first GEMM, so nothing chunk-wide separates the layers: a CTA
+// keeps the activations of its row tiles in shared memory from the encoding to the occupancy -- no H_l ever reaches HBM
+// (the layered kernels move 1 KB per sample per layer).  Per CTA: two 128-row tiles X, Y in flight ("ping-pong"): while
+// the eight epilogue warps turn the TMEM accumulator of (layer l, X) into the fp16 A operand of layer l+1 (written
+// straight into the SWIZZLE_128B K-major layout a TMA load would have produced), the tensor core runs (layer l, Y).
+//   shared memory: enc[2] 2 x 16 KB | act[2] 2 x 64 KB | weight ring 4 x 16 KB (128 weight rows x 64 k, streamed from
+//   the L2-resident folded fp16 weights, ~1 MB per tile pair) = 224 KB;  TMEM: 2 x (128 lanes x 256 fp32 columns).
+//   warp 0: TMA producer (encoding tiles, weight ring);  warp 1: tcgen05.mma issuer;  warps 2..9: epilogue.
+// ---------------------------------------------------------------------------------------------------------------
+#define FZ_STAGES 4
+#define FZ_BLK (128 * 128)       // 16 KB: 128 rows x 64 fp16 (one k-block of A, or one weight stage)
+
+struct FusedMaps { CUtensorMap w[8]; };
+struct FusedArgs {
+    int rows;
+    const float* bias[8];       // fp32 [256]: b_0, then the folded biases b_l + W_l s_{l-1}
+    const float* wout;          // folded output layer: w[256] | b
+    float* out_p;               // [rows] sigmoid(logit)
+};
+
+__device__ __forceinline__ int fz_kblocks(int l) { return l == 0 ? 1 : (l == 4 ? 5 : 4); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_fused_eval(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ FusedMaps wm, const FusedArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 + 2 + 2 * FZ_STAGES + 2 + 2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float part[2][128];                        // [tile slot][row]: partial logit of column half 1
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sEnc = smem;                                  // [2] x 16 KB
+    uint8_t* sAct = sEnc + 2 * FZ_BLK;                     // [2] x 64 KB (4 k-blocks)
+    uint8_t* sW = sAct + 2 * 4 * FZ_BLK;                   // FZ_STAGES x 16 KB
+    const uint32_t bar_encf = smem_u32(bars), bar_ence = smem_u32(bars + 2), bar_wf = smem_u32(bars + 4);
+    const uint32_t bar_we = smem_u32(bars + 4 + FZ_STAGES), bar_accf = smem_u32(bars + 4 + 2 * FZ_STAGES);
+    const uint32_t bar_epi = smem_u32(bars + 6 + 2 * FZ_STAGES);
+
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 2; ++j) {
+            mbar_init(bar_encf + 8 * j, 1);
+            mbar_init(bar_ence + 8 * j, 1);
+            mbar_init(bar_accf + 8 * j, 1);
+            mbar_init(bar_epi + 8 * j, 8);
+        }
+        for (int s = 0; s < FZ_STAGES; ++s) { mbar_init(bar_wf + 8 * s, 1); mbar_init(bar_we + 8 * s, 1); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmE);
+        for (int l = 0; l < 8; ++l) tma_prefetch_desc(&wm.w[l]);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int ntiles = (g.rows + 127) >> 7, npairs = (ntiles + 1) >> 1;
+
+    if (warp == 0) {
+        // ===== producer
+        if (lane == 0) {
+            auto issue_enc = [&](int it, int pair) {
+                for (int j = 0; j < 2; ++j) {
+                    mbar_wait(bar_ence + 8 * j, (uint32_t)((it & 1) ^ 1), 21);
+                    mbar_expect_tx(bar_encf + 8 * j, FZ_BLK);
+                    tma_load_2d(smem_u32(sEnc + j * FZ_BLK), &tmE, bar_encf + 8 * j, 0, (2 * pair + j) * 128);
+                }
+            };
+            int s = 0, it = 0;
+            uint32_t ph = 0;
+            if ((int)blockIdx.x < npairs) issue_enc(0, blockIdx.x);
+            for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
+                for (int l = 0; l < 8; ++l) {
+                    const int KB = fz_kblocks(l);
+                    for (int j = 0; j < 2; ++j)
+                        for (int kb = 0; kb < KB; ++kb)
+                            for (int h = 0; h < 2; ++h) {
+                                mbar_wait(bar_we + 8 * s, ph ^ 1, 22);
+                                mbar_expect_tx(bar_wf + 8 * s, FZ_BLK);
+                                tma_load_2d(smem_u32(sW + s * FZ_BLK), &wm.w[l], bar_wf + 8 * s, kb * 64, h * 128);
+                                if (++s == FZ_STAGES) { s = 0; ph ^= 1; }
+                            }
+                    // the encoding tiles were last read by layer 4: fetch the next pair's while layers 6, 7 run
+                    if (l == 5 && pair + (int)gridDim.x < npairs) issue_enc(it + 1, pair + gridDim.x);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        constexpr uint32_t idesc = make_idesc(0, 0, 0, 0, 128, 128);
+        int s = 0, it = 0;
+        uint32_t ph = 0, ed[2] = {0, 0};
+        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
+            for (int l = 0; l < 8; ++l) {
+                const int KB = fz_kblocks(l);
+                for (int j = 0; j < 2; ++j) {
+                    if (l == 0) mbar_wait(bar_encf + 8 * j, (uint32_t)(it & 1), 23);
+                    // accumulator j drained and (l > 0) the fp16 activations of layer l-1 written by the epilogue
+                    mbar_wait_spin(bar_epi + 8 * j, ed[j] ^ 1, 24);
+                    ed[j] ^= 1;
+                    tc_fence_after();
+                    const uint32_t enc_a = smem_u32(sEnc + j * FZ_BLK), act_a = smem_u32(sAct + j * 4 * FZ_BLK);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint32_t a0 = l == 0 ? enc_a : (l == 4 ? (kb == 0 ? enc_a : act_a + (kb - 1) * FZ_BLK) : act_a + kb * FZ_BLK);
+                        for (int h = 0; h < 2; ++h) {
+                            mbar_wait_spin(bar_wf + 8 * s, ph, 25);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint32_t b0 = smem_u32(sW + s * FZ_BLK);
+                                const uint32_t d = tmem_base + (uint32_t)(j * 256 + h * 128);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16(d, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                             (uint32_t)((kb | k) != 0));
+                                umma_commit(bar_we + 8 * s);
+                            }
+                            __syncwarp();
+                            if (++s == FZ_STAGES) { s = 0; ph ^= 1; }
+                        }
+                    }
+                    if (lane == 0) {
+                        umma_commit(bar_accf + 8 * j);
+                        if (l == 4) umma_commit(bar_ence + 8 * j);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warp -> TMEM lane quadrant q (rows q*32 + lane of the tile), column half (128 of the 256 features)
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        uint32_t af[2] = {0, 0};
+        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            for (int l = 0; l < 8; ++l) {
+                for (int j = 0; j < 2; ++j) {
+                    mbar_wait_spin(bar_accf + 8 * j, af[j], 26);
+                    af[j] ^= 1;
+                    tc_fence_after();
+                    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 256 + half * 128);
+                    const float* bias = g.bias[l] + half * 128;
+                    const uint32_t act_a = smem_u32(sAct + j * 4 * FZ_BLK);
+                    float dot = 0.f;
+#pragma unroll
+                    for (int cp = 0; cp < 2; ++cp) {
+                        uint32_t r[2][32];
+                        tmem_ld32_issue(tbase + cp * 64, r[0]);
+                        tmem_ld32_issue(tbase + cp * 64 + 32, r[1]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const int n0 = cp * 64 + c2 * 32;              // first of this thread's 32 columns within the half
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + j4);
+                                const __half2 h01 = __floats2half2_rn(__uint_as_float(r[c2][4 * j4 + 0]) + b4.x,
+                                                                      __uint_as_float(r[c2][4 * j4 + 1]) + b4.y);
+                                const __half2 h23 = __floats2half2_rn(__uint_as_float(r[c2][4 * j4 + 2]) + b4.z,
+                                                                      __uint_as_float(r[c2][4 * j4 + 3]) + b4.w);
+                                pk[2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
+                                pk[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                                if (l == 7) {
+                                    // the output layer sees the same fp16-rounded H_7 the layered path stores
+                                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wout + half * 128 + n0) + j4);
+                                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                                    dot = fmaf(f01.x, w4.x, dot);
+                                    dot = fmaf(f01.y, w4.y, dot);
+                                    dot = fmaf(f23.x, w4.z, dot);
+                                    dot = fmaf(f23.y, w4.w, dot);
+                                }
+                            }
+                            if (l < 7) {
+                                // columns half*128 + n0 .. +31 = k-block (half*2 + cp) of the next layer's A, 16-byte chunks
+                                // c2*4 .. c2*4+3 of this row, at their SWIZZLE_128B positions
+                                const uint32_t rb = act_a + (uint32_t)((half * 2 + cp) * FZ_BLK + row * 128);
+#pragma unroll
+                                for (int m = 0; m < 4; ++m)
+                                    sts128(rb + (uint32_t)((((c2 * 4 + m) ^ (row & 7))) << 4),
+                                           make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]));
+                            }
+                        }
+                    }
+                    if (l < 7) fence_proxy_async();               // the tensor core reads these stores through the async proxy
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_epi + 8 * j);
+                    if (l == 7) {
+                        if (half == 1) part[j][row] = dot;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (half == 0) {
+                            const int64_t grow = (int64_t)(2 * pair + j) * 128 + row;
+                            if (grow < g.rows) {
+                                const float t = dot + part[j][row] + __ldg(g.wout + 256);
+                                g.out_p[grow] = 1.f / (1.f + expf(-t));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 16-bit weight copies
 // ---------------------------------------------------------------------------------------------------------------
 // Wh0[256][64] = fp16(Wp0)
@@ -912,6 +1120,10 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
 
 }  // namespace
 
+static int g_fused_eval = 1;
+extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on ? 1 : 0; }
+extern "C" int pcnerf_tc_get_fused_eval(void) { return g_fused_eval; }
+
 // fp32 padded weight copies (same kernel as the fp32 path; defined in mlp_small.cuh)
 static void tc_prep_weights(const pcnerf_mlp_params* P, const MlpLayout& L, char* scratch, cudaStream_t st) {
     PrepArgs pa;
@@ -942,6 +1154,43 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     // Eval mode (running statistics): every fold is a function of the parameters alone, so the folded fp16 weights of all
     // layers are derived once per pass (first chunk) and the row GEMMs neither wait for nor compute batch statistics.
     const int ns = P->training ? 0 : 1;
+    if (!P->training && g_fused_eval) {
+        // ... and all nine layers run as ONE kernel with the activations resident in shared memory / TMEM (k_tc_fused_eval)
+        if (!P->prepared) {
+            for (int l = 0; l < 8; ++l) {
+                const bool last = l == 7;
+                PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
+                          k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
+                              l, 0, rows, nullptr, nullptr, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],
+                              P->num_batches_tracked[l], P->momentum, P->eps, L.coef(scratch) /* (mean, invstd, a, s): unused */,
+                              last ? P->W[8] : L.Wp(scratch, l + 1), last ? P->b[8] : P->b[l + 1],
+                              last ? L.wout_f(scratch) : L.Wf(scratch, l + 1),
+                              last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1), last ? nullptr : tc_Wh(L, scratch, l + 1)));
+            }
+        }
+        CUtensorMap mE;
+        FusedMaps wm;
+        int rc = make_map(&mE, ench, rows, 64, 64, 128);
+        if (rc) return rc;
+        for (int l = 0; l < 8; ++l) {
+            rc = make_map(&wm.w[l], tc_Wh(L, scratch, l), 256, mlp_kpad(l), mlp_kpad(l), 128);
+            if (rc) return rc;
+        }
+        FusedArgs fa;
+        fa.rows = (int)rows;
+        fa.bias[0] = P->b[0];
+        for (int l = 1; l < 8; ++l) fa.bias[l] = L.bf(scratch, l);
+        fa.wout = L.wout_f(scratch);
+        fa.out_p = out_p;
+        const size_t smem = 1024 + (size_t)(2 + 8 + FZ_STAGES) * FZ_BLK;
+        const int npairs = (int)pcn_cdiv(pcn_cdiv(rows, 128), 2);
+        const int grid = npairs < sm_count() ? npairs : sm_count();
+        PCN_CUDA(cudaFuncSetAttribute(k_tc_fused_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PcnScope ps(PCN_K_GEMM_FWD, st, (double)rows * 982528.0);
+        k_tc_fused_eval<<<grid, TC_THREADS, smem, st>>>(mE, wm, fa);
+        PCN_LAUNCH_CHECK();
+        return 0;
+    }
     for (int l = 0; l < 8; ++l) {
         __half* Hout = (__half*)L.Hraw(sv, l);
         const __half* Hin = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;

@@ -302,6 +302,13 @@ def _mlp_params(tensors, buffers, training, precision, momentum=0.1, eps=1e-5):
 GRAD_SIZES = [256 * 63, 256] + [256 * 256, 256] * 3 + [256 * 319, 256] + [256 * 256, 256] * 3 + [256, 1] + [256, 256] * 8
 
 
+def tc_fused_eval(on=None):
+    """Get / set the eval-mode engine of the precision-1 MLP: fused single kernel (default) or layered row GEMMs."""
+    if on is not None:
+        lib().pcnerf_tc_set_fused_eval(1 if on else 0)
+    return bool(lib().pcnerf_tc_get_fused_eval())
+
+
 class MLPFunction(torch.autograd.Function):
     """p = NOF(enc) evaluated chunk by chunk (one BN batch per chunk, nof/render.py:47-49)."""
 
@@ -320,9 +327,11 @@ class MLPFunction(torch.autograd.Function):
         scratch = _scratch(min(chunk, rows), precision, dev)
         shared = None
         esz = 2 if precision == 1 else 4
+        fused_eval = (not training) and precision == 1 and bool(lib().pcnerf_tc_get_fused_eval())
         for i in range(0, rows, chunk):
             r = min(chunk, rows - i)
-            nbytes = lib().pcnerf_mlp_saved_bytes(r, precision)
+            # (the fused eval kernel keeps every activation on chip: nothing is saved)
+            nbytes = 256 if fused_eval else lib().pcnerf_mlp_saved_bytes(r, precision)
             if need_grad:
                 sv = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 saved.append(sv)

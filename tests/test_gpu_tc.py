@@ -166,3 +166,34 @@ def test_mlp_eval_tc_chunking_is_invisible():
     assert float(err.max()) < 6e-3 and float(err.mean()) < 1e-3, (float(err.max()), float(err.mean()))
     for k in ("layer1.1.running_mean", "layer2.7.running_var"):    # eval mode leaves the running statistics alone
         assert torch.equal(mc.state_dict()[k].cpu(), sd[k])
+
+
+@pytest.mark.parametrize("rows", [127, 130, 3000, 100003])
+def test_mlp_eval_fused_matches_layered(rows):
+    """k_tc_fused_eval (all layers in one kernel, activations in shared memory / TMEM) against the layered eval path (same
+    fp16 operands, same folded weights: the hidden activations are bit-identical, only the 256-term output dot is summed in
+    a different order) and against the fp32 oracle at the tensor-core gate.  Row counts: a lone partial tile (the pair's
+    second tile is entirely out of bounds), a partial second tile, many pairs, and more pairs than CTAs (barrier phases
+    wrap, encoding prefetch of the next pair)."""
+    from pcnerf_b200 import ops
+    enc = _enc(rows, rows + 3)
+    mc, _, _ = make_nets(42, 43, True, "tc")
+    encd = torch.nn.functional.pad(enc, (0, 1)).to(dev())
+    mc.forward_encoded(encd[:4096], 4096)                # one train-mode pass: non-trivial running statistics
+    mc.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in mc.state_dict().items()}
+    try:
+        ops.tc_fused_eval(False)
+        with torch.no_grad():
+            p_lay = mc.forward_encoded(encd, 1 << 20).cpu()
+        ops.tc_fused_eval(True)
+        with torch.no_grad():
+            p_fus = mc.forward_encoded(encd, 1 << 20).cpu()
+    finally:
+        ops.tc_fused_eval(True)
+    assert ops.lib().pcnerf_tc_last_fault() == 0
+    np.testing.assert_allclose(p_fus.numpy(), p_lay.numpy(), rtol=2e-5, atol=1e-7)
+    n_ref = min(rows, 4096)
+    p_ref = orc.nof_forward(sd, enc[:n_ref], False).reshape(-1)
+    err = (p_fus[:n_ref] - p_ref).abs() / p_ref
+    assert float(err.max()) < 6e-3 and float(err.mean()) < 1e-3, (float(err.max()), float(err.mean()))
