@@ -211,9 +211,12 @@ int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_
                     int col_off, void* stream);
 int pcnerf_tc_last_fault(void);
 
-/* Eval-mode (running-statistics) forward of the precision-1 MLP: 1 (default) = all nine layers in one persistent kernel with
- * the activations resident in shared memory / TMEM (k_tc_fused_eval, replaces the per-chunk loop of nof/render.py:21-24 for
- * model.eval()); 0 = the layered row GEMMs (one kernel per Linear, activations through HBM).  Process-wide switch. */
+/* Eval-mode (running-statistics) forward of the precision-1 MLP (replaces the per-chunk loop of nof/render.py:21-24 for
+ * model.eval()).  Process-wide switch:
+ *   2 (default) = all nine layers in one persistent kernel, activations resident in shared memory / TMEM, CTA pairs
+ *       (clusters of two, tcgen05.mma.cta_group::2 with M = 256: each SM streams half of every weight block);
+ *   1 = the same kernel with one CTA per unit of work (cta_group::1);
+ *   0 = the layered row GEMMs (one kernel per Linear, activations through HBM). */
 void pcnerf_tc_set_fused_eval(int on);
 int pcnerf_tc_get_fused_eval(void);
 

@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #define TC_THREADS 320           // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: epilogue
 #define TC_A_BYTES (128 * 128)   // one A k-block: 128 rows x 64 x 2 B
@@ -707,204 +708,317 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 // (the layered kernels move 1 KB per sample per layer).  Per CTA: two 128-row tiles X, Y in flight ("ping-pong"): while
 // the eight epilogue warps turn the TMEM accumulator of (layer l, X) into the fp16 A operand of layer l+1 (written
 // straight into the SWIZZLE_128B K-major layout a TMA load would have produced), the tensor core runs (layer l, Y).
-//   shared memory: enc[2] 2 x 16 KB | act[2] 2 x 64 KB | weight ring 4 x 16 KB (128 weight rows x 64 k, streamed from
-//   the L2-resident folded fp16 weights, ~1 MB per tile pair) = 224 KB;  TMEM: 2 x (128 lanes x 256 fp32 columns).
-//   warp 0: TMA producer (encoding tiles, weight ring);  warp 1: tcgen05.mma issuer;  warps 2..9: epilogue.
+//   shared memory: act[2] 2 x 64 KB | operand ring 6 x 16 KB = 224 KB;  TMEM: 2 x (128 lanes x 256 fp32 columns).
+//   Everything that is not an activation streams through the ring in the order the MMA warp consumes it: 128 weight rows
+//   x 64 k per stage (from the L2-resident folded fp16 weights, ~1 MB per tile pair) and, ahead of layers 0 and 4, the
+//   tile's 128 x 64 encoding block (the A operand of layer 0 and of the skip columns of layer 4).  The ring is the
+//   kernel's limiter: a stage feeds 256 tensor-core cycles and comes back ~1 us after it is released, so the bytes in flight
+//   (not L2 bandwidth: ncu lts 21 %) set the pace -- hence every byte that is not act[] belongs to it.
+//   warp 0: TMA producer;  warp 1: tcgen05.mma issuer;  warps 2..9: epilogue.
 // ---------------------------------------------------------------------------------------------------------------
-#define FZ_STAGES 4
+// ---- CTA-pair (cta_group::2) forms: the pair's leader (cluster rank 0) issues one MMA for both SMs (M = 256: 128 rows
+// from each CTA's shared memory, B split -- each CTA holds half of the N weight rows), TMA loads of either CTA signal the
+// LEADER's mbarrier, commits are multicast to the same barrier offset in both CTAs.  Within a pair the shared::cluster
+// address of the peer's copy of a shared variable differs in bit 24 only (the even CTA has it clear).
+#define TC_PEER_MASK 0xFEFFFFFFu
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(0x1000000000000000ull) /* evict normal */
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrive on the barrier at this shared-memory offset in both CTAs of the pair once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// arrive (release at cluster scope) on the LEADER's copy of a barrier, from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int code) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
+            atomicExch(&g_tc_err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+#define FZ_STAGES 6
 #define FZ_BLK (128 * 128)       // 16 KB: 128 rows x 64 fp16 (one k-block of A, or one weight stage)
 
 struct FusedMaps { CUtensorMap w[8]; };
 struct FusedArgs {
     int rows;
-    const float* bias[8];       // fp32 [256]: b_0, then the folded biases b_l + W_l s_{l-1}
-    const float* wout;          // folded output layer: w[256] | b
     float* out_p;               // [rows] sigmoid(logit)
 };
+// fp32 epilogue constants of the model whose pass is running (uploaded stream-ordered before its first chunk):
+// bias[8][256] = b_0 and the folded biases b_l + W_l s_{l-1};  folded output layer w[256], b
+__constant__ float c_fz[8 * 256 + 256 + 4];
 
 __device__ __forceinline__ int fz_kblocks(int l) { return l == 0 ? 1 : (l == 4 ? 5 : 4); }
 
+// NCTA = 1: every CTA on its own (two 128-row tiles per unit of work, N = 128 MMAs, 2 ring stages per k-block).
+// NCTA = 2: clusters of two CTAs (four tiles per unit); one M = 256, N = 256 MMA covers a tile of each CTA and all 256
+//           features with each CTA streaming HALF of every weight k-block (1 ring stage per k-block): shared-memory
+//           operand traffic per SM and per MMA cycle halves (128 -> 64 B/clk), which is what bounds the single-CTA form.
+template <int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_fused_eval(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ FusedMaps wm, const FusedArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 + 2 + 2 * FZ_STAGES + 2 + 2];
+    __shared__ __align__(8) uint64_t bars[2 * FZ_STAGES + 2 + 2];
     __shared__ uint32_t tmem_slot;
     __shared__ float part[2][128];                        // [tile slot][row]: partial logit of column half 1
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sEnc = smem;                                  // [2] x 16 KB
-    uint8_t* sAct = sEnc + 2 * FZ_BLK;                     // [2] x 64 KB (4 k-blocks)
+    uint8_t* sAct = smem;                                  // [2] x 64 KB (4 k-blocks)
     uint8_t* sW = sAct + 2 * 4 * FZ_BLK;                   // FZ_STAGES x 16 KB
-    const uint32_t bar_encf = smem_u32(bars), bar_ence = smem_u32(bars + 2), bar_wf = smem_u32(bars + 4);
-    const uint32_t bar_we = smem_u32(bars + 4 + FZ_STAGES), bar_accf = smem_u32(bars + 4 + 2 * FZ_STAGES);
-    const uint32_t bar_epi = smem_u32(bars + 6 + 2 * FZ_STAGES);
+    const uint32_t bar_wf = smem_u32(bars), bar_we = smem_u32(bars + FZ_STAGES);
+    const uint32_t bar_accf = smem_u32(bars + 2 * FZ_STAGES), bar_epi = smem_u32(bars + 2 * FZ_STAGES + 2);
 
+    const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;          // 0 = the pair's leader
     if (threadIdx.x == 0) {
         for (int j = 0; j < 2; ++j) {
-            mbar_init(bar_encf + 8 * j, 1);
-            mbar_init(bar_ence + 8 * j, 1);
             mbar_init(bar_accf + 8 * j, 1);
-            mbar_init(bar_epi + 8 * j, 8);
+            mbar_init(bar_epi + 8 * j, 8 * NCTA);              // the epilogue warps of BOTH CTAs report to the leader
         }
         for (int s = 0; s < FZ_STAGES; ++s) { mbar_init(bar_wf + 8 * s, 1); mbar_init(bar_we + 8 * s, 1); }
         fence_barrier_init();
         tma_prefetch_desc(&tmE);
         for (int l = 0; l < 8; ++l) tma_prefetch_desc(&wm.w[l]);
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+    if (warp == 1) {
+        if (NCTA == 2) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
+        else tmem_alloc(smem_u32(&tmem_slot), 512);
+    }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();                                // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const int ntiles = (g.rows + 127) >> 7, npairs = (ntiles + 1) >> 1;
+    // unit of work: 2 * NCTA row tiles; CTA `rank` of the unit owns tiles unit * 2 NCTA + 2 rank + {0, 1}
+    const int ntiles = (g.rows + 127) >> 7, npairs = (ntiles + 2 * NCTA - 1) / (2 * NCTA);
+    const int unit0 = (int)blockIdx.x / NCTA, ustep = (int)gridDim.x / NCTA;
+    auto tile_of = [&](int unit, int j) { return unit * 2 * NCTA + 2 * rank + j; };
 
     if (warp == 0) {
-        // ===== producer
+        // ===== producer (a dedicated warp: it polls, no suspend)
         if (lane == 0) {
-            auto issue_enc = [&](int it, int pair) {
-                for (int j = 0; j < 2; ++j) {
-                    mbar_wait(bar_ence + 8 * j, (uint32_t)((it & 1) ^ 1), 21);
-                    mbar_expect_tx(bar_encf + 8 * j, FZ_BLK);
-                    tma_load_2d(smem_u32(sEnc + j * FZ_BLK), &tmE, bar_encf + 8 * j, 0, (2 * pair + j) * 128);
-                }
-            };
-            int s = 0, it = 0;
+            int s = 0;
             uint32_t ph = 0;
-            if ((int)blockIdx.x < npairs) issue_enc(0, blockIdx.x);
-            for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
+            auto put = [&](const CUtensorMap* m, int c0, int c1) {
+                mbar_wait_spin(bar_we + 8 * s, ph ^ 1, 22);
+                if (NCTA == 2) {
+                    // both CTAs fill the same stage of their own ring; the bytes of both count on the leader's barrier
+                    if (rank == 0) mbar_expect_tx(bar_wf + 8 * s, 2 * FZ_BLK);
+                    tma_load_2d_2sm(smem_u32(sW + s * FZ_BLK), m, (bar_wf + 8 * s) & TC_PEER_MASK, c0, c1);
+                } else {
+                    mbar_expect_tx(bar_wf + 8 * s, FZ_BLK);
+                    tma_load_2d(smem_u32(sW + s * FZ_BLK), m, bar_wf + 8 * s, c0, c1);
+                }
+                if (++s == FZ_STAGES) { s = 0; ph ^= 1; }
+            };
+            for (int pair = unit0; pair < npairs; pair += ustep)
                 for (int l = 0; l < 8; ++l) {
                     const int KB = fz_kblocks(l);
-                    for (int j = 0; j < 2; ++j)
-                        for (int kb = 0; kb < KB; ++kb)
-                            for (int h = 0; h < 2; ++h) {
-                                mbar_wait(bar_we + 8 * s, ph ^ 1, 22);
-                                mbar_expect_tx(bar_wf + 8 * s, FZ_BLK);
-                                tma_load_2d(smem_u32(sW + s * FZ_BLK), &wm.w[l], bar_wf + 8 * s, kb * 64, h * 128);
-                                if (++s == FZ_STAGES) { s = 0; ph ^= 1; }
-                            }
-                    // the encoding tiles were last read by layer 4: fetch the next pair's while layers 6, 7 run
-                    if (l == 5 && pair + (int)gridDim.x < npairs) issue_enc(it + 1, pair + gridDim.x);
+                    for (int j = 0; j < 2; ++j) {
+                        if (l == 0 || l == 4) put(&tmE, 0, tile_of(pair, j) * 128);      // rows past the end read as zero
+                        for (int kb = 0; kb < KB; ++kb) {
+                            if (NCTA == 2) put(&wm.w[l], kb * 64, rank * 128);           // this CTA's half of the 256 weight rows
+                            else for (int h = 0; h < 2; ++h) put(&wm.w[l], kb * 64, h * 128);
+                        }
+                    }
                 }
-            }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer
-        constexpr uint32_t idesc = make_idesc(0, 0, 0, 0, 128, 128);
-        int s = 0, it = 0;
-        uint32_t ph = 0, ed[2] = {0, 0};
-        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
+    } else if (warp == 1 && rank == 0) {
+        // ===== MMA issuer (NCTA = 2: the leader's, for both SMs)
+        constexpr uint32_t idesc = NCTA == 2 ? make_idesc(0, 0, 0, 0, 256, 256) : make_idesc(0, 0, 0, 0, 128, 128);
+        int s = 0;
+        uint32_t ph = 0, ed0 = 0, ed1 = 0;
+        for (int pair = unit0; pair < npairs; pair += ustep) {
             for (int l = 0; l < 8; ++l) {
                 const int KB = fz_kblocks(l);
                 for (int j = 0; j < 2; ++j) {
-                    if (l == 0) mbar_wait(bar_encf + 8 * j, (uint32_t)(it & 1), 23);
                     // accumulator j drained and (l > 0) the fp16 activations of layer l-1 written by the epilogue
-                    mbar_wait_spin(bar_epi + 8 * j, ed[j] ^ 1, 24);
-                    ed[j] ^= 1;
+                    uint32_t& ed = j ? ed1 : ed0;
+                    if (NCTA == 2) mbar_wait_cluster(bar_epi + 8 * j, ed ^ 1, 24);
+                    else mbar_wait_spin(bar_epi + 8 * j, ed ^ 1, 24);
+                    ed ^= 1;
                     tc_fence_after();
-                    const uint32_t enc_a = smem_u32(sEnc + j * FZ_BLK), act_a = smem_u32(sAct + j * 4 * FZ_BLK);
+                    const uint32_t act_a = smem_u32(sAct + j * 4 * FZ_BLK);
+                    uint32_t enc_a = 0, enc_bar = 0;
+                    if (l == 0 || l == 4) {                    // this tile's encoding block arrives through the ring
+                        mbar_wait_spin(bar_wf + 8 * s, ph, 23);
+                        enc_a = smem_u32(sW + s * FZ_BLK);
+                        enc_bar = bar_we + 8 * s;
+                        if (++s == FZ_STAGES) { s = 0; ph ^= 1; }
+                    }
                     for (int kb = 0; kb < KB; ++kb) {
                         const uint32_t a0 = l == 0 ? enc_a : (l == 4 ? (kb == 0 ? enc_a : act_a + (kb - 1) * FZ_BLK) : act_a + kb * FZ_BLK);
-                        for (int h = 0; h < 2; ++h) {
+                        for (int h = 0; h < (NCTA == 2 ? 1 : 2); ++h) {
                             mbar_wait_spin(bar_wf + 8 * s, ph, 25);
                             tc_fence_after();
                             if (lane == 0) {
                                 const uint32_t b0 = smem_u32(sW + s * FZ_BLK);
                                 const uint32_t d = tmem_base + (uint32_t)(j * 256 + h * 128);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_f16(d, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
-                                             (uint32_t)((kb | k) != 0));
-                                umma_commit(bar_we + 8 * s);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (NCTA == 2)
+                                        umma_f16_2sm(d, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                                     (uint32_t)((kb | k) != 0));
+                                    else
+                                        umma_f16(d, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                                 (uint32_t)((kb | k) != 0));
+                                }
+                                if (NCTA == 2) {
+                                    umma_commit_2sm(bar_we + 8 * s);
+                                    if (enc_bar && kb == 0) umma_commit_2sm(enc_bar);
+                                } else {
+                                    umma_commit(bar_we + 8 * s);
+                                    if (enc_bar && kb == 0 && h == 1) umma_commit(enc_bar);     // both halves have read the encoding
+                                }
                             }
                             __syncwarp();
                             if (++s == FZ_STAGES) { s = 0; ph ^= 1; }
                         }
                     }
                     if (lane == 0) {
-                        umma_commit(bar_accf + 8 * j);
-                        if (l == 4) umma_commit(bar_ence + 8 * j);
+                        if (NCTA == 2) umma_commit_2sm(bar_accf + 8 * j);
+                        else umma_commit(bar_accf + 8 * j);
                     }
                     __syncwarp();
                 }
             }
         }
-    } else {
-        // ===== epilogue: warp -> TMEM lane quadrant q (rows q*32 + lane of the tile), column half (128 of the 256 features)
+    } else if (warp >= 2) {
+        // ===== epilogue: warp -> TMEM lane quadrant q (rows q*32 + lane of the tile), column half (128 of the 256 features).
+        // The two 64-column TMEM loads of a step are software-pipelined (the second is in flight while the first is
+        // converted), biases / output weights come from constant memory (warp-uniform addresses: no load latency on the
+        // critical path; ncu on the first version: 28 % of all stall samples behind tcgen05.wait::ld, long-scoreboard
+        // stalls on the bias loads, tensor pipe 40 % busy because the epilogue, not the MMA, set the pace).
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        uint32_t af[2] = {0, 0};
-        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            for (int l = 0; l < 8; ++l) {
-                for (int j = 0; j < 2; ++j) {
-                    mbar_wait_spin(bar_accf + 8 * j, af[j], 26);
-                    af[j] ^= 1;
-                    tc_fence_after();
-                    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 256 + half * 128);
-                    const float* bias = g.bias[l] + half * 128;
-                    const uint32_t act_a = smem_u32(sAct + j * 4 * FZ_BLK);
-                    float dot = 0.f;
+        uint32_t af0 = 0, af1 = 0;
+        auto step = [&](auto last_tag, int l, int j, int pair) {
+            constexpr bool LAST = decltype(last_tag)::value;
+            uint32_t& af = j ? af1 : af0;
+            mbar_wait_spin(bar_accf + 8 * j, af, 26);
+            af ^= 1;
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 256 + half * 128);
+            const float* cb = c_fz + l * 256 + half * 128;
+            const float* cw = c_fz + 8 * 256 + half * 128;
+            const uint32_t act_a = smem_u32(sAct + j * 4 * FZ_BLK);
+            float dot = 0.f;
+            uint32_t r[2][32];
+            auto process = [&](uint32_t (&rr)[32], int ch) {
+                const int n0 = ch * 32;                              // first of this thread's 32 columns within the half
+                uint32_t pk[16];
 #pragma unroll
-                    for (int cp = 0; cp < 2; ++cp) {
-                        uint32_t r[2][32];
-                        tmem_ld32_issue(tbase + cp * 64, r[0]);
-                        tmem_ld32_issue(tbase + cp * 64 + 32, r[1]);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int c2 = 0; c2 < 2; ++c2) {
-                            const int n0 = cp * 64 + c2 * 32;              // first of this thread's 32 columns within the half
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + j4);
-                                const __half2 h01 = __floats2half2_rn(__uint_as_float(r[c2][4 * j4 + 0]) + b4.x,
-                                                                      __uint_as_float(r[c2][4 * j4 + 1]) + b4.y);
-                                const __half2 h23 = __floats2half2_rn(__uint_as_float(r[c2][4 * j4 + 2]) + b4.z,
-                                                                      __uint_as_float(r[c2][4 * j4 + 3]) + b4.w);
-                                pk[2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
-                                pk[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                                if (l == 7) {
-                                    // the output layer sees the same fp16-rounded H_7 the layered path stores
-                                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.wout + half * 128 + n0) + j4);
-                                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                                    dot = fmaf(f01.x, w4.x, dot);
-                                    dot = fmaf(f01.y, w4.y, dot);
-                                    dot = fmaf(f23.x, w4.z, dot);
-                                    dot = fmaf(f23.y, w4.w, dot);
-                                }
-                            }
-                            if (l < 7) {
-                                // columns half*128 + n0 .. +31 = k-block (half*2 + cp) of the next layer's A, 16-byte chunks
-                                // c2*4 .. c2*4+3 of this row, at their SWIZZLE_128B positions
-                                const uint32_t rb = act_a + (uint32_t)((half * 2 + cp) * FZ_BLK + row * 128);
-#pragma unroll
-                                for (int m = 0; m < 4; ++m)
-                                    sts128(rb + (uint32_t)((((c2 * 4 + m) ^ (row & 7))) << 4),
-                                           make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]));
-                            }
-                        }
+                for (int i = 0; i < 16; ++i) {
+                    const __half2 h2 = __floats2half2_rn(__uint_as_float(rr[2 * i]) + cb[n0 + 2 * i],
+                                                         __uint_as_float(rr[2 * i + 1]) + cb[n0 + 2 * i + 1]);
+                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    if (LAST) {
+                        // the output layer sees the same fp16-rounded H_7 the layered path stores
+                        const float2 f = __half22float2(h2);
+                        dot = fmaf(f.x, cw[n0 + 2 * i], dot);
+                        dot = fmaf(f.y, cw[n0 + 2 * i + 1], dot);
                     }
-                    if (l < 7) fence_proxy_async();               // the tensor core reads these stores through the async proxy
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_epi + 8 * j);
-                    if (l == 7) {
-                        if (half == 1) part[j][row] = dot;
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
-                        if (half == 0) {
-                            const int64_t grow = (int64_t)(2 * pair + j) * 128 + row;
-                            if (grow < g.rows) {
-                                const float t = dot + part[j][row] + __ldg(g.wout + 256);
-                                g.out_p[grow] = 1.f / (1.f + expf(-t));
-                            }
-                        }
+                }
+                if (!LAST) {
+                    // columns half*128 + n0 .. +31 = half a k-block (half*2 + ch/2) of the next layer's A: 16-byte chunks
+                    // (ch&1)*4 .. +3 of this row, at their SWIZZLE_128B positions
+                    const uint32_t rbase = act_a + (uint32_t)((half * 2 + (ch >> 1)) * FZ_BLK + row * 128);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        sts128(rbase + (uint32_t)(((((ch & 1) * 4 + m) ^ (row & 7))) << 4),
+                               make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]));
+                }
+            };
+            // 32-column TMEM loads, one ahead of the conversion
+            tmem_ld32_issue(tbase, r[0]);
+            tmem_ld_wait();
+            tmem_ld32_issue(tbase + 32, r[1]);
+            process(r[0], 0);
+            tmem_ld_wait();
+            tmem_ld32_issue(tbase + 64, r[0]);
+            process(r[1], 1);
+            tmem_ld_wait();
+            tmem_ld32_issue(tbase + 96, r[1]);
+            process(r[0], 2);
+            tmem_ld_wait();
+            process(r[1], 3);
+            if (!LAST) fence_proxy_async();                   // the tensor core reads these stores through the async proxy
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (NCTA == 2) mbar_arrive_leader(bar_epi + 8 * j);
+                else mbar_arrive(bar_epi + 8 * j);
+            }
+            if (LAST) {
+                if (half == 1) part[j][row] = dot;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0) {
+                    const int64_t grow = (int64_t)tile_of(pair, j) * 128 + row;
+                    if (grow < g.rows) {
+                        const float t = dot + part[j][row] + c_fz[8 * 256 + 256];
+                        g.out_p[grow] = 1.f / (1.f + expf(-t));
                     }
                 }
             }
+        };
+        for (int pair = unit0; pair < npairs; pair += ustep) {
+            for (int l = 0; l < 7; ++l) {
+                step(std::false_type{}, l, 0, pair);
+                step(std::false_type{}, l, 1, pair);
+            }
+            step(std::true_type{}, 7, 0, pair);
+            step(std::true_type{}, 7, 1, pair);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (NCTA == 2) {
+        cluster_sync_all();                                           // the peer may still be reading its accumulators
+        if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+    } else if (warp == 1) {
+        tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1120,8 +1234,8 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
 
 }  // namespace
 
-static int g_fused_eval = 1;
-extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on ? 1 : 0; }
+static int g_fused_eval = 2;     // 0 = layered, 1 = fused (one CTA per unit), 2 = fused on CTA pairs (cta_group::2)
+extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on < 0 ? 0 : (on > 2 ? 2 : on); }
 extern "C" int pcnerf_tc_get_fused_eval(void) { return g_fused_eval; }
 
 // fp32 padded weight copies (same kernel as the fp32 path; defined in mlp_small.cuh)
@@ -1176,18 +1290,42 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
             rc = make_map(&wm.w[l], tc_Wh(L, scratch, l), 256, mlp_kpad(l), mlp_kpad(l), 128);
             if (rc) return rc;
         }
+        if (!P->prepared) {
+            PCN_CUDA(cudaMemcpyToSymbolAsync(c_fz, P->b[0], 256 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+            PCN_CUDA(cudaMemcpyToSymbolAsync(c_fz, L.bf(scratch, 1), 7 * 256 * sizeof(float), 256 * sizeof(float),
+                                             cudaMemcpyDeviceToDevice, st));
+            PCN_CUDA(cudaMemcpyToSymbolAsync(c_fz, L.wout_f(scratch), 257 * sizeof(float), 8 * 256 * sizeof(float),
+                                             cudaMemcpyDeviceToDevice, st));
+        }
         FusedArgs fa;
         fa.rows = (int)rows;
-        fa.bias[0] = P->b[0];
-        for (int l = 1; l < 8; ++l) fa.bias[l] = L.bf(scratch, l);
-        fa.wout = L.wout_f(scratch);
         fa.out_p = out_p;
-        const size_t smem = 1024 + (size_t)(2 + 8 + FZ_STAGES) * FZ_BLK;
-        const int npairs = (int)pcn_cdiv(pcn_cdiv(rows, 128), 2);
-        const int grid = npairs < sm_count() ? npairs : sm_count();
-        PCN_CUDA(cudaFuncSetAttribute(k_tc_fused_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = 1024 + (size_t)(8 + FZ_STAGES) * FZ_BLK;
         PcnScope ps(PCN_K_GEMM_FWD, st, (double)rows * 982528.0);
-        k_tc_fused_eval<<<grid, TC_THREADS, smem, st>>>(mE, wm, fa);
+        if (g_fused_eval == 2) {
+            // CTA pairs (cta_group::2): clusters of two CTAs, four row tiles per unit of work
+            const int nunits = (int)pcn_cdiv(pcn_cdiv(rows, 128), 4);
+            const int ncl = nunits < sm_count() / 2 ? nunits : sm_count() / 2;
+            PCN_CUDA(cudaFuncSetAttribute(k_tc_fused_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * ncl);
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_fused_eval<2>, mE, wm, fa));
+        } else {
+            const int npairs = (int)pcn_cdiv(pcn_cdiv(rows, 128), 2);
+            const int grid = npairs < sm_count() ? npairs : sm_count();
+            PCN_CUDA(cudaFuncSetAttribute(k_tc_fused_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_tc_fused_eval<1><<<grid, TC_THREADS, smem, st>>>(mE, wm, fa);
+        }
         PCN_LAUNCH_CHECK();
         return 0;
     }

@@ -305,8 +305,8 @@ GRAD_SIZES = [256 * 63, 256] + [256 * 256, 256] * 3 + [256 * 319, 256] + [256 * 
 def tc_fused_eval(on=None):
     """Get / set the eval-mode engine of the precision-1 MLP: fused single kernel (default) or layered row GEMMs."""
     if on is not None:
-        lib().pcnerf_tc_set_fused_eval(1 if on else 0)
-    return bool(lib().pcnerf_tc_get_fused_eval())
+        lib().pcnerf_tc_set_fused_eval(int(on))
+    return int(lib().pcnerf_tc_get_fused_eval())
 
 
 class MLPFunction(torch.autograd.Function):

@@ -20,7 +20,7 @@ out = {"peak_tflops_sustained": peak["bf16_tflops_sustained"], "peak_tflops_burs
 for rows in (262144, 1 << 20, 1 << 22):
     enc = (torch.randn(rows, 64, device=dev) * 0.7).half()
     enc[:, 63] = 0
-    for fused in (True, False):
+    for fused in (2, 1, 0):
         ops.tc_fused_eval(fused)
         with torch.no_grad():
             for _ in range(2):
@@ -36,7 +36,7 @@ for rows in (262144, 1 << 20, 1 << 22):
         ms = prof["mlp_gemm_fwd"][0] / n
         small = prof["mlp_small"][0] / n
         tf = rows * 982528.0 / (ms * 1e-3) / 1e12
-        out["runs"].append({"rows": rows, "engine": "fused" if fused else "layered", "gemm_ms": ms, "small_ms": small,
+        out["runs"].append({"rows": rows, "engine": ("layered", "fused", "fused, CTA pairs")[fused], "gemm_ms": ms, "small_ms": small,
                             "tflops": tf, "frac_sustained": tf / peak["bf16_tflops_sustained"]})
-ops.tc_fused_eval(True)
+ops.tc_fused_eval(2)
 print(json.dumps(out))

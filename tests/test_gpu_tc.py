@@ -71,6 +71,9 @@ def test_wgrad_mn_major(rows, ncols, xdt):
     assert float(rest.abs().max()) == 0.0
 
 
+DEFAULT_FUSED = 2
+
+
 def _enc(rows, seed):
     gen = torch.Generator().manual_seed(seed)
     x = (torch.rand(rows, 3, generator=gen) - 0.5) * 60.0
@@ -168,13 +171,14 @@ def test_mlp_eval_tc_chunking_is_invisible():
         assert torch.equal(mc.state_dict()[k].cpu(), sd[k])
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("rows", [127, 130, 3000, 100003])
-def test_mlp_eval_fused_matches_layered(rows):
+def test_mlp_eval_fused_matches_layered(rows, mode):
     """k_tc_fused_eval (all layers in one kernel, activations in shared memory / TMEM) against the layered eval path (same
     fp16 operands, same folded weights: the hidden activations are bit-identical, only the 256-term output dot is summed in
     a different order) and against the fp32 oracle at the tensor-core gate.  Row counts: a lone partial tile (the pair's
     second tile is entirely out of bounds), a partial second tile, many pairs, and more pairs than CTAs (barrier phases
-    wrap, encoding prefetch of the next pair)."""
+    wrap).  mode 1 = one CTA per unit of work, mode 2 = CTA pairs (cta_group::2 MMAs, M = 256)."""
     from pcnerf_b200 import ops
     enc = _enc(rows, rows + 3)
     mc, _, _ = make_nets(42, 43, True, "tc")
@@ -183,14 +187,14 @@ def test_mlp_eval_fused_matches_layered(rows):
     mc.eval()
     sd = {k: v.detach().cpu().clone() for k, v in mc.state_dict().items()}
     try:
-        ops.tc_fused_eval(False)
+        ops.tc_fused_eval(0)
         with torch.no_grad():
             p_lay = mc.forward_encoded(encd, 1 << 20).cpu()
-        ops.tc_fused_eval(True)
+        ops.tc_fused_eval(mode)
         with torch.no_grad():
             p_fus = mc.forward_encoded(encd, 1 << 20).cpu()
     finally:
-        ops.tc_fused_eval(True)
+        ops.tc_fused_eval(DEFAULT_FUSED)
     assert ops.lib().pcnerf_tc_last_fault() == 0
     np.testing.assert_allclose(p_fus.numpy(), p_lay.numpy(), rtol=2e-5, atol=1e-7)
     n_ref = min(rows, 4096)
