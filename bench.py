@@ -490,6 +490,26 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
     ms = torch.tensor([e0.elapsed_time(e1) / reps_t], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # where the frame goes (separate pass with the library's per-class CUDA events) and the tensor roofline of the
+    # eval-mode MLP kernel (k_tc_fused_eval when precision = tc): 982,528 FLOP per sample evaluation
+    ops_mod.profile(True)
+    frame()
+    torch.cuda.synchronize()
+    prof = ops_mod.profile_read()
+    ops_mod.profile(False)
+    classes = {k: {"ms_per_frame": v[0], "launches": v[1]} for k, v in prof.items() if v[1]}
+    mlp_roof = None
+    f_ms, f_n, f_fl = prof["mlp_gemm_fwd"]
+    if f_ms > 0 and a.precision == "tc":
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            src = "MEASURED_PEAKS.json bf16_tflops_sustained"
+        except (OSError, ValueError, KeyError):
+            peak, src = 1400.0, "fallback 1400"
+        tf = f_fl / (f_ms * 1e-3) / 1e12
+        mlp_roof = {"kernel": "k_tc_fused_eval (eval-mode MLP, all layers in one tcgen05 kernel, CTA pairs)", "bound": "tensor",
+                    "achieved": tf, "peak": peak, "peak_source": src, "unit": "TFLOP/s", "frac": tf / peak,
+                    "launches_per_frame": f_n, "share_of_frame": f_ms / float(ms.item())}
     # downstream step: Chamfer distance / F-score of the rendered cloud against the returns
     from pcnerf_b200.nof.criteria.metrics import eval_points
     heads = np.nonzero(rows[:base_phys * 40, 12] >= 0)[0][:base_phys]
@@ -522,7 +542,7 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
             "chamfer_untrained_net": cd, "value": world * n_phys / (float(ms.item()) * 1e-3),
             "unit": "rays/s", "ms_per_frame": float(ms.item()), "physical_rays_per_gpu": n_phys,
             "candidate_rows_per_gpu": int(rows.shape[0]), "N_samples": S, "N_importance": NI, "batch_rows": 18432,
-            "precision": a.precision}
+            "precision": a.precision, "kernels": classes, "roofline": mlp_roof}
 
 
 def run_reference(a):
