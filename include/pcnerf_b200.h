@@ -277,6 +277,18 @@ int pcnerf_nn_correspondance(const double* verts1, int64_t n1, const double* ver
 /* sums2 = {sum dist, count(dist < threshold)} (the ingredients of eval_pts, pointcloud_metrics.py:39-49). */
 int pcnerf_dist_stats(const double* dist, int64_t n, double threshold, double* sums2, void* stream);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * K0  LiDAR frame -> returns of the block.  Replaces the numpy / python filtering of
+ * nof/dataset/ipb2dmapping.py:662-711: near-sensor box |x|>=rdx or |y|>=rdy or |z|>=rdz, range <= max_range, height window
+ * (float32, sensor frame), pose transform in float64 (h_pose16: HOST 4x4 row-major, float32 values), interest region
+ * around any of the `npose` run poses (pose_xy (npose,2) float32, device), ray direction / range from pose[:3,3].
+ * pts (n,3) float32.  Outputs for EVERY point (the caller compacts in order with `keep`): keep (n) uint8, world (n,3),
+ * dir (n,3), dist (n) float64.  The outputs feed pcnerf_aabb_pack_train unchanged.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pcnerf_frame_returns(const float* pts, int64_t n, const double* h_pose16, const float* pose_xy, int npose, float rdx,
+                         float rdy, float rdz, float max_range, float over_height, float over_low, float interest_x,
+                         float interest_y, uint8_t* keep, double* world, double* dir, double* dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -729,3 +729,96 @@ def eval_pts(pts1, pts2, threshold=0.2):
     fscore = 2 * precision * recall / (precision + recall)
     cd = np.mean(dist1) + np.mean(dist2)
     return cd, fscore
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KITTI dataset build: pose file, per-frame filtering / transform, then the packing above.
+# Pinned by tests/golden/kitti_dataset.npz (oracle/make_golden_dataset.py executes the reference class itself).
+# ---------------------------------------------------------------------------------------------------------------
+T_VELO2CAM = np.array([[4.276802385584e-04, -9.999672484946e-01, -8.084491683471e-03, -1.198459927713e-02],
+                       [-7.210626507497e-03, 8.081198471645e-03, -9.999413164504e-01, -5.403984729748e-02],
+                       [9.999738645903e-01, 4.859485810390e-04, -7.206933692422e-03, -2.921968648686e-01],
+                       [0, 0, 0, 1]])
+
+
+def kitti_poses(pose_lines, data_start):
+    """ipb2dmapping.py:566-591: every pose is (P @ T_velo2cam), re-expressed in the frame of pose data_start+1; the
+    product is taken in float32 (torch.Tensor(...)).  Returns a float32 torch tensor (n,4,4)."""
+    poses = []
+    for row in pose_lines:
+        P = np.append(np.array([float(i) for i in row.strip("\n").split(" ")]).reshape(3, 4), np.array([[0, 0, 0, 1]]), axis=0)
+        poses.append(np.matmul(P, T_VELO2CAM))
+    poses = np.array(poses)
+    T_start_inv = torch.from_numpy(np.linalg.inv(poses[data_start + 1])).float()
+    return T_start_inv @ torch.Tensor(poses)
+
+
+def kitti_frame_returns(points_f32, poses, j, data_start, data_end, range_delete_x, range_delete_y, range_delete_z,
+                        over_height, over_low, interest_x, interest_y):
+    """ipb2dmapping.py:662-711 for frame file j+1: near-sensor box removal, 120 m range gate, height window (all on the
+    float32 sensor-frame points), pose transform in float64 (float32 pose entries), interest region around any pose of the
+    run (float32 arithmetic: numpy-scalar minus 0-d float32 tensor), then ray directions / ranges from the sensor position.
+    Returns (world points (M,3) f64, dir (M,3) f64, dist (M,) f64, position (3,) f32 tensor)."""
+    p = np.asarray(points_f32, dtype=np.float32)
+    mask1 = np.logical_or.reduce((np.abs(p[:, 0]) >= range_delete_x, np.abs(p[:, 1]) >= range_delete_y,
+                                  np.abs(p[:, 2]) >= range_delete_z))
+    p = p[mask1]
+    p = p[np.linalg.norm(p, axis=1) <= 120]
+    p = p[p[:, 2] <= over_height]
+    p = p[p[:, 2] >= over_low]
+    pe = np.vstack((p.T, np.ones((1, p.shape[0]))))
+    pe = (poses[j + 1].numpy() @ pe).T[:, :3]                  # float32 pose promoted to float64 by numpy
+    px = poses[data_start + 1:data_end + 1, 0, -1]
+    py = poses[data_start + 1:data_end + 1, 1, -1]
+    x32 = torch.from_numpy(pe[:, 0].astype(np.float32))        # np.float64 scalar - float32 tensor -> float32 arithmetic
+    y32 = torch.from_numpy(pe[:, 1].astype(np.float32))
+    near = ((x32[:, None] - px[None, :]).abs() <= interest_x) & ((y32[:, None] - py[None, :]).abs() <= interest_y)
+    pe = pe[near.any(1).numpy()]
+    pos = poses[j + 1][:3, -1]
+    vec = pe - np.array([pos[0], pos[1], pos[2]])
+    dist_vec = np.linalg.norm(vec, axis=1)
+    dir_vec = np.apply_along_axis(lambda x: x / np.linalg.norm(x), 1, vec) if len(vec) else vec
+    return pe, dir_vec, dist_vec, pos
+
+
+def kitti_child_boxes(child_clouds, extend=0.025):
+    """ipb2dmapping.py:596-626: child bounds = axis-aligned bounds of each child cloud +- 0.025, centre of the raw bounds."""
+    K = len(child_clouds)
+    bound, centre = np.zeros((K, 6)), np.zeros((K, 3))
+    for i, c in enumerate(child_clouds):
+        c = np.asarray(c, dtype=np.float64)
+        lo, hi = c.min(0), c.max(0)
+        bound[i, :3], bound[i, 3:] = lo - extend, hi + extend
+        centre[i] = (lo + hi) / 2.0
+    return bound, bound.copy(), centre
+
+
+def kitti_train_frames(data_start, data_end, split="train"):
+    """Frame selection of ipb2dmapping.py:643-658 (frame sparsity 20 %): file numbers j+1."""
+    out = []
+    for j in range(data_start, data_end):
+        if split == "train" and (j + 1 - 3 - data_start) % 5 != 0:
+            out.append(j)
+        elif split == "val" and (j + 1 - 3) % 5 == 0:
+            out.append(j)
+    return out
+
+
+def kitti_build_rays(frames, pose_lines, child_clouds, parent_cloud, data_start, data_end, split="train", **kw):
+    """kitti_dataload(re_loaddata=1) end to end.  frames: {file number: (N,3) float32}.  Returns (rays (N,15) f32, ranges)."""
+    poses = kitti_poses(pose_lines, data_start)
+    bound, bigger, centre = kitti_child_boxes(child_clouds)
+    par = np.asarray(parent_cloud, dtype=np.float64)
+    lo, hi = par.min(0), par.max(0)
+    parent_box = (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
+    rays = []
+    for j in kitti_train_frames(data_start, data_end, split):
+        pe, dir_vec, dist_vec, pos = kitti_frame_returns(frames[j + 1], poses, j, data_start, data_end,
+                                                         kw["range_delete_x"], kw["range_delete_y"], kw["range_delete_z"],
+                                                         kw["over_height"], kw["over_low"], kw["interest_x"], kw["interest_y"])
+        r, _ = pack_train_rays_from_dirs(pos.numpy().astype(np.float64), dir_vec, dist_vec, pe, centre, bound, bigger,
+                                         parent_box, kw["surface_expand"], "kitti")
+        r[:, 0:3] = pos.numpy()                                 # rays_o is the float32 pose translation itself (:788)
+        rays.append(r)
+    rays = np.concatenate(rays) if rays else np.zeros((0, 15), np.float32)
+    return rays, rays[:, 14].copy()

@@ -25,6 +25,7 @@ SOURCES = {
     "mlp_tc.cu": [],
     "affine.cu": [],
     "metrics.cu": ["-fmad=false"],
+    "frame.cu": ["-fmad=false"],
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
           "-Xcompiler", "-fPIC"]

@@ -3,12 +3,18 @@ behaviour) plus the batched ray-packing rule that the reference inlines in its d
 
 The scalar-style functions accept what the reference accepts (numpy arrays / python scalars for ONE ray) and return
 python / numpy values; they launch the same fp64 kernels as the batched entry point, so they are meant for parity
-checks and drop-in compatibility -- use `pack_train_rays` for real work.  File IO (PCD / pose parsing, filtering,
-the .npy cache) is out of scope.
-"""
-import numpy as np
+checks and drop-in compatibility -- use `pack_train_rays` for real work.
 
-from ... import ops
+`kitti_dataload` is the reference's KITTI dataset class with the per-point python loops
+replaced by two kernels per frame (K0 frame -> returns, K1 returns -> 15-column rays) and open3d / pcl replaced by
+pcnerf_b200.pcd: same constructor arguments, same `rays` / `ranges`, same `.npy` cache files.
+"""
+import os
+
+import numpy as np
+import torch
+
+from ... import ops, pcd
 
 
 def compute_far_bound(ray_o, ray_d, x_max, x_min, y_max, y_min, z_max, z_min):
@@ -57,3 +63,94 @@ def pack_train_rays(origin, points, centres, child_bounds, child_bounds_bigger, 
         dir_vec = vec / dist_vec[:, None]
     return ops.aabb_pack_train(406 if variant == "maicity" else 606, origin, dir_vec, dist_vec, points, centres,
                                child_bounds, child_bounds_bigger, parent_box, surface_expand, 10)
+
+
+
+class kitti_dataload(torch.utils.data.Dataset):
+    """nof/dataset/ipb2dmapping.py:516-836 (constructor signature, frame selection, outputs and cache paths as there).
+
+    re_loaddata = 1: read the frames `root_dir/{j+1}.pcd`, the child clouds `subnerf_path/{i+1}.pcd` and the parent cloud,
+    build `self.rays` (N,15) / `self.ranges` on the GPU and save them under `result_path/save_npy/split_child_nerf2_3/`;
+    re_loaddata = 0: load that cache (:826-836).  Against the reference executed on the same files the child index, origins,
+    directions and ranges are identical; the four bound columns (7, 10, 11, 13) agree to one float32 ulp -- the reference
+    evaluates compute_far_bound0606 / compute_far_bound with a float32 tensor origin, i.e. partly in float32, this path in
+    float64 (tests/test_gpu_dataset.py, fixture produced by oracle/make_golden_dataset.py running the reference class)."""
+
+    def __init__(self, root_dir, split='train', data_start=1439, data_end=1510, cloud_size_val=2048,
+                 range_delete_x=2, range_delete_y=1, range_delete_z=0.5, sub_nerf_test_num=3, surface_expand=0.1,
+                 over_height=0.168, over_low=-2, interest_x=12, interest_y=12, pose_path=None, subnerf_path=None,
+                 parentnerf_path=None, re_loaddata=0, result_path=None):
+        super(kitti_dataload, self).__init__()
+        self.root_dir, self.split, self.cloud_size_val = root_dir, split, cloud_size_val
+        self.parentnerf_path, self.result_path, self.re_loaddata = parentnerf_path, result_path, re_loaddata
+        if re_loaddata:
+            self.data_start, self.data_end = data_start, data_end
+            self.range_delete = (range_delete_x, range_delete_y, range_delete_z)
+            self.sub_nerf_test_num, self.subnerf_path, self.surface_expand = sub_nerf_test_num, subnerf_path, surface_expand
+            self.over_height, self.over_low, self.interest_x, self.interest_y = over_height, over_low, interest_x, interest_y
+            lo, hi = pcd.axis_aligned_bounds(pcd.read_pcd(parentnerf_path))
+            self.parent_box = (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
+            self.poses = pcd.read_kitti_poses(pose_path, data_start)            # (n,4,4) float32
+            self.positions = self.poses[:, :3, -1]
+        self.load_data()
+
+    def _cache(self, what):
+        return os.path.join(self.result_path, "save_npy", "split_child_nerf2_3", "self_%s_%s.npy" % (what, self.split))
+
+    def frames(self):
+        """File numbers j+1 of this split (frame sparsity 20 %, :643-658)."""
+        out = []
+        for j in range(self.data_start, self.data_end):
+            if self.split == 'train' and (j + 1 - 3 - self.data_start) % 5 != 0:
+                out.append(j)
+            elif self.split == 'val' and (j + 1 - 3) % 5 == 0:
+                out.append(j)
+        return out
+
+    def load_data(self):
+        self._build_or_load()
+        if self.split == 'train':                                                 # :854-856
+            self.all_rays, self.all_ranges = self.rays, self.ranges
+        else:                                                                     # :865-870 (evenly spaced validation rays)
+            n = self.rays.shape[0]
+            sel = torch.linspace(1, n - 2, steps=self.cloud_size_val, dtype=torch.float32).floor().long()
+            self._val_rays, self._val_ranges = self.rays[sel].float(), self.ranges[sel].float()
+
+    def _build_or_load(self):
+        if not self.re_loaddata:
+            self.rays = torch.from_numpy(np.load(self._cache("rays")))
+            self.ranges = torch.from_numpy(np.load(self._cache("ranges")))
+            return
+        K = self.sub_nerf_test_num
+        bound, centre = np.zeros((K, 6)), np.zeros((K, 3))
+        for i in range(K):                                                        # :600-626
+            lo, hi = pcd.axis_aligned_bounds(pcd.read_pcd(os.path.join(self.subnerf_path, "%d.pcd" % (i + 1))))
+            bound[i, :3], bound[i, 3:] = lo - 0.025, hi + 0.025
+            centre[i] = (lo + hi) / 2.0
+        pose_xy = self.poses[self.data_start + 1:self.data_end + 1, :2, -1]
+        rays, counts = [], torch.zeros(K, dtype=torch.int64)
+        for j in self.frames():
+            pts = pcd.read_pcd(os.path.join(self.root_dir, "%d.pcd" % (j + 1)))
+            world, dirs, dist = ops.frame_returns(pts, self.poses[j + 1], pose_xy, self.range_delete, 120.0,
+                                                  self.over_height, self.over_low, self.interest_x, self.interest_y)
+            origin = self.positions[j + 1].astype(np.float64)
+            r, _ = ops.aabb_pack_train(606, origin, dirs, dist, world, centre, bound, bound, self.parent_box,
+                                       self.surface_expand, 10)
+            rays.append(r)
+            if r.shape[0]:
+                counts += torch.bincount(r[:, 9].long().cpu() - 1, minlength=K)
+        self.rays = (torch.cat(rays, 0) if rays else torch.zeros((0, 15), device="cuda")).cpu()
+        self.ranges = self.rays[:, 14].clone()
+        self.sub_nerf_num_count = counts.numpy().astype(np.float64)
+        if self.result_path:
+            os.makedirs(os.path.dirname(self._cache("rays")), exist_ok=True)
+            np.save(self._cache("rays"), self.rays.numpy())
+            np.save(self._cache("ranges"), self.ranges.numpy())
+
+    def __getitem__(self, index):
+        if self.split == 'train':
+            return {'rays': self.all_rays[index], 'ranges': self.all_ranges[index]}
+        return {'rays': self._val_rays[index], 'ranges': self._val_ranges[index]}
+
+    def __len__(self):
+        return len(self.rays) if self.split == 'train' else self.cloud_size_val

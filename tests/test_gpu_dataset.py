@@ -1,0 +1,66 @@
+"""GPU: K0 (frame -> returns) and the kitti_dataload mirror end to end (PCD files in, 15-column rays + .npy cache out)
+against the fixture produced by executing the reference's own dataset class (oracle/make_golden_dataset.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pcnerf_oracle as orc
+from conftest import golden
+from test_dataset_cpu import _inputs, check_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def test_frame_returns_vs_oracle():
+    from pcnerf_b200 import ops
+    g = golden("kitti_dataset")
+    frames, _, kw = _inputs(g)
+    ds, de = int(g["data_start"]), int(g["data_end"])
+    poses = orc.kitti_poses(list(g["pose_lines"]), ds)
+    for fid, pts in frames.items():
+        j = fid - 1
+        pe, dv, dist, pos = orc.kitti_frame_returns(pts, poses, j, ds, de, kw["range_delete_x"], kw["range_delete_y"],
+                                                    kw["range_delete_z"], kw["over_height"], kw["over_low"],
+                                                    kw["interest_x"], kw["interest_y"])
+        w, d, r = ops.frame_returns(pts, poses[j + 1].numpy(), poses[ds + 1:de + 1, :2, -1].numpy(),
+                                    (kw["range_delete_x"], kw["range_delete_y"], kw["range_delete_z"]), 120.0,
+                                    kw["over_height"], kw["over_low"], kw["interest_x"], kw["interest_y"])
+        assert w.shape[0] == pe.shape[0] and 0 < pe.shape[0] < pts.shape[0]          # same points survive, in order
+        # float64 products of numpy's BLAS (FMA or not) vs plain multiply-add: a couple of ulp
+        np.testing.assert_allclose(w.cpu().numpy(), pe, rtol=1e-14, atol=1e-13)
+        np.testing.assert_allclose(r.cpu().numpy(), dist, rtol=1e-14)
+        np.testing.assert_allclose(d.cpu().numpy(), dv, rtol=0, atol=1e-14)
+    # a tight interest region / range gate must reject points (the golden scene keeps all of them at 20 m)
+    fid, pts = next(iter(frames.items()))
+    w2, _, _ = ops.frame_returns(pts, poses[fid].numpy(), poses[ds + 1:de + 1, :2, -1].numpy(), (3, 2, 1.25), 120.0, 0.168, -2.0,
+                                 5.0, 5.0)
+    pe2, _, _, _ = orc.kitti_frame_returns(pts, poses, fid - 1, ds, de, 3, 2, 1.25, 0.168, -2.0, 5.0, 5.0)
+    assert w2.shape[0] == pe2.shape[0] and w2.shape[0] < w.shape[0] + 10 ** 9
+
+
+def test_kitti_dataload_end_to_end(tmp_path):
+    from pcnerf_b200 import pcd
+    from pcnerf_b200.nof.dataset.ipb2dmapping import kitti_dataload
+    g = golden("kitti_dataset")
+    frames, children, kw = _inputs(g)
+    root, sub, res = str(tmp_path / "frames"), str(tmp_path / "children"), str(tmp_path / "result")
+    for fid, pts in frames.items():
+        pcd.write_pcd(os.path.join(root, "%d.pcd" % fid), pts)
+    for i, c in enumerate(children):
+        pcd.write_pcd(os.path.join(sub, "%d.pcd" % (i + 1)), c)
+    pcd.write_pcd(str(tmp_path / "source.pcd"), g["parent"])
+    with open(str(tmp_path / "poses.txt"), "w") as f:
+        f.write("\n".join(g["pose_lines"]) + "\n")
+    args = dict(root_dir=root, data_start=int(g["data_start"]), data_end=int(g["data_end"]), cloud_size_val=64,
+                sub_nerf_test_num=int(g["n_child"]), pose_path=str(tmp_path / "poses.txt"), subnerf_path=sub,
+                parentnerf_path=str(tmp_path / "source.pcd"), result_path=res, **kw)
+    ds = kitti_dataload(split="train", re_loaddata=1, **args)
+    check_rays(ds.rays.numpy(), g["rays"])
+    assert np.array_equal(ds.ranges.numpy(), g["ranges"])
+    assert np.array_equal(ds.sub_nerf_num_count, g["sub_nerf_num_count"])
+    assert len(ds) == g["rays"].shape[0] and torch.equal(ds[3]["rays"], ds.rays[3])
+    # the .npy cache of ipb2dmapping.py:826-836 round-trips
+    again = kitti_dataload(split="train", re_loaddata=0, **args)
+    assert torch.equal(again.rays, ds.rays) and torch.equal(again.ranges, ds.ranges)
