@@ -1,5 +1,6 @@
 """Hot-path part of eval_kitti_render.py: the AABB leaf functions (:170-244), the candidate-group builder
-(:353-461 / :681-803), the group-aligned batch driver (:979-1030 / :1111-1161).  PCD / pose file IO is out of scope.
+(:353-461 / :681-803), the group-aligned batch driver (:979-1030 / :1111-1161) and the file-level frame builder
+multi_frame_kitti (:538-881) on pcnerf_b200.pcd (no open3d / pcl).
 """
 import numpy as np
 import torch
@@ -78,3 +79,58 @@ def render_frame(nof_coarse_model, nof_fine_model, embedding_position, dataset_r
         keep = res['rays_effective_flag_fine'].reshape(-1).bool()
         pts.append(res['points_inference_fine'][keep])
     return torch.cat(pts, 0) if pts else torch.zeros((0, 3), device=dataset_rays.device)
+
+
+def multi_frame_kitti(root_dir, split='test', data_start=1439, data_end=1510, range_delete_x=2, range_delete_y=1,
+                      range_delete_z=0.5, sub_nerf_test_num=4, over_height=0.168, over_low=-2, interest_x=12, interest_y=10,
+                      pose_path=None, subnerf_path=None, parentnerf_path=None, view_pcd_number=0, result_path=None,
+                      depth_inference_method=2):
+    """eval_kitti_render.py:538-881 with the reference's signature: candidate rows of frame `view_pcd_number` from the files
+    on disk -- PCD / pose IO by pcnerf_b200.pcd instead of open3d / pcl, the point filters and the pose transform by K0
+    (:641-693; the range gate is `< 120` here, `<= 120` in the training loader), the per-ray group construction by K1
+    (:695-803).  Writes the reference's artefacts under result_path/{one,two}_step/<frame>pcd/childnerf_ray_intersect/
+    (all_rays_child.npy, all_ranges_child.npy, other_interest_sub_nerf_number_child.npy, <frame>_source.pcd,
+    <frame>_pose.pcd) and returns (all_rays (N',13) f32, all_ranges (N',1) f32, other (N',1) i64) on the CPU like it."""
+    import os
+    from . import pcd
+    lo, hi = pcd.axis_aligned_bounds(pcd.read_pcd(parentnerf_path))
+    poses = pcd.read_kitti_poses(pose_path, data_start)
+    bound = np.zeros((sub_nerf_test_num, 6))
+    for i in range(sub_nerf_test_num):                                             # :590-604 (extend_tmp = 0)
+        blo, bhi = pcd.axis_aligned_bounds(pcd.read_pcd(os.path.join(subnerf_path, "%d.pcd" % (i + 1))))
+        bound[i, :3], bound[i, 3:] = blo, bhi
+    j = view_pcd_number - 1
+    if not (data_start <= j < data_end):
+        raise ValueError("view_pcd_number %d is outside [data_start+1, data_end]" % view_pcd_number)
+    pts = pcd.read_pcd(os.path.join(root_dir, "%d.pcd" % view_pcd_number))
+    strict_120 = float(np.nextafter(np.float32(120.0), np.float32(0.0)))           # r < 120  <=>  r <= prev(120) in float32
+    world, dirs, dist = ops.frame_returns(pts, poses[j + 1], poses[data_start + 1:data_end + 1, :2, -1],
+                                          (range_delete_x, range_delete_y, range_delete_z), strict_120, over_height,
+                                          over_low, interest_x, interest_y)
+    origin = poses[j + 1][:3, -1].astype(np.float64)
+    rays, ranges, other, kept = ops.aabb_build_groups(origin, dirs, dist, bound, bound, lo, hi, depth_inference_method,
+                                                      0.05, 0.65)
+    rays, ranges, other = rays.cpu(), ranges.cpu(), other.cpu()
+    if result_path:
+        d = os.path.join(result_path, "two_step" if depth_inference_method == 2 else "one_step",
+                         "%dpcd" % view_pcd_number, "childnerf_ray_intersect")
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, "all_ranges_child.npy"), ranges.numpy())
+        np.save(os.path.join(d, "all_rays_child.npy"), rays.numpy())
+        np.save(os.path.join(d, "other_interest_sub_nerf_number_child.npy"), other.numpy())
+        pcd.write_pcd(os.path.join(d, "%d_source.pcd" % view_pcd_number), world[kept.bool()].cpu().numpy())
+        pcd.write_pcd(os.path.join(d, "%d_pose.pcd" % view_pcd_number), origin.reshape(1, 3))
+    return rays, ranges, other
+
+
+def render_view_to_pcd(nof_coarse_model, nof_fine_model, embedding_position, dataset_rays, dataset_other, out_path,
+                       N_samples, N_importance, chunk, depth_inference_method=2, batch_size_set=18432):
+    """The frame loop of the reference's __main__ (:979-1044): render the candidate rows in group-aligned batches, keep the
+    rows flagged by the fine pass, write the rendered cloud as a binary PCD.  Returns the (M,3) points (device)."""
+    from . import pcd
+    dev = next(nof_coarse_model.parameters()).device
+    pts = render_frame(nof_coarse_model, nof_fine_model, embedding_position, torch.as_tensor(dataset_rays).to(dev),
+                       torch.as_tensor(dataset_other).to(dev), N_samples, N_importance, chunk,
+                       depth_inference_method=depth_inference_method, batch_size_set=batch_size_set)
+    pcd.write_pcd(out_path, pts.cpu().numpy())
+    return pts

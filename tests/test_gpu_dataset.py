@@ -64,3 +64,48 @@ def test_kitti_dataload_end_to_end(tmp_path):
     # the .npy cache of ipb2dmapping.py:826-836 round-trips
     again = kitti_dataload(split="train", re_loaddata=0, **args)
     assert torch.equal(again.rays, ds.rays) and torch.equal(again.ranges, ds.ranges)
+
+
+@pytest.mark.parametrize("method", [2, 1])
+def test_multi_frame_kitti_files_to_candidate_rows(tmp_path, method):
+    """eval_kitti_render.multi_frame_kitti from files on disk: K0 + K1 against the oracle chain (frame filter ->
+    build_candidate_groups, itself pinned against the reference's leaf functions), artefacts written where the reference
+    writes them."""
+    from pcnerf_b200 import eval_kitti_render as ev
+    from pcnerf_b200 import pcd
+    g = golden("kitti_dataset")
+    frames, children, kw = _inputs(g)
+    ds, de = int(g["data_start"]), int(g["data_end"])
+    root, sub, res = str(tmp_path / "frames"), str(tmp_path / "children"), str(tmp_path / "result")
+    for fid, pts in frames.items():
+        pcd.write_pcd(os.path.join(root, "%d.pcd" % fid), pts)
+    for i, c in enumerate(children):
+        pcd.write_pcd(os.path.join(sub, "%d.pcd" % (i + 1)), c)
+    pcd.write_pcd(str(tmp_path / "source.pcd"), g["parent"])
+    with open(str(tmp_path / "poses.txt"), "w") as f:
+        f.write("\n".join(g["pose_lines"]) + "\n")
+    fid = int(g["frame_ids"][0])
+    rays, ranges, other = ev.multi_frame_kitti(root, data_start=ds, data_end=de, range_delete_x=kw["range_delete_x"],
+                                               range_delete_y=kw["range_delete_y"], range_delete_z=kw["range_delete_z"],
+                                               sub_nerf_test_num=len(children), over_height=kw["over_height"],
+                                               over_low=kw["over_low"], interest_x=kw["interest_x"], interest_y=kw["interest_y"],
+                                               pose_path=str(tmp_path / "poses.txt"), subnerf_path=sub,
+                                               parentnerf_path=str(tmp_path / "source.pcd"), view_pcd_number=fid,
+                                               result_path=res, depth_inference_method=method)
+    poses = orc.kitti_poses(list(g["pose_lines"]), ds)
+    pe, dv, dist, pos = orc.kitti_frame_returns(frames[fid], poses, fid - 1, ds, de, kw["range_delete_x"], kw["range_delete_y"],
+                                                kw["range_delete_z"], kw["over_height"], kw["over_low"], kw["interest_x"],
+                                                kw["interest_y"])
+    bound = np.stack([np.concatenate([c.astype(np.float64).min(0), c.astype(np.float64).max(0)]) for c in children])
+    par = g["parent"].astype(np.float64)
+    r_ref, rg_ref, o_ref = orc.build_candidate_groups(pos.numpy().astype(np.float64), dv, dist, bound, bound, par.min(0),
+                                                      par.max(0), method, 0.05)[:3]
+    assert rays.shape == tuple(r_ref.shape) and rays.shape[0] > 0
+    assert np.array_equal(other.numpy().reshape(-1), np.asarray(o_ref).reshape(-1))            # group structure: exact
+    np.testing.assert_allclose(rays.numpy(), np.asarray(r_ref), rtol=3e-7, atol=1e-6)
+    np.testing.assert_allclose(ranges.numpy().reshape(-1), np.asarray(rg_ref).reshape(-1), rtol=3e-7)
+    d = os.path.join(res, "two_step" if method == 2 else "one_step", "%dpcd" % fid, "childnerf_ray_intersect")
+    assert np.array_equal(np.load(os.path.join(d, "all_rays_child.npy")), rays.numpy())
+    assert np.load(os.path.join(d, "other_interest_sub_nerf_number_child.npy")).shape == (rays.shape[0], 1)
+    assert pcd.read_pcd(os.path.join(d, "%d_pose.pcd" % fid)).shape == (1, 3)
+    assert pcd.read_pcd(os.path.join(d, "%d_source.pcd" % fid)).shape[0] > 0
