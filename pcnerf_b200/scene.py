@@ -1,0 +1,75 @@
+"""Large scenes made of several parent NeRF blocks (BASELINE.json configs[4], SURVEY.md 8e "multi-parent scene").
+
+The reference trains and renders ONE parent block per run (one `parentnerf_path`, one checkpoint, one set of child boxes:
+train_kitti.py / eval_kitti_render.py); a large scene is a collection of such blocks (README.md:46).  This module is the
+orchestration around the unchanged single-block path: each LiDAR return is routed to the parent block whose box contains
+it, blocks are sharded over the ranks (every rank owns whole blocks: their networks, child boxes and rays), and a frame
+is rendered block by block with K1 (candidate groups) + `eval_kitti_render.render_frame`.  No per-step communication:
+a block's rays never leave its rank; gathering the rendered points is optional and happens once per frame.
+"""
+import numpy as np
+import torch
+
+from . import ops, parallel
+from .eval_kitti_render import render_frame
+
+
+class ParentBlock:
+    """One parent NeRF: its box, its child boxes and its two occupancy networks (None until loaded on the owning rank)."""
+
+    def __init__(self, parent_min, parent_max, child_bounds, child_bounds_larger=None, nof_coarse=None, nof_fine=None):
+        self.parent_min = np.asarray(parent_min, dtype=np.float64).reshape(3)
+        self.parent_max = np.asarray(parent_max, dtype=np.float64).reshape(3)
+        self.child_bounds = np.asarray(child_bounds, dtype=np.float64).reshape(-1, 6)
+        self.child_bounds_larger = self.child_bounds if child_bounds_larger is None else \
+            np.asarray(child_bounds_larger, dtype=np.float64).reshape(-1, 6)
+        self.nof_coarse, self.nof_fine = nof_coarse, nof_fine
+
+
+def route_points(points, parents):
+    """Index of the first parent block whose closed box contains each point, -1 if none.  points (N,3); host numpy
+    (one pass per frame, N x P comparisons; P is tens of blocks)."""
+    p = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    out = np.full(p.shape[0], -1, dtype=np.int64)
+    for i in range(len(parents) - 1, -1, -1):                  # descending so that the FIRST containing block wins
+        b = parents[i]
+        inside = np.all((p >= b.parent_min) & (p <= b.parent_max), axis=1)
+        out[inside] = i
+    return out
+
+
+def owned_blocks(n_parents, world_size=None, rank_=None):
+    """Parent indices of this rank: contiguous shards of whole blocks (parallel.shard_rows)."""
+    w = parallel.world() if world_size is None else world_size
+    r = parallel.rank() if rank_ is None else rank_
+    a, b = parallel.shard_rows(n_parents, w, r)
+    return list(range(a, b))
+
+
+@torch.no_grad()
+def render_scene_frame(parents, origin, points, embedding_position, N_samples, N_importance, chunk,
+                       depth_inference_method=2, batch_size_set=18432, grow_step=0.05, world_size=None, rank_=None):
+    """Depth inference of one frame over the blocks THIS rank owns.  origin (3,), points (N,3): the frame's returns in
+    the scene frame (they define the ray directions; eval_kitti_render.py:706-709).  Returns {parent index: (M,3) rendered
+    points on the device} -- only owned blocks that received rays appear."""
+    origin = np.asarray(origin, dtype=np.float64).reshape(3)
+    points = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    which = route_points(points, parents)
+    out = {}
+    for i in owned_blocks(len(parents), world_size, rank_):
+        sel = np.nonzero(which == i)[0]
+        if sel.size == 0:
+            continue
+        b = parents[i]
+        if b.nof_coarse is None or b.nof_fine is None:
+            raise RuntimeError("parent block %d is owned by this rank but its networks are not loaded" % i)
+        vec = points[sel] - origin
+        dist = np.linalg.norm(vec, axis=1)
+        dirs = vec / dist[:, None]
+        rays, _, other, _ = ops.aabb_build_groups(origin, dirs, dist, b.child_bounds, b.child_bounds_larger, b.parent_min,
+                                                  b.parent_max, depth_inference_method, grow_step, 0.65)
+        if rays.shape[0] == 0:
+            continue
+        out[i] = render_frame(b.nof_coarse, b.nof_fine, embedding_position, rays, other, N_samples, N_importance, chunk,
+                              depth_inference_method=depth_inference_method, batch_size_set=batch_size_set)
+    return out

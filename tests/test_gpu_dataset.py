@@ -109,3 +109,30 @@ def test_multi_frame_kitti_files_to_candidate_rows(tmp_path, method):
     assert np.load(os.path.join(d, "other_interest_sub_nerf_number_child.npy")).shape == (rays.shape[0], 1)
     assert pcd.read_pcd(os.path.join(d, "%d_pose.pcd" % fid)).shape == (1, 3)
     assert pcd.read_pcd(os.path.join(d, "%d_source.pcd" % fid)).shape[0] > 0
+
+
+def test_render_scene_frame_blocks_partition_the_work():
+    """Multi-parent scene (BASELINE configs[4]): two parent blocks with their own child boxes and networks.  Rendering with
+    world_size 2 (each simulated rank owns one block) yields exactly the blocks' single-rank results: a block's rays never
+    leave its owner, nothing is rendered twice."""
+    from gpu_util import make_nets
+    from pcnerf_b200 import scene, synth
+    blocks = []
+    pts_all = []
+    for i in range(2):
+        parent = (-20.0 + 45 * i, 20.0 + 45 * i, -20.0, 20.0, -1.7, 0.5)
+        sc = synth.make_scene(300 + i, 24, parent)
+        mc, mf, emb = make_nets(42 + 2 * i, 43 + 2 * i, False, None)
+        blocks.append(scene.ParentBlock(sc.parent_min, sc.parent_max, sc.child_bounds,
+                                        sc.child_bounds + np.array([-0.025] * 3 + [0.025] * 3), mc, mf))
+        pts_all.append(synth.make_points(sc, 17 + i, 300))
+    origin = np.array([22.0, 0.0, -0.5])                      # between the two blocks
+    pts = np.concatenate(pts_all)
+    which = scene.route_points(pts, blocks)
+    assert (which[:300] == 0).all() and (which[300:] == 1).all()
+    full = scene.render_scene_frame(blocks, origin, pts, emb, 32, 64, 8192, world_size=1, rank_=0)
+    assert sorted(full) == [0, 1] and all(v.shape[0] > 0 and v.shape[1] == 3 for v in full.values())
+    for r in range(2):
+        part = scene.render_scene_frame(blocks, origin, pts, emb, 32, 64, 8192, world_size=2, rank_=r)
+        assert list(part) == [r]
+        assert torch.equal(part[r], full[r])

@@ -43,3 +43,17 @@ def test_mirror_signatures_match_reference_names():
     d = {k: v.default for k, v in inspect.signature(render.render_rays_train).parameters.items()}
     assert (d["N_samples"], d["N_importance"], d["chunk"], d["noise_std"], d["childnerf_ratio"]) == (64, 128, 1024 * 3, 1, 0.5)
     assert render.__all__ == ["render_rays"]
+
+
+def test_scene_routing_and_block_sharding():
+    """Multi-parent scenes (BASELINE configs[4]): returns go to the first parent box that contains them, whole blocks are
+    sharded contiguously over the ranks, every block is owned exactly once."""
+    import numpy as np
+    from pcnerf_b200 import scene
+    blocks = [scene.ParentBlock([10 * i, 0, -2], [10 * i + 10, 10, 1], np.zeros((0, 6))) for i in range(5)]
+    pts = np.array([[5.0, 5, 0], [10.0, 5, 0], [49.9, 9.9, 0.9], [50.1, 5, 0], [25, -1, 0], [25, 5, 0]])
+    assert scene.route_points(pts, blocks).tolist() == [0, 0, 4, -1, -1, 2]        # a shared face goes to the first block
+    owned = [scene.owned_blocks(5, 3, r) for r in range(3)]
+    assert owned == [[0, 1], [2, 3], [4]]
+    assert sorted(sum([scene.owned_blocks(64, 8, r) for r in range(8)], [])) == list(range(64))
+    assert all(len(scene.owned_blocks(64, 8, r)) == 8 for r in range(8))
