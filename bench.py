@@ -346,6 +346,8 @@ def run_b200(a):
     roofline, kernels = None, None
     if not a.no_profile:
         barrier()
+        lanes = ops.TC_LANES
+        ops.TC_LANES = 1              # one chunk at a time: event intervals of concurrent kernels would overlap
         ops.profile(True)
         psteps = min(a.steps, 2)
         for _ in range(psteps):
@@ -353,6 +355,7 @@ def run_b200(a):
         torch.cuda.synchronize()
         prof = ops.profile_read()
         ops.profile(False)
+        ops.TC_LANES = lanes
         kernels = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps} for k, v in prof.items() if v[1]}
         gemm = [prof[k] for k in ("mlp_gemm_fwd", "mlp_gemm_dgrad", "mlp_gemm_wgrad")]
         g_ms, g_fl = sum(g[0] for g in gemm), sum(g[2] for g in gemm)
@@ -405,6 +408,7 @@ def run_b200(a):
            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16 fwd / bf16 bwd operands, f32 accumulate", "affine": "f32 data kernels, f64 closed-form algebra"}[a.precision], "data": "synthetic",
            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "N_samples": S, "N_importance": NI, "chunk": CHUNK,
                       "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam(fused)", "cuda_graph": graph_note,
+                      "mlp_chunks_in_flight": ops.TC_LANES if a.precision == "tc" else 1,
                       "parallelism": "dp%d (rays sharded, one flat NCCL all-reduce of 3.98 MB grads)" % world,
                       "l2": "per-step working set (>2 GB encodings, >30 GB activations) exceeds the 126 MB L2"},
            "clocks": clk,

@@ -1238,6 +1238,28 @@ static int g_fused_eval = 2;     // 0 = layered, 1 = fused (one CTA per unit), 2
 extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on < 0 ? 0 : (on > 2 ? 2 : on); }
 extern "C" int pcnerf_tc_get_fused_eval(void) { return g_fused_eval; }
 
+// ---- two BN batches (chunks) in flight: pcnerf_mlp_tc_{forward,backward}_chunks issue consecutive chunks on two internal
+// streams ("lanes").  The kernels of a chunk form a serial chain (GEMM -> fold -> GEMM ...) whose fixed costs -- prologue,
+// pipeline fill, last-tile drain, statistics reduction, the small kernels and the launch gaps between them, ~10 us of a
+// 62 us forward GEMM at 262,144 rows -- are dead time for the whole GPU; with a second, independent chain the CTAs of the
+// other chunk's GEMM take over every SM the moment it is released.  What the chains share is ordered explicitly: the
+// running-statistics update of BN(l) (forward, k_bn_fold) and the += into the parameter gradients (backward,
+// k_out_bwd_finalize / k_tc_wgrad_finish) of chunk c+1 wait for the same kernel of chunk c, so every sum and every
+// momentum update happens in the sequential order (results are bit-identical to one lane).
+struct ChainSync {
+    cudaEvent_t wait[9];         // recorded by the previous chunk (other lane) after its kernel of this slot; may be null
+    cudaEvent_t rec[9];          // recorded by this chunk after its kernel of this slot
+};
+static thread_local const ChainSync* g_chain = nullptr;
+static int chain_before(int slot, cudaStream_t st) {
+    if (g_chain && g_chain->wait[slot]) PCN_CUDA(cudaStreamWaitEvent(st, g_chain->wait[slot], 0));
+    return 0;
+}
+static int chain_after(int slot, cudaStream_t st) {
+    if (g_chain && g_chain->rec[slot]) PCN_CUDA(cudaEventRecord(g_chain->rec[slot], st));
+    return 0;
+}
+
 // fp32 padded weight copies (same kernel as the fp32 path; defined in mlp_small.cuh)
 static void tc_prep_weights(const pcnerf_mlp_params* P, const MlpLayout& L, char* scratch, cudaStream_t st) {
     PrepArgs pa;
@@ -1342,12 +1364,14 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
         if (rc) return rc;
         const bool last = l == 7;
         if (!P->training && P->prepared) continue;       // folded copies of the first chunk are still in `scratch`
+        if (int rc2 = chain_before(l, st)) return rc2;   // (running statistics: after the previous chunk's update)
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_bn_fold<<<last ? 1 : 256, 256, 0, st>>>(
                       l, P->training, rows, s0, s0 + 256, P->gamma[l], P->beta[l], P->running_mean[l], P->running_var[l],
                       P->num_batches_tracked[l], P->momentum, P->eps, L.stats(sv, l), last ? P->W[8] : L.Wp(scratch, l + 1),
                       last ? P->b[8] : P->b[l + 1], last ? L.wout_f(scratch) : L.Wf(scratch, l + 1),
                       last ? L.wout_f(scratch) + 256 : L.bf(scratch, l + 1), last ? nullptr : tc_Wh(L, scratch, l + 1)));
+        if (int rc2 = chain_after(l, st)) return rc2;
     }
     int64_t blocks = pcn_cdiv(rows, 8);
     if (blocks > PCN_SM_COUNT * 16) blocks = PCN_SM_COUNT * 16;
@@ -1380,9 +1404,11 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     const int strips = (int)(pcn_cdiv(rows, STRIP) < 4 * PCN_SM_COUNT ? pcn_cdiv(rows, STRIP) : 4 * PCN_SM_COUNT);
     const __half* H7 = (const __half*)L.Hraw(sv, 7);
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_out_bwd_reduce<__half><<<strips, 256, 0, st>>>(grad_p, out_p, H7, rows, gvec, acc_out));
+    if (int rc2 = chain_before(8, st)) return rc2;       // (+= into the parameter gradients: after the previous chunk's)
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
               k_out_bwd_finalize<<<1, 256, 0, st>>>(acc_out, rows, P->W[8], L.stats(sv, 7), G->dW[8], G->db[8], G->dgamma[7],
                                                     G->dbeta[7], coef));
+    if (int rc2 = chain_after(8, st)) return rc2;
     int cur = 0;
     PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
               k_bn_bwd_apply<true, __half, __nv_bfloat16><<<strips, 256, 0, st>>>(gvec, Gb[cur], H7, rows, coef, L.stats(sv, 7),
@@ -1403,11 +1429,13 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
         if (rc) return rc;
         if (l != 0) rc = launch_wgrad(DH, Hprev, 256, 256, 0, rows, part, kpad, off, st);
         if (rc) return rc;
+        if (int rc2 = chain_before(l, st)) return rc2;
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0,
                   k_tc_wgrad_finish<<<kpad, 256, 0, st>>>(l, part, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
                                                           L.Wp(scratch, l), rows, G->dW[l], G->db[l],
                                                           l == 0 ? nullptr : G->dgamma[l - 1], l == 0 ? nullptr : G->dbeta[l - 1],
                                                           coef));
+        if (int rc2 = chain_after(l, st)) return rc2;
         if (l == 0) break;
         rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
                             nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), 1, st);
@@ -1416,6 +1444,82 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     }
     PCN_LAUNCH_CHECK();
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// All chunks of a pass, two in flight (see ChainSync)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct Lanes {
+    cudaStream_t stream[2];
+    cudaEvent_t fork, join[2], slot[2][9];
+    bool ok = false;
+};
+int lanes_get(Lanes** out) {
+    static Lanes L;
+    if (!L.ok) {
+        for (int k = 0; k < 2; ++k) {
+            PCN_CUDA(cudaStreamCreateWithFlags(&L.stream[k], cudaStreamNonBlocking));
+            PCN_CUDA(cudaEventCreateWithFlags(&L.join[k], cudaEventDisableTiming));
+            for (int i = 0; i < 9; ++i) PCN_CUDA(cudaEventCreateWithFlags(&L.slot[k][i], cudaEventDisableTiming));
+        }
+        PCN_CUDA(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+        L.ok = true;
+    }
+    *out = &L;
+    return 0;
+}
+}  // namespace
+
+static int tc_chunks(bool backward, const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const void* enc, int64_t rows,
+                     int64_t chunk, float* out_p, const float* grad_p, void* const* saved, void* const* scratch, int lanes,
+                     cudaStream_t st) {
+    PCN_CHECK_ARG(P && P->precision == 1 && enc && out_p && saved && scratch && rows >= 1 && chunk >= 1 && (lanes == 1 || lanes == 2),
+                  "mlp_tc_chunks: bad arguments (precision 1, lanes 1 or 2)");
+    Lanes* L = nullptr;
+    if (lanes == 2) {
+        if (int rc = lanes_get(&L)) return rc;
+        PCN_CUDA(cudaEventRecord(L->fork, st));
+        for (int k = 0; k < 2; ++k) PCN_CUDA(cudaStreamWaitEvent(L->stream[k], L->fork, 0));
+    }
+    const int64_t nchunks = pcn_cdiv(rows, chunk);
+    int rc = 0;
+    for (int64_t c = 0; c < nchunks && !rc; ++c) {
+        const int k = lanes == 2 ? (int)(c & 1) : 0;
+        const int64_t r0 = c * chunk, r = rows - r0 < chunk ? rows - r0 : chunk;
+        pcnerf_mlp_params Pc = *P;
+        Pc.prepared = c >= lanes ? 1 : P->prepared;      // every lane derives its weight copies on its first chunk
+        ChainSync cs;
+        for (int i = 0; i < 9; ++i) {
+            cs.rec[i] = lanes == 2 ? L->slot[k][i] : nullptr;
+            cs.wait[i] = (lanes == 2 && c > 0) ? L->slot[k ^ 1][i] : nullptr;
+        }
+        cudaStream_t s = lanes == 2 ? L->stream[k] : st;
+        const void* e = (const char*)enc + (size_t)r0 * 64 * 2;
+        g_chain = lanes == 2 ? &cs : nullptr;
+        rc = backward ? mlp_tc_backward(&Pc, G, e, r, out_p + r0, grad_p + r0, saved[c], 0, scratch[k], 0, s)
+                      : mlp_tc_forward(&Pc, e, r, out_p + r0, saved[c], 0, scratch[k], 0, s);
+        g_chain = nullptr;
+    }
+    if (lanes == 2)
+        for (int k = 0; k < 2; ++k) {                     // join even after an error: never leave a capture forked
+            cudaEventRecord(L->join[k], L->stream[k]);
+            cudaStreamWaitEvent(st, L->join[k], 0);
+        }
+    return rc;
+}
+
+extern "C" int pcnerf_mlp_tc_forward_chunks(const pcnerf_mlp_params* P, const void* enc, int64_t rows, int64_t chunk,
+                                            float* out_p, void* const* saved, void* const* scratch, int lanes, void* stream) {
+    PCN_CHECK_ARG(P && P->training, "mlp_tc_forward_chunks: training mode only (eval mode has no per-chunk state)");
+    return tc_chunks(false, P, nullptr, enc, rows, chunk, out_p, nullptr, saved, scratch, lanes, (cudaStream_t)stream);
+}
+
+extern "C" int pcnerf_mlp_tc_backward_chunks(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const void* enc,
+                                             int64_t rows, int64_t chunk, const float* out_p, const float* grad_p,
+                                             void* const* saved, void* const* scratch, int lanes, void* stream) {
+    PCN_CHECK_ARG(G && grad_p, "mlp_tc_backward_chunks: null argument");
+    return tc_chunks(true, P, G, enc, rows, chunk, const_cast<float*>(out_p), grad_p, saved, scratch, lanes, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

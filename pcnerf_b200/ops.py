@@ -295,9 +295,12 @@ _SCRATCH = {}
 EVAL_CHUNK_FLOOR = 1 << 20        # rows per launch of the eval-mode tensor-core MLP (tests lower it to cover chunking)
 
 
-def _scratch(rows, precision, device):
+TC_LANES = int(__import__('os').environ.get('PCNERF_TC_LANES', '2'))   # BN chunks in flight in the training-mode tensor-core MLP
+
+
+def _scratch(rows, precision, device, lane=0):
     need = lib().pcnerf_mlp_scratch_bytes(rows, precision)
-    key = (str(device), precision)
+    key = (str(device), precision, lane)
     buf = _SCRATCH.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty(need, dtype=torch.uint8, device=device)
@@ -347,6 +350,21 @@ class MLPFunction(torch.autograd.Function):
             # does not change any value, and the row GEMMs run closer to their steady-state rate on >= 1 M-row launches
             chunk = max(int(chunk), EVAL_CHUNK_FLOOR)
         saved = []
+        if need_grad and precision == 1:
+            # training pass of the tensor-core engine: the library walks the chunks itself, TC_LANES of them in flight
+            nch = -(-rows // chunk)
+            saved = [torch.empty(lib().pcnerf_mlp_saved_bytes(min(chunk, rows - c * chunk), 1), dtype=torch.uint8, device=dev)
+                     for c in range(nch)]
+            lanes = TC_LANES if nch > 1 else 1
+            scr = [_scratch(min(chunk, rows), 1, dev, k) for k in range(lanes)]
+            sv_arr = (ctypes.c_void_p * nch)(*[t.data_ptr() for t in saved])
+            sc_arr = (ctypes.c_void_p * lanes)(*[t.data_ptr() for t in scr])
+            check(lib().pcnerf_mlp_tc_forward_chunks(ctypes.byref(P), _p(enc), rows, chunk, _p(out), sv_arr, sc_arr, lanes,
+                                                     _stream()))
+            ctx.saved_chunks = saved
+            ctx.meta = (chunk, precision, buffers, rows)
+            ctx.save_for_backward(enc, out, *params)
+            return out
         scratch = _scratch(min(chunk, rows), precision, dev)
         shared = None
         esz = 2 if precision == 1 else 4
@@ -391,6 +409,16 @@ class MLPFunction(torch.autograd.Function):
         for l in range(8):
             G.dgamma[l] = views[18 + 2 * l].data_ptr()
             G.dbeta[l] = views[19 + 2 * l].data_ptr()
+        if precision == 1:
+            nch = len(ctx.saved_chunks)
+            lanes = TC_LANES if nch > 1 else 1
+            scr = [_scratch(min(chunk, rows), 1, dev, k) for k in range(lanes)]
+            sv_arr = (ctypes.c_void_p * nch)(*[t.data_ptr() for t in ctx.saved_chunks])
+            sc_arr = (ctypes.c_void_p * lanes)(*[t.data_ptr() for t in scr])
+            check(lib().pcnerf_mlp_tc_backward_chunks(ctypes.byref(P), ctypes.byref(G), _p(enc), rows, chunk, _p(out), _p(gp),
+                                                      sv_arr, sc_arr, lanes, _stream()))
+            ctx.saved_chunks = None
+            return (None, None, None, None, None) + tuple(views)
         scratch = _scratch(min(chunk, rows), precision, dev)
         esz = 2 if precision == 1 else 4
         for ci_, i in enumerate(range(0, rows, chunk)):
