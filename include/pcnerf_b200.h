@@ -151,7 +151,9 @@ typedef struct pcnerf_mlp_params {
                                            bf16 gradients, fp32 accumulation (1e-3 gate) */
     int prepared;                       /* 1: `scratch` still holds the padded / transposed weight copies written by the
                                            previous call with these same weights (next chunk of the same pass): skip
-                                           re-deriving them.  0 is always safe. */
+                                           re-deriving them.  0 is always safe.  2 (eval mode, precision 1 only): the
+                                           copies in `scratch` are valid but this is the first chunk of a new call (the
+                                           per-call constants of the fused eval kernel are re-loaded). */
 } pcnerf_mlp_params;
 
 typedef struct pcnerf_mlp_grads {       /* accumulated (+=) by pcnerf_mlp_backward */

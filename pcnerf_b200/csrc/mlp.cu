@@ -226,7 +226,9 @@ extern "C" int pcnerf_mlp_forward(const pcnerf_mlp_params* P, const void* enc, i
     // (the fused eval kernel of precision 1 keeps every activation on chip and saves nothing)
     const bool no_saved = P->precision == 1 && !P->training && pcnerf_tc_get_fused_eval();
     PCN_CHECK_ARG(no_saved || (saved && saved_bytes >= L.saved_bytes), "mlp_forward: saved buffer too small (%zu < %zu)", saved_bytes, L.saved_bytes);
-    PCN_CHECK_ARG(scratch_v && scratch_bytes >= L.scratch_bytes, "mlp_forward: scratch too small (%zu < %zu)", scratch_bytes, L.scratch_bytes);
+    // (... and uses only the rows-independent head of the scratch layout: weight copies, folded biases)
+    const size_t need_scratch = no_saved ? MlpLayout(1, 1).scratch_bytes : L.scratch_bytes;
+    PCN_CHECK_ARG(scratch_v && scratch_bytes >= need_scratch, "mlp_forward: scratch too small (%zu < %zu)", scratch_bytes, need_scratch);
     if (P->precision == 1) return mlp_tc_forward(P, enc, rows, out_p, saved, saved_bytes, scratch_v, scratch_bytes, st);
     PCN_CHECK_ARG(P->precision == 0, "mlp_forward: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
     char* scratch = (char*)scratch_v;

@@ -1279,8 +1279,6 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
     char* scratch = (char*)scratch_v;
     char* sv = (char*)saved;
     const __half* ench = (const __half*)enc;
-    PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
-    PCN_CUDA(cudaMemsetAsync(L.rgwork(scratch), 0, 4, st));
     if (!P->prepared) {
         tc_prep_weights(P, L, scratch, st);
         PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_prep_fwd<<<64, 256, 0, st>>>(L.Wp(scratch, 0), tc_Wh(L, scratch, 0)));
@@ -1312,7 +1310,7 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
             rc = make_map(&wm.w[l], tc_Wh(L, scratch, l), 256, mlp_kpad(l), mlp_kpad(l), 128);
             if (rc) return rc;
         }
-        if (!P->prepared) {
+        if (P->prepared != 1) {                           // 0 or 2: first chunk of a call (another model may have run since)
             PCN_CUDA(cudaMemcpyToSymbolAsync(c_fz, P->b[0], 256 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
             PCN_CUDA(cudaMemcpyToSymbolAsync(c_fz, L.bf(scratch, 1), 7 * 256 * sizeof(float), 256 * sizeof(float),
                                              cudaMemcpyDeviceToDevice, st));
@@ -1351,6 +1349,8 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
         PCN_LAUNCH_CHECK();
         return 0;
     }
+    PCN_CUDA(cudaMemsetAsync(L.dstat(scratch, 0), 0, sizeof(double) * 8 * 512, st));
+    PCN_CUDA(cudaMemsetAsync(L.rgwork(scratch), 0, 4, st));
     for (int l = 0; l < 8; ++l) {
         __half* Hout = (__half*)L.Hraw(sv, l);
         const __half* Hin = l > 0 ? (const __half*)L.Hraw(sv, l - 1) : nullptr;

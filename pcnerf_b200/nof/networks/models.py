@@ -186,7 +186,10 @@ class NOF(nn.Module):
         chunk = rows if chunk is None else int(chunk)
         if prec == 2:
             return self._forward_affine(enc.contiguous(), max(chunk, 1))
+        if not hasattr(self, "_eval_fold_cache"):
+            object.__setattr__(self, "_eval_fold_cache", {})       # folded eval-mode weights (ops.MLPFunction), not module state
         return ops.MLPFunction.apply(enc.contiguous(), max(chunk, 1), self.training, prec, self._buffers3(),
+                                     self._eval_fold_cache,
                                      *self.kernel_params())
 
     def forward(self, x):

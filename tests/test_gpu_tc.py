@@ -235,3 +235,34 @@ def test_two_chunks_in_flight_is_bit_identical():
         if k.endswith(".bias") and k.split(".")[0] in ("layer1", "layer2") and k != "layer2.7.bias":
             continue                                       # exactly zero in exact arithmetic: rounding noise either way
         assert float((a - b).abs().max()) <= 1e-2 * float(a.abs().max()) + 1e-12, k
+
+
+def test_eval_fold_cache_follows_parameter_updates():
+    """The folded eval-mode weights are cached per model and re-derived only when a parameter or a running statistic was
+    written to: two models alternating (coarse / fine) must not see each other's weights or epilogue constants, and an
+    in-place parameter update must invalidate the cache."""
+    rows = 2000
+    enc = torch.nn.functional.pad(_enc(rows, 5), (0, 1)).to(dev())
+    ma, mb, _ = make_nets(42, 43, False, "tc")
+
+    def ref(m):
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        return orc.nof_forward(sd, enc.cpu()[:, :63].float(), False).reshape(-1)
+
+    def close(p, r):
+        err = (p.cpu() - r).abs() / r
+        return float(err.max()) < 6e-3 and float(err.mean()) < 1e-3
+
+    with torch.no_grad():
+        pa1 = mb.forward_encoded(enc, rows) * 0 + ma.forward_encoded(enc, rows)      # b then a: a must not inherit b's constants
+        pb1 = mb.forward_encoded(enc, rows)
+        pa2 = ma.forward_encoded(enc, rows)                                          # cached path (prepared = 2)
+        assert torch.equal(pa1, pa2) and close(pa1, ref(ma)) and close(pb1, ref(mb))
+        assert not torch.equal(pa1, pb1)
+        ma.occ_out[0].bias.add_(0.5)                                                 # in-place update -> new version
+        ma.layer1[0].weight.mul_(1.1)
+        pa3 = ma.forward_encoded(enc, rows)
+        assert not torch.equal(pa3, pa2) and close(pa3, ref(ma))
+        ma.layer1[1].running_mean.add_(0.05)                                         # running statistics count too
+        pa4 = ma.forward_encoded(enc, rows)
+        assert not torch.equal(pa4, pa3) and close(pa4, ref(ma))
