@@ -219,3 +219,31 @@ def test_fused_sample_encode_rows_vs_oracle(S, n):
     ulp = np.maximum(np.abs(ref), 2.0 ** -14) * 2.0 ** -10
     assert np.all(np.abs(got16[:, :63] - ref16) <= ulp + 1.5e-6)
     assert np.mean(got16[:, 3:63] != ref16[:, 3:]) < 0.05          # and such flips are rare (near-zero values)
+
+
+def test_fused_encode_extreme_coordinates():
+    """K2 range reduction outside its fast range: |x| >= 8e6, NaN and +-Inf take the plain sincosf path (what torch
+    computes: accurate sin/cos of the fp32 product, NaN for non-finite arguments); coordinates just below the switch still
+    use the integer reduction and must stay within the fp32 gate."""
+    from pcnerf_b200 import ops
+    vals = [7.9e6, -7.9e6, 8.1e6, -3.0e7, 1.0e12, 0.0, -0.0, 1e-30, float("nan"), float("inf"), -float("inf"), 123456.789]
+    n = len(vals)
+    rays = torch.zeros(n, 15)
+    rays[:, 0] = torch.tensor(vals)                        # origin x carries the value; direction (0, 1, 0), z in [1, 2]
+    rays[:, 4] = 1.0
+    rays[:, 6], rays[:, 7] = 1.0, 2.0
+    z, enc = ops.sample_encode_coarse(rays.to(dev()), 4, 0, 6, 7, 10, 11, False, 0.0, None, want_enc=True)
+    zc = z.cpu()
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * zc[:, :, None]).reshape(-1, 3)
+    ref = orc.embedding(pts).numpy()
+    got = enc.cpu().numpy()[:, :63]
+    finite = np.isfinite(ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(got[finite], ref[finite], rtol=0, atol=4e-7)
+    _, enc16 = ops.sample_encode_coarse(rays.to(dev()), 4, 0, 6, 7, 10, 11, False, 0.0, None, want_enc=True, f16=True)
+    got16 = enc16.float().cpu().numpy()[:, :63]
+    ref16 = torch.from_numpy(ref).half().float().numpy()
+    ok = np.isfinite(ref16)
+    assert np.array_equal(np.isnan(got16), np.isnan(ref16))
+    ulp = np.maximum(np.abs(ref[ok]), 2.0 ** -14) * 2.0 ** -10
+    assert np.all(np.abs(got16[ok] - ref16[ok]) <= ulp + 1.5e-6)
