@@ -2,9 +2,9 @@
 //
 // Mapping: one warp per ray.  The ray's depths live in shared memory; z placement uses explicit
 // round-to-nearest mul/add (no FMA contraction) in the reference's operation order so that every later
-// mask decision sees bit-identical z.  The encoding of one sample is produced by 30 lanes (one sincosf each, accurate
-// range reduction: arguments reach 512*60 rad), staged in shared memory and written as one coalesced row
-// (256 B fp32 / 128 B fp16) -- the fp32 (rows,64) layout is the MLP's A operand, column 63 is zero padding.
+// mask decision sees bit-identical z.  The encoding is produced 32 samples at a time, one sample per lane (see
+// encode_ray_t), and written as coalesced 512-byte runs -- the (rows,64) layout (256 B fp32 / 128 B fp16 per row) is the
+// MLP's A operand, column 63 is zero padding.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
