@@ -8,8 +8,12 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_` (host, read during the call);
  *   - tensors are dense row-major; `ld` parameters are row strides in elements;
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the device,
- *     allocates device memory or keeps global mutable state;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the device or
+ *     allocates device memory.  Process-wide state is limited to: the instrumentation counters, the eval-engine switch
+ *     (pcnerf_tc_set_fused_eval), the constant bank holding the epilogue constants of the fused eval MLP (re-loaded at the
+ *     first chunk of every call) and the two internal streams of pcnerf_mlp_tc_*_chunks (forked from / joined to
+ *     `stream`).  The reference drives the path from one host thread (the Lightning main loop); the precision-1 MLP entry
+ *     points assume the same: one host thread, one stream at a time per process.  Everything else is re-entrant per stream;
  *   - return value: 0 on success, negative on error; pcnerf_last_error() gives the message (thread local).
  *   - fp32 "renderer" arithmetic follows the reference's operation order where masks/indices depend on it
  *     (no FMA contraction in z placement and thresholds); the AABB stage is fp64 like the reference's numpy.
