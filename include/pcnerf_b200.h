@@ -306,6 +306,16 @@ int pcnerf_frame_returns(const float* pts, int64_t n, const double* h_pose16, co
                          float rdy, float rdz, float max_range, float over_height, float over_low, float interest_x,
                          float interest_y, uint8_t* keep, double* world, double* dir, double* dist, void* stream);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * Optimizer step on one flat buffer: torch.optim.Adam as configured by nof/nof_utils.py:162-173
+ * (amsgrad off, L2 weight decay) over n contiguous fp32 parameters, their gradients (the buffer the gradient all-reduce
+ * runs on; grad_scale = 1/world folds the averaging in) and the two moment vectors.  step (int64), lr (float) and coef2
+ * (2 floats of scratch) live on the device: the call is replayable from a CUDA graph.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pcnerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step,
+                     const float* lr, float* coef2, float beta1, float beta2, float eps, float weight_decay,
+                     float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ SOURCES = {
     "affine.cu": [],
     "metrics.cu": ["-fmad=false"],
     "frame.cu": ["-fmad=false"],
+    "optim.cu": [],
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
           "-Xcompiler", "-fPIC"]

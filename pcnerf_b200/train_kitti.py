@@ -19,6 +19,9 @@ def get_optimizer(hparams, parameters):
         return SGD(parameters, lr=hparams.lr, momentum=hparams.momentum, weight_decay=hparams.weight_decay)
     if hparams.optimizer == 'adam':
         return Adam(parameters, lr=hparams.lr, eps=eps, weight_decay=hparams.weight_decay)
+    if hparams.optimizer == 'flat_adam':            # same update, one kernel over one flat buffer (pcnerf_b200.optim)
+        from .optim import FlatAdam
+        return FlatAdam(parameters, lr=hparams.lr, eps=eps, weight_decay=hparams.weight_decay)
     raise ValueError('optimizer not recognized!')
 
 
