@@ -218,9 +218,11 @@ def run_b200(a):
     mc.precision = mf.precision = a.precision
     emb = Embedding(3, 10)
     params = list(mc.parameters()) + list(mf.parameters())
-    bucket = parallel.GradBucket(params)
     use_graph = a.graph != "off"
-    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, weight_decay=1e-3, fused=True, capturable=use_graph)
+    # torch.optim.Adam as the reference configures it, on one flat buffer: one kernel per step, 1/world folded in
+    from pcnerf_b200.optim import FlatAdam
+    opt = FlatAdam(params, lr=5e-4, eps=1e-8, weight_decay=1e-3)
+    bucket = opt.bucket
     sl1 = torch.nn.SmoothL1Loss(reduction="mean")
     dscale = parallel.depth_loss_scale()
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -243,8 +245,7 @@ def run_b200(a):
     def finish():
         """Gradient all-reduce (N > 1) + Adam.  Kept OUT of the captured graph when N > 1: NCCL collectives replayed from a
         CUDA graph hung the process at teardown on this stack (profiles/README.md), and the step has exactly one."""
-        bucket.allreduce_mean()
-        opt.step()
+        opt.step()                                   # (all-reduce of the flat gradients when N > 1, then the update)
 
     def step(from_host):
         """One eager step (every kernel launched from the host)."""
@@ -407,7 +408,7 @@ def run_b200(a):
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16 fwd / bf16 bwd operands, f32 accumulate", "affine": "f32 data kernels, f64 closed-form algebra"}[a.precision], "data": "synthetic",
            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "N_samples": S, "N_importance": NI, "chunk": CHUNK,
-                      "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam(fused)", "cuda_graph": graph_note,
+                      "child_aabbs": K_BOXES, "precision": a.precision, "optimizer": "Adam on one flat buffer (pcnerf_b200.optim.FlatAdam)", "cuda_graph": graph_note,
                       "mlp_chunks_in_flight": ops.TC_LANES if a.precision == "tc" else 1,
                       "parallelism": "dp%d (rays sharded, one flat NCCL all-reduce of 3.98 MB grads)" % world,
                       "l2": "per-step working set (>2 GB encodings, >30 GB activations) exceeds the 126 MB L2"},
