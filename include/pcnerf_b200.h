@@ -298,13 +298,17 @@ int pcnerf_dist_stats(const double* dist, int64_t n, double threshold, double* s
  * K0  LiDAR frame -> returns of the block.  Replaces the numpy / python filtering of
  * nof/dataset/ipb2dmapping.py:662-711: near-sensor box |x|>=rdx or |y|>=rdy or |z|>=rdz, range <= max_range, height window
  * (float32, sensor frame), pose transform in float64 (h_pose16: HOST 4x4 row-major, float32 values), interest region
- * around any of the `npose` run poses (pose_xy (npose,2) float32, device), ray direction / range from pose[:3,3].
+ * around any of the `npose` run poses (pose_xy (npose,2) float32, device; npose = 0: no such test), optional closed
+ * parent-box test on the transformed points (h_box6: HOST x_min,x_max,y_min,y_max,z_min,z_max or NULL; the MaiCity loader,
+ * :334-336, which passes +-inf for the height window), ray direction / range from the sensor position h_pos3 (HOST,
+ * NULL = pose[:3,3]; the MaiCity loader transforms with the float32 pose but measures from the float64 position).
  * pts (n,3) float32.  Outputs for EVERY point (the caller compacts in order with `keep`): keep (n) uint8, world (n,3),
  * dir (n,3), dist (n) float64.  The outputs feed pcnerf_aabb_pack_train unchanged.
  * ------------------------------------------------------------------------------------------------------------- */
 int pcnerf_frame_returns(const float* pts, int64_t n, const double* h_pose16, const float* pose_xy, int npose, float rdx,
                          float rdy, float rdz, float max_range, float over_height, float over_low, float interest_x,
-                         float interest_y, uint8_t* keep, double* world, double* dir, double* dist, void* stream);
+                         float interest_y, const double* h_box6, const double* h_pos3, uint8_t* keep, double* world,
+                         double* dir, double* dist, void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
  * Optimizer step on one flat buffer: torch.optim.Adam as configured by nof/nof_utils.py:162-173

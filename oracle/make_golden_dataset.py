@@ -145,5 +145,62 @@ def main():
         print("wrote", OUT, "rays", rays.shape, "frame points", [v.shape for v in frames.values()], "bytes", os.path.getsize(OUT))
 
 
+OUT_M = os.path.join(os.path.dirname(HERE), "tests", "golden", "maicity_dataset.npz")
+M_START, M_END, M_FRAMES = 0, 2, (1, 2)                                   # both 'train' frames of the sparsity rule (:306)
+M_ARGS = dict(range_delete_x=2, range_delete_y=1, range_delete_z=0.5, surface_expand=0.05, nerf_length_min=-12,
+              nerf_length_max=61, nerf_width_min=-12, nerf_width_max=12, nerf_height_min=-2, nerf_height_max=0.5)
+
+
+def main_maicity():
+    """Same for `maicity_dataload` (ipb2dmapping.py:200-463): shipped frames data/maicity/00/pcd/{1,2}.pcd (every 25th
+    point), shipped poses, 40 synthetic child clouds; compute_far_bound0406 raises IndexError when a ray misses its box,
+    so the children are 1 m cells around returns (every ray crosses the box that contains its return)."""
+    install_functional_stubs()
+    ref = ref_shim.import_reference()
+    src_dir = os.path.join(ref_shim.REF_ROOT, "data", "maicity", "00")
+    frames = {f: read_xyz_pcd(os.path.join(src_dir, "pcd", "%d.pcd" % f))[::25] for f in M_FRAMES}
+    pose_lines = open(os.path.join(src_dir, "poses.txt")).read().splitlines()[:M_END + 2]
+    rng = np.random.default_rng(11)
+    with tempfile.TemporaryDirectory() as tmp:
+        root, sub, res = os.path.join(tmp, "frames"), os.path.join(tmp, "children"), os.path.join(tmp, "result")
+        os.makedirs(root)
+        os.makedirs(sub)
+        os.makedirs(os.path.join(res, "save_npy", "split_child_nerf2_3"))
+        for f, pts in frames.items():
+            write_xyz_pcd(os.path.join(root, "%d.pcd" % f), pts)
+        pose_path = os.path.join(tmp, "poses.txt")
+        open(pose_path, "w").write("\n".join(pose_lines) + "\n")
+        P = [np.vstack([np.array([float(v) for v in l.split(" ")]).reshape(3, 4), [[0, 0, 0, 1]]]) for l in pose_lines]
+        world = []
+        for f, frame in frames.items():
+            keep = ((np.abs(frame[:, 0]) >= 2) | (np.abs(frame[:, 1]) >= 1) | (np.abs(frame[:, 2]) >= 0.5))
+            w = (P[f - 1] @ np.vstack([frame[keep].T.astype(np.float64), np.ones((1, int(keep.sum())))])).T[:, :3]
+            world.append(w[(w[:, 0] >= -12) & (w[:, 0] <= 61) & (np.abs(w[:, 1]) <= 12) & (w[:, 2] >= -2) & (w[:, 2] <= 0.5)])
+        world = np.concatenate(world)
+        children = []
+        for c in world[rng.choice(len(world), N_CHILD, replace=False)]:
+            children.append(world[np.all(np.abs(world - c) <= 0.5, axis=1)].astype(np.float32))
+        for i, ch in enumerate(children):
+            write_xyz_pcd(os.path.join(sub, "%d.pcd" % (i + 1)), ch)
+        ds = ref.ipb.maicity_dataload(root, split="train", data_start=M_START, data_end=M_END, cloud_size_val=64,
+                                      sub_nerf_test_num=N_CHILD, pose_path=pose_path, subnerf_path=sub, re_loaddata=1,
+                                      result_path=res, **M_ARGS)
+        rays, ranges = ds.rays.numpy(), ds.ranges.numpy()
+        out = {"frame_ids": np.array(M_FRAMES), "pose_lines": np.array(pose_lines), "rays": rays, "ranges": ranges,
+               "sub_nerf_num_count": ds.sub_nerf_num_count, "n_child": np.int64(N_CHILD), "data_start": np.int64(M_START),
+               "data_end": np.int64(M_END)}
+        for f, pts in frames.items():
+            out["frame_%d" % f] = pts
+        for i, ch in enumerate(children):
+            out["child_%d" % (i + 1)] = ch
+        for k, v in M_ARGS.items():
+            out["arg_" + k] = np.float64(v)
+        np.savez_compressed(OUT_M, **out)
+        print("wrote", OUT_M, "rays", rays.shape, "frame points", [v.shape for v in frames.values()], "bytes", os.path.getsize(OUT_M))
+
+
 if __name__ == "__main__":
-    main()
+    if "--maicity" in sys.argv:
+        main_maicity()
+    else:
+        main()

@@ -822,3 +822,38 @@ def kitti_build_rays(frames, pose_lines, child_clouds, parent_cloud, data_start,
         rays.append(r)
     rays = np.concatenate(rays) if rays else np.zeros((0, 15), np.float32)
     return rays, rays[:, 14].copy()
+
+
+def maicity_build_rays(frames, pose_lines, child_clouds, data_start, data_end, split="train", **kw):
+    """maicity_dataload(re_loaddata=1), ipb2dmapping.py:200-463: raw poses (no calibration / re-basing), frame file j+1 uses
+    pose j, near-sensor box and `< 120 m` gates on the float32 points, pose transform in float64 (float32 pose entries),
+    closed parent-box test on the transformed points, float64 sensor position, compute_far_bound0406 (every kept ray hits its
+    box).  Returns (rays (N,15) f32, ranges)."""
+    P = np.array([np.append(np.array([float(i) for i in r.strip("\n").split(" ")]).reshape(3, 4), np.array([[0, 0, 0, 1]]), axis=0)
+                  for r in pose_lines])
+    positions = P[:, :3, -1]
+    poses32 = torch.Tensor(P)
+    bound, bigger, centre = kitti_child_boxes(child_clouds)
+    parent_box = (kw["nerf_length_min"], kw["nerf_length_max"], kw["nerf_width_min"], kw["nerf_width_max"],
+                  kw["nerf_height_min"], kw["nerf_height_max"])
+    rays = []
+    for j in range(data_start, data_end):
+        if not ((split == "train" and (j + 1 - 3 - data_start) % 5 != 0) or (split == "val" and (j + 1 - 3 - data_start) % 5 == 0)):
+            continue
+        p = np.asarray(frames[j + 1], dtype=np.float32)
+        p = p[np.logical_or.reduce((np.abs(p[:, 0]) >= kw["range_delete_x"], np.abs(p[:, 1]) >= kw["range_delete_y"],
+                                    np.abs(p[:, 2]) >= kw["range_delete_z"]))]
+        p = p[np.linalg.norm(p, axis=1) < 120]
+        pe = (poses32[j].numpy() @ np.vstack((p.T, np.ones((1, p.shape[0]))))).T[:, :3]
+        m = (pe[:, 0] >= parent_box[0]) & (pe[:, 1] >= parent_box[2]) & (pe[:, 2] >= parent_box[4]) & \
+            (pe[:, 0] <= parent_box[1]) & (pe[:, 1] <= parent_box[3]) & (pe[:, 2] <= parent_box[5])
+        pe = pe[m]
+        vec = pe - positions[j]
+        dist_vec = np.linalg.norm(vec, axis=1)
+        dir_vec = np.apply_along_axis(lambda x: x / np.linalg.norm(x), 1, vec) if len(vec) else vec
+        r, _ = pack_train_rays_from_dirs(positions[j], dir_vec, dist_vec, pe, centre, bound, bigger, parent_box,
+                                         kw["surface_expand"], "maicity")
+        r[:, 0:3] = poses32[j][:3, -1].numpy()
+        rays.append(r)
+    rays = np.concatenate(rays) if rays else np.zeros((0, 15), np.float32)
+    return rays, rays[:, 14].copy()

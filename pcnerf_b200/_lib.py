@@ -69,7 +69,7 @@ SIGNATURES = {
     "pcnerf_search_select": (ci, [vp, vp, vp, i64, vp, vp]),
     "pcnerf_points": (ci, [vp, ci, i64, vp, vp, vp]),
     "pcnerf_adam_step": (ci, [vp, vp, vp, vp, i64, vp, vp, vp, f32, f32, f32, f32, f32, vp]),
-    "pcnerf_frame_returns": (ci, [vp, i64, PD, vp, ci, f32, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]),
+    "pcnerf_frame_returns": (ci, [vp, i64, PD, vp, ci, f32, f32, f32, f32, f32, f32, f32, f32, PD, PD, vp, vp, vp, vp, vp]),
     "pcnerf_nn_correspondance": (ci, [vp, i64, vp, i64, vp, vp, vp]),
     "pcnerf_dist_stats": (ci, [vp, i64, f64, vp, vp]),
 }

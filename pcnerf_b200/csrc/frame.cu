@@ -1,4 +1,5 @@
-// K0: LiDAR frame -> returns of the block (nof/dataset/ipb2dmapping.py:662-711, MaiCity :319-345).
+// K0: LiDAR frame -> returns of the block (nof/dataset/ipb2dmapping.py:662-711 KITTI, :319-345 MaiCity:
+// no height window, no interest region, but a parent-box test on the transformed points).
 //
 // One thread per raw point.  The reference filters the sensor-frame float32 points with numpy masks (near-sensor box,
 // 120 m range gate, height window), transforms the survivors with the frame pose in float64 (pose entries are float32
@@ -15,7 +16,9 @@ struct FrameParams {
     float max_range;            // 120
     float over_height, over_low;
     float interest_x, interest_y;
-    int npose;
+    int npose;                  // 0: no interest-region test (MaiCity loader)
+    int use_box;                // 1: keep only world points inside the closed parent box (MaiCity loader, :334-336)
+    double box[6];              // x_min, x_max, y_min, y_max, z_min, z_max
 };
 
 __global__ void k_frame_returns(const float* __restrict__ pts, int64_t n, FrameParams fp,
@@ -37,10 +40,12 @@ __global__ void k_frame_returns(const float* __restrict__ pts, int64_t n, FrameP
         w[a] = ((fp.pose[4 * a] * X + fp.pose[4 * a + 1] * Y) + fp.pose[4 * a + 2] * Z) + fp.pose[4 * a + 3];
     // interest region (:690-699): |x - pose_k.x| <= interest_x and |y - pose_k.y| <= interest_y for some pose k
     const float xf = (float)w[0], yf = (float)w[1];
-    bool near = false;
+    bool near = fp.npose == 0;
     for (int p = 0; p < fp.npose && !near; ++p)
         near = !(fabsf(__fsub_rn(xf, sxy[2 * p])) > fp.interest_x || fabsf(__fsub_rn(yf, sxy[2 * p + 1])) > fp.interest_y);
     k = k && near;
+    if (fp.use_box)
+        k = k && w[0] >= fp.box[0] && w[1] >= fp.box[2] && w[2] >= fp.box[4] && w[0] <= fp.box[1] && w[1] <= fp.box[3] && w[2] <= fp.box[5];
     const double vx = w[0] - fp.pos[0], vy = w[1] - fp.pos[1], vz = w[2] - fp.pos[2];       // :706-709
     const double d = sqrt((vx * vx + vy * vy) + vz * vz);
     keep[i] = k ? 1 : 0;
@@ -51,16 +56,18 @@ __global__ void k_frame_returns(const float* __restrict__ pts, int64_t n, FrameP
 
 extern "C" int pcnerf_frame_returns(const float* pts, int64_t n, const double* h_pose16, const float* pose_xy, int npose,
                                     float rdx, float rdy, float rdz, float max_range, float over_height, float over_low,
-                                    float interest_x, float interest_y, uint8_t* keep, double* world, double* dir,
-                                    double* dist, void* stream) {
+                                    float interest_x, float interest_y, const double* h_box6, const double* h_pos3,
+                                    uint8_t* keep, double* world, double* dir, double* dist, void* stream) {
     PCN_CHECK_ARG(n >= 0 && h_pose16 && npose >= 0 && npose <= 8192, "frame_returns: bad arguments (at most 8192 poses)");
     if (n == 0) return 0;
     PCN_CHECK_ARG(pts && keep && world && dir && dist && (npose == 0 || pose_xy), "frame_returns: null argument");
     FrameParams fp;
     for (int i = 0; i < 12; ++i) fp.pose[i] = h_pose16[i];
-    for (int a = 0; a < 3; ++a) fp.pos[a] = h_pose16[4 * a + 3];
+    for (int a = 0; a < 3; ++a) fp.pos[a] = h_pos3 ? h_pos3[a] : h_pose16[4 * a + 3];
     fp.rdx = rdx; fp.rdy = rdy; fp.rdz = rdz; fp.max_range = max_range; fp.over_height = over_height; fp.over_low = over_low;
     fp.interest_x = interest_x; fp.interest_y = interest_y; fp.npose = npose;
+    fp.use_box = h_box6 ? 1 : 0;
+    for (int i = 0; i < 6; ++i) fp.box[i] = h_box6 ? h_box6[i] : 0.0;
     const size_t smem = (size_t)2 * npose * sizeof(float);
     if (smem > 48 * 1024) PCN_CUDA(cudaFuncSetAttribute(k_frame_returns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)n * (12.0 + 1.0 + 56.0));

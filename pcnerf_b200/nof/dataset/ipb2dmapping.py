@@ -154,3 +154,74 @@ class kitti_dataload(torch.utils.data.Dataset):
 
     def __len__(self):
         return len(self.rays) if self.split == 'train' else self.cloud_size_val
+
+
+class maicity_dataload(kitti_dataload):
+    """nof/dataset/ipb2dmapping.py:200-463 (constructor signature, frame selection, outputs and cache paths as there): raw
+    poses (frame file j+1 uses pose j), near-sensor box and `< 120 m` gates, closed parent-box test on the transformed
+    points (the box is given by the nerf_* arguments, there is no parent cloud), float64 sensor positions and
+    compute_far_bound0406.  Against the reference executed on the same files every column is identical
+    (tests/test_gpu_dataset.py::test_maicity_dataload_end_to_end)."""
+
+    def __init__(self, root_dir, split='train', data_start=0, data_end=36, cloud_size_val=2048, range_delete_x=2,
+                 range_delete_y=1, range_delete_z=0.5, sub_nerf_test_num=3, surface_expand=0.1, nerf_length_min=-4.5,
+                 nerf_length_max=25.5, nerf_width_min=-12, nerf_width_max=12, nerf_height_min=-2, nerf_height_max=0.5,
+                 pose_path=None, subnerf_path=None, re_loaddata=0, result_path=None):
+        torch.utils.data.Dataset.__init__(self)
+        self.root_dir, self.split, self.cloud_size_val = root_dir, split, cloud_size_val
+        self.result_path, self.re_loaddata = result_path, re_loaddata
+        if re_loaddata:
+            self.data_start, self.data_end = data_start, data_end
+            self.range_delete = (range_delete_x, range_delete_y, range_delete_z)
+            self.sub_nerf_test_num, self.subnerf_path, self.surface_expand = sub_nerf_test_num, subnerf_path, surface_expand
+            self.parent_box = (nerf_length_min, nerf_length_max, nerf_width_min, nerf_width_max, nerf_height_min,
+                               nerf_height_max)
+            with open(pose_path, "r", encoding="utf-8") as f:
+                rows = [r.strip() for r in f.readlines() if r.strip()]
+            poses = np.array([np.append(np.array([float(i) for i in r.split(' ')]).reshape(3, 4), np.array([[0, 0, 0, 1]]),
+                                        axis=0) for r in rows])
+            self.positions = poses[:, :3, -1]                                     # float64 (:245-246)
+            self.poses = torch.Tensor(poses).numpy()                              # float32 (:247)
+        self.load_data()
+
+    def frames(self):
+        out = []
+        for j in range(self.data_start, self.data_end):
+            if self.split == 'train' and (j + 1 - 3 - self.data_start) % 5 != 0:
+                out.append(j)
+            elif self.split == 'val' and (j + 1 - 3 - self.data_start) % 5 == 0:
+                out.append(j)
+        return out
+
+    def _build_or_load(self):
+        if not self.re_loaddata:
+            self.rays = torch.from_numpy(np.load(self._cache("rays")))
+            self.ranges = torch.from_numpy(np.load(self._cache("ranges")))
+            return
+        K = self.sub_nerf_test_num
+        bound, centre = np.zeros((K, 6)), np.zeros((K, 3))
+        for i in range(K):                                                        # :256-280
+            lo, hi = pcd.axis_aligned_bounds(pcd.read_pcd(os.path.join(self.subnerf_path, "%d.pcd" % (i + 1))))
+            bound[i, :3], bound[i, 3:] = lo - 0.025, hi + 0.025
+            centre[i] = (lo + hi) / 2.0
+        strict_120 = float(np.nextafter(np.float32(120.0), np.float32(0.0)))      # dist < 120 (:327)
+        rays, counts = [], torch.zeros(K, dtype=torch.int64)
+        for j in self.frames():
+            pts = pcd.read_pcd(os.path.join(self.root_dir, "%d.pcd" % (j + 1)))
+            # transform with the float32 pose, directions / ranges from the float64 position (:331, :340)
+            world, dirs, dist = ops.frame_returns(pts, self.poses[j], None, self.range_delete, strict_120, float("inf"),
+                                                  -float("inf"), 0.0, 0.0, parent_box=self.parent_box,
+                                                  position=self.positions[j])
+            r, keep = ops.aabb_pack_train(406, self.positions[j], dirs, dist, world, centre, bound, bound, self.parent_box,
+                                          self.surface_expand, 10)
+            r[:, 0:3] = torch.from_numpy(self.poses[j][:3, -1]).to(r.device)      # rays_o = float32 pose translation (:410)
+            rays.append(r)
+            if r.shape[0]:
+                counts += torch.bincount(r[:, 9].long().cpu() - 1, minlength=K)
+        self.rays = (torch.cat(rays, 0) if rays else torch.zeros((0, 15), device="cuda")).cpu()
+        self.ranges = self.rays[:, 14].clone()
+        self.sub_nerf_num_count = counts.numpy().astype(np.float64)
+        if self.result_path:
+            os.makedirs(os.path.dirname(self._cache("rays")), exist_ok=True)
+            np.save(self._cache("rays"), self.rays.numpy())
+            np.save(self._cache("ranges"), self.ranges.numpy())

@@ -161,7 +161,8 @@ def aabb_pack_train(variant, ray_o, ray_d, dist, points, centres, boxes, boxes_b
     return (rays[keep] if compact else rays), keep
 
 
-def frame_returns(points_f32, pose, pose_xy, range_delete, max_range, over_height, over_low, interest_x, interest_y):
+def frame_returns(points_f32, pose, pose_xy, range_delete, max_range, over_height, over_low, interest_x, interest_y,
+                  parent_box=None, position=None):
     """K0 (ipb2dmapping.py:662-711): raw sensor-frame points (n,3) float32 -> (world points (M,3), dir (M,3), dist (M,))
     float64 CUDA tensors of the points the block keeps, in their original order.  pose: (4,4) host array (float32 values),
     pose_xy: (P,2) float32 x / y translations of the run's poses, range_delete = (x, y, z)."""
@@ -169,16 +170,21 @@ def frame_returns(points_f32, pose, pose_xy, range_delete, max_range, over_heigh
     pts = _cuda_f32(pts.to("cuda") if not pts.is_cuda else pts, "points").reshape(-1, 3)
     n = pts.shape[0]
     dev = pts.device
+    if pose_xy is None:
+        pose_xy = np.zeros((0, 2), dtype=np.float32)
     pxy = pose_xy if isinstance(pose_xy, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pose_xy, dtype=np.float32))
     pxy = pxy.to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 2)
     keep_h, hp = _h3(np.asarray(pose, dtype=np.float64).reshape(16))
+    keep_b, hb = _h3(parent_box) if parent_box is not None else (None, None)
+    keep_s, hs = _h3(position) if position is not None else (None, None)      # sensor position (default: pose[:3, 3])
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
     world = torch.empty((n, 3), dtype=torch.float64, device=dev)
     dirs = torch.empty((n, 3), dtype=torch.float64, device=dev)
     dist = torch.empty(n, dtype=torch.float64, device=dev)
     check(lib().pcnerf_frame_returns(_p(pts), n, hp, _p(pxy), pxy.shape[0], float(range_delete[0]), float(range_delete[1]),
                                      float(range_delete[2]), float(max_range), float(over_height), float(over_low),
-                                     float(interest_x), float(interest_y), _p(keep), _p(world), _p(dirs), _p(dist), _stream()))
+                                     float(interest_x), float(interest_y), hb, hs, _p(keep), _p(world), _p(dirs), _p(dist),
+                                     _stream()))
     _count()
     sel = keep.bool()
     return world[sel], dirs[sel], dist[sel]

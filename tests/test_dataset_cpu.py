@@ -81,3 +81,11 @@ def test_kitti_poses_match_oracle():
     got = pcd.read_kitti_poses(list(g["pose_lines"]), int(g["data_start"]))
     assert got.dtype == np.float32 and np.array_equal(got, ref)
     assert np.allclose(got[int(g["data_start"]) + 1], np.eye(4), atol=1e-4)       # the run's first pose is the origin (float32 product)
+
+
+def test_oracle_maicity_build_matches_reference_run():
+    """maicity_dataload restated (float64 sensor positions there: every column is exact)."""
+    g = golden("maicity_dataset")
+    frames, children, kw = _inputs(g)
+    rays, ranges = orc.maicity_build_rays(frames, list(g["pose_lines"]), children, int(g["data_start"]), int(g["data_end"]), **kw)
+    assert np.array_equal(rays, g["rays"]) and np.array_equal(ranges, g["ranges"])

@@ -136,3 +136,26 @@ def test_render_scene_frame_blocks_partition_the_work():
         part = scene.render_scene_frame(blocks, origin, pts, emb, 32, 64, 8192, world_size=2, rank_=r)
         assert list(part) == [r]
         assert torch.equal(part[r], full[r])
+
+
+def test_maicity_dataload_end_to_end(tmp_path):
+    from pcnerf_b200 import pcd
+    from pcnerf_b200.nof.dataset.ipb2dmapping import maicity_dataload
+    g = golden("maicity_dataset")
+    frames, children, kw = _inputs(g)
+    root, sub, res = str(tmp_path / "frames"), str(tmp_path / "children"), str(tmp_path / "result")
+    for fid, pts in frames.items():
+        pcd.write_pcd(os.path.join(root, "%d.pcd" % fid), pts)
+    for i, c in enumerate(children):
+        pcd.write_pcd(os.path.join(sub, "%d.pcd" % (i + 1)), c)
+    with open(str(tmp_path / "poses.txt"), "w") as f:
+        f.write("\n".join(g["pose_lines"]) + "\n")
+    args = dict(root_dir=root, data_start=int(g["data_start"]), data_end=int(g["data_end"]), cloud_size_val=64,
+                sub_nerf_test_num=int(g["n_child"]), pose_path=str(tmp_path / "poses.txt"), subnerf_path=sub,
+                result_path=res, **kw)
+    ds = maicity_dataload(split="train", re_loaddata=1, **args)
+    assert np.array_equal(ds.rays.numpy(), g["rays"])                           # every column, bit for bit
+    assert np.array_equal(ds.ranges.numpy(), g["ranges"])
+    assert np.array_equal(ds.sub_nerf_num_count, g["sub_nerf_num_count"])
+    again = maicity_dataload(split="train", re_loaddata=0, **args)
+    assert torch.equal(again.rays, ds.rays)
