@@ -9,7 +9,7 @@ def install_as_nof():
     import sys
     from . import nof as _nof
     sys.modules.setdefault("nof", _nof)
-    for sub in ("render", "networks", "criteria", "dataset"):
+    for sub in ("render", "networks", "criteria", "criteria.metrics", "dataset", "dataset.ipb2dmapping"):
         mod = __import__("pcnerf_b200.nof." + sub, fromlist=["x"])
         sys.modules.setdefault("nof." + sub, mod)
     return _nof
