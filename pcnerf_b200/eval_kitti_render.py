@@ -134,3 +134,46 @@ def render_view_to_pcd(nof_coarse_model, nof_fine_model, embedding_position, dat
                        depth_inference_method=depth_inference_method, batch_size_set=batch_size_set)
     pcd.write_pcd(out_path, pts.cpu().numpy())
     return pts
+
+
+def multi_frame_maicity(root_dir, split='test', data_start=1, data_end=2, range_delete_x=2, range_delete_y=1,
+                        range_delete_z=0.5, sub_nerf_test_num=4, nerf_length_min=-4.5, nerf_length_max=25.5,
+                        nerf_width_min=-12, nerf_width_max=12, nerf_height_min=-2, nerf_height_max=0.5, pose_path=None,
+                        subnerf_path=None, view_pcd_number=0, result_path=None, depth_inference_method=2):
+    """eval_kitti_render.py:246-535 with the reference's signature: the MaiCity counterpart of multi_frame_kitti -- raw
+    poses (frame file j+1 uses pose j), child boxes +-0.025 (:277-292), `< 120 m` gate, closed parent-box test on the
+    transformed points (:343-345), float32 sensor position (:265), group growth step 0.005 (:353-461).  Same artefacts."""
+    import os
+    from . import pcd
+    with open(pose_path, "r", encoding="utf-8") as f:
+        rows = [r.strip() for r in f.readlines() if r.strip()]
+    poses = torch.Tensor(np.array([np.append(np.array([float(i) for i in r.split(' ')]).reshape(3, 4),
+                                             np.array([[0, 0, 0, 1]]), axis=0) for r in rows])).numpy()
+    bound = np.zeros((sub_nerf_test_num, 6))
+    for i in range(sub_nerf_test_num):
+        blo, bhi = pcd.axis_aligned_bounds(pcd.read_pcd(os.path.join(subnerf_path, "%d.pcd" % (i + 1))))
+        bound[i, :3], bound[i, 3:] = blo - 0.025, bhi + 0.025
+    j = view_pcd_number - 1
+    if not (data_start <= j < data_end):
+        raise ValueError("view_pcd_number %d is outside [data_start+1, data_end]" % view_pcd_number)
+    pts = pcd.read_pcd(os.path.join(root_dir, "%d.pcd" % view_pcd_number))
+    box = (nerf_length_min, nerf_length_max, nerf_width_min, nerf_width_max, nerf_height_min, nerf_height_max)
+    strict_120 = float(np.nextafter(np.float32(120.0), np.float32(0.0)))
+    world, dirs, dist = ops.frame_returns(pts, poses[j], None, (range_delete_x, range_delete_y, range_delete_z), strict_120,
+                                          float("inf"), -float("inf"), 0.0, 0.0, parent_box=box)
+    origin = poses[j][:3, -1].astype(np.float64)
+    pmin = np.array([nerf_length_min, nerf_width_min, nerf_height_min], dtype=np.float64)
+    pmax = np.array([nerf_length_max, nerf_width_max, nerf_height_max], dtype=np.float64)
+    rays, ranges, other, kept = ops.aabb_build_groups(origin, dirs, dist, bound, bound, pmin, pmax, depth_inference_method,
+                                                      0.005, 0.65)
+    rays, ranges, other = rays.cpu(), ranges.cpu(), other.cpu()
+    if result_path:
+        d = os.path.join(result_path, "two_step" if depth_inference_method == 2 else "one_step",
+                         "%dpcd" % view_pcd_number, "childnerf_ray_intersect")
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, "all_ranges_child.npy"), ranges.numpy())
+        np.save(os.path.join(d, "all_rays_child.npy"), rays.numpy())
+        np.save(os.path.join(d, "other_interest_sub_nerf_number_child.npy"), other.numpy())
+        pcd.write_pcd(os.path.join(d, "%d_source.pcd" % view_pcd_number), world[kept.bool()].cpu().numpy())
+        pcd.write_pcd(os.path.join(d, "%d_pose.pcd" % view_pcd_number), origin.reshape(1, 3))
+    return rays, ranges, other

@@ -159,3 +159,48 @@ def test_maicity_dataload_end_to_end(tmp_path):
     assert np.array_equal(ds.sub_nerf_num_count, g["sub_nerf_num_count"])
     again = maicity_dataload(split="train", re_loaddata=0, **args)
     assert torch.equal(again.rays, ds.rays)
+
+
+def test_multi_frame_maicity_files_to_candidate_rows(tmp_path):
+    """eval_kitti_render.multi_frame_maicity from files on disk against the oracle chain (frame filter -> parent-box test ->
+    build_candidate_groups with the MaiCity growth step)."""
+    from pcnerf_b200 import eval_kitti_render as ev
+    from pcnerf_b200 import pcd
+    g = golden("maicity_dataset")
+    frames, children, kw = _inputs(g)
+    root, sub, res = str(tmp_path / "frames"), str(tmp_path / "children"), str(tmp_path / "result")
+    for fid, pts in frames.items():
+        pcd.write_pcd(os.path.join(root, "%d.pcd" % fid), pts)
+    for i, c in enumerate(children):
+        pcd.write_pcd(os.path.join(sub, "%d.pcd" % (i + 1)), c)
+    with open(str(tmp_path / "poses.txt"), "w") as f:
+        f.write("\n".join(g["pose_lines"]) + "\n")
+    fid = int(g["frame_ids"][1])
+    box = {k: kw[k] for k in kw if k.startswith("nerf_")}
+    rays, ranges, other = ev.multi_frame_maicity(root, data_start=0, data_end=2, range_delete_x=kw["range_delete_x"],
+                                                 range_delete_y=kw["range_delete_y"], range_delete_z=kw["range_delete_z"],
+                                                 sub_nerf_test_num=len(children), pose_path=str(tmp_path / "poses.txt"),
+                                                 subnerf_path=sub, view_pcd_number=fid, result_path=res,
+                                                 depth_inference_method=2, **box)
+    P = torch.Tensor(np.array([np.append(np.array([float(i) for i in r.split(" ")]).reshape(3, 4), np.array([[0, 0, 0, 1]]), axis=0)
+                               for r in g["pose_lines"]])).numpy()
+    p = frames[fid]
+    p = p[(np.abs(p[:, 0]) >= kw["range_delete_x"]) | (np.abs(p[:, 1]) >= kw["range_delete_y"]) | (np.abs(p[:, 2]) >= kw["range_delete_z"])]
+    p = p[np.linalg.norm(p, axis=1) < 120]
+    pe = (P[fid - 1] @ np.vstack((p.T, np.ones((1, p.shape[0]))))).T[:, :3]
+    m = (pe[:, 0] >= box["nerf_length_min"]) & (pe[:, 1] >= box["nerf_width_min"]) & (pe[:, 2] >= box["nerf_height_min"]) & \
+        (pe[:, 0] <= box["nerf_length_max"]) & (pe[:, 1] <= box["nerf_width_max"]) & (pe[:, 2] <= box["nerf_height_max"])
+    pe = pe[m]
+    origin = P[fid - 1][:3, -1].astype(np.float64)
+    vec = pe - origin
+    dist = np.linalg.norm(vec, axis=1)
+    dv = vec / dist[:, None]
+    bound = np.stack([np.concatenate([c.astype(np.float64).min(0) - 0.025, c.astype(np.float64).max(0) + 0.025]) for c in children])
+    pmin = np.array([box["nerf_length_min"], box["nerf_width_min"], box["nerf_height_min"]])
+    pmax = np.array([box["nerf_length_max"], box["nerf_width_max"], box["nerf_height_max"]])
+    r_ref, rg_ref, o_ref = orc.build_candidate_groups(origin, dv, dist, bound, bound, pmin, pmax, 2, 0.005)[:3]
+    assert rays.shape == tuple(r_ref.shape) and rays.shape[0] > 0
+    assert np.array_equal(other.numpy().reshape(-1), np.asarray(o_ref).reshape(-1))
+    np.testing.assert_allclose(rays.numpy(), np.asarray(r_ref), rtol=3e-7, atol=1e-6)
+    d = os.path.join(res, "two_step", "%dpcd" % fid, "childnerf_ray_intersect")
+    assert np.array_equal(np.load(os.path.join(d, "all_rays_child.npy")), rays.numpy())
