@@ -89,3 +89,73 @@ class NOFSystem(torch.nn.Module):
             hp.lambda_child_depth_loss * results['child_depth_loss_fine'] + hp.lambda_child_depth_loss * results['child_depth_loss']
         self.last_terms = {"loss_range": loss_range, "loss_range_fine": loss_range_fine, **results}
         return loss
+
+
+def load_ckpt(model, ckpt_path, model_name='model', prefixes_to_ignore=()):
+    """nof/nof_utils.py:176-199: load the `model_name.*` entries of a (Lightning-style) checkpoint into `model`."""
+    ckpt = torch.load(ckpt_path, map_location=torch.device('cpu'))
+    if 'state_dict' in ckpt:
+        ckpt = ckpt['state_dict']
+    sd = model.state_dict()
+    for k, v in ckpt.items():
+        if k.startswith(model_name) and not any(k[len(model_name) + 1:].startswith(p) for p in prefixes_to_ignore):
+            sd[k[len(model_name) + 1:]] = v
+    model.load_state_dict(sd)
+
+
+def fit(hparams, max_steps=None, device="cuda", precision=None, ckpt_path=None, history_paths=None):
+    """A Lightning-free `trainer.fit(NOFSystem(hparams))` for the hot path (train_kitti.py:52-86, :262-296): build the dataset
+    named by hparams.datasettype (`nof.dataset.nof_dataset`, .npy cache or files), shuffle it into batches of
+    hparams.batch_size rays, and run training_step -> backward -> optimizer -> MultiStepLR (stepped per epoch) for
+    hparams.num_epochs epochs (or max_steps).  The seven loss curves go to a device-side LossHistory (no per-step host
+    synchronisation); a checkpoint with the reference's key layout (`state_dict` -> `nof_coarse.*`, `nof_fine.*`) is written
+    to ckpt_path.  Returns (system, history array (steps, 7))."""
+    from .nof.dataset import nof_dataset
+    from .optim import LossHistory
+    common = dict(root_dir=hparams.root_dir, data_start=hparams.data_start, data_end=hparams.data_end,
+                  cloud_size_val=hparams.cloud_size_val, range_delete_x=hparams.range_delete_x,
+                  range_delete_y=hparams.range_delete_y, range_delete_z=hparams.range_delete_z,
+                  sub_nerf_test_num=hparams.sub_nerf_test_num, pose_path=hparams.pose_path, subnerf_path=hparams.subnerf_path,
+                  surface_expand=hparams.surface_expand, re_loaddata=hparams.re_loaddata, result_path=hparams.result_path)
+    if hparams.datasettype == "kitti_dataload":                                   # train_kitti.py:52-64
+        common.update(parentnerf_path=hparams.parentnerf_path, interest_x=hparams.interest_x, interest_y=hparams.interest_y,
+                      over_height=hparams.over_height, over_low=hparams.over_low)
+    else:                                                                         # :65-77
+        common.update(nerf_length_min=hparams.nerf_length_min, nerf_length_max=hparams.nerf_length_max,
+                      nerf_width_min=hparams.nerf_width_min, nerf_width_max=hparams.nerf_width_max,
+                      nerf_height_min=hparams.nerf_height_min, nerf_height_max=hparams.nerf_height_max)
+    train = nof_dataset[hparams.datasettype](split='train', **common)
+    system = NOFSystem(hparams).to(device)
+    if precision is not None:
+        system.nof_coarse.precision = system.nof_fine.precision = precision
+    (opt,), (sched,) = system.configure_optimizers()
+    hist = LossHistory(device=device)
+    rays_all, ranges_all = train.all_rays.to(device), train.all_ranges.to(device)
+    gen = torch.Generator(device="cpu").manual_seed(int(getattr(hparams, "seed", 0) or 0))
+    step = 0
+    system.train()
+    for _ in range(hparams.num_epochs):
+        perm = torch.randperm(rays_all.shape[0], generator=gen).to(device)
+        for b in range(0, perm.shape[0], hparams.batch_size):
+            idx = perm[b:b + hparams.batch_size]
+            if idx.shape[0] < 2:                                                  # a one-row BN batch raises (like torch)
+                continue
+            opt.zero_grad()
+            loss = system.training_step({'rays': rays_all[idx], 'ranges': ranges_all[idx]}, step)
+            loss.backward()
+            opt.step()
+            t = system.last_terms
+            hist.append([loss, t["loss_range"], t["loss_range_fine"],
+                         hparams.lambda_child_free_loss * t["child_free_loss"], hparams.lambda_child_free_loss * t["child_free_loss_fine"],
+                         hparams.lambda_child_depth_loss * t["child_depth_loss"], hparams.lambda_child_depth_loss * t["child_depth_loss_fine"]])
+            step += 1
+            if max_steps is not None and step >= max_steps:
+                break
+        sched.step()
+        if max_steps is not None and step >= max_steps:
+            break
+    if ckpt_path:
+        torch.save({'state_dict': {k: v.detach().cpu() for k, v in system.state_dict().items()}}, ckpt_path)
+    if history_paths:
+        hist.save(history_paths)
+    return system, hist.to_numpy()

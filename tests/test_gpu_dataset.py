@@ -204,3 +204,54 @@ def test_multi_frame_maicity_files_to_candidate_rows(tmp_path):
     np.testing.assert_allclose(rays.numpy(), np.asarray(r_ref), rtol=3e-7, atol=1e-6)
     d = os.path.join(res, "two_step", "%dpcd" % fid, "childnerf_ray_intersect")
     assert np.array_equal(np.load(os.path.join(d, "all_rays_child.npy")), rays.numpy())
+
+
+def test_fit_from_files_then_render_to_pcd(tmp_path):
+    """The two entry points end to end on the reference's data layout, without open3d / pcl / Lightning: PCD frames + poses
+    + child clouds -> maicity_dataload -> train_kitti.fit (NOFSystem, FlatAdam, MultiStepLR, device-side loss history,
+    reference-style checkpoint) -> load_ckpt -> multi_frame_maicity -> render_view_to_pcd."""
+    import types
+    from pcnerf_b200 import eval_kitti_render as ev
+    from pcnerf_b200 import pcd, train_kitti
+    from pcnerf_b200.nof.networks import NOF_coarse, NOF_fine, Embedding
+    g = golden("maicity_dataset")
+    frames, children, kw = _inputs(g)
+    root, sub, res = str(tmp_path / "frames"), str(tmp_path / "children"), str(tmp_path / "result")
+    for fid, pts in frames.items():
+        pcd.write_pcd(os.path.join(root, "%d.pcd" % fid), pts)
+    for i, c in enumerate(children):
+        pcd.write_pcd(os.path.join(sub, "%d.pcd" % (i + 1)), c)
+    with open(str(tmp_path / "poses.txt"), "w") as f:
+        f.write("\n".join(g["pose_lines"]) + "\n")
+    hp = types.SimpleNamespace(
+        root_dir=root, pose_path=str(tmp_path / "poses.txt"), subnerf_path=sub, result_path=res, datasettype="maicity_dataload",
+        data_start=0, data_end=2, cloud_size_val=64, sub_nerf_test_num=len(children), re_loaddata=1, batch_size=256,
+        num_epochs=1, seed=42, optimizer="flat_adam", lr=5e-4, weight_decay=1e-3, momentum=0.9, decay_gamma=0.1,
+        L_pos=10, feature_size=256, use_skip=True, loss_type="smoothl1", N_samples=32, N_importance=64, use_disp=False,
+        perturb=1.0, noise_std=0.0, chunk=262144, use_segmentated_sample=1, segmentated_child_nerf_ratio=0.1,
+        use_child_nerf_divide=0, use_child_nerf_loss=1, lambda_loss=1.0, lambda_loss_fine=1.0, lambda_child_free_loss=1e6,
+        lambda_child_depth_loss=1e5, **kw)
+    ckpt = str(tmp_path / "best.ckpt")
+    paths = [str(tmp_path / ("curve%d.npy" % i)) for i in range(7)]
+    system, hist = train_kitti.fit(hp, max_steps=6, ckpt_path=ckpt, history_paths=paths)
+    assert hist.shape == (6, 7) and np.isfinite(hist).all() and np.load(paths[0]).shape == (6,)
+    assert np.allclose(hist[:, 0], hist[:, 1:].sum(1), rtol=1e-4)                  # the total is the sum of its six terms
+    mc, mf = NOF_coarse(), NOF_fine()
+    train_kitti.load_ckpt(mc, ckpt, model_name="nof_coarse")
+    train_kitti.load_ckpt(mf, ckpt, model_name="nof_fine")
+    assert torch.equal(mc.state_dict()["layer1.0.weight"], system.nof_coarse.state_dict()["layer1.0.weight"].cpu())
+    mc.to(dev_()).eval()
+    mf.to(dev_()).eval()
+    box = {k: kw[k] for k in kw if k.startswith("nerf_")}
+    rays, ranges, other = ev.multi_frame_maicity(root, data_start=0, data_end=2, range_delete_x=kw["range_delete_x"],
+                                                 range_delete_y=kw["range_delete_y"], range_delete_z=kw["range_delete_z"],
+                                                 sub_nerf_test_num=len(children), pose_path=str(tmp_path / "poses.txt"),
+                                                 subnerf_path=sub, view_pcd_number=2, result_path=res, **box)
+    out = str(tmp_path / "render" / "2_render.pcd")
+    pts = ev.render_view_to_pcd(mc, mf, Embedding(3, 10), rays, other, out, 32, 64, 184320)
+    back = pcd.read_pcd(out)
+    assert back.shape == (pts.shape[0], 3) and pts.shape[0] > 0 and np.isfinite(back).all()
+
+
+def dev_():
+    return torch.device("cuda:0")
