@@ -441,17 +441,19 @@ def smooth_l1_mean(a, b):
 
 def train_head(p, z, rays, noise=None, noise_std=0.0, epsilon=1e-10, use_child_nerf_loss=1,
                use_child_nerf_divide=0, sub_nerf_test_num=4):
-    """nof/render.py:51-163 after the MLP: weights, masks, child free / depth losses, depth."""
+    """nof/render.py:51-163 after the MLP: weights, masks, child free / depth losses, depth.
+    With float64 p / z / rays (exact images of the fp32 inputs) the masks are still decided in fp32, everything else runs
+    in double: the gradient "truth" the fp32 kernels and fp32 autograd are both measured against in tests."""
     near_far_child = rays[:, 10:12]
     range_readings = rays[:, -1]
     N, S = z.shape
     w = composite(p, noise, noise_std, epsilon)
     if use_child_nerf_loss == 1:
-        m0, _ = child_mask(z, near_far_child, 0.0, strict=False)
-        m2, _ = child_mask(z, near_far_child, 2, strict=False)
-        w_non = w * (~m0).float()
-        w_child = w * m2.float()
-        z_child = z * m2.float()
+        m0, _ = child_mask(z.float(), near_far_child.float(), 0.0, strict=False)
+        m2, _ = child_mask(z.float(), near_far_child.float(), 2, strict=False)
+        w_non = w * (~m0).to(w.dtype)
+        w_child = w * m2.to(w.dtype)
+        z_child = z * m2.to(w.dtype)
         w_child = w_child / (torch.sum(w_child, -1).reshape(-1, 1) + epsilon)
         d_hat = torch.sum(w_child * z_child, -1)
         if use_child_nerf_divide == 1:

@@ -279,7 +279,7 @@ __device__ __forceinline__ void inverse_cdf(const float* bins, float* cdf, const
 __global__ void k_sample_pdf(const float* __restrict__ bins_g, const float* __restrict__ wts, int64_t n, int nb,
                              const float* __restrict__ u, int u_ld, int Ni, float* __restrict__ out) {
     extern __shared__ float smf[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_in_block(), wpb = blockDim.x >> 5;
     float* bins = smf + (size_t)wib * (2 * nb + Ni);
     float* cdf = bins + nb;
     float* zs = cdf + nb;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) k_sample_encode_coarse(const float* __
                                        float* __restrict__ out_enc, __half* __restrict__ out_bf, int stage_f) {
     extern __shared__ __align__(16) float smf[];
     const int S = n_a + n_b;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_in_block(), wpb = blockDim.x >> 5;
     float* za = smf + (size_t)wib * (al4(2 * S) + stage_f);
     float* tmp = za + S;
     float* stage = za + al4(2 * S);
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256, 2) k_sample_encode_fine(const float* __re
                                      __half* __restrict__ out_bf, int stage_f) {
     extern __shared__ __align__(16) float smf[];
     const int F = S + Ni;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_in_block(), wpb = blockDim.x >> 5;
     const size_t arrays = al4(S + 2 * (S - 1) + NiPad + F);
     float* zc = smf + wib * (arrays + stage_f);
     float* bins = zc + S;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256, 2) k_sample_encode_fine(const float* __re
 // Embedding.forward alone (models.py:27-41): one warp per point.
 __global__ void k_embed(const float* __restrict__ x, int64_t b, float* __restrict__ out, int out_ld) {
     __shared__ float stage_all[8 * 64];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_in_block(), wpb = blockDim.x >> 5;
     float* st = stage_all + wib * 64;
     const int k = lane / 3, c = lane - 3 * k;
     const float freq = (float)(1 << (k < 10 ? k : 0));

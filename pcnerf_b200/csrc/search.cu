@@ -43,7 +43,7 @@ __global__ void k_search_rows(const float* __restrict__ p, const float* __restri
                               double* __restrict__ sums) {
     extern __shared__ float smf[];
     __shared__ double red[8];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_in_block(), wpb = blockDim.x >> 5;
     float* sz = smf + (size_t)wib * 2 * P;
     float* sw = sz + P;
     double acc_op = 0;
