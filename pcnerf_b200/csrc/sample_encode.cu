@@ -144,6 +144,100 @@ __device__ __forceinline__ void encode_ray_t(const float o0, const float o1, con
     }
 }
 
+// ---- fp16 rows only (precision 1, the tensor-core path): the same values as encode_ray_t<false, true>, produced octave
+// by octave and packed into the 32 half2 registers of the row as they appear (column order x0 x1 x2 | s_k0 s_k1 s_k2
+// c_k0 c_k1 c_k2 ...), instead of building the 64-float row first.  ~60 live registers instead of 128: four CTAs per SM
+// instead of two (ncu on the 128-register form: MUFU pipe 45 % busy, issue slots 52 % busy, 4 warps per scheduler --
+// neither pipe hidden behind the other).  Lanes with an out-of-range / non-finite coordinate (|x| >= ENC_BIG: never in
+// a real scene) rewrite their own staged row from a scalar loop afterwards.
+__device__ __forceinline__ void sincos_q(uint32_t lo, uint32_t hi, int k, float& sn, float& cs) {
+    const uint32_t w = __funnelshift_r(lo, hi, 18 - k);
+    const float f = __uint_as_float((w & 0x7FFFFFu) ^ 0x3FC00000u);
+    const float ang = fmaf(f - 1.5f, 6.2831853071795865f, 3.7450703e-7f);
+    sn = __sinf(ang);
+    cs = __cosf(ang);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __noinline__ void encode_row_slow_f16(float x0, float x1, float x2, uint32_t row_base, int lane) {
+    auto put = [&](int col, float v) {
+        const uint32_t a = row_base + (uint32_t)(((((col >> 3) ^ lane) & 7) << 4) + ((col & 7) << 1));
+        const unsigned short h = __half_as_ushort(__float2half_rn(v));
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
+    };
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+        const float x = c == 0 ? x0 : (c == 1 ? x1 : x2);
+        const bool fast = fabsf(x) < ENC_BIG;
+        const long long q = enc_phase(fast ? x : 0.f);
+        const uint32_t lo = (uint32_t)q, hi = (uint32_t)((unsigned long long)q >> 32);
+#pragma unroll 1
+        for (int k = 0; k < 10; ++k) {
+            float sn, cs;
+            if (fast) sincos_q(lo, hi, k, sn, cs);
+            else sincosf((float)(1 << k) * x, &sn, &cs);
+            put(3 + 6 * k + c, sn);
+            put(6 + 6 * k + c, cs);
+        }
+    }
+}
+__device__ __forceinline__ void encode_ray_f16(const float o0, const float o1, const float o2, const float d0,
+                                               const float d1, const float d2, const float* zs, int P, int64_t row0,
+                                               __half* __restrict__ out_bf, float* stage, int lane) {
+    const uint32_t sbase = enc_smem_u32(stage);
+    for (int j0 = 0; j0 < P; j0 += 32) {
+        const int j = j0 + lane;
+        const float z = zs[j < P ? j : P - 1];
+        // rays_o + rays_d * z, nof/render.py:458 (mul then add, no FMA)
+        const float x0 = __fadd_rn(o0, __fmul_rn(d0, z));
+        const float x1 = __fadd_rn(o1, __fmul_rn(d1, z));
+        const float x2 = __fadd_rn(o2, __fmul_rn(d2, z));
+        const bool big = !(fabsf(x0) < ENC_BIG && fabsf(x1) < ENC_BIG && fabsf(x2) < ENC_BIG);
+        const long long q0 = enc_phase(x0), q1 = enc_phase(x1), q2 = enc_phase(x2);
+        const uint32_t l0 = (uint32_t)q0, h0 = (uint32_t)((unsigned long long)q0 >> 32);
+        const uint32_t l1 = (uint32_t)q1, h1 = (uint32_t)((unsigned long long)q1 >> 32);
+        const uint32_t l2 = (uint32_t)q2, h2 = (uint32_t)((unsigned long long)q2 >> 32);
+        uint32_t pk[32];
+        pk[0] = pack_h2(x0, x1);
+        float carry = x2;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float s0, c0, s1, c1, s2, c2;
+            sincos_q(l0, h0, k, s0, c0);
+            sincos_q(l1, h1, k, s1, c1);
+            sincos_q(l2, h2, k, s2, c2);
+            pk[1 + 3 * k] = pack_h2(carry, s0);
+            pk[2 + 3 * k] = pack_h2(s1, s2);
+            pk[3 + 3 * k] = pack_h2(c0, c1);
+            carry = c2;
+        }
+        pk[31] = pack_h2(carry, 0.f);
+        const int nrows = min(32, P - j0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t a = sbase + (uint32_t)(lane * 128 + (((c ^ lane) & 7) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                         "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+        }
+        if (big) encode_row_slow_f16(x0, x1, x2, sbase + (uint32_t)(lane * 128), lane);
+        __syncwarp();
+        uint4* dst = reinterpret_cast<uint4*>(out_bf + (row0 + j0) * 64);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int idx = it * 32 + lane, row = idx >> 3, c = idx & 7;
+            if (row < nrows) {
+                uint4 v;
+                const uint32_t a = sbase + (uint32_t)(row * 128 + (((c ^ row) & 7) << 4));
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+                dst[idx] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void encode_ray(const float o0, const float o1, const float o2, const float d0,
                                            const float d1, const float d2, const float* zs, int P, int64_t row0,
                                            float* __restrict__ out_enc, __half* __restrict__ out_bf,
@@ -153,20 +247,46 @@ __device__ __forceinline__ void encode_ray(const float o0, const float o1, const
     else encode_ray_t<false, true>(o0, o1, o2, d0, d1, d2, zs, P, row0, out_enc, out_bf, stage, lane);
 }
 
+// out[i + #{b (<|<=) a[i]}] = a[i] for every element of the ascending list a: one half of a stable merge by rank.
+// Each lane runs RB binary searches at once with a fixed step count (bit_length(nb) probes close any interval of [0, nb]):
+// the probes of one search form a dependent chain of shared-memory loads (~45 cycles per step), and ncu had put half of
+// the resampling kernel's stall samples on the three one-search-at-a-time `while (lo < hi)` loops of this file.
+#define RB 4
+template <bool LE>
+__device__ __forceinline__ void rank_scatter(const float* a, int na, const float* b, int nb, float* out, int lane) {
+    const int steps = 32 - __clz(nb);
+    for (int base = 0; base < na; base += 32 * RB) {
+        float v[RB];
+        int lo[RB], hi[RB];
+#pragma unroll
+        for (int e = 0; e < RB; ++e) {
+            const int i = base + 32 * e + lane;
+            v[e] = a[i < na ? i : na - 1];
+            lo[e] = 0;
+            hi[e] = i < na ? nb : 0;
+        }
+        for (int s = 0; s < steps; ++s) {
+#pragma unroll
+            for (int e = 0; e < RB; ++e) {
+                const bool act = lo[e] < hi[e];
+                const int m = (lo[e] + hi[e]) >> 1;
+                const float bv = b[act ? m : 0];
+                const bool right = LE ? (bv <= v[e]) : (bv < v[e]);
+                if (act) { if (right) lo[e] = m + 1; else hi[e] = m; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < RB; ++e) {
+            const int i = base + 32 * e + lane;
+            if (i < na) out[i + lo[e]] = v[e];
+        }
+    }
+}
+
 // stable merge of two ascending lists a (na) and b (nb) into out (na+nb); ties: a first (torch.sort of cat([a,b]))
 __device__ __forceinline__ void rank_merge(const float* a, int na, const float* b, int nb, float* out, int lane) {
-    for (int i = lane; i < na; i += 32) {
-        const float v = a[i];
-        int lo = 0, hi = nb;                  // count of b < v
-        while (lo < hi) { int m = (lo + hi) >> 1; if (b[m] < v) lo = m + 1; else hi = m; }
-        out[i + lo] = v;
-    }
-    for (int j = lane; j < nb; j += 32) {
-        const float v = b[j];
-        int lo = 0, hi = na;                  // count of a <= v
-        while (lo < hi) { int m = (lo + hi) >> 1; if (a[m] <= v) lo = m + 1; else hi = m; }
-        out[j + lo] = v;
-    }
+    rank_scatter<false>(a, na, b, nb, out, lane);         // a[i] lands after the b's that are <  it
+    rank_scatter<true>(b, nb, a, na, out, lane);          // b[j] lands after the a's that are <= it
 }
 
 __device__ __forceinline__ void bitonic_sort_smem(float* s, int npad, int lane) {
@@ -259,19 +379,42 @@ __device__ __forceinline__ void inverse_cdf(const float* bins, float* cdf, const
         carry = __shfl_sync(FULL_MASK, v, 31);
     }
     __syncwarp();
-    for (int j = lane; j < NiPad; j += 32) {
-        float out = INFINITY;
-        if (j < Ni) {
-            const float uu = u[j];
-            int lo = 0, hi = nb;            // searchsorted(cdf, u, right=True)
-            while (lo < hi) { int m = (lo + hi) >> 1; if (cdf[m] <= uu) lo = m + 1; else hi = m; }
-            const int below = max(lo - 1, 0), above = min(lo, nb - 1);
-            float denom = __fsub_rn(cdf[above], cdf[below]);
-            if (denom < 1e-5f) denom = 1.f;
-            const float t = __fdiv_rn(__fsub_rn(uu, cdf[below]), denom);
-            out = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+    // searchsorted(cdf, u, right=True) (:380), RB samples per lane at a time (see rank_scatter)
+    const int steps = 32 - __clz(nb);
+    for (int base = 0; base < NiPad; base += 32 * RB) {
+        float uu[RB];
+        int lo[RB], hi[RB];
+#pragma unroll
+        for (int e = 0; e < RB; ++e) {
+            const int j = base + 32 * e + lane;
+            uu[e] = j < Ni ? u[j] : 0.f;
+            lo[e] = 0;
+            hi[e] = j < Ni ? nb : 0;
         }
-        zs[j] = out;
+        for (int s = 0; s < steps; ++s) {
+#pragma unroll
+            for (int e = 0; e < RB; ++e) {
+                const bool act = lo[e] < hi[e];
+                const int m = (lo[e] + hi[e]) >> 1;
+                const bool right = cdf[act ? m : 0] <= uu[e];
+                if (act) { if (right) lo[e] = m + 1; else hi[e] = m; }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < RB; ++e) {
+            const int j = base + 32 * e + lane;
+            if (j >= NiPad) continue;
+            float out = INFINITY;
+            if (j < Ni) {
+                const int below = max(lo[e] - 1, 0), above = min(lo[e], nb - 1);
+                const float cb = cdf[below], bb = bins[below];
+                float denom = __fsub_rn(cdf[above], cb);
+                if (denom < 1e-5f) denom = 1.f;
+                const float t = __fdiv_rn(__fsub_rn(uu[e], cb), denom);
+                out = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(bins[above], bb)));
+            }
+            zs[j] = out;
+        }
     }
     __syncwarp();
 }
@@ -292,7 +435,9 @@ __global__ void k_sample_pdf(const float* __restrict__ bins_g, const float* __re
     }
 }
 
-__global__ void __launch_bounds__(256, 2) k_sample_encode_coarse(const float* __restrict__ rays, int ld, int64_t n, int near_col, int far_col,
+// LIGHT: fp16 rows only (out_enc == nullptr, out_bf != nullptr) -> encode_ray_f16, four CTAs per SM
+template <bool LIGHT>
+__global__ void __launch_bounds__(256, LIGHT ? 4 : 2) k_sample_encode_coarse(const float* __restrict__ rays, int ld, int64_t n, int near_col, int far_col,
                                        int cnear_col, int cfar_col, const float* __restrict__ steps_a, int n_a,
                                        const float* __restrict__ steps_b, int n_b, int use_disp, float perturb,
                                        const float* __restrict__ U, float* __restrict__ out_z,
@@ -343,13 +488,15 @@ __global__ void __launch_bounds__(256, 2) k_sample_encode_coarse(const float* __
             __syncwarp();
         }
         for (int i = lane; i < S; i += 32) out_z[r * S + i] = za[i];
-        if (out_enc || out_bf)
+        if (LIGHT) encode_ray_f16(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], za, S, r * S, out_bf, stage, lane);
+        else if (out_enc || out_bf)
             encode_ray(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], za, S, r * S, out_enc, out_bf, stage, lane);
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(256, 2) k_sample_encode_fine(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ z,
+template <bool LIGHT>
+__global__ void __launch_bounds__(256, LIGHT ? 4 : 2) k_sample_encode_fine(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ z,
                                      const float* __restrict__ w, int S, const float* __restrict__ u, int u_ld, int Ni,
                                      int NiPad, float* __restrict__ out_z, float* __restrict__ out_enc,
                                      __half* __restrict__ out_bf, int stage_f) {
@@ -379,7 +526,8 @@ __global__ void __launch_bounds__(256, 2) k_sample_encode_fine(const float* __re
         __syncwarp();
         for (int i = lane; i < F; i += 32) out_z[r * F + i] = zo[i];
         const float* ray = rays + r * ld;
-        if (out_enc || out_bf)
+        if (LIGHT) encode_ray_f16(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], zo, F, r * F, out_bf, stage, lane);
+        else if (out_enc || out_bf)
             encode_ray(ray[0], ray[1], ray[2], ray[3], ray[4], ray[5], zo, F, r * F, out_enc, out_bf, stage, lane);
         __syncwarp();
     }
@@ -439,14 +587,16 @@ extern "C" int pcnerf_sample_encode_coarse(const float* rays, int ld, int64_t n,
     int rc = pick_warps(per_warp, "sample_encode_coarse", &wpb);
     if (rc) return rc;
     const size_t smem = per_warp * wpb;
+    const bool light = !out_enc && out_enc_f16;
     if (smem > 48 * 1024)
-        PCN_CUDA(cudaFuncSetAttribute(k_sample_encode_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCN_CUDA(cudaFuncSetAttribute(light ? k_sample_encode_coarse<true> : k_sample_encode_coarse<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = pcn_cdiv(n, wpb);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
     PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
                 (double)n * (60.0 + S * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_f16 ? 128.0 : 0.0))));
-    k_sample_encode_coarse<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+    (light ? k_sample_encode_coarse<true> : k_sample_encode_coarse<false>)<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
         rays, ld, n, near_col, far_col, cnear_col, cfar_col, steps_a, n_a, steps_b, n_b, use_disp, perturb, U, out_z,
         out_enc, (__half*)out_enc_f16, stage_f);
     PCN_LAUNCH_CHECK();
@@ -466,14 +616,16 @@ extern "C" int pcnerf_sample_encode_fine(const float* rays, int ld, int64_t n, c
     int rc = pick_warps(per_warp, "sample_encode_fine", &wpb);
     if (rc) return rc;
     const size_t smem = per_warp * wpb;
+    const bool light = !out_enc && out_enc_f16;
     if (smem > 48 * 1024)
-        PCN_CUDA(cudaFuncSetAttribute(k_sample_encode_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCN_CUDA(cudaFuncSetAttribute(light ? k_sample_encode_fine<true> : k_sample_encode_fine<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = pcn_cdiv(n, wpb);
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
     PcnScope ps(PCN_K_SAMPLE_ENCODE, (cudaStream_t)stream,
                 (double)n * (60.0 + 8.0 * S + (S + Ni) * (4.0 + (out_enc ? 256.0 : 0.0) + (out_enc_f16 ? 128.0 : 0.0))));
-    k_sample_encode_fine<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+    (light ? k_sample_encode_fine<true> : k_sample_encode_fine<false>)<<<(int)grid, wpb * 32, smem, (cudaStream_t)stream>>>(
         rays, ld, n, z, w, S, u, u_ld, Ni, NiPad, out_z, out_enc, (__half*)out_enc_f16, stage_f);
     PCN_LAUNCH_CHECK();
     return 0;
