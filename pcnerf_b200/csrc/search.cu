@@ -41,10 +41,12 @@ __global__ void k_search_rows(const float* __restrict__ p, const float* __restri
                               GaussK gk, float* __restrict__ w, float* __restrict__ depth,
                               uint8_t* __restrict__ peak_in, float* __restrict__ wsum_child,
                               double* __restrict__ sums) {
-    extern __shared__ float smf[];
+    extern __shared__ double smd[];
     __shared__ double red[8];
     const int lane = threadIdx.x & 31, wib = warp_in_block(), wpb = blockDim.x >> 5;
-    float* sz = smf + (size_t)wib * 2 * P;
+    // per warp: the weights as doubles with GAUSS_R reflected samples on either side | z | w
+    double* sd = smd + (size_t)wib * (2 * P + 2 * GAUSS_R);
+    float* sz = reinterpret_cast<float*>(sd + P + 2 * GAUSS_R);
     float* sw = sz + P;
     double acc_op = 0;
     for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
@@ -82,15 +84,19 @@ __global__ void k_search_rows(const float* __restrict__ p, const float* __restri
         const float cn = rays[r * ld + cnear_col], cf = rays[r * ld + cfar_col];
         const MaskBounds b = strict_bounds(sz, P, cn, cf, lane);
         // Gaussian smoothing + first-max argmax (render.py:303-308)
+        // The 'reflect' extension is materialised once per row (fp32 -> fp64 once per sample as well): the 41-tap loop
+        // is then 2 loads + 3 fp64 operations per tap pair, same operands in the same order, instead of two integer
+        // modulo reductions and two conversions per tap pair.
+        for (int i = lane; i < P + 2 * GAUSS_R; i += 32) sd[i] = (double)sw[reflect_idx(i - GAUSS_R, P)];
+        __syncwarp();
         float best = -INFINITY;
         int besti = 0x7fffffff;
         for (int i = lane; i < P; i += 32) {
-            double t = __dmul_rn((double)sw[i], gk.k[GAUSS_R]);
-            for (int j = -GAUSS_R; j < 0; ++j) {
-                const double a = (double)sw[reflect_idx(i + j, P)];
-                const double c = (double)sw[reflect_idx(i - j, P)];
-                t = __dadd_rn(t, __dmul_rn(__dadd_rn(a, c), gk.k[j + GAUSS_R]));
-            }
+            const double* c0 = sd + GAUSS_R + i;
+            double t = __dmul_rn(c0[0], gk.k[GAUSS_R]);
+#pragma unroll
+            for (int j = -GAUSS_R; j < 0; ++j)
+                t = __dadd_rn(t, __dmul_rn(__dadd_rn(c0[j], c0[-j]), gk.k[j + GAUSS_R]));
             const float s = (float)t;
             if (s > best) { best = s; besti = i; }   // ascending i per lane -> keeps the first maximum
         }
@@ -205,7 +211,7 @@ extern "C" int pcnerf_search_rows(const float* p, const float* z, const float* r
         0x1.46d39dcd3d08cp-4};
     GaussK gk;
     for (int j = 0; j <= GAUSS_R; ++j) gk.k[j] = kGauss[j];
-    const size_t per_warp = (size_t)2 * P * sizeof(float);
+    const size_t per_warp = (size_t)(2 * P + 2 * GAUSS_R) * sizeof(double);    // (P + 2R) doubles + 2P floats
     int wpb = (int)(SRCH_MAX_SMEM / per_warp);
     if (wpb < 1) {
         pcn_set_error("search_rows: %d samples per row exceed the shared-memory budget", P);
