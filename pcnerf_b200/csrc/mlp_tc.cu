@@ -679,18 +679,39 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
             mbar_wait(bar_tfull, 0, 13);
             tc_fence_after();
-            for (int h = 0; h < ((g.debug & 4) ? 0 : 2); ++h) {
-                const int m = h * 128 + q * 32 + lane;
-                for (int c = half; c < (N >> 5); c += 2) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * N + c * 32), r);
-                    float* dst = g.out + (size_t)m * g.ldo + g.col_off + c * 32;
+            // Split-K reduction: 148 CTAs add their 256 x N fp32 partial into `out` with vector atomics -- 2.4 M 16-byte
+            // reductions per launch, all at kernel exit, bound by the L2's atomic units (timing experiment: 4.4 of the
+            // 18 ms/step of this kernel class).  (a) Lane pairs swap half of their chunks so that the two lanes of a pair
+            // write ADJACENT 16-byte chunks of one row (one 32-byte sector per pair instead of two); (b) every CTA starts at
+            // a different (h, c) block so that the CTAs do not walk the same addresses in lockstep.
+            const int ncw = (N >> 5) >> 1;                              // 32-column blocks per epilogue warp and h: 4 or 1
+            const int nblk = (g.debug & 4) ? 0 : 2 * ncw;
+            const bool odd = lane & 1;
+            for (int t0 = 0; t0 < nblk; ++t0) {
+                const int tt = (t0 + (int)blockIdx.x) % nblk;
+                const int h = tt / ncw, c = half + 2 * (tt % ncw);
+                const int m_even = h * 128 + q * 32 + (lane & ~1), m_odd = m_even + 1;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * N + c * 32), r);
+                float* base = g.out + g.col_off + c * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
-                                     "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                                     "f"(__uint_as_float(r[j + 3]))
-                                     : "memory");
+                for (int t = 0; t < 4; ++t) {
+                    // even lane keeps chunk 2t of its row and sends chunk 2t+1; odd lane keeps 2t+1 and sends 2t
+                    float keep[4], recv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float lo = __uint_as_float(r[8 * t + i]), hi = __uint_as_float(r[8 * t + 4 + i]);
+                        keep[i] = odd ? hi : lo;
+                        recv[i] = __shfl_xor_sync(FULL_MASK, odd ? lo : hi, 1);
+                    }
+                    float* d0 = base + (size_t)m_even * g.ldo + (2 * t + (odd ? 1 : 0)) * 4;   // row of the even lane
+                    float* d1 = base + (size_t)m_odd * g.ldo + (2 * t + (odd ? 1 : 0)) * 4;    // row of the odd lane
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d0), "f"(odd ? recv[0] : keep[0]),
+                                 "f"(odd ? recv[1] : keep[1]), "f"(odd ? recv[2] : keep[2]), "f"(odd ? recv[3] : keep[3])
+                                 : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d1), "f"(odd ? keep[0] : recv[0]),
+                                 "f"(odd ? keep[1] : recv[1]), "f"(odd ? keep[2] : recv[2]), "f"(odd ? keep[3] : recv[3])
+                                 : "memory");
                 }
             }
         }
