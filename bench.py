@@ -387,22 +387,44 @@ def run_b200(a):
         # (rows,256) 16-bit activations, layer 0 reads the (rows,64) encoding, layer 4 reads both
         esz = 2 if a.precision == "tc" else 4
         alg_bytes = CHUNK * esz * (7 * 256 + 2 * 64 + 8 * 256) / 8.0 if a.precision in ("tc", "fp32") else 0
-        roofline = {"kernel": "mlp forward row GEMM (%s)" % ("k_tc_rowgemm<FWD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32"),
-                    "bound": "tensor", "achieved": achieved, "peak": peak,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                    "launches_per_step": f_n / psteps, "us_per_launch": 1e3 * f_ms / max(f_n, 1),
-                    "gflop_per_launch": f_fl / max(f_n, 1) / 1e9, "share_of_step": f_ms / all_ms,
-                    # the layered GEMM moves one activation matrix in and one out per layer (train-mode BN needs a
-                    # chunk-wide reduction between layers): its arithmetic intensity caps it below the tensor peak
-                    "hbm": ({"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes * f_n / (f_ms * 1e-3) / 1e9,
-                             "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)),
-                             "frac": alg_bytes * f_n / (f_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
-                             "attainable_tflops": (f_fl / max(f_n, 1)) / alg_bytes * float(peaks.get("hbm_gbs", 6650.0)) / 1e3}
-                            if alg_bytes else None),
-                    "all_mlp_gemms": {"achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
-                                      "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms > 0 else 0.0,
-                                      "share_of_step": g_ms / all_ms}}
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        kname = "mlp forward row GEMM (%s)" % ("k_tc_rowgemm<FWD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32")
+        tensor = {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                  "gflop_per_launch": f_fl / max(f_n, 1) / 1e9}
+        gemms = {"achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
+                 "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms > 0 else 0.0, "unit": "TFLOP/s",
+                 "share_of_step": g_ms / all_ms}
+        common = {"launches_per_step": f_n / psteps, "us_per_launch": 1e3 * f_ms / max(f_n, 1), "share_of_step": f_ms / all_ms}
+        if a.precision == "tc" and alg_bytes:
+            # The layered GEMM moves one 16-bit activation matrix in and one out per layer (train-mode BN needs a chunk-wide
+            # reduction between layers): 124 FLOP/byte against a machine balance of 210 -> the roofline that bounds it is HBM
+            # (attainable = intensity x bandwidth, below the tensor peak).  The tensor-pipe view is kept beside it.
+            gbs = alg_bytes * f_n / (f_ms * 1e-3) / 1e9
+            tensor["attainable_tflops"] = (f_fl / max(f_n, 1)) / alg_bytes * hbm_peak / 1e3
+            # the other two GEMM classes by the same rule (bytes per launch)
+            d_ms, d_n, _ = prof["mlp_gemm_dgrad"]
+            w_ms, w_n, _ = prof["mlp_gemm_wgrad"]
+            d_bytes = d_n * CHUNK * 512.0 * 3                         # DH_l in, H_{l-1} in (BN backward), DH_{l-1} out
+            w_bytes = (w_n / 9.0) * CHUNK * (7 * 1024.0 + 2 * 640.0)  # per chunk: 7 launches on H (256 wide), 2 on the encoding
+            for k, ms_k, by in (("mlp_gemm_fwd", f_ms, alg_bytes * f_n), ("mlp_gemm_dgrad", d_ms, d_bytes),
+                                ("mlp_gemm_wgrad", w_ms, w_bytes)):
+                if ms_k > 0:
+                    kernels[k]["algorithmic_gbs"] = by / (ms_k * 1e-3) / 1e9
+                    kernels[k]["hbm_frac"] = kernels[k]["algorithmic_gbs"] / hbm_peak
+            gemms["hbm_frac"] = (alg_bytes * f_n + d_bytes + w_bytes) / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms > 0 else 0.0
+            roofline = dict({"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                             "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
+                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "intensity_flop_per_byte": (f_fl / max(f_n, 1)) / alg_bytes,
+                             "machine_balance_flop_per_byte": peak * 1e3 / hbm_peak,
+                             "tensor": tensor, "all_mlp_gemms": gemms}, **common)
+        else:
+            roofline = dict({"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak,
+                             "peak_source": tensor["peak_source"], "unit": "TFLOP/s", "frac": achieved / peak,
+                             "traffic": traffic, "gflop_per_launch": tensor["gflop_per_launch"],
+                             "all_mlp_gemms": gemms}, **common)
 
     out = {"metric": METRIC, "value": rays_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
