@@ -247,7 +247,10 @@ int pcnerf_tc_get_fused_eval(void);
 /* p, z (n,P).  rays (n,ld): child near/far in columns cnear_col/cfar_col, range reading in range_col.
  * noise (n,P) or NULL is added as noise*noise_std before normalisation.
  * Outputs: w (n,P); depth (n); per_ray (n,8) f32 = {free_r, dhat_r, sl1_child_r, C_r, lo0, hi0, lo2, hi2};
- * sums (4) f64 = {sum free_r, sum sl1_child_r, sum opacity terms, unused} (zeroed by the call). */
+ * sums (4) f64 = {sum free_r, sum sl1_child_r, sum opacity terms, unused} (zeroed by the call).
+ * P = 64 / 128 / 192 / 384 with 16-byte aligned p / z / w / noise / per_ray take the register-resident kernels; any other P
+ * or alignment takes the generic kernels. Both
+ * forms evaluate the same formulas; products and sums are associated differently (ulp-level differences). */
 int pcnerf_composite_fwd(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
                          int cnear_col, int cfar_col, int range_col, const float* noise, float noise_std,
                          float epsilon, int flags, float* w, float* depth, float* per_ray, double* sums,
