@@ -295,3 +295,66 @@ def test_fused_encode_extreme_coordinates():
     assert np.array_equal(np.isnan(got16), np.isnan(ref16))
     ulp = np.maximum(np.abs(ref[ok]), 2.0 ** -14) * 2.0 ** -10
     assert np.all(np.abs(got16[ok] - ref16[ok]) <= ulp + 1.5e-6)
+
+
+def _rows_agree(a16, b16):
+    """fp16 rows of the fp16-only kernels (MUFU on the exactly reduced argument) vs the fp16 rounding of the generic
+    kernels' fp32 rows (sincospif): same NaN pattern, within one fp16 ulp everywhere, different in < 5 % of the values."""
+    a, b = a16.float(), b16.float()
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    fin = torch.isfinite(b)
+    ulp = torch.clamp(b[fin].abs(), min=2.0 ** -14) * 2.0 ** -10
+    assert bool(((a[fin] - b[fin]).abs() <= ulp + 1.5e-6).all())
+    assert float((a[fin] != b[fin]).float().mean()) < 0.05
+
+
+def test_fp16_row_kernels_agree_with_the_generic_kernels():
+    """The fp16-only kernels (rows packed octave by octave, 64 registers) against the generic kernels asked for fp32 AND
+    fp16 rows in one launch, straight through the C ABI: z bit-identical, fp16 rows within one rounding, coarse and resample
+    pass, including rows with out-of-range / non-finite coordinates (scalar fallback of the fp16-only form)."""
+    from pcnerf_b200 import ops
+    n, S, Ni = 301, 57 + 7, 100
+    gen = torch.Generator().manual_seed(77)
+    rays = torch.zeros(n, 15)
+    rays[:, 0:3] = (torch.rand(n, 3, generator=gen) - 0.5) * 40.0
+    d = torch.randn(n, 3, generator=gen)
+    rays[:, 3:6] = d / d.norm(dim=1, keepdim=True)
+    rays[:, 6] = 0.5
+    rays[:, 7] = 20.0 + torch.rand(n, generator=gen) * 30.0
+    rng = 2.5 + torch.rand(n, generator=gen) * 15.0
+    rays[:, 10], rays[:, 11], rays[:, 14] = rng - 0.5, rng + 0.5, rng
+    rays[5, 0], rays[6, 1], rays[7, 2], rays[8, 0] = 3.0e7, float("nan"), float("inf"), -9.0e6
+    rays = rays.to(dev())
+    U = torch.rand((n, S), device=dev(), generator=torch.Generator(device=dev()).manual_seed(1))
+    u = torch.rand((n, Ni), device=dev(), generator=torch.Generator(device=dev()).manual_seed(2))
+    sa, sb = ops.linspace01(57, dev()), ops.linspace01(7, dev())
+    L, P_, st = ops.lib(), ops._p, ops._stream()
+
+    def coarse(both):
+        z = torch.empty((n, S), device=dev())
+        e32 = torch.empty((n * S, 64), device=dev()) if both else None
+        e16 = torch.empty((n * S, 64), dtype=torch.float16, device=dev())
+        ops.check(L.pcnerf_sample_encode_coarse(P_(rays), 15, n, 6, 7, 10, 11, P_(sa), 57, P_(sb), 7, 0, 1.0, P_(U),
+                                                P_(z), P_(e32), P_(e16), st))
+        return z, e16
+
+    z_a, e_a = coarse(False)
+    z_b, e_b = coarse(True)
+    assert torch.equal(z_a, z_b)
+    _rows_agree(e_a, e_b)
+    ok = torch.ones(n, dtype=torch.bool, device=dev())
+    ok[5:9] = False                                           # (their z is fine, their weights below are arbitrary)
+    w = torch.rand((n, S), device=dev(), generator=torch.Generator(device=dev()).manual_seed(3))
+
+    def fine(both):
+        zf = torch.empty((n, S + Ni), device=dev())
+        e32 = torch.empty((n * (S + Ni), 64), device=dev()) if both else None
+        e16 = torch.empty((n * (S + Ni), 64), dtype=torch.float16, device=dev())
+        ops.check(L.pcnerf_sample_encode_fine(P_(rays), 15, n, P_(z_a), P_(w), S, P_(u), Ni, Ni, P_(zf), P_(e32), P_(e16), st))
+        return zf, e16
+
+    f_a, g_a = fine(False)
+    f_b, g_b = fine(True)
+    assert torch.equal(f_a, f_b)
+    _rows_agree(g_a, g_b)
+    assert bool((f_a[ok][:, 1:] >= f_a[ok][:, :-1]).all())
