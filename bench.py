@@ -14,6 +14,9 @@ importance samples, render_rays_train's own default), ~200 
 
 `value`  : rays/s with the raw returns already resident in HBM.
 `e2e`    : the same step driven from pinned HOST buffers (H2D of the returns, D2H of the loss) every step.
+`roofline`: the dominant kernel (forward row GEMM of the layered training MLP) against the roofline that bounds it -- HBM at
+its 124 FLOP per algorithmic byte (machine balance 210) -- with the tensor-pipe view in `roofline.tensor`; `kernels`: device
+time per kernel class and step, with the HBM fraction of every class that has a byte model (DESIGN.md sections 4, 5).
 `--impl reference`: the CPU restatement of the reference path (oracle/, kind "port") on a bounded sample of the same
 workload with all host threads -- the reference itself is Python that imports from /root/reference and cannot
 travel to the GPU box.
