@@ -237,6 +237,14 @@ int pcnerf_mlp_tc_backward_chunks(const pcnerf_mlp_params* h_params, const pcner
 void pcnerf_tc_set_fused_eval(int on);
 int pcnerf_tc_get_fused_eval(void);
 
+/* Training-mode row GEMMs (forward and data gradient of every Linear, pcnerf_tc_rowgemm and the precision-1 MLP passes).
+ * Process-wide switch: 0 (default) = one CTA per SM, the two CTAs of a pair split the 256 output columns of a row tile;
+ * 1 = clusters of two CTAs (tcgen05.mma.cta_group::2, M = 256): the pair splits the ROWS, every A tile is loaded once.
+ * Same results up to fp32 summation order in the column statistics; measured at parity (csrc/mlp_tc.cu, k_tc_rowgemm2).
+ * Initial value: environment variable PCNERF_TC_PAIRS. */
+void pcnerf_tc_set_row_pairs(int on);
+int pcnerf_tc_get_row_pairs(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K4  compositing + losses (nof/render.py:51-61, :75-161, :13-36, :166-226; train_kitti.py:145-146).
  * ---------------------------------------------------------------------------------------------------------- */

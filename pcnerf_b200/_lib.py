@@ -62,6 +62,8 @@ SIGNATURES = {
     "pcnerf_mlp_tc_backward_chunks": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, i64, i64, vp, vp, vp, vp, ci, vp]),
     "pcnerf_tc_set_fused_eval": (None, [ci]),
     "pcnerf_tc_get_fused_eval": (ci, []),
+    "pcnerf_tc_set_row_pairs": (None, [ci]),
+    "pcnerf_tc_get_row_pairs": (ci, []),
     "pcnerf_composite_fwd": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, ci, vp, f32, f32, ci, vp, vp, vp, vp, vp]),
     "pcnerf_composite_losses": (ci, [vp, i64, vp, vp]),
     "pcnerf_composite_bwd": (ci, [vp, vp, vp, vp, ci, i64, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, vp, vp]),

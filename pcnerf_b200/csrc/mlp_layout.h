@@ -43,7 +43,7 @@ struct MlpLayout {
         o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
         off_hf[0] = off_hf[1] = off_encb = o;      // (unused since the weight-gradient kernel converts in shared memory)
         off_rgwork = o;                            // row-GEMM CTA counter + per-CTA statistic partials (precision 1)
-        if (precision == 1) o += al256(256 + 160 * 2 * 128 * 8);
+        if (precision == 1) o += al256(256 + 160 * 2 * 256 * 8);
         off_gvec = o; o += al256((size_t)rows * 4);
         for (int i = 0; i < 2; ++i) { off_g[i] = o; o += al256((size_t)rows * 256 * esz); }
         scratch_bytes = o;

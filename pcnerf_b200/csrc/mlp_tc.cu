@@ -799,6 +799,317 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_tc_rowgemm on CTA PAIRS (cta_group::2): C[rows,256] = A[rows,K] * B[256,K]^T, same epilogues as k_tc_rowgemm.
+//
+// Why: timing experiments on the single-CTA form (profiles/README.md, v13) put its floor at ~55 us per 262,144-row launch
+// = 2 us per tile, four times the tile's MMA time, with nothing saturated: the kernel is bound by the UNIQUE bytes it keeps
+// in flight.  There both CTAs of a column-split pair stream the SAME A tiles (the second read is an L2 hit), so half of
+// every ring is a duplicate.  Here the pair splits the M dimension instead: a unit of work is two row tiles, CTA `rank`
+// loads only ITS 128 rows of A (every ring byte is unique, L2 -> SM traffic halves), each CTA keeps half of the weight
+// rows resident (128 x K, as before), and the leader issues one M = 256, N = 256 MMA per 16 k for both SMs.  Each CTA's
+// accumulator is its 128 rows x 256 columns (two stages = all 512 TMEM columns); its eight epilogue warps take 128
+// columns each, in two rounds of 64 through the same staging buffers.
+// Protocol = the one of k_tc_fused_eval<2>: TMA loads of either CTA complete on the LEADER's full barrier, commits are
+// multicast to the same barrier offset in both CTAs, the sixteen epilogue warps report to the leader's tempty barrier.
+// Selected by pcnerf_tc_set_row_pairs(1) / PCNERF_TC_PAIRS=1; NOT the default: parity-tested (tests/test_gpu_tc.py runs the
+// GEMM and MLP checks in both forms) but measured SLOWER.  Same box, C2 step, class times per step (weight-gradient class
+// 16.66 ms in both runs): k_tc_rowgemm forward 16.4 / data gradient 19.3 ms, step 56.5 ms at 1.65 GHz; this kernel 18.5 /
+// 22.9 ms, step 59.9 ms at 1.77 GHz (the first version, which held the TMEM stage through round 0's stores and
+// statistics, 19.0 / 20.8).  Halving the L2 -> SM traffic and doubling the unique bytes in flight does not shorten the
+// ~2 us per tile -- neither is what bounds the row GEMMs; the per-CTA epilogue (two serial 64-column rounds per tile, 168
+// registers) now sets the pace.  The SM clock under the power cap rises (less energy per step), which is why the form is
+// kept as a starting point for round 2.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                                     uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
+#define TC_L2_EVICT_NORMAL 0x1000000000000000ull
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const RowGemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[24];            // full[8] | empty[8] | bfull | tfull[2] | tempty[2]
+    __shared__ uint32_t tmem_slot;
+    __shared__ unsigned int s_last;
+    __shared__ __align__(16) float cvec[(EPI == TC_FWD ? 1 : 3) * 256];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nstage = g.nstage, KB = g.kb_total;
+    uint8_t* sB = smem;                                   // KB x 16 KB: this CTA's 128 weight rows, resident
+    uint8_t* sA = sB + (size_t)KB * TC_B_BYTES;           // nstage x 16 KB ring: this CTA's 128 rows of A
+    uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 warps x TC_NBUF x TC_STAGE_BYTES
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
+    const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
+    const int rank = (int)cluster_ctarank();              // 0 = the pair's leader
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_bfull, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 16); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
+    if (EPI == TC_FWD) {
+        for (int i = threadIdx.x; i < 256; i += TC_THREADS) cvec[i] = g.vec[i];
+    } else {
+        for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+            const float c0 = g.vec[i], c1 = g.vec[256 + i], c2 = g.vec[512 + i], mean = g.vec[768 + i];
+            cvec[i] = c0;
+            cvec[256 + i] = c2;
+            cvec[512 + i] = c2 * mean - c1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int ntiles = (g.rows + 127) >> 7, nunits = (ntiles + 1) >> 1;
+    const TilePlan tp = tile_plan(g.sched, nunits, blockIdx.x >> 1, gridDim.x >> 1);   // in units of two row tiles
+    const uint64_t pol = g.hint ? TC_L2_EVICT_FIRST : TC_L2_EVICT_NORMAL;
+
+    if (warp == 0) {
+        // ===== TMA producer (one per CTA: its own rows of A, its own half of B)
+        if (lane == 0) {
+            if (rank == 0) mbar_expect_tx(bar_bfull, 2u * (uint32_t)KB * TC_B_BYTES);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d_2sm_hint(smem_u32(sB + (size_t)kb * TC_B_BYTES), &tmB, bar_bfull & TC_PEER_MASK, kb * 64,
+                                     rank * TC_NCTA, TC_L2_EVICT_NORMAL);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < tp.count; ++it) {
+                const int tile = (tp.first + it * tp.step) * 2 + rank;     // rows past the end read as zero
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait_spin(bar_empty + 8 * s, ph ^ 1, 31);
+                    if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * TC_A_BYTES);
+                    const CUtensorMap* m = kb < g.kb0 ? &tmA0 : &tmA1;
+                    const int c0 = (kb < g.kb0 ? kb : kb - g.kb0) * 64;
+                    tma_load_2d_2sm_hint(smem_u32(sA + (size_t)s * TC_A_BYTES), m, (bar_full + 8 * s) & TC_PEER_MASK, c0,
+                                         tile * 128, pol);
+                    if (++s == nstage) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===== MMA issuer: the leader's, for both SMs
+        constexpr uint32_t idesc = (EPI == TC_FWD) ? make_idesc(0, 0, 0, 0, 256, 256) : make_idesc(1, 1, 0, 0, 256, 256);
+        mbar_wait_spin(bar_bfull, 0, 32);
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int it = 0; it < tp.count; ++it) {
+            mbar_wait_cluster(bar_tempty + 8 * as, aph ^ 1, 33);
+            tc_fence_after();
+            const uint32_t dcol = tmem_base + (uint32_t)as * 256;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait_spin(bar_full + 8 * s, ph, 34);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = smem_u32(sA + (size_t)s * TC_A_BYTES), b0 = smem_u32(sB + (size_t)kb * TC_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_2sm(dcol, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                     (uint32_t)((kb | k) != 0));
+                    umma_commit_2sm(bar_empty + 8 * s);
+                    if (kb == KB - 1) umma_commit_2sm(bar_tfull + 8 * as);
+                }
+                __syncwarp();
+                if (++s == nstage) { s = 0; ph ^= 1; }
+            }
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4 (rows q*32 + lane of THIS CTA's tile), 128-column half
+        // (warp-2)/4, in two rounds of 64 columns; per round the code of k_tc_rowgemm's epilogue.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF * TC_STAGE_BYTES);
+        const uint32_t bufs[2] = {buf0, buf0 + TC_STAGE_BYTES};
+        double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int as = 0;
+        uint32_t aph = 0;
+        uint4 e[2][4];
+        auto load_e = [&](int tile_, int cc_) {
+            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_, cb_ = half * 128 + cc_ * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (lane >> 2) + 8 * i;
+                    e[c][i] = make_uint4(0, 0, 0, 0);
+                    if (row < left_)
+                        e[c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + cb_ + c * 32 + (lane & 3) * 8);
+                }
+        };
+        if (EPI == TC_DGRAD && tp.count > 0) load_e(tp.first * 2 + rank, 0);
+        for (int it = 0; it < tp.count; ++it) {
+            const int tile = (tp.first + it * tp.step) * 2 + rank;
+            mbar_wait_spin(bar_tfull + 8 * as, aph, 35);
+            tc_fence_after();
+            const int row0 = tile * 128 + q * 32;
+            const bool valid = row0 + lane < g.rows;
+            // ---- phase A: both 64-column rounds of the accumulator -> packed 16-bit registers, then the TMEM stage goes
+            //      straight back to the MMA warp (with the stage held through round 0's stores and statistics the pair form
+            //      was measured SLOWER than the single-CTA kernel: the leader stalled on tempty)
+            uint32_t pk[2][2][16];
+            if (EPI == TC_DGRAD) {
+                if (lane == 0) tma_store_wait_read<0>();      // the previous tile's stores have read the staging buffers
+                __syncwarp();
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int colb = half * 128 + cc * 64;            // first output column of this round
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + colb);
+                uint32_t r[2][32];
+                if (EPI == TC_DGRAD) {
+                    // this thread's row of H_{l-1}: staged through the (currently idle) output buffers, re-read row-wise
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sts128(stage_addr(bufs[c], (lane >> 2) + 8 * i, lane & 3), e[c][i]);
+                    __syncwarp();
+                    if (cc == 0) load_e(tile, 1);
+                }
+                tmem_ld32_issue(tbase, r[0]);
+                tmem_ld32_issue(tbase + 32, r[1]);
+                tmem_ld_wait();
+                if (cc == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * as);
+                }
+                if (EPI == TC_FWD) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(&cvec[colb + c * 32 + 4 * j4]);
+                            const float v0 = valid ? __uint_as_float(r[c][4 * j4 + 0]) + b4.x : 0.f;
+                            const float v1 = valid ? __uint_as_float(r[c][4 * j4 + 1]) + b4.y : 0.f;
+                            const float v2 = valid ? __uint_as_float(r[c][4 * j4 + 2]) + b4.z : 0.f;
+                            const float v3 = valid ? __uint_as_float(r[c][4 * j4 + 3]) + b4.w : 0.f;
+                            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                            pk[cc][c][2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
+                            pk[cc][c][2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint4 hv = lds128(stage_addr(bufs[c], lane, k));
+                            const __half2* hb = reinterpret_cast<const __half2*>(&hv);
+                            float hf[8];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 h2 = __half22float2(hb[t]);
+                                hf[2 * t] = h2.x;
+                                hf[2 * t + 1] = h2.y;
+                            }
+#pragma unroll
+                            for (int t4 = 0; t4 < 2; ++t4) {
+                                const int j = k * 8 + t4 * 4, col = colb + c * 32 + j;
+                                const float4 a0 = *reinterpret_cast<const float4*>(&cvec[col]);
+                                const float4 a2 = *reinterpret_cast<const float4*>(&cvec[256 + col]);
+                                const float4 ak = *reinterpret_cast<const float4*>(&cvec[512 + col]);
+                                const float v0 = valid ? fmaf(a0.x, __uint_as_float(r[c][j + 0]), fmaf(-a2.x, hf[t4 * 4 + 0], ak.x)) : 0.f;
+                                const float v1 = valid ? fmaf(a0.y, __uint_as_float(r[c][j + 1]), fmaf(-a2.y, hf[t4 * 4 + 1], ak.y)) : 0.f;
+                                const float v2 = valid ? fmaf(a0.z, __uint_as_float(r[c][j + 2]), fmaf(-a2.z, hf[t4 * 4 + 2], ak.z)) : 0.f;
+                                const float v3 = valid ? fmaf(a0.w, __uint_as_float(r[c][j + 3]), fmaf(-a2.w, hf[t4 * 4 + 3], ak.w)) : 0.f;
+                                const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+                                pk[cc][c][k * 4 + t4 * 2] = *reinterpret_cast<const uint32_t*>(&b01);
+                                pk[cc][c][k * 4 + t4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
+                            }
+                        }
+                    __syncwarp();                          // every lane has read its row of E: the buffers can be rewritten
+                }
+            }
+            if (EPI == TC_DGRAD && it + 1 < tp.count) load_e((tp.first + (it + 1) * tp.step) * 2 + rank, 0);
+            // ---- phase B: the two rounds leave through the staging buffers (TMA stores) and feed the column statistics
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int colb = half * 128 + cc * 64;
+                if (!(EPI == TC_DGRAD && cc == 0)) {
+                    if (lane == 0) tma_store_wait_read<0>();  // earlier stores have read both staging buffers
+                    __syncwarp();
+                }
+                stage_put_row(bufs[0], pk[cc][0], lane);
+                stage_put_row(bufs[1], pk[cc][1], lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !(g.debug & 2)) {
+                    tma_store_2d_nocommit(&tmO, bufs[0], colb, row0);
+                    tma_store_2d_nocommit(&tmO, bufs[1], colb + 32, row0);
+                    tma_store_commit();
+                }
+                if (!(g.debug & 1) && !g.nostat) {
+                    if (EPI == TC_FWD) {
+                        stage_col_sums<true, true>(bufs[0], lane, acc0 + 4 * cc, acc1 + 4 * cc);
+                        stage_col_sums<true, true>(bufs[1], lane, acc0 + 4 * cc + 2, acc1 + 4 * cc + 2);
+                    } else {
+                        stage_col_sums<false, false>(bufs[0], lane, acc0 + 4 * cc, acc1 + 4 * cc);
+                        stage_col_sums<false, false>(bufs[1], lane, acc0 + 4 * cc + 2, acc1 + 4 * cc + 2);
+                    }
+                }
+            }
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if (lane == 0) tma_store_wait_all();
+        // ---- column statistics: quadrant warps -> CTA partial (staging memory is free now) -> global per-CTA slot of 256
+        //      columns; the last CTA to arrive adds the slots up.
+        double* sred = reinterpret_cast<double*>(sStage);              // [2 stats][4 quadrants][256 columns] = 16 KB
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lane < 16) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int cl = half * 128 + cc * 64 + c * 32 + 2 * lane + j;
+                        sred[(0 * 4 + q) * 256 + cl] = acc0[4 * cc + 2 * c + j];
+                        sred[(1 * 4 + q) * 256 + cl] = acc1[4 * cc + 2 * c + j];
+                    }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int t = threadIdx.x - 64;                                 // 0..255 = column
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+            const double v = sred[(st * 4 + 0) * 256 + t] + sred[(st * 4 + 1) * 256 + t] + sred[(st * 4 + 2) * 256 + t] +
+                             sred[(st * 4 + 3) * 256 + t];
+            g.partials[((size_t)blockIdx.x * 2 + st) * 256 + t] = v;
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (t == 0) s_last = atomicAdd(g.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (s_last) {
+            __threadfence();
+            double a0 = 0.0, a1 = 0.0;
+            for (int b = 0; b < (int)gridDim.x; ++b) {
+                a0 += g.partials[((size_t)b * 2 + 0) * 256 + t];
+                if (EPI == TC_FWD) a1 += g.partials[((size_t)b * 2 + 1) * 256 + t];
+            }
+            g.stat0[t] = a0;
+            if (EPI == TC_FWD) g.stat1[t] = a1;
+            if (t == 0) *g.counter = 0;                                 // ready for the next launch on this stream
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                               // the peer may still be reading its accumulators
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
 #define FZ_STAGES 6
 #define FZ_BLK (128 * 128)       // 16 KB: 128 rows x 64 fp16 (one k-block of A, or one weight stage)
 
@@ -1157,6 +1468,13 @@ int tc_sched_mode() {
     return m;
 }
 
+// row GEMMs on CTA pairs (k_tc_rowgemm2): pcnerf_tc_set_row_pairs(1) or PCNERF_TC_PAIRS=1; default off (see the kernel)
+int g_row_pairs = -1;
+int tc_pairs_mode() {
+    if (g_row_pairs < 0) { const char* e = getenv("PCNERF_TC_PAIRS"); g_row_pairs = e ? (atoi(e) != 0) : 0; }
+    return g_row_pairs;
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -1170,7 +1488,7 @@ int sm_count() {
 // mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias), out2 bf16 copy;  TC_DGRAD: A bf16, B bf16 -> out bf16 (BN backward
 // fused: vec = c0|c1|c2|mean, E = fp16 H)
 // `work` = >= TC_ROWGEMM_WORK_BYTES of device memory: [0,4) CTA counter (zeroed here), then the per-CTA partials
-#define TC_ROWGEMM_WORK_BYTES (256 + 160 * 2 * 128 * 8)
+#define TC_ROWGEMM_WORK_BYTES (256 + 160 * 2 * 256 * 8)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
                    const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
                    double* stat1, void* work, int dir, cudaStream_t st, int nostat = 0) {
@@ -1214,6 +1532,34 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     const int ntiles = (int)pcn_cdiv(rows, 128);
     const int grid = 2 * ntiles < sm_count() ? 2 * ntiles : (sm_count() & ~1);
     const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
+    if (tc_pairs_mode()) {
+        // CTA pairs (k_tc_rowgemm2): clusters of two, a unit of work = two row tiles
+        const int nunits = (ntiles + 1) / 2;
+        const int ncl = nunits < sm_count() / 2 ? nunits : sm_count() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * ncl);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (mode == TC_FWD) {
+            PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PcnScope ps(PCN_K_GEMM_FWD, st, flops);
+            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD>, mA0, mA1, mB, mO, g));
+        } else {
+            PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PcnScope ps(PCN_K_GEMM_DGRAD, st, flops);
+            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_DGRAD>, mA0, mA1, mB, mO, g));
+        }
+        PCN_LAUNCH_CHECK();
+        return 0;
+    }
     if (mode == TC_FWD) {
         PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PcnScope ps(PCN_K_GEMM_FWD, st, flops);
@@ -1258,6 +1604,8 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
 static int g_fused_eval = 2;     // 0 = layered, 1 = fused (one CTA per unit), 2 = fused on CTA pairs (cta_group::2)
 extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on < 0 ? 0 : (on > 2 ? 2 : on); }
 extern "C" int pcnerf_tc_get_fused_eval(void) { return g_fused_eval; }
+extern "C" void pcnerf_tc_set_row_pairs(int on) { g_row_pairs = on ? 1 : 0; }
+extern "C" int pcnerf_tc_get_row_pairs(void) { return tc_pairs_mode(); }
 
 // ---- two BN batches (chunks) in flight: pcnerf_mlp_tc_{forward,backward}_chunks issue consecutive chunks on two internal
 // streams ("lanes").  The kernels of a chunk form a serial chain (GEMM -> fold -> GEMM ...) whose fixed costs -- prologue,

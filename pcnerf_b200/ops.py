@@ -341,6 +341,13 @@ def tc_fused_eval(on=None):
     return int(lib().pcnerf_tc_get_fused_eval())
 
 
+def tc_row_pairs(on=None):
+    """Get / set the training-mode row-GEMM form of the precision-1 MLP: 0 = one CTA per SM (default), 1 = CTA pairs."""
+    if on is not None:
+        lib().pcnerf_tc_set_row_pairs(int(on))
+    return int(lib().pcnerf_tc_get_row_pairs())
+
+
 class MLPFunction(torch.autograd.Function):
     """p = NOF(enc) evaluated chunk by chunk (one BN batch per chunk, nof/render.py:47-49)."""
 

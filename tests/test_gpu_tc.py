@@ -17,8 +17,18 @@ def _rand(shape, dt, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(dt).to(dev())
 
 
+@pytest.fixture(params=[0, 1], ids=["cta", "pairs"])
+def row_form(request):
+    """Both forms of the training-mode row GEMM: one CTA per SM (default) and CTA pairs (cta_group::2, k_tc_rowgemm2)."""
+    from pcnerf_b200 import ops
+    old = ops.tc_row_pairs()
+    ops.tc_row_pairs(request.param)
+    yield request.param
+    ops.tc_row_pairs(old)
+
+
 @pytest.mark.parametrize("rows,k0,k1", [(128, 64, 0), (128, 256, 0), (1000, 256, 0), (4096 + 77, 64, 256), (40000, 256, 0)])
-def test_rowgemm_forward_fp16(rows, k0, k1):
+def test_rowgemm_forward_fp16(rows, k0, k1, row_form):
     from pcnerf_b200 import ops
     A0 = _rand((rows, k0), torch.float16, 1)
     A1 = _rand((rows, k1), torch.float16, 2) if k1 else None
@@ -37,7 +47,7 @@ def test_rowgemm_forward_fp16(rows, k0, k1):
 
 
 @pytest.mark.parametrize("rows", [128, 300, 20000])
-def test_rowgemm_dgrad_bf16_fused_bn_backward(rows):
+def test_rowgemm_dgrad_bf16_fused_bn_backward(rows, row_form):
     from pcnerf_b200 import ops
     A = _rand((rows, 256), torch.bfloat16, 5)
     B = _rand((256, 256), torch.bfloat16, 6, 0.1)
@@ -81,7 +91,7 @@ def _enc(rows, seed):
 
 
 @pytest.mark.parametrize("rows,chunk", [(4096, 4096), (5000, 2048), (130, 130)])
-def test_mlp_forward_tc(rows, chunk):
+def test_mlp_forward_tc(rows, chunk, row_form):
     enc = _enc(rows, rows)
     sd = orc.init_state_dict(42)
     p_ref = torch.cat([orc.nof_forward(sd, enc[i:i + chunk], True) for i in range(0, rows, chunk)]).reshape(-1)
@@ -95,7 +105,7 @@ def test_mlp_forward_tc(rows, chunk):
 
 
 @pytest.mark.parametrize("rows,chunk", [(4096, 4096), (3000, 1024)])
-def test_mlp_backward_tc(rows, chunk):
+def test_mlp_backward_tc(rows, chunk, row_form):
     enc = _enc(rows, rows + 1)
     gen = torch.Generator().manual_seed(rows)
     gp = torch.randn(rows, generator=gen)
