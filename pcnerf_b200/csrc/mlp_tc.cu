@@ -79,6 +79,8 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, in
         }
     }
 }
+// (spin != 0: plain polling instead of the suspend-hinted wait -- PCNERF_TC_DEBUG & 8, timing experiments)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code, int spin);
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -89,6 +91,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int cod
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code, int spin) {
+    if (spin) mbar_wait_spin(bar, parity, code);
+    else mbar_wait(bar, parity, code);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -189,7 +195,7 @@ struct RowGemmArgs {
     double* partials;           // [gridDim.x][2][128] per-CTA column sums: no same-address fp64 atomics (296 adds per
                                 // address at kernel exit serialise in the L2 atomic unit)
     unsigned int* counter;      // zeroed by the caller; counts finished CTAs
-    int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores
+    int debug;                  // timing experiments only (PCNERF_TC_DEBUG): 1 = no statistics, 2 = no output stores, 8 = polling waits
     int sched;                  // row-tile order of a CTA pair: 0 interleaved (pair, pair + npairs, ...), 1 contiguous slab
                                 // walked upwards, 2 contiguous slab walked downwards (see tile_plan)
     int nostat;                 // 1: eval-mode BN (running statistics): the epilogue skips the column sums
@@ -360,7 +366,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         for (int it = 0; it < tp.count; ++it) {
             const int tile = tp.first + it * tp.step;
             for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(bar_empty + 8 * s, ph ^ 1, 1);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1, 1, g.debug & 8);
                 if (lane == 0) {
                     mbar_expect_tx(bar_full + 8 * s, TC_A_BYTES);
                     const CUtensorMap* m = kb < g.kb0 ? &tmA0 : &tmA1;
@@ -614,7 +620,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             int s = 0;
             uint32_t ph = 0;
             for (int kb = kb_beg; kb < kb_end; ++kb) {
-                mbar_wait(bar_empty + 8 * s, ph ^ 1, 11);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1, 11, g.debug & 8);
                 if (lane == 0) {
                     uint8_t* st = smem + (size_t)s * TC_WG_STAGE;
                     mbar_expect_tx(bar_full + 8 * s, (uint32_t)(4 + nboxB) * 8192);
@@ -630,7 +636,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             int s = 0;
             uint32_t ph = 0;
             for (int kb = kb_beg; kb < kb_end; ++kb) {
-                mbar_wait((g.convert_b ? bar_conv : bar_full) + 8 * s, ph, 12);
+                mbar_wait((g.convert_b ? bar_conv : bar_full) + 8 * s, ph, 12, g.debug & 8);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a0 = smem_u32(smem + (size_t)s * TC_WG_STAGE), b0 = a0 + 32768;
@@ -658,7 +664,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 int s = 0;
                 uint32_t ph = 0;
                 for (int kb = kb_beg; kb < kb_end; ++kb) {
-                    mbar_wait(bar_full + 8 * s, ph, 14);
+                    mbar_wait(bar_full + 8 * s, ph, 14, g.debug & 8);
                     const uint32_t b0 = smem_u32(smem + (size_t)s * TC_WG_STAGE) + 32768;
                     for (int i = t256; i < nch; i += 256) {
                         uint4 v = lds128(b0 + (uint32_t)i * 16);
