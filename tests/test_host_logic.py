@@ -76,3 +76,37 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config"):
         assert k in line
+
+
+def test_hoisted_reciprocal_division_matches_ieee_division():
+    """K4's `div_rc` (csrc/composite.cu): q = a * rc, two residual corrections q += fma(-d, q, a) * rc with
+    rc = RN(1 / d) hoisted out of the per-sample loop.  Exact emulation (rational arithmetic, one rounding per fp32
+    operation / FMA): the result equals the correctly rounded quotient RN(a / d) for operands in the range the weights
+    and normalisers of the compositing stage live in."""
+    from fractions import Fraction
+    import numpy as np
+
+    def rn(x):                                             # Fraction -> nearest float32, ties to even
+        c = np.float32(float(x))
+        best, bd = c, abs(Fraction(float(c)) - x)
+        for n in (np.nextafter(c, np.float32(-np.inf)), np.nextafter(c, np.float32(np.inf))):
+            dlt = abs(Fraction(float(n)) - x)
+            if dlt < bd or (dlt == bd and (n.view(np.uint32) & 1) == 0 and (best.view(np.uint32) & 1) == 1):
+                best, bd = n, dlt
+        return best
+
+    rng = np.random.default_rng(7)
+    a = (rng.random(4000) * 10.0 ** rng.uniform(-12, 0, 4000)).astype(np.float32)      # weights: 1e-12 .. 1
+    d = (rng.random(4000) * 0.999 + 0.001).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 2, 4000).astype(np.float32)
+    bad = 0
+    for ai, di in zip(a, d):
+        if ai == 0 or di == 0:
+            continue
+        A, D = Fraction(float(ai)), Fraction(float(di))
+        rc = Fraction(float(rn(1 / D)))
+        q = Fraction(float(rn(A * rc)))
+        for _ in range(2):
+            r = Fraction(float(rn(A - D * q)))             # fma(-d, q, a): exact product and sum, one rounding
+            q = Fraction(float(rn(q + r * rc)))            # fma(r, rc, q)
+        bad += (np.float32(float(q)) != rn(A / D))
+    assert bad == 0
