@@ -219,14 +219,20 @@ int pcnerf_tc_last_fault(void);
 
 /* All chunks (BN batches) of one pass of the precision-1 MLP in training mode, `lanes` (1 or 2) chunks in flight on
  * internal streams forked from / joined to `stream` (capturable in a CUDA graph).  Chunk c covers rows [c*chunk, ...) of
- * enc (rows,64) fp16; saved[c] >= pcnerf_mlp_saved_bytes(rows of chunk c, 1); scratch[k], k < lanes, >=
- * pcnerf_mlp_scratch_bytes(chunk, 1).  Results are bit-identical to calling pcnerf_mlp_forward / pcnerf_mlp_backward chunk
- * after chunk (nof/render.py:47-49): running statistics and gradient sums are updated in chunk order. */
+ * enc (rows,64) fp16; h_saved[c] holds h_saved_bytes[c] >= pcnerf_mlp_saved_bytes(rows of chunk c, 1) bytes; h_scratch[k],
+ * k < lanes, holds scratch_bytes >= pcnerf_mlp_scratch_bytes(min(chunk, rows), 1) bytes (h_*: host arrays of device
+ * pointers / sizes).  Every chunk is validated like a pcnerf_mlp_forward call BEFORE anything is launched: a training-mode
+ * chunk of exactly one row fails with torch's "Expected more than 1 value per channel" message (ValueError in the host
+ * mirror), oversized chunks and undersized buffers with PCNERF_ERR_ARG.  Results are bit-identical to calling
+ * pcnerf_mlp_forward / pcnerf_mlp_backward chunk after chunk (nof/render.py:47-49): running statistics and gradient sums
+ * are updated in chunk order. */
 int pcnerf_mlp_tc_forward_chunks(const pcnerf_mlp_params* h_params, const void* enc, int64_t rows, int64_t chunk,
-                                 float* out_p, void* const* saved, void* const* scratch, int lanes, void* stream);
+                                 float* out_p, void* const* h_saved, const size_t* h_saved_bytes, void* const* h_scratch,
+                                 size_t scratch_bytes, int lanes, void* stream);
 int pcnerf_mlp_tc_backward_chunks(const pcnerf_mlp_params* h_params, const pcnerf_mlp_grads* h_grads, const void* enc,
-                                  int64_t rows, int64_t chunk, const float* out_p, const float* grad_p, void* const* saved,
-                                  void* const* scratch, int lanes, void* stream);
+                                  int64_t rows, int64_t chunk, const float* out_p, const float* grad_p,
+                                  void* const* h_saved, const size_t* h_saved_bytes, void* const* h_scratch,
+                                  size_t scratch_bytes, int lanes, void* stream);
 
 /* Eval-mode (running-statistics) forward of the precision-1 MLP (replaces the per-chunk loop of nof/render.py:21-24 for
  * model.eval()).  Process-wide switch:

@@ -58,8 +58,9 @@ SIGNATURES = {
     "pcnerf_tc_rowgemm": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     "pcnerf_tc_wgrad": (ci, [vp, vp, ci, ci, ci, i64, vp, ci, ci, vp]),
     "pcnerf_tc_last_fault": (ci, []),
-    "pcnerf_mlp_tc_forward_chunks": (ci, [ctypes.POINTER(MlpParams), vp, i64, i64, vp, vp, vp, ci, vp]),
-    "pcnerf_mlp_tc_backward_chunks": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, i64, i64, vp, vp, vp, vp, ci, vp]),
+    "pcnerf_mlp_tc_forward_chunks": (ci, [ctypes.POINTER(MlpParams), vp, i64, i64, vp, vp, vp, vp, ctypes.c_size_t, ci, vp]),
+    "pcnerf_mlp_tc_backward_chunks": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, i64, i64, vp, vp, vp, vp,
+                                          vp, ctypes.c_size_t, ci, vp]),
     "pcnerf_tc_set_fused_eval": (None, [ci]),
     "pcnerf_tc_get_fused_eval": (ci, []),
     "pcnerf_tc_set_row_pairs": (None, [ci]),

@@ -1847,10 +1847,30 @@ int lanes_get(Lanes** out) {
 }  // namespace
 
 static int tc_chunks(bool backward, const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const void* enc, int64_t rows,
-                     int64_t chunk, float* out_p, const float* grad_p, void* const* saved, void* const* scratch, int lanes,
-                     cudaStream_t st) {
-    PCN_CHECK_ARG(P && P->precision == 1 && enc && out_p && saved && scratch && rows >= 1 && chunk >= 1 && (lanes == 1 || lanes == 2),
+                     int64_t chunk, float* out_p, const float* grad_p, void* const* saved, const size_t* saved_bytes,
+                     void* const* scratch, size_t scratch_bytes, int lanes, cudaStream_t st) {
+    PCN_CHECK_ARG(P && P->precision == 1 && enc && out_p && saved && saved_bytes && scratch && rows >= 1 && chunk >= 1 &&
+                      (lanes == 1 || lanes == 2),
                   "mlp_tc_chunks: bad arguments (precision 1, lanes 1 or 2)");
+    {
+        // the per-chunk checks of pcnerf_mlp_forward / pcnerf_mlp_backward, for every chunk, BEFORE anything is launched
+        const int64_t nch = pcn_cdiv(rows, chunk);
+        const int64_t big = rows < chunk ? rows : chunk;
+        PCN_CHECK_ARG(big < (1ll << 31) / 320, "mlp_tc_chunks: chunk of %lld rows is too large (use a smaller chunk)", (long long)big);
+        PCN_CHECK_ARG(scratch_bytes >= MlpLayout(big, 1).scratch_bytes, "mlp_tc_chunks: scratch too small (%zu < %zu)",
+                      scratch_bytes, MlpLayout(big, 1).scratch_bytes);
+        for (int k = 0; k < lanes; ++k) PCN_CHECK_ARG(scratch[k], "mlp_tc_chunks: null scratch[%d]", k);
+        for (int64_t c = 0; c < nch; ++c) {
+            const int64_t r = rows - c * chunk < chunk ? rows - c * chunk : chunk;
+            if (P->training && r == 1) {                     // what torch's BatchNorm1d raises for a one-row batch
+                pcn_set_error("Expected more than 1 value per channel when training, got input size [1, 256]");
+                return PCNERF_ERR_ARG;
+            }
+            PCN_CHECK_ARG(saved[c] && saved_bytes[c] >= MlpLayout(r, 1).saved_bytes,
+                          "mlp_tc_chunks: saved buffer of chunk %lld too small (%zu < %zu)", (long long)c, saved_bytes[c],
+                          MlpLayout(r, 1).saved_bytes);
+        }
+    }
     Lanes* L = nullptr;
     if (lanes == 2) {
         if (int rc = lanes_get(&L)) return rc;
@@ -1885,16 +1905,21 @@ static int tc_chunks(bool backward, const pcnerf_mlp_params* P, const pcnerf_mlp
 }
 
 extern "C" int pcnerf_mlp_tc_forward_chunks(const pcnerf_mlp_params* P, const void* enc, int64_t rows, int64_t chunk,
-                                            float* out_p, void* const* saved, void* const* scratch, int lanes, void* stream) {
+                                            float* out_p, void* const* saved, const size_t* saved_bytes,
+                                            void* const* scratch, size_t scratch_bytes, int lanes, void* stream) {
     PCN_CHECK_ARG(P && P->training, "mlp_tc_forward_chunks: training mode only (eval mode has no per-chunk state)");
-    return tc_chunks(false, P, nullptr, enc, rows, chunk, out_p, nullptr, saved, scratch, lanes, (cudaStream_t)stream);
+    return tc_chunks(false, P, nullptr, enc, rows, chunk, out_p, nullptr, saved, saved_bytes, scratch, scratch_bytes, lanes,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int pcnerf_mlp_tc_backward_chunks(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const void* enc,
                                              int64_t rows, int64_t chunk, const float* out_p, const float* grad_p,
-                                             void* const* saved, void* const* scratch, int lanes, void* stream) {
+                                             void* const* saved, const size_t* saved_bytes, void* const* scratch,
+                                             size_t scratch_bytes, int lanes, void* stream) {
     PCN_CHECK_ARG(G && grad_p, "mlp_tc_backward_chunks: null argument");
-    return tc_chunks(true, P, G, enc, rows, chunk, const_cast<float*>(out_p), grad_p, saved, scratch, lanes, (cudaStream_t)stream);
+    PCN_CHECK_ARG(P && P->training, "mlp_tc_backward_chunks: only the training-mode (batch-statistics) backward exists");
+    return tc_chunks(true, P, G, enc, rows, chunk, const_cast<float*>(out_p), grad_p, saved, saved_bytes, scratch,
+                     scratch_bytes, lanes, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -8,6 +8,8 @@ shapes are not capturable, so the caller must keep the number of rays fixed (`op
 """
 import torch
 
+from . import ops
+
 
 class GraphedStep:
     """Capture `fn()` (no arguments; it reads / writes fixed tensors) after `warmup` eager calls on a side stream.
@@ -29,4 +31,5 @@ class GraphedStep:
 
     def __call__(self):
         self.graph.replay()
+        ops.note_param_write()      # the replayed kernels write parameters / running statistics behind torch's back
         return self.out

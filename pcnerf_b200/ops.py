@@ -34,8 +34,16 @@ def profile_read():
     return out
 
 
-def _count(n=1):
-    pass
+# Writes the LIBRARY makes to parameters / BN running statistics go through raw pointers and never bump torch's tensor
+# version counters (pcnerf_adam_step on FlatAdam's flat buffer, k_bn_fold's running-statistics update in every
+# training-mode forward, and any replay of a captured step).  Everything that caches values derived from those tensors
+# (the folded eval-mode weights of MLPFunction) keys on this generation as well.
+_PARAM_GEN = [0]
+
+
+def note_param_write():
+    """Tell the caches that parameters / running statistics were (or may have been) written by the library."""
+    _PARAM_GEN[0] += 1
 
 
 def _p(t):
@@ -95,7 +103,6 @@ def aabb_far_bound(ray_o, ray_d, x_max, x_min, y_max, y_min, z_max, z_min):
     out = torch.empty(d.shape[0], dtype=torch.float64, device=d.device)
     keep, hp = _h3([x_max, x_min, y_max, y_min, z_max, z_min])
     check(lib().pcnerf_aabb_far_bound(_p(o), _p(d), d.shape[0], hp, _p(out), _stream()))
-    _count()
     return out
 
 
@@ -105,7 +112,6 @@ def aabb_slab(ray_o, ray_d, aabb_min, aabb_max):
     k1, pmin = _h3(aabb_min)
     k2, pmax = _h3(aabb_max)
     check(lib().pcnerf_aabb_slab(_p(o), _p(d), d.shape[0], pmin, pmax, _p(out), _stream()))
-    _count()
     return out
 
 
@@ -117,7 +123,6 @@ def aabb_child_pairs(variant, ray_o, ray_d, boxes):
     near = torch.empty((n, K), dtype=torch.float64, device=d.device)
     far = torch.empty((n, K), dtype=torch.float64, device=d.device)
     check(lib().pcnerf_aabb_child_pairs(int(variant), _p(o), _p(d), n, _p(b), K, _p(flag), _p(near), _p(far), _stream()))
-    _count()
     return flag.bool(), near, far
 
 
@@ -126,7 +131,6 @@ def aabb_dist_to_ray(ray_o, ray_d, centres):
     c = _f64(centres).reshape(-1, 3)
     out = torch.empty((d.shape[0], c.shape[0]), dtype=torch.float64, device=d.device)
     check(lib().pcnerf_aabb_dist_to_ray(_p(o), _p(d), d.shape[0], _p(c), c.shape[0], _p(out), _stream()))
-    _count()
     return out
 
 
@@ -136,7 +140,6 @@ def aabb_find_box(centres, boxes, points, knn=10):
     q = _f64(points).reshape(-1, 3)
     out = torch.empty(q.shape[0], dtype=torch.int32, device=q.device)
     check(lib().pcnerf_aabb_find_box(_p(c), _p(b), c.shape[0], _p(q), q.shape[0], int(knn), _p(out), _stream()))
-    _count()
     return out
 
 
@@ -156,7 +159,6 @@ def aabb_pack_train(variant, ray_o, ray_d, dist, points, centres, boxes, boxes_b
     k, hp = _h3([x_max, x_min, y_max, y_min, z_max, z_min])
     check(lib().pcnerf_aabb_pack_train(int(variant), _p(o), _p(d), _p(dist), _p(pts), n, _p(c), _p(b), _p(bb), c.shape[0],
                                        hp, float(surface_expand), int(knn), _p(rays), _p(keep), _stream()))
-    _count()
     keep = keep.bool()
     return (rays[keep] if compact else rays), keep
 
@@ -185,7 +187,6 @@ def frame_returns(points_f32, pose, pose_xy, range_delete, max_range, over_heigh
                                      float(range_delete[2]), float(max_range), float(over_height), float(over_low),
                                      float(interest_x), float(interest_y), hb, hs, _p(keep), _p(world), _p(dirs), _p(dist),
                                      _stream()))
-    _count()
     sel = keep.bool()
     return world[sel], dirs[sel], dist[sel]
 
@@ -213,7 +214,6 @@ def aabb_build_groups(ray_o, ray_d, dist, boxes, boxes_larger, parent_min, paren
     check(lib().pcnerf_aabb_groups_fill(_p(o), _p(d), _p(dist), n, _p(b), _p(bl), K, int(depth_inference_method),
                                         float(grow_step), float(prefilter), _p(count), _p(offset), _p(pfar), _p(scratch),
                                         _p(rays), _p(ranges), _p(other), _stream()))
-    _count(2)
     return rays, ranges, other, count > 0
 
 
@@ -241,7 +241,6 @@ def sample_encode_coarse(rays, n_a, n_b=0, near_col=6, far_col=7, cnear_col=10, 
     check(lib().pcnerf_sample_encode_coarse(_p(rays), ld, n, near_col, far_col, cnear_col, cfar_col, _p(sa), n_a, _p(sb),
                                             n_b, int(bool(use_disp)), float(perturb), _p(U) if perturb > 0 else None,
                                             _p(z), _p(enc), _p(enc_bf), _stream()))
-    _count()
     return z, (enc_bf if f16 else enc)
 
 
@@ -265,7 +264,6 @@ def sample_encode_fine(rays, z, w, Ni, u=None, det=True, want_enc=True, f16=Fals
             enc = torch.empty((n * (S + Ni), 64), dtype=torch.float32, device=rays.device)
     check(lib().pcnerf_sample_encode_fine(_p(rays), rays.shape[1], n, _p(z), _p(w), S, _p(u), u_ld, Ni, _p(zf), _p(enc),
                                           _p(enc_bf), _stream()))
-    _count()
     return zf, (enc_bf if f16 else enc)
 
 
@@ -281,7 +279,6 @@ def sample_pdf(bins, weights, Ni, u=None, det=False):
         u, u_ld = _cuda_f32(u, "u"), Ni
     out = torch.empty((n, Ni), dtype=torch.float32, device=bins.device)
     check(lib().pcnerf_sample_pdf(_p(bins), _p(weights), n, nb, _p(u), u_ld, Ni, _p(out), _stream()))
-    _count()
     return out
 
 
@@ -291,13 +288,13 @@ def embed(x, out_ld=63):
         raise ValueError("embed: x must be (B,3)")
     out = torch.empty((x.shape[0], out_ld), dtype=torch.float32, device=x.device)
     check(lib().pcnerf_embed(_p(x), x.shape[0], _p(out), out_ld, _stream()))
-    _count()
     return out
 
 
 # ------------------------------------------------------------------------------------------------------- K3 MLP
 
 _SCRATCH = {}
+_SCRATCH_RETIRED = []             # outgrown scratch buffers, kept alive for the graphs that may still reference them
 EVAL_CHUNK_FLOOR = 1 << 20        # rows per launch of the eval-mode tensor-core MLP (tests lower it to cover chunking)
 
 
@@ -309,6 +306,9 @@ def _scratch(rows, precision, device, lane=0):
     key = (str(device), precision, lane)
     buf = _SCRATCH.get(key)
     if buf is None or buf.numel() < need:
+        if buf is not None:
+            # a CUDA graph captured earlier has the old buffer's address baked into its kernel nodes: never free it
+            _SCRATCH_RETIRED.append(buf)
         buf = torch.empty(need, dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
     return buf
@@ -358,6 +358,8 @@ class MLPFunction(torch.autograd.Function):
         P = _mlp_params(params, buffers, training, precision)
         out = torch.empty(rows, dtype=torch.float32, device=dev)
         need_grad = training and any(ctx.needs_input_grad[6:])
+        if training:
+            note_param_write()          # k_bn_fold updates the BN running statistics through raw pointers
         if not training and precision == 1:
             # eval-mode BN is row-wise (running statistics): `chunk` (an OOM guard in the reference, nof/render.py:21-24)
             # does not change any value, and the row GEMMs run closer to their steady-state rate on >= 1 M-row launches
@@ -371,9 +373,10 @@ class MLPFunction(torch.autograd.Function):
             lanes = TC_LANES if nch > 1 else 1
             scr = [_scratch(min(chunk, rows), 1, dev, k) for k in range(lanes)]
             sv_arr = (ctypes.c_void_p * nch)(*[t.data_ptr() for t in saved])
+            sb_arr = (ctypes.c_size_t * nch)(*[t.numel() for t in saved])
             sc_arr = (ctypes.c_void_p * lanes)(*[t.data_ptr() for t in scr])
-            check(lib().pcnerf_mlp_tc_forward_chunks(ctypes.byref(P), _p(enc), rows, chunk, _p(out), sv_arr, sc_arr, lanes,
-                                                     _stream()))
+            check(lib().pcnerf_mlp_tc_forward_chunks(ctypes.byref(P), _p(enc), rows, chunk, _p(out), sv_arr, sb_arr, sc_arr,
+                                                     min(t.numel() for t in scr), lanes, _stream()))
             ctx.saved_chunks = saved
             ctx.meta = (chunk, precision, buffers, rows)
             ctx.save_for_backward(enc, out, *params)
@@ -387,10 +390,12 @@ class MLPFunction(torch.autograd.Function):
             # (tensor version counters), not on every call -- 18 small launches per call otherwise.
             # `cache` is a dict owned by the model (its lifetime bounds the cached copies)
             cache = cache if cache is not None else {}
-            ver = tuple((t.data_ptr(), t._version) for t in params) + \
+            ver = (_PARAM_GEN[0],) + tuple((t.data_ptr(), t._version) for t in params) + \
                 tuple((b.data_ptr(), b._version) for grp in buffers[:2] for b in grp)
             scratch = cache.get("scratch")
             if scratch is None or scratch.device != dev:
+                if scratch is not None:
+                    _SCRATCH_RETIRED.append(scratch)
                 scratch = torch.empty(lib().pcnerf_mlp_scratch_bytes(1, 1), dtype=torch.uint8, device=dev)
                 cache["scratch"], cache["ver"] = scratch, None
             P.prepared = 2 if cache.get("ver") == ver else 0       # 2: weight copies valid, per-call constants to be loaded
@@ -412,7 +417,6 @@ class MLPFunction(torch.autograd.Function):
                                            ctypes.c_void_p(out.data_ptr() + i * 4), _p(sv), sv.numel(), _p(scratch),
                                            scratch.numel(), _stream()))
             P.prepared = 1              # later chunks of this pass reuse the weight copies in `scratch`
-            _count(18)
         ctx.saved_chunks = saved
         ctx.meta = (chunk, precision, buffers, rows)
         ctx.save_for_backward(enc, out, *params)
@@ -442,9 +446,10 @@ class MLPFunction(torch.autograd.Function):
             lanes = TC_LANES if nch > 1 else 1
             scr = [_scratch(min(chunk, rows), 1, dev, k) for k in range(lanes)]
             sv_arr = (ctypes.c_void_p * nch)(*[t.data_ptr() for t in ctx.saved_chunks])
+            sb_arr = (ctypes.c_size_t * nch)(*[t.numel() for t in ctx.saved_chunks])
             sc_arr = (ctypes.c_void_p * lanes)(*[t.data_ptr() for t in scr])
             check(lib().pcnerf_mlp_tc_backward_chunks(ctypes.byref(P), ctypes.byref(G), _p(enc), rows, chunk, _p(out), _p(gp),
-                                                      sv_arr, sc_arr, lanes, _stream()))
+                                                      sv_arr, sb_arr, sc_arr, min(t.numel() for t in scr), lanes, _stream()))
             ctx.saved_chunks = None
             return (None, None, None, None, None, None) + tuple(views)
         scratch = _scratch(min(chunk, rows), precision, dev)
@@ -457,7 +462,6 @@ class MLPFunction(torch.autograd.Function):
                                             ctypes.c_void_p(gp.data_ptr() + i * 4), _p(sv), sv.numel(), _p(scratch),
                                             scratch.numel(), _stream()))
             P.prepared = 1
-            _count(45)
         ctx.saved_chunks = None
         return (None, None, None, None, None, None) + tuple(views)
 
@@ -535,11 +539,9 @@ class CompositeFunction(torch.autograd.Function):
             noise = _cuda_f32(noise, "noise")
         check(lib().pcnerf_composite_fwd(_p(p), _p(z), _p(rays), ld, n, P_, cn, cf, rc, _p(noise), float(noise_std),
                                          float(epsilon), int(flags), _p(w), _p(depth), _p(per_ray), _p(sums), _stream()))
-        _count()
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
         if child and n > 0:
             check(lib().pcnerf_composite_losses(_p(sums), n, _p(losses), _stream()))
-            _count()
         if flags & COMP_OPACITY:
             opacity = (sums[2] / max(n * P_, 1)).to(torch.float32)
         else:
@@ -568,7 +570,6 @@ class CompositeFunction(torch.autograd.Function):
         check(lib().pcnerf_composite_bwd(_p(p), _p(z), _p(w), _p(rays), ld, n, P_, rc, noise_std, epsilon, flags,
                                          _p(per_ray), _p(g_depth), _p(g_free), _p(g_dl), _p(g_free_r), _p(g_sl1_r), n,
                                          _p(gp), _stream()))
-        _count()
         return gp, None, None, None, None, None, None, None, None
 
 
@@ -590,7 +591,6 @@ def search_rows(p, z, rays, cnear_col=6, cfar_col=7, epsilon=1e-10, method=0):
     sums = torch.empty(4, dtype=torch.float64, device=dev)
     check(lib().pcnerf_search_rows(_p(p), _p(z), _p(rays), rays.shape[1], n, P_, cnear_col, cfar_col, float(epsilon),
                                    int(method), _p(w), _p(depth), _p(peak), _p(wsum), _p(sums), _stream()))
-    _count()
     opacity = (sums[0] / max(n * P_, 1)).to(torch.float32)
     return depth, w, opacity, peak, wsum
 
@@ -600,7 +600,6 @@ def search_select(other, peak, wsum):
     n = other.shape[0]
     flag = torch.empty(n, dtype=torch.uint8, device=other.device)
     check(lib().pcnerf_search_select(_p(other), _p(peak), _p(wsum), n, _p(flag), _stream()))
-    _count(3)
     return flag.bool().reshape(-1, 1)
 
 
@@ -608,7 +607,6 @@ def points(rays, depth):
     rays, depth = _cuda_f32(rays, "rays"), _cuda_f32(depth, "depth")
     out = torch.empty((rays.shape[0], 3), dtype=torch.float32, device=rays.device)
     check(lib().pcnerf_points(_p(rays), rays.shape[1], rays.shape[0], _p(depth), _p(out), _stream()))
-    _count()
     return out
 
 

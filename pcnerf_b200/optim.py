@@ -15,7 +15,7 @@ import torch
 
 from . import parallel
 from ._lib import check, lib
-from .ops import _p, _stream
+from .ops import _p, _stream, note_param_write
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -51,10 +51,12 @@ class FlatAdam(torch.optim.Optimizer):
         """All-reduce (sum) of the flat gradients when running data-parallel, then ONE Adam kernel (1/world folded in)."""
         loss = closure() if closure is not None else None
         g = self.param_groups[0]
-        if float(g["lr"]) != self._lr_host:                    # a scheduler moved the rate: mirror it (outside any graph)
+        if self._lr_host is None or float(g["lr"]) != self._lr_host:                    # a scheduler moved the rate: mirror it (outside any graph)
             self._lr_host = float(g["lr"])
             self.lr_dev.fill_(self._lr_host)
         w = parallel.world()
+        if not torch.cuda.is_current_stream_capturing():
+            self.bucket.realias()                              # nn.Module.zero_grad(set_to_none=True) detaches .grad
         if allreduce and w > 1:
             torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM)
         b1, b2 = g["betas"]
@@ -62,7 +64,26 @@ class FlatAdam(torch.optim.Optimizer):
                                      self.flat.numel(), _p(self.step_dev), _p(self.lr_dev), _p(self._coef), float(b1),
                                      float(b2), float(g["eps"]), float(g["weight_decay"]), 1.0 / w if allreduce else 1.0,
                                      _stream()))
+        note_param_write()                                     # the kernel wrote every parameter through a raw pointer
         return loss
+
+    # ---- checkpoint / resume: the moments and the step count live outside Optimizer.state (flat buffers)
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat_adam"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                           "step": self.step_dev.detach().clone()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        extra = state_dict.pop("flat_adam", None)
+        super().load_state_dict(state_dict)
+        if extra is not None:
+            with torch.no_grad():
+                self.exp_avg.copy_(extra["exp_avg"])
+                self.exp_avg_sq.copy_(extra["exp_avg_sq"])
+                self.step_dev.copy_(extra["step"])
+        self._lr_host = None                                   # re-mirror the (possibly restored) learning rate
 
 
 class LossHistory:

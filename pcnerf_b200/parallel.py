@@ -43,19 +43,27 @@ class GradBucket:
     def zero(self):
         self.flat.zero_()
 
+    def realias(self):
+        """Make every p.grad alias its slice of the flat buffer again.  Autograd accumulates in place when .grad exists,
+        so normally nothing changed; `zero_grad(set_to_none=True)` / `p.grad = None` make it allocate fresh tensors, whose
+        values are copied in (a parameter that received no gradient contributes zeros)."""
+        o = 0
+        for p in self.params:
+            v = self.flat[o:o + p.numel()].view_as(p)
+            if p.grad is None:
+                v.zero_()
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+            o += p.numel()
+
     def allreduce_mean(self):
         """Sum over ranks then scale by 1/world (in place); returns the async work handle already waited on."""
         w = world()
         if w == 1:
             return
-        # autograd may have replaced p.grad (it accumulates in place when .grad exists, so normally it has not)
-        o = 0
-        for p in self.params:
-            v = self.flat[o:o + p.numel()].view_as(p)
-            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
-                p.grad = v
-            o += p.numel()
+        self.realias()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.flat.mul_(1.0 / w)
 

@@ -1,0 +1,175 @@
+#!/usr/bin/env python
+"""CPU emulation (float64 arithmetic + explicit fp16 roundings) of the tensor-core MLP's number formats on a C2-shaped
+batch: which rounding contributes what to the relative depth error, and what each candidate fix buys.
+
+    python scripts/emulate_tc_precision.py [--rays 4096] [--chunk 262144]
+
+Roundings that can be switched on one by one:
+  E  encoding stored as fp16                          (csrc/sample_encode.cu, fp16 rows)
+  H  pre-BN activations H_l stored as fp16            (k_tc_rowgemm epilogue)
+  W  folded weights W_{l+1} diag(a_l) stored as fp16  (k_bn_fold), W_0 as fp16 (k_tc_prep_fwd)
+  C  W with the linear correction block: layer l+1 also accumulates C_{l+1} x  (x = the 64-d encoding), with
+     C_{l+1} = fp16((W' - fp16(W')) A_l), A_l the affine map x -> H_l  (identity activations: H_l = A_l x + d_l)
+Test infrastructure / design study: imports oracle/ for the weights and the sampling only.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pcnerf_oracle as orc  # noqa: E402
+from pcnerf_b200 import synth  # noqa: E402
+
+f64 = torch.float64
+
+
+def r16(t):
+    return t.to(torch.float16).to(f64)
+
+
+def lin_names():
+    return list(orc.LAYER1_LIN) + list(orc.LAYER2_LIN)
+
+
+def bn_names():
+    return list(orc.LAYER1_BN) + list(orc.LAYER2_BN)
+
+
+def forward(sd, x, mode, correct_layers=(), eps=1e-5, h_layers=None):
+    """x (rows,63) float64 exact encoding.  mode: set of letters from EHWC.  Returns p (rows,)."""
+    E = r16(x) if "E" in mode else x
+    lins, bns = lin_names(), bn_names()
+    h = None
+    A = None            # affine map of the activations actually computed: H_l = A x + const
+    a_prev = s_prev = None
+    for l in range(8):
+        W = sd[lins[l] + ".weight"].to(f64)
+        b = sd[lins[l] + ".bias"].to(f64)
+        if l == 0:
+            Wf, bias = W, b
+            inp = E
+        elif l == 4:
+            Wf = torch.cat([W[:, :63], W[:, 63:] * a_prev[None, :]], 1)
+            bias = b + W[:, 63:] @ s_prev
+            inp = torch.cat([E, h], 1)
+        else:
+            Wf = W * a_prev[None, :]
+            bias = b + W @ s_prev
+            inp = h
+        if "W" in mode or "C" in mode:
+            Wr = r16(Wf)
+        else:
+            Wr = Wf
+        out = inp @ Wr.t() + bias
+        if "C" in mode and (l in correct_layers):
+            dW = Wf - Wr
+            if "M" in mode:
+                # as implementable without a kernel change: layer 0 uncorrected, layer 4's correction merged into its
+                # (single) encoding block before the fp16 rounding, the others get an extra K = 64 block [C_l | W'_l]
+                if l == 0:
+                    pass
+                elif l == 4:
+                    merged = r16(Wf[:, :63] + dW[:, 63:] @ A)
+                    out = E @ merged.t() + h @ Wr[:, 63:].t() + bias
+                else:
+                    out = out + E @ r16(dW @ A).t()
+            else:
+                if l == 0:
+                    Cm = dW
+                elif l == 4:
+                    Cm = dW[:, :63] + dW[:, 63:] @ A
+                else:
+                    Cm = dW @ A
+                out = out + E @ r16(Cm).t()
+        # affine map actually realised by this layer (given its realised inputs)
+        if l == 0:
+            A_new = Wf
+        elif l == 4:
+            A_new = Wf[:, :63] + Wf[:, 63:] @ A
+        else:
+            A_new = Wf @ A
+        A = A_new
+        h = r16(out) if ("H" in mode and (h_layers is None or l in h_layers)) else out
+        mean = h.mean(0)
+        var = h.var(0, unbiased=False)
+        g, be = sd[bns[l] + ".weight"].to(f64), sd[bns[l] + ".bias"].to(f64)
+        a_prev = g / torch.sqrt(var + eps)
+        s_prev = be - mean * a_prev
+    wo = sd["occ_out.0.weight"].to(f64)[0]
+    bo = sd["occ_out.0.bias"].to(f64)[0]
+    logit = h @ (wo * a_prev) + (wo @ s_prev) + bo
+    return torch.sigmoid(logit)
+
+
+def depth_of(p, z):
+    w = orc.composite(p)
+    return (w * z).sum(1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=262144)
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--study", default="all", choices=["all", "layers", "tail", "merged"])
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    N, S = a.rays, 64
+    rays = torch.from_numpy(synth.synth_train_rays(a.seed, N, K=200, parent=synth.KITTI_PARENT))
+    U = torch.rand((N, S), generator=torch.Generator().manual_seed(4))
+    z = orc.sample_z(rays, S, 1, 0.1, 1.0, U)
+    samples = (rays[:, None, :3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3)
+    x = orc.embedding(samples.to(f64))
+    sd = orc.init_state_dict(42)
+    zz = z.to(f64)
+
+    def run(mode, correct=(), h_layers=None):
+        ps = []
+        for i in range(0, x.shape[0], a.chunk):
+            ps.append(forward(sd, x[i:i + a.chunk], mode, correct, h_layers=h_layers))
+        return depth_of(torch.cat(ps).view(N, S), zz)
+
+    ref = run("")
+    allL = tuple(range(8))
+
+    def rep(name, d):
+        rel = ((d - ref).abs() / ref.abs()).numpy()
+        print("%-34s median %.2e  p99 %.2e  p99.9 %.2e  max %.2e" % (name, np.median(rel), np.quantile(rel, 0.99),
+                                                                    np.quantile(rel, 0.999), rel.max()), flush=True)
+
+    if a.study == "layers":
+        for l in range(8):
+            rep("H at layer %d only" % l, run("H", h_layers=(l,)))
+        return
+    if a.study == "tail":
+        rep("E+H+W (shipped)", run("EHW"))
+        rep("E+H", run("EH"))
+        rep("E+H+C all layers", run("EHC", allL))
+        rep("E+H+C layer 4 only", run("EHC", (4,)))
+        return
+    if a.study == "merged":
+        rep("E+H+W (shipped)", run("EHW"))
+        rep("E+H+C all layers", run("EHC", allL))
+        rep("E+H+C merged form", run("EHCM", allL))
+        return
+    rep("E only", run("E"))
+    rep("H only", run("H"))
+    rep("W only", run("W"))
+    rep("E+H+W (shipped)", run("EHW"))
+    rep("E+H", run("EH"))
+    rep("E+H+C all layers", run("EHC", allL))
+    rep("E+H+C layers 1-7", run("EHC", (1, 2, 3, 4, 5, 6, 7)))
+    rep("E+H+C layer 4 only", run("EHC", (4,)))
+    rep("E+H+C layers 4,7", run("EHC", (4, 7)))
+    rep("E+H+C layers 2,4,6,7", run("EHC", (2, 4, 6, 7)))
+    rep("E+H+C layers 4,5,6,7", run("EHC", (4, 5, 6, 7)))
+    rep("E+H+C layers 0,4", run("EHC", (0, 4)))
+
+
+if __name__ == "__main__":
+    main()

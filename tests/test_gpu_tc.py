@@ -276,3 +276,100 @@ def test_eval_fold_cache_follows_parameter_updates():
         ma.layer1[1].running_mean.add_(0.05)                                         # running statistics count too
         pa4 = ma.forward_encoded(enc, rows)
         assert not torch.equal(pa4, pa3) and close(pa4, ref(ma))
+
+
+def test_eval_fold_cache_sees_library_side_writes():
+    """FlatAdam's kernel and the running-statistics update of a training-mode forward write through raw
+    pointers, which never bump torch's tensor versions -- the cached folded eval-mode weights must still be re-derived
+    (train -> validate -> train -> validate)."""
+    from pcnerf_b200.graphed import GraphedStep
+    from pcnerf_b200.optim import FlatAdam
+    rows = 3000
+    enc = torch.nn.functional.pad(_enc(rows, 6), (0, 1)).to(dev())
+    m, _, _ = make_nets(42, 43, False, "tc")
+    opt = FlatAdam(list(m.parameters()), lr=5e-2, eps=1e-8, weight_decay=1e-3)
+
+    def ref():
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        return orc.nof_forward(sd, enc.cpu()[:, :63].float(), False).reshape(-1)
+
+    def close(p, r):
+        err = (p.cpu() - r).abs() / r
+        return float(err.max()) < 6e-3 and float(err.mean()) < 1e-3
+
+    def evaluate():
+        m.eval()
+        with torch.no_grad():
+            return m.forward_encoded(enc, rows).clone()
+
+    p0 = evaluate()
+    assert torch.equal(p0, evaluate()) and close(p0, ref())          # second call: cached fold
+    # (1) optimizer step by the library's Adam kernel
+    opt.bucket.flat.normal_(generator=torch.Generator(device=dev()).manual_seed(3))
+    opt.step()
+    p1 = evaluate()
+    assert not torch.equal(p1, p0) and close(p1, ref())
+    # (2) a training-mode forward moves the running statistics
+    m.train()
+    m.forward_encoded(enc, rows)
+    p2 = evaluate()
+    assert not torch.equal(p2, p1) and close(p2, ref())
+    # (3) the same two writes replayed from a CUDA graph (no Python runs during a replay)
+    m.train()
+
+    def step():
+        opt.bucket.zero()
+        m.forward_encoded(enc, rows).sum().backward()
+        opt.step()
+
+    g = GraphedStep(step, warmup=1)
+    p3 = evaluate()
+    g()
+    p4 = evaluate()
+    assert not torch.equal(p4, p3) and close(p4, ref())
+
+
+def test_tc_training_tail_chunk_of_one_row_raises_before_any_launch():
+    """the chunked training pass validates every chunk like pcnerf_mlp_forward does -- a tail chunk of
+    exactly one row raises torch's ValueError and nothing has been launched (running statistics untouched)."""
+    chunk = 512
+    enc = torch.nn.functional.pad(_enc(chunk + 1, 7), (0, 1)).to(dev())
+    m, _, _ = make_nets(42, 43, True, "tc")
+    before = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        m.forward_encoded(enc, chunk)
+    torch.cuda.synchronize()
+    for k, v in m.state_dict().items():
+        if k in before:
+            assert torch.equal(v, before[k]), k
+    p = m.forward_encoded(enc[:chunk].contiguous(), chunk)
+    assert bool(torch.isfinite(p).all())
+
+
+def test_flat_adam_state_dict_roundtrip_and_grad_realias():
+    """the Adam moments / step count survive state_dict() -> load_state_dict(), and a parameter whose
+    .grad was detached (zero_grad(set_to_none=True)) is re-aliased instead of silently skipped."""
+    from pcnerf_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    ma, _, _ = make_nets(42, 43, True, "tc")
+    mb, _, _ = make_nets(42, 43, True, "tc")
+    oa = FlatAdam(list(ma.parameters()), lr=1e-3, eps=1e-8, weight_decay=1e-3)
+    ob = FlatAdam(list(mb.parameters()), lr=1e-3, eps=1e-8, weight_decay=1e-3)
+    gen = torch.Generator(device=dev()).manual_seed(11)
+    for _ in range(3):
+        oa.bucket.flat.normal_(generator=gen)
+        oa.step()
+    ob.load_state_dict(oa.state_dict())
+    with torch.no_grad():
+        ob.flat.copy_(oa.flat)
+    g = torch.randn(oa.flat.numel(), device=dev(), generator=gen)
+    oa.bucket.flat.copy_(g)
+    oa.step()
+    # b: gradients arrive in fresh tensors (set_to_none semantics)
+    o = 0
+    for p in ob.bucket.params:
+        p.grad = g[o:o + p.numel()].view_as(p).clone()
+        o += p.numel()
+    ob.step()
+    torch.cuda.synchronize()
+    assert torch.equal(oa.flat, ob.flat) and torch.equal(oa.exp_avg, ob.exp_avg) and int(ob.step_dev.item()) == 4
