@@ -57,6 +57,11 @@ def parse():
     ap.add_argument("--no-inference", action="store_true", help="skip the depth-inference (C3) block")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra closed-form (affine) measurement")
     ap.add_argument("--infer-rays", type=int, default=131072, help="physical LiDAR rays of the inference frame per GPU")
+    ap.add_argument("--no-c4", action="store_true", help="skip the strong-scaling C4 block (262,144 rays x 128+256 samples)")
+    ap.add_argument("--c4-rays", type=int, default=262144, help="global rays per optimizer step of the C4 block")
+    ap.add_argument("--no-c5", action="store_true", help="skip the multi-parent scene block (C5)")
+    ap.add_argument("--c5-frames", type=int, default=0, help="frames of the C5 block (0 = a bounded sample: 2 frames per GPU)")
+    ap.add_argument("--c5-parents", type=int, default=64)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay each step as one CUDA graph (pcnerf_b200.graphed.GraphedStep); auto = fall back to eager "
                          "launches if capture fails")
@@ -231,17 +236,21 @@ def run_b200(a):
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     staged = [torch.empty_like(r) for r in resident]          # device landing buffers of the e2e graph
 
-    def core(d_, r_, p_, compact):
+    def core(d_, r_, p_, compact, n_s=S, n_i=NI, f_mean=1.0, f_depth=None, zero=True):
+        """K1 packing -> render -> six-term loss -> backward into the flat gradient bucket.  (f_mean, f_depth): loss factors
+        of a ray micro-batch (pcnerf_b200.train_kitti.microbatch_scales); default = one batch per step per rank."""
         rays, keep = ops.aabb_pack_train(606, origin, d_, r_, p_, centres, boxes, boxes_big, scene.parent, 0.05, 10,
                                          compact=compact)
-        res = render.render_rays_train(mc, mf, emb, rays, N_samples=S, N_importance=NI, perturb=1.0, noise_std=0,
+        res = render.render_rays_train(mc, mf, emb, rays, N_samples=n_s, N_importance=n_i, perturb=1.0, noise_std=0,
                                        chunk=CHUNK, issegmentated=1, childnerf_ratio=0.1, use_child_nerf_divide=0,
                                        use_child_nerf_loss=1)
-        gt = rays[:, 14]
-        loss = 0.1 * LAM[0] * sl1(10 * res["depth"], 10 * gt) + 0.1 * LAM[0] * sl1(10 * res["depth_fine"], 10 * gt) \
-            + LAM[1] * (res["child_free_loss_fine"] + res["child_free_loss"]) \
-            + LAM[2] * dscale * (res["child_depth_loss_fine"] + res["child_depth_loss"])
-        bucket.zero()
+        f_depth = dscale if f_depth is None else f_depth
+        # (the two scene-level range terms SmoothL1(10 depth, 10 gt) come out of K4's compositing pass: res["range_sl1*"])
+        loss = f_mean * (0.1 * LAM[0] * (res["range_sl1"] + res["range_sl1_fine"])
+                         + LAM[1] * (res["child_free_loss_fine"] + res["child_free_loss"])) \
+            + LAM[2] * f_depth * (res["child_depth_loss_fine"] + res["child_depth_loss"])
+        if zero:
+            bucket.zero()
         loss.backward()
         return loss.detach().reshape(1), rays.shape[0], keep
 
@@ -330,6 +339,77 @@ def run_b200(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         return float(ms.item()), float(tot.item()), ops.launch_count()
+
+    def time_c4():
+        """BASELINE.json configs[3]: ONE optimizer step over 262,144 rays x (128 coarse + 256 importance) samples
+        (nof/nof_utils.py:121-124 defaults) with the rays STRONG-sharded over the ranks (262,144 / N per GPU), every rank
+        accumulating gradients over micro-batches of 32,768 rays (the saved activations of one micro-batch are 69 GB), then
+        one NCCL all-reduce of the flat gradient buffer + Adam.  BatchNorm batches are the same 262,144-row chunks the
+        reference would form on the whole batch (a micro-batch holds 16 / 48 whole chunks).  value = global rays / s."""
+        from pcnerf_b200 import synth
+        from pcnerf_b200.graphed import GraphedStep
+        from pcnerf_b200.train_kitti import microbatch_scales
+        NG, S4, NI4, MB = a.c4_rays, 128, 256, 32768
+        n_l = NG // world
+        mb = min(MB, n_l)
+        nmb = n_l // mb
+        pts4 = synth.make_points(scene, 4000 + rank, n_l + n_l // 32 + 64)
+        dirs4, dist4 = synth.rays_from_points(scene.origin, pts4)
+        _, keep4 = ops.aabb_pack_train(606, scene.origin, dirs4, dist4, pts4, scene.centres, scene.child_bounds,
+                                       scene.child_bounds_bigger, scene.parent, 0.05, 10, compact=False)
+        sel4 = np.nonzero(keep4.cpu().numpy())[0][:n_l]
+        res4 = [torch.from_numpy(np.ascontiguousarray(x[sel4])).to(dev) for x in (dirs4, dist4, pts4)]
+        stage4 = [torch.empty_like(r[:mb]) for r in res4]
+        f_mean, f_depth = microbatch_scales(mb, n_l, world)
+
+        def micro():
+            core(*stage4, False, S4, NI4, f_mean, f_depth, zero=False)
+
+        g4, note4 = None, "off"
+        if use_graph:
+            try:
+                for s_, r_ in zip(stage4, res4):
+                    s_.copy_(r_[:mb])
+                g4, note4 = GraphedStep(micro, warmup=1), "on (one graph per ray micro-batch)"
+            except Exception as exc:                           # noqa: BLE001
+                if a.graph == "on":
+                    raise
+                sys.stderr.write("bench.py: c4 graph capture failed (%s: %s); eager launches\n" % (type(exc).__name__, exc))
+                torch.cuda.synchronize()
+                g4, note4 = None, "capture failed, eager"
+
+        def step4():
+            bucket.zero()
+            for m in range(nmb):
+                for s_, r_ in zip(stage4, res4):
+                    s_.copy_(r_[m * mb:(m + 1) * mb])
+                if g4 is not None:
+                    g4()
+                else:
+                    micro()
+            finish()
+
+        step4()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k4 = max(1, min(a.steps, 2))
+        e0.record()
+        for _ in range(k4):
+            step4()
+        e1.record()
+        barrier()
+        ms4 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        ms4 = float(ms4.item()) / k4
+        del g4
+        return {"workload": "C4: %d rays x (128 coarse + 256 importance) samples per optimizer step, rays strong-sharded "
+                            "over %d GPU(s), %d micro-batch(es) of %d rays per GPU with gradient accumulation, one flat NCCL "
+                            "all-reduce + Adam per step" % (NG, world, nmb, mb),
+                "metric": METRIC, "value": NG / (ms4 * 1e-3), "unit": "rays/s", "scaling": "strong", "ms_per_step": ms4,
+                "rays_global": NG, "rays_per_gpu": n_l, "micro_batches_per_gpu": nmb, "micro_batch_rays": mb,
+                "N_samples": S4, "N_importance": NI4, "chunk": CHUNK, "steps": k4, "warmup": 1, "cuda_graph": note4,
+                "sample_evals_per_step": NG * (S4 + S4 + NI4), "precision": a.precision}
 
     clocks = ClockSampler(local)                     # started before the warm-up: nvidia-smi needs ~1 s to come up
     clocks.start()
@@ -467,6 +547,22 @@ def run_b200(a):
         out["fast_mode"] = fast
         graphs.clear()
         mc.precision = mf.precision = a.precision
+    if not a.no_c4:
+        graphs.clear()
+        torch.cuda.empty_cache()
+        out["c4"] = time_c4()
+    if not a.no_c5:
+        torch.cuda.empty_cache()
+        out["c5"] = time_c5(a, rank, world, dev, emb)
+    # the driver keeps `config` of every per-N line: compact copies of the other workloads' headline numbers go there
+    other = {}
+    if "inference" in out:
+        other["c3_depth_inference"] = {k: out["inference"][k] for k in ("value", "unit", "ms_per_frame", "physical_rays_per_gpu")}
+    if "c4" in out:
+        other["c4_train_strong"] = {k: out["c4"][k] for k in ("value", "unit", "ms_per_step", "rays_global", "rays_per_gpu")}
+    if "c5" in out:
+        other["c5_multi_parent_inference"] = {k: out["c5"][k] for k in ("value", "unit", "frames_per_s", "frames_timed", "parents")}
+    out["config"]["other_workloads"] = other
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, ms_cpu = time_cpu(a.cpu_rays, 2, 1)
         out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
@@ -502,8 +598,13 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
     mc.eval()
     mf.eval()
 
+    # group structure of the frame's candidate rows (which rows start a physical ray): produced once with the rows -- by the
+    # group builder K1 (ops.aabb_build_groups) or when a cached frame is loaded -- not per rendering
+    plan = ev.FramePlan(rays_d, other_d, 18432)
+
     def frame():
-        return ev.render_frame(mc, mf, emb, rays_d, other_d, S, NI, 184320, depth_inference_method=2, batch_size_set=18432)
+        return ev.render_frame(mc, mf, emb, rays_d, other_d, S, NI, 184320, depth_inference_method=2, batch_size_set=18432,
+                               plan=plan)
 
     pts = frame()
     assert pts.shape[0] == n_phys, (pts.shape, n_phys)          # exactly one rendered point per physical ray
@@ -573,6 +674,89 @@ def time_inference(a, rank, world, dev, mc, mf, emb):
             "unit": "rays/s", "ms_per_frame": float(ms.item()), "physical_rays_per_gpu": n_phys,
             "candidate_rows_per_gpu": int(rows.shape[0]), "N_samples": S, "N_importance": NI, "batch_rows": 18432,
             "precision": a.precision, "kernels": classes, "roofline": mlp_roof}
+
+
+def time_c5(a, rank, world, dev, emb):
+    """BASELINE.json configs[4]: a large scene of 64 parent blocks (8 x 8 grid of 40 x 40 x 2.2 m KITTI-like blocks), each
+    with ~500 child AABBs and its OWN pair of occupancy networks, the blocks sharded over the GPUs (8 per GPU at 8 GPUs);
+    batched depth inference of full 64-beam frames (131,072 returns each; the sensor of frame f stands in block f mod 64 and
+    sees that block and its neighbours): returns routed to their block (K0'), candidate groups per block over all frames of
+    the batch (K1), two-step search rendering once per physical ray.  No communication.  value = physical rays / s over all
+    GPUs; frames_per_s = value / 131,072.  A default run times a bounded sample (2 frames per GPU per batch, the batch
+    rendered `reps` times); --c5-frames 1000 renders 1,000 frames."""
+    import torch.distributed as dist
+    from pcnerf_b200 import scene as sc
+    from pcnerf_b200 import synth
+    from pcnerf_b200.nof.networks import NOF_coarse, NOF_fine
+    P, K5, RAYS = a.c5_parents, 500, 131072
+    side = int(round(P ** 0.5))
+    assert side * side == P, "--c5-parents must be a square number"
+    bw = 40.0
+    rng = np.random.default_rng(5000)
+    parents, scenes = [], []
+    owned = set(sc.owned_blocks(P, world, rank))
+    for i in range(P):
+        gx, gy = i % side, i // side
+        box = (gx * bw, (gx + 1) * bw, gy * bw, (gy + 1) * bw, -1.7, 0.5)
+        s_i = synth.make_scene(7000 + i, K5, box)
+        scenes.append(s_i)
+        blk = sc.ParentBlock(s_i.parent_min, s_i.parent_max, s_i.child_bounds,
+                             s_i.child_bounds + np.array([-0.025] * 3 + [0.025] * 3))
+        if i in owned:
+            torch.manual_seed(9000 + i)
+            blk.nof_coarse, blk.nof_fine = NOF_coarse().to(dev).eval(), NOF_fine().to(dev).eval()
+            blk.nof_coarse.precision = blk.nof_fine.precision = a.precision
+        parents.append(blk)
+    # one batch of frames (every rank builds the same batch: frames are broadcast, blocks are sharded)
+    fb = 2 * world
+    origins, pts, fid = [], [], []
+    for f in range(fb):
+        c = (f * 7) % P
+        gx, gy = c % side, c // side
+        nb = [(x, y) for x in range(max(gx - 1, 0), min(gx + 2, side)) for y in range(max(gy - 1, 0), min(gy + 2, side))]
+        o = np.array([(gx + 0.5) * bw + rng.uniform(-5, 5), (gy + 0.5) * bw + rng.uniform(-5, 5), rng.uniform(-0.3, 0.0)])
+        per = RAYS // len(nb)
+        for j, (x, y) in enumerate(nb):
+            n_j = per if j < len(nb) - 1 else RAYS - per * (len(nb) - 1)
+            pts.append(synth.make_points(scenes[y * side + x], 100 * f + j, n_j))
+            fid.append(np.full(n_j, f, dtype=np.int32))
+        origins.append(o)
+    origins_d = torch.tensor(np.stack(origins), dtype=torch.float64, device=dev)
+    pts_d = torch.tensor(np.concatenate(pts), dtype=torch.float64, device=dev)
+    fid_d = torch.tensor(np.concatenate(fid), dtype=torch.int32, device=dev)
+    boxes_d = torch.as_tensor(sc.parent_boxes(parents), dtype=torch.float64, device=dev)
+
+    def batch():
+        res = sc.render_scene_frames(parents, origins_d, pts_d, fid_d, emb, S, NI, 184320, 2, 18432, 0.05, world, rank,
+                                     boxes_dev=boxes_d)
+        return sum(int(v.shape[0]) for v in res.values())
+
+    rendered = batch()                                     # warm-up (also loads every block's folded weights)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    frames_total = a.c5_frames if a.c5_frames > 0 else 2 * fb
+    reps = max(1, -(-frames_total // fb))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        batch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    tot = torch.tensor([float(rendered)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    sec = float(ms.item()) * 1e-3
+    frames = reps * fb
+    return {"workload": "C5: %d parent blocks x %d child AABBs, own networks per block, blocks sharded over %d GPU(s), batched "
+                        "two-step depth inference, %d frames x %d returns per batch" % (P, K5, world, fb, RAYS),
+            "metric": "depth-inference rays/s (physical rays, multi-parent scene)", "value": frames * RAYS / sec,
+            "unit": "rays/s", "frames_per_s": frames / sec, "frames_timed": frames, "frames_per_batch": fb,
+            "parents": P, "parents_per_gpu": len(owned), "child_aabbs_per_parent": K5,
+            "rendered_points_per_batch": float(tot.item()), "returns_per_batch": fb * RAYS, "ms_per_batch": 1e3 * sec / reps,
+            "N_samples": S, "N_importance": NI, "precision": a.precision, "scaling": "weak (frames per batch grow with N)"}
 
 
 def run_reference(a):

@@ -251,12 +251,24 @@ int pcnerf_tc_get_fused_eval(void);
 void pcnerf_tc_set_row_pairs(int on);
 int pcnerf_tc_get_row_pairs(void);
 
+/* Layered precision-1 forward (training mode, and eval mode with the fused kernel switched off): linear correction of
+ * the fp16 rounding of the folded weights W' = W_{l+1} diag(a_l) (nof/networks/models.py:183-203 evaluated layer by
+ * layer).  As the reference builds the network every activation is the identity (models.py:152,172), so the input of
+ * every layer is an affine function of the 64-d encoding x and the term the rounding loses, (W' - fp16(W')) H_l, is
+ * restored exactly by one extra K = 64 block [C | fp16(W')] x [x | H_l], C = (W' - fp16(W')) T_l (csrc/mlp_tc.cu,
+ * k_tc_fold); the layer-0 and skip-connection weights enter as hi + lo fp16 pairs.  1 (default) = on, 0 = the plain
+ * fp16(W') operands.  Initial value: environment variable PCNERF_TC_CORRECT. */
+void pcnerf_tc_set_weight_correction(int on);
+int pcnerf_tc_get_weight_correction(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K4  compositing + losses (nof/render.py:51-61, :75-161, :13-36, :166-226; train_kitti.py:145-146).
  * ---------------------------------------------------------------------------------------------------------- */
 
 #define PCNERF_COMP_CHILD_LOSS 1        /* masks + child free / depth losses (use_child_nerf_loss == 1) */
 #define PCNERF_COMP_OPACITY 2           /* opacity regulariser partial sums (render.py:224) */
+#define PCNERF_COMP_RANGE_LOSS 4        /* scene-level range loss term sum_r SmoothL1(10 depth_r, 10 rays[r, range_col]) -> sums[3]
+                                           (train_kitti.py:145-146 with loss_type smoothl1), fused into the same pass */
 
 /* p, z (n,P).  rays (n,ld): child near/far in columns cnear_col/cfar_col, range reading in range_col.
  * noise (n,P) or NULL is added as noise*noise_std before normalisation.
@@ -270,17 +282,31 @@ int pcnerf_composite_fwd(const float* p, const float* z, const float* rays, int 
                          float epsilon, int flags, float* w, float* depth, float* per_ray, double* sums,
                          void* stream);
 
-/* child_free_loss = sums[0]/n; child_depth_loss = (1/n)*0.1*(sums[1]/n)  (render.py:121,155) -> out2 (2) f32 */
-int pcnerf_composite_losses(const double* sums, int64_t n, float* out2, void* stream);
+/* child_free_loss = sums[0]/n; child_depth_loss = (1/n)*0.1*(sums[1]/n)  (render.py:121,155); range term =
+ * sums[3]/n = SmoothL1Loss(mean)(10 depth, 10 gt) (train_kitti.py:145-146 before the 0.1 * lambda_loss factor) -> out3 (3) f32 */
+int pcnerf_composite_losses(const double* sums, int64_t n, float* out3, void* stream);
 
 /* Backward.  Upstream gradients (any may be NULL): g_depth (n) for depth; g_free / g_dloss device scalars for the two
  * losses of pcnerf_composite_losses (n_total = number of rays their means are taken over); g_free_r / g_sl1_r (n) for
- * per_ray[:,0] / per_ray[:,2] (used by the use_child_nerf_divide == 1 segmented variant, render.py:106-119,135-152).
- * out grad_p (n,P) = dL/dp. */
+ * per_ray[:,0] / per_ray[:,2] (used by the use_child_nerf_divide == 1 segmented variant, render.py:106-119,135-152);
+ * g_range device scalar for the range term of pcnerf_composite_losses (flags & PCNERF_COMP_RANGE_LOSS; needs `depth`
+ * (n), the forward's output).  out grad_p (n,P) = dL/dp. */
 int pcnerf_composite_bwd(const float* p, const float* z, const float* w, const float* rays, int ld, int64_t n,
                          int P, int range_col, float noise_std, float epsilon, int flags, const float* per_ray,
                          const float* g_depth, const float* g_free, const float* g_dloss, const float* g_free_r,
-                         const float* g_sl1_r, int64_t n_total, float* grad_p, void* stream);
+                         const float* g_sl1_r, int64_t n_total, const float* depth, const float* g_range,
+                         float* grad_p, void* stream);
+
+/* Masked-mean losses / metrics on (n) vectors of rendered depths: nof/criteria/loss.py:7-50 (NOFSmoothL1Loss, NOFMSELoss,
+ * NOFL1Loss behind `nof_loss`; the scene-level range loss of train_kitti.py:145-146) and nof/criteria/metrics.py:5-21.
+ * kind: 0 SmoothL1 (beta 1), 1 MSE, 2 L1, 3 abs_error, 4 acc_thres (percent of |pred - target| < 0.2).  mask (n) uint8 or
+ * NULL (all elements).  acc2 (2) f64 scratch: sum of the elementwise terms, number of selected elements (kept for the
+ * backward).  out (1) f32 = the mean (NaN for an empty selection, like torch).  Backward (kinds 0..2): g_pred / g_target
+ * (n) = g_out[0] * d(mean)/d(pred | target); either may be NULL. */
+int pcnerf_masked_loss_fwd(int kind, const float* pred, const float* target, const uint8_t* mask, int64_t n, double* acc2,
+                           float* out, void* stream);
+int pcnerf_masked_loss_bwd(int kind, const float* pred, const float* target, const uint8_t* mask, int64_t n,
+                           const double* acc2, const float* g_out, float* g_pred, float* g_target, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K5  two-step depth-inference search (nof/render.py:229-368, :674-684).
@@ -293,9 +319,34 @@ int pcnerf_search_rows(const float* p, const float* z, const float* rays, int ld
                        int cnear_col, int cfar_col, float epsilon, int method, float* w, float* depth,
                        uint8_t* peak_in_child, float* wsum_child, double* sums, void* stream);
 
-/* Group winner selection (:317-340).  other (n) i64: head = followers, followers = 0.  out_flag (n) u8. */
+/* The same per-row search with the samples evaluated ONCE PER PHYSICAL RAY: all candidate rows of a group share origin,
+ * direction and the parent segment (:619-628; eval_kitti_render.py:379-390), so z, the occupancies and the weights of a
+ * group's rows are identical -- the reference recomputes them for every row.  p_ray / z_ray / w_ray (G,P) are indexed by
+ * physical ray, row r of `rays` (n_rows, ld) belongs to ray row_ray[r] (non-decreasing); only the child interval
+ * (cnear_col, cfar_col) and therefore masks, peak test, in-child sum and depth are per row.  w_ray may be NULL. */
+int pcnerf_search_rows_grouped(const float* p_ray, const float* z_ray, const float* rays, int ld, int64_t n_rows, int P,
+                               int cnear_col, int cfar_col, float epsilon, int method, const int32_t* row_ray,
+                               float* w_ray, float* depth, uint8_t* peak_in_child, float* wsum_child, double* sums,
+                               void* stream);
+
+/* Group winner selection (:317-340).  other (n) i64: head = followers, followers = 0.  out_flag (n) u8.
+ * n_rendered (device scalar, may be NULL): rows at or beyond *n_rendered never win (pcnerf_eval_rows_rendered). */
 int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in_child, const float* wsum_child, int64_t n,
-                         uint8_t* out_flag, void* stream);
+                         const int64_t* n_rendered, uint8_t* out_flag, void* stream);
+
+/* Group structure of the candidate rows, on the device: head_flag[i] = 1 where row i starts a group (the sequential walk
+ * of :317-340 / eval_kitti_render.py:449-450: a head carries its follower count, followers carry 0).
+ * pcnerf_group_uniform: *mismatch = number of rows whose ray (columns 0..5, pnear_col, pfar_col) differs bit-wise from the
+ * ray of their group's head row head_row[row_ray[i]] (0 for rows built by the reference's frame builders). */
+int pcnerf_group_heads(const int64_t* other, int64_t n, uint8_t* head_flag, void* stream);
+int pcnerf_group_uniform(const float* rays, int ld, int64_t n, const int32_t* row_ray, const int64_t* head_row,
+                         int pnear_col, int pfar_col, int* mismatch, void* stream);
+
+/* The group-aligned batch walk of eval_kitti_render.py:979-1005 / :1111-1136 (tag column: followers carry -1) on the
+ * device: *out_n = number of leading rows the reference's loop hands to the renderer -- n, or n - 1 when a batch ends one
+ * row before the end (`if i == n - 1: break`).  Batch boundaries change no value in eval mode (running statistics). */
+int pcnerf_eval_rows_rendered(const float* rays, int ld, int tag_col, int64_t n, int64_t batch_size_set, int64_t* out_n,
+                              void* stream);
 
 /* points = o + depth*d (:674-684). */
 int pcnerf_points(const float* rays, int ld, int64_t n, const float* depth, float* out_xyz, void* stream);
@@ -326,6 +377,15 @@ int pcnerf_frame_returns(const float* pts, int64_t n, const double* h_pose16, co
                          float rdy, float rdz, float max_range, float over_height, float over_low, float interest_x,
                          float interest_y, const double* h_box6, const double* h_pos3, uint8_t* keep, double* world,
                          double* dir, double* dist, void* stream);
+
+/* Multi-parent scenes (BASELINE.json configs[4]; the reference renders ONE parent block per run, README.md:46 describes a
+ * large scene as a collection of them): which[i] = index of the first of the P parent boxes (P x 6 doubles, min xyz then
+ * max xyz, closed) that contains return i, -1 if none.  origins (F,3) != NULL: also the ray of every return from the sensor
+ * position of its frame frame_id[i] (NULL: frame 0) -- origin_out (n,3), dir (n,3), dist (n), the expressions of
+ * eval_kitti_render.py:706-709 -- in the layout pcnerf_aabb_groups_count / _fill take.  All float64, P <= 1024. */
+int pcnerf_route_points(const double* pts, int64_t n, const double* boxes, int P, const double* origins,
+                        const int32_t* frame_id, int32_t* which, double* origin_out, double* dir, double* dist,
+                        void* stream);
 
 /* -------------------------------------------------------------------------------------------------------------
  * Optimizer step on one flat buffer: torch.optim.Adam as configured by nof/nof_utils.py:162-173

@@ -366,6 +366,68 @@ def golden_heads(ref):
     np.savez_compressed(os.path.join(OUT, "head_search.npz"), **save)
 
 
+def golden_c1(ref):
+    """BASELINE.json configs[0] ("C1"): MaiCity-00-shaped block, 1 parent + 8 child AABBs, 4,096 rays x 64 coarse (+128
+    importance, render_rays_train's own default, nof/render.py:417) samples, chunk 32,768, shipped training flags (segmented
+    sampling ratio 0.1, child losses on), perturb 0 (deterministic) -- the reference's own render_rays_train + the six-term
+    loss of train_kitti.py:145-155 + backward, executed TWICE: as shipped (float32) and with every tensor in float64
+    (torch default dtype float64: same code, same inputs, same weights) as the ground truth that arbitrates which
+    float32 differences are the reference's own rounding noise."""
+    import time
+    N, S, Ni, chunk, K = 4096, 64, 128, 32768, 8
+    rays32 = torch.from_numpy(synth.synth_train_rays(101, N, K=K))
+    lam = (1.0, 1e6, 1e5)
+    save = dict(rays=rays32.numpy(), S=S, Ni=Ni, chunk=chunk, K=K, lam=np.array(lam))
+
+    sd_c, sd_f = orc.init_state_dict(42), orc.init_state_dict(43)      # float32 values (drawn BEFORE the dtype switch)
+
+    def run(dtype, tag):
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)
+        try:
+            # parameters in the default dtype, holding exactly the float32 values
+            mc, mf, emb = ref.networks.NOF_coarse(), ref.networks.NOF_fine(), ref.networks.Embedding(3, 10)
+            mc.load_state_dict(sd_c)
+            mf.load_state_dict(sd_f)
+            mc.train()
+            mf.train()
+            rays = rays32.to(dtype)
+            t0 = time.time()
+            with ref_shim.cuda0_to_cpu():
+                res = ref.render.render_rays_train(mc, mf, emb, rays, N_samples=S, N_importance=Ni, perturb=0,
+                                                   noise_std=0, chunk=chunk, issegmentated=1, childnerf_ratio=0.1,
+                                                   use_child_nerf_divide=0, use_child_nerf_loss=1)
+            gt = rays[:, 14]
+            sl1 = torch.nn.SmoothL1Loss(reduction="mean")
+            lr_c = 1e-1 * lam[0] * sl1(1e1 * res["depth"], 1e1 * gt)
+            lr_f = 1e-1 * lam[0] * sl1(1e1 * res["depth_fine"], 1e1 * gt)
+            loss = lr_c + lr_f + lam[1] * res["child_free_loss_fine"] + lam[1] * res["child_free_loss"] \
+                + lam[2] * res["child_depth_loss_fine"] + lam[2] * res["child_depth_loss"]
+            loss.backward()
+            dt = time.time() - t0
+        finally:
+            torch.set_default_dtype(old)
+        save["%s_loss" % tag] = loss.item()
+        save["%s_loss_range" % tag] = lr_c.item()
+        save["%s_loss_range_fine" % tag] = lr_f.item()
+        save["%s_seconds" % tag] = dt
+        for k, v in res.items():
+            save["%s_%s" % (tag, k)] = v.detach().numpy()
+        for t_, m in (("c", mc), ("f", mf)):
+            for k, g in compress_grads({n: p.grad for n, p in m.named_parameters()}).items():
+                save["%s_grad_%s_%s" % (tag, t_, k)] = g
+        print("c1", tag, "loss", loss.item(), "%.1f s" % dt, {k: float(v.detach().sum()) for k, v in res.items()})
+        return res
+
+    r32 = run(torch.float32, "f32")
+    r64 = run(torch.float64, "f64")
+    for k in ("depth", "depth_fine"):
+        a, b = r32[k].detach().double().numpy(), r64[k].detach().numpy()
+        rel = np.abs(a - b) / np.abs(b)
+        print("c1 reference float32 vs float64 %s: median %.2e p99 %.2e max %.2e" % (k, np.median(rel), np.quantile(rel, .99), rel.max()))
+    np.savez_compressed(os.path.join(OUT, "c1_train.npz"), **save)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -382,6 +444,7 @@ def main():
         "system": lambda: golden_system(ref),
         "val": lambda: golden_val(ref),
         "view": lambda: golden_view(ref),
+        "c1": lambda: golden_c1(ref),
     }
     for k, fn in jobs.items():
         if a.only and a.only != k:

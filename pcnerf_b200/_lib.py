@@ -65,11 +65,20 @@ SIGNATURES = {
     "pcnerf_tc_get_fused_eval": (ci, []),
     "pcnerf_tc_set_row_pairs": (None, [ci]),
     "pcnerf_tc_get_row_pairs": (ci, []),
+    "pcnerf_tc_set_weight_correction": (None, [ci]),
+    "pcnerf_tc_get_weight_correction": (ci, []),
     "pcnerf_composite_fwd": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, ci, vp, f32, f32, ci, vp, vp, vp, vp, vp]),
     "pcnerf_composite_losses": (ci, [vp, i64, vp, vp]),
-    "pcnerf_composite_bwd": (ci, [vp, vp, vp, vp, ci, i64, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, vp, vp]),
+    "pcnerf_composite_bwd": (ci, [vp, vp, vp, vp, ci, i64, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
     "pcnerf_search_rows": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, f32, ci, vp, vp, vp, vp, vp, vp]),
-    "pcnerf_search_select": (ci, [vp, vp, vp, i64, vp, vp]),
+    "pcnerf_search_rows_grouped": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, f32, ci, vp, vp, vp, vp, vp, vp, vp]),
+    "pcnerf_search_select": (ci, [vp, vp, vp, i64, vp, vp, vp]),
+    "pcnerf_masked_loss_fwd": (ci, [ci, vp, vp, vp, i64, vp, vp, vp]),
+    "pcnerf_masked_loss_bwd": (ci, [ci, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
+    "pcnerf_route_points": (ci, [vp, i64, vp, ci, vp, vp, vp, vp, vp, vp, vp]),
+    "pcnerf_group_heads": (ci, [vp, i64, vp, vp]),
+    "pcnerf_group_uniform": (ci, [vp, ci, i64, vp, vp, ci, ci, vp, vp]),
+    "pcnerf_eval_rows_rendered": (ci, [vp, ci, ci, i64, i64, vp, vp]),
     "pcnerf_points": (ci, [vp, ci, i64, vp, vp, vp]),
     "pcnerf_adam_step": (ci, [vp, vp, vp, vp, i64, vp, vp, vp, f32, f32, f32, f32, f32, vp]),
     "pcnerf_frame_returns": (ci, [vp, i64, PD, vp, ci, f32, f32, f32, f32, f32, f32, f32, f32, PD, PD, vp, vp, vp, vp, vp]),

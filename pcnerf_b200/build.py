@@ -27,6 +27,7 @@ SOURCES = {
     "metrics.cu": ["-fmad=false"],
     "frame.cu": ["-fmad=false"],
     "optim.cu": [],
+    "loss.cu": [],
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
           "-Xcompiler", "-fPIC"]

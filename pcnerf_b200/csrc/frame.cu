@@ -75,3 +75,49 @@ extern "C" int pcnerf_frame_returns(const float* pts, int64_t n, const double* h
     PCN_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-parent scenes (BASELINE.json configs[4]; README.md:46: a large scene is a collection of parent NeRF blocks, each
+// with its own networks and child boxes).  One thread per return: index of the FIRST parent block whose closed box contains
+// the point (-1: none), and the ray from the sensor position of the return's frame (direction, range: the expressions of
+// eval_kitti_render.py:706-709).  The parent boxes (P x 6 doubles: min xyz, max xyz) sit in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_route_points(const double* __restrict__ pts, int64_t n, const double* __restrict__ boxes, int P,
+                               const double* __restrict__ origins, const int32_t* __restrict__ frame_id,
+                               int32_t* __restrict__ which, double* __restrict__ origin_out, double* __restrict__ dir,
+                               double* __restrict__ dist) {
+    extern __shared__ double sb[];
+    for (int i = threadIdx.x; i < 6 * P; i += blockDim.x) sb[i] = boxes[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    int w = -1;
+    for (int b = 0; b < P; ++b) {
+        const double* q = sb + 6 * b;
+        if (x >= q[0] && y >= q[1] && z >= q[2] && x <= q[3] && y <= q[4] && z <= q[5]) { w = b; break; }
+    }
+    which[i] = w;
+    if (origins) {
+        const double* o = origins + 3 * (frame_id ? frame_id[i] : 0);
+        const double vx = x - o[0], vy = y - o[1], vz = z - o[2];
+        const double d = sqrt((vx * vx + vy * vy) + vz * vz);
+        origin_out[3 * i] = o[0]; origin_out[3 * i + 1] = o[1]; origin_out[3 * i + 2] = o[2];
+        dir[3 * i] = vx / d; dir[3 * i + 1] = vy / d; dir[3 * i + 2] = vz / d;
+        dist[i] = d;
+    }
+}
+
+extern "C" int pcnerf_route_points(const double* pts, int64_t n, const double* boxes, int P, const double* origins,
+                                   const int32_t* frame_id, int32_t* which, double* origin_out, double* dir, double* dist,
+                                   void* stream) {
+    PCN_CHECK_ARG(n >= 0 && P >= 1 && P <= 1024 && boxes && (n == 0 || (pts && which)), "route_points: bad arguments (at most 1024 parent blocks)");
+    PCN_CHECK_ARG(!origins || (origin_out && dir && dist), "route_points: origins given but no ray outputs");
+    if (n == 0) return 0;
+    const size_t smem = (size_t)6 * P * sizeof(double);
+    PcnScope ps(PCN_K_AABB, (cudaStream_t)stream, (double)n * (24.0 + 4.0 + (origins ? 84.0 : 0.0)));
+    k_route_points<<<(int)pcn_cdiv(n, 256), 256, smem, (cudaStream_t)stream>>>(pts, n, boxes, P, origins, frame_id, which,
+                                                                               origin_out, dir, dist);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}

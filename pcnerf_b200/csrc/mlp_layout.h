@@ -40,7 +40,7 @@ struct MlpLayout {
         n_dstat = 16 * 512 + 8 * 256;
         off_dstat = o; o += al256(n_dstat * sizeof(double));
         off_tc = o;              // 16-bit copies of the weights for the tensor-core path
-        o += al256((size_t)2 * 8 * 256 * 320 * 2 + 4096);
+        o += al256((size_t)8 * 256 * 384 * 2 + (size_t)8 * 256 * 256 * 2 + 4096);
         off_hf[0] = off_hf[1] = off_encb = o;      // (unused since the weight-gradient kernel converts in shared memory)
         off_rgwork = o;                            // row-GEMM CTA counter + per-CTA statistic partials (precision 1)
         if (precision == 1) o += al256(256 + 160 * 2 * 256 * 8);

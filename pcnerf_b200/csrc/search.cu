@@ -36,10 +36,14 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     return m >= n ? per - 1 - m : m;
 }
 
+// row_ray != NULL ("grouped" form): p, z and w are indexed by PHYSICAL ray, row r reads ray row_ray[r] (all candidate rows of
+// a group share origin, direction and the parent segment, nof/render.py:619-628, so their samples, occupancies and
+// weights are identical: they are evaluated once per ray); the head row of every group (the first row that maps to the
+// ray) writes the ray's weights.  row_ray == NULL: one (p, z, w) row per candidate row, as the reference evaluates them.
 __global__ void k_search_rows(const float* __restrict__ p, const float* __restrict__ z, const float* __restrict__ rays,
                               int ld, int64_t n, int P, int cnear_col, int cfar_col, float epsilon, int method,
-                              GaussK gk, float* __restrict__ w, float* __restrict__ depth,
-                              uint8_t* __restrict__ peak_in, float* __restrict__ wsum_child,
+                              GaussK gk, const int32_t* __restrict__ row_ray, float* __restrict__ w,
+                              float* __restrict__ depth, uint8_t* __restrict__ peak_in, float* __restrict__ wsum_child,
                               double* __restrict__ sums) {
     extern __shared__ double smd[];
     __shared__ double red[8];
@@ -50,12 +54,14 @@ __global__ void k_search_rows(const float* __restrict__ p, const float* __restri
     float* sw = sz + P;
     double acc_op = 0;
     for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < n; r += (int64_t)gridDim.x * wpb) {
-        for (int i = lane; i < P; i += 32) sz[i] = z[r * P + i];
+        const int64_t g = row_ray ? (int64_t)row_ray[r] : r;               // row of p / z / w
+        const bool put_w = w != nullptr && (!row_ray || r == 0 || row_ray[r - 1] != row_ray[r]);
+        for (int i = lane; i < P; i += 32) sz[i] = z[g * P + i];
         // weights (render.py:241-246)
         float carry = 1.f, sumv = 0.f, op = 0.f;
         for (int base = 0; base < P; base += 32) {
             const int i = base + lane;
-            const float pi = i < P ? p[r * P + i] : 0.f;
+            const float pi = i < P ? p[g * P + i] : 0.f;
             const float fr = __fsub_rn(1.f, pi);
             float incl = fr;
 #pragma unroll
@@ -78,7 +84,7 @@ __global__ void k_search_rows(const float* __restrict__ p, const float* __restri
         for (int i = lane; i < P; i += 32) {
             const float wi = __fdiv_rn(sw[i], denom);
             sw[i] = wi;
-            w[r * P + i] = wi;
+            if (put_w) w[g * P + i] = wi;
         }
         __syncwarp();
         const float cn = rays[r * ld + cnear_col], cf = rays[r * ld + cfar_col];
@@ -175,9 +181,53 @@ __global__ void k_select_winner(const int64_t* __restrict__ other, const uint8_t
     flag[win] = (win == i) ? 1 : 3;            // single writer per byte: rows i+1..i+k belong to this head only
 }
 
-__global__ void k_select_clear(int64_t n, uint8_t* __restrict__ flag) {
+// (rows at or beyond *n_eff were never handed to the renderer by the batch driver: see k_eval_walk)
+__global__ void k_select_clear(int64_t n, const int64_t* __restrict__ n_eff, uint8_t* __restrict__ flag) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) flag[i] &= 1;
+    if (i < n) flag[i] = (n_eff && i >= *n_eff) ? 0 : (flag[i] & 1);
+}
+
+// head_flag[i] = 1 for rows that start a candidate group (everything k_select_cover did not mark as a follower)
+__global__ void k_group_heads(int64_t n, uint8_t* __restrict__ flag) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (flag[i] & 2) ? 0 : 1;
+}
+
+// mismatch += number of rows whose ray (columns 0..5 and the parent segment columns) differs from their group head's
+__global__ void k_group_uniform(const float* __restrict__ rays, int ld, int64_t n, const int32_t* __restrict__ row_ray,
+                                const int64_t* __restrict__ head_row, int c0, int c1, int* __restrict__ mismatch) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = rays + i * ld;
+    const float* b = rays + head_row[row_ray[i]] * ld;
+    bool same = a[c0] == b[c0] && a[c1] == b[c1];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) same = same && a[k] == b[k];
+    if (!same) atomicAdd(mismatch, 1);
+}
+
+// The batch walk of eval_kitti_render.py:979-1005 / :1111-1136 on the device (one thread: ~n / batch steps).  Batches are
+// extended so that no candidate group is split (follower rows carry -1 in the tag column); results do not depend on the
+// batch boundaries in eval mode (running statistics) EXCEPT for one quirk: when a batch ends exactly one row before the
+// end, the loop stops (`if i == n - 1: break`) and that last row is never rendered.  out[0] = number of rows rendered.
+__global__ void k_eval_walk(const float* __restrict__ rays, int ld, int tag_col, int64_t n, int64_t batch,
+                            int64_t* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int64_t i = 0;
+    while (i < n) {
+        if (i == n - 1) break;
+        if ((double)(i + batch) < (double)n - 0.5 * (double)batch) {
+            int64_t extra = 0;
+            while (rays[(i + batch + extra) * ld + tag_col] < -0.5f) {
+                ++extra;
+                if (i + batch + extra == n) break;
+            }
+            i = i + batch + extra;
+        } else {
+            i = n;
+        }
+    }
+    out[0] = i;
 }
 
 __global__ void k_points(const float* __restrict__ rays, int ld, int64_t n, const float* __restrict__ depth,
@@ -191,10 +241,11 @@ __global__ void k_points(const float* __restrict__ rays, int ld, int64_t n, cons
     out[3 * i + 2] = __fadd_rn(r[2], __fmul_rn(d, r[5]));
 }
 
-extern "C" int pcnerf_search_rows(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
-                                  int cnear_col, int cfar_col, float epsilon, int method, float* w, float* depth,
-                                  uint8_t* peak_in_child, float* wsum_child, double* sums, void* stream) {
+static int search_rows_impl(const float* p, const float* z, const float* rays, int ld, int64_t n, int P, int cnear_col,
+                            int cfar_col, float epsilon, int method, const int32_t* row_ray, float* w, float* depth,
+                            uint8_t* peak_in_child, float* wsum_child, double* sums, void* stream) {
     PCN_CHECK_ARG(n >= 0 && P >= 1 && cnear_col < ld && cfar_col < ld && sums, "search_rows: bad arguments");
+    PCN_CHECK_ARG(row_ray || w, "search_rows: the per-row form needs the weights output");
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), st));
     if (n == 0) return 0;
@@ -225,14 +276,64 @@ extern "C" int pcnerf_search_rows(const float* p, const float* z, const float* r
     const int64_t cap = (int64_t)PCN_SM_COUNT * 16;
     if (grid > cap) grid = cap;
     PcnScope ps(PCN_K_SEARCH, st, (double)n * (8.0 + 12.0 * P + 13.0));
-    k_search_rows<<<(int)grid, wpb * 32, smem, st>>>(p, z, rays, ld, n, P, cnear_col, cfar_col, epsilon, method, gk, w,
-                                                    depth, peak_in_child, wsum_child, sums);
+    k_search_rows<<<(int)grid, wpb * 32, smem, st>>>(p, z, rays, ld, n, P, cnear_col, cfar_col, epsilon, method, gk, row_ray,
+                                                    w, depth, peak_in_child, wsum_child, sums);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_search_rows(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
+                                  int cnear_col, int cfar_col, float epsilon, int method, float* w, float* depth,
+                                  uint8_t* peak_in_child, float* wsum_child, double* sums, void* stream) {
+    return search_rows_impl(p, z, rays, ld, n, P, cnear_col, cfar_col, epsilon, method, nullptr, w, depth, peak_in_child,
+                            wsum_child, sums, stream);
+}
+
+extern "C" int pcnerf_search_rows_grouped(const float* p_ray, const float* z_ray, const float* rays, int ld, int64_t n_rows,
+                                          int P, int cnear_col, int cfar_col, float epsilon, int method,
+                                          const int32_t* row_ray, float* w_ray, float* depth, uint8_t* peak_in_child,
+                                          float* wsum_child, double* sums, void* stream) {
+    PCN_CHECK_ARG(row_ray, "search_rows_grouped: null row -> ray map");
+    return search_rows_impl(p_ray, z_ray, rays, ld, n_rows, P, cnear_col, cfar_col, epsilon, method, row_ray, w_ray, depth,
+                            peak_in_child, wsum_child, sums, stream);
+}
+
+extern "C" int pcnerf_group_heads(const int64_t* other, int64_t n, uint8_t* head_flag, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && (n == 0 || (other && head_flag)), "group_heads: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    PCN_CUDA(cudaMemsetAsync(head_flag, 0, (size_t)n, st));
+    const int g = (int)pcn_cdiv(n, 256);
+    PcnScope ps(PCN_K_SEARCH, st, (double)n * 10.0, 2);
+    k_select_cover<<<g, 256, 0, st>>>(other, n, head_flag);
+    k_group_heads<<<g, 256, 0, st>>>(n, head_flag);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_group_uniform(const float* rays, int ld, int64_t n, const int32_t* row_ray, const int64_t* head_row,
+                                    int pnear_col, int pfar_col, int* mismatch, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && ld >= 6 && pnear_col < ld && pfar_col < ld && mismatch, "group_uniform: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCN_CUDA(cudaMemsetAsync(mismatch, 0, sizeof(int), st));
+    if (n == 0) return 0;
+    PcnScope ps(PCN_K_SEARCH, st, (double)n * 68.0);
+    k_group_uniform<<<(int)pcn_cdiv(n, 256), 256, 0, st>>>(rays, ld, n, row_ray, head_row, pnear_col, pfar_col, mismatch);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pcnerf_eval_rows_rendered(const float* rays, int ld, int tag_col, int64_t n, int64_t batch_size_set,
+                                         int64_t* out_n, void* stream) {
+    PCN_CHECK_ARG(n >= 0 && batch_size_set >= 1 && tag_col < ld && out_n, "eval_rows_rendered: bad arguments");
+    PcnScope ps(PCN_K_SEARCH, (cudaStream_t)stream, (double)n * 4.0 / (double)batch_size_set);
+    k_eval_walk<<<1, 32, 0, (cudaStream_t)stream>>>(rays, ld, tag_col, n, batch_size_set, out_n);
     PCN_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in_child, const float* wsum_child,
-                                    int64_t n, uint8_t* out_flag, void* stream) {
+                                    int64_t n, const int64_t* n_rendered, uint8_t* out_flag, void* stream) {
     PCN_CHECK_ARG(n >= 0, "search_select: bad size");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return 0;
@@ -241,7 +342,7 @@ extern "C" int pcnerf_search_select(const int64_t* other, const uint8_t* peak_in
     PcnScope ps(PCN_K_SEARCH, st, (double)n * 15.0, 3);
     k_select_cover<<<g, 256, 0, st>>>(other, n, out_flag);
     k_select_winner<<<g, 256, 0, st>>>(other, peak_in_child, wsum_child, n, out_flag);
-    k_select_clear<<<g, 256, 0, st>>>(n, out_flag);
+    k_select_clear<<<g, 256, 0, st>>>(n, n_rendered, out_flag);
     PCN_LAUNCH_CHECK();
     return 0;
 }

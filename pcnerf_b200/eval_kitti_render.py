@@ -61,12 +61,78 @@ def eval_batches(dataset_rays_last_col, batch_size_set):
     return out
 
 
+class FramePlan(ops.GroupPlan):
+    """ops.GroupPlan of one frame's candidate rows + the number of rows the reference's batch loop renders (device scalar).
+    Built once per frame by whoever produces the rows (the group builder K1 / a loaded .npy cache); costs one host sync."""
+
+    def __init__(self, dataset_rays, dataset_other, batch_size_set):
+        super().__init__(dataset_rays, dataset_other)
+        self.batch_size_set = int(batch_size_set)
+        self.n_rendered = ops.eval_rows_rendered(dataset_rays, batch_size_set)
+
+
+FRAME_ENC_BYTES = 6 << 30       # encodings of one ray batch of the grouped frame path (fp32: 256 B, fp16: 128 B per sample)
+
+
 @torch.no_grad()
 def render_frame(nof_coarse_model, nof_fine_model, embedding_position, dataset_rays, dataset_other, N_samples,
                  N_importance, chunk, depth_inference_method=2, batch_size_set=18432, use_disp=False, perturb=0,
-                 noise_std=0):
-    """The per-frame loop of eval_kitti_render.py:979-1030: batch, render, keep the rows flagged by the fine pass.
-    Returns the rendered point cloud (M,3) on the device."""
+                 noise_std=0, plan=None):
+    """The per-frame loop of eval_kitti_render.py:979-1030: render the candidate rows, keep the rows flagged by the fine
+    pass.  Returns the rendered point cloud (M,3) on the device.
+
+    The reference walks the rows in group-aligned batches of `batch_size_set` (an out-of-memory guard: with eval-mode
+    BatchNorm no value depends on the batch boundaries) and evaluates every candidate row.  Here the frame is rendered
+    ONCE PER PHYSICAL RAY (nof.render._view_grouped's argument: the rows of a group share their samples): coarse and fine
+    MLP passes over the G physical rays in a few large ray batches, then one K5 pass over all N' rows (child masks, peak
+    test, in-child depth, group winner).  No host synchronisation besides the final compaction; the one quirk of the
+    reference loop that does depend on the batch walk (a lone trailing row is never rendered) is reproduced on the device
+    (FramePlan.n_rendered).  With perturb != 0 (per-row random numbers) the per-row batch loop below is used."""
+    from .nof import render as R
+    if perturb != 0 or not R.GROUP_RAYS or dataset_rays.shape[0] == 0:
+        return _render_frame_rows(nof_coarse_model, nof_fine_model, embedding_position, dataset_rays, dataset_other,
+                                  N_samples, N_importance, chunk, depth_inference_method, batch_size_set, use_disp, perturb,
+                                  noise_std)
+    if plan is None:
+        plan = FramePlan(dataset_rays, dataset_other, batch_size_set)
+    if not plan.uniform or plan.batch_size_set != int(batch_size_set):
+        return _render_frame_rows(nof_coarse_model, nof_fine_model, embedding_position, dataset_rays, dataset_other,
+                                  N_samples, N_importance, chunk, depth_inference_method, batch_size_set, use_disp, perturb,
+                                  noise_std)
+    rays = dataset_rays.contiguous()
+    dev = rays.device
+    G, S, F = plan.G, int(N_samples), int(N_samples) + int(N_importance)
+    tc_c, tc_f = nof_coarse_model.mlp_precision() == 1, nof_fine_model.mlp_precision() == 1
+    hr = rays.index_select(0, plan.head_rows)                        # (G,13): one row per physical ray
+    per_ray = F * (128 if tc_f else 256)
+    B = max(1, min(G, FRAME_ENC_BYTES // per_ray))
+    zf = torch.empty((G, F), dtype=torch.float32, device=dev)
+    pf = torch.empty((G, F), dtype=torch.float32, device=dev)
+    for g0 in range(0, G, B):
+        h = hr[g0:g0 + B]
+        z, enc = ops.sample_encode_coarse(h, S, 0, 9, 10, 10, 11, False, 0.0, None, True, tc_c)
+        p = nof_coarse_model.forward_encoded(enc, chunk).view(-1, S)
+        del enc
+        _, w, _, _, _ = ops.search_rows(p, z, h, 6, 7, 1e-10, depth_inference_method)     # the coarse weights (K5 arithmetic)
+        zf_b, encf = ops.sample_encode_fine(h, z, w, int(N_importance), None, True, True, tc_f)
+        pf_b = nof_fine_model.forward_encoded(encf, chunk).view(-1, F)
+        del encf
+        if B >= G:
+            zf, pf = zf_b, pf_b
+        else:
+            zf[g0:g0 + B].copy_(zf_b)
+            pf[g0:g0 + B].copy_(pf_b)
+    depth, _, _, peak, wsum = ops.search_rows(pf, zf, rays, 6, 7, 1e-10, depth_inference_method, row_ray=plan.row_ray,
+                                              want_w=False)
+    keep = ops.search_select(plan.other, peak, wsum, n_rendered=plan.n_rendered).reshape(-1)
+    return ops.points(rays, depth)[keep]
+
+
+@torch.no_grad()
+def _render_frame_rows(nof_coarse_model, nof_fine_model, embedding_position, dataset_rays, dataset_other, N_samples,
+                       N_importance, chunk, depth_inference_method=2, batch_size_set=18432, use_disp=False, perturb=0,
+                       noise_std=0):
+    """The reference's loop as it stands (eval_kitti_render.py:979-1030): group-aligned batches, every candidate row."""
     tags = dataset_rays[:, -1].cpu().numpy()
     pts = []
     for a, b in eval_batches(tags, batch_size_set):

@@ -1,33 +1,31 @@
-"""Drop-in for nof/criteria/loss.py:7-50 (masked-mean SmoothL1 / MSE / L1 wrappers).  These act on (N,) vectors of
-rendered depths -- negligible work, kept as torch ops on the device so that they stay on the autograd tape."""
+"""Drop-in for nof/criteria/loss.py:7-50: the range-loss modules behind `nof_loss` (train_kitti.py:46-48, :145-146).
+
+Same class names and call signature `loss(pred, target, valid_mask=None)` as the reference; the arithmetic (optional
+boolean selection, elementwise SmoothL1 / squared / absolute difference, mean over the selected elements, and the backward of
+all of it) is one reduction kernel and one elementwise kernel of libpcnerf_b200.so (csrc/loss.cu, ops.masked_loss) instead
+of a chain of eager torch kernels."""
 from torch import nn
+
+from ... import ops
 
 
 class NOFLoss(nn.Module):
-    def __init__(self):
-        super(NOFLoss, self).__init__()
-        self.loss = None
+    """Base: `kind` names the elementwise term (ops.LOSS_KINDS); subclasses only choose it."""
+    kind = None
 
     def forward(self, pred, target, valid_mask=None):
-        if valid_mask is not None:
-            pred = pred[valid_mask]
-            target = target[valid_mask]
-        return self.loss(pred, target)
+        if self.kind is None:
+            raise TypeError("NOFLoss is abstract: use NOFSmoothL1Loss, NOFMSELoss or NOFL1Loss (nof_loss[...])")
+        return ops.masked_loss(pred, target, valid_mask, self.kind)
 
 
 class NOFMSELoss(NOFLoss):
-    def __init__(self):
-        super(NOFMSELoss, self).__init__()
-        self.loss = nn.MSELoss(reduction='mean')
+    kind = "mse"
 
 
 class NOFL1Loss(NOFLoss):
-    def __init__(self):
-        super(NOFL1Loss, self).__init__()
-        self.loss = nn.L1Loss(reduction='mean')
+    kind = "l1"
 
 
 class NOFSmoothL1Loss(NOFLoss):
-    def __init__(self):
-        super(NOFSmoothL1Loss, self).__init__()
-        self.loss = nn.SmoothL1Loss(reduction='mean')
+    kind = "smoothl1"

@@ -58,24 +58,28 @@ def inference_val(model, embedding_xy, samples_xy, rays, z_vals, near_far_child,
     enc = _enc if _enc is not None else _embed_samples(samples_xy, _tc(model))
     p = model.forward_encoded(enc, chunk).view(N_rays, N_samples)
     nz = _noise(z_vals.shape, z_vals.device, noise_std, noise)
-    w, depth, _, _, _, _, _ = ops.composite(p, z_vals, None, (0, 0, 0), nz, noise_std, epsilon, 0)
+    w, depth = ops.composite(p, z_vals, None, (0, 0, 0), nz, noise_std, epsilon, 0)[:2]
     return depth, w
 
 
 def inference_train(model, embedding_xy, samples_xy, rays, z_vals, near_far_child, near_far_point, range_readings,
                     ray_class, chunk=1024 * 32, noise_std=1, epsilon=1e-10, isval=False, sub_nerf_test_num=4,
-                    use_child_nerf_divide=1, use_child_nerf_loss=0, *, noise=None, _enc=None):
+                    use_child_nerf_divide=1, use_child_nerf_loss=0, *, noise=None, _enc=None, _extra=None):
     """nof/render.py:38-163.  `near_far_child` / `range_readings` are read from `rays` columns 10:12 / -1 exactly as
-    the reference's caller packs them (render.py:424-427)."""
+    the reference's caller packs them (render.py:424-427).
+    _extra (dict, optional): receives 'range_sl1' = SmoothL1Loss(mean)(10 depth, 10 rays[:, -1]) -- the scene-level range term
+    of train_kitti.py:145-146 before its 0.1 * lambda_loss factor -- accumulated by K4 in the same pass (and back-propagated
+    by K4's backward), so the caller needs no separate loss kernels."""
     N_rays, N_samples = z_vals.shape
     enc = _enc if _enc is not None else _embed_samples(samples_xy, _tc(model))
     p = model.forward_encoded(enc, chunk).view(N_rays, N_samples)
     nz = _noise(z_vals.shape, z_vals.device, noise_std, noise)
     ld = rays.shape[1]
+    rl = ops.COMP_RANGE_LOSS if (_extra is not None and noise_std == 0) else 0
     if use_child_nerf_loss == 1:
         divide = use_child_nerf_divide == 1
-        w, depth, fl, dl, free_r, sl1_r, _ = ops.composite(p, z_vals, rays, (10, 11, ld - 1), nz, noise_std, epsilon,
-                                                          ops.COMP_CHILD_LOSS, divide)
+        w, depth, fl, dl, free_r, sl1_r, _, rsl = ops.composite(p, z_vals, rays, (10, 11, ld - 1), nz, noise_std, epsilon,
+                                                               ops.COMP_CHILD_LOSS | rl, divide)
         if divide:
             # render.py:106-119, :135-152: per-child means summed over sub_nerf_test_num children (column 9)
             sub = rays[:, 9]
@@ -88,9 +92,12 @@ def inference_train(model, embedding_xy, samples_xy, rays, z_vals, near_far_chil
                     fl = fl + free_r[sel].sum() / cnt
                     dl = dl + 1 / cnt * 0.1 * sl1_r[sel].mean()
     else:
-        w, depth, _, _, _, _, _ = ops.composite(p, z_vals, None, (0, 0, 0), nz, noise_std, epsilon, 0)
+        out = ops.composite(p, z_vals, rays if rl else None, (0, 0, ld - 1) if rl else (0, 0, 0), nz, noise_std, epsilon, rl)
+        w, depth, rsl = out[0], out[1], out[7]
         fl = torch.tensor(0.0)          # CPU scalars, as in the reference (render.py:123-125,157-159)
         dl = torch.tensor(0.0)
+    if rl:
+        _extra["range_sl1"] = rsl
     return fl, dl, depth, w
 
 
@@ -104,9 +111,8 @@ def inference(model, embedding_xy, samples_xy, z_vals, chunk=1024 * 32, noise_st
     if isval is not False:
         raise NotImplementedError("inference(isval=True) returns un-normalised weights in the reference; no caller "
                                   "reaches that branch (render_rays passes isval into the epsilon slot)")
-    w, depth, _, _, _, _, opacity = ops.composite(p, z_vals, None, (0, 0, 0), nz, noise_std, float(epsilon),
-                                                  ops.COMP_OPACITY)
-    return depth, w, opacity
+    out = ops.composite(p, z_vals, None, (0, 0, 0), nz, noise_std, float(epsilon), ops.COMP_OPACITY)
+    return out[1], out[0], out[6]
 
 
 def inference_0525_2(model, embedding_xy, samples_xy, z_vals, other_interest_sub_nerf_number, near_far_child,
@@ -156,14 +162,20 @@ def render_rays_train(model, model_fine, embedding_xy, rays, sub_nerf_test_num=4
     noises = (noise, noise_fine)
 
     def head(net, enc, z, which):
+        extra = {}
         fl, dl, depth, w = inference_train(net, embedding_xy, None, rays, z, None, None, None, None, chunk, noise_std,
                                            1e-10, isval, sub_nerf_test_num, use_child_nerf_divide, use_child_nerf_loss,
-                                           noise=noises[which], _enc=enc)
-        return {"fl": fl, "dl": dl, "depth": depth, "w": w}
+                                           noise=noises[which], _enc=enc, _extra=extra)
+        return {"fl": fl, "dl": dl, "depth": depth, "w": w, "rsl": extra.get("range_sl1")}
 
     _, _, c, f = _two_pass(model, model_fine, rays, n_a, n_b, N_importance, False, perturb, U, u, 6, 7, head)
-    return {'child_free_loss_fine': f["fl"], 'child_depth_loss_fine': f["dl"], "depth_fine": f["depth"],
-            'child_free_loss': c["fl"], 'child_depth_loss': c["dl"], 'depth': c["depth"]}
+    out = {'child_free_loss_fine': f["fl"], 'child_depth_loss_fine': f["dl"], "depth_fine": f["depth"],
+           'child_free_loss': c["fl"], 'child_depth_loss': c["dl"], 'depth': c["depth"]}
+    if c["rsl"] is not None:
+        # beyond the reference's six keys: SmoothL1Loss(mean)(10 depth, 10 rays[:, -1]) of both passes, fused into K4
+        # (train_kitti.py:145-146; `batch['ranges']` IS rays[:, 14], ipb2dmapping.py:447-453)
+        out["range_sl1"], out["range_sl1_fine"] = c["rsl"], f["rsl"]
+    return out
 
 
 def render_rays_val(model, model_fine, embedding_xy, rays, sub_nerf_test_num=4, N_samples=64, N_importance=128,
@@ -200,10 +212,24 @@ def render_rays(model, model_fine, embedding_xy, rays, N_samples=64, N_importanc
             "depth2": zf[weights_mask], "opacity_fine": f["opacity"]}
 
 
+GROUP_RAYS = True       # depth inference: evaluate samples once per physical ray instead of once per candidate row
+
+
 def render_rays_view_0525_2_2(model, model_fine, embedding_xy, rays, other_interest_sub_nerf_number, N_samples=64,
                               N_importance=128, use_disp=False, perturb=0, noise_std=1, chunk=1024 * 3, isval=False,
-                              depth_inference_method=0, *, U=None, u=None):
-    """nof/render.py:614-699: z uniform over the PARENT segment (cols 9,10), child interval in cols 6,7."""
+                              depth_inference_method=0, *, U=None, u=None, plan=None):
+    """nof/render.py:614-699: z uniform over the PARENT segment (cols 9,10), child interval in cols 6,7.
+
+    All candidate rows of a group share origin, direction and the parent segment (eval_kitti_render.py:379-390), so with
+    perturb == 0 their samples, occupancies and weights are identical; the reference evaluates them once per ROW, this
+    path once per PHYSICAL RAY (2.9 rows per ray on the shipped frames) whenever that holds for the given
+    rows (checked on the device, ops.GroupPlan) -- the per-row quantities (child masks, peak test, in-child sum, depth,
+    flags) are computed per row from the ray's samples.  Results are bit-identical to the per-row evaluation."""
+    if GROUP_RAYS and perturb == 0 and U is None and u is None and rays.shape[0] > 0:
+        if plan is None:
+            plan = ops.GroupPlan(rays, other_interest_sub_nerf_number)
+        if plan.uniform and plan.G < rays.shape[0]:
+            return _view_grouped(model, model_fine, rays, plan, N_samples, N_importance, chunk, depth_inference_method)
     nfc = rays[:, 6:8]
 
     def head(net, enc, z, which):
@@ -217,3 +243,23 @@ def render_rays_view_0525_2_2(model, model_fine, embedding_xy, rays, other_inter
             "opacity_fine": f["opacity"], "points_inference_fine": ops.points(rays, f["depth"]),
             "points_inference": ops.points(rays, c["depth"]), "rays_effective_flag": c["flag"],
             "rays_effective_flag_fine": f["flag"]}
+
+
+def _view_grouped(model, model_fine, rays, plan, N_samples, N_importance, chunk, method):
+    """render_rays_view_0525_2_2 with the samples evaluated once per physical ray (same result dict, per candidate row)."""
+    rays = rays.contiguous()
+    hr = rays.index_select(0, plan.head_rows)                       # (G,13) one row per physical ray
+    G = plan.G
+    z, enc = ops.sample_encode_coarse(hr, N_samples, 0, 9, 10, 10, 11, False, 0.0, None, True, _tc(model))
+    p = model.forward_encoded(enc, chunk).view(G, N_samples)
+    depth_c, w, op_c, peak, wsum = ops.search_rows(p, z, rays, 6, 7, 1e-10, method, row_ray=plan.row_ray)
+    flag_c = ops.search_select(plan.other, peak, wsum)
+    zf, encf = ops.sample_encode_fine(hr, z, w, N_importance, None, True, True, _tc(model_fine))
+    pf = model_fine.forward_encoded(encf, chunk).view(G, N_samples + N_importance)
+    depth_f, wf, op_f, peak, wsum = ops.search_rows(pf, zf, rays, 6, 7, 1e-10, method, row_ray=plan.row_ray)
+    flag_f = ops.search_select(plan.other, peak, wsum)
+    rr = plan.row_ray.to(torch.int64)
+    return {'depth_fine': depth_f, 'weights': wf.index_select(0, rr), 'opacity': op_c, 'z_vals': zf.index_select(0, rr),
+            "depth": depth_c, "opacity_fine": op_f, "points_inference_fine": ops.points(rays, depth_f),
+            "points_inference": ops.points(rays, depth_c), "rays_effective_flag": flag_c,
+            "rays_effective_flag_fine": flag_f}

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import MlpGrads, MlpParams, check, lib
 
-COMP_CHILD_LOSS, COMP_OPACITY = 1, 2
+COMP_CHILD_LOSS, COMP_OPACITY, COMP_RANGE_LOSS = 1, 2, 4
 _f64p = ctypes.POINTER(ctypes.c_double)
 
 def launch_count(reset=False):
@@ -191,6 +191,27 @@ def frame_returns(points_f32, pose, pose_xy, range_delete, max_range, over_heigh
     return world[sel], dirs[sel], dist[sel]
 
 
+def route_points(points, parent_boxes, origins=None, frame_id=None):
+    """Multi-parent scenes: (which (n,) int32 = first parent box containing each return or -1, origin (n,3), dir (n,3),
+    dist (n,) float64 rays from the sensor position of each return's frame).  parent_boxes (P,6) min xyz, max xyz."""
+    pts = _f64(points).reshape(-1, 3)
+    b = _f64(parent_boxes).reshape(-1, 6)
+    n = pts.shape[0]
+    dev = pts.device
+    which = torch.empty(n, dtype=torch.int32, device=dev)
+    o = d = r = None
+    if origins is not None:
+        origins = _f64(origins).reshape(-1, 3)
+        if frame_id is not None:
+            frame_id = frame_id.to(device=dev, dtype=torch.int32).contiguous()
+        o = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        d = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        r = torch.empty(n, dtype=torch.float64, device=dev)
+    check(lib().pcnerf_route_points(_p(pts), n, _p(b), b.shape[0], _p(origins), _p(frame_id), _p(which), _p(o), _p(d),
+                                    _p(r), _stream()))
+    return which, o, d, r
+
+
 def aabb_build_groups(ray_o, ray_d, dist, boxes, boxes_larger, parent_min, parent_max, depth_inference_method=2,
                       grow_step=0.005, prefilter=0.65):
     """Returns (rays (N',13) f32, ranges (N',1) f32, other (N',1) i64, kept ray mask (N,))."""
@@ -346,6 +367,13 @@ def tc_row_pairs(on=None):
     if on is not None:
         lib().pcnerf_tc_set_row_pairs(int(on))
     return int(lib().pcnerf_tc_get_row_pairs())
+
+
+def tc_weight_correction(on=None):
+    """Get / set the linear correction of the fp16 weight rounding in the layered precision-1 forward (k_tc_fold)."""
+    if on is not None:
+        lib().pcnerf_tc_set_weight_correction(int(on))
+    return int(lib().pcnerf_tc_get_weight_correction())
 
 
 class MLPFunction(torch.autograd.Function):
@@ -518,7 +546,7 @@ class AffineApplyFunction(torch.autograd.Function):
 
 
 class CompositeFunction(torch.autograd.Function):
-    """(w, depth, child_free_loss, child_depth_loss, free_r, sl1_r, opacity) = composite(p, z, rays)."""
+    """(w, depth, child_free_loss, child_depth_loss, free_r, sl1_r, opacity, range_sl1) = composite(p, z, rays)."""
 
     @staticmethod
     def forward(ctx, p, z, rays, cols, noise, noise_std, epsilon, flags, want_per_ray=False):
@@ -527,6 +555,7 @@ class CompositeFunction(torch.autograd.Function):
         n, P_ = z.shape
         dev = z.device
         child = bool(flags & COMP_CHILD_LOSS)
+        rloss = bool(flags & COMP_RANGE_LOSS)
         if rays is not None:
             rays = _cuda_f32(rays, "rays")
         ld = rays.shape[1] if rays is not None else 0
@@ -539,24 +568,25 @@ class CompositeFunction(torch.autograd.Function):
             noise = _cuda_f32(noise, "noise")
         check(lib().pcnerf_composite_fwd(_p(p), _p(z), _p(rays), ld, n, P_, cn, cf, rc, _p(noise), float(noise_std),
                                          float(epsilon), int(flags), _p(w), _p(depth), _p(per_ray), _p(sums), _stream()))
-        losses = torch.zeros(2, dtype=torch.float32, device=dev)
-        if child and n > 0:
+        losses = torch.zeros(3, dtype=torch.float32, device=dev)
+        if (child or rloss) and n > 0:
             check(lib().pcnerf_composite_losses(_p(sums), n, _p(losses), _stream()))
         if flags & COMP_OPACITY:
             opacity = (sums[2] / max(n * P_, 1)).to(torch.float32)
         else:
             opacity = torch.zeros((), dtype=torch.float32, device=dev)
-        ctx.save_for_backward(p, z, w, rays, per_ray)
+        ctx.save_for_backward(p, z, w, rays, per_ray, depth if rloss else None)
         ctx.meta = (rc, float(noise_std), float(epsilon), int(flags), n, P_, ld)
         ctx.set_materialize_grads(False)
         free_r = per_ray[:, 0].contiguous() if (child and want_per_ray) else None
         sl1_r = per_ray[:, 2].contiguous() if (child and want_per_ray) else None
         ctx.mark_non_differentiable(w, opacity)
-        return w, depth, losses[0].clone(), losses[1].clone(), free_r, sl1_r, opacity
+        # (views of one 3-element tensor: no clone kernels; autograd hands back one gradient per view)
+        return w, depth, losses[0], losses[1], free_r, sl1_r, opacity, losses[2]
 
     @staticmethod
-    def backward(ctx, g_w, g_depth, g_free, g_dl, g_free_r, g_sl1_r, g_op):
-        p, z, w, rays, per_ray = ctx.saved_tensors
+    def backward(ctx, g_w, g_depth, g_free, g_dl, g_free_r, g_sl1_r, g_op, g_range):
+        p, z, w, rays, per_ray, depth = ctx.saved_tensors
         rc, noise_std, epsilon, flags, n, P_, ld = ctx.meta
         if g_w is not None or g_op is not None:
             raise NotImplementedError("pcnerf_b200: gradients through `weights` / `opacity` outputs are not supported "
@@ -566,41 +596,147 @@ class CompositeFunction(torch.autograd.Function):
         def c(t):
             return None if t is None else t.contiguous().to(torch.float32)
 
-        g_depth, g_free, g_dl, g_free_r, g_sl1_r = c(g_depth), c(g_free), c(g_dl), c(g_free_r), c(g_sl1_r)
+        g_depth, g_free, g_dl, g_free_r, g_sl1_r, g_range = c(g_depth), c(g_free), c(g_dl), c(g_free_r), c(g_sl1_r), c(g_range)
         check(lib().pcnerf_composite_bwd(_p(p), _p(z), _p(w), _p(rays), ld, n, P_, rc, noise_std, epsilon, flags,
                                          _p(per_ray), _p(g_depth), _p(g_free), _p(g_dl), _p(g_free_r), _p(g_sl1_r), n,
-                                         _p(gp), _stream()))
+                                         _p(depth), _p(g_range), _p(gp), _stream()))
         return gp, None, None, None, None, None, None, None, None
 
 
 def composite(p, z, rays=None, cols=(10, 11, 14), noise=None, noise_std=0.0, epsilon=1e-10, flags=0, want_per_ray=False):
+    """-> (w, depth, child_free_loss, child_depth_loss, free_r, sl1_r, opacity, range_sl1).  range_sl1 (flags &
+    COMP_RANGE_LOSS) = SmoothL1Loss(mean)(10 depth, 10 rays[:, cols[2]]), the scene-level range term of
+    train_kitti.py:145-146 before its 0.1 * lambda_loss factor, computed (and back-propagated) inside K4."""
     return CompositeFunction.apply(p, z, rays, cols, noise, noise_std, epsilon, flags, want_per_ray)
+
+
+# ------------------------------------------------------------------------------------ masked-mean losses / metrics
+
+LOSS_KINDS = {"smoothl1": 0, "mse": 1, "l1": 2, "abs_error": 3, "acc_thres": 4}
+
+
+def _mask_u8(valid_mask, n, device):
+    if valid_mask is None:
+        return None
+    m = valid_mask.reshape(-1)
+    if m.shape[0] != n:
+        raise ValueError("valid_mask must have one entry per element")
+    return m.to(device=device, dtype=torch.uint8).contiguous()
+
+
+class MaskedLossFunction(torch.autograd.Function):
+    """mean over the selected elements of SmoothL1 / MSE / L1 (pred - target): one reduction kernel + a finaliser forward,
+    one elementwise kernel backward (nof/criteria/loss.py:7-50)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask, kind):
+        pred = _cuda_f32(pred.reshape(-1), "pred")
+        target = _cuda_f32(target.reshape(-1), "target")
+        n = pred.shape[0]
+        if target.shape[0] != n:
+            raise ValueError("pred and target must have the same number of elements")
+        acc = torch.empty(2, dtype=torch.float64, device=pred.device)
+        out = torch.empty(1, dtype=torch.float32, device=pred.device)
+        check(lib().pcnerf_masked_loss_fwd(int(kind), _p(pred), _p(target), _p(mask), n, _p(acc), _p(out), _stream()))
+        ctx.save_for_backward(pred, target, mask, acc)
+        ctx.kind = int(kind)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, mask, acc = ctx.saved_tensors
+        g = g.reshape(1).contiguous().to(torch.float32)
+        need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gp = torch.empty_like(pred) if need_p else None
+        gt = torch.empty_like(target) if need_t else None
+        if need_p or need_t:
+            check(lib().pcnerf_masked_loss_bwd(ctx.kind, _p(pred), _p(target), _p(mask), pred.shape[0], _p(acc), _p(g), _p(gp),
+                                               _p(gt), _stream()))
+        return gp, gt, None, None
+
+
+def masked_loss(pred, target, valid_mask=None, kind="smoothl1"):
+    """Masked mean of the elementwise loss / metric `kind` (LOSS_KINDS) of pred - target; differentiable for the losses."""
+    k = LOSS_KINDS[kind]
+    shape = pred.shape
+    mask = _mask_u8(valid_mask, pred.numel(), pred.device)
+    if k >= 3:
+        with torch.no_grad():
+            return MaskedLossFunction.apply(pred.detach(), target.detach().expand(shape), mask, k)
+    return MaskedLossFunction.apply(pred, target.expand(shape), mask, k)
 
 
 # -------------------------------------------------------------------------------------------------------- K5 search
 
 
-def search_rows(p, z, rays, cnear_col=6, cfar_col=7, epsilon=1e-10, method=0):
+def search_rows(p, z, rays, cnear_col=6, cfar_col=7, epsilon=1e-10, method=0, row_ray=None, want_w=True):
+    """K5 per candidate row.  row_ray (N',) int32: p / z are (G,P) per PHYSICAL ray and row r of `rays` reads ray
+    row_ray[r] (the weights come back per ray as well); None: one p / z row per candidate row (the reference's layout)."""
     p, z, rays = _cuda_f32(p, "p"), _cuda_f32(z, "z"), _cuda_f32(rays, "rays")
-    n, P_ = z.shape
+    n = rays.shape[0] if row_ray is not None else z.shape[0]
+    P_ = z.shape[1]
     dev = z.device
-    w = torch.empty((n, P_), dtype=torch.float32, device=dev)
+    w = torch.empty(z.shape, dtype=torch.float32, device=dev) if (want_w or row_ray is None) else None
     depth = torch.empty(n, dtype=torch.float32, device=dev)
     peak = torch.empty(n, dtype=torch.uint8, device=dev)
     wsum = torch.empty(n, dtype=torch.float32, device=dev)
     sums = torch.empty(4, dtype=torch.float64, device=dev)
-    check(lib().pcnerf_search_rows(_p(p), _p(z), _p(rays), rays.shape[1], n, P_, cnear_col, cfar_col, float(epsilon),
-                                   int(method), _p(w), _p(depth), _p(peak), _p(wsum), _p(sums), _stream()))
+    if row_ray is None:
+        check(lib().pcnerf_search_rows(_p(p), _p(z), _p(rays), rays.shape[1], n, P_, cnear_col, cfar_col, float(epsilon),
+                                       int(method), _p(w), _p(depth), _p(peak), _p(wsum), _p(sums), _stream()))
+    else:
+        if row_ray.dtype != torch.int32 or row_ray.shape[0] != n:
+            raise TypeError("search_rows: row_ray must be an int32 tensor with one entry per candidate row")
+        check(lib().pcnerf_search_rows_grouped(_p(p), _p(z), _p(rays), rays.shape[1], n, P_, cnear_col, cfar_col,
+                                               float(epsilon), int(method), _p(row_ray.contiguous()), _p(w), _p(depth),
+                                               _p(peak), _p(wsum), _p(sums), _stream()))
     opacity = (sums[0] / max(n * P_, 1)).to(torch.float32)
     return depth, w, opacity, peak, wsum
 
 
-def search_select(other, peak, wsum):
+def search_select(other, peak, wsum, n_rendered=None):
     other = other.reshape(-1).to(torch.int64).contiguous()
     n = other.shape[0]
     flag = torch.empty(n, dtype=torch.uint8, device=other.device)
-    check(lib().pcnerf_search_select(_p(other), _p(peak), _p(wsum), n, _p(flag), _stream()))
+    check(lib().pcnerf_search_select(_p(other), _p(peak), _p(wsum), n, _p(n_rendered), _p(flag), _stream()))
     return flag.bool().reshape(-1, 1)
+
+
+class GroupPlan:
+    """Group structure of a set of candidate rows (nof/render.py:317-340 walks it row by row on the host): which rows start
+    a group (= one physical LiDAR ray), the row -> ray map, and whether every row of a group really carries its head's ray
+    (origin, direction, parent segment) -- the condition under which the samples are evaluated once per ray.
+    Building it costs ONE host synchronisation (the number of physical rays sizes every later launch)."""
+
+    def __init__(self, rays, other, pnear_col=9, pfar_col=10):
+        rays = _cuda_f32(rays, "rays")
+        other = other.reshape(-1).to(torch.int64).contiguous()
+        n = rays.shape[0]
+        if other.shape[0] != n:
+            raise ValueError("GroupPlan: `other` must have one entry per candidate row")
+        dev = rays.device
+        head = torch.empty(n, dtype=torch.uint8, device=dev)
+        check(lib().pcnerf_group_heads(_p(other), n, _p(head), _stream()))
+        self.row_ray = (torch.cumsum(head, 0, dtype=torch.int32) - 1).contiguous()      # (N',) physical-ray index of a row
+        self.head_rows = torch.nonzero(head).reshape(-1)                                # (G,) first row of every group (sync)
+        self.G = int(self.head_rows.shape[0])
+        mism = torch.zeros(1, dtype=torch.int32, device=dev)
+        if n:
+            check(lib().pcnerf_group_uniform(_p(rays), rays.shape[1], n, _p(self.row_ray), _p(self.head_rows), pnear_col,
+                                             pfar_col, _p(mism), _stream()))
+        self.uniform = int(mism.item()) == 0
+        self.n = n
+        self.other = other
+
+
+def eval_rows_rendered(rays, batch_size_set, tag_col=-1):
+    """Device scalar (int64): the number of leading rows the reference's batch loop hands to the renderer
+    (eval_kitti_render.py:979-1005; n, or n - 1 when a batch ends one row before the end)."""
+    rays = _cuda_f32(rays, "rays")
+    ld = rays.shape[1]
+    out = torch.empty(1, dtype=torch.int64, device=rays.device)
+    check(lib().pcnerf_eval_rows_rendered(_p(rays), ld, tag_col % ld, rays.shape[0], int(batch_size_set), _p(out), _stream()))
+    return out
 
 
 def points(rays, depth):

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import ops, parallel
-from .eval_kitti_render import render_frame
+from .eval_kitti_render import FramePlan, render_frame
 
 
 class ParentBlock:
@@ -24,6 +24,20 @@ class ParentBlock:
         self.child_bounds_larger = self.child_bounds if child_bounds_larger is None else \
             np.asarray(child_bounds_larger, dtype=np.float64).reshape(-1, 6)
         self.nof_coarse, self.nof_fine = nof_coarse, nof_fine
+        self._dev = {}
+
+    def child_bounds_dev(self, device):
+        """The child boxes as a float64 device tensor (uploaded once per block)."""
+        k = ("b", str(device))
+        if k not in self._dev:
+            self._dev[k] = torch.as_tensor(self.child_bounds, dtype=torch.float64, device=device)
+        return self._dev[k]
+
+    def child_bounds_larger_dev(self, device):
+        k = ("l", str(device))
+        if k not in self._dev:
+            self._dev[k] = torch.as_tensor(self.child_bounds_larger, dtype=torch.float64, device=device)
+        return self._dev[k]
 
 
 def route_points(points, parents):
@@ -72,4 +86,51 @@ def render_scene_frame(parents, origin, points, embedding_position, N_samples, N
             continue
         out[i] = render_frame(b.nof_coarse, b.nof_fine, embedding_position, rays, other, N_samples, N_importance, chunk,
                               depth_inference_method=depth_inference_method, batch_size_set=batch_size_set)
+    return out
+
+
+def parent_boxes(parents):
+    """(P,6) float64: min xyz, max xyz of every parent block (the layout ops.route_points takes)."""
+    return np.stack([np.concatenate([b.parent_min, b.parent_max]) for b in parents], 0)
+
+
+@torch.no_grad()
+def render_scene_frames(parents, origins, points, frame_id, embedding_position, N_samples, N_importance, chunk,
+                        depth_inference_method=2, batch_size_set=18432, grow_step=0.05, world_size=None, rank_=None,
+                        boxes_dev=None):
+    """BATCHED depth inference of several frames over the parent blocks THIS rank owns (BASELINE.json configs[4]).
+
+    origins (F,3): sensor position of every frame; points (M,3): the returns of all F frames in the scene frame;
+    frame_id (M,): the frame of every return (device tensors, float64 / integer).  Every return is routed to the parent block
+    that contains it (K0', one kernel); per owned block the rays of ALL frames of the batch are grouped (K1: candidate child
+    boxes per ray) and rendered together (`render_frame`, once per physical ray) -- a block's networks are loaded once per
+    batch instead of once per frame, and the MLP kernels see F times more rows per launch.  No communication: a block's rays
+    never leave its rank.  Host synchronisations: one for the per-block ray counts, one per block for its group structure.
+    Returns {parent index: (m,3) rendered points on the device}."""
+    pts = ops._f64(points).reshape(-1, 3)
+    dev = pts.device
+    P = len(parents)
+    if boxes_dev is None:
+        boxes_dev = torch.as_tensor(parent_boxes(parents), dtype=torch.float64, device=dev)
+    which, o, d, r = ops.route_points(pts, boxes_dev, origins, frame_id)
+    order = torch.argsort(which, stable=True)                       # returns of block 0, block 1, ... (-1 first)
+    counts = torch.bincount((which + 1).to(torch.int64), minlength=P + 1).tolist()
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    out = {}
+    for i in owned_blocks(P, world_size, rank_):
+        a, b_ = int(starts[i + 1]), int(starts[i + 2])
+        if b_ <= a:
+            continue
+        blk = parents[i]
+        if blk.nof_coarse is None or blk.nof_fine is None:
+            raise RuntimeError("parent block %d is owned by this rank but its networks are not loaded" % i)
+        idx = order[a:b_]
+        rays, _, other, _ = ops.aabb_build_groups(o.index_select(0, idx), d.index_select(0, idx), r.index_select(0, idx),
+                                                  blk.child_bounds_dev(dev), blk.child_bounds_larger_dev(dev),
+                                                  blk.parent_min, blk.parent_max, depth_inference_method, grow_step, 0.65)
+        if rays.shape[0] == 0:
+            continue
+        plan = FramePlan(rays, other, batch_size_set)
+        out[i] = render_frame(blk.nof_coarse, blk.nof_fine, embedding_position, rays, other, N_samples, N_importance, chunk,
+                              depth_inference_method=depth_inference_method, batch_size_set=batch_size_set, plan=plan)
     return out

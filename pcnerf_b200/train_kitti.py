@@ -41,6 +41,7 @@ class NOFSystem(torch.nn.Module):
                                  use_skip=hparams.use_skip)
         self.loss = nof_loss[hparams.loss_type]()
         self.loss2 = nof_loss[hparams.loss_type]()
+        self.fuse_range_loss = True        # take the scene-level SmoothL1 range terms from K4 (False: the nof_loss modules)
 
     def forward(self, rays, isval, **rng):
         """train_kitti.py:88-106."""
@@ -81,6 +82,11 @@ class NOFSystem(torch.nn.Module):
                     loss_range = loss_range + 1e-1 * hp.lambda_loss * self.loss(1e1 * pred_ranges[sel], 1e1 * gt_ranges[sel])
                     loss_range_fine = loss_range_fine + 1e-1 * hp.lambda_loss_fine * self.loss(
                         1e1 * pred_ranges_fine[sel], 1e1 * gt_ranges[sel])
+        elif self.fuse_range_loss and hp.loss_type == 'smoothl1' and results.get('range_sl1') is not None:
+            # the SmoothL1 means were accumulated by K4 in the compositing pass (forward and backward): no loss kernels
+            # here.  Uses rays[:, 14] as ground truth, which is what batch['ranges'] holds (ipb2dmapping.py:447-453).
+            loss_range = 1e-1 * hp.lambda_loss * results['range_sl1']
+            loss_range_fine = 1e-1 * hp.lambda_loss * results['range_sl1_fine']                            # sic: lambda_loss
         else:
             loss_range = 1e-1 * hp.lambda_loss * self.loss(1e1 * pred_ranges, 1e1 * gt_ranges)
             loss_range_fine = 1e-1 * hp.lambda_loss * self.loss(1e1 * pred_ranges_fine, 1e1 * gt_ranges)   # sic: lambda_loss
@@ -89,6 +95,40 @@ class NOFSystem(torch.nn.Module):
             hp.lambda_child_depth_loss * results['child_depth_loss_fine'] + hp.lambda_child_depth_loss * results['child_depth_loss']
         self.last_terms = {"loss_range": loss_range, "loss_range_fine": loss_range_fine, **results}
         return loss
+
+
+def microbatch_scales(n_micro, n_local, world=1):
+    """Loss factors that make gradient ACCUMULATION over ray micro-batches (and averaging over `world` data-parallel ranks)
+    reproduce one batch of world x n_local rays (BASELINE.json configs[3]: 262,144 rays x 384 samples do not fit one pass:
+    the saved activations alone are 8 x 512 B per sample).  The range and child-free losses are batch means
+    (train_kitti.py:145-146, nof/render.py:121), so a micro-batch of n_micro rays contributes with n_micro / n_local; the
+    child depth loss carries an extra 1/N (nof/render.py:155): (n_micro / n_local)^2 / world.  BatchNorm batches are the
+    `chunk`-row chunks of the flattened samples either way, provided n_micro x N_samples and n_micro x (N_samples +
+    N_importance) are multiples of `chunk`.  Returns (mean-term factor, depth-term factor)."""
+    f = float(n_micro) / float(n_local)
+    return f, f * f / float(world)
+
+
+def accumulate_microbatches(system, rays, gt_ranges, micro_rays, world=1, **rng):
+    """Forward + backward of one optimizer step's batch in micro-batches of `micro_rays` rays; gradients accumulate in
+    .grad (zero them before).  Returns the batch loss (detached; the value one pass over the whole batch would log)."""
+    hp = system.hparams
+    n = rays.shape[0]
+    total = None
+    for a in range(0, n, micro_rays):
+        r, g = rays[a:a + micro_rays], gt_ranges[a:a + micro_rays]
+        f_mean, f_depth = microbatch_scales(r.shape[0], n, world)
+        res = system.forward(r, False, **rng)
+        if system.fuse_range_loss and hp.loss_type == 'smoothl1' and res.get('range_sl1') is not None:
+            lr_c, lr_f = res['range_sl1'], res['range_sl1_fine']
+        else:
+            lr_c, lr_f = system.loss(1e1 * res['depth'], 1e1 * g), system.loss2(1e1 * res['depth_fine'], 1e1 * g)
+        loss = f_mean * (1e-1 * hp.lambda_loss * lr_c + 1e-1 * hp.lambda_loss * lr_f
+                         + hp.lambda_child_free_loss * (res['child_free_loss_fine'] + res['child_free_loss'])) \
+            + f_depth * hp.lambda_child_depth_loss * (res['child_depth_loss_fine'] + res['child_depth_loss'])
+        loss.backward()
+        total = loss.detach() if total is None else total + loss.detach()
+    return total
 
 
 def load_ckpt(model, ckpt_path, model_name='model', prefixes_to_ignore=()):

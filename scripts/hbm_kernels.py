@@ -73,7 +73,7 @@ def main():
     report("k_sample_encode_coarse", ms, n * (60.0 + S * (4.0 + 4.0 + esz)))        # + 4 B/sample of U
     z, _ = ops.sample_encode_coarse(rays, S, 0, 6, 7, 10, 11, False, 1.0, U, want_enc=False)
     p = torch.rand(n, S, device=dev) * 0.2
-    w, depth, _, _, _, _, _ = ops.composite(p, z, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS)
+    w, depth, _, _, *_ = ops.composite(p, z, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS)
     u = torch.rand(n, Ni, device=dev)
     ms = timed(lambda: ops.sample_encode_fine(rays, z, w, Ni, u, False, want_enc=True, f16=bool(a.f16)))
     report("k_sample_encode_fine", ms, n * (60.0 + 8.0 * S + 4.0 * Ni + F * (4.0 + esz)))

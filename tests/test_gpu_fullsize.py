@@ -29,7 +29,7 @@ def test_sampling_and_compositing_invariants_c2():
     sc = e[..., 3:63].reshape(N, S, 10, 2, 3)
     assert float((sc[..., 0, :] ** 2 + sc[..., 1, :] ** 2 - 1).abs().max()) < 1e-5   # sin^2 + cos^2
     p = torch.sigmoid(torch.randn((N, S), device=dev(), generator=torch.Generator(device=dev()).manual_seed(2)) * 2 - 1)
-    w, depth, fl, dl, _, _, _ = ops.composite(p, z, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS)
+    w, depth, fl, dl, *_ = ops.composite(p, z, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS)
     assert bool((w >= 0).all()) and float((w.sum(1) - 1).abs().max()) < 1e-5      # normalised weights (render.py:59)
     assert bool((depth >= z[:, 0] - 1e-4).all()) and bool((depth <= z[:, -1] + 1e-4).all())
     assert float(fl) >= 0 and float(dl) >= 0
@@ -67,14 +67,16 @@ def test_engines_agree_on_a_full_training_step_c2():
     ref = out["fp32"]
     for k in ("depth", "child_free_loss", "child_depth_loss"):
         np.testing.assert_allclose(out["affine"][0][k], ref[0][k], rtol=3e-5, atol=1e-6, err_msg=k)
-    # tensor-core engine: both losses and 99.9 % of the 32,768 depths within the 1e-3 gate; the worst rays of a batch this
-    # large reach 1.2e-3 (measured; fp16 rounding of the folded weights is the largest contribution)
-    for k in ("child_free_loss", "child_depth_loss"):
+    # tensor-core engine (north_star: depth and losses within 1e-3 relative): EVERY one of the 32,768 coarse and fine depths
+    # and all four losses.  Measured with the linear weight-rounding correction of k_tc_fold: worst coarse depth 8.1e-4,
+    # worst fine depth 7.1e-4 (1.17e-3 / 9.2e-4 without it), losses 1e-6 .. 5e-6 (profiles/r02_tc_error_c2.json).
+    for k in ("child_free_loss", "child_depth_loss", "child_free_loss_fine", "child_depth_loss_fine"):
         np.testing.assert_allclose(out["tc"][0][k], ref[0][k], rtol=1e-3, err_msg=k)
     rel = np.abs(out["tc"][0]["depth"] - ref[0]["depth"]) / np.abs(ref[0]["depth"])
-    assert np.quantile(rel, 0.999) < 1e-3 and rel.max() < 2e-3, (np.quantile(rel, 0.999), rel.max())
+    assert rel.max() < 1e-3, (np.quantile(rel, 0.999), rel.max())
+    relf = np.abs(out["tc"][0]["depth_fine"] - ref[0]["depth_fine"]) / np.abs(ref[0]["depth_fine"])
+    assert relf.max() < 1e-3, (np.quantile(relf, 0.999), relf.max())
     np.testing.assert_allclose(out["affine"][0]["depth_fine"], ref[0]["depth_fine"], rtol=2e-3, atol=1e-5)
-    np.testing.assert_allclose(out["tc"][0]["depth_fine"], ref[0]["depth_fine"], rtol=1e-2, atol=1e-4)
     for i in (1, 2):
         scale = np.abs(ref[i]).max()
         assert np.abs(out["affine"][i] - ref[i]).max() <= 1e-3 * scale

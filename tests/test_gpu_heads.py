@@ -24,7 +24,7 @@ def test_composite_losses_and_grad_vs_reference():
                                      ("zu", "pu", "free_u", "depthloss_u", "depth_u", "grad_pu")):
         z = _t(g[zk])
         p = _t(g[pk]).requires_grad_(True)
-        w, depth, fl, dl, _, _, _ = ops.composite(p, z, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS)
+        w, depth, fl, dl, *_ = ops.composite(p, z, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS)
         np.testing.assert_allclose(fl.item(), g[fk], rtol=1e-5)
         np.testing.assert_allclose(dl.item(), g[dk], rtol=1e-5)
         np.testing.assert_allclose(depth.detach().cpu().numpy(), g[depk], rtol=1e-5, atol=1e-6)
@@ -87,7 +87,7 @@ def test_composite_vs_oracle_sizes(N, P):
     loss = 0.1 * orc.smooth_l1_mean(10 * depth, 10 * rays[:, 14]) + 1e6 * fl + 1e5 * dl
     loss.backward()
     p = p_ref.detach().to(dev()).requires_grad_(True)
-    wg, dg, flg, dlg, _, _, _ = ops.composite(p, z.to(dev()), rays.to(dev()), (10, 11, 14), None, 0.0, 1e-10,
+    wg, dg, flg, dlg, *_ = ops.composite(p, z.to(dev()), rays.to(dev()), (10, 11, 14), None, 0.0, 1e-10,
                                               ops.COMP_CHILD_LOSS)
     lg_ = 0.1 * torch.nn.functional.smooth_l1_loss(10 * dg, 10 * rays[:, 14].to(dev())) + 1e6 * flg + 1e5 * dlg
     lg_.backward()
@@ -358,3 +358,41 @@ def test_fp16_row_kernels_agree_with_the_generic_kernels():
     assert torch.equal(f_a, f_b)
     _rows_agree(g_a, g_b)
     assert bool((f_a[ok][:, 1:] >= f_a[ok][:, :-1]).all())
+
+
+@pytest.mark.parametrize("name,ref", [("smoothl1", torch.nn.SmoothL1Loss), ("mse", torch.nn.MSELoss), ("l1", torch.nn.L1Loss)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_nof_loss_modules_vs_torch(name, ref, masked):
+    """nof/criteria/loss.py:7-50: the range-loss modules (one reduction kernel forward, one elementwise kernel backward) against
+    the torch.nn modules the reference wraps, values and gradients, with and without a validity mask."""
+    from pcnerf_b200.nof.criteria import nof_loss
+    gen = torch.Generator().manual_seed(5)
+    n = 10007
+    pred = (torch.randn(n, generator=gen) * 3).to(dev()).requires_grad_(True)
+    tgt = (torch.randn(n, generator=gen) * 3).to(dev()).requires_grad_(True)
+    mask = (torch.rand(n, generator=gen) > 0.3).to(dev()) if masked else None
+    loss = nof_loss[name]()(10 * pred, 10 * tgt, mask)
+    (3.0 * loss).backward()
+    p2, t2 = pred.detach().clone().requires_grad_(True), tgt.detach().clone().requires_grad_(True)
+    a, b = 10 * p2, 10 * t2
+    if masked:
+        a, b = a[mask], b[mask]
+    want = ref(reduction="mean")(a, b)
+    (3.0 * want).backward()
+    assert loss.shape == ()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=2e-6)
+    np.testing.assert_allclose(pred.grad.cpu().numpy(), p2.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(tgt.grad.cpu().numpy(), t2.grad.cpu().numpy(), rtol=1e-5, atol=1e-9)
+
+
+def test_logging_metrics_vs_formulas():
+    """nof/criteria/metrics.py:5-21: abs_error = mean |pred - gt|, acc_thres = 100 * mean(|pred - gt| < 0.2)."""
+    from pcnerf_b200.nof.criteria import metrics
+    gen = torch.Generator().manual_seed(6)
+    pred = (torch.rand(5000, generator=gen) * 30).to(dev())
+    gt = pred + (torch.randn(5000, generator=gen) * 0.25).to(dev())
+    mask = (torch.rand(5000, generator=gen) > 0.5).to(dev())
+    for m in (None, mask):
+        e = (pred - gt).abs() if m is None else (pred - gt).abs()[m]
+        np.testing.assert_allclose(metrics.abs_error(pred, gt, m).item(), e.mean().item(), rtol=2e-6)
+        np.testing.assert_allclose(metrics.acc_thres(pred, gt, m).item(), ((e < 0.2).sum() / e.shape[0] * 100).item(), rtol=2e-6)

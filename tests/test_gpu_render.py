@@ -285,3 +285,46 @@ def test_c4_sample_counts_train_step():
     for k in ("depth", "child_free_loss", "child_depth_loss"):
         np.testing.assert_allclose(res[k].detach().cpu().numpy(), ref[k].numpy(), rtol=3e-5, atol=1e-6, err_msg=k)
     np.testing.assert_allclose(res["depth_fine"].detach().cpu().numpy(), ref["depth_fine"].numpy(), rtol=FINE_E2E_RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("use_child", [1, 0])
+def test_fused_range_loss_equals_the_nof_loss_modules(use_child):
+    """train_kitti.py:145-146: the scene-level SmoothL1 range terms taken from K4's compositing pass (forward value and the
+    gradient K4's backward adds to dL/d depth) against the explicit nof_loss modules on (10 depth, 10 ranges)."""
+    from pcnerf_b200.train_kitti import NOFSystem, accumulate_microbatches
+    hp = argparse.Namespace(L_pos=10, feature_size=256, use_skip=True, ckpt_path=None, loss_type="smoothl1",
+                            N_samples=64, N_importance=128, use_disp=False, perturb=0, noise_std=0, chunk=8192,
+                            sub_nerf_test_num=8, use_segmentated_sample=1, segmentated_child_nerf_ratio=0.1,
+                            use_child_nerf_divide=0, use_child_nerf_loss=use_child, lambda_loss=1.0, lambda_loss_fine=1.0,
+                            lambda_child_free_loss=1e6, lambda_child_depth_loss=1e5, optimizer="adam", lr=5e-4,
+                            momentum=0.9, weight_decay=1e-3, decay_gamma=0.1)
+    from pcnerf_b200 import synth
+    rays = _t(synth.synth_train_rays(8, 512, K=8))
+    out = {}
+    for fuse in (True, False):
+        sys_ = NOFSystem(hp)
+        sys_.nof_coarse.load_state_dict(orc.init_state_dict(42))
+        sys_.nof_fine.load_state_dict(orc.init_state_dict(43))
+        sys_.to(dev()).train()
+        sys_.fuse_range_loss = fuse
+        loss = sys_.training_step({"rays": rays, "ranges": rays[:, 14]}, 0)
+        loss.backward()
+        out[fuse] = (loss.item(), sys_.last_terms["loss_range"].item(), sys_.last_terms["loss_range_fine"].item(),
+                     {k: p.grad.clone() for k, p in sys_.named_parameters()})
+    for i in range(3):
+        np.testing.assert_allclose(out[True][i], out[False][i], rtol=2e-6)
+    for k, g in out[False][3].items():
+        scale = float(g.abs().max())
+        assert float((out[True][3][k] - g).abs().max()) <= 2e-5 * scale + 1e-12, k
+    # micro-batched accumulation (BASELINE configs[3]) reproduces the one-pass gradient: 4 micro-batches of whole BN chunks
+    sys_ = NOFSystem(hp)
+    sys_.nof_coarse.load_state_dict(orc.init_state_dict(42))
+    sys_.nof_fine.load_state_dict(orc.init_state_dict(43))
+    sys_.to(dev()).train()
+    total = accumulate_microbatches(sys_, rays, rays[:, 14], 128)
+    np.testing.assert_allclose(total.item(), out[True][0], rtol=2e-5)
+    for k, p in sys_.named_parameters():
+        g = out[True][3][k]
+        if k.endswith(".bias") and k.split(".")[1] in ("layer1", "layer2") and not k.endswith("layer2.7.bias"):
+            continue
+        assert float((p.grad - g).abs().max()) <= 2e-4 * float(g.abs().max()) + 1e-12, k

@@ -198,6 +198,7 @@ def test_mlp_eval_fused_matches_layered(rows, mode):
     sd = {k: v.detach().cpu().clone() for k, v in mc.state_dict().items()}
     try:
         ops.tc_fused_eval(0)
+        ops.tc_weight_correction(0)      # the fused kernel streams the plain fp16(W') operands: compare like with like
         with torch.no_grad():
             p_lay = mc.forward_encoded(encd, 1 << 20).cpu()
         ops.tc_fused_eval(mode)
@@ -205,6 +206,7 @@ def test_mlp_eval_fused_matches_layered(rows, mode):
             p_fus = mc.forward_encoded(encd, 1 << 20).cpu()
     finally:
         ops.tc_fused_eval(DEFAULT_FUSED)
+        ops.tc_weight_correction(1)
     assert ops.lib().pcnerf_tc_last_fault() == 0
     np.testing.assert_allclose(p_fus.numpy(), p_lay.numpy(), rtol=2e-5, atol=1e-7)
     n_ref = min(rows, 4096)
@@ -287,7 +289,7 @@ def test_eval_fold_cache_sees_library_side_writes():
     rows = 3000
     enc = torch.nn.functional.pad(_enc(rows, 6), (0, 1)).to(dev())
     m, _, _ = make_nets(42, 43, False, "tc")
-    opt = FlatAdam(list(m.parameters()), lr=5e-2, eps=1e-8, weight_decay=1e-3)
+    opt = FlatAdam(list(m.parameters()), lr=1e-3, eps=1e-8, weight_decay=1e-3)      # (one step moves every weight by ~lr)
 
     def ref():
         sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
@@ -373,3 +375,34 @@ def test_flat_adam_state_dict_roundtrip_and_grad_realias():
     ob.step()
     torch.cuda.synchronize()
     assert torch.equal(oa.flat, ob.flat) and torch.equal(oa.exp_avg, ob.exp_avg) and int(ob.step_dev.item()) == 4
+
+
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval_layered"])
+def test_weight_correction_removes_the_weight_rounding_term(training):
+    """k_tc_fold's correction block (C = (W' - fp16(W')) T_l applied to the encoding) against the plain fp16(W') operands:
+    the mean relative error of p against the fp32 oracle must drop (what remains is the fp16 rounding of the activations
+    and of the encoding), in training mode (batch statistics) and in the layered eval path (running statistics)."""
+    from pcnerf_b200 import ops
+    rows = 8192
+    enc = _enc(rows, 21)
+    encd = torch.nn.functional.pad(enc, (0, 1)).to(dev())
+    errs = {}
+    try:
+        ops.tc_fused_eval(0)
+        for corr in (0, 1):
+            ops.tc_weight_correction(corr)
+            mc, _, _ = make_nets(42, 43, training, "tc")
+            sd = {k: v.detach().cpu().clone() for k, v in mc.state_dict().items()}
+            with torch.no_grad():
+                p = mc.forward_encoded(encd, rows).cpu()
+            ref = orc.nof_forward(sd, enc, training).reshape(-1)
+            rel = ((p - ref).abs() / ref).double()
+            errs[corr] = (float(rel.mean()), float(rel.max()))
+            if training:                                        # running statistics updated exactly once, from the same batch
+                np.testing.assert_allclose(mc.state_dict()["layer2.7.running_var"].cpu().numpy(),
+                                           sd["layer2.7.running_var"].numpy(), rtol=2e-3)
+    finally:
+        ops.tc_fused_eval(DEFAULT_FUSED)
+        ops.tc_weight_correction(1)
+    assert errs[1][0] < 0.85 * errs[0][0], errs
+    assert errs[1][1] < 6e-3, errs

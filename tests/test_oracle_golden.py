@@ -201,3 +201,34 @@ def test_system_step_loss():
     for tag, sd in (("c", sd_c), ("f", sd_f)):
         for k in ("layer1.1.weight", "occ_out.0.weight", "occ_out.0.bias"):
             np.testing.assert_allclose(sd[k].detach().numpy(), g["after_%s_%s" % (tag, k)], rtol=1e-4, atol=1e-6)
+
+
+def test_c1_baseline_size_forward_vs_reference_and_float64_truth():
+    """BASELINE.json configs[0] (4,096 rays x 64 + 128 samples, K = 8, chunk 32,768, shipped flags): the oracle's forward
+    against the reference's own float32 run AND against the same reference code run in float64 (oracle/make_golden.py
+    golden_c1).  The float64 run arbitrates the tolerances: the reference's float32 output is itself 1.1e-5 (coarse depth)
+    / 2.0e-4 (fine depth: 1-ulp differences of the pdf move the resampled depths, nof/render.py:371-412) away from it."""
+    g = golden("c1_train")
+    rays = torch.from_numpy(g["rays"])
+    S, Ni, chunk = int(g["S"]), int(g["Ni"]), int(g["chunk"])
+    torch.set_num_threads(max(1, min(16, (__import__("os").cpu_count() or 1))))
+    with torch.no_grad():
+        res = orc.render_rays_train(orc.init_state_dict(42), orc.init_state_dict(43), rays, S, Ni, 0, 0, chunk, 1, 0.1, 0, 1)
+        loss = orc.training_loss(res, rays[:, 14], *[float(x) for x in g["lam"]])
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.max(np.abs(a - b) / np.abs(b)))
+
+    # the reference against its own float64 run: the noise floor every float32 implementation shares
+    floor_c, floor_f = rel(g["f32_depth"], g["f64_depth"]), rel(g["f32_depth_fine"], g["f64_depth_fine"])
+    assert floor_c < 2e-5 and 5e-5 < floor_f < 5e-4, (floor_c, floor_f)
+    # oracle vs the reference's float32 run
+    assert rel(res["depth"].numpy(), g["f32_depth"]) < 2e-5
+    assert rel(res["depth_fine"].numpy(), g["f32_depth_fine"]) < 2 * floor_f
+    for k in ("child_free_loss", "child_depth_loss", "child_free_loss_fine", "child_depth_loss_fine"):
+        assert abs(float(res[k]) - float(g["f32_" + k])) <= 1e-4 * abs(float(g["f32_" + k])), k
+    assert abs(float(loss) - float(g["f32_loss"])) <= 1e-4 * abs(float(g["f32_loss"]))
+    # ... and vs the float64 truth: no further from it than twice the reference's own float32 run
+    assert rel(res["depth"].numpy(), g["f64_depth"]) < 2 * floor_c + 1e-6
+    assert rel(res["depth_fine"].numpy(), g["f64_depth_fine"]) < 2 * floor_f
