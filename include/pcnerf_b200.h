@@ -217,7 +217,7 @@ int pcnerf_tc_wgrad(const void* DH, const void* X, int ldx, int ncols, int x_is_
                     int col_off, void* stream);
 int pcnerf_tc_last_fault(void);
 
-/* All chunks (BN batches) of one pass of the precision-1 MLP in training mode, `lanes` (1 or 2) chunks in flight on
+/* All chunks (BN batches) of one pass of the precision-1 MLP in training mode, `lanes` (1 .. 4) chunks in flight on
  * internal streams forked from / joined to `stream` (capturable in a CUDA graph).  Chunk c covers rows [c*chunk, ...) of
  * enc (rows,64) fp16; h_saved[c] holds h_saved_bytes[c] >= pcnerf_mlp_saved_bytes(rows of chunk c, 1) bytes; h_scratch[k],
  * k < lanes, holds scratch_bytes >= pcnerf_mlp_scratch_bytes(min(chunk, rows), 1) bytes (h_*: host arrays of device
@@ -273,14 +273,16 @@ int pcnerf_tc_get_weight_correction(void);
 /* p, z (n,P).  rays (n,ld): child near/far in columns cnear_col/cfar_col, range reading in range_col.
  * noise (n,P) or NULL is added as noise*noise_std before normalisation.
  * Outputs: w (n,P); depth (n); per_ray (n,8) f32 = {free_r, dhat_r, sl1_child_r, C_r, lo0, hi0, lo2, hi2};
- * sums (4) f64 = {sum free_r, sum sl1_child_r, sum opacity terms, unused} (zeroed by the call).
+ * sums (5) f64 = {sum free_r, sum sl1_child_r, sum opacity terms, sum SmoothL1(10 depth_r, 10 range_r), arrival counter of
+ * the finaliser} (zeroed by the call); out3 (3) f32 or NULL: the loss scalars of pcnerf_composite_losses, written by the
+ * last block of the forward kernel to finish (no separate launch).
  * P = 64 / 128 / 192 / 384 with 16-byte aligned p / z / w / noise / per_ray take the register-resident kernels; any other P
  * or alignment takes the generic kernels. Both
  * forms evaluate the same formulas; products and sums are associated differently (ulp-level differences). */
 int pcnerf_composite_fwd(const float* p, const float* z, const float* rays, int ld, int64_t n, int P,
                          int cnear_col, int cfar_col, int range_col, const float* noise, float noise_std,
                          float epsilon, int flags, float* w, float* depth, float* per_ray, double* sums,
-                         void* stream);
+                         float* out3, void* stream);
 
 /* child_free_loss = sums[0]/n; child_depth_loss = (1/n)*0.1*(sums[1]/n)  (render.py:121,155); range term =
  * sums[3]/n = SmoothL1Loss(mean)(10 depth, 10 gt) (train_kitti.py:145-146 before the 0.1 * lambda_loss factor) -> out3 (3) f32 */

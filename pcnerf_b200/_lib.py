@@ -67,7 +67,7 @@ SIGNATURES = {
     "pcnerf_tc_get_row_pairs": (ci, []),
     "pcnerf_tc_set_weight_correction": (None, [ci]),
     "pcnerf_tc_get_weight_correction": (ci, []),
-    "pcnerf_composite_fwd": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, ci, vp, f32, f32, ci, vp, vp, vp, vp, vp]),
+    "pcnerf_composite_fwd": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, ci, vp, f32, f32, ci, vp, vp, vp, vp, vp, vp]),
     "pcnerf_composite_losses": (ci, [vp, i64, vp, vp]),
     "pcnerf_composite_bwd": (ci, [vp, vp, vp, vp, ci, i64, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
     "pcnerf_search_rows": (ci, [vp, vp, vp, ci, i64, ci, ci, ci, f32, ci, vp, vp, vp, vp, vp, vp]),

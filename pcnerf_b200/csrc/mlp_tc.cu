@@ -225,6 +225,7 @@ __device__ __forceinline__ TilePlan tile_plan(int sched, int ntiles, int pair, i
 
 #define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
 #define TC_NBUF 2               // staging buffers per epilogue warp
+#define TC_NBUF2 4              // ... of the CTA-pair form (two 64-column rounds per tile, a pair of buffers each)
 
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -373,7 +374,10 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     mbar_expect_tx(bar_full + 8 * s, TC_A_BYTES);
                     const CUtensorMap* m = kb < g.kb0 ? &tmA0 : &tmA1;
                     const int c0 = (kb < g.kb0 ? kb % g.a0_blocks : kb - g.kb0) * 64;
-                    if (g.hint) tma_load_2d_hint(smem_u32(sA + (size_t)s * TC_A_BYTES), m, bar_full + 8 * s, c0, tile * 128, TC_L2_EVICT_FIRST);
+                    // A0 next to an A1 = the chunk's encoding, which EVERY layer of the chunk reads (correction block /
+                    // skip connection): keep its 33.5 MB in L2; the activations are read once: evict first
+                    if (g.hint) tma_load_2d_hint(smem_u32(sA + (size_t)s * TC_A_BYTES), m, bar_full + 8 * s, c0, tile * 128,
+                                                 (kb < g.kb0 && g.kb_total > g.kb0) ? TC_L2_EVICT_LAST : TC_L2_EVICT_FIRST);
                     else tma_load_2d(smem_u32(sA + (size_t)s * TC_A_BYTES), m, bar_full + 8 * s, c0, tile * 128);
                 }
                 __syncwarp();
@@ -852,7 +856,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const int nstage = g.nstage, KB = g.kb_total;
     uint8_t* sB = smem;                                   // KB x 16 KB: this CTA's 128 weight rows, resident
     uint8_t* sA = sB + (size_t)KB * TC_B_BYTES;           // nstage x 16 KB ring: this CTA's 128 rows of A
-    uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 warps x TC_NBUF x TC_STAGE_BYTES
+    uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 warps x TC_NBUF2 x TC_STAGE_BYTES
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
     const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
     const int rank = (int)cluster_ctarank();              // 0 = the pair's leader
@@ -904,7 +908,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     const CUtensorMap* m = kb < g.kb0 ? &tmA0 : &tmA1;
                     const int c0 = (kb < g.kb0 ? kb % g.a0_blocks : kb - g.kb0) * 64;
                     tma_load_2d_2sm_hint(smem_u32(sA + (size_t)s * TC_A_BYTES), m, (bar_full + 8 * s) & TC_PEER_MASK, c0,
-                                         tile * 128, pol);
+                                         tile * 128, (g.hint && kb < g.kb0 && g.kb_total > g.kb0) ? TC_L2_EVICT_LAST : pol);
                     if (++s == nstage) { s = 0; ph ^= 1; }
                 }
             }
@@ -940,8 +944,11 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4 (rows q*32 + lane of THIS CTA's tile), 128-column half
         // (warp-2)/4, in two rounds of 64 columns; per round the code of k_tc_rowgemm's epilogue.
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF * TC_STAGE_BYTES);
-        const uint32_t bufs[2] = {buf0, buf0 + TC_STAGE_BYTES};
+        // one pair of staging buffers PER ROUND: round 1 does not wait for the bulk stores of round 0 to have read theirs
+        // (with two buffers per warp every tile exposed the pick-up latency of a TMA store once; the pair form was
+        // measured 12-19 % slower than the column-split kernel that way)
+        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF2 * TC_STAGE_BYTES);
+        const uint32_t bufs4[2][2] = {{buf0, buf0 + TC_STAGE_BYTES}, {buf0 + 2 * TC_STAGE_BYTES, buf0 + 3 * TC_STAGE_BYTES}};
         double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
@@ -977,6 +984,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             for (int cc = 0; cc < 2; ++cc) {
                 const int colb = half * 128 + cc * 64;            // first output column of this round
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + colb);
+                const uint32_t* bufs = bufs4[cc];
                 uint32_t r[2][32];
                 if (EPI == TC_DGRAD) {
                     // this thread's row of H_{l-1}: staged through the (currently idle) output buffers, re-read row-wise
@@ -1046,8 +1054,9 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int colb = half * 128 + cc * 64;
-                if (!(EPI == TC_DGRAD && cc == 0)) {
-                    if (lane == 0) tma_store_wait_read<0>();  // earlier stores have read both staging buffers
+                const uint32_t* bufs = bufs4[cc];
+                if (EPI == TC_FWD && cc == 0) {
+                    if (lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have read the staging buffers
                     __syncwarp();
                 }
                 stage_put_row(bufs[0], pk[cc][0], lane);
@@ -1459,12 +1468,14 @@ __global__ void __launch_bounds__(256) k_tc_fold(int l, int training, int64_t ro
     }
     const int c = i & 63, part = i >> 6;
     float accT = 0.f, accC = 0.f;
-#pragma unroll 8
+    // this thread's 64 values of column c of T_prev: all loads in flight at once (L2 hits, ~1 latency instead of 8)
+    float tv[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) tv[k] = __ldg(T_prev + (part * 64 + k) * 64 + c);
+#pragma unroll
     for (int k = 0; k < 64; ++k) {
-        const int ii = part * 64 + k;
-        const float tv = T_prev[ii * 64 + c];
-        accT = fmaf(sh_w[ii], tv, accT);
-        accC = fmaf(sh_d[ii], tv, accC);
+        accT = fmaf(sh_w[part * 64 + k], tv[k], accT);
+        accC = fmaf(sh_d[part * 64 + k], tv[k], accC);
     }
     redc[0][part][c] = accT;
     redc[1][part][c] = accC;
@@ -1631,9 +1642,10 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     RowGemmArgs g;
     g.rows = (int)rows; g.a0_blocks = k0 / 64; g.kb0 = a0_rep * k0 / 64; g.kb_total = g.kb0 + k1 / 64;
+    const int nbuf = tc_pairs_mode() ? TC_NBUF2 : TC_NBUF;
     {
         // everything that is left of the 227 KB after the resident weights and the staging buffers becomes A ring
-        const size_t fixed = 1024 + (size_t)g.kb_total * TC_B_BYTES + 8 * TC_NBUF * TC_STAGE_BYTES + 4096 /* static */;
+        const size_t fixed = 1024 + (size_t)g.kb_total * TC_B_BYTES + 8 * nbuf * TC_STAGE_BYTES + 4096 /* static */;
         int ns = (int)((232448 - fixed) / TC_A_BYTES);
         g.nstage = ns > 8 ? 8 : ns;
     }
@@ -1652,7 +1664,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
         g.debug = dbg;
     }
-    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * TC_NBUF * TC_STAGE_BYTES;
+    const size_t smem = 1024 + (size_t)g.kb_total * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * nbuf * TC_STAGE_BYTES;
     const int ntiles = (int)pcn_cdiv(rows, 128);
     const int grid = 2 * ntiles < sm_count() ? 2 * ntiles : (sm_count() & ~1);
     // (algorithmic FLOPs: the repeated encoding blocks carry the split / correction weights -- extra tensor work, not
@@ -1975,16 +1987,17 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
 // ---------------------------------------------------------------------------------------------------------------
 // All chunks of a pass, two in flight (see ChainSync)
 // ---------------------------------------------------------------------------------------------------------------
+#define TC_MAX_LANES 4
 namespace {
 struct Lanes {
-    cudaStream_t stream[2];
-    cudaEvent_t fork, join[2], slot[2][9];
+    cudaStream_t stream[TC_MAX_LANES];
+    cudaEvent_t fork, join[TC_MAX_LANES], slot[TC_MAX_LANES][9];
     bool ok = false;
 };
 int lanes_get(Lanes** out) {
     static Lanes L;
     if (!L.ok) {
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < TC_MAX_LANES; ++k) {
             PCN_CUDA(cudaStreamCreateWithFlags(&L.stream[k], cudaStreamNonBlocking));
             PCN_CUDA(cudaEventCreateWithFlags(&L.join[k], cudaEventDisableTiming));
             for (int i = 0; i < 9; ++i) PCN_CUDA(cudaEventCreateWithFlags(&L.slot[k][i], cudaEventDisableTiming));
@@ -2001,8 +2014,8 @@ static int tc_chunks(bool backward, const pcnerf_mlp_params* P, const pcnerf_mlp
                      int64_t chunk, float* out_p, const float* grad_p, void* const* saved, const size_t* saved_bytes,
                      void* const* scratch, size_t scratch_bytes, int lanes, cudaStream_t st) {
     PCN_CHECK_ARG(P && P->precision == 1 && enc && out_p && saved && saved_bytes && scratch && rows >= 1 && chunk >= 1 &&
-                      (lanes == 1 || lanes == 2),
-                  "mlp_tc_chunks: bad arguments (precision 1, lanes 1 or 2)");
+                      lanes >= 1 && lanes <= TC_MAX_LANES,
+                  "mlp_tc_chunks: bad arguments (precision 1, 1..4 lanes)");
     {
         // the per-chunk checks of pcnerf_mlp_forward / pcnerf_mlp_backward, for every chunk, BEFORE anything is launched
         const int64_t nch = pcn_cdiv(rows, chunk);
@@ -2023,32 +2036,33 @@ static int tc_chunks(bool backward, const pcnerf_mlp_params* P, const pcnerf_mlp
         }
     }
     Lanes* L = nullptr;
-    if (lanes == 2) {
+    if (lanes > 1) {
         if (int rc = lanes_get(&L)) return rc;
         PCN_CUDA(cudaEventRecord(L->fork, st));
-        for (int k = 0; k < 2; ++k) PCN_CUDA(cudaStreamWaitEvent(L->stream[k], L->fork, 0));
+        for (int k = 0; k < lanes; ++k) PCN_CUDA(cudaStreamWaitEvent(L->stream[k], L->fork, 0));
     }
     const int64_t nchunks = pcn_cdiv(rows, chunk);
     int rc = 0;
     for (int64_t c = 0; c < nchunks && !rc; ++c) {
-        const int k = lanes == 2 ? (int)(c & 1) : 0;
+        const int k = lanes > 1 ? (int)(c % lanes) : 0;
+        const int kprev = lanes > 1 ? (int)((c + lanes - 1) % lanes) : 0;       // lane of chunk c - 1
         const int64_t r0 = c * chunk, r = rows - r0 < chunk ? rows - r0 : chunk;
         pcnerf_mlp_params Pc = *P;
         Pc.prepared = c >= lanes ? 1 : P->prepared;      // every lane derives its weight copies on its first chunk
         ChainSync cs;
         for (int i = 0; i < 9; ++i) {
-            cs.rec[i] = lanes == 2 ? L->slot[k][i] : nullptr;
-            cs.wait[i] = (lanes == 2 && c > 0) ? L->slot[k ^ 1][i] : nullptr;
+            cs.rec[i] = lanes > 1 ? L->slot[k][i] : nullptr;
+            cs.wait[i] = (lanes > 1 && c > 0) ? L->slot[kprev][i] : nullptr;
         }
-        cudaStream_t s = lanes == 2 ? L->stream[k] : st;
+        cudaStream_t s = lanes > 1 ? L->stream[k] : st;
         const void* e = (const char*)enc + (size_t)r0 * 64 * 2;
-        g_chain = lanes == 2 ? &cs : nullptr;
+        g_chain = lanes > 1 ? &cs : nullptr;
         rc = backward ? mlp_tc_backward(&Pc, G, e, r, out_p + r0, grad_p + r0, saved[c], 0, scratch[k], 0, s)
                       : mlp_tc_forward(&Pc, e, r, out_p + r0, saved[c], 0, scratch[k], 0, s);
         g_chain = nullptr;
     }
-    if (lanes == 2)
-        for (int k = 0; k < 2; ++k) {                     // join even after an error: never leave a capture forked
+    if (lanes > 1)
+        for (int k = 0; k < lanes; ++k) {                 // join even after an error: never leave a capture forked
             cudaEventRecord(L->join[k], L->stream[k]);
             cudaStreamWaitEvent(st, L->join[k], 0);
         }

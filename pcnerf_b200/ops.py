@@ -319,7 +319,7 @@ _SCRATCH_RETIRED = []             # outgrown scratch buffers, kept alive for the
 EVAL_CHUNK_FLOOR = 1 << 20        # rows per launch of the eval-mode tensor-core MLP (tests lower it to cover chunking)
 
 
-TC_LANES = int(__import__('os').environ.get('PCNERF_TC_LANES', '2'))   # BN chunks in flight in the training-mode tensor-core MLP
+TC_LANES = int(__import__('os').environ.get('PCNERF_TC_LANES', '4'))   # BN chunks in flight in the training-mode tensor-core MLP (1..4; measured 61.4 / 60.1 / 59.8 ms per C2 step with 2 / 3 / 4)
 
 
 def _scratch(rows, precision, device, lane=0):
@@ -563,14 +563,14 @@ class CompositeFunction(torch.autograd.Function):
         w = torch.empty((n, P_), dtype=torch.float32, device=dev)
         depth = torch.empty(n, dtype=torch.float32, device=dev)
         per_ray = torch.empty((n, 8), dtype=torch.float32, device=dev) if child else None
-        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        sums = torch.empty(5, dtype=torch.float64, device=dev)
         if noise is not None:
             noise = _cuda_f32(noise, "noise")
+        # (the three loss scalars are written by the last block of the forward kernel: no finaliser launch)
+        losses = torch.empty(3, dtype=torch.float32, device=dev)
         check(lib().pcnerf_composite_fwd(_p(p), _p(z), _p(rays), ld, n, P_, cn, cf, rc, _p(noise), float(noise_std),
-                                         float(epsilon), int(flags), _p(w), _p(depth), _p(per_ray), _p(sums), _stream()))
-        losses = torch.zeros(3, dtype=torch.float32, device=dev)
-        if (child or rloss) and n > 0:
-            check(lib().pcnerf_composite_losses(_p(sums), n, _p(losses), _stream()))
+                                         float(epsilon), int(flags), _p(w), _p(depth), _p(per_ray), _p(sums), _p(losses),
+                                         _stream()))
         if flags & COMP_OPACITY:
             opacity = (sums[2] / max(n * P_, 1)).to(torch.float32)
         else:

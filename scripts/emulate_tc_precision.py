@@ -116,7 +116,7 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--chunk", type=int, default=262144)
     ap.add_argument("--seed", type=int, default=2024)
-    ap.add_argument("--study", default="all", choices=["all", "layers", "tail", "merged"])
+    ap.add_argument("--study", default="all", choices=["all", "layers", "tail", "merged", "subsets"])
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     N, S = a.rays, 64
@@ -151,6 +151,14 @@ def main():
         rep("E+H", run("EH"))
         rep("E+H+C all layers", run("EHC", allL))
         rep("E+H+C layer 4 only", run("EHC", (4,)))
+        return
+    if a.study == "subsets":
+        rep("E+H+W (shipped r1)", run("EHW"))
+        rep("E+H+C all layers", run("EHC", allL))
+        rep("E+H+C layers 4-7", run("EHC", (4, 5, 6, 7)))
+        rep("E+H+C layers 0,4-7", run("EHC", (0, 4, 5, 6, 7)))
+        rep("E+H+C layers 0-4", run("EHC", (0, 1, 2, 3, 4)))
+        rep("E+H+C layers 0,2,4,6,7", run("EHC", (0, 2, 4, 6, 7)))
         return
     if a.study == "merged":
         rep("E+H+W (shipped)", run("EHW"))

@@ -43,3 +43,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+(oracle|pcnerf_oracle|ref_shim)", txt, re.M), f
+
+
+def test_torch_ops_registered_for_cuda_only():
+    """the stages are dispatcher ops `torch.ops.pcnerf.*` with a CUDA kernel only -- a CPU tensor finds no
+    kernel (the dispatcher raises), nothing is computed on the host."""
+    import pcnerf_b200.torch_ops as t
+    for name in t.OPS:
+        assert hasattr(torch.ops.pcnerf, name), name
+    with pytest.raises(NotImplementedError):
+        torch.ops.pcnerf.points(torch.zeros(4, 13), torch.zeros(4))
+    with pytest.raises(NotImplementedError):
+        torch.ops.pcnerf.search_select(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.uint8), torch.zeros(4))

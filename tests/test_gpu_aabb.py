@@ -114,12 +114,13 @@ def test_empty_inputs():
     assert r.shape == (0, 13) and o.shape == (0, 1)
 
 
-def test_real_scale_box_count_bit_exact_vs_oracle():
-    """K = 3,000 child boxes: more than fits the shared-memory staging (the shipped KITTI scene has 15,333), so the
-    kernels read the boxes through L2 instead -- results must not change."""
+@pytest.mark.parametrize("K,parent", [(3000, "kitti"), (15333, "kitti"), (5729, "maicity")])
+def test_real_scale_box_count_bit_exact_vs_oracle(K, parent):
+    """The child-box counts of the shipped scenes (15,333 boxes KITTI, 5,729 MaiCity; 3,000 = the first
+    size beyond the shared-memory staging): the kernels read the boxes through L2 instead -- results must not change."""
     from pcnerf_b200 import ops, synth
-    K, n = 3000, 300
-    scene = synth.make_scene(4242, K, synth.KITTI_PARENT)
+    n = 300
+    scene = synth.make_scene(4242, K, synth.KITTI_PARENT if parent == "kitti" else synth.MAICITY_PARENT)
     pts = synth.make_points(scene, 6, n)
     dirs, dist = synth.rays_from_points(scene.origin, pts)
     ref, _ = orc.pack_train_rays_from_dirs(scene.origin, dirs, dist, pts, scene.centres, scene.child_bounds,

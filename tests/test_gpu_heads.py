@@ -396,3 +396,21 @@ def test_logging_metrics_vs_formulas():
         e = (pred - gt).abs() if m is None else (pred - gt).abs()[m]
         np.testing.assert_allclose(metrics.abs_error(pred, gt, m).item(), e.mean().item(), rtol=2e-6)
         np.testing.assert_allclose(metrics.acc_thres(pred, gt, m).item(), ((e < 0.2).sum() / e.shape[0] * 100).item(), rtol=2e-6)
+
+
+def test_torch_ops_dispatch_to_the_same_kernels():
+    """torch.ops.pcnerf.* (pcnerf_b200.torch_ops) against the direct wrappers: identical results."""
+    import pcnerf_b200.torch_ops  # noqa: F401
+    from pcnerf_b200 import ops, synth
+    rays = torch.from_numpy(synth.synth_train_rays(3, 256, K=8)).to(dev())
+    z0, e0 = ops.sample_encode_coarse(rays, 57, 7, 6, 7, 10, 11, False, 0.0, None, True, False)
+    z1, e1 = torch.ops.pcnerf.sample_encode_coarse(rays, 57, 7, 6, 7, 0.0, None, False)
+    assert torch.equal(z0, z1) and torch.equal(e0, e1)
+    p = torch.sigmoid(torch.randn((256, 64), device=dev(), generator=torch.Generator(device=dev()).manual_seed(1)))
+    w0, d0, fl0, dl0, *_ = ops.composite(p, z0, rays, (10, 11, 14), None, 0.0, 1e-10, ops.COMP_CHILD_LOSS | ops.COMP_RANGE_LOSS)
+    w1, d1, l1 = torch.ops.pcnerf.composite_fwd(p, z0, rays, 10, 11, 14, 1e-10, 5)
+    assert torch.equal(w0, w1) and torch.equal(d0, d1) and float(l1[0]) == float(fl0) and float(l1[1]) == float(dl0)
+    zf0, _ = ops.sample_encode_fine(rays, z0, w0, 128, None, True, True, False)
+    zf1, _ = torch.ops.pcnerf.sample_encode_fine(rays, z0, w0, 128, None, False)
+    assert torch.equal(zf0, zf1)
+    assert torch.equal(torch.ops.pcnerf.points(rays, d0), ops.points(rays, d0))
