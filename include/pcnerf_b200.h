@@ -244,10 +244,12 @@ void pcnerf_tc_set_fused_eval(int on);
 int pcnerf_tc_get_fused_eval(void);
 
 /* Training-mode row GEMMs (forward and data gradient of every Linear, pcnerf_tc_rowgemm and the precision-1 MLP passes).
- * Process-wide switch: 0 (default) = one CTA per SM, the two CTAs of a pair split the 256 output columns of a row tile;
- * 1 = clusters of two CTAs (tcgen05.mma.cta_group::2, M = 256): the pair splits the ROWS, every A tile is loaded once.
- * Same results up to fp32 summation order in the column statistics; measured at parity (csrc/mlp_tc.cu, k_tc_rowgemm2).
- * Initial value: environment variable PCNERF_TC_PAIRS. */
+ * Process-wide switch, a bit mask: bit 0 = forward GEMMs, bit 1 = data-gradient GEMMs on clusters of two CTAs
+ * (tcgen05.mma.cta_group::2, M = 256: the pair splits the ROWS of a two-tile unit, every A tile is loaded once, each SM holds
+ * half of the weight rows); a clear bit = one CTA per SM, the two CTAs of a twin split the 256 output columns of a row tile
+ * (N = 128 MMAs).  Same results up to fp32 summation order in the column statistics.  Default 1 (forward on pairs: measured
+ * 17.4 vs 19.0 ms per C2 step; the data-gradient epilogue is faster in the column-split form).  Initial value: environment
+ * variable PCNERF_TC_PAIRS. */
 void pcnerf_tc_set_row_pairs(int on);
 int pcnerf_tc_get_row_pairs(void);
 

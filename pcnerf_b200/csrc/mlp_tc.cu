@@ -225,6 +225,7 @@ __device__ __forceinline__ TilePlan tile_plan(int sched, int ntiles, int pair, i
 
 #define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
 #define TC_NBUF 2               // staging buffers per epilogue warp
+#define TC_PAIRS_DEFAULT 1      // row-GEMM form: bit 0 = forward on CTA pairs, bit 1 = data gradient on CTA pairs
 #define TC_NBUF2 4              // ... of the CTA-pair form (two 64-column rounds per tile, a pair of buffers each)
 
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
@@ -793,6 +794,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_MASK) : "memory");
 }
+// The same arrive WITHOUT cluster-scope release semantics (default .release.cta, what CUTLASS's ClusterBarrier::arrive
+// emits): for hand-offs that publish nothing through generic memory -- the TMEM-stage hand-back of k_tc_rowgemm2, whose
+// ordering is carried by tcgen05.fence::before/after_thread_sync.  With .release.cluster every arrive compiled to a
+// cluster-scope MEMBAR that waited for the warp's outstanding global loads (ncu on the first pair form: 25 % of all stall
+// samples on ERRBAR / SYNCS.ARRIVE with stall_membar; the data-gradient kernel, whose epilogue keeps H_{l-1} loads in
+// flight, was hit hardest: 23.8 vs 19.4 ms per step).
+__device__ __forceinline__ void mbar_arrive_leader_cta(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_MASK) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int code) {
     const long long t0 = clock64();
     for (;;) {
@@ -952,22 +962,41 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
-        uint4 e[2][4];
-        auto load_e = [&](int tile_, int cc_) {
-            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_, cb_ = half * 128 + cc_ * 64;
+        // DGRAD: this warp's 32 rows x 128 columns of H_{l-1} (fp16) for BOTH rounds of the NEXT unit are requested while the
+        // current unit is processed (a whole unit of prefetch distance; with the second round requested during the first,
+        // the load latency was exposed once per unit: data-gradient class 22.6 vs 19.4 ms per step).
+        uint4 e[2][2][4];
+        auto load_e = [&](int tile_) {
+            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_;
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+            for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = (lane >> 2) + 8 * i;
-                    e[c][i] = make_uint4(0, 0, 0, 0);
-                    if (row < left_)
-                        e[c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + cb_ + c * 32 + (lane & 3) * 8);
-                }
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = (lane >> 2) + 8 * i;
+                        e[cc][c][i] = make_uint4(0, 0, 0, 0);
+                        if (row < left_)
+                            e[cc][c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + half * 128 + cc * 64 +
+                                                                         c * 32 + (lane & 3) * 8);
+                    }
         };
-        if (EPI == TC_DGRAD && tp.count > 0) load_e(tp.first * 2 + rank, 0);
+        if (EPI == TC_DGRAD && tp.count > 0) load_e(tp.first * 2 + rank);
         for (int it = 0; it < tp.count; ++it) {
             const int tile = (tp.first + it * tp.step) * 2 + rank;
+            if (EPI == TC_DGRAD) {
+                // this thread's rows of H_{l-1}: staged through the (idle) output buffers of both rounds, re-read row-wise below
+                if (lane == 0) tma_store_wait_read<0>();      // the previous unit's stores have read the staging buffers
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sts128(stage_addr(bufs4[cc][c], (lane >> 2) + 8 * i, lane & 3), e[cc][c][i]);
+                __syncwarp();
+                if (it + 1 < tp.count) load_e((tp.first + (it + 1) * tp.step) * 2 + rank);
+            }
             mbar_wait_spin(bar_tfull + 8 * as, aph, 35);
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
@@ -976,32 +1005,19 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             //      straight back to the MMA warp (with the stage held through round 0's stores and statistics the pair form
             //      was measured SLOWER than the single-CTA kernel: the leader stalled on tempty)
             uint32_t pk[2][2][16];
-            if (EPI == TC_DGRAD) {
-                if (lane == 0) tma_store_wait_read<0>();      // the previous tile's stores have read the staging buffers
-                __syncwarp();
-            }
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 const int colb = half * 128 + cc * 64;            // first output column of this round
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + colb);
                 const uint32_t* bufs = bufs4[cc];
                 uint32_t r[2][32];
-                if (EPI == TC_DGRAD) {
-                    // this thread's row of H_{l-1}: staged through the (currently idle) output buffers, re-read row-wise
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sts128(stage_addr(bufs[c], (lane >> 2) + 8 * i, lane & 3), e[c][i]);
-                    __syncwarp();
-                    if (cc == 0) load_e(tile, 1);
-                }
                 tmem_ld32_issue(tbase, r[0]);
                 tmem_ld32_issue(tbase + 32, r[1]);
                 tmem_ld_wait();
                 if (cc == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * as);
+                    if (lane == 0) mbar_arrive_leader_cta(bar_tempty + 8 * as);
                 }
                 if (EPI == TC_FWD) {
 #pragma unroll
@@ -1049,7 +1065,6 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                     __syncwarp();                          // every lane has read its row of E: the buffers can be rewritten
                 }
             }
-            if (EPI == TC_DGRAD && it + 1 < tp.count) load_e((tp.first + (it + 1) * tp.step) * 2 + rank, 0);
             // ---- phase B: the two rounds leave through the staging buffers (TMA stores) and feed the column statistics
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -1602,11 +1617,13 @@ int tc_sched_mode() {
 }
 
 // row GEMMs on CTA pairs (k_tc_rowgemm2): pcnerf_tc_set_row_pairs(1) or PCNERF_TC_PAIRS=1; default off (see the kernel)
+// bit 0: forward GEMMs, bit 1: data-gradient GEMMs
 int g_row_pairs = -1;
 int tc_pairs_mode() {
-    if (g_row_pairs < 0) { const char* e = getenv("PCNERF_TC_PAIRS"); g_row_pairs = e ? (atoi(e) != 0) : 0; }
+    if (g_row_pairs < 0) { const char* e = getenv("PCNERF_TC_PAIRS"); g_row_pairs = e ? (atoi(e) & 3) : TC_PAIRS_DEFAULT; }
     return g_row_pairs;
 }
+bool tc_pairs_for(int mode) { return (tc_pairs_mode() >> (mode == TC_FWD ? 0 : 1)) & 1; }
 
 int sm_count() {
     static int n = 0;
@@ -1642,7 +1659,8 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     RowGemmArgs g;
     g.rows = (int)rows; g.a0_blocks = k0 / 64; g.kb0 = a0_rep * k0 / 64; g.kb_total = g.kb0 + k1 / 64;
-    const int nbuf = tc_pairs_mode() ? TC_NBUF2 : TC_NBUF;
+    const bool pairs = tc_pairs_for(mode);
+    const int nbuf = pairs ? TC_NBUF2 : TC_NBUF;
     {
         // everything that is left of the 227 KB after the resident weights and the staging buffers becomes A ring
         const size_t fixed = 1024 + (size_t)g.kb_total * TC_B_BYTES + 8 * nbuf * TC_STAGE_BYTES + 4096 /* static */;
@@ -1670,7 +1688,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     // (algorithmic FLOPs: the repeated encoding blocks carry the split / correction weights -- extra tensor work, not
     // extra algorithmic work)
     const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
-    if (tc_pairs_mode()) {
+    if (pairs) {
         // CTA pairs (k_tc_rowgemm2): clusters of two, a unit of work = two row tiles
         const int nunits = (ntiles + 1) / 2;
         const int ncl = nunits < sm_count() / 2 ? nunits : sm_count() / 2;
@@ -1742,7 +1760,7 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
 static int g_fused_eval = 2;     // 0 = layered, 1 = fused (one CTA per unit), 2 = fused on CTA pairs (cta_group::2)
 extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on < 0 ? 0 : (on > 2 ? 2 : on); }
 extern "C" int pcnerf_tc_get_fused_eval(void) { return g_fused_eval; }
-extern "C" void pcnerf_tc_set_row_pairs(int on) { g_row_pairs = on ? 1 : 0; }
+extern "C" void pcnerf_tc_set_row_pairs(int on) { g_row_pairs = on & 3; }
 extern "C" int pcnerf_tc_get_row_pairs(void) { return tc_pairs_mode(); }
 
 // ---- two BN batches (chunks) in flight: pcnerf_mlp_tc_{forward,backward}_chunks issue consecutive chunks on two internal

@@ -363,7 +363,8 @@ def tc_fused_eval(on=None):
 
 
 def tc_row_pairs(on=None):
-    """Get / set the training-mode row-GEMM form of the precision-1 MLP: 0 = one CTA per SM (default), 1 = CTA pairs."""
+    """Get / set the training-mode row-GEMM form of the precision-1 MLP (bit mask): bit 0 = forward GEMMs on CTA pairs
+    (cta_group::2, k_tc_rowgemm2), bit 1 = data-gradient GEMMs on CTA pairs; 0 = column-split CTAs (k_tc_rowgemm)."""
     if on is not None:
         lib().pcnerf_tc_set_row_pairs(int(on))
     return int(lib().pcnerf_tc_get_row_pairs())

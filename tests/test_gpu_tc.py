@@ -17,9 +17,10 @@ def _rand(shape, dt, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(dt).to(dev())
 
 
-@pytest.fixture(params=[0, 1], ids=["cta", "pairs"])
+@pytest.fixture(params=[0, 3], ids=["cta", "pairs"])
 def row_form(request):
-    """Both forms of the training-mode row GEMM: one CTA per SM (default) and CTA pairs (cta_group::2, k_tc_rowgemm2)."""
+    """Both forms of the training-mode row GEMMs: column-split CTAs (k_tc_rowgemm) and CTA pairs (cta_group::2,
+    k_tc_rowgemm2) -- bit 0 = forward, bit 1 = data gradient; the shipped default is forward on pairs."""
     from pcnerf_b200 import ops
     old = ops.tc_row_pairs()
     ops.tc_row_pairs(request.param)
