@@ -503,59 +503,73 @@ def run_b200(a):
                 kernels[k]["algorithmic_gbs"] = gbs
                 kernels[k]["hbm_frac"] = gbs / float(peaks.get("hbm_gbs", 6650.0))
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        # dominant kernel = the forward row GEMM (k_tc_rowgemm<FWD> / k_gemm<fwd>): FLOPs per launch / mean launch time
-        f_ms, f_n, f_fl = prof["mlp_gemm_fwd"]
-        achieved = f_fl / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if a.precision == "tc" and CHUNK == tr["rows"]:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]      # one ncu --set full capture, per launch
-        except (OSError, ValueError, KeyError):
-            pass
-        all_ms = max(sum(v[0] for v in prof.values()), 1e-9)
-        # mean algorithmic bytes of one forward row GEMM of this workload: 7 of 8 layers read (rows,256) and write
-        # (rows,256) 16-bit activations, layer 0 reads the (rows,64) encoding, layer 4 reads both
-        esz = 2 if a.precision == "tc" else 4
-        alg_bytes = CHUNK * esz * (7 * 256 + 2 * 64 + 8 * 256) / 8.0 if a.precision in ("tc", "fp32") else 0
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        kname = "mlp forward row GEMM (%s)" % ("k_tc_rowgemm<FWD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32")
-        tensor = {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
-                  "gflop_per_launch": f_fl / max(f_n, 1) / 1e9}
-        gemms = {"achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
-                 "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms > 0 else 0.0, "unit": "TFLOP/s",
-                 "share_of_step": g_ms / all_ms}
-        common = {"launches_per_step": f_n / psteps, "us_per_launch": 1e3 * f_ms / max(f_n, 1), "share_of_step": f_ms / all_ms}
-        if a.precision == "tc" and alg_bytes:
-            # The layered GEMM moves one 16-bit activation matrix in and one out per layer (train-mode BN needs a chunk-wide
-            # reduction between layers): 124 FLOP/byte against a machine balance of 210 -> the roofline that bounds it is HBM
-            # (attainable = intensity x bandwidth, below the tensor peak).  The tensor-pipe view is kept beside it.
-            gbs = alg_bytes * f_n / (f_ms * 1e-3) / 1e9
-            tensor["attainable_tflops"] = (f_fl / max(f_n, 1)) / alg_bytes * hbm_peak / 1e3
-            # the other two GEMM classes by the same rule (bytes per launch)
-            d_ms, d_n, _ = prof["mlp_gemm_dgrad"]
-            w_ms, w_n, _ = prof["mlp_gemm_wgrad"]
-            d_bytes = d_n * CHUNK * 512.0 * 3                         # DH_l in, H_{l-1} in (BN backward), DH_{l-1} out
-            w_bytes = (w_n / 9.0) * CHUNK * (7 * 1024.0 + 2 * 640.0)  # per chunk: 7 launches on H (256 wide), 2 on the encoding
-            for k, ms_k, by in (("mlp_gemm_fwd", f_ms, alg_bytes * f_n), ("mlp_gemm_dgrad", d_ms, d_bytes),
-                                ("mlp_gemm_wgrad", w_ms, w_bytes)):
-                if ms_k > 0:
-                    kernels[k]["algorithmic_gbs"] = by / (ms_k * 1e-3) / 1e9
-                    kernels[k]["hbm_frac"] = kernels[k]["algorithmic_gbs"] / hbm_peak
-            gemms["hbm_frac"] = (alg_bytes * f_n + d_bytes + w_bytes) / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms > 0 else 0.0
-            roofline = dict({"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                             "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
-                             "algorithmic_bytes_per_launch": alg_bytes,
-                             "intensity_flop_per_byte": (f_fl / max(f_n, 1)) / alg_bytes,
-                             "machine_balance_flop_per_byte": peak * 1e3 / hbm_peak,
-                             "tensor": tensor, "all_mlp_gemms": gemms}, **common)
-        else:
-            roofline = dict({"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak,
-                             "peak_source": tensor["peak_source"], "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": traffic, "gflop_per_launch": tensor["gflop_per_launch"],
-                             "all_mlp_gemms": gemms}, **common)
+        all_ms = max(sum(v[0] for v in prof.values()), 1e-9)
+        f_ms, f_n, f_fl = prof["mlp_gemm_fwd"]
+        d_ms, d_n, d_fl = prof["mlp_gemm_dgrad"]
+        w_ms, w_n, w_fl = prof["mlp_gemm_wgrad"]
+        esz = 2 if a.precision == "tc" else 4
+        # ALGORITHMIC bytes per launch: forward = one activation matrix in, one out per layer (layer 0
+        # reads the (rows,64) encoding, layer 4 both; the correction blocks of k_tc_fold re-read the L2-resident encoding and
+        # are overhead, not algorithmic traffic); data gradient = DH_l in, H_{l-1} in, DH_{l-1} out; weight gradient = DH_l and
+        # H_{l-1} (or the encoding) in
+        by = {"mlp_gemm_fwd": CHUNK * esz * (7 * 256 + 2 * 64 + 8 * 256) / 8.0 * f_n,
+              "mlp_gemm_dgrad": d_n * CHUNK * 256.0 * esz * 3,
+              "mlp_gemm_wgrad": (w_n / 9.0) * CHUNK * esz * (7 * 512.0 + 2 * 320.0)}
+        names = {"mlp_gemm_fwd": "mlp forward row GEMM (%s)" % ("k_tc_rowgemm2<FWD>: TMA + tcgen05.mma.cta_group::2 + TMEM, CTA pairs"
+                                                                 if a.precision == "tc" else "k_gemm fp32"),
+                 "mlp_gemm_dgrad": "mlp data-gradient row GEMM with the BN backward in its epilogue (%s)"
+                                   % ("k_tc_rowgemm<DGRAD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32"),
+                 "mlp_gemm_wgrad": "mlp weight-gradient GEMM, split-K over the rows (%s)"
+                                   % ("k_tc_wgrad: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32")}
+        cls = {}
+        for k, (ms_k, n_k, fl_k) in (("mlp_gemm_fwd", (f_ms, f_n, f_fl)), ("mlp_gemm_dgrad", (d_ms, d_n, d_fl)),
+                                    ("mlp_gemm_wgrad", (w_ms, w_n, w_fl))):
+            if ms_k > 0 and n_k > 0:
+                gbs = by[k] / (ms_k * 1e-3) / 1e9
+                tfl = fl_k / (ms_k * 1e-3) / 1e12
+                kernels[k]["algorithmic_gbs"] = gbs
+                kernels[k]["hbm_frac"] = gbs / hbm_peak
+                cls[k] = {"ms_per_step": ms_k / psteps, "us_per_launch": 1e3 * ms_k / n_k, "launches_per_step": n_k / psteps,
+                          "algorithmic_gbs": gbs, "hbm_frac": gbs / hbm_peak, "tflops": tfl, "tensor_frac": tfl / peak,
+                          "share_of_step": ms_k / all_ms, "algorithmic_bytes_per_launch": by[k] / n_k,
+                          "intensity_flop_per_byte": fl_k / by[k]}
+        g_ms, g_fl = f_ms + d_ms + w_ms, f_fl + d_fl + w_fl
+        gemms = {"achieved": g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0, "unit": "TFLOP/s",
+                 "frac": (g_fl / (g_ms * 1e-3) / 1e12 / peak) if g_ms > 0 else 0.0, "share_of_step": g_ms / all_ms,
+                 "hbm_frac": (sum(by.values()) / (g_ms * 1e-3) / 1e9 / hbm_peak) if g_ms > 0 else 0.0}
+        traffic, traffic_src = None, None
+        dom = max(cls, key=lambda k: cls[k]["ms_per_step"]) if cls else None
+        if dom is not None:
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+                if a.precision == "tc" and CHUNK == tr["rows"] and dom in tr:
+                    traffic = tr[dom]["dram_bytes_read"] + tr[dom]["dram_bytes_write"]
+                    traffic_src = "static: one ncu --set full capture of this kernel (profiles/r02_traffic.json: %s), not measured in this run" % tr[dom]["source"]
+            except (OSError, ValueError, KeyError):
+                pass
+            c = cls[dom]
+            if a.precision == "tc":
+                # 16-bit layered GEMMs: 124-149 FLOP per algorithmic byte against a machine balance of 210 -> HBM is the
+                # roofline that bounds every class (train-mode BN forces each layer's activations through HBM once)
+                roofline = {"kernel": names[dom], "class": dom, "dominant_by": "largest device time per step of the three GEMM classes",
+                            "bound": "hbm", "achieved": c["algorithmic_gbs"], "peak": hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650", "unit": "GB/s",
+                            "frac": c["hbm_frac"], "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_launch": c["algorithmic_bytes_per_launch"],
+                            "intensity_flop_per_byte": c["intensity_flop_per_byte"],
+                            "machine_balance_flop_per_byte": peak * 1e3 / hbm_peak, "us_per_launch": c["us_per_launch"],
+                            "launches_per_step": c["launches_per_step"], "share_of_step": c["share_of_step"],
+                            "tensor": {"achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": c["tensor_frac"],
+                                       "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                                       "attainable_tflops": c["intensity_flop_per_byte"] * hbm_peak / 1e3},
+                            "classes": cls, "all_mlp_gemms": gemms}
+            else:
+                roofline = {"kernel": names[dom], "class": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak,
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                            "unit": "TFLOP/s", "frac": c["tensor_frac"], "traffic": None, "us_per_launch": c["us_per_launch"],
+                            "launches_per_step": c["launches_per_step"], "share_of_step": c["share_of_step"],
+                            "classes": cls, "all_mlp_gemms": gemms}
 
     out = {"metric": METRIC, "value": rays_total / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": a.steps,
            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -742,7 +756,9 @@ def time_c5(a, rank, world, dev, emb):
     bw = 40.0
     rng = np.random.default_rng(5000)
     parents, scenes = [], []
-    owned = set(sc.owned_blocks(P, world, rank))
+    # adjacent blocks on different ranks (scene.spread_owners): a frame only sees the 3 x 3 blocks around its sensor
+    owners = [((i % side) + 3 * (i // side)) % world for i in range(P)]
+    owned = set(sc.owned_blocks(P, world, rank, owners))
     for i in range(P):
         gx, gy = i % side, i // side
         box = (gx * bw, (gx + 1) * bw, gy * bw, (gy + 1) * bw, -1.7, 0.5)
@@ -759,8 +775,9 @@ def time_c5(a, rank, world, dev, emb):
     fb = 2 * world
     origins, pts, fid = [], [], []
     for f in range(fb):
-        c = (f * 7) % P
-        gx, gy = c % side, c // side
+        # the frames of a batch are spread over the whole scene (a batch of a 1,000-frame job spans the trajectory), so that
+        # every rank's parent blocks receive rays: sensor blocks spaced P / fb apart
+        gx, gy = (3 * f + 1) % side, ((f * side) // fb + 1) % side
         nb = [(x, y) for x in range(max(gx - 1, 0), min(gx + 2, side)) for y in range(max(gy - 1, 0), min(gy + 2, side))]
         o = np.array([(gx + 0.5) * bw + rng.uniform(-5, 5), (gy + 0.5) * bw + rng.uniform(-5, 5), rng.uniform(-0.3, 0.0)])
         per = RAYS // len(nb)
@@ -776,7 +793,7 @@ def time_c5(a, rank, world, dev, emb):
 
     def batch():
         res = sc.render_scene_frames(parents, origins_d, pts_d, fid_d, emb, S, NI, 184320, 2, 18432, 0.05, world, rank,
-                                     boxes_dev=boxes_d)
+                                     boxes_dev=boxes_d, owners=owners)
         return sum(int(v.shape[0]) for v in res.values())
 
     rendered = batch()                                     # warm-up (also loads every block's folded weights)
@@ -802,7 +819,7 @@ def time_c5(a, rank, world, dev, emb):
                         "two-step depth inference, %d frames x %d returns per batch" % (P, K5, world, fb, RAYS),
             "metric": "depth-inference rays/s (physical rays, multi-parent scene)", "value": frames * RAYS / sec,
             "unit": "rays/s", "frames_per_s": frames / sec, "frames_timed": frames, "frames_per_batch": fb,
-            "parents": P, "parents_per_gpu": len(owned), "child_aabbs_per_parent": K5,
+            "parents": P, "parents_per_gpu": len(owned), "block_ownership": "(ix + 3 iy) mod N: adjacent blocks on different ranks", "child_aabbs_per_parent": K5,
             "rendered_points_per_batch": float(tot.item()), "returns_per_batch": fb * RAYS, "ms_per_batch": 1e3 * sec / reps,
             "N_samples": S, "N_importance": NI, "precision": a.precision, "scaling": "weak (frames per batch grow with N)"}
 

@@ -201,6 +201,7 @@ struct RowGemmArgs {
     int sched;                  // row-tile order of a CTA pair: 0 interleaved (pair, pair + npairs, ...), 1 contiguous slab
                                 // walked upwards, 2 contiguous slab walked downwards (see tile_plan)
     int nostat;                 // 1: eval-mode BN (running statistics): the epilogue skips the column sums
+    int stage_pairs;            // pair form: staging-buffer pairs per epilogue warp (2 = one per 64-column round, 1 = shared)
     int hint;                   // 1: the A tiles are not read again soon -> L2 evict_first, so that the freshly WRITTEN
                                 // output matrix is what stays in the 126 MB L2 for the next kernel
 };
@@ -852,8 +853,12 @@ __device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtenso
 }
 #define TC_L2_EVICT_NORMAL 0x1000000000000000ull
 
-template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NEW = epilogue warps per CTA: 8 (each takes 128 columns of its quadrant's 32 rows in two 64-column rounds) or 16 (64
+// columns, one round; 576 threads, <= 113 registers).  The pair form is bound by its epilogue (ncu: the epilogue warps wait
+// for the MMA 14 % of their time, 1.1 warp instructions issued per cycle and SM: latency of a long dependent chain per
+// warp), so more warps per scheduler hide more of it.
+template <int EPI, int NEW>
+__global__ void __launch_bounds__(64 + 32 * NEW, 1)
 k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const RowGemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -870,11 +875,12 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
     const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
     const int rank = (int)cluster_ctarank();              // 0 = the pair's leader
+    constexpr int ROUNDS = 16 / NEW;                      // 64-column rounds per epilogue warp and tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_bfull, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 16); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 2 * NEW); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmA1);
@@ -883,9 +889,9 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
     if (EPI == TC_FWD) {
-        for (int i = threadIdx.x; i < 256; i += TC_THREADS) cvec[i] = g.vec[i];
+        for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) cvec[i] = g.vec[i];
     } else {
-        for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+        for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) {
             const float c0 = g.vec[i], c1 = g.vec[256 + i], c2 = g.vec[512 + i], mean = g.vec[768 + i];
             cvec[i] = c0;
             cvec[256 + i] = c2;
@@ -953,23 +959,32 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     } else if (warp >= 2) {
         // ===== epilogue: warp (2..9) -> TMEM lane quadrant warp%4 (rows q*32 + lane of THIS CTA's tile), 128-column half
         // (warp-2)/4, in two rounds of 64 columns; per round the code of k_tc_rowgemm's epilogue.
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, half = (warp - 2) >> 2;   // TMEM lane quadrant (= warp index mod 4), column group of 64 * ROUNDS
         // one pair of staging buffers PER ROUND: round 1 does not wait for the bulk stores of round 0 to have read theirs
         // (with two buffers per warp every tile exposed the pick-up latency of a TMA store once; the pair form was
         // measured 12-19 % slower than the column-split kernel that way)
-        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF2 * TC_STAGE_BYTES);
-        const uint32_t bufs4[2][2] = {{buf0, buf0 + TC_STAGE_BYTES}, {buf0 + 2 * TC_STAGE_BYTES, buf0 + 3 * TC_STAGE_BYTES}};
-        double acc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, acc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int spairs = ROUNDS == 1 ? 1 : g.stage_pairs;           // staging-buffer pairs of this warp
+        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (2 * spairs * TC_STAGE_BYTES);
+        uint32_t bufs4[ROUNDS][2];
+#pragma unroll
+        for (int cc = 0; cc < ROUNDS; ++cc) {
+            const int pr = cc % spairs;
+            bufs4[cc][0] = buf0 + (2 * pr) * TC_STAGE_BYTES;
+            bufs4[cc][1] = buf0 + (2 * pr + 1) * TC_STAGE_BYTES;
+        }
+        double acc0[4 * ROUNDS], acc1[4 * ROUNDS];
+#pragma unroll
+        for (int i = 0; i < 4 * ROUNDS; ++i) { acc0[i] = 0.0; acc1[i] = 0.0; }
         int as = 0;
         uint32_t aph = 0;
         // DGRAD: this warp's 32 rows x 128 columns of H_{l-1} (fp16) for BOTH rounds of the NEXT unit are requested while the
         // current unit is processed (a whole unit of prefetch distance; with the second round requested during the first,
         // the load latency was exposed once per unit: data-gradient class 22.6 vs 19.4 ms per step).
-        uint4 e[2][2][4];
+        uint4 e[ROUNDS][2][4];
         auto load_e = [&](int tile_) {
             const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc)
+            for (int cc = 0; cc < ROUNDS; ++cc)
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -977,7 +992,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                         const int row = (lane >> 2) + 8 * i;
                         e[cc][c][i] = make_uint4(0, 0, 0, 0);
                         if (row < left_)
-                            e[cc][c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + half * 128 + cc * 64 +
+                            e[cc][c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + half * (64 * ROUNDS) + cc * 64 +
                                                                          c * 32 + (lane & 3) * 8);
                     }
         };
@@ -989,7 +1004,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 if (lane == 0) tma_store_wait_read<0>();      // the previous unit's stores have read the staging buffers
                 __syncwarp();
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc)
+                for (int cc = 0; cc < ROUNDS; ++cc)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1004,17 +1019,17 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             // ---- phase A: both 64-column rounds of the accumulator -> packed 16-bit registers, then the TMEM stage goes
             //      straight back to the MMA warp (with the stage held through round 0's stores and statistics the pair form
             //      was measured SLOWER than the single-CTA kernel: the leader stalled on tempty)
-            uint32_t pk[2][2][16];
+            uint32_t pk[ROUNDS][2][16];
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int colb = half * 128 + cc * 64;            // first output column of this round
+            for (int cc = 0; cc < ROUNDS; ++cc) {
+                const int colb = half * (64 * ROUNDS) + cc * 64;  // first output column of this round
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + colb);
                 const uint32_t* bufs = bufs4[cc];
                 uint32_t r[2][32];
                 tmem_ld32_issue(tbase, r[0]);
                 tmem_ld32_issue(tbase + 32, r[1]);
                 tmem_ld_wait();
-                if (cc == 1) {
+                if (cc == ROUNDS - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader_cta(bar_tempty + 8 * as);
@@ -1067,11 +1082,11 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             }
             // ---- phase B: the two rounds leave through the staging buffers (TMA stores) and feed the column statistics
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int colb = half * 128 + cc * 64;
+            for (int cc = 0; cc < ROUNDS; ++cc) {
+                const int colb = half * (64 * ROUNDS) + cc * 64;
                 const uint32_t* bufs = bufs4[cc];
-                if (EPI == TC_FWD && cc == 0) {
-                    if (lane == 0) tma_store_wait_read<0>();  // the previous tile's stores have read the staging buffers
+                if ((EPI == TC_FWD && cc == 0) || (cc > 0 && spairs == 1)) {
+                    if (lane == 0) tma_store_wait_read<0>();  // earlier stores have read the staging buffers written next
                     __syncwarp();
                 }
                 stage_put_row(bufs[0], pk[cc][0], lane);
@@ -1099,32 +1114,35 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // ---- column statistics: quadrant warps -> CTA partial (staging memory is free now) -> global per-CTA slot of 256
         //      columns; the last CTA to arrive adds the slots up.
         double* sred = reinterpret_cast<double*>(sStage);              // [2 stats][4 quadrants][256 columns] = 16 KB
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"r"(32 * NEW) : "memory"); };    // the epilogue warps only
+        epi_sync();
         if (lane < 16) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc)
+            for (int cc = 0; cc < ROUNDS; ++cc)
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const int cl = half * 128 + cc * 64 + c * 32 + 2 * lane + j;
+                        const int cl = half * (64 * ROUNDS) + cc * 64 + c * 32 + 2 * lane + j;
                         sred[(0 * 4 + q) * 256 + cl] = acc0[4 * cc + 2 * c + j];
                         sred[(1 * 4 + q) * 256 + cl] = acc1[4 * cc + 2 * c + j];
                     }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int t = threadIdx.x - 64;                                 // 0..255 = column
+        epi_sync();
+        const int t = threadIdx.x - 64;                                 // 0 .. 32 NEW - 1; the first 256 = one column each
+        if (t < 256) {
 #pragma unroll
-        for (int st = 0; st < 2; ++st) {
-            const double v = sred[(st * 4 + 0) * 256 + t] + sred[(st * 4 + 1) * 256 + t] + sred[(st * 4 + 2) * 256 + t] +
-                             sred[(st * 4 + 3) * 256 + t];
-            g.partials[((size_t)blockIdx.x * 2 + st) * 256 + t] = v;
+            for (int st = 0; st < 2; ++st) {
+                const double v = sred[(st * 4 + 0) * 256 + t] + sred[(st * 4 + 1) * 256 + t] + sred[(st * 4 + 2) * 256 + t] +
+                                 sred[(st * 4 + 3) * 256 + t];
+                g.partials[((size_t)blockIdx.x * 2 + st) * 256 + t] = v;
+            }
+            __threadfence();
         }
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
         if (t == 0) s_last = atomicAdd(g.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (s_last) {
+        epi_sync();
+        if (s_last && t < 256) {
             __threadfence();
             double a0 = 0.0, a1 = 0.0;
             for (int b = 0; b < (int)gridDim.x; ++b) {
@@ -1642,7 +1660,7 @@ int sm_count() {
 // a0_rep: every 64-column block of A0 is consumed a0_rep times (k-blocks 0 .. a0_rep*k0/64 - 1 of B multiply A0)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
                    const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
-                   double* stat1, void* work, int dir, cudaStream_t st, int nostat = 0, int a0_rep = 1) {
+                   double* stat1, void* work, int dir, cudaStream_t st, int nostat = 0, int a0_rep = 1, int alg_k = -1) {
     PCN_CHECK_ARG(k0 % 64 == 0 && k1 % 64 == 0 && k0 >= 64 && a0_rep >= 1 && (k0 * a0_rep + k1) <= 384,
                   "tc rowgemm: K must be 64..384 in 64s");
     CUtensorMap mA0, mA1, mB;
@@ -1660,7 +1678,16 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     RowGemmArgs g;
     g.rows = (int)rows; g.a0_blocks = k0 / 64; g.kb0 = a0_rep * k0 / 64; g.kb_total = g.kb0 + k1 / 64;
     const bool pairs = tc_pairs_for(mode);
-    const int nbuf = pairs ? TC_NBUF2 : TC_NBUF;
+    static int sp_env = -1;
+    // forward on pairs: ONE pair of 2 KB staging buffers per epilogue warp (round 1 waits for round 0's bulk stores to have
+    // read them) leaves room for 6 A-ring stages instead of 4 -- measured 17.2 vs 18.0-18.9 ms per step: bytes in flight per
+    // SM count for more than the exposed store pick-up latency
+    if (sp_env < 0) { const char* e = getenv("PCNERF_TC_STAGE_PAIRS"); sp_env = e ? (atoi(e) == 2 ? 2 : 1) : 1; }
+    static int epi8 = -1;     // forward on pairs: 8 epilogue warps (two 64-column rounds each) or 16 (PCNERF_TC_EPI8=0)
+    if (epi8 < 0) { const char* e = getenv("PCNERF_TC_EPI8"); epi8 = e ? (atoi(e) != 0) : 1; }
+    const bool wide = pairs && mode == TC_FWD && !epi8;
+    const int spairs = wide ? 1 : (mode == TC_DGRAD ? 2 : sp_env);     // (the data-gradient epilogue stages H_{l-1} of both rounds at once)
+    const int nbuf = pairs ? (wide ? 4 : 2 * spairs) : TC_NBUF;       // 2 KB staging buffers per 8 epilogue warps' worth
     {
         // everything that is left of the 227 KB after the resident weights and the staging buffers becomes A ring
         const size_t fixed = 1024 + (size_t)g.kb_total * TC_B_BYTES + 8 * nbuf * TC_STAGE_BYTES + 4096 /* static */;
@@ -1677,6 +1704,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         g.hint = m == 2 ? 1 : 0;
     }
     g.nostat = nostat;
+    g.stage_pairs = spairs;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -1687,7 +1715,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     const int grid = 2 * ntiles < sm_count() ? 2 * ntiles : (sm_count() & ~1);
     // (algorithmic FLOPs: the repeated encoding blocks carry the split / correction weights -- extra tensor work, not
     // extra algorithmic work)
-    const double flops = 2.0 * (double)rows * 256.0 * (double)(k0 + k1);
+    const double flops = 2.0 * (double)rows * 256.0 * (double)(alg_k >= 0 ? alg_k : k0 + k1);
     if (pairs) {
         // CTA pairs (k_tc_rowgemm2): clusters of two, a unit of work = two row tiles
         const int nunits = (ntiles + 1) / 2;
@@ -1705,13 +1733,20 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         cfg.attrs = at;
         cfg.numAttrs = 1;
         if (mode == TC_FWD) {
-            PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // forward: 8 epilogue warps by default; 16 (one 64-column round each) measured no faster (18.4 vs 17.9 ms per step)
             PcnScope ps(PCN_K_GEMM_FWD, st, flops);
-            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD>, mA0, mA1, mB, mO, g));
+            if (epi8) {
+                PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_FWD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD, 8>, mA0, mA1, mB, mO, g));
+            } else {
+                cfg.blockDim = dim3(64 + 32 * 16);
+                PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_FWD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD, 16>, mA0, mA1, mB, mO, g));
+            }
         } else {
-            PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_DGRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             PcnScope ps(PCN_K_GEMM_DGRAD, st, flops);
-            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_DGRAD>, mA0, mA1, mB, mO, g));
+            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_DGRAD, 8>, mA0, mA1, mB, mO, g));
         }
         PCN_LAUNCH_CHECK();
         return 0;
@@ -1902,8 +1937,9 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
         // operand layout of layer l (k_tc_fold): [encoding blocks | H_{l-1}] x [their weight blocks | fp16(W')]
         const int encb = corr ? (l == 0 || l == 4 ? 2 : 1) : (l == 0 || l == 4 ? 1 : 0);
         const int ldw = encb * 64 + (l == 0 ? 0 : 256);
-        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), ldw, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns, encb);
-        else if (encb) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, l), ldw, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns, encb);
+        const int alg_k = mlp_kpad(l);                    // the Linear's own K: split / correction blocks are not algorithmic work
+        if (l == 0) rc = launch_rowgemm(TC_FWD, ench, 64, 64, nullptr, 0, 0, tc_Wh(L, scratch, 0), ldw, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns, encb, alg_k);
+        else if (encb) rc = launch_rowgemm(TC_FWD, ench, 64, 64, Hin, 256, 256, tc_Wh(L, scratch, l), ldw, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns, encb, alg_k);
         else rc = launch_rowgemm(TC_FWD, Hin, 256, 256, nullptr, 0, 0, tc_Wh(L, scratch, l), ldw, bias, nullptr, rows, Hout, Hsave, s0, s0 + 256, L.rgwork(scratch), l & 1, st, ns);
         if (rc) return rc;
         const bool last = l == 7;

@@ -52,12 +52,26 @@ def route_points(points, parents):
     return out
 
 
-def owned_blocks(n_parents, world_size=None, rank_=None):
-    """Parent indices of this rank: contiguous shards of whole blocks (parallel.shard_rows)."""
+def owned_blocks(n_parents, world_size=None, rank_=None, owners=None):
+    """Parent indices of this rank.  owners (one rank per parent, e.g. `spread_owners`) or None: contiguous shards of whole
+    blocks (parallel.shard_rows)."""
     w = parallel.world() if world_size is None else world_size
     r = parallel.rank() if rank_ is None else rank_
+    if owners is not None:
+        return [i for i in range(n_parents) if int(owners[i]) == r]
     a, b = parallel.shard_rows(n_parents, w, r)
     return list(range(a, b))
+
+
+def spread_owners(parents, world_size):
+    """Owner rank of every parent block such that spatially ADJACENT blocks land on different ranks: a LiDAR frame only sees
+    the blocks around the sensor, so with contiguous shards one rank would render the whole frame.  Blocks are binned on
+    the grid of their own typical size, block (ix, iy) goes to rank (ix + 3 iy) mod world (a 3 x 3 neighbourhood spreads over
+    min(world, 8) ranks)."""
+    c = np.stack([(b.parent_min + b.parent_max) / 2 for b in parents], 0)
+    ext = np.median(np.stack([b.parent_max - b.parent_min for b in parents], 0), 0)
+    ij = np.round((c[:, :2] - c[:, :2].min(0)) / np.maximum(ext[:2], 1e-9)).astype(np.int64)
+    return ((ij[:, 0] + 3 * ij[:, 1]) % world_size).tolist()
 
 
 @torch.no_grad()
@@ -97,11 +111,12 @@ def parent_boxes(parents):
 @torch.no_grad()
 def render_scene_frames(parents, origins, points, frame_id, embedding_position, N_samples, N_importance, chunk,
                         depth_inference_method=2, batch_size_set=18432, grow_step=0.05, world_size=None, rank_=None,
-                        boxes_dev=None):
+                        boxes_dev=None, owners=None):
     """BATCHED depth inference of several frames over the parent blocks THIS rank owns (BASELINE.json configs[4]).
 
     origins (F,3): sensor position of every frame; points (M,3): the returns of all F frames in the scene frame;
-    frame_id (M,): the frame of every return (device tensors, float64 / integer).  Every return is routed to the parent block
+    frame_id (M,): the frame of every return (device tensors, float64 / integer); owners: rank of every parent block
+    (`spread_owners`; None = contiguous shards).  Every return is routed to the parent block
     that contains it (K0', one kernel); per owned block the rays of ALL frames of the batch are grouped (K1: candidate child
     boxes per ray) and rendered together (`render_frame`, once per physical ray) -- a block's networks are loaded once per
     batch instead of once per frame, and the MLP kernels see F times more rows per launch.  No communication: a block's rays
@@ -117,7 +132,7 @@ def render_scene_frames(parents, origins, points, frame_id, embedding_position, 
     counts = torch.bincount((which + 1).to(torch.int64), minlength=P + 1).tolist()
     starts = np.concatenate([[0], np.cumsum(counts)])
     out = {}
-    for i in owned_blocks(P, world_size, rank_):
+    for i in owned_blocks(P, world_size, rank_, owners):
         a, b_ = int(starts[i + 1]), int(starts[i + 2])
         if b_ <= a:
             continue

@@ -101,12 +101,20 @@ def main():
             if t > 1e-6 * scale:
                 worst = max(worst, float((grad_dp[s_] - g1[s_]).abs().max()) / t)
             o += p.numel()
-        werr = float((w_dp - opt1.flat).abs().max())
+        # the first Adam step moves every weight by ~lr * sign(g): where the exact gradient is zero (the Linear biases in front
+        # of a train-mode BatchNorm) the sign is rounding noise, so the updated weights are compared where the gradient is
+        # resolved (|g| > 1e-3 of the largest entry) -- everywhere for the fp32 engine's own check below
+        sel = g1.abs() > 1e-3 * scale
+        werr = float((w_dp - opt1.flat)[sel].abs().max())
+        werr_all = float((w_dp - opt1.flat).abs().max())
         tol_g = 2e-4 if precision == "fp32" else 5e-2
         out.update({"grad_max_err_over_global_max": gerr, "grad_worst_tensor_rel_err": worst, "weights_max_abs_diff": werr,
+                    "weights_max_abs_diff_incl_zero_gradient_entries": werr_all, "resolved_entries": int(sel.sum()),
                     "loss_global": float(loss1), "tolerance_grad": tol_g})
         # Adam normalises the step: |dw| <= lr per element, so weights agree to a fraction of lr
-        ok = ok and gerr < tol_g and werr < (5e-5 if precision == "fp32" else 6e-4)
+        ok = ok and gerr < tol_g and werr < (5e-5 if precision == "fp32" else 2e-4)
+        if precision == "fp32":
+            ok = ok and werr_all < 5e-5
         out["ok"] = bool(ok)
         print(json.dumps(out), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
