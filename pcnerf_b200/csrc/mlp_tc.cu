@@ -180,7 +180,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int afmt, int bfmt, int amaj, 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-enum { TC_FWD = 0, TC_DGRAD = 1 };
+enum { TC_FWD = 0, TC_DGRAD = 1, TC_DGRAD2 = 2 };     // DGRAD2: pair form with the BN-backward H term on the tensor core
 
 struct RowGemmArgs {
     int rows;
@@ -226,7 +226,7 @@ __device__ __forceinline__ TilePlan tile_plan(int sched, int ntiles, int pair, i
 
 #define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
 #define TC_NBUF 2               // staging buffers per epilogue warp
-#define TC_PAIRS_DEFAULT 1      // row-GEMM form: bit 0 = forward on CTA pairs, bit 1 = data gradient on CTA pairs
+#define TC_PAIRS_DEFAULT 3      // row-GEMM form: bit 0 = forward on CTA pairs, bit 1 = data gradient on CTA pairs
 #define TC_NBUF2 4              // ... of the CTA-pair form (two 64-column rounds per tile, a pair of buffers each)
 
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
@@ -860,7 +860,8 @@ __device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtenso
 template <int EPI, int NEW>
 __global__ void __launch_bounds__(64 + 32 * NEW, 1)
 k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const RowGemmArgs g) {
+              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+              const __grid_constant__ CUtensorMap tmD, const RowGemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[24];            // full[8] | empty[8] | bfull | tfull[2] | tempty[2]
     __shared__ uint32_t tmem_slot;
@@ -869,8 +870,12 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nstage = g.nstage, KB = g.kb_total;
-    uint8_t* sB = smem;                                   // KB x 16 KB: this CTA's 128 weight rows, resident
-    uint8_t* sA = sB + (size_t)KB * TC_B_BYTES;           // nstage x 16 KB ring: this CTA's 128 rows of A
+    // resident B: this CTA's 128 weight rows, KBW k-blocks of 16 KB; DGRAD2: + its 32 rows of the four 64 x 64 diagonal blocks
+    constexpr bool D2 = EPI == TC_DGRAD2;
+    const int KBW = D2 ? g.kb0 : KB;
+    uint8_t* sB = smem;
+    uint8_t* sDg = sB + (size_t)KBW * TC_B_BYTES;         // DGRAD2: 4 x 4 KB
+    uint8_t* sA = sDg + (D2 ? TC_B_BYTES : 0);            // nstage x 16 KB ring: this CTA's 128 rows of A
     uint8_t* sStage = sA + (size_t)nstage * TC_A_BYTES;   // 8 warps x TC_NBUF2 x TC_STAGE_BYTES
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_bfull = smem_u32(bars + 16);
     const uint32_t bar_tfull = smem_u32(bars + 17), bar_tempty = smem_u32(bars + 19);
@@ -890,6 +895,8 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
     if (EPI == TC_FWD) {
         for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) cvec[i] = g.vec[i];
+    } else if (D2) {
+        for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) cvec[i] = g.vec[i];       // 1 / t | k
     } else {
         for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) {
             const float c0 = g.vec[i], c1 = g.vec[256 + i], c2 = g.vec[512 + i], mean = g.vec[768 + i];
@@ -910,10 +917,14 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer (one per CTA: its own rows of A, its own half of B)
         if (lane == 0) {
-            if (rank == 0) mbar_expect_tx(bar_bfull, 2u * (uint32_t)KB * TC_B_BYTES);
-            for (int kb = 0; kb < KB; ++kb)
+            if (rank == 0) mbar_expect_tx(bar_bfull, 2u * ((uint32_t)KBW * TC_B_BYTES + (D2 ? 4u * 4096u : 0u)));
+            for (int kb = 0; kb < KBW; ++kb)
                 tma_load_2d_2sm_hint(smem_u32(sB + (size_t)kb * TC_B_BYTES), &tmB, bar_bfull & TC_PEER_MASK, kb * 64,
                                      rank * TC_NCTA, TC_L2_EVICT_NORMAL);
+            if (D2)     // diagonal block kb: rows kb*64 + 32*rank .. +31 of Dg [256][64] (this CTA's half of the N = 64 operand)
+                for (int kb = 0; kb < 4; ++kb)
+                    tma_load_2d_2sm_hint(smem_u32(sDg + (size_t)kb * 4096), &tmD, bar_bfull & TC_PEER_MASK, 0,
+                                         kb * 64 + rank * 32, TC_L2_EVICT_NORMAL);
             int s = 0;
             uint32_t ph = 0;
             for (int it = 0; it < tp.count; ++it) {
@@ -932,6 +943,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     } else if (warp == 1 && rank == 0) {
         // ===== MMA issuer: the leader's, for both SMs
         constexpr uint32_t idesc = (EPI == TC_FWD) ? make_idesc(0, 0, 0, 0, 256, 256) : make_idesc(1, 1, 0, 0, 256, 256);
+        constexpr uint32_t idesc_d = make_idesc(0, 0, 0, 0, 256, 64);     // DGRAD2: fp16 H x fp16 diagonal block, N = 64
         mbar_wait_spin(bar_bfull, 0, 32);
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
@@ -943,11 +955,22 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 mbar_wait_spin(bar_full + 8 * s, ph, 34);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a0 = smem_u32(sA + (size_t)s * TC_A_BYTES), b0 = smem_u32(sB + (size_t)kb * TC_B_BYTES);
+                    const uint32_t a0 = smem_u32(sA + (size_t)s * TC_A_BYTES);
+                    if (D2 && kb >= KBW) {
+                        // D[:, 64 j .. 64 j + 63] += H[:, 64 j ..] * diag_j   (j = kb - KBW): the -c2 (.) H term of the BN backward
+                        const int j = kb - KBW;
+                        const uint32_t b0 = smem_u32(sDg + (size_t)j * 4096);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_2sm(dcol, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
-                                     (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_2sm(dcol + (uint32_t)(64 * j), make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024),
+                                         idesc_d, 1u);
+                    } else {
+                        const uint32_t b0 = smem_u32(sB + (size_t)kb * TC_B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_2sm(dcol, make_desc(a0 + k * 32, 16, 1024), make_desc(b0 + k * 32, 16, 1024), idesc,
+                                         (uint32_t)((kb | k) != 0));
+                    }
                     umma_commit_2sm(bar_empty + 8 * s);
                     if (kb == KB - 1) umma_commit_2sm(bar_tfull + 8 * as);
                 }
@@ -1048,6 +1071,22 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                             pk[cc][c][2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
                             pk[cc][c][2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
                         }
+                } else if (D2) {
+                    // out = D / t + k  (a and t are folded into the weight operand, -c2 t (.) H came from the tensor core)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 rt = *reinterpret_cast<const float4*>(&cvec[colb + c * 32 + 4 * j4]);
+                            const float4 kk = *reinterpret_cast<const float4*>(&cvec[256 + colb + c * 32 + 4 * j4]);
+                            const float v0 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 0]), rt.x, kk.x) : 0.f;
+                            const float v1 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 1]), rt.y, kk.y) : 0.f;
+                            const float v2 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 2]), rt.z, kk.z) : 0.f;
+                            const float v3 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 3]), rt.w, kk.w) : 0.f;
+                            const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+                            pk[cc][c][2 * j4] = *reinterpret_cast<const uint32_t*>(&b01);
+                            pk[cc][c][2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
+                        }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
@@ -1085,7 +1124,7 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             for (int cc = 0; cc < ROUNDS; ++cc) {
                 const int colb = half * (64 * ROUNDS) + cc * 64;
                 const uint32_t* bufs = bufs4[cc];
-                if ((EPI == TC_FWD && cc == 0) || (cc > 0 && spairs == 1)) {
+                if ((EPI != TC_DGRAD && cc == 0) || (cc > 0 && spairs == 1)) {
                     if (lane == 0) tma_store_wait_read<0>();  // earlier stores have read the staging buffers written next
                     __syncwarp();
                 }
@@ -1538,8 +1577,10 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __r
                                                          const float* __restrict__ prev_stats, const float* __restrict__ Wp,
                                                          int64_t rows, float* __restrict__ dW, float* __restrict__ db,
                                                          float* __restrict__ dgamma_prev, float* __restrict__ dbeta_prev,
-                                                         float* __restrict__ coef) {
+                                                         float* __restrict__ coef, __nv_bfloat16* __restrict__ B1,
+                                                         __half* __restrict__ Dg, float* __restrict__ rtk) {
     __shared__ double r0[8], r1[8];
+    __shared__ float s_c2t[2];                          // c2, t of this block's column (DGRAD2 operands)
     const int kin = mlp_kin(l), kpad = mlp_kpad(l);
     const int c = blockIdx.x, o = threadIdx.x;
     int real = c, hid = c;
@@ -1559,21 +1600,43 @@ __global__ void __launch_bounds__(256) k_tc_wgrad_finish(int l, const float* __r
     double st0 = warp_sum_d(cs * (double)w), st1 = warp_sum_d((double)w * (double)v);
     if ((o & 31) == 0) { r0[o >> 5] = st0; r1[o >> 5] = st1; }
     __syncthreads();
-    if (o != 0) return;
-    st0 = 0.0;
-    st1 = 0.0;
-    for (int k = 0; k < 8; ++k) { st0 += r0[k]; st1 += r1[k]; }
     const int n = hid;
-    const float mean = prev_stats[n], invstd = prev_stats[256 + n], a = prev_stats[512 + n];
-    const float dbt = (float)st0;
-    const float dg = invstd * (float)(st1 - (double)mean * st0);
-    dgamma_prev[n] += dg;
-    dbeta_prev[n] += dbt;
-    const float B = (float)rows;
-    coef[n] = a;
-    coef[256 + n] = a * dbt / B;
-    coef[512 + n] = a * invstd * dg / B;
-    coef[768 + n] = mean;
+    const float a = prev_stats[512 + n];
+    if (o == 0) {
+        st0 = 0.0;
+        st1 = 0.0;
+        for (int k = 0; k < 8; ++k) { st0 += r0[k]; st1 += r1[k]; }
+        const float mean = prev_stats[n], invstd = prev_stats[256 + n];
+        const float dbt = (float)st0;
+        const float dg = invstd * (float)(st1 - (double)mean * st0);
+        dgamma_prev[n] += dg;
+        dbeta_prev[n] += dbt;
+        const float B = (float)rows;
+        const float c1 = a * dbt / B, c2 = a * invstd * dg / B;
+        coef[n] = a;
+        coef[256 + n] = c1;
+        coef[512 + n] = c2;
+        coef[768 + n] = mean;
+        if (B1) {
+            // operands of the pair-form data-gradient GEMM (see k_tc_dgrad2_prep): per-column power-of-two scale t
+            float t = 1.f;
+            if (c2 != 0.f && isfinite(c2)) {
+                int e = 0;
+                frexpf(fabsf(c2), &e);
+                e = e < -100 ? -100 : (e > 100 ? 100 : e);
+                t = ldexpf(1.f, -e);
+            }
+            s_c2t[0] = c2;
+            s_c2t[1] = t;
+            rtk[n] = 1.f / t;
+            rtk[256 + n] = c2 * mean - c1;
+        }
+    }
+    if (!B1) return;                                      // (uniform)
+    __syncthreads();
+    const float c2 = s_c2t[0], t = s_c2t[1];
+    B1[(size_t)n * 256 + o] = __float2bfloat16_rn(w * a * t);
+    if (o < 64) Dg[n * 64 + o] = (o == (n & 63)) ? __float2half_rn(-c2 * t) : __float2half_rn(0.f);
 }
 
 struct PrepTArgs {
@@ -1656,7 +1719,8 @@ int sm_count() {
 // mode TC_FWD: A fp16, B fp16 -> out fp16 (+bias), out2 bf16 copy;  TC_DGRAD: A bf16, B bf16 -> out bf16 (BN backward
 // fused: vec = c0|c1|c2|mean, E = fp16 H)
 // `work` = >= TC_ROWGEMM_WORK_BYTES of device memory: [0,4) CTA counter (zeroed here), then the per-CTA partials
-#define TC_ROWGEMM_WORK_BYTES (256 + 160 * 2 * 256 * 8)
+#define TC_ROWGEMM_WORK_CORE (256 + 160 * 2 * 256 * 8)
+#define TC_ROWGEMM_WORK_BYTES (TC_ROWGEMM_WORK_CORE + 256 * 256 * 2 + 256 * 64 * 2 + 512 * 4)     // + the DGRAD2 operands
 // a0_rep: every 64-column block of A0 is consumed a0_rep times (k-blocks 0 .. a0_rep*k0/64 - 1 of B multiply A0)
 int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, int lda1, int k1, const void* B, int ldb,
                    const float* vec, const __half* E, int64_t rows, void* out, __nv_bfloat16* out2, double* stat0,
@@ -1677,7 +1741,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     if (rc) return rc;
     RowGemmArgs g;
     g.rows = (int)rows; g.a0_blocks = k0 / 64; g.kb0 = a0_rep * k0 / 64; g.kb_total = g.kb0 + k1 / 64;
-    const bool pairs = tc_pairs_for(mode);
+    const bool pairs = mode == TC_FWD && tc_pairs_for(mode);      // (the data gradient on pairs is launch_dgrad2)
     static int sp_env = -1;
     // forward on pairs: ONE pair of 2 KB staging buffers per epilogue warp (round 1 waits for round 0's bulk stores to have
     // read them) leaves room for 6 A-ring stages instead of 4 -- measured 17.2 vs 18.0-18.9 ms per step: bytes in flight per
@@ -1737,16 +1801,12 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
             PcnScope ps(PCN_K_GEMM_FWD, st, flops);
             if (epi8) {
                 PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_FWD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD, 8>, mA0, mA1, mB, mO, g));
+                PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD, 8>, mA0, mA1, mB, mO, mO, g));
             } else {
                 cfg.blockDim = dim3(64 + 32 * 16);
                 PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_FWD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD, 16>, mA0, mA1, mB, mO, g));
+                PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_FWD, 16>, mA0, mA1, mB, mO, mO, g));
             }
-        } else {
-            PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_DGRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PcnScope ps(PCN_K_GEMM_DGRAD, st, flops);
-            PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_DGRAD, 8>, mA0, mA1, mB, mO, g));
         }
         PCN_LAUNCH_CHECK();
         return 0;
@@ -1786,6 +1846,95 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
     PCN_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PcnScope ps(PCN_K_GEMM_WGRAD, st, 2.0 * (double)rows * 256.0 * (double)N);
     k_tc_wgrad<<<grid, TC_THREADS, smem, st>>>(mA, mB, g);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+// Operands of the DGRAD2 form for one layer and chunk (grid: 256 blocks = hidden column n of layer l-1, 256 threads = output
+// row o of layer l).  DH_{l-1}[r,n] = a_n G[r,n] - c2_n H[r,n] + (c2_n mean_n - c1_n), G = DH_l W_l.  With t_n the power of
+// two that brings |c2_n| t_n into [0.5, 1):
+//   B1[n][o] = bf16(W_l[o][n] a_n t_n)   (K-major in o: the B operand of the N = 256 MMAs)
+//   Dg[n][k] = (k == n mod 64) ? fp16(-c2_n t_n) : 0   (four 64 x 64 diagonal blocks: the B operand of the N = 64 MMAs on H)
+//   rtk = 1 / t_n | c2_n mean_n - c1_n   (epilogue: out = D / t + k)
+// The per-column power-of-two scale keeps the fp16 diagonal exact to 11 bits whatever the gradient magnitude.
+__global__ void __launch_bounds__(256) k_tc_dgrad2_prep(const float* __restrict__ Wp, int kpad, int off,
+                                                        const __nv_bfloat16* __restrict__ WT, const float* __restrict__ coef,
+                                                        __nv_bfloat16* __restrict__ B1, __half* __restrict__ Dg,
+                                                        float* __restrict__ rtk) {
+    const int n = blockIdx.x, o = threadIdx.x;
+    const float a = coef[n], c1 = coef[256 + n], c2 = coef[512 + n], mean = coef[768 + n];
+    float t = 1.f;
+    if (c2 != 0.f && isfinite(c2)) {
+        int e = 0;
+        frexpf(fabsf(c2), &e);
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        t = ldexpf(1.f, -e);
+    }
+    const float w = Wp ? Wp[(size_t)o * kpad + off + n] : __bfloat162float(WT[(size_t)n * 256 + o]);
+    B1[(size_t)n * 256 + o] = __float2bfloat16_rn(w * a * t);
+    if (o < 64) Dg[n * 64 + o] = (o == (n & 63)) ? __float2half_rn(-c2 * t) : __float2half_rn(0.f);
+    if (o == 0) { rtk[n] = 1.f / t; rtk[256 + n] = c2 * mean - c1; }
+}
+
+#define TC_DGRAD2_SCRATCH (256 * 256 * 2 + 256 * 64 * 2 + 512 * 4)     // B1 | Dg | rtk
+// data-gradient GEMM + BN backward on CTA pairs, H_{l-1} term on the tensor core (k_tc_rowgemm2<TC_DGRAD2>)
+// (Wp == NULL and WT == NULL: the operands in `opscratch` were already written, by k_tc_wgrad_finish)
+int launch_dgrad2(const void* DH, const __half* Hprev, const float* Wp, int kpad, int off, const __nv_bfloat16* WT,
+                  const float* coef, int64_t rows, void* out, double* colsum, void* work, char* opscratch, int dir,
+                  cudaStream_t st) {
+    __nv_bfloat16* B1 = (__nv_bfloat16*)opscratch;
+    __half* Dg = (__half*)(opscratch + 256 * 256 * 2);
+    float* rtk = (float*)(opscratch + 256 * 256 * 2 + 256 * 64 * 2);
+    if (Wp || WT)
+        PCN_TIMED(PCN_K_MLP_SMALL, st, 0.0, k_tc_dgrad2_prep<<<256, 256, 0, st>>>(Wp, kpad, off, WT, coef, B1, Dg, rtk));
+    CUtensorMap mA0, mA1, mB, mO, mD;
+    int rc = make_map(&mA0, DH, rows, 256, 256, 128);
+    if (rc) return rc;
+    rc = make_map(&mA1, Hprev, rows, 256, 256, 128);
+    if (rc) return rc;
+    rc = make_map(&mB, B1, 256, 256, 256, TC_NCTA);
+    if (rc) return rc;
+    rc = make_map(&mD, Dg, 256, 64, 64, 32);
+    if (rc) return rc;
+    rc = make_map(&mO, out, rows, 256, 256, 32, 32);
+    if (rc) return rc;
+    RowGemmArgs g = {};
+    g.rows = (int)rows; g.a0_blocks = 4; g.kb0 = 4; g.kb_total = 8;
+    g.stage_pairs = 1;
+    const int nbuf = 2;
+    {
+        const size_t fixed = 1024 + (size_t)5 * TC_B_BYTES + 8 * nbuf * TC_STAGE_BYTES + 4096;
+        int ns = (int)((232448 - fixed) / TC_A_BYTES);
+        g.nstage = ns > 8 ? 8 : ns;
+    }
+    g.out = out; g.out2 = nullptr; g.vec = rtk; g.E = nullptr; g.stat0 = colsum; g.stat1 = nullptr;
+    g.counter = (unsigned int*)work;
+    g.partials = (double*)((char*)work + 256);
+    {
+        const int m = tc_sched_mode();
+        g.sched = m == 0 ? 0 : (dir ? 2 : 1);
+        g.hint = m == 2 ? 1 : 0;
+    }
+    g.nostat = 0;
+    g.debug = 0;
+    const size_t smem = 1024 + (size_t)5 * TC_B_BYTES + (size_t)g.nstage * TC_A_BYTES + 8 * nbuf * TC_STAGE_BYTES;
+    const int ntiles = (int)pcn_cdiv(rows, 128), nunits = (ntiles + 1) / 2;
+    const int ncl = nunits < sm_count() / 2 ? nunits : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ncl);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PCN_CUDA(cudaFuncSetAttribute(k_tc_rowgemm2<TC_DGRAD2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PcnScope ps(PCN_K_GEMM_DGRAD, st, 2.0 * (double)rows * 256.0 * 256.0);
+    PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_rowgemm2<TC_DGRAD2, 8>, mA0, mA1, mB, mO, mD, g));
     PCN_LAUNCH_CHECK();
     return 0;
 }
@@ -2010,6 +2159,8 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
     // k_tc_bn_bwd_coef2), then the data-gradient GEMM whose epilogue applies the BN backward and emits DH_{l-1} directly.
     // tcgen05 kind::f16 needs A and B in the same 16-bit format (bf16 x fp16 is an illegal instruction on sm_100a): the
     // weight-gradient kernel converts the fp16 activation / encoding tiles to bf16 in shared memory.
+    const bool d2 = tc_pairs_for(TC_DGRAD);              // data gradient on CTA pairs (k_tc_rowgemm2<TC_DGRAD2>)
+    char* ops2 = (char*)L.Wf(scratch, 3);                // its operands (B1 | Dg | rtk), rewritten per layer
     for (int l = 7; l >= 0; --l) {
         const __nv_bfloat16* DH = Gb[cur];
         const int kpad = mlp_kpad(l), off = l == 4 ? 64 : 0;
@@ -2026,11 +2177,17 @@ int mlp_tc_backward(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* G, const
                   k_tc_wgrad_finish<<<kpad, 256, 0, st>>>(l, part, L.colsum(scratch, l), l == 0 ? nullptr : L.stats(sv, l - 1),
                                                           L.Wp(scratch, l), rows, G->dW[l], G->db[l],
                                                           l == 0 ? nullptr : G->dgamma[l - 1], l == 0 ? nullptr : G->dbeta[l - 1],
-                                                          coef));
+                                                          coef, d2 ? (__nv_bfloat16*)ops2 : nullptr,
+                                                          d2 ? (__half*)(ops2 + 256 * 256 * 2) : nullptr,
+                                                          d2 ? (float*)(ops2 + 256 * 256 * 2 + 256 * 64 * 2) : nullptr));
         if (int rc2 = chain_after(l, st)) return rc2;
         if (l == 0) break;
-        rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
-                            nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), 1, st);
+        if (d2)      // (its operands were written by k_tc_wgrad_finish above)
+            rc = launch_dgrad2(DH, Hprev, nullptr, kpad, off, nullptr, coef, rows, Gb[cur ^ 1], L.colsum(scratch, l - 1),
+                               L.rgwork(scratch), ops2, 1, st);
+        else
+            rc = launch_rowgemm(TC_DGRAD, DH, 256, 256, nullptr, 0, 0, tc_WT(L, scratch, l), 256, coef, Hprev, rows, Gb[cur ^ 1],
+                                nullptr, L.colsum(scratch, l - 1), nullptr, L.rgwork(scratch), 1, st);
         if (rc) return rc;
         cur ^= 1;
     }
@@ -2156,6 +2313,11 @@ extern "C" int pcnerf_tc_rowgemm(int mode, const void* A0, int k0, const void* A
     cudaStream_t st = (cudaStream_t)stream;
     PCN_CUDA(cudaMemsetAsync(stats, 0, 512 * sizeof(double), st));
     PCN_CUDA(cudaMemsetAsync(work, 0, 4, st));
+    if (mode == 1 && tc_pairs_for(TC_DGRAD)) {
+        PCN_CHECK_ARG(k0 == 256 && k1 == 0, "tc_rowgemm: the data-gradient form on CTA pairs needs K = 256");
+        return launch_dgrad2(A0, (const __half*)E, nullptr, 0, 0, (const __nv_bfloat16*)B, vec, rows, out, stats, work,
+                             (char*)work + TC_ROWGEMM_WORK_CORE, mode, st);
+    }
     return launch_rowgemm(mode, A0, k0, k0, A1, k1, k1, B, k0 + k1, vec, (const __half*)E, rows, out, nullptr, stats,
                           stats + 256, work, mode, st);
 }

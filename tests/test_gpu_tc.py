@@ -57,7 +57,9 @@ def test_rowgemm_dgrad_bf16_fused_bn_backward(rows, row_form):
     out, _, stats = ops.tc_rowgemm(1, A, B, None, vec, E)
     C = A.float() @ B.float().t()
     ref = vec[0] * C - vec[1] - (E.float() - vec[3]) * vec[2]
-    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=2e-2)    # bf16 output rounding
+    # bf16 output rounding; the pair form (k_tc_rowgemm2<DGRAD2>) folds vec[0] into the bf16 weight operand (here from an
+    # already-bf16 B: one more 2^-9 rounding per weight) and takes the (E - mean) c2 term on the tensor core
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), rtol=1e-2, atol=5e-2 if row_form else 2e-2)
     np.testing.assert_allclose(stats[0].cpu().numpy(), out.double().sum(0).cpu().numpy(), rtol=1e-5, atol=2e-3)
 
 
