@@ -272,7 +272,7 @@ __device__ __forceinline__ void stage_put_row(uint32_t buf, const uint32_t* pk, 
 // 32-bit word (l % 16) = columns 2(l%16), 2(l%16)+1 of the even rows (l < 16) or the odd rows (l >= 16): 32 distinct banks
 // per access.  After the xor-16 shuffle lanes l and l^16 both hold the totals of their two columns.
 template <bool HALF, bool SQ>
-__device__ __forceinline__ void stage_col_sums(uint32_t buf, int lane, double* acc0, double* acc1) {
+__device__ __forceinline__ void stage_col_sums(uint32_t buf, int lane, float* acc0, float* acc1) {
     const int w = lane & 15, par = lane >> 4;
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
@@ -286,15 +286,18 @@ __device__ __forceinline__ void stage_col_sums(uint32_t buf, int lane, double* a
         s1 += f.y;
         if (SQ) { q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1); }
     }
+    // Per-lane running sums stay in fp32 (a CTA adds <= 30 tile partials of 32 values each: ~1e-6 relative, far below the
+    // fp16 rounding of the values themselves); the cross-quadrant / cross-CTA reduction is fp64.  fp64 adds here showed up
+    // as stall_math in the epilogue (ncu: DADD 5 % of the stall samples of k_tc_rowgemm2).
     s0 += __shfl_xor_sync(FULL_MASK, s0, 16);
     s1 += __shfl_xor_sync(FULL_MASK, s1, 16);
-    acc0[0] += (double)s0;
-    acc0[1] += (double)s1;
+    acc0[0] += s0;
+    acc0[1] += s1;
     if (SQ) {
         q0 += __shfl_xor_sync(FULL_MASK, q0, 16);
         q1 += __shfl_xor_sync(FULL_MASK, q1, 16);
-        acc1[0] += (double)q0;
-        acc1[1] += (double)q1;
+        acc1[0] += q0;
+        acc1[1] += q1;
     }
 }
 
@@ -421,7 +424,7 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         const int colb = nhalf * TC_NCTA + half * 64;     // first output column of this warp
         const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (TC_NBUF * TC_STAGE_BYTES);
         const uint32_t bufs[2] = {buf0, buf0 + TC_STAGE_BYTES};
-        double acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        float acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
         int as = 0;
         uint32_t aph = 0;
         // DGRAD: this warp's 32 rows x 128 B piece of H_{l-1} for the NEXT tile is in flight (8 rows x 64 B per load
@@ -543,8 +546,8 @@ k_tc_rowgemm(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int cl = half * 64 + c * 32 + 2 * lane + j;   // column within this CTA's 128
-                    sred[(0 * 4 + q) * 128 + cl] = acc0[2 * c + j];
-                    sred[(1 * 4 + q) * 128 + cl] = acc1[2 * c + j];
+                    sred[(0 * 4 + q) * 128 + cl] = (double)acc0[2 * c + j];
+                    sred[(1 * 4 + q) * 128 + cl] = (double)acc1[2 * c + j];
                 }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -986,166 +989,97 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // one pair of staging buffers PER ROUND: round 1 does not wait for the bulk stores of round 0 to have read theirs
         // (with two buffers per warp every tile exposed the pick-up latency of a TMA store once; the pair form was
         // measured 12-19 % slower than the column-split kernel that way)
-        const int spairs = ROUNDS == 1 ? 1 : g.stage_pairs;           // staging-buffer pairs of this warp
-        const uint32_t buf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (2 * spairs * TC_STAGE_BYTES);
-        uint32_t bufs4[ROUNDS][2];
+        // two 2 KB staging buffers per warp, used alternately by its 32-column chunks
+        const uint32_t sbuf0 = smem_u32(sStage) + (uint32_t)(warp - 2) * (2 * TC_STAGE_BYTES), sbuf1 = sbuf0 + TC_STAGE_BYTES;
+        float acc0[4 * ROUNDS], acc1[4 * ROUNDS];
 #pragma unroll
-        for (int cc = 0; cc < ROUNDS; ++cc) {
-            const int pr = cc % spairs;
-            bufs4[cc][0] = buf0 + (2 * pr) * TC_STAGE_BYTES;
-            bufs4[cc][1] = buf0 + (2 * pr + 1) * TC_STAGE_BYTES;
-        }
-        double acc0[4 * ROUNDS], acc1[4 * ROUNDS];
-#pragma unroll
-        for (int i = 0; i < 4 * ROUNDS; ++i) { acc0[i] = 0.0; acc1[i] = 0.0; }
+        for (int i = 0; i < 4 * ROUNDS; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
         int as = 0;
         uint32_t aph = 0;
-        // DGRAD: this warp's 32 rows x 128 columns of H_{l-1} (fp16) for BOTH rounds of the NEXT unit are requested while the
-        // current unit is processed (a whole unit of prefetch distance; with the second round requested during the first,
-        // the load latency was exposed once per unit: data-gradient class 22.6 vs 19.4 ms per step).
-        uint4 e[ROUNDS][2][4];
-        auto load_e = [&](int tile_) {
-            const int r0_ = tile_ * 128 + q * 32, left_ = g.rows - r0_;
-#pragma unroll
-            for (int cc = 0; cc < ROUNDS; ++cc)
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = (lane >> 2) + 8 * i;
-                        e[cc][c][i] = make_uint4(0, 0, 0, 0);
-                        if (row < left_)
-                            e[cc][c][i] = *reinterpret_cast<const uint4*>(g.E + (size_t)(r0_ + row) * 256 + half * (64 * ROUNDS) + cc * 64 +
-                                                                         c * 32 + (lane & 3) * 8);
-                    }
-        };
-        if (EPI == TC_DGRAD && tp.count > 0) load_e(tp.first * 2 + rank);
+        static_assert(EPI == TC_FWD || EPI == TC_DGRAD2, "the pair form has a forward and a DGRAD2 epilogue");
         for (int it = 0; it < tp.count; ++it) {
             const int tile = (tp.first + it * tp.step) * 2 + rank;
-            if (EPI == TC_DGRAD) {
-                // this thread's rows of H_{l-1}: staged through the (idle) output buffers of both rounds, re-read row-wise below
-                if (lane == 0) tma_store_wait_read<0>();      // the previous unit's stores have read the staging buffers
-                __syncwarp();
-#pragma unroll
-                for (int cc = 0; cc < ROUNDS; ++cc)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sts128(stage_addr(bufs4[cc][c], (lane >> 2) + 8 * i, lane & 3), e[cc][c][i]);
-                __syncwarp();
-                if (it + 1 < tp.count) load_e((tp.first + (it + 1) * tp.step) * 2 + rank);
-            }
             mbar_wait_spin(bar_tfull + 8 * as, aph, 35);
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
             const bool valid = row0 + lane < g.rows;
-            // ---- phase A: both 64-column rounds of the accumulator -> packed 16-bit registers, then the TMEM stage goes
-            //      straight back to the MMA warp (with the stage held through round 0's stores and statistics the pair form
-            //      was measured SLOWER than the single-CTA kernel: the leader stalled on tempty)
-            uint32_t pk[ROUNDS][2][16];
+            // ---- phase A: the accumulator (this warp's 32 rows x 64 ROUNDS columns) -> packed 16-bit registers, in 32-column
+            //      chunks with the TMEM load of chunk i + 1 in flight while chunk i is converted (as in k_tc_fused_eval); the
+            //      TMEM stage goes back to the MMA warp as soon as the last load has landed.
+            uint32_t ra[32], rb[32];
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + half * (64 * ROUNDS));
+            // one 32-column chunk: accumulator registers -> 16-bit row -> staging buffer -> bulk store + column statistics.
+            // Buffer `sb` was last used two chunks ago: at most the previous chunk's store group may still be pending.
+            auto chunk = [&](const uint32_t (&rr)[32], const int ch, const uint32_t sb) {
+                const int col0 = half * (64 * ROUNDS) + ch * 32;   // first output column of this chunk
+                uint32_t po[16];
 #pragma unroll
-            for (int cc = 0; cc < ROUNDS; ++cc) {
-                const int colb = half * (64 * ROUNDS) + cc * 64;  // first output column of this round
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + colb);
-                const uint32_t* bufs = bufs4[cc];
-                uint32_t r[2][32];
-                tmem_ld32_issue(tbase, r[0]);
-                tmem_ld32_issue(tbase + 32, r[1]);
-                tmem_ld_wait();
-                if (cc == ROUNDS - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader_cta(bar_tempty + 8 * as);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float v0, v1, v2, v3;
+                    if (EPI == TC_FWD) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&cvec[col0 + 4 * j4]);
+                        v0 = __uint_as_float(rr[4 * j4 + 0]) + b4.x;
+                        v1 = __uint_as_float(rr[4 * j4 + 1]) + b4.y;
+                        v2 = __uint_as_float(rr[4 * j4 + 2]) + b4.z;
+                        v3 = __uint_as_float(rr[4 * j4 + 3]) + b4.w;
+                    } else {
+                        // out = D / t + k  (a and t are folded into the weight operand, -c2 t (.) H came from the tensor core)
+                        const float4 rt = *reinterpret_cast<const float4*>(&cvec[col0 + 4 * j4]);
+                        const float4 kk = *reinterpret_cast<const float4*>(&cvec[256 + col0 + 4 * j4]);
+                        v0 = fmaf(__uint_as_float(rr[4 * j4 + 0]), rt.x, kk.x);
+                        v1 = fmaf(__uint_as_float(rr[4 * j4 + 1]), rt.y, kk.y);
+                        v2 = fmaf(__uint_as_float(rr[4 * j4 + 2]), rt.z, kk.z);
+                        v3 = fmaf(__uint_as_float(rr[4 * j4 + 3]), rt.w, kk.w);
+                    }
+                    if (!valid) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }
+                    if (EPI == TC_FWD) {
+                        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                        po[2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
+                        po[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    } else {
+                        const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
+                        po[2 * j4] = *reinterpret_cast<const uint32_t*>(&b01);
+                        po[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
+                    }
                 }
-                if (EPI == TC_FWD) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(&cvec[colb + c * 32 + 4 * j4]);
-                            const float v0 = valid ? __uint_as_float(r[c][4 * j4 + 0]) + b4.x : 0.f;
-                            const float v1 = valid ? __uint_as_float(r[c][4 * j4 + 1]) + b4.y : 0.f;
-                            const float v2 = valid ? __uint_as_float(r[c][4 * j4 + 2]) + b4.z : 0.f;
-                            const float v3 = valid ? __uint_as_float(r[c][4 * j4 + 3]) + b4.w : 0.f;
-                            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-                            pk[cc][c][2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
-                            pk[cc][c][2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                        }
-                } else if (D2) {
-                    // out = D / t + k  (a and t are folded into the weight operand, -c2 t (.) H came from the tensor core)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 rt = *reinterpret_cast<const float4*>(&cvec[colb + c * 32 + 4 * j4]);
-                            const float4 kk = *reinterpret_cast<const float4*>(&cvec[256 + colb + c * 32 + 4 * j4]);
-                            const float v0 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 0]), rt.x, kk.x) : 0.f;
-                            const float v1 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 1]), rt.y, kk.y) : 0.f;
-                            const float v2 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 2]), rt.z, kk.z) : 0.f;
-                            const float v3 = valid ? fmaf(__uint_as_float(r[c][4 * j4 + 3]), rt.w, kk.w) : 0.f;
-                            const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
-                            pk[cc][c][2 * j4] = *reinterpret_cast<const uint32_t*>(&b01);
-                            pk[cc][c][2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
-                        }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint4 hv = lds128(stage_addr(bufs[c], lane, k));
-                            const __half2* hb = reinterpret_cast<const __half2*>(&hv);
-                            float hf[8];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 h2 = __half22float2(hb[t]);
-                                hf[2 * t] = h2.x;
-                                hf[2 * t + 1] = h2.y;
-                            }
-#pragma unroll
-                            for (int t4 = 0; t4 < 2; ++t4) {
-                                const int j = k * 8 + t4 * 4, col = colb + c * 32 + j;
-                                const float4 a0 = *reinterpret_cast<const float4*>(&cvec[col]);
-                                const float4 a2 = *reinterpret_cast<const float4*>(&cvec[256 + col]);
-                                const float4 ak = *reinterpret_cast<const float4*>(&cvec[512 + col]);
-                                const float v0 = valid ? fmaf(a0.x, __uint_as_float(r[c][j + 0]), fmaf(-a2.x, hf[t4 * 4 + 0], ak.x)) : 0.f;
-                                const float v1 = valid ? fmaf(a0.y, __uint_as_float(r[c][j + 1]), fmaf(-a2.y, hf[t4 * 4 + 1], ak.y)) : 0.f;
-                                const float v2 = valid ? fmaf(a0.z, __uint_as_float(r[c][j + 2]), fmaf(-a2.z, hf[t4 * 4 + 2], ak.z)) : 0.f;
-                                const float v3 = valid ? fmaf(a0.w, __uint_as_float(r[c][j + 3]), fmaf(-a2.w, hf[t4 * 4 + 3], ak.w)) : 0.f;
-                                const __nv_bfloat162 b01 = __floats2bfloat162_rn(v0, v1), b23 = __floats2bfloat162_rn(v2, v3);
-                                pk[cc][c][k * 4 + t4 * 2] = *reinterpret_cast<const uint32_t*>(&b01);
-                                pk[cc][c][k * 4 + t4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
-                            }
-                        }
-                    __syncwarp();                          // every lane has read its row of E: the buffers can be rewritten
-                }
-            }
-            // ---- phase B: the two rounds leave through the staging buffers (TMA stores) and feed the column statistics
-#pragma unroll
-            for (int cc = 0; cc < ROUNDS; ++cc) {
-                const int colb = half * (64 * ROUNDS) + cc * 64;
-                const uint32_t* bufs = bufs4[cc];
-                if ((EPI != TC_DGRAD && cc == 0) || (cc > 0 && spairs == 1)) {
-                    if (lane == 0) tma_store_wait_read<0>();  // earlier stores have read the staging buffers written next
-                    __syncwarp();
-                }
-                stage_put_row(bufs[0], pk[cc][0], lane);
-                stage_put_row(bufs[1], pk[cc][1], lane);
+                if (lane == 0) tma_store_wait_read<1>();      // the group that last read `sb` (two chunks ago) is done
+                __syncwarp();
+                stage_put_row(sb, po, lane);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && !(g.debug & 2)) {
-                    tma_store_2d_nocommit(&tmO, bufs[0], colb, row0);
-                    tma_store_2d_nocommit(&tmO, bufs[1], colb + 32, row0);
+                    tma_store_2d_nocommit(&tmO, sb, col0, row0);
                     tma_store_commit();
                 }
                 if (!(g.debug & 1) && !g.nostat) {
-                    if (EPI == TC_FWD) {
-                        stage_col_sums<true, true>(bufs[0], lane, acc0 + 4 * cc, acc1 + 4 * cc);
-                        stage_col_sums<true, true>(bufs[1], lane, acc0 + 4 * cc + 2, acc1 + 4 * cc + 2);
-                    } else {
-                        stage_col_sums<false, false>(bufs[0], lane, acc0 + 4 * cc, acc1 + 4 * cc);
-                        stage_col_sums<false, false>(bufs[1], lane, acc0 + 4 * cc + 2, acc1 + 4 * cc + 2);
-                    }
+                    if (EPI == TC_FWD) stage_col_sums<true, true>(sb, lane, acc0 + 2 * ch, acc1 + 2 * ch);
+                    else stage_col_sums<false, false>(sb, lane, acc0 + 2 * ch, acc1 + 2 * ch);
                 }
+            };
+            auto release_tmem = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader_cta(bar_tempty + 8 * as);
+            };
+            // the TMEM load of chunk i + 1 is in flight while chunk i is processed (as in k_tc_fused_eval); the TMEM stage goes
+            // back to the MMA warp as soon as the last load has landed
+            tmem_ld32_issue(tbase, ra);
+            tmem_ld_wait();
+            tmem_ld32_issue(tbase + 32, rb);
+            chunk(ra, 0, sbuf0);
+            tmem_ld_wait();
+            if (ROUNDS == 2) {
+                tmem_ld32_issue(tbase + 64, ra);
+                chunk(rb, 1, sbuf1);
+                tmem_ld_wait();
+                tmem_ld32_issue(tbase + 96, rb);
+                chunk(ra, 2, sbuf0);
+                tmem_ld_wait();
+                release_tmem();
+                chunk(rb, 3, sbuf1);
+            } else {
+                release_tmem();
+                chunk(rb, 1, sbuf1);
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
@@ -1163,8 +1097,8 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const int cl = half * (64 * ROUNDS) + cc * 64 + c * 32 + 2 * lane + j;
-                        sred[(0 * 4 + q) * 256 + cl] = acc0[4 * cc + 2 * c + j];
-                        sred[(1 * 4 + q) * 256 + cl] = acc1[4 * cc + 2 * c + j];
+                        sred[(0 * 4 + q) * 256 + cl] = (double)acc0[4 * cc + 2 * c + j];
+                        sred[(1 * 4 + q) * 256 + cl] = (double)acc1[4 * cc + 2 * c + j];
                     }
         }
         epi_sync();
@@ -1742,16 +1676,12 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
     RowGemmArgs g;
     g.rows = (int)rows; g.a0_blocks = k0 / 64; g.kb0 = a0_rep * k0 / 64; g.kb_total = g.kb0 + k1 / 64;
     const bool pairs = mode == TC_FWD && tc_pairs_for(mode);      // (the data gradient on pairs is launch_dgrad2)
-    static int sp_env = -1;
-    // forward on pairs: ONE pair of 2 KB staging buffers per epilogue warp (round 1 waits for round 0's bulk stores to have
-    // read them) leaves room for 6 A-ring stages instead of 4 -- measured 17.2 vs 18.0-18.9 ms per step: bytes in flight per
-    // SM count for more than the exposed store pick-up latency
-    if (sp_env < 0) { const char* e = getenv("PCNERF_TC_STAGE_PAIRS"); sp_env = e ? (atoi(e) == 2 ? 2 : 1) : 1; }
-    static int epi8 = -1;     // forward on pairs: 8 epilogue warps (two 64-column rounds each) or 16 (PCNERF_TC_EPI8=0)
+    static int epi8 = -1;     // forward on pairs: 8 epilogue warps (four 32-column chunks each) or 16 (PCNERF_TC_EPI8=0)
     if (epi8 < 0) { const char* e = getenv("PCNERF_TC_EPI8"); epi8 = e ? (atoi(e) != 0) : 1; }
     const bool wide = pairs && mode == TC_FWD && !epi8;
-    const int spairs = wide ? 1 : (mode == TC_DGRAD ? 2 : sp_env);     // (the data-gradient epilogue stages H_{l-1} of both rounds at once)
-    const int nbuf = pairs ? (wide ? 4 : 2 * spairs) : TC_NBUF;       // 2 KB staging buffers per 8 epilogue warps' worth
+    // 2 KB staging buffers per 8 epilogue warps' worth: the pair form alternates two per warp (its A ring gets the rest:
+    // six stages at K = 320 -- measured 17.2 vs 18.0-18.9 ms per step against four stages with four buffers per warp)
+    const int nbuf = pairs ? (wide ? 4 : 2) : TC_NBUF;
     {
         // everything that is left of the 227 KB after the resident weights and the staging buffers becomes A ring
         const size_t fixed = 1024 + (size_t)g.kb_total * TC_B_BYTES + 8 * nbuf * TC_STAGE_BYTES + 4096 /* static */;
@@ -1768,7 +1698,7 @@ int launch_rowgemm(int mode, const void* A0, int lda0, int k0, const void* A1, i
         g.hint = m == 2 ? 1 : 0;
     }
     g.nostat = nostat;
-    g.stage_pairs = spairs;
+    g.stage_pairs = 1;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("PCNERF_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
