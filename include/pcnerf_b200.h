@@ -243,13 +243,16 @@ int pcnerf_mlp_tc_backward_chunks(const pcnerf_mlp_params* h_params, const pcner
 void pcnerf_tc_set_fused_eval(int on);
 int pcnerf_tc_get_fused_eval(void);
 
-/* Training-mode row GEMMs (forward and data gradient of every Linear, pcnerf_tc_rowgemm and the precision-1 MLP passes).
- * Process-wide switch, a bit mask: bit 0 = forward GEMMs, bit 1 = data-gradient GEMMs on clusters of two CTAs
- * (tcgen05.mma.cta_group::2, M = 256: the pair splits the ROWS of a two-tile unit, every A tile is loaded once, each SM holds
- * half of the weight rows); a clear bit = one CTA per SM, the two CTAs of a twin split the 256 output columns of a row tile
- * (N = 128 MMAs).  Same results up to fp32 summation order in the column statistics.  Default 1 (forward on pairs: measured
- * 17.4 vs 19.0 ms per C2 step; the data-gradient epilogue is faster in the column-split form).  Initial value: environment
- * variable PCNERF_TC_PAIRS. */
+/* Training-mode GEMMs of the precision-1 MLP (forward, data gradient, weight gradient of every Linear; also
+ * pcnerf_tc_rowgemm / pcnerf_tc_wgrad).  Process-wide switch, a bit mask: bit 0 = forward, bit 1 = data gradient, bit 2 =
+ * weight gradient (N = 256) on clusters of two CTAs (tcgen05.mma.cta_group::2, M = 256):
+ *   forward / data gradient: the pair splits the ROWS of a two-tile unit, every A tile is loaded once, each SM keeps half of
+ *     the weight rows resident; the data-gradient form (DGRAD2) also takes the BN-backward term -c2 (.) H_{l-1} on the tensor
+ *     core (a block-diagonal fp16 operand) with `a` folded into the bf16 weight operand per chunk;
+ *   weight gradient: one 256 x 256 accumulator per pair, half the split-K atomics.
+ * A clear bit = the single-CTA kernels of round 1 (column-split row GEMMs with N = 128 MMAs, k_tc_wgrad).  Same results up
+ * to fp32 summation order (and, for the data gradient, the rounding of a W instead of W to bf16).  Default 7; initial value:
+ * environment variable PCNERF_TC_PAIRS. */
 void pcnerf_tc_set_row_pairs(int on);
 int pcnerf_tc_get_row_pairs(void);
 

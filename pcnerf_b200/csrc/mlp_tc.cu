@@ -226,7 +226,7 @@ __device__ __forceinline__ TilePlan tile_plan(int sched, int ntiles, int pair, i
 
 #define TC_STAGE_BYTES 2048     // one epilogue staging buffer: 32 rows x 64 B (32 x 16-bit), SWIZZLE_64B like its TMA box
 #define TC_NBUF 2               // staging buffers per epilogue warp
-#define TC_PAIRS_DEFAULT 3      // row-GEMM form: bit 0 = forward on CTA pairs, bit 1 = data gradient on CTA pairs
+#define TC_PAIRS_DEFAULT 7      // row-GEMM form: bit 0 = forward on CTA pairs, bit 1 = data gradient on CTA pairs
 #define TC_NBUF2 4              // ... of the CTA-pair form (two 64-column rounds per tile, a pair of buffers each)
 
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
@@ -1133,11 +1133,168 @@ k_tc_rowgemm2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_tc_wgrad on CTA PAIRS (cta_group::2), N = 256: out[256,256] += DH^T X over the rows of the chunk (split-K).
+// The pair owns ONE 256 x 256 accumulator between its two SMs (M = 256: CTA `rank` holds the DH columns / output rows
+// 128 rank .. +127 in its TMEM) and walks the 64-row k-blocks of its share of the rows together: per k-block each CTA loads
+// only ITS 128 columns of DH and ITS 128 columns of X (32 KB instead of 64 KB: six ring stages), the leader issues one
+// M = 256, N = 256 MMA per 16 rows for both SMs.  What this buys: the split-K reduction -- fp32 vector atomics of every
+// CTA's whole accumulator at kernel exit, bound by the L2 atomic units (3 of the class's 16.7 ms per step) -- halves: 74
+// pairs x 256 KB instead of 148 CTAs x 256 KB per launch.  X is fp16 (the forward's H_{l-1}): each CTA's eight otherwise
+// idle epilogue warps rewrite its B half as bf16 in shared memory before the MMA may touch it (as in k_tc_wgrad); the
+// converters of BOTH CTAs report to the leader's barrier.
+// ---------------------------------------------------------------------------------------------------------------
+#define TC_WG2_STAGE (32 * 1024)   // A: 2 boxes of 64 DH columns (16 KB) + B: 2 boxes of 64 X columns (16 KB)
+#define TC_WG2_NST 6
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_wgrad2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NST = TC_WG2_NST;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)NST * TC_WG2_STAGE);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_conv = smem_u32(bars + 16);
+    const uint32_t bar_tfull = smem_u32(bars + 24);
+    uint32_t* tmem_slot = (uint32_t*)(bars + 25);
+    const int rank = (int)cluster_ctarank();
+    const int nkb = (g.rows + 63) >> 6;
+    const int pair = (int)blockIdx.x >> 1;
+    const int kb_beg = pair * g.kb_per_cta;                       // (kb_per_cta = k-blocks per PAIR here)
+    const int kb_end = min(nkb, kb_beg + g.kb_per_cta);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 16);                      // eight converter warps of each CTA
+        }
+        mbar_init(bar_tfull, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 256);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (kb_beg < kb_end) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int s = 0;
+                uint32_t ph = 0;
+                for (int kb = kb_beg; kb < kb_end; ++kb) {
+                    mbar_wait_spin(bar_empty + 8 * s, ph ^ 1, 41);
+                    uint8_t* st = smem + (size_t)s * TC_WG2_STAGE;
+                    // (each CTA's loads complete on ITS OWN full barrier: an mbarrier can only be waited on locally, and the
+                    // converter warps of both CTAs wait for their own tiles)
+                    mbar_expect_tx(bar_full + 8 * s, 4u * 8192u);
+                    for (int j = 0; j < 2; ++j) tma_load_2d(smem_u32(st + j * 8192), &tmA, bar_full + 8 * s, (2 * rank + j) * 64, kb * 64);
+                    for (int j = 0; j < 2; ++j)
+                        tma_load_2d(smem_u32(st + 16384 + j * 8192), &tmB, bar_full + 8 * s, (2 * rank + j) * 64, kb * 64);
+                    if (++s == NST) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (rank == 0) {
+                constexpr uint32_t idesc = make_idesc(1, 1, 1, 1, 256, 256);
+                int s = 0;
+                uint32_t ph = 0;
+                for (int kb = kb_beg; kb < kb_end; ++kb) {
+                    // the tiles of both CTAs have landed and (fp16 X) both B halves are rewritten as bf16: sixteen arrivals
+                    mbar_wait_cluster(bar_conv + 8 * s, ph, 42);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a0 = smem_u32(smem + (size_t)s * TC_WG2_STAGE), b0 = a0 + 16384;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_2sm(tmem_base, make_desc(a0 + k * 2048, 8192, 1024), make_desc(b0 + k * 2048, 8192, 1024), idesc,
+                                         (uint32_t)((kb != kb_beg) | (k != 0)));
+                        umma_commit_2sm(bar_empty + 8 * s);
+                        if (kb == kb_end - 1) umma_commit_2sm(bar_tfull);
+                    }
+                    __syncwarp();
+                    if (++s == NST) { s = 0; ph ^= 1; }
+                }
+            }
+        } else {
+            const int q = warp & 3, half = (warp - 2) >> 2;
+            {
+                // this CTA's B half (64 rows x 128 columns fp16 = 1024 chunks of 16 B) -> bf16 in place (bf16 X: nothing to
+                // rewrite, the warps only report that this CTA's tiles have landed)
+                const int t256 = threadIdx.x - 64;
+                int s = 0;
+                uint32_t ph = 0;
+                for (int kb = kb_beg; kb < kb_end; ++kb) {
+                    mbar_wait(bar_full + 8 * s, ph, 44);
+                    const uint32_t b0 = smem_u32(smem + (size_t)s * TC_WG2_STAGE) + 16384;
+                    for (int i = t256; g.convert_b && i < 1024; i += 256) {
+                        uint4 v = lds128(b0 + (uint32_t)i * 16);
+                        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[t]));
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(f.x, f.y);
+                            w[t] = *reinterpret_cast<const uint32_t*>(&b2);
+                        }
+                        sts128(b0 + (uint32_t)i * 16, v);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    // (CTA-scope release: the rewritten tile is read by THIS SM's tensor core; the arrive only tells the leader
+                    // that it may issue -- fence.proxy.async above has made the writes visible to the async proxy)
+                    if (lane == 0) mbar_arrive_leader_cta(bar_conv + 8 * s);
+                    if (++s == NST) { s = 0; ph ^= 1; }
+                }
+            }
+            mbar_wait_spin(bar_tfull, 0, 43);
+            tc_fence_after();
+            // split-K reduction of this CTA's 128 output rows x 256 columns (see k_tc_wgrad: pair-coalesced vector atomics,
+            // every CTA starts at a rotated block)
+            const int nblk = (g.debug & 4) ? 0 : 4;
+            const bool odd = lane & 1;
+            for (int t0 = 0; t0 < nblk; ++t0) {
+                const int c = half + 2 * ((t0 + (int)blockIdx.x) % 4);      // 32-column block 0..7
+                const int m_even = rank * 128 + q * 32 + (lane & ~1), m_odd = m_even + 1;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                float* base = g.out + g.col_off + c * 32;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float keep[4], recv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float lo = __uint_as_float(r[8 * t + i]), hi = __uint_as_float(r[8 * t + 4 + i]);
+                        keep[i] = odd ? hi : lo;
+                        recv[i] = __shfl_xor_sync(FULL_MASK, odd ? lo : hi, 1);
+                    }
+                    float* d0 = base + (size_t)m_even * g.ldo + (2 * t + (odd ? 1 : 0)) * 4;
+                    float* d1 = base + (size_t)m_odd * g.ldo + (2 * t + (odd ? 1 : 0)) * 4;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d0), "f"(odd ? recv[0] : keep[0]),
+                                 "f"(odd ? recv[1] : keep[1]), "f"(odd ? recv[2] : keep[2]), "f"(odd ? recv[3] : keep[3])
+                                 : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d1), "f"(odd ? keep[0] : recv[0]),
+                                 "f"(odd ? keep[1] : recv[1]), "f"(odd ? keep[2] : recv[2]), "f"(odd ? keep[3] : recv[3])
+                                 : "memory");
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 256);
+}
+
 #define FZ_STAGES 6
 #define FZ_BLK (128 * 128)       // 16 KB: 128 rows x 64 fp16 (one k-block of A, or one weight stage)
 
 struct FusedMaps { CUtensorMap w[8]; };
 struct FusedArgs {
+    int cluster_arrive;         // 1: epilogue -> leader hand-off with mbarrier.arrive.release.cluster (round-1 form)
     int rows;
     float* out_p;               // [rows] sigmoid(logit)
 };
@@ -1342,7 +1499,10 @@ k_tc_fused_eval(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (NCTA == 2) mbar_arrive_leader(bar_epi + 8 * j);
+                // (CTA-scope release, like the hand-offs of k_tc_rowgemm2 / k_tc_wgrad2: the activations written above are read
+                // by THIS SM's tensor core, fence.proxy.async has published them; PCNERF_TC_EVAL_CLUSTER_ARRIVE=1 restores
+                // the cluster-scope release of round 1 for A/B runs)
+                if (NCTA == 2) { if (g.cluster_arrive) mbar_arrive_leader(bar_epi + 8 * j); else mbar_arrive_leader_cta(bar_epi + 8 * j); }
                 else mbar_arrive(bar_epi + 8 * j);
             }
             if (LAST) {
@@ -1632,10 +1792,10 @@ int tc_sched_mode() {
 }
 
 // row GEMMs on CTA pairs (k_tc_rowgemm2): pcnerf_tc_set_row_pairs(1) or PCNERF_TC_PAIRS=1; default off (see the kernel)
-// bit 0: forward GEMMs, bit 1: data-gradient GEMMs
+// bit 0: forward GEMMs, bit 1: data-gradient GEMMs, bit 2: weight-gradient GEMMs (N = 256)
 int g_row_pairs = -1;
 int tc_pairs_mode() {
-    if (g_row_pairs < 0) { const char* e = getenv("PCNERF_TC_PAIRS"); g_row_pairs = e ? (atoi(e) & 3) : TC_PAIRS_DEFAULT; }
+    if (g_row_pairs < 0) { const char* e = getenv("PCNERF_TC_PAIRS"); g_row_pairs = e ? (atoi(e) & 7) : TC_PAIRS_DEFAULT; }
     return g_row_pairs;
 }
 bool tc_pairs_for(int mode) { return (tc_pairs_mode() >> (mode == TC_FWD ? 0 : 1)) & 1; }
@@ -1770,6 +1930,30 @@ int launch_wgrad(const void* DH, const void* X, int ldx, int N, int x_is_bf16, i
         g.debug = dbg;
     }
     const int nkb = (int)pcn_cdiv(rows, 64);
+    if (N == 256 && ((tc_pairs_mode() >> 2) & 1)) {
+        // CTA pairs (k_tc_wgrad2): one 256 x 256 accumulator per pair, half the split-K atomics
+        const int npairs = sm_count() / 2;
+        g.kb_per_cta = (int)pcn_cdiv(nkb, npairs);                    // k-blocks per PAIR
+        const int ncl = (int)pcn_cdiv(nkb, g.kb_per_cta);
+        const size_t smem2 = 1024 + (size_t)TC_WG2_NST * TC_WG2_STAGE + 32 * 8;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * ncl);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem2;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        PCN_CUDA(cudaFuncSetAttribute(k_tc_wgrad2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        PcnScope ps(PCN_K_GEMM_WGRAD, st, 2.0 * (double)rows * 256.0 * (double)N);
+        PCN_CUDA(cudaLaunchKernelEx(&cfg, k_tc_wgrad2, mA, mB, g));
+        PCN_LAUNCH_CHECK();
+        return 0;
+    }
     g.kb_per_cta = (int)pcn_cdiv(nkb, sm_count());
     const int grid = (int)pcn_cdiv(nkb, g.kb_per_cta);
     const size_t smem = 1024 + 3 * (size_t)TC_WG_STAGE + 16 * 8 + 64;      // 13 barriers + the TMEM slot
@@ -1874,7 +2058,7 @@ int launch_dgrad2(const void* DH, const __half* Hprev, const float* Wp, int kpad
 static int g_fused_eval = 2;     // 0 = layered, 1 = fused (one CTA per unit), 2 = fused on CTA pairs (cta_group::2)
 extern "C" void pcnerf_tc_set_fused_eval(int on) { g_fused_eval = on < 0 ? 0 : (on > 2 ? 2 : on); }
 extern "C" int pcnerf_tc_get_fused_eval(void) { return g_fused_eval; }
-extern "C" void pcnerf_tc_set_row_pairs(int on) { g_row_pairs = on & 3; }
+extern "C" void pcnerf_tc_set_row_pairs(int on) { g_row_pairs = on & 7; }
 extern "C" int pcnerf_tc_get_row_pairs(void) { return tc_pairs_mode(); }
 
 // ---- two BN batches (chunks) in flight: pcnerf_mlp_tc_{forward,backward}_chunks issue consecutive chunks on two internal
@@ -1973,6 +2157,11 @@ int mlp_tc_forward(const pcnerf_mlp_params* P, const void* enc, int64_t rows, fl
                                              cudaMemcpyDeviceToDevice, st));
         }
         FusedArgs fa;
+        {
+            static int ca = -1;
+            if (ca < 0) { const char* e = getenv("PCNERF_TC_EVAL_CLUSTER_ARRIVE"); ca = e ? (atoi(e) != 0) : 0; }
+            fa.cluster_arrive = ca;
+        }
         fa.rows = (int)rows;
         fa.out_p = out_p;
         const size_t smem = 1024 + (size_t)(8 + FZ_STAGES) * FZ_BLK;

@@ -363,8 +363,8 @@ def tc_fused_eval(on=None):
 
 
 def tc_row_pairs(on=None):
-    """Get / set the training-mode row-GEMM form of the precision-1 MLP (bit mask): bit 0 = forward GEMMs on CTA pairs
-    (cta_group::2, k_tc_rowgemm2), bit 1 = data-gradient GEMMs on CTA pairs; 0 = column-split CTAs (k_tc_rowgemm)."""
+    """Get / set the training-mode GEMM forms of the precision-1 MLP (bit mask): bit 0 = forward, bit 1 = data gradient
+    (k_tc_rowgemm2: cta_group::2), bit 2 = weight gradient (k_tc_wgrad2) on CTA pairs; 0 = the single-CTA kernels."""
     if on is not None:
         lib().pcnerf_tc_set_row_pairs(int(on))
     return int(lib().pcnerf_tc_get_row_pairs())

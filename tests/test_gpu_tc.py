@@ -17,10 +17,10 @@ def _rand(shape, dt, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(dt).to(dev())
 
 
-@pytest.fixture(params=[0, 3], ids=["cta", "pairs"])
+@pytest.fixture(params=[0, 7], ids=["cta", "pairs"])
 def row_form(request):
     """Both forms of the training-mode row GEMMs: column-split CTAs (k_tc_rowgemm) and CTA pairs (cta_group::2,
-    k_tc_rowgemm2) -- bit 0 = forward, bit 1 = data gradient; the shipped default is forward on pairs."""
+    k_tc_rowgemm2 / k_tc_wgrad2) -- bit 0 = forward, bit 1 = data gradient, bit 2 = weight gradient."""
     from pcnerf_b200 import ops
     old = ops.tc_row_pairs()
     ops.tc_row_pairs(request.param)
@@ -65,15 +65,24 @@ def test_rowgemm_dgrad_bf16_fused_bn_backward(rows, row_form):
 
 @pytest.mark.parametrize("rows,ncols,xdt", [(64, 256, torch.bfloat16), (64, 256, torch.float16), (1000, 256, torch.float16),
                                             (30000, 64, torch.float16), (70000, 256, torch.float16)])
-def test_wgrad_mn_major(rows, ncols, xdt):
+@pytest.mark.parametrize("wg_pairs", [0, 4], ids=["cta", "pairs"])
+def test_wgrad_mn_major(rows, ncols, xdt, wg_pairs):
     """DH^T X with both operands MN-major.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands (measured: illegal
     instruction), so an fp16 X is rewritten as bf16 tile by tile in shared memory by the kernel's idle epilogue warps:
-    the reference result for fp16 X is therefore computed from bf16(X)."""
+    the reference result for fp16 X is therefore computed from bf16(X).  wg_pairs = 4: the N = 256 products on CTA pairs
+    (k_tc_wgrad2: one accumulator per pair, half the split-K atomics)."""
     from pcnerf_b200 import ops
     DH = _rand((rows, 256), torch.bfloat16, 8)
     X = _rand((rows, ncols), xdt, 9)
     out = torch.zeros((256, 320), dtype=torch.float32, device=dev())
-    ops.tc_wgrad(DH, X, ncols, out, 64 if ncols == 256 else 0)
+    old = ops.tc_row_pairs()
+    try:
+        ops.tc_row_pairs((old & 3) | wg_pairs)
+        ops.tc_wgrad(DH, X, ncols, out, 64 if ncols == 256 else 0)
+        torch.cuda.synchronize()
+    finally:
+        ops.tc_row_pairs(old)
+    assert ops.lib().pcnerf_tc_last_fault() == 0
     ref = DH.double().t() @ X.to(torch.bfloat16).double()
     off = 64 if ncols == 256 else 0
     got = out[:, off:off + ncols].double()
