@@ -352,6 +352,8 @@ def _mlp_params(tensors, buffers, training, precision, momentum=0.1, eps=1e-5):
     return P
 
 
+DIRECT_PARAM_GRADS = True     # MLP backward accumulates into existing .grad tensors instead of returning fresh gradients
+
 GRAD_SIZES = [256 * 63, 256] + [256 * 256, 256] * 3 + [256 * 319, 256] + [256 * 256, 256] * 3 + [256, 1] + [256, 256] * 8
 
 
@@ -458,11 +460,23 @@ class MLPFunction(torch.autograd.Function):
         dev = enc.device
         gp = gp.contiguous()
         P = _mlp_params(params, buffers, True, precision)
-        flat = torch.zeros(sum(GRAD_SIZES), dtype=torch.float32, device=dev)
-        views, o = [], 0
-        for sz_, p in zip(GRAD_SIZES, params):
-            views.append(flat[o:o + sz_].view_as(p))
-            o += sz_
+        # The library ACCUMULATES (+=) parameter gradients.  When every parameter already owns a dense fp32 .grad (the flat
+        # GradBucket of FlatAdam / parallel, or any earlier backward), it accumulates straight into those tensors and autograd
+        # is handed None -- otherwise 68 tiny `grad += new` kernels per step (one per parameter) follow every backward.
+        # Only for parameters whose .grad aliases a parallel.GradBucket (FlatAdam): that is an explicit opt-in to "gradients
+        # live in the bucket"; torch.autograd.grad() on such parameters is not supported.
+        direct = DIRECT_PARAM_GRADS and all(
+            getattr(p, "_pcnerf_bucketed", False) and isinstance(p.grad, torch.Tensor) and p.grad.dtype == torch.float32 and
+            p.grad.is_contiguous() and p.grad.device == dev and p.grad.shape == p.shape for p in params)
+        if direct:
+            views = [p.grad for p in params]
+        else:
+            flat = torch.zeros(sum(GRAD_SIZES), dtype=torch.float32, device=dev)
+            views, o = [], 0
+            for sz_, p in zip(GRAD_SIZES, params):
+                views.append(flat[o:o + sz_].view_as(p))
+                o += sz_
+        ret = (None,) * len(views) if direct else tuple(views)
         G = MlpGrads()
         for l in range(9):
             G.dW[l] = views[2 * l].data_ptr()
@@ -480,7 +494,7 @@ class MLPFunction(torch.autograd.Function):
             check(lib().pcnerf_mlp_tc_backward_chunks(ctypes.byref(P), ctypes.byref(G), _p(enc), rows, chunk, _p(out), _p(gp),
                                                       sv_arr, sb_arr, sc_arr, min(t.numel() for t in scr), lanes, _stream()))
             ctx.saved_chunks = None
-            return (None, None, None, None, None, None) + tuple(views)
+            return (None, None, None, None, None, None) + ret
         scratch = _scratch(min(chunk, rows), precision, dev)
         esz = 2 if precision == 1 else 4
         for ci_, i in enumerate(range(0, rows, chunk)):
@@ -492,7 +506,7 @@ class MLPFunction(torch.autograd.Function):
                                             scratch.numel(), _stream()))
             P.prepared = 1
         ctx.saved_chunks = None
-        return (None, None, None, None, None, None) + tuple(views)
+        return (None, None, None, None, None, None) + ret
 
 
 # ------------------------------------------------------------------------------------ K3' closed-form ("affine") MLP

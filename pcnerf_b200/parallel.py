@@ -38,6 +38,7 @@ class GradBucket:
         o = 0
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view_as(p)
+            p._pcnerf_bucketed = True          # ops.MLPFunction.backward may accumulate straight into p.grad
             o += p.numel()
 
     def zero(self):
