@@ -40,8 +40,8 @@ SIGNATURES = {
     "pcnerf_aabb_dist_to_ray": (ci, [vp, vp, i64, vp, ci, vp, vp]),
     "pcnerf_aabb_find_box": (ci, [vp, vp, ci, vp, i64, ci, vp, vp]),
     "pcnerf_aabb_pack_train": (ci, [ci, vp, vp, vp, vp, i64, vp, vp, vp, ci, PD, f64, ci, vp, vp, vp]),
-    "pcnerf_aabb_groups_count": (ci, [vp, vp, i64, vp, vp, ci, PD, PD, ci, f64, f64, vp, vp, vp]),
-    "pcnerf_aabb_groups_fill": (ci, [vp, vp, vp, i64, vp, vp, ci, ci, f64, f64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pcnerf_aabb_groups_count": (ci, [vp, vp, i64, vp, vp, ci, PD, PD, ci, f64, f64, PD, vp, vp, vp, vp, vp]),
+    "pcnerf_aabb_groups_fill": (ci, [vp, vp, vp, i64, vp, vp, ci, ci, f64, f64, PD, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pcnerf_sample_encode_coarse": (ci, [vp, ci, i64, ci, ci, ci, ci, vp, ci, vp, ci, ci, f32, vp, vp, vp, vp, vp]),
     "pcnerf_sample_encode_fine": (ci, [vp, ci, i64, vp, vp, ci, vp, ci, ci, vp, vp, vp, vp]),
     "pcnerf_sample_pdf": (ci, [vp, vp, i64, ci, vp, ci, ci, vp, vp]),

@@ -46,13 +46,15 @@ def main():
         m = n if K <= 5729 else n // 8          # the dense synthetic K = 15,333 scene yields > 100 candidate rows per ray
         rows = {}
 
-        def groups():
-            rows["n"] = ops.aabb_build_groups(o, d[:m], r[:m], b, sbl, scene.parent_min, scene.parent_max, 2, 0.05, 0.65)[0].shape[0]
+        def groups(grid=None):
+            rows["n"] = ops.aabb_build_groups(o, d[:m], r[:m], b, sbl, scene.parent_min, scene.parent_max, 2, 0.05, 0.65,
+                                              grid=grid)[0].shape[0]
 
-        t_groups = timed(groups, reps=3)
+        t_groups = timed(groups, reps=3)                       # default: uniform grid over the box centres from K >= 1024
+        t_scan = timed(lambda: groups(False), reps=3)          # the reference's scan of every box
         out[name] = {"K": K, "pack_train_ms": t_pack, "pack_train_ns_per_ray_box": 1e6 * t_pack / (n * K),
-                     "groups_rays": m, "groups_ms": t_groups, "groups_rows": rows["n"],
-                     "groups_ns_per_ray_box": 1e6 * t_groups / (m * K)}
+                     "groups_rays": m, "groups_ms": t_groups, "groups_full_scan_ms": t_scan, "groups_rows": rows["n"],
+                     "groups_full_scan_ns_per_ray_box": 1e6 * t_scan / (m * K)}
     print(json.dumps(out))
 
 

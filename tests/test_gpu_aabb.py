@@ -135,3 +135,33 @@ def test_real_scale_box_count_bit_exact_vs_oracle(K, parent):
     r, rg, o, _ = ops.aabb_build_groups(scene.origin, dirs[:m], dist[:m], scene.child_bounds, sbl, scene.parent_min,
                                         scene.parent_max, 2, 0.05, 0.65)
     assert np.array_equal(_np(r), r_ref) and np.array_equal(_np(rg), rg_ref) and np.array_equal(_np(o), o_ref)
+
+
+@pytest.mark.parametrize("method", [2, 1])
+@pytest.mark.parametrize("K,parent", [(1500, "kitti"), (5729, "maicity")])
+def test_group_builder_grid_equals_full_scan(K, parent, method):
+    """The uniform grid over the box centres (ops.BoxGrid) only restricts WHICH boxes a ray looks at (a superset of those the
+    0.65 m prefilter keeps): rows, order, ranges and the side array must be identical to scanning every box -- also for vertical
+    rays, rays whose origin lies outside the grid, rays that miss everything and NaN directions."""
+    from pcnerf_b200 import ops, synth
+    scene = synth.make_scene(99, K, synth.KITTI_PARENT if parent == "kitti" else synth.MAICITY_PARENT)
+    n = 4000
+    pts = synth.make_points(scene, 8, n)
+    dirs, dist = synth.rays_from_points(scene.origin, pts)
+    rng = np.random.default_rng(3)
+    origins = np.tile(scene.origin, (n, 1))
+    origins[:200] += rng.uniform(-30, 30, size=(200, 3)) * np.array([1, 1, 0.02])          # outside / elsewhere in the box
+    dirs[200:230] = np.array([0.0, 0.0, -1.0])                                               # vertical
+    dirs[230:260] = np.array([0.0, 1e-12, 1.0]) / np.linalg.norm([0.0, 1e-12, 1.0])
+    d = rng.normal(size=(300, 3))
+    dirs[260:560] = d / np.linalg.norm(d, axis=1, keepdims=True)                             # random: many miss everything
+    dirs[560] = np.nan
+    sbl = scene.child_bounds + np.array([-0.025] * 3 + [0.025] * 3)
+    grow = 0.05 if parent == "kitti" else 0.005
+    a = ops.aabb_build_groups(origins, dirs, dist, scene.child_bounds, sbl, scene.parent_min, scene.parent_max, method, grow,
+                              0.65, grid=False)
+    b = ops.aabb_build_groups(origins, dirs, dist, scene.child_bounds, sbl, scene.parent_min, scene.parent_max, method, grow,
+                              0.65)
+    assert a[0].shape[0] > n // 2
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
