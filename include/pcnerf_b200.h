@@ -207,6 +207,23 @@ int pcnerf_affine_apply(const float* enc, int64_t rows, int64_t chunk, const flo
 int pcnerf_affine_grad(const float* enc, const float* p, const float* grad_p, int64_t rows, int64_t chunk,
                        double* out_part, void* stream);
 
+/* K3' closed form on RAYS, training mode (csrc/affine_rays.cu): the whole precision-2 MLP of one pass -- batch moments,
+ * the parameter-sized float64 algebra (forward and hand-derived backward, repo kernels) and the per-row dot + sigmoid -- from
+ * (rays, z) directly: row r = (ray r / S, depth z[r]) and its encoding embed(o + d z) (models.py:27-41, nof/render.py:458)
+ * is re-derived inside the kernels that need it, so no (rows,64) encoding tensor exists.  Replaces, for a training pass,
+ * NOF.forward over every chunk (nof/render.py:47-49 -> models.py:183-203) and its autograd backward.
+ * rays (n_rays, ld) f32 with the origin in columns 0..2 and the direction in 3..5; z (n_rays, S) f32; chunks are
+ * consecutive ranges of `chunk` rows of the (n_rays S) samples, one BatchNorm batch each; running statistics are updated
+ * once per chunk in chunk order.  `work` (pcnerf_affine_work_bytes(nchunk) bytes) carries the forward's intermediate
+ * matrices to the backward call of the same pass.  h_params->training must be 1 (PCNERF_ERR_UNSUPPORTED otherwise).
+ * pcnerf_affine_backward_rays ACCUMULATES (+=) into h_grads like pcnerf_mlp_backward. */
+size_t pcnerf_affine_work_bytes(int64_t nchunk);
+int pcnerf_affine_forward_rays(const pcnerf_mlp_params* h_params, const float* rays, int ld, int64_t n_rays, const float* z,
+                               int S, int64_t chunk, float* out_p, void* work, size_t work_bytes, void* stream);
+int pcnerf_affine_backward_rays(const pcnerf_mlp_params* h_params, const pcnerf_mlp_grads* h_grads, const float* rays,
+                                int ld, int64_t n_rays, const float* z, int S, int64_t chunk, const float* out_p,
+                                const float* grad_p, void* work, size_t work_bytes, void* stream);
+
 /* Building blocks of the precision-1 path (TMA + tcgen05 + TMEM), exported for unit tests and reuse.
  * pcnerf_tc_rowgemm: C[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T, k0, k1 multiples of 64, k0 + k1 <= 320.
  *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 reserved (NULL);

@@ -54,6 +54,10 @@ SIGNATURES = {
     "pcnerf_affine_moments": (ci, [vp, i64, i64, vp, vp]),
     "pcnerf_affine_apply": (ci, [vp, i64, i64, vp, vp, vp, vp]),
     "pcnerf_affine_grad": (ci, [vp, vp, vp, i64, i64, vp, vp]),
+    "pcnerf_affine_work_bytes": (sz, [i64]),
+    "pcnerf_affine_forward_rays": (ci, [ctypes.POINTER(MlpParams), vp, ci, i64, vp, ci, i64, vp, vp, sz, vp]),
+    "pcnerf_affine_backward_rays": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, ci, i64, vp, ci, i64, vp, vp,
+                                        vp, sz, vp]),
     "pcnerf_tc_rowgemm_work_bytes": (sz, []),
     "pcnerf_tc_rowgemm": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     "pcnerf_tc_wgrad": (ci, [vp, vp, ci, ci, ci, i64, vp, ci, ci, vp]),

@@ -24,6 +24,7 @@ SOURCES = {
     "mlp.cu": [],
     "mlp_tc.cu": [],
     "affine.cu": [],
+    "affine_rays.cu": [],
     "metrics.cu": ["-fmad=false"],
     "frame.cu": ["-fmad=false"],
     "optim.cu": [],
@@ -31,7 +32,7 @@ SOURCES = {
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
           "-Xcompiler", "-fPIC"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "mlp_layout.h"), os.path.join(CSRC, "mlp_small.cuh"),
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "mlp_layout.h"), os.path.join(CSRC, "mlp_small.cuh"), os.path.join(CSRC, "encode.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "pcnerf_b200.h")]
 
 

@@ -1,0 +1,697 @@
+// K3' on rays -- the closed-form ("affine", precision 2) occupancy MLP of a TRAINING pass without an encoding tensor and
+// without torch algebra: everything between (rays, z) and p_occ, forward and backward, in this file.
+//
+// affine.cu explains the formulation: as the reference builds it (nof/networks/models.py:152,172: identity activations) the
+// logit of one BatchNorm batch (= one `chunk` of nof/render.py:47-49) is exactly affine in the encoding x of the sample,
+// and the affine map depends on the batch only through the first two moments of x.  Two things change here:
+//   * rows are (ray, depth) pairs: a kernel that needs x re-derives it (encode.cuh: ~25 instructions per sin/cos pair)
+//     instead of reading 256 bytes per row -- the 2.1 GB encoding tensor of a C2 step and its four passes over HBM are gone;
+//   * the parameter-sized algebra runs in float64 in repo kernels, in HOMOGENEOUS coordinates: x_63 := 1 (column 63 of the
+//     encoding is zero padding), so that every layer is one 256 x 64 matrix per chunk,  H_l = A_l x,  and
+//         mean_l = A_l m,  var_l = diag(A_l C A_l^T),  a_l = gamma_l / sqrt(var_l + eps),  s_l = beta_l - a_l mean_l,
+//         Ab_l = diag(a_l) A_l + s_l e_63^T            (BN_l o Linear_l as a map of x)
+//         A_{l+1} = W_{l+1} Ab_l + b_{l+1} e_63^T      (+ [W_x | 0] for the skip layer, models.py:192-194)
+//         alpha = w_out Ab_7 + b_out e_63^T,           logit = alpha . x
+//     with m = E[x] (m_63 = 1) and C = Cov[x] (row / column 63 zero).  The backward is the hand-derived reverse of exactly
+//     these lines (k_aff_layer_bwd); the three GEMM shapes per layer (A_{l+1} = W Ab_l, G_{l} = W^T G_{l+1},
+//     dW = sum_chunks G Ab^T) go through one tiled DFMA kernel with the chunks concatenated along N (or K).
+// Data-sized kernels: k_affine_moments_rays (second moments: the only O(rows x 64 x 64) work, upper triangle only),
+// k_affine_apply_rays, k_affine_grad_rays.  Test infrastructure compares against the torch formulation of the same algebra
+// (NOF._affine_coeffs) and the fp32 engine (tests/test_gpu_affine.py).
+#include "common.cuh"
+#include "encode.cuh"
+
+#define AFR_PARTS 64            // CTAs (partial results) per chunk of the data-sized kernels
+#define AFR_T 256               // rows per shared-memory sub-tile of the moments kernel
+#define AFR_TILES 136           // 4 x 4 tiles of the upper triangle of the 64 x 64 moment matrix (16 * 17 / 2)
+#define AFR_THREADS 288         // 9 warps: two row groups x 136 tile owners (+ 16 threads that only encode)
+#define AFR_FLUSH 2             // sub-tiles (= 256 rows per tile owner) accumulated in fp32 before the fold into fp64
+#define AFR_SPLITS 8            // split-K factor of the weight-gradient GEMM
+
+struct RayRows {
+    const float* rays;          // (n_rays, ld): origin in columns 0..2, direction in 3..5
+    int ld;
+    const float* z;             // (n_rays, S) depths, row r = ray r / S, sample r % S
+    int S;
+};
+
+// rays_o + rays_d * z (nof/render.py:458: mul then add, no FMA) -- the position K2 encodes
+__device__ __forceinline__ void ray_row_pos(const RayRows& s, int64_t r, float& x0, float& x1, float& x2) {
+    const uint32_t ray = (uint32_t)r / (uint32_t)s.S;
+    const float* q = s.rays + (int64_t)ray * s.ld;
+    const float zz = __ldg(s.z + r);
+    x0 = __fadd_rn(__ldg(q), __fmul_rn(__ldg(q + 3), zz));
+    x1 = __fadd_rn(__ldg(q + 1), __fmul_rn(__ldg(q + 4), zz));
+    x2 = __fadd_rn(__ldg(q + 2), __fmul_rn(__ldg(q + 5), zz));
+}
+
+__device__ __forceinline__ void part_range(int64_t rows, int64_t chunk, int ci, int pi, int64_t& c_beg, int64_t& r_beg,
+                                           int64_t& r_end) {
+    c_beg = (int64_t)ci * chunk;
+    const int64_t c_end = min(rows, c_beg + chunk), per = (c_end - c_beg + AFR_PARTS - 1) / AFR_PARTS;
+    r_beg = min(c_end, c_beg + pi * per);
+    r_end = min(c_end, r_beg + per);
+}
+
+// 16-byte chunk c of row `row` of the [AFR_T][64] tile lives at chunk c ^ (row & 15): a column written by 32 consecutive
+// rows spreads over 16 bank groups (2-way conflicts instead of 32-way), a row is read conflict-free in any chunk order
+__device__ __forceinline__ int afr_swz(int row, int col) { return row * 64 + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// data-sized kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+// part[(ci, pi)][64][64] (only the 4 x 4 tiles with tile row <= tile column are written):
+//   sum over the part's rows of y y^T,  y = (x_0 - s_0, ..., x_62 - s_62, 1),  s = encoding of the chunk's first row.
+// Column 63 of the result holds the first moments, element (63, 63) the row count.
+__global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows, int64_t chunk,
+                                                                        double* __restrict__ part,
+                                                                        double* __restrict__ shift_out) {
+    extern __shared__ __align__(16) float xs[];
+    __shared__ float shift[64];
+    const int ci = blockIdx.y, pi = blockIdx.x, tid = threadIdx.x;
+    int64_t c_beg, r_beg, r_end;
+    part_range(rows, chunk, ci, pi, c_beg, r_beg, r_end);
+    const bool worker = tid < 2 * AFR_TILES;
+    const int grp = tid >= AFR_TILES ? 1 : 0, id = tid - grp * AFR_TILES;
+    int ti = 0, tj = 0;
+    if (worker) {                                   // id -> (ti, tj), ti <= tj, rows of the upper triangle one after the other
+        int rem = id;
+        while (rem >= 16 - ti) { rem -= 16 - ti; ++ti; }
+        tj = ti + rem;
+    }
+    if (tid < 3) {
+        float x0, x1, x2;
+        ray_row_pos(src, c_beg, x0, x1, x2);
+        auto put = [&](int col, float v) { shift[col] = v; };
+        if (tid == 0) {
+            shift[0] = x0; shift[1] = x1; shift[2] = x2; shift[63] = 0.f;
+            enc_visit_coord<0>(x0, put);
+        } else if (tid == 1) {
+            enc_visit_coord<1>(x1, put);
+        } else {
+            enc_visit_coord<2>(x2, put);
+        }
+    }
+    __syncthreads();
+    if (pi == 0 && tid < 64) shift_out[ci * 64 + tid] = (double)shift[tid];
+
+    double acc[4][4];
+    float f[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.0; f[i][j] = 0.f; }
+    int oa[8], ob[8];                               // float offsets of chunks ti / tj in rows grp + 2 u (u = 0..7) of any 16
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        oa[u] = grp * 64 + ((ti ^ (grp + 2 * u)) << 2);
+        ob[u] = grp * 64 + ((tj ^ (grp + 2 * u)) << 2);
+    }
+    int since = 0;
+    for (int64_t r0 = r_beg; r0 < r_end; r0 += AFR_T) {
+        if (tid < AFR_T) {
+            const int64_t r = r0 + tid;
+            if (r < r_end) {
+                float x0, x1, x2;
+                ray_row_pos(src, r, x0, x1, x2);
+                enc_visit(x0, x1, x2, [&](int col, float v) { xs[afr_swz(tid, col)] = v - shift[col]; });
+                xs[afr_swz(tid, 63)] = 1.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) *reinterpret_cast<float4*>(&xs[tid * 64 + c * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        if (worker) {
+            // this group's rows are grp, grp + 2, ...: within 16 rows the swizzle key (row & 15) takes 8 values known at
+            // compile time, so the 16 chunk offsets are loop invariants (oa / ob) and the row offset an immediate
+            for (int rb = 0; rb < AFR_T; rb += 16) {
+                const float* base = xs + rb * 64;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 a = *reinterpret_cast<const float4*>(base + (2 * u) * 64 + oa[u]);
+                    const float4 b = *reinterpret_cast<const float4*>(base + (2 * u) * 64 + ob[u]);
+                    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) f[i][j] = fmaf(av[i], bv[j], f[i][j]);
+                }
+            }
+        }
+        __syncthreads();
+        if (++since == AFR_FLUSH) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acc[i][j] += (double)f[i][j]; f[i][j] = 0.f; }
+            since = 0;
+        }
+    }
+    // the two row groups meet in shared memory (the tile is free now); group 0 writes the part
+    double* red = reinterpret_cast<double*>(xs);
+    if (worker && grp == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[id * 16 + i * 4 + j] = acc[i][j] + (double)f[i][j];
+    }
+    __syncthreads();
+    if (worker && grp == 0) {
+        double* out = part + ((size_t)ci * AFR_PARTS + pi) * 4096;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                out[(ti * 4 + i) * 64 + tj * 4 + j] = acc[i][j] + (double)f[i][j] + red[id * 16 + i * 4 + j];
+    }
+}
+
+// S[ci][e] = sum over the chunk's parts (upper-triangle tiles only; fixed order: deterministic)
+__global__ void __launch_bounds__(256) k_affine_moments_reduce(const double* __restrict__ part, double* __restrict__ S) {
+    const int ci = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x, i = e >> 6, j = e & 63;
+    if ((i >> 2) > (j >> 2)) return;
+    const double* base = part + (size_t)ci * AFR_PARTS * 4096 + e;
+    double s = 0.0;
+#pragma unroll 8
+    for (int p = 0; p < AFR_PARTS; ++p) s += base[(size_t)p * 4096];
+    S[(size_t)ci * 4096 + e] = s;
+}
+
+// per chunk: S -> m (64; m_63 = 1), C (64 x 64 covariance; row / column 63 zero), cnt
+__global__ void __launch_bounds__(256) k_affine_moments_finish(const double* __restrict__ S, const double* __restrict__ shift,
+                                                               double* __restrict__ m, double* __restrict__ C,
+                                                               double* __restrict__ cnt) {
+    __shared__ double s1[64];
+    const int ci = blockIdx.x, tid = threadIdx.x;
+    const double* Sc = S + (size_t)ci * 4096;
+    const double n = Sc[63 * 64 + 63];
+    if (tid < 64) s1[tid] = Sc[tid * 64 + 63] / n;
+    __syncthreads();
+    for (int e = tid; e < 4096; e += 256) {
+        const int i = e >> 6, j = e & 63;
+        double v = 0.0;
+        if (i < 63 && j < 63) v = Sc[(i >> 2) <= (j >> 2) ? e : j * 64 + i] / n - s1[i] * s1[j];
+        C[(size_t)ci * 4096 + e] = v;
+    }
+    if (tid < 64) m[ci * 64 + tid] = tid < 63 ? shift[ci * 64 + tid] + s1[tid] : 1.0;
+    if (tid == 0) cnt[ci] = n;
+}
+
+// p_r = sigmoid(alpha[chunk(r)] . (x_r, 1))
+__global__ void __launch_bounds__(256) k_affine_apply_rays(RayRows src, int64_t rows, int64_t chunk,
+                                                           const float* __restrict__ alpha, float* __restrict__ out_p) {
+    __shared__ float sa[64];
+    const int ci = blockIdx.y, pi = blockIdx.x, tid = threadIdx.x;
+    int64_t c_beg, r_beg, r_end;
+    part_range(rows, chunk, ci, pi, c_beg, r_beg, r_end);
+    if (tid < 64) sa[tid] = alpha[ci * 64 + tid];
+    __syncthreads();
+    for (int64_t r = r_beg + tid; r < r_end; r += 256) {
+        float x0, x1, x2;
+        ray_row_pos(src, r, x0, x1, x2);
+        float t0 = fmaf(x0, sa[0], sa[63]), t1 = x1 * sa[1], t2 = x2 * sa[2];      // one chain per coordinate
+        enc_visit_coord<0>(x0, [&](int col, float v) { t0 = fmaf(v, sa[col], t0); });
+        enc_visit_coord<1>(x1, [&](int col, float v) { t1 = fmaf(v, sa[col], t1); });
+        enc_visit_coord<2>(x2, [&](int col, float v) { t2 = fmaf(v, sa[col], t2); });
+        const float t = t0 + (t1 + t2);
+        out_p[r] = 1.f / (1.f + expf(-t));
+    }
+}
+
+// part[(ci, pi)][64]: sum over the part's rows of g_r (x_r, 1),  g_r = dL/dp_r * p_r (1 - p_r)
+__global__ void __launch_bounds__(256, 2) k_affine_grad_rays(RayRows src, const float* __restrict__ p,
+                                                             const float* __restrict__ grad_p, int64_t rows, int64_t chunk,
+                                                             double* __restrict__ part) {
+    __shared__ double red[8][64];
+    const int ci = blockIdx.y, pi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    int64_t c_beg, r_beg, r_end;
+    part_range(rows, chunk, ci, pi, c_beg, r_beg, r_end);
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int64_t r = r_beg + tid; r < r_end; r += 256) {
+        const float pv = p[r];
+        const float g = grad_p[r] * pv * (1.f - pv);
+        float x0, x1, x2;
+        ray_row_pos(src, r, x0, x1, x2);
+        enc_visit(x0, x1, x2, [&](int col, float v) { acc[col] = fmaf(g, v, acc[col]); });
+        acc[63] += g;
+    }
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const double v = warp_sum_d((double)acc[i]);
+        if (lane == 0) red[wib][i] = v;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][tid];
+        part[((size_t)ci * AFR_PARTS + pi) * 64 + tid] = t;
+    }
+}
+
+__global__ void k_affine_grad_finish(const double* __restrict__ part, double* __restrict__ dalpha) {
+    const int ci = blockIdx.x, j = threadIdx.x;
+    double s = 0.0;
+    for (int p = 0; p < AFR_PARTS; ++p) s += part[((size_t)ci * AFR_PARTS + p) * 64 + j];
+    dalpha[ci * 64 + j] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// parameter-sized algebra (float64).  Per-layer matrices are stored [256][nc][64]: the chunks side by side along the
+// columns, so that W X is ONE 256 x 256 x (nc 64) GEMM and sum_chunks G X^T one 256 x (nc 64) x 256 GEMM.
+// ---------------------------------------------------------------------------------------------------------------
+
+// C[m][n] = sum_{k in split} A(m, k) B(k, n): 32 x 32 tiles, 16-wide k steps, 64 threads with 4 x 4 outputs each (hundreds of
+// small blocks: the fp64 pipe is latency-bound, it wants many resident warps rather than big tiles).
+// A(m, k) = A[m a_sm + k a_sk], B(k, n) = B[k b_sk + n b_sn]; *_KC: the operand is contiguous along k (else along m / n) --
+// only the thread -> element mapping of the tile loads depends on it.  M, N multiples of 32, K of 16.
+template <typename TA, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(64) k_aff_dgemm(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
+                                                  const double* __restrict__ B, int64_t b_sk, int64_t b_sn,
+                                                  double* __restrict__ C, int64_t ldc, int64_t split_stride, int K,
+                                                  int k_per_split) {
+    __shared__ double As[16][34], Bs[16][34];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int k_beg = blockIdx.z * k_per_split, k_end = min(K, k_beg + k_per_split);
+    double c[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = 0.0;
+    double ra[8], rb[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int ka = A_KC ? (tid & 15) : (tid >> 5) + 2 * q, mm = A_KC ? (tid >> 4) + 4 * q : (tid & 31);
+            ra[q] = (double)A[(int64_t)(m0 + mm) * a_sm + (int64_t)(k0 + ka) * a_sk];
+            const int kb = B_KC ? (tid & 15) : (tid >> 5) + 2 * q, nn = B_KC ? (tid >> 4) + 4 * q : (tid & 31);
+            rb[q] = B[(int64_t)(k0 + kb) * b_sk + (int64_t)(n0 + nn) * b_sn];
+        }
+    };
+    fetch(k_beg);
+    for (int k0 = k_beg; k0 < k_end; k0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int ka = A_KC ? (tid & 15) : (tid >> 5) + 2 * q, mm = A_KC ? (tid >> 4) + 4 * q : (tid & 31);
+            As[ka][mm] = ra[q];
+            const int kb = B_KC ? (tid & 15) : (tid >> 5) + 2 * q, nn = B_KC ? (tid >> 4) + 4 * q : (tid & 31);
+            Bs[kb][nn] = rb[q];
+        }
+        __syncthreads();
+        if (k0 + 16 < k_end) fetch(k0 + 16);                 // next k step's loads in flight behind this step's DFMAs
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[i][j] = fma(a[i], b[j], c[i][j]);
+        }
+        __syncthreads();
+    }
+    double* out = C + (size_t)blockIdx.z * split_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[(int64_t)(m0 + ty * 4 + i) * ldc + n0 + tx * 4 + j] = c[i][j];
+}
+
+// dW[i][k] += sum_splits part[s][i][k]   (256 x 256 block of a weight gradient with leading dimension ld)
+__global__ void k_aff_wgrad_reduce(const double* __restrict__ part, int splits, float* __restrict__ dW, int ld) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 65536) return;
+    double s = 0.0;
+    for (int q = 0; q < splits; ++q) s += part[(size_t)q * 65536 + e];
+    dW[(e >> 8) * ld + (e & 255)] += (float)s;
+}
+
+struct AffLayer {
+    double *A, *AC, *Ab;                    // [256][nc][64]
+    double *a, *r, *mean, *var;             // [nc][256]
+    const double *m, *C;                    // [nc][64], [nc][64][64]
+    const float* Wx; int wx_ld;             // l == 0: W_0 (ld 63);  l == 4: W_4[:, :63] (ld 319);  else null
+    int init;                               // 1 (l == 0): A is not read
+    const float *bias, *gamma, *beta;
+    int nc;
+    double eps;
+};
+
+__device__ __forceinline__ double half_warp_sum(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// grid (16, nc): 16 feature rows per block, 16 lanes per row; lane q owns columns q, q + 16, q + 32, q + 48.
+// A <- A (+ [Wx | 0]) + bias e_63^T;  AC = A C;  mean, var, a, r;  Ab = a A + (beta - a mean) e_63^T
+__global__ void __launch_bounds__(256) k_aff_layer_fwd(AffLayer g) {
+    __shared__ double Cs[64][64];
+    __shared__ double As[16][64];
+    __shared__ double ms[64];
+    const int tid = threadIdx.x, lr = tid >> 4, q = tid & 15, c = blockIdx.y, row = blockIdx.x * 16 + lr;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) Cs[0][tid + 256 * e] = g.C[(size_t)c * 4096 + tid + 256 * e];
+    if (tid < 64) ms[tid] = g.m[c * 64 + tid];
+    const size_t idx = ((size_t)row * g.nc + c) * 64 + q;
+    double av[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = q + 16 * e;
+        double v = g.init ? 0.0 : g.A[idx + 16 * e];
+        if (g.Wx && j < 63) v += (double)g.Wx[(size_t)row * g.wx_ld + j];
+        if (j == 63) v += (double)g.bias[row];
+        av[e] = v;
+        As[lr][j] = v;
+    }
+    __syncthreads();
+    double ac[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+        const double ak = As[lr][k];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ac[e] = fma(ak, Cs[k][q + 16 * e], ac[e]);
+    }
+    double pv = 0.0, pm = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { pv = fma(ac[e], av[e], pv); pm = fma(av[e], ms[q + 16 * e], pm); }
+    pv = half_warp_sum(pv);
+    pm = half_warp_sum(pm);
+    const double var = pv > 0.0 ? pv : 0.0;
+    const double rr = 1.0 / sqrt(var + g.eps), aa = (double)g.gamma[row] * rr, s = (double)g.beta[row] - aa * pm;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        g.A[idx + 16 * e] = av[e];
+        g.AC[idx + 16 * e] = ac[e];
+        g.Ab[idx + 16 * e] = aa * av[e] + ((q + 16 * e) == 63 ? s : 0.0);
+    }
+    if (q == 0) {
+        const int o = c * 256 + row;
+        g.a[o] = aa; g.r[o] = rr; g.mean[o] = pm; g.var[o] = var;
+    }
+}
+
+// alpha[c][j] = sum_i w_out[i] Ab_7[i][c][j] (+ b_out at j = 63)
+__global__ void __launch_bounds__(256) k_aff_alpha(const double* __restrict__ Ab, const float* __restrict__ wo,
+                                                   const float* __restrict__ bo, int nc, float* __restrict__ alpha) {
+    __shared__ double red[4][64];
+    const int c = blockIdx.x, j = threadIdx.x & 63, part = threadIdx.x >> 6;
+    double s = 0.0;
+    for (int i = part * 64; i < part * 64 + 64; ++i) s = fma((double)wo[i], Ab[((size_t)i * nc + c) * 64 + j], s);
+    red[part][j] = s;
+    __syncthreads();
+    if (part == 0) {
+        double t = red[0][j] + red[1][j] + red[2][j] + red[3][j];
+        if (j == 63) t += (double)bo[0];
+        alpha[c * 64 + j] = (float)t;
+    }
+}
+
+struct AffRunning {
+    float* rm[PCNERF_NBN];
+    float* rv[PCNERF_NBN];
+    int64_t* nbt[PCNERF_NBN];
+    const double* mean[PCNERF_NBN];
+    const double* var[PCNERF_NBN];
+    const double* cnt;
+    int nc;
+    double mom;
+};
+
+// BatchNorm1d's running statistics: one update per chunk, in chunk order (momentum, unbiased variance)
+__global__ void k_aff_running(AffRunning g) {
+    const int l = blockIdx.x, i = threadIdx.x;
+    double rm = (double)g.rm[l][i], rv = (double)g.rv[l][i];
+    for (int c = 0; c < g.nc; ++c) {
+        const double n = g.cnt[c];
+        rm = (1.0 - g.mom) * rm + g.mom * g.mean[l][c * 256 + i];
+        rv = (1.0 - g.mom) * rv + g.mom * g.var[l][c * 256 + i] * (n / (n - 1.0));
+    }
+    g.rm[l][i] = (float)rm;
+    g.rv[l][i] = (float)rv;
+    if (i == 0) *g.nbt[l] += g.nc;
+}
+
+// grid 256 (feature i), block 64 (column j): G_7 = w_out^T dalpha;  dw_out += Ab_7 dalpha;  db_out += sum_c dalpha[c][63]
+__global__ void __launch_bounds__(64) k_aff_head_bwd(const double* __restrict__ Ab, const double* __restrict__ dalpha,
+                                                     const float* __restrict__ wo, int nc, double* __restrict__ G,
+                                                     float* __restrict__ dwo, float* __restrict__ dbo) {
+    __shared__ double red[2];
+    const int i = blockIdx.x, j = threadIdx.x;
+    const double w = (double)wo[i];
+    double acc = 0.0, sb = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        const double da = dalpha[c * 64 + j];
+        const size_t idx = ((size_t)i * nc + c) * 64 + j;
+        acc = fma(Ab[idx], da, acc);
+        G[idx] = w * da;
+        if (j == 63) sb += da;
+    }
+    acc = warp_sum_d(acc);
+    if ((j & 31) == 0) red[j >> 5] = acc;
+    __syncthreads();
+    if (j == 0) dwo[i] += (float)(red[0] + red[1]);
+    if (i == 0 && j == 63) dbo[0] += (float)sb;
+}
+
+struct AffLayerBwd {
+    double* G;                              // in: dL/dAb_l, out: dL/dA_l   [256][nc][64]
+    const double *A, *AC;
+    const double *a, *r, *mean, *var, *m;
+    const float* gamma;
+    double *gpart, *bpart;                  // [nc][256]: per-chunk contributions to dgamma_l, dbeta_l
+    int nc;
+};
+
+// reverse of k_aff_layer_fwd's last four lines (same thread -> element mapping)
+__global__ void __launch_bounds__(256) k_aff_layer_bwd(AffLayerBwd g) {
+    const int tid = threadIdx.x, lr = tid >> 4, q = tid & 15, c = blockIdx.y, row = blockIdx.x * 16 + lr;
+    const size_t idx = ((size_t)row * g.nc + c) * 64 + q;
+    double gv[4], av[4], dot = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { gv[e] = g.G[idx + 16 * e]; av[e] = g.A[idx + 16 * e]; dot = fma(gv[e], av[e], dot); }
+    dot = half_warp_sum(dot);
+    const double sbar = __shfl_sync(FULL_MASK, gv[3], (threadIdx.x & 16) | 15);      // dL/ds = column 63 of dL/dAb
+    const int o = c * 256 + row;
+    const double aa = g.a[o], rr = g.r[o];
+    const double abar = dot - sbar * g.mean[o];
+    const double mbar = -sbar * aa;
+    const double vbar = g.var[o] > 0.0 ? -0.5 * abar * (double)g.gamma[row] * rr * rr * rr : 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        g.G[idx + 16 * e] = aa * gv[e] + 2.0 * vbar * g.AC[idx + 16 * e] + mbar * g.m[c * 64 + q + 16 * e];
+    if (q == 0) { g.gpart[o] = abar * rr; g.bpart[o] = sbar; }
+}
+
+// grid 256 (i), block 64 (j): the sums over chunks that end in parameter gradients of layer l
+__global__ void __launch_bounds__(64) k_aff_colsum_bwd(const double* __restrict__ G, const double* __restrict__ gpart,
+                                                       const double* __restrict__ bpart, int nc, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                       float* __restrict__ dWx, int wx_ld) {
+    const int i = blockIdx.x, j = threadIdx.x;
+    if (dWx || j == 63) {
+        double s = 0.0;
+        for (int c = 0; c < nc; ++c) s += G[((size_t)i * nc + c) * 64 + j];
+        if (j == 63) dbias[i] += (float)s;
+        else dWx[(size_t)i * wx_ld + j] += (float)s;
+    }
+    if (j < 2) {
+        const double* src = j == 0 ? gpart : bpart;
+        double s = 0.0;
+        for (int c = 0; c < nc; ++c) s += src[c * 256 + i];
+        (j == 0 ? dgamma : dbeta)[i] += (float)s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct Work {                 // offsets in doubles
+    size_t part, shift, m, C, cnt, layer[8], small[8], G0, G1, dalpha, gpart, bpart, wsplit, alpha, total;
+    size_t mat;               // 256 * nc * 64
+};
+
+Work work_layout(int64_t nc) {
+    Work w;
+    size_t o = 0;
+    w.mat = (size_t)256 * nc * 64;
+    auto take = [&](size_t n) { size_t at = o; o += (n + 15) & ~(size_t)15; return at; };
+    w.part = take((size_t)nc * AFR_PARTS * 4096);
+    w.shift = take(nc * 64);
+    w.m = take(nc * 64);
+    w.C = take(nc * 4096);
+    w.cnt = take(nc);
+    for (int l = 0; l < 8; ++l) { w.layer[l] = take(3 * w.mat); w.small[l] = take(4 * nc * 256); }
+    w.G0 = take(w.mat);
+    w.G1 = take(w.mat);
+    w.dalpha = take(nc * 64);
+    w.gpart = take(nc * 256);
+    w.bpart = take(nc * 256);
+    w.wsplit = take((size_t)AFR_SPLITS * 65536);
+    w.alpha = take(nc * 32);              // nc x 64 floats
+    w.total = o;
+    return w;
+}
+
+struct LayerView { double *A, *AC, *Ab, *a, *r, *mean, *var; };
+LayerView layer_view(double* base, const Work& w, int l, int64_t nc) {
+    LayerView v;
+    v.A = base + w.layer[l]; v.AC = v.A + w.mat; v.Ab = v.AC + w.mat;
+    v.a = base + w.small[l]; v.r = v.a + nc * 256; v.mean = v.r + nc * 256; v.var = v.mean + nc * 256;
+    return v;
+}
+
+int check_common(const pcnerf_mlp_params* P, const float* rays, int ld, int64_t n_rays, const float* z, int S, int64_t chunk,
+                 void* work, size_t work_bytes, const char* who) {
+    PCN_CHECK_ARG(P && rays && z && work, "%s: null argument", who);
+    PCN_CHECK_ARG(ld >= 6 && n_rays >= 1 && S >= 1 && chunk >= 2, "%s: bad shape", who);
+    const int64_t rows = n_rays * S;
+    PCN_CHECK_ARG(rows < ((int64_t)1 << 31), "%s: %lld rows (limit 2^31 - 1)", who, (long long)rows);
+    const int64_t nc = pcn_cdiv(rows, chunk);
+    PCN_CHECK_ARG(nc <= 65535, "%s: too many chunks (%lld)", who, (long long)nc);
+    PCN_CHECK_ARG(rows - (nc - 1) * chunk >= 2, "%s: a BatchNorm batch of one row has no variance", who);
+    PCN_CHECK_ARG(work_bytes >= work_layout(nc).total * sizeof(double), "%s: work area too small", who);
+    if (!P->training) {
+        pcn_set_error("%s: training-mode (batch statistics) only; eval-mode BN goes through pcnerf_affine_apply", who);
+        return PCNERF_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+const int kLd[8] = {63, 256, 256, 256, 319, 256, 256, 256};       // leading dimension of W_l
+const int kOff[8] = {0, 0, 0, 0, 63, 0, 0, 0};                    // first column of the block that multiplies H_{l-1}
+
+}  // namespace
+
+extern "C" size_t pcnerf_affine_work_bytes(int64_t nchunk) {
+    return nchunk < 1 ? 0 : work_layout(nchunk).total * sizeof(double);
+}
+
+extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const float* rays, int ld, int64_t n_rays,
+                                          const float* z, int S, int64_t chunk, float* out_p, void* work, size_t work_bytes,
+                                          void* stream) {
+    int rc = check_common(P, rays, ld, n_rays, z, S, chunk, work, work_bytes, "affine_forward_rays");
+    if (rc) return rc;
+    PCN_CHECK_ARG(out_p, "affine_forward_rays: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows = n_rays * S, nc = pcn_cdiv(rows, chunk);
+    const Work w = work_layout(nc);
+    double* base = (double*)work;
+    const RayRows src{rays, ld, z, S};
+    static bool attr_done = false;
+    if (!attr_done) {
+        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, AFR_T * 64 * 4));
+        attr_done = true;
+    }
+    {
+        PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0, 3);
+        k_affine_moments_rays<<<dim3(AFR_PARTS, (unsigned)nc), AFR_THREADS, AFR_T * 64 * 4, st>>>(src, rows, chunk, base + w.part,
+                                                                                                base + w.shift);
+        PCN_LAUNCH_CHECK();
+        k_affine_moments_reduce<<<dim3(16, (unsigned)nc), 256, 0, st>>>(base + w.part, base + w.G0);    // (G0: free until backward)
+        PCN_LAUNCH_CHECK();
+        k_affine_moments_finish<<<(unsigned)nc, 256, 0, st>>>(base + w.G0, base + w.shift, base + w.m, base + w.C,
+                                                              base + w.cnt);
+        PCN_LAUNCH_CHECK();
+    }
+    const int N = (int)nc * 64;
+    AffRunning run;
+    {
+        PcnScope ps(PCN_K_MLP_SMALL, st, 0.0, 17);
+        for (int l = 0; l < 8; ++l) {
+            const LayerView v = layer_view(base, w, l, nc);
+            if (l > 0) {
+                const LayerView pv = layer_view(base, w, l - 1, nc);
+                k_aff_dgemm<float, true, false><<<dim3(N / 32, 8, 1), 64, 0, st>>>(P->W[l] + kOff[l], kLd[l], 1, pv.Ab, N, 1, v.A,
+                                                                                    N, 0, 256, 256);
+                PCN_LAUNCH_CHECK();
+            }
+            AffLayer g;
+            g.A = v.A; g.AC = v.AC; g.Ab = v.Ab; g.a = v.a; g.r = v.r; g.mean = v.mean; g.var = v.var;
+            g.m = base + w.m; g.C = base + w.C;
+            g.Wx = (l == 0 || l == 4) ? P->W[l] : nullptr;
+            g.wx_ld = kLd[l];
+            g.init = l == 0;
+            g.bias = P->b[l]; g.gamma = P->gamma[l]; g.beta = P->beta[l];
+            g.nc = (int)nc; g.eps = (double)P->eps;
+            k_aff_layer_fwd<<<dim3(16, (unsigned)nc), 256, 0, st>>>(g);
+            PCN_LAUNCH_CHECK();
+            run.rm[l] = P->running_mean[l]; run.rv[l] = P->running_var[l]; run.nbt[l] = P->num_batches_tracked[l];
+            run.mean[l] = v.mean; run.var[l] = v.var;
+        }
+        run.cnt = base + w.cnt; run.nc = (int)nc; run.mom = (double)P->momentum;
+        k_aff_running<<<8, 256, 0, st>>>(run);
+        PCN_LAUNCH_CHECK();
+        k_aff_alpha<<<(unsigned)nc, 256, 0, st>>>(layer_view(base, w, 7, nc).Ab, P->W[8], P->b[8], (int)nc,
+                                                  (float*)(base + w.alpha));
+        PCN_LAUNCH_CHECK();
+    }
+    {
+        PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0);
+        k_affine_apply_rays<<<dim3(AFR_PARTS, (unsigned)nc), 256, 0, st>>>(src, rows, chunk, (const float*)(base + w.alpha), out_p);
+        PCN_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int pcnerf_affine_backward_rays(const pcnerf_mlp_params* P, const pcnerf_mlp_grads* Gr, const float* rays, int ld,
+                                           int64_t n_rays, const float* z, int S, int64_t chunk, const float* out_p,
+                                           const float* grad_p, void* work, size_t work_bytes, void* stream) {
+    int rc = check_common(P, rays, ld, n_rays, z, S, chunk, work, work_bytes, "affine_backward_rays");
+    if (rc) return rc;
+    PCN_CHECK_ARG(Gr && out_p && grad_p, "affine_backward_rays: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows = n_rays * S, nc = pcn_cdiv(rows, chunk);
+    const Work w = work_layout(nc);
+    double* base = (double*)work;
+    const RayRows src{rays, ld, z, S};
+    const int N = (int)nc * 64;
+    {
+        PcnScope ps(PCN_K_AFFINE, st, (double)rows * 16.0, 2);
+        k_affine_grad_rays<<<dim3(AFR_PARTS, (unsigned)nc), 256, 0, st>>>(src, out_p, grad_p, rows, chunk, base + w.part);
+        PCN_LAUNCH_CHECK();
+        k_affine_grad_finish<<<(unsigned)nc, 64, 0, st>>>(base + w.part, base + w.dalpha);
+        PCN_LAUNCH_CHECK();
+    }
+    PcnScope ps(PCN_K_MLP_SMALL, st, 0.0, 45);
+    double* G = base + w.G0;
+    double* Gn = base + w.G1;
+    k_aff_head_bwd<<<256, 64, 0, st>>>(layer_view(base, w, 7, nc).Ab, base + w.dalpha, P->W[8], (int)nc, G, Gr->dW[8], Gr->db[8]);
+    PCN_LAUNCH_CHECK();
+    // chunks per split of the weight-gradient GEMM (K = nc * 64)
+    const int cps = (int)pcn_cdiv(nc, AFR_SPLITS), splits = (int)pcn_cdiv(nc, cps);
+    for (int l = 7; l >= 0; --l) {
+        const LayerView v = layer_view(base, w, l, nc);
+        AffLayerBwd g;
+        g.G = G; g.A = v.A; g.AC = v.AC; g.a = v.a; g.r = v.r; g.mean = v.mean; g.var = v.var; g.m = base + w.m;
+        g.gamma = P->gamma[l]; g.gpart = base + w.gpart; g.bpart = base + w.bpart; g.nc = (int)nc;
+        k_aff_layer_bwd<<<dim3(16, (unsigned)nc), 256, 0, st>>>(g);
+        PCN_LAUNCH_CHECK();
+        k_aff_colsum_bwd<<<256, 64, 0, st>>>(G, base + w.gpart, base + w.bpart, (int)nc, Gr->dgamma[l], Gr->dbeta[l], Gr->db[l],
+                                             (l == 0 || l == 4) ? Gr->dW[l] : nullptr, kLd[l]);
+        PCN_LAUNCH_CHECK();
+        if (l == 0) break;
+        const LayerView pv = layer_view(base, w, l - 1, nc);
+        // dW'_l += sum_chunks G Ab_{l-1}^T
+        k_aff_dgemm<double, true, true><<<dim3(8, 8, splits), 64, 0, st>>>(G, N, 1, pv.Ab, 1, N, base + w.wsplit, 256, 65536, N,
+                                                                             cps * 64);
+        PCN_LAUNCH_CHECK();
+        k_aff_wgrad_reduce<<<256, 256, 0, st>>>(base + w.wsplit, splits, Gr->dW[l] + kOff[l], kLd[l]);
+        PCN_LAUNCH_CHECK();
+        // dL/dAb_{l-1} = W'_l^T G
+        k_aff_dgemm<float, false, false><<<dim3(N / 32, 8, 1), 64, 0, st>>>(P->W[l] + kOff[l], 1, kLd[l], G, N, 1, Gn, N, 0, 256,
+                                                                             256);
+        PCN_LAUNCH_CHECK();
+        double* t = G; G = Gn; Gn = t;
+    }
+    return 0;
+}

@@ -6,6 +6,7 @@
 // encode_ray_t), and written as coalesced 512-byte runs -- the (rows,64) layout (256 B fp32 / 128 B fp16 per row) is the
 // MLP's A operand, column 63 is zero padding.
 #include "common.cuh"
+#include "encode.cuh"         // ENC_BIG, enc_phase (shared with the closed-form kernels of affine.cu)
 #include <cuda_fp16.h>
 
 #define SE_MAX_SMEM (200 * 1024)
@@ -29,12 +30,6 @@ __device__ __forceinline__ float lerp_rn(float a, float b, float s) {
 //     (abs error ~5e-7 on a reduced argument, 1000 x below the fp16 rounding of the stored value).
 // Each lane builds its whole 64-column row in registers; rows are transposed through a swizzled shared-memory tile so
 // that the global stores are 512 contiguous bytes per instruction (the 32 rows of a round are contiguous in HBM).
-#define ENC_BIG 8.0e6f          // |x| beyond this (or NaN/Inf): plain sincosf, whose result is what torch computes
-
-__device__ __forceinline__ long long enc_phase(float x) {
-    return __double2ll_rn((double)x * (0.15915494309189535 * 2199023255552.0));        // x / (2 pi) * 2^41
-}
-
 template <bool FAST>
 __device__ __forceinline__ void enc_coord(float x, float* __restrict__ e, int c) {
     // e: this lane's row; writes columns 3 + 6k + c (sin) and 6 + 6k + c (cos), k = 0..9

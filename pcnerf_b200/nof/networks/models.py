@@ -179,6 +179,17 @@ class NOF(nn.Module):
         One BN batch per `chunk` rows.  Returns p_occ (rows,)."""
         self._check_supported()
         prec = self.mlp_precision()
+        if isinstance(enc, ops.LazyEnc):
+            # (ray, depth) rows of a sampling pass (nof/render.py builds them for precision-2 models): the training pass of the
+            # closed-form engine never materialises the encodings; everything else gets the tensor K2 would have written
+            rows = enc.shape[0]
+            chunk = rows if chunk is None else max(int(chunk), 1)
+            if prec == 2 and self.training:
+                last = rows - (-(-rows // chunk) - 1) * chunk
+                if last == 1 or chunk == 1:
+                    raise ValueError("Expected more than 1 value per channel when training, got input size [1, 256]")
+                return ops.AffineRaysFunction.apply(enc.rays, enc.z, chunk, self._buffers3(), *self.kernel_params())
+            enc = enc.materialise()
         want = torch.float16 if prec == 1 else torch.float32
         if enc.dtype != want:
             enc = enc.to(want)

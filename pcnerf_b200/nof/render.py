@@ -23,6 +23,11 @@ def _tc(model):
     return model.mlp_precision() == 1
 
 
+def _lazy(model):
+    """Training pass of a closed-form (precision 2) model: K2 / K2' write depths only, the engine re-derives the encodings."""
+    return model.mlp_precision() == 2 and model.training
+
+
 def _draw_u(n, Ni, device):
     if RNG_ON_CPU:
         return torch.rand(n, Ni).to(device)
@@ -142,14 +147,15 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
 def _two_pass(model, model_fine, rays, n_a, n_b, N_importance, use_disp, perturb, U, u, near_col, far_col, head):
     """Shared skeleton of the four render_* entry points: coarse sample+encode -> head -> resample+encode -> head."""
     tc = _tc(model)
-    z, enc = ops.sample_encode_coarse(rays, n_a, n_b, near_col, far_col, 10, 11, use_disp, float(perturb), U, True, tc)
-    out_c = head(model, enc, z, 0)
+    lazy, lazy_f = _lazy(model), _lazy(model_fine)
+    z, enc = ops.sample_encode_coarse(rays, n_a, n_b, near_col, far_col, 10, 11, use_disp, float(perturb), U, not lazy, tc)
+    out_c = head(model, ops.LazyEnc(rays, z) if lazy else enc, z, 0)
     w = out_c["w"]
     det = (perturb == 0.)
     if not det and u is None:
         u = _draw_u(rays.shape[0], N_importance, rays.device)
-    zf, encf = ops.sample_encode_fine(rays, z, w, N_importance, u, det, True, _tc(model_fine))
-    out_f = head(model_fine, encf, zf, 1)
+    zf, encf = ops.sample_encode_fine(rays, z, w, N_importance, u, det, not lazy_f, _tc(model_fine))
+    out_f = head(model_fine, ops.LazyEnc(rays, zf) if lazy_f else encf, zf, 1)
     return z, zf, out_c, out_f
 
 

@@ -603,6 +603,85 @@ class AffineApplyFunction(torch.autograd.Function):
         return None, g[:, :64].to(torch.float32), g[:, 64].to(torch.float32), None
 
 
+class LazyEnc:
+    """The (rows,64) encoding tensor of a sampling pass, NOT materialised: rows are (ray, depth) pairs and every kernel of the
+    closed-form engine that needs a row's encoding re-derives it from rays[:, 0:6] and z (csrc/affine_rays.cu).  Produced by
+    nof/render.py for precision-2 models in training mode; `materialise()` gives the tensor K2 would have written."""
+
+    def __init__(self, rays, z):
+        self.rays = _cuda_f32(rays, "rays")
+        self.z = _cuda_f32(z, "z")
+        if self.rays.dim() != 2 or self.rays.shape[1] < 6 or self.z.dim() != 2 or self.z.shape[0] != self.rays.shape[0]:
+            raise ValueError("LazyEnc: rays (N, >=6) and z (N, S) expected")
+        self.shape = (self.z.shape[0] * self.z.shape[1], 64)
+        self.dtype = torch.float32
+        self.device = self.z.device
+
+    def materialise(self):
+        pts = self.rays[:, None, 0:3] + self.rays[:, None, 3:6] * self.z[..., None]        # nof/render.py:458
+        return embed(pts.reshape(-1, 3).contiguous(), 64)
+
+
+def _grad_views(params, dev):
+    """(views, returned): where a backward accumulates the 34 parameter gradients -- straight into the existing .grad tensors
+    when every parameter lives in a parallel.GradBucket (autograd is handed None), else into a fresh flat buffer."""
+    direct = DIRECT_PARAM_GRADS and all(
+        getattr(p, "_pcnerf_bucketed", False) and isinstance(p.grad, torch.Tensor) and p.grad.dtype == torch.float32 and
+        p.grad.is_contiguous() and p.grad.device == dev and p.grad.shape == p.shape for p in params)
+    if direct:
+        views = [p.grad for p in params]
+    else:
+        flat = torch.zeros(sum(GRAD_SIZES), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for sz_, p in zip(GRAD_SIZES, params):
+            views.append(flat[o:o + sz_].view_as(p))
+            o += sz_
+    G = MlpGrads()
+    for l in range(9):
+        G.dW[l] = views[2 * l].data_ptr()
+        G.db[l] = views[2 * l + 1].data_ptr()
+    for l in range(8):
+        G.dgamma[l] = views[18 + 2 * l].data_ptr()
+        G.dbeta[l] = views[19 + 2 * l].data_ptr()
+    return G, views, ((None,) * len(views) if direct else tuple(views))
+
+
+class AffineRaysFunction(torch.autograd.Function):
+    """p = NOF(embed(o + d z)) of a TRAINING pass of the closed-form engine, from (rays, z): batch moments, float64 algebra
+    and per-row dot + sigmoid in repo kernels, hand-derived backward (pcnerf_affine_forward_rays / _backward_rays)."""
+
+    @staticmethod
+    def forward(ctx, rays, z, chunk, buffers, *params):
+        dev = z.device
+        n, S = z.shape
+        rows = n * S
+        nc = -(-rows // chunk)
+        P = _mlp_params(params, buffers, True, 2)
+        out = torch.empty(rows, dtype=torch.float32, device=dev)
+        work = torch.empty(lib().pcnerf_affine_work_bytes(nc), dtype=torch.uint8, device=dev)
+        note_param_write()              # the BN running statistics are updated through raw pointers
+        check(lib().pcnerf_affine_forward_rays(ctypes.byref(P), _p(rays), rays.shape[1], n, _p(z), S, int(chunk), _p(out),
+                                               _p(work), work.numel(), _stream()))
+        ctx.meta = (int(chunk), buffers)
+        ctx.work = work
+        ctx.save_for_backward(rays, z, out, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gp):
+        chunk, buffers = ctx.meta
+        rays, z, out, *params = ctx.saved_tensors
+        n, S = z.shape
+        P = _mlp_params(params, buffers, True, 2)
+        G, views, ret = _grad_views(params, z.device)
+        gp = gp.contiguous()
+        work = ctx.work
+        check(lib().pcnerf_affine_backward_rays(ctypes.byref(P), ctypes.byref(G), _p(rays), rays.shape[1], n, _p(z), S, chunk,
+                                                _p(out), _p(gp), _p(work), work.numel(), _stream()))
+        ctx.work = None
+        return (None, None, None, None) + ret
+
+
 # -------------------------------------------------------------------------------------------- K4 composite + losses
 
 
