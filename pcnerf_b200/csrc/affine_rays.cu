@@ -21,11 +21,13 @@
 #include "common.cuh"
 #include "encode.cuh"
 
-#define AFR_PARTS 64            // CTAs (partial results) per chunk of the data-sized kernels
-#define AFR_T 256               // rows per shared-memory sub-tile of the moments kernel
+#define AFR_PARTS 64            // most CTAs (partial results) per chunk of the data-sized kernels (buffer sizing)
+#define AFR_T 96                // rows per shared-memory sub-tile of the moments kernel (two buffers)
+#define AFR_PROD 96             // producer threads of the moments kernel: warps 0..2 encode one row each per sub-tile
 #define AFR_TILES 136           // 4 x 4 tiles of the upper triangle of the 64 x 64 moment matrix (16 * 17 / 2)
-#define AFR_THREADS 288         // 9 warps: two row groups x 136 tile owners (+ 16 threads that only encode)
-#define AFR_FLUSH 2             // sub-tiles (= 256 rows per tile owner) accumulated in fp32 before the fold into fp64
+#define AFR_THREADS 256         // 8 warps: 3 producers + 5 consumers (136 tile owners, 24 idle lanes); 112 registers x 8
+                                // warps = two CTAs per SM (nine warps are allocated as twelve: one CTA)
+#define AFR_FLUSH 2             // sub-tiles (= 256 rows) accumulated in fp32 before the fold into fp64 (power of two)
 #define AFR_SPLITS 8            // split-K factor of the weight-gradient GEMM
 
 struct RayRows {
@@ -48,14 +50,25 @@ __device__ __forceinline__ void ray_row_pos(const RayRows& s, int64_t r, float& 
 __device__ __forceinline__ void part_range(int64_t rows, int64_t chunk, int ci, int pi, int64_t& c_beg, int64_t& r_beg,
                                            int64_t& r_end) {
     c_beg = (int64_t)ci * chunk;
-    const int64_t c_end = min(rows, c_beg + chunk), per = (c_end - c_beg + AFR_PARTS - 1) / AFR_PARTS;
+    const int parts = (int)gridDim.x;
+    const int64_t c_end = min(rows, c_beg + chunk), per = (c_end - c_beg + parts - 1) / parts;
     r_beg = min(c_end, c_beg + pi * per);
     r_end = min(c_end, r_beg + per);
 }
 
-// 16-byte chunk c of row `row` of the [AFR_T][64] tile lives at chunk c ^ (row & 15): a column written by 32 consecutive
-// rows spreads over 16 bank groups (2-way conflicts instead of 32-way), a row is read conflict-free in any chunk order
-__device__ __forceinline__ int afr_swz(int row, int col) { return row * 64 + ((((col >> 2) ^ (row & 15)) << 2) | (col & 3)); }
+// 16-byte chunk c of row `row` of a [AFR_T][64] tile lives at chunk c ^ (row & 7): a column written by 32 consecutive
+// rows spreads over all 8 bank groups (4-way conflicts instead of 32-way), a row is read conflict-free in any chunk order
+__device__ __forceinline__ int afr_swz(int row, int col) { return row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
+
+// named barriers 1 + b / 3 + b (b = buffer; immediates, so that the kernel reserves 5 hardware barriers and not all 16)
+template <int ID>
+__device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(AFR_THREADS) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(AFR_THREADS) : "memory"); }
+template <int ID0>
+__device__ __forceinline__ void bar_sync(int b) { if (b) bar_sync_id<ID0 + 1>(); else bar_sync_id<ID0>(); }
+template <int ID0>
+__device__ __forceinline__ void bar_arrive(int b) { if (b) bar_arrive_id<ID0 + 1>(); else bar_arrive_id<ID0>(); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // data-sized kernels
@@ -64,22 +77,17 @@ __device__ __forceinline__ int afr_swz(int row, int col) { return row * 64 + (((
 // part[(ci, pi)][64][64] (only the 4 x 4 tiles with tile row <= tile column are written):
 //   sum over the part's rows of y y^T,  y = (x_0 - s_0, ..., x_62 - s_62, 1),  s = encoding of the chunk's first row.
 // Column 63 of the result holds the first moments, element (63, 63) the row count.
-__global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows, int64_t chunk,
-                                                                        double* __restrict__ part,
-                                                                        double* __restrict__ shift_out) {
-    extern __shared__ __align__(16) float xs[];
+// Warp-specialised: warps 0..2 (one row per thread) encode sub-tile t + 1 into one shared-memory buffer while warps 3..7 (one
+// 4 x 4 tile of the upper triangle per thread, 136 owners) accumulate the outer products of sub-tile t from the other --
+// the sin/cos polynomials and the FMA / shared-load stream of the products fill each other's issue slots.  Hand-off through
+// named barriers (full / empty per buffer: producers `arrive` on full and `sync` on empty, consumers the reverse).
+__global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows, int64_t chunk, double* __restrict__ part,
+                                                       double* __restrict__ shift_out) {
+    extern __shared__ __align__(16) float xs[];             // 2 x [AFR_T][64]
     __shared__ float shift[64];
     const int ci = blockIdx.y, pi = blockIdx.x, tid = threadIdx.x;
     int64_t c_beg, r_beg, r_end;
     part_range(rows, chunk, ci, pi, c_beg, r_beg, r_end);
-    const bool worker = tid < 2 * AFR_TILES;
-    const int grp = tid >= AFR_TILES ? 1 : 0, id = tid - grp * AFR_TILES;
-    int ti = 0, tj = 0;
-    if (worker) {                                   // id -> (ti, tj), ti <= tj, rows of the upper triangle one after the other
-        int rem = id;
-        while (rem >= 16 - ti) { rem -= 16 - ti; ++ti; }
-        tj = ti + rem;
-    }
     if (tid < 3) {
         float x0, x1, x2;
         ray_row_pos(src, c_beg, x0, x1, x2);
@@ -95,44 +103,62 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
     }
     __syncthreads();
     if (pi == 0 && tid < 64) shift_out[ci * 64 + tid] = (double)shift[tid];
+    const int nt = (int)((r_end - r_beg + AFR_T - 1) / AFR_T);
+    enum { FULL = 1, EMPTY = 3 };                           // named barriers FULL + b, EMPTY + b (0 is __syncthreads)
 
+    if (tid < AFR_PROD) {
+        for (int t = 0; t < nt; ++t) {
+            const int b = t & 1;
+            if (t >= 2) bar_sync<EMPTY>(b);
+            float* buf = xs + b * (AFR_T * 64);
+            const int64_t r = r_beg + (int64_t)t * AFR_T + tid;
+            if (r < r_end) {
+                float x0, x1, x2;
+                ray_row_pos(src, r, x0, x1, x2);
+                enc_visit(x0, x1, x2, [&](int col, float v) { buf[afr_swz(tid, col)] = v - shift[col]; });
+                buf[afr_swz(tid, 63)] = 1.f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) *reinterpret_cast<float4*>(&buf[tid * 64 + c * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __threadfence_block();
+            bar_arrive<FULL>(b);
+        }
+        return;
+    }
+    const int id = tid - AFR_PROD;
+    const bool worker = id < AFR_TILES;
+    int ti = 0, tj = 0;
+    if (worker) {                                   // id -> (ti, tj), ti <= tj, rows of the upper triangle one after the other
+        int rem = id;
+        while (rem >= 16 - ti) { rem -= 16 - ti; ++ti; }
+        tj = ti + rem;
+    }
     double acc[4][4];
     float f[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j] = 0.0; f[i][j] = 0.f; }
-    int oa[8], ob[8];                               // float offsets of chunks ti / tj in rows grp + 2 u (u = 0..7) of any 16
+    int oa[8], ob[8];                               // float offsets of chunks ti / tj in rows u = 0..7 of any 8 rows
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        oa[u] = grp * 64 + ((ti ^ (grp + 2 * u)) << 2);
-        ob[u] = grp * 64 + ((tj ^ (grp + 2 * u)) << 2);
+        oa[u] = u * 64 + ((ti ^ u) << 2);
+        ob[u] = u * 64 + ((tj ^ u) << 2);
     }
-    int since = 0;
-    for (int64_t r0 = r_beg; r0 < r_end; r0 += AFR_T) {
-        if (tid < AFR_T) {
-            const int64_t r = r0 + tid;
-            if (r < r_end) {
-                float x0, x1, x2;
-                ray_row_pos(src, r, x0, x1, x2);
-                enc_visit(x0, x1, x2, [&](int col, float v) { xs[afr_swz(tid, col)] = v - shift[col]; });
-                xs[afr_swz(tid, 63)] = 1.f;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) *reinterpret_cast<float4*>(&xs[tid * 64 + c * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+        const int b = t & 1;
+        bar_sync<FULL>(b);
         if (worker) {
-            // this group's rows are grp, grp + 2, ...: within 16 rows the swizzle key (row & 15) takes 8 values known at
-            // compile time, so the 16 chunk offsets are loop invariants (oa / ob) and the row offset an immediate
-            for (int rb = 0; rb < AFR_T; rb += 16) {
-                const float* base = xs + rb * 64;
+            const float* buf = xs + b * (AFR_T * 64);
+#pragma unroll 2
+            for (int rb = 0; rb < AFR_T; rb += 8) {
+                const float* base = buf + rb * 64;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const float4 a = *reinterpret_cast<const float4*>(base + (2 * u) * 64 + oa[u]);
-                    const float4 b = *reinterpret_cast<const float4*>(base + (2 * u) * 64 + ob[u]);
-                    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                    const float4 a = *reinterpret_cast<const float4*>(base + oa[u]);
+                    const float4 bb = *reinterpret_cast<const float4*>(base + ob[u]);
+                    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -140,42 +166,32 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
                 }
             }
         }
-        __syncthreads();
-        if (++since == AFR_FLUSH) {
+        if (t + 2 < nt) bar_arrive<EMPTY>(b);
+        if ((t & (AFR_FLUSH - 1)) == AFR_FLUSH - 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { acc[i][j] += (double)f[i][j]; f[i][j] = 0.f; }
-            since = 0;
         }
     }
-    // the two row groups meet in shared memory (the tile is free now); group 0 writes the part
-    double* red = reinterpret_cast<double*>(xs);
-    if (worker && grp == 1) {
+    if (worker) {
+        double* out = part + ((size_t)ci * gridDim.x + pi) * 4096;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) red[id * 16 + i * 4 + j] = acc[i][j] + (double)f[i][j];
-    }
-    __syncthreads();
-    if (worker && grp == 0) {
-        double* out = part + ((size_t)ci * AFR_PARTS + pi) * 4096;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                out[(ti * 4 + i) * 64 + tj * 4 + j] = acc[i][j] + (double)f[i][j] + red[id * 16 + i * 4 + j];
+            for (int j = 0; j < 4; ++j) out[(ti * 4 + i) * 64 + tj * 4 + j] = acc[i][j] + (double)f[i][j];
     }
 }
 
 // S[ci][e] = sum over the chunk's parts (upper-triangle tiles only; fixed order: deterministic)
-__global__ void __launch_bounds__(256) k_affine_moments_reduce(const double* __restrict__ part, double* __restrict__ S) {
+__global__ void __launch_bounds__(256) k_affine_moments_reduce(const double* __restrict__ part, int parts,
+                                                               double* __restrict__ S) {
     const int ci = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x, i = e >> 6, j = e & 63;
     if ((i >> 2) > (j >> 2)) return;
-    const double* base = part + (size_t)ci * AFR_PARTS * 4096 + e;
+    const double* base = part + (size_t)ci * parts * 4096 + e;
     double s = 0.0;
-#pragma unroll 8
-    for (int p = 0; p < AFR_PARTS; ++p) s += base[(size_t)p * 4096];
+#pragma unroll 4
+    for (int p = 0; p < parts; ++p) s += base[(size_t)p * 4096];
     S[(size_t)ci * 4096 + e] = s;
 }
 
@@ -249,14 +265,14 @@ __global__ void __launch_bounds__(256, 2) k_affine_grad_rays(RayRows src, const 
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][tid];
-        part[((size_t)ci * AFR_PARTS + pi) * 64 + tid] = t;
+        part[((size_t)ci * gridDim.x + pi) * 64 + tid] = t;
     }
 }
 
-__global__ void k_affine_grad_finish(const double* __restrict__ part, double* __restrict__ dalpha) {
+__global__ void k_affine_grad_finish(const double* __restrict__ part, int parts, double* __restrict__ dalpha) {
     const int ci = blockIdx.x, j = threadIdx.x;
     double s = 0.0;
-    for (int p = 0; p < AFR_PARTS; ++p) s += part[((size_t)ci * AFR_PARTS + p) * 64 + j];
+    for (int p = 0; p < parts; ++p) s += part[((size_t)ci * parts + p) * 64 + j];
     dalpha[ci * 64 + j] = s;
 }
 
@@ -265,62 +281,83 @@ __global__ void k_affine_grad_finish(const double* __restrict__ part, double* __
 // columns, so that W X is ONE 256 x 256 x (nc 64) GEMM and sum_chunks G X^T one 256 x (nc 64) x 256 GEMM.
 // ---------------------------------------------------------------------------------------------------------------
 
-// C[m][n] = sum_{k in split} A(m, k) B(k, n): 32 x 32 tiles, 16-wide k steps, 64 threads with 4 x 4 outputs each (hundreds of
-// small blocks: the fp64 pipe is latency-bound, it wants many resident warps rather than big tiles).
+// D (8 x 8) += A (8 x 4, row) B (4 x 8, col) on the fp64 tensor pipe.  Lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and
+// D[l / 4][2 (l % 4) + {0, 1}].  (The CUDA-core DFMA form of this GEMM ran at 8 TFLOP/s; cuBLAS's DMMA kernels reach 36.)
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// C[m][n] = sum_{k in split} A(m, k) B(k, n), one 32 x 32 tile per block.  The kernel is bound by the latency of its operand
+// loads (L2 -> registers -> shared memory), not by the tensor pipe (ncu: long-scoreboard stalls, 10 % issue activity with one
+// k pipeline per block), so the block's k range is split over its FOUR WARPS: each warp runs its own
+// load -> shared -> DMMA pipeline over a quarter of the k steps for the whole tile (4 x 4 DMMA tiles, 16-wide k steps, no
+// block-wide barrier), and the four partial tiles meet in shared memory at the end.
 // A(m, k) = A[m a_sm + k a_sk], B(k, n) = B[k b_sk + n b_sn]; *_KC: the operand is contiguous along k (else along m / n) --
-// only the thread -> element mapping of the tile loads depends on it.  M, N multiples of 32, K of 16.
+// only the lane -> element mapping of the tile loads depends on it.  M, N multiples of 32, K (per split) of 64.
 template <typename TA, bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(64) k_aff_dgemm(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
-                                                  const double* __restrict__ B, int64_t b_sk, int64_t b_sn,
-                                                  double* __restrict__ C, int64_t ldc, int64_t split_stride, int K,
-                                                  int k_per_split) {
-    __shared__ double As[16][34], Bs[16][34];
-    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+__global__ void __launch_bounds__(128) k_aff_dgemm(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
+                                                   const double* __restrict__ B, int64_t b_sk, int64_t b_sn,
+                                                   double* __restrict__ C, int64_t ldc, int64_t split_stride, int K,
+                                                   int k_per_split) {
+    // leading dimension 40: the four k rows of a fragment load start 0 / 8 / 0 / 8 (mod 16) eight-byte banks apart, so the 32
+    // lanes of a fragment load touch every bank exactly twice (the minimum for 256 bytes)
+    __shared__ double sm[4][2][16][40];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fk = lane & 3;
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int k_beg = blockIdx.z * k_per_split, k_end = min(K, k_beg + k_per_split);
-    double c[4][4];
+    const int kq = (k_end - k_beg) >> 2;                    // k steps of this warp: [k_beg + w kq, + kq)
+    double (*As)[40] = sm[w][0];
+    double (*Bs)[40] = sm[w][1];
+    double c[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c[i][j] = 0.0;
-    double ra[8], rb[8];
-    auto fetch = [&](int k0) {
+        for (int u = 0; u < 4; ++u) c[t][u][0] = c[t][u][1] = 0.0;
+    for (int k0 = k_beg + w * kq; k0 < k_beg + (w + 1) * kq; k0 += 16) {
+        double ra[16], rb[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int ka = A_KC ? (tid & 15) : (tid >> 5) + 2 * q, mm = A_KC ? (tid >> 4) + 4 * q : (tid & 31);
+        for (int q = 0; q < 16; ++q) {
+            const int ka = A_KC ? (lane & 15) : q, mm = A_KC ? (lane >> 4) + 2 * q : lane;
             ra[q] = (double)A[(int64_t)(m0 + mm) * a_sm + (int64_t)(k0 + ka) * a_sk];
-            const int kb = B_KC ? (tid & 15) : (tid >> 5) + 2 * q, nn = B_KC ? (tid >> 4) + 4 * q : (tid & 31);
+            const int kb = B_KC ? (lane & 15) : q, nn = B_KC ? (lane >> 4) + 2 * q : lane;
             rb[q] = B[(int64_t)(k0 + kb) * b_sk + (int64_t)(n0 + nn) * b_sn];
         }
-    };
-    fetch(k_beg);
-    for (int k0 = k_beg; k0 < k_end; k0 += 16) {
+        __syncwarp();                                        // the previous step's fragment loads are done
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int ka = A_KC ? (tid & 15) : (tid >> 5) + 2 * q, mm = A_KC ? (tid >> 4) + 4 * q : (tid & 31);
+        for (int q = 0; q < 16; ++q) {
+            const int ka = A_KC ? (lane & 15) : q, mm = A_KC ? (lane >> 4) + 2 * q : lane;
             As[ka][mm] = ra[q];
-            const int kb = B_KC ? (tid & 15) : (tid >> 5) + 2 * q, nn = B_KC ? (tid >> 4) + 4 * q : (tid & 31);
+            const int kb = B_KC ? (lane & 15) : q, nn = B_KC ? (lane >> 4) + 2 * q : lane;
             Bs[kb][nn] = rb[q];
         }
-        __syncthreads();
-        if (k0 + 16 < k_end) fetch(k0 + 16);                 // next k step's loads in flight behind this step's DFMAs
+        __syncwarp();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
+        for (int ks = 0; ks < 4; ++ks) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+            for (int t = 0; t < 4; ++t) { a[t] = As[4 * ks + fk][8 * t + fr]; b[t] = Bs[4 * ks + fk][8 * t + fr]; }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c[i][j] = fma(a[i], b[j], c[i][j]);
+                for (int u = 0; u < 4; ++u) dmma_884(c[t][u][0], c[t][u][1], a[t], b[u]);
         }
-        __syncthreads();
     }
+    // the four partial tiles -> shared memory ([w][32][32 + 2]: 8.7 KB each, the operand buffers are free now) -> C
+    __syncthreads();
+    double* red = &sm[0][0][0][0];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<double2*>(red + (w * 32 + 8 * t + fr) * 34 + 8 * u + 2 * fk) = make_double2(c[t][u][0], c[t][u][1]);
+    __syncthreads();
     double* out = C + (size_t)blockIdx.z * split_stride;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) out[(int64_t)(m0 + ty * 4 + i) * ldc + n0 + tx * 4 + j] = c[i][j];
+    for (int q = 0; q < 8; ++q) {
+        const int e = tid + 128 * q, r = e >> 5, cc = e & 31;
+        out[(int64_t)(m0 + r) * ldc + n0 + cc] = (red[r * 34 + cc] + red[(32 + r) * 34 + cc]) + (red[(64 + r) * 34 + cc] + red[(96 + r) * 34 + cc]);
+    }
 }
 
 // dW[i][k] += sum_splits part[s][i][k]   (256 x 256 block of a weight gradient with leading dimension ld)
@@ -567,6 +604,15 @@ int check_common(const pcnerf_mlp_params* P, const float* rays, int ld, int64_t 
     return 0;
 }
 
+// CTAs per chunk of the data-sized kernels: whole waves of two CTAs per SM, about 48 per chunk, at most AFR_PARTS
+int parts_for(int64_t nc) {
+    const int slots = 2 * PCN_SM_COUNT;
+    int waves = (int)((nc * 48 + slots / 2) / slots);
+    if (waves < 1) waves = 1;
+    int64_t p = (int64_t)slots * waves / nc;
+    return (int)(p < 1 ? 1 : (p > AFR_PARTS ? AFR_PARTS : p));
+}
+
 const int kLd[8] = {63, 256, 256, 256, 319, 256, 256, 256};       // leading dimension of W_l
 const int kOff[8] = {0, 0, 0, 0, 63, 0, 0, 0};                    // first column of the block that multiplies H_{l-1}
 
@@ -587,17 +633,18 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     const Work w = work_layout(nc);
     double* base = (double*)work;
     const RayRows src{rays, ld, z, S};
+    const int parts = parts_for(nc);
     static bool attr_done = false;
     if (!attr_done) {
-        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, AFR_T * 64 * 4));
+        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * AFR_T * 64 * 4));
         attr_done = true;
     }
     {
         PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0, 3);
-        k_affine_moments_rays<<<dim3(AFR_PARTS, (unsigned)nc), AFR_THREADS, AFR_T * 64 * 4, st>>>(src, rows, chunk, base + w.part,
+        k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, 2 * AFR_T * 64 * 4, st>>>(src, rows, chunk, base + w.part,
                                                                                                 base + w.shift);
         PCN_LAUNCH_CHECK();
-        k_affine_moments_reduce<<<dim3(16, (unsigned)nc), 256, 0, st>>>(base + w.part, base + w.G0);    // (G0: free until backward)
+        k_affine_moments_reduce<<<dim3(16, (unsigned)nc), 256, 0, st>>>(base + w.part, parts, base + w.G0);    // (G0: free until backward)
         PCN_LAUNCH_CHECK();
         k_affine_moments_finish<<<(unsigned)nc, 256, 0, st>>>(base + w.G0, base + w.shift, base + w.m, base + w.C,
                                                               base + w.cnt);
@@ -611,7 +658,7 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
             const LayerView v = layer_view(base, w, l, nc);
             if (l > 0) {
                 const LayerView pv = layer_view(base, w, l - 1, nc);
-                k_aff_dgemm<float, true, false><<<dim3(N / 32, 8, 1), 64, 0, st>>>(P->W[l] + kOff[l], kLd[l], 1, pv.Ab, N, 1, v.A,
+                k_aff_dgemm<float, true, false><<<dim3(N / 32, 8, 1), 128, 0, st>>>(P->W[l] + kOff[l], kLd[l], 1, pv.Ab, N, 1, v.A,
                                                                                     N, 0, 256, 256);
                 PCN_LAUNCH_CHECK();
             }
@@ -637,7 +684,7 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     }
     {
         PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0);
-        k_affine_apply_rays<<<dim3(AFR_PARTS, (unsigned)nc), 256, 0, st>>>(src, rows, chunk, (const float*)(base + w.alpha), out_p);
+        k_affine_apply_rays<<<dim3(parts, (unsigned)nc), 256, 0, st>>>(src, rows, chunk, (const float*)(base + w.alpha), out_p);
         PCN_LAUNCH_CHECK();
     }
     return 0;
@@ -654,12 +701,12 @@ extern "C" int pcnerf_affine_backward_rays(const pcnerf_mlp_params* P, const pcn
     const Work w = work_layout(nc);
     double* base = (double*)work;
     const RayRows src{rays, ld, z, S};
-    const int N = (int)nc * 64;
+    const int N = (int)nc * 64, parts = parts_for(nc);
     {
         PcnScope ps(PCN_K_AFFINE, st, (double)rows * 16.0, 2);
-        k_affine_grad_rays<<<dim3(AFR_PARTS, (unsigned)nc), 256, 0, st>>>(src, out_p, grad_p, rows, chunk, base + w.part);
+        k_affine_grad_rays<<<dim3(parts, (unsigned)nc), 256, 0, st>>>(src, out_p, grad_p, rows, chunk, base + w.part);
         PCN_LAUNCH_CHECK();
-        k_affine_grad_finish<<<(unsigned)nc, 64, 0, st>>>(base + w.part, base + w.dalpha);
+        k_affine_grad_finish<<<(unsigned)nc, 64, 0, st>>>(base + w.part, parts, base + w.dalpha);
         PCN_LAUNCH_CHECK();
     }
     PcnScope ps(PCN_K_MLP_SMALL, st, 0.0, 45);
@@ -682,13 +729,13 @@ extern "C" int pcnerf_affine_backward_rays(const pcnerf_mlp_params* P, const pcn
         if (l == 0) break;
         const LayerView pv = layer_view(base, w, l - 1, nc);
         // dW'_l += sum_chunks G Ab_{l-1}^T
-        k_aff_dgemm<double, true, true><<<dim3(8, 8, splits), 64, 0, st>>>(G, N, 1, pv.Ab, 1, N, base + w.wsplit, 256, 65536, N,
+        k_aff_dgemm<double, true, true><<<dim3(8, 8, splits), 128, 0, st>>>(G, N, 1, pv.Ab, 1, N, base + w.wsplit, 256, 65536, N,
                                                                              cps * 64);
         PCN_LAUNCH_CHECK();
         k_aff_wgrad_reduce<<<256, 256, 0, st>>>(base + w.wsplit, splits, Gr->dW[l] + kOff[l], kLd[l]);
         PCN_LAUNCH_CHECK();
         // dL/dAb_{l-1} = W'_l^T G
-        k_aff_dgemm<float, false, false><<<dim3(N / 32, 8, 1), 64, 0, st>>>(P->W[l] + kOff[l], 1, kLd[l], G, N, 1, Gn, N, 0, 256,
+        k_aff_dgemm<float, false, false><<<dim3(N / 32, 8, 1), 128, 0, st>>>(P->W[l] + kOff[l], 1, kLd[l], G, N, 1, Gn, N, 0, 256,
                                                                              256);
         PCN_LAUNCH_CHECK();
         double* t = G; G = Gn; Gn = t;
