@@ -94,11 +94,11 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
         auto put = [&](int col, float v) { shift[col] = v; };
         if (tid == 0) {
             shift[0] = x0; shift[1] = x1; shift[2] = x2; shift[63] = 0.f;
-            enc_visit_coord<0>(x0, put);
+            enc_visit_coord_poly<0>(x0, put);
         } else if (tid == 1) {
-            enc_visit_coord<1>(x1, put);
+            enc_visit_coord_poly<1>(x1, put);
         } else {
-            enc_visit_coord<2>(x2, put);
+            enc_visit_coord_poly<2>(x2, put);
         }
     }
     __syncthreads();
@@ -115,7 +115,7 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
             if (r < r_end) {
                 float x0, x1, x2;
                 ray_row_pos(src, r, x0, x1, x2);
-                enc_visit(x0, x1, x2, [&](int col, float v) { buf[afr_swz(tid, col)] = v - shift[col]; });
+                enc_visit_poly(x0, x1, x2, [&](int col, float v) { buf[afr_swz(tid, col)] = v - shift[col]; });
                 buf[afr_swz(tid, 63)] = 1.f;
             } else {
 #pragma unroll
@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(256) k_affine_apply_rays(RayRows src, int64_t 
         float x0, x1, x2;
         ray_row_pos(src, r, x0, x1, x2);
         float t0 = fmaf(x0, sa[0], sa[63]), t1 = x1 * sa[1], t2 = x2 * sa[2];      // one chain per coordinate
-        enc_visit_coord<0>(x0, [&](int col, float v) { t0 = fmaf(v, sa[col], t0); });
-        enc_visit_coord<1>(x1, [&](int col, float v) { t1 = fmaf(v, sa[col], t1); });
-        enc_visit_coord<2>(x2, [&](int col, float v) { t2 = fmaf(v, sa[col], t2); });
+        enc_visit_coord_poly<0>(x0, [&](int col, float v) { t0 = fmaf(v, sa[col], t0); });
+        enc_visit_coord_poly<1>(x1, [&](int col, float v) { t1 = fmaf(v, sa[col], t1); });
+        enc_visit_coord_poly<2>(x2, [&](int col, float v) { t2 = fmaf(v, sa[col], t2); });
         const float t = t0 + (t1 + t2);
         out_p[r] = 1.f / (1.f + expf(-t));
     }
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256, 2) k_affine_grad_rays(RayRows src, const 
         const float g = grad_p[r] * pv * (1.f - pv);
         float x0, x1, x2;
         ray_row_pos(src, r, x0, x1, x2);
-        enc_visit(x0, x1, x2, [&](int col, float v) { acc[col] = fmaf(g, v, acc[col]); });
+        enc_visit_poly(x0, x1, x2, [&](int col, float v) { acc[col] = fmaf(g, v, acc[col]); });
         acc[63] += g;
     }
 #pragma unroll

@@ -51,3 +51,56 @@ __device__ __forceinline__ void enc_visit(float x0, float x1, float x2, F&& f) {
     enc_visit_coord<1>(x1, f);
     enc_visit_coord<2>(x2, f);
 }
+
+// ---- the same 63 values for kernels that RE-DERIVE a row instead of reading it (affine_rays.cu): sin / cos of the exact
+// phase by quadrant + degree-7 / degree-8 polynomials on [-pi/4, pi/4] (Cephes sinf / cosf coefficients) instead of
+// sincospif: ~24 instead of ~32 instructions per pair, max abs error 1.2e-7 against the exact angle (sincospif on the
+// fp32-rounded phase: 9.4e-8 + its own 2 ulp) -- scripts-level study in DESIGN.md section 4.4.  Not bit-identical to
+// enc_coord<false>: the closed-form engine is self-consistent (moments, apply and gradient all use this form).
+__device__ __forceinline__ void sincos_turn(int fr, float& sn, float& cs) {
+    // fr: angle in 2^-32 turns (signed).  q = nearest quarter turn, y = the rest in radians, |y| <= pi/4
+    const uint32_t t = (uint32_t)fr + 0x20000000u;
+    const uint32_t q = t >> 30;
+    const float y = (float)((int)(t & 0x3FFFFFFFu) - 0x20000000) * 1.4629180792671596e-9f;      // 2 pi / 2^32
+    const float z = y * y;
+    const float sp = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    const float s = fmaf(y * z, sp, y);
+    const float cp = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    const float c = fmaf(z * z, cp, fmaf(-0.5f, z, 1.f));
+    const float a = (q & 1u) ? c : s, b = (q & 1u) ? s : c;          // sin(q pi/2 + y), cos(q pi/2 + y) up to sign
+    sn = __uint_as_float(__float_as_uint(a) ^ ((q & 2u) << 30));
+    cs = __uint_as_float(__float_as_uint(b) ^ (((q + 1u) & 2u) << 30));
+}
+
+template <int C, class F>
+__device__ __forceinline__ void enc_visit_coord_poly(float x, F&& f) {
+    if (fabsf(x) < ENC_BIG) {
+        const long long q = enc_phase(x);
+        const uint32_t lo = (uint32_t)q, hi = (uint32_t)((unsigned long long)q >> 32);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float sn, cs;
+            sincos_turn((int)__funnelshift_r(lo, hi, 9 - k), sn, cs);
+            f(3 + 6 * k + C, sn);
+            f(6 + 6 * k + C, cs);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float sn, cs;
+            sincosf((float)(1 << k) * x, &sn, &cs);
+            f(3 + 6 * k + C, sn);
+            f(6 + 6 * k + C, cs);
+        }
+    }
+}
+
+template <class F>
+__device__ __forceinline__ void enc_visit_poly(float x0, float x1, float x2, F&& f) {
+    f(0, x0);
+    f(1, x1);
+    f(2, x2);
+    enc_visit_coord_poly<0>(x0, f);
+    enc_visit_coord_poly<1>(x1, f);
+    enc_visit_coord_poly<2>(x2, f);
+}
