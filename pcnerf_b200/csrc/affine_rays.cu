@@ -56,9 +56,30 @@ __device__ __forceinline__ void part_range(int64_t rows, int64_t chunk, int ci, 
     r_end = min(c_end, r_beg + per);
 }
 
-// 16-byte chunk c of row `row` of a [AFR_T][64] tile lives at chunk c ^ (row & 7): a column written by 32 consecutive
-// rows spreads over all 8 bank groups (4-way conflicts instead of 32-way), a row is read conflict-free in any chunk order
-__device__ __forceinline__ int afr_swz(int row, int col) { return row * 64 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)); }
+// Sub-tile layout of the moments kernel: rows are stored in PAIRS (512 bytes per pair).  Columns 4g, 4g+1 of column group g
+// sit in 16-byte chunk (g ^ key) of the pair's first 256 bytes, columns 4g+2, 4g+3 in the same chunk of the second 256 bytes,
+// key = (row / 2) & 7; inside a chunk {x[r0][c], x[r1][c], x[r0][c+1], x[r1][c+1]}.  One 16-byte load therefore yields
+// register pairs (r0, r1) per column -- the operand form of the packed FFMA2 (fma.rn.f32x2: even rows accumulate in the low
+// lanes, odd rows in the high lanes) -- and the 16 column groups a warp reads side by side are 256 contiguous bytes (two
+// wavefronts, the minimum), while a column written by 32 consecutive rows spreads over 16 banks (2-way conflicts).
+__device__ __forceinline__ int afr_idx(int row, int col) {
+    const int rp = row >> 1, g = col >> 2, w = col & 3;
+    return rp * 128 + ((w >> 1) << 6) + ((g ^ (rp & 7)) << 2) + ((w & 1) << 1) + (row & 1);
+}
+
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ double sum2(unsigned long long v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return (double)lo + (double)hi;
+}
 
 // named barriers 1 + b / 3 + b (b = buffer; immediates, so that the kernel reserves 5 hardware barriers and not all 16)
 template <int ID>
@@ -115,11 +136,11 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
             if (r < r_end) {
                 float x0, x1, x2;
                 ray_row_pos(src, r, x0, x1, x2);
-                enc_visit_poly(x0, x1, x2, [&](int col, float v) { buf[afr_swz(tid, col)] = v - shift[col]; });
-                buf[afr_swz(tid, 63)] = 1.f;
+                enc_visit_poly(x0, x1, x2, [&](int col, float v) { buf[afr_idx(tid, col)] = v - shift[col]; });
+                buf[afr_idx(tid, 63)] = 1.f;
             } else {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) *reinterpret_cast<float4*>(&buf[tid * 64 + c * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int col = 0; col < 64; ++col) buf[afr_idx(tid, col)] = 0.f;
             }
             __threadfence_block();
             bar_arrive<FULL>(b);
@@ -135,16 +156,16 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
         tj = ti + rem;
     }
     double acc[4][4];
-    float f[4][4];
+    unsigned long long f[4][4];                     // packed pairs: low lane = even rows, high lane = odd rows
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.0; f[i][j] = 0.f; }
-    int oa[8], ob[8];                               // float offsets of chunks ti / tj in rows u = 0..7 of any 8 rows
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.0; f[i][j] = 0ull; }
+    int oa[8], ob[8];                               // float offsets of column groups ti / tj in row pairs u = 0..7 (mod 8)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        oa[u] = u * 64 + ((ti ^ u) << 2);
-        ob[u] = u * 64 + ((tj ^ u) << 2);
+        oa[u] = u * 128 + ((ti ^ u) << 2);
+        ob[u] = u * 128 + ((tj ^ u) << 2);
     }
     for (int t = 0; t < nt; ++t) {
         const int b = t & 1;
@@ -152,17 +173,20 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
         if (worker) {
             const float* buf = xs + b * (AFR_T * 64);
 #pragma unroll 2
-            for (int rb = 0; rb < AFR_T; rb += 8) {
-                const float* base = buf + rb * 64;
+            for (int rb = 0; rb < AFR_T / 2; rb += 8) {
+                const float* base = buf + rb * 128;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const float4 a = *reinterpret_cast<const float4*>(base + oa[u]);
-                    const float4 bb = *reinterpret_cast<const float4*>(base + ob[u]);
-                    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                    const float4 a0 = *reinterpret_cast<const float4*>(base + oa[u]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(base + oa[u] + 64);
+                    const float4 b0 = *reinterpret_cast<const float4*>(base + ob[u]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(base + ob[u] + 64);
+                    const unsigned long long av[4] = {pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), pack2(a1.z, a1.w)};
+                    const unsigned long long bv[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) f[i][j] = fmaf(av[i], bv[j], f[i][j]);
+                        for (int j = 0; j < 4; ++j) ffma2(f[i][j], av[i], bv[j]);
                 }
             }
         }
@@ -171,7 +195,7 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { acc[i][j] += (double)f[i][j]; f[i][j] = 0.f; }
+                for (int j = 0; j < 4; ++j) { acc[i][j] += sum2(f[i][j]); f[i][j] = 0ull; }
         }
     }
     if (worker) {
@@ -179,7 +203,7 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) out[(ti * 4 + i) * 64 + tj * 4 + j] = acc[i][j] + (double)f[i][j];
+            for (int j = 0; j < 4; ++j) out[(ti * 4 + i) * 64 + tj * 4 + j] = acc[i][j] + sum2(f[i][j]);
     }
 }
 
