@@ -22,13 +22,14 @@
 #include "encode.cuh"
 
 #define AFR_PARTS 64            // most CTAs (partial results) per chunk of the data-sized kernels (buffer sizing)
-#define AFR_T 96                // rows per shared-memory sub-tile of the moments kernel (two buffers)
-#define AFR_PROD 96             // producer threads of the moments kernel: warps 0..2 encode one row each per sub-tile
-#define AFR_TILES 136           // 4 x 4 tiles of the upper triangle of the 64 x 64 moment matrix (16 * 17 / 2)
-#define AFR_THREADS 256         // 8 warps: 3 producers + 5 consumers (136 tile owners, 24 idle lanes); 112 registers x 8
-                                // warps = two CTAs per SM (nine warps are allocated as twelve: one CTA)
-#define AFR_FLUSH 2             // sub-tiles (= 256 rows) accumulated in fp32 before the fold into fp64 (power of two)
-#define AFR_SPLITS 8            // split-K factor of the weight-gradient GEMM
+#define AFR_T 120               // rows per shared-memory sub-tile of the moments kernel (two buffers); 8 rows per row group
+#define AFR_GROUPS 3            // consumer row groups (rows = g mod 3), 36 tile owners each
+#define AFR_PROD 128            // producer threads of the moments kernel: warps 0..3 encode one row each per sub-tile (120 used)
+#define AFR_TILES 36            // 8 x 8 tiles of the upper triangle of the 64 x 64 moment matrix (8 * 9 / 2)
+#define AFR_THREADS 256         // 8 warps: 4 producers + 4 consumers (3 row groups x 36 tile owners, 20 idle lanes)
+#define AFR_FLUSH 4             // sub-tiles (= 160 rows per tile owner) accumulated in fp32 before the fold into fp64 (power of two)
+#define AFR_MOM_SMEM (2 * AFR_T * 64 * 4 + AFR_GROUPS * AFR_TILES * 64 * 4 + AFR_TILES * 64 * 8)     // dynamic shared memory of the moments kernel: two sub-tile buffers, fp32 scratch, fp64 accumulators
+#define AFR_SPLITS 6            // split-K factor of the weight-gradient GEMM (64 tiles x 6 = 384 blocks: one wave of 3 per SM)
 
 struct RayRows {
     const float* rays;          // (n_rays, ld): origin in columns 0..2, direction in 3..5
@@ -56,154 +57,182 @@ __device__ __forceinline__ void part_range(int64_t rows, int64_t chunk, int ci, 
     r_end = min(c_end, r_beg + per);
 }
 
-// Sub-tile layout of the moments kernel: rows are stored in PAIRS (512 bytes per pair).  Columns 4g, 4g+1 of column group g
-// sit in 16-byte chunk (g ^ key) of the pair's first 256 bytes, columns 4g+2, 4g+3 in the same chunk of the second 256 bytes,
-// key = (row / 2) & 7; inside a chunk {x[r0][c], x[r1][c], x[r0][c+1], x[r1][c+1]}.  One 16-byte load therefore yields
-// register pairs (r0, r1) per column -- the operand form of the packed FFMA2 (fma.rn.f32x2: even rows accumulate in the low
-// lanes, odd rows in the high lanes) -- and the 16 column groups a warp reads side by side are 256 contiguous bytes (two
-// wavefronts, the minimum), while a column written by 32 consecutive rows spreads over 16 banks (2-way conflicts).
-__device__ __forceinline__ int afr_idx(int row, int col) {
-    const int rp = row >> 1, g = col >> 2, w = col & 3;
-    return rp * 128 + ((w >> 1) << 6) + ((g ^ (rp & 7)) << 2) + ((w & 1) << 1) + (row & 1);
-}
+// Sub-tile layout of the moments kernel: row-major [AFR_T][64] floats; the first four columns of the 8-column group tg sit in
+// 16-byte chunk (tg ^ key) of the row's first 128 bytes, the last four in the same chunk of the second 128 bytes, key =
+// row & 7.  The 8 rows a quarter-warp writes with one STS.128 land in 8 different bank groups, and the quarter-warp of tile
+// owners that reads the first (second) halves of 8 different column groups of one row reads 128 contiguous bytes.
+__device__ __forceinline__ int afr_chunk(int row, int tg, int h) { return row * 64 + (h << 5) + ((tg ^ (row & 7)) << 2); }
 
-__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+// d.lo += a * b.lo, d.hi += a * b.hi: the packed FFMA2 with a scalar multiplicand (ptxas folds the {a, a} pair into the
+// instruction's .F32 broadcast operand)
+__device__ __forceinline__ void ffma2s(unsigned long long& d, float a, unsigned long long b) {
+    unsigned long long aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(b));
 }
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ double sum2(unsigned long long v) {
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return (double)lo + (double)hi;
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
 }
 
-// named barriers 1 + b / 3 + b (b = buffer; immediates, so that the kernel reserves 5 hardware barriers and not all 16)
-template <int ID>
-__device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(AFR_THREADS) : "memory"); }
-template <int ID>
-__device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(AFR_THREADS) : "memory"); }
+// named barriers (immediates, so that the kernel reserves 6 hardware barriers and not all 16): FULL + b / EMPTY + b hand
+// buffer b between producers and consumers (all AFR_THREADS take part), CONS synchronises the consumer warps only
+template <int ID, int N>
+__device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int ID, int N>
+__device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 template <int ID0>
-__device__ __forceinline__ void bar_sync(int b) { if (b) bar_sync_id<ID0 + 1>(); else bar_sync_id<ID0>(); }
+__device__ __forceinline__ void bar_sync(int b) { if (b) bar_sync_id<ID0 + 1, AFR_THREADS>(); else bar_sync_id<ID0, AFR_THREADS>(); }
 template <int ID0>
-__device__ __forceinline__ void bar_arrive(int b) { if (b) bar_arrive_id<ID0 + 1>(); else bar_arrive_id<ID0>(); }
+__device__ __forceinline__ void bar_arrive(int b) { if (b) bar_arrive_id<ID0 + 1, AFR_THREADS>(); else bar_arrive_id<ID0, AFR_THREADS>(); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // data-sized kernels
 // ---------------------------------------------------------------------------------------------------------------
 
-// part[(ci, pi)][64][64] (only the 4 x 4 tiles with tile row <= tile column are written):
+// part[(ci, pi)][64][64] (only the 8 x 8 tiles with tile row <= tile column are written):
 //   sum over the part's rows of y y^T,  y = (x_0 - s_0, ..., x_62 - s_62, 1),  s = encoding of the chunk's first row.
 // Column 63 of the result holds the first moments, element (63, 63) the row count.
-// Warp-specialised: warps 0..2 (one row per thread) encode sub-tile t + 1 into one shared-memory buffer while warps 3..7 (one
-// 4 x 4 tile of the upper triangle per thread, 136 owners) accumulate the outer products of sub-tile t from the other --
-// the sin/cos polynomials and the FMA / shared-load stream of the products fill each other's issue slots.  Hand-off through
-// named barriers (full / empty per buffer: producers `arrive` on full and `sync` on empty, consumers the reverse).
-__global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows, int64_t chunk, double* __restrict__ part,
-                                                       double* __restrict__ shift_out) {
-    extern __shared__ __align__(16) float xs[];             // 2 x [AFR_T][64]
+//
+// The kernel is bound by shared-memory wavefronts (ncu on the 4 x 4-tile form: 89 % of the LSU-shared peak, every 128-bit
+// load of a warp costs four wavefronts whatever its lanes share), so the outer products use the largest register tile that
+// fits: 8 x 8 per thread, 36 tiles for the upper triangle, accumulated with packed FFMA2 (scalar x pair) -- 4 loads and 32
+// FFMA2 per row and thread.  Warp-specialised: warps 0..3 (one row per thread) encode sub-tile t + 1 into one buffer while
+// warps 4..7 accumulate sub-tile t from the other: three row groups (rows = g mod 3) x 36 tile owners.  fp32 accumulation
+// over AFR_FLUSH sub-tiles (160 rows per thread), then the groups' partial tiles are added into fp64 accumulators in shared
+// memory.
+__global__ void __launch_bounds__(AFR_THREADS, 2) k_affine_moments_rays(RayRows src, int64_t rows, int64_t chunk,
+                                                                        double* __restrict__ part,
+                                                                        double* __restrict__ shift_out) {
+    extern __shared__ __align__(16) float xs[];             // 2 x [AFR_T][64] | scratch [3][36][64] fp32 | acc [36][64] fp64
     __shared__ float shift[64];
+    float* scratch = xs + 2 * AFR_T * 64;
+    double* accs = reinterpret_cast<double*>(scratch + AFR_GROUPS * AFR_TILES * 64);
     const int ci = blockIdx.y, pi = blockIdx.x, tid = threadIdx.x;
     int64_t c_beg, r_beg, r_end;
     part_range(rows, chunk, ci, pi, c_beg, r_beg, r_end);
-    if (tid < 3) {
-        float x0, x1, x2;
-        ray_row_pos(src, c_beg, x0, x1, x2);
-        auto put = [&](int col, float v) { shift[col] = v; };
-        if (tid == 0) {
-            shift[0] = x0; shift[1] = x1; shift[2] = x2; shift[63] = 0.f;
-            enc_visit_coord_poly<0>(x0, put);
-        } else if (tid == 1) {
-            enc_visit_coord_poly<1>(x1, put);
-        } else {
-            enc_visit_coord_poly<2>(x2, put);
-        }
-    }
+    // shift: the position of the chunk's first row for columns 0..2 (|x| reaches tens of metres); the sin / cos columns are
+    // bounded with means near zero and are accumulated unshifted
+    if (tid < 64) shift[tid] = 0.f;
+    __syncthreads();
+    if (tid == 0) ray_row_pos(src, c_beg, shift[0], shift[1], shift[2]);
+    for (int e = tid; e < AFR_TILES * 64; e += AFR_THREADS) accs[e] = 0.0;
     __syncthreads();
     if (pi == 0 && tid < 64) shift_out[ci * 64 + tid] = (double)shift[tid];
     const int nt = (int)((r_end - r_beg + AFR_T - 1) / AFR_T);
-    enum { FULL = 1, EMPTY = 3 };                           // named barriers FULL + b, EMPTY + b (0 is __syncthreads)
+    enum { FULL = 1, EMPTY = 3, CONS = 5 };
 
     if (tid < AFR_PROD) {
+        const float s0 = shift[0], s1 = shift[1], s2 = shift[2];
         for (int t = 0; t < nt; ++t) {
             const int b = t & 1;
             if (t >= 2) bar_sync<EMPTY>(b);
             float* buf = xs + b * (AFR_T * 64);
             const int64_t r = r_beg + (int64_t)t * AFR_T + tid;
-            if (r < r_end) {
-                float x0, x1, x2;
-                ray_row_pos(src, r, x0, x1, x2);
-                enc_visit_poly(x0, x1, x2, [&](int col, float v) { buf[afr_idx(tid, col)] = v - shift[col]; });
-                buf[afr_idx(tid, 63)] = 1.f;
-            } else {
+            if (tid < AFR_T) {
+                float e[64];
+                if (r < r_end) {
+                    float x0, x1, x2;
+                    ray_row_pos(src, r, x0, x1, x2);
+                    enc_visit_poly(x0, x1, x2, [&](int col, float v) { e[col] = v; });
+                    e[0] -= s0; e[1] -= s1; e[2] -= s2;
+                    e[63] = 1.f;
+                } else {
 #pragma unroll
-                for (int col = 0; col < 64; ++col) buf[afr_idx(tid, col)] = 0.f;
+                    for (int col = 0; col < 64; ++col) e[col] = 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    *reinterpret_cast<float4*>(buf + afr_chunk(tid, c >> 1, c & 1)) =
+                        make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
             }
             __threadfence_block();
             bar_arrive<FULL>(b);
         }
         return;
     }
-    const int id = tid - AFR_PROD;
-    const bool worker = id < AFR_TILES;
+    const int cid = tid - AFR_PROD;                  // 0 .. 127
+    const bool worker = cid < AFR_GROUPS * AFR_TILES;
+    const int g = worker ? cid / AFR_TILES : 0, id = worker ? cid - g * AFR_TILES : 0;
     int ti = 0, tj = 0;
-    if (worker) {                                   // id -> (ti, tj), ti <= tj, rows of the upper triangle one after the other
+    {                                               // id -> (ti, tj), ti <= tj < 8, rows of the upper triangle one after the other
         int rem = id;
-        while (rem >= 16 - ti) { rem -= 16 - ti; ++ti; }
+        while (rem >= 8 - ti) { rem -= 8 - ti; ++ti; }
         tj = ti + rem;
     }
-    double acc[4][4];
-    unsigned long long f[4][4];                     // packed pairs: low lane = even rows, high lane = odd rows
+    unsigned long long f[8][4];                     // f[i][jp] = (tile[i][2 jp], tile[i][2 jp + 1])
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.0; f[i][j] = 0ull; }
-    int oa[8], ob[8];                               // float offsets of column groups ti / tj in row pairs u = 0..7 (mod 8)
+        for (int j = 0; j < 4; ++j) f[i][j] = 0ull;
+    // this group's rows are g, g + 3, g + 6, ...: 8 of them span 24 rows, after which the swizzle keys (row & 7) repeat --
+    // the offsets of column groups ti / tj in those 8 rows are loop invariants (second halves: + 32 floats)
+    int oa[8], ob[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        oa[u] = u * 128 + ((ti ^ u) << 2);
-        ob[u] = u * 128 + ((tj ^ u) << 2);
+        oa[u] = afr_chunk(g + AFR_GROUPS * u, ti, 0);
+        ob[u] = afr_chunk(g + AFR_GROUPS * u, tj, 0);
     }
+    auto flush = [&]() {
+        // the groups' fp32 partial tiles -> scratch -> fp64 accumulators (the 108 tile owners fold 64 / 3 elements each)
+        if (worker) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; j += 2) {
+                    const float2 p0 = unpack2(f[i][j]), p1 = unpack2(f[i][j + 1]);
+                    *reinterpret_cast<float4*>(scratch + (g * AFR_TILES + id) * 64 + i * 8 + 2 * j) = make_float4(p0.x, p0.y, p1.x, p1.y);
+                    f[i][j] = 0ull; f[i][j + 1] = 0ull;
+                }
+            }
+        }
+        bar_sync_id<CONS, AFR_THREADS - AFR_PROD>();
+        for (int e = cid; e < AFR_TILES * 64; e += AFR_THREADS - AFR_PROD) {
+            double v = 0.0;
+#pragma unroll
+            for (int gg = 0; gg < AFR_GROUPS; ++gg) v += (double)scratch[gg * AFR_TILES * 64 + e];
+            accs[e] += v;
+        }
+        bar_sync_id<CONS, AFR_THREADS - AFR_PROD>();
+    };
     for (int t = 0; t < nt; ++t) {
         const int b = t & 1;
         bar_sync<FULL>(b);
         if (worker) {
             const float* buf = xs + b * (AFR_T * 64);
-#pragma unroll 2
-            for (int rb = 0; rb < AFR_T / 2; rb += 8) {
-                const float* base = buf + rb * 128;
+            for (int rb = 0; rb < AFR_T; rb += 8 * AFR_GROUPS) {
+                const float* base = buf + rb * 64;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const float4 a0 = *reinterpret_cast<const float4*>(base + oa[u]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(base + oa[u] + 64);
+                    const float4 a1 = *reinterpret_cast<const float4*>(base + oa[u] + 32);
                     const float4 b0 = *reinterpret_cast<const float4*>(base + ob[u]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(base + ob[u] + 64);
-                    const unsigned long long av[4] = {pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), pack2(a1.z, a1.w)};
+                    const float4 b1 = *reinterpret_cast<const float4*>(base + ob[u] + 32);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                     const unsigned long long bv[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 8; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ffma2(f[i][j], av[i], bv[j]);
+                        for (int j = 0; j < 4; ++j) ffma2s(f[i][j], av[i], bv[j]);
                 }
             }
         }
         if (t + 2 < nt) bar_arrive<EMPTY>(b);
-        if ((t & (AFR_FLUSH - 1)) == AFR_FLUSH - 1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { acc[i][j] += sum2(f[i][j]); f[i][j] = 0ull; }
-        }
+        if ((t & (AFR_FLUSH - 1)) == AFR_FLUSH - 1) flush();
     }
-    if (worker) {
-        double* out = part + ((size_t)ci * gridDim.x + pi) * 4096;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[(ti * 4 + i) * 64 + tj * 4 + j] = acc[i][j] + sum2(f[i][j]);
+    if (nt & (AFR_FLUSH - 1)) flush();
+    double* out = part + ((size_t)ci * gridDim.x + pi) * 4096;
+    for (int e = cid; e < AFR_TILES * 64; e += AFR_THREADS - AFR_PROD) {
+        int tt = e >> 6, t_i = 0;                   // tile index -> (t_i, t_j) as above
+        while (tt >= 8 - t_i) { tt -= 8 - t_i; ++t_i; }
+        const int t_j = t_i + tt, el = e & 63;
+        out[(t_i * 8 + (el >> 3)) * 64 + t_j * 8 + (el & 7)] = accs[e];
     }
 }
 
@@ -211,7 +240,7 @@ __global__ void __maxnreg__(112) k_affine_moments_rays(RayRows src, int64_t rows
 __global__ void __launch_bounds__(256) k_affine_moments_reduce(const double* __restrict__ part, int parts,
                                                                double* __restrict__ S) {
     const int ci = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x, i = e >> 6, j = e & 63;
-    if ((i >> 2) > (j >> 2)) return;
+    if ((i >> 3) > (j >> 3)) return;
     const double* base = part + (size_t)ci * parts * 4096 + e;
     double s = 0.0;
 #pragma unroll 4
@@ -232,7 +261,7 @@ __global__ void __launch_bounds__(256) k_affine_moments_finish(const double* __r
     for (int e = tid; e < 4096; e += 256) {
         const int i = e >> 6, j = e & 63;
         double v = 0.0;
-        if (i < 63 && j < 63) v = Sc[(i >> 2) <= (j >> 2) ? e : j * 64 + i] / n - s1[i] * s1[j];
+        if (i < 63 && j < 63) v = Sc[(i >> 3) <= (j >> 3) ? e : j * 64 + i] / n - s1[i] * s1[j];
         C[(size_t)ci * 4096 + e] = v;
     }
     if (tid < 64) m[ci * 64 + tid] = tid < 63 ? shift[ci * 64 + tid] + s1[tid] : 1.0;
@@ -660,12 +689,12 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     const int parts = parts_for(nc);
     static bool attr_done = false;
     if (!attr_done) {
-        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * AFR_T * 64 * 4));
+        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, AFR_MOM_SMEM));
         attr_done = true;
     }
     {
         PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0, 3);
-        k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, 2 * AFR_T * 64 * 4, st>>>(src, rows, chunk, base + w.part,
+        k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, AFR_MOM_SMEM, st>>>(src, rows, chunk, base + w.part,
                                                                                                 base + w.shift);
         PCN_LAUNCH_CHECK();
         k_affine_moments_reduce<<<dim3(16, (unsigned)nc), 256, 0, st>>>(base + w.part, parts, base + w.G0);    // (G0: free until backward)
