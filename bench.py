@@ -585,6 +585,7 @@ def run_b200(a):
            "gpu_launches": launches}
     if roofline:
         out["roofline"] = roofline
+    if kernels:
         out["kernels"] = kernels
     if not a.no_inference:
         out["inference"] = time_inference(a, rank, world, dev, mc, mf, emb)
@@ -604,8 +605,45 @@ def run_b200(a):
         fast = {"precision": "affine (closed form of the identity-activation network, 1e-5 parity gate: "
                              "tests/test_gpu_affine.py)", "value": rays_f / (ms_f * 1e-3), "unit": "rays/s",
                 "ms_per_step": ms_f / a.steps, "e2e": rays_fe / (ms_fe * 1e-3), "cuda_graph": note2}
+        if not a.no_profile:
+            # where the closed-form step goes (library CUDA events per kernel class, eager launches) and the roofline of its
+            # dominant kernel: the second-moment kernel is fp32 FMA work (rows x 2,304 FMA, upper triangle of x x^T), bounded
+            # by the CUDA-core FMA pipe -- neither HBM (8 bytes per row are read) nor the tensor cores
+            barrier()
+            ops.profile(True)
+            psteps = min(a.steps, 2)
+            for _ in range(psteps):
+                step(False)
+            torch.cuda.synchronize()
+            prof_f = ops.profile_read()
+            ops.profile(False)
+            fast["kernels"] = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps}
+                               for k, v in prof_f.items() if v[1]}
+            m_ms, m_n, m_fl = prof_f.get("affine_moments", (0.0, 0, 0.0))
+            a_ms, a_n, a_fl = prof_f.get("affine_algebra", (0.0, 0, 0.0))
+            sm_mhz = float((clk or {}).get("sm_mhz") or 0.0) or 1965.0
+            fma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            if m_ms > 0:
+                tf = m_fl / (m_ms * 1e-3) / 1e12
+                fast["roofline"] = {"kernel": "k_affine_moments_rays (per-chunk second moments of the re-derived encodings: "
+                                              "8 x 8 register tiles, packed fp32 FFMA2, fp64 fold)",
+                                    "bound": "fp32 FMA pipe (CUDA cores)", "achieved": tf, "peak": fma_peak, "unit": "TFLOP/s",
+                                    "peak_source": "148 SMs x 128 FMA lanes x 2 FLOP x %.0f MHz (median SM clock sampled by this "
+                                                   "run)" % sm_mhz, "frac": tf / fma_peak,
+                                    "share_of_step": m_ms / max(sum(v[0] for v in prof_f.values()), 1e-9),
+                                    "ms_per_step": m_ms / psteps,
+                                    "algorithmic_flop_per_row": 36 * 64 * 2, "hbm_bytes_per_row": 8,
+                                    "note": "encoding re-derivation (30 sin/cos pairs per row, ~24 instructions each) runs on "
+                                            "the same pipes inside this kernel and is not counted as algorithmic work"}
+            if a_ms > 0:
+                fast["algebra"] = {"what": "float64 parameter-sized chain (mma.sync m8n8k4 f64 GEMMs + per-layer kernels), "
+                                           "forward and hand-derived backward", "ms_per_step": a_ms / psteps,
+                                   "tflops_f64": a_fl / (a_ms * 1e-3) / 1e12, "launches_per_step": a_n / psteps}
         if not a.no_inference:
-            fast["inference"] = time_inference(a, rank, world, dev, mc, mf, emb)["value"]
+            inf_f = time_inference(a, rank, world, dev, mc, mf, emb)
+            fast["inference"] = inf_f["value"]
+            fast["inference_ms_per_frame"] = inf_f.get("ms_per_frame")
+            fast["inference_kernels"] = inf_f.get("kernels")
         out["fast_mode"] = fast
         graphs.clear()
         mc.precision = mf.precision = a.precision

@@ -224,6 +224,17 @@ int pcnerf_affine_backward_rays(const pcnerf_mlp_params* h_params, const pcnerf_
                                 int ld, int64_t n_rays, const float* z, int S, int64_t chunk, const float* out_p,
                                 const float* grad_p, void* work, size_t work_bytes, void* stream);
 
+/* K3' closed form on RAYS, eval mode (model.eval(): BatchNorm1d on its running statistics, models.py:183-203 as called from
+ * nof/render.py:47-49 by the depth-inference path render.py:614-699): the logit is alpha . (x, 1) with alpha a function of the
+ * parameters and running statistics alone.
+ * pcnerf_affine_eval_alpha: alpha (64 floats, device; element 63 = the constant term) from h_params in float64 repo kernels;
+ *   work: pcnerf_affine_work_bytes(1) bytes of scratch.  Callers cache alpha until a parameter or running statistic changes.
+ * pcnerf_affine_apply_rays: out_p[r] = sigmoid(alpha . (embed(o + d z[r]), 1)) for the n_rays * S (ray, depth) rows
+ *   (rays (n_rays, ld) f32: origin in columns 0..2, direction in 3..5; z (n_rays, S) f32); no encoding tensor is read. */
+int pcnerf_affine_eval_alpha(const pcnerf_mlp_params* h_params, float* alpha, void* work, size_t work_bytes, void* stream);
+int pcnerf_affine_apply_rays(const float* rays, int ld, int64_t n_rays, const float* z, int S, const float* alpha,
+                             float* out_p, void* stream);
+
 /* Building blocks of the precision-1 path (TMA + tcgen05 + TMEM), exported for unit tests and reuse.
  * pcnerf_tc_rowgemm: C[rows,256] = [A0 | A1][rows, k0+k1] * B[256, k0+k1]^T, k0, k1 multiples of 64, k0 + k1 <= 320.
  *   mode 0 (forward): A, B fp16; vec = bias[256]; out = fp16(C + bias); out2 reserved (NULL);

@@ -58,6 +58,8 @@ SIGNATURES = {
     "pcnerf_affine_forward_rays": (ci, [ctypes.POINTER(MlpParams), vp, ci, i64, vp, ci, i64, vp, vp, sz, vp]),
     "pcnerf_affine_backward_rays": (ci, [ctypes.POINTER(MlpParams), ctypes.POINTER(MlpGrads), vp, ci, i64, vp, ci, i64, vp, vp,
                                         vp, sz, vp]),
+    "pcnerf_affine_eval_alpha": (ci, [ctypes.POINTER(MlpParams), vp, vp, sz, vp]),
+    "pcnerf_affine_apply_rays": (ci, [vp, ci, i64, vp, ci, vp, vp, vp]),
     "pcnerf_tc_rowgemm_work_bytes": (sz, []),
     "pcnerf_tc_rowgemm": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     "pcnerf_tc_wgrad": (ci, [vp, vp, ci, ci, ci, i64, vp, ci, ci, vp]),

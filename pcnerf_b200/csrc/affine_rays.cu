@@ -429,6 +429,8 @@ struct AffLayer {
     const float* Wx; int wx_ld;             // l == 0: W_0 (ld 63);  l == 4: W_4[:, :63] (ld 319);  else null
     int init;                               // 1 (l == 0): A is not read
     const float *bias, *gamma, *beta;
+    const float *rmean, *rvar;              // eval mode (running statistics, models.py:183-203 under model.eval()): mean / var of
+                                            // BN_l are these instead of A_l m / diag(A_l C A_l^T); m, C, AC and the small vectors unused
     int nc;
     double eps;
 };
@@ -446,9 +448,12 @@ __global__ void __launch_bounds__(256) k_aff_layer_fwd(AffLayer g) {
     __shared__ double As[16][64];
     __shared__ double ms[64];
     const int tid = threadIdx.x, lr = tid >> 4, q = tid & 15, c = blockIdx.y, row = blockIdx.x * 16 + lr;
+    const bool eval = g.rvar != nullptr;
+    if (!eval) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) Cs[0][tid + 256 * e] = g.C[(size_t)c * 4096 + tid + 256 * e];
-    if (tid < 64) ms[tid] = g.m[c * 64 + tid];
+        for (int e = 0; e < 16; ++e) Cs[0][tid + 256 * e] = g.C[(size_t)c * 4096 + tid + 256 * e];
+        if (tid < 64) ms[tid] = g.m[c * 64 + tid];
+    }
     const size_t idx = ((size_t)row * g.nc + c) * 64 + q;
     double av[4];
 #pragma unroll
@@ -459,6 +464,16 @@ __global__ void __launch_bounds__(256) k_aff_layer_fwd(AffLayer g) {
         if (j == 63) v += (double)g.bias[row];
         av[e] = v;
         As[lr][j] = v;
+    }
+    if (eval) {
+        const double rr = 1.0 / sqrt((double)g.rvar[row] + g.eps), aa = (double)g.gamma[row] * rr;
+        const double s = (double)g.beta[row] - aa * (double)g.rmean[row];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            g.A[idx + 16 * e] = av[e];
+            g.Ab[idx + 16 * e] = aa * av[e] + ((q + 16 * e) == 63 ? s : 0.0);
+        }
+        return;
     }
     __syncthreads();
     double ac[4] = {0.0, 0.0, 0.0, 0.0};
@@ -693,7 +708,8 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
         attr_done = true;
     }
     {
-        PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0, 3);
+        // work: the FMAs of the upper-triangle outer products (36 tiles x 64 per row), 2 FLOP each
+        PcnScope ps(PCN_K_AFFINE_MOMENTS, st, (double)rows * (AFR_TILES * 64) * 2.0, 3);
         k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, AFR_MOM_SMEM, st>>>(src, rows, chunk, base + w.part,
                                                                                                 base + w.shift);
         PCN_LAUNCH_CHECK();
@@ -706,7 +722,8 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     const int N = (int)nc * 64;
     AffRunning run;
     {
-        PcnScope ps(PCN_K_MLP_SMALL, st, 0.0, 17);
+        // work: float64 FLOPs of the seven 256 x 256 x (nc 64) products and of A C (256 x 64 x 64 per layer and chunk)
+        PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 7.0 * 2.0 * 256 * 256 * N + 8.0 * 2.0 * 256 * 64 * N, 17);
         for (int l = 0; l < 8; ++l) {
             const LayerView v = layer_view(base, w, l, nc);
             if (l > 0) {
@@ -722,6 +739,7 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
             g.wx_ld = kLd[l];
             g.init = l == 0;
             g.bias = P->b[l]; g.gamma = P->gamma[l]; g.beta = P->beta[l];
+            g.rmean = nullptr; g.rvar = nullptr;
             g.nc = (int)nc; g.eps = (double)P->eps;
             k_aff_layer_fwd<<<dim3(16, (unsigned)nc), 256, 0, st>>>(g);
             PCN_LAUNCH_CHECK();
@@ -740,6 +758,59 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
         k_affine_apply_rays<<<dim3(parts, (unsigned)nc), 256, 0, st>>>(src, rows, chunk, (const float*)(base + w.alpha), out_p);
         PCN_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+// Eval mode (model.eval(): BatchNorm on its running statistics): alpha is a function of the parameters alone -- the same
+// chain as above with one "chunk" and (mean, var) = (running_mean, running_var); callers cache it per parameter version.
+extern "C" int pcnerf_affine_eval_alpha(const pcnerf_mlp_params* P, float* alpha, void* work, size_t work_bytes, void* stream) {
+    PCN_CHECK_ARG(P && alpha && work, "affine_eval_alpha: null argument");
+    PCN_CHECK_ARG(work_bytes >= work_layout(1).total * sizeof(double), "affine_eval_alpha: work area too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Work w = work_layout(1);
+    double* base = (double*)work;
+    PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 7.0 * 2.0 * 256 * 256 * 64, 16);
+    for (int l = 0; l < 8; ++l) {
+        const LayerView v = layer_view(base, w, l, 1);
+        if (l > 0) {
+            const LayerView pv = layer_view(base, w, l - 1, 1);
+            k_aff_dgemm<float, true, false><<<dim3(2, 8, 1), 128, 0, st>>>(P->W[l] + kOff[l], kLd[l], 1, pv.Ab, 64, 1, v.A, 64, 0,
+                                                                           256, 256);
+            PCN_LAUNCH_CHECK();
+        }
+        AffLayer g;
+        g.A = v.A; g.AC = v.AC; g.Ab = v.Ab; g.a = v.a; g.r = v.r; g.mean = v.mean; g.var = v.var;
+        g.m = nullptr; g.C = nullptr;
+        g.Wx = (l == 0 || l == 4) ? P->W[l] : nullptr;
+        g.wx_ld = kLd[l];
+        g.init = l == 0;
+        g.bias = P->b[l]; g.gamma = P->gamma[l]; g.beta = P->beta[l];
+        g.rmean = P->running_mean[l]; g.rvar = P->running_var[l];
+        g.nc = 1; g.eps = (double)P->eps;
+        k_aff_layer_fwd<<<dim3(16, 1), 256, 0, st>>>(g);
+        PCN_LAUNCH_CHECK();
+    }
+    k_aff_alpha<<<1, 256, 0, st>>>(layer_view(base, w, 7, 1).Ab, P->W[8], P->b[8], 1, alpha);
+    PCN_LAUNCH_CHECK();
+    return 0;
+}
+
+// p_r = sigmoid(alpha . (embed(o + d z_r), 1)) for every (ray, depth) row: the eval-mode closed-form MLP of a sampling pass
+// without an encoding tensor (alpha: 64 floats on the device, from pcnerf_affine_eval_alpha).
+extern "C" int pcnerf_affine_apply_rays(const float* rays, int ld, int64_t n_rays, const float* z, int S, const float* alpha,
+                                        float* out_p, void* stream) {
+    PCN_CHECK_ARG(rays && z && alpha && out_p, "affine_apply_rays: null argument");
+    PCN_CHECK_ARG(ld >= 6 && n_rays >= 0 && S >= 1, "affine_apply_rays: bad shape");
+    const int64_t rows = n_rays * S;
+    PCN_CHECK_ARG(rows < ((int64_t)1 << 31), "affine_apply_rays: %lld rows (limit 2^31 - 1)", (long long)rows);
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const RayRows src{rays, ld, z, S};
+    const int64_t want = pcn_cdiv(rows, 512);               // at least two rows per thread
+    const int parts = (int)(want < 1 ? 1 : (want > 8 * PCN_SM_COUNT ? 8 * PCN_SM_COUNT : want));
+    PcnScope ps(PCN_K_AFFINE, st, (double)rows * 8.0);
+    k_affine_apply_rays<<<dim3(parts, 1), 256, 0, st>>>(src, rows, rows, alpha, out_p);
+    PCN_LAUNCH_CHECK();
     return 0;
 }
 
@@ -762,7 +833,7 @@ extern "C" int pcnerf_affine_backward_rays(const pcnerf_mlp_params* P, const pcn
         k_affine_grad_finish<<<(unsigned)nc, 64, 0, st>>>(base + w.part, parts, base + w.dalpha);
         PCN_LAUNCH_CHECK();
     }
-    PcnScope ps(PCN_K_MLP_SMALL, st, 0.0, 45);
+    PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 14.0 * 2.0 * 256 * 256 * N, 45);       // two products per layer (dW, dAb)
     double* G = base + w.G0;
     double* Gn = base + w.G1;
     k_aff_head_bwd<<<256, 64, 0, st>>>(layer_view(base, w, 7, nc).Ab, base + w.dalpha, P->W[8], (int)nc, G, Gr->dW[8], Gr->db[8]);

@@ -38,10 +38,11 @@ void pcn_set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-// kernel classes of the built-in profiler (pcnerf_prof_*); `work` is algorithmic FLOPs (GEMMs) or bytes (the rest)
+// kernel classes of the built-in profiler (pcnerf_prof_*); `work` is algorithmic FLOPs (GEMMs, the closed-form engine's
+// moments kernel and float64 algebra) or bytes (the rest)
 enum {
     PCN_K_GEMM_FWD = 0, PCN_K_GEMM_DGRAD, PCN_K_GEMM_WGRAD, PCN_K_MLP_SMALL, PCN_K_SAMPLE_ENCODE, PCN_K_COMPOSITE_FWD,
-    PCN_K_COMPOSITE_BWD, PCN_K_AABB, PCN_K_SEARCH, PCN_K_AFFINE, PCN_K_COUNT
+    PCN_K_COMPOSITE_BWD, PCN_K_AABB, PCN_K_SEARCH, PCN_K_AFFINE, PCN_K_AFFINE_MOMENTS, PCN_K_AFFINE_ALGEBRA, PCN_K_COUNT
 };
 
 // Counts kernel launches (always) and, when pcnerf_prof_enable(1) is active, brackets them with CUDA events on the

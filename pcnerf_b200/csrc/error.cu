@@ -28,7 +28,8 @@ static double g_work[PCN_K_COUNT];
 static long long g_count[PCN_K_COUNT];
 
 static const char* k_names[PCN_K_COUNT] = {"mlp_gemm_fwd", "mlp_gemm_dgrad", "mlp_gemm_wgrad", "mlp_small",
-                                           "sample_encode", "composite_fwd", "composite_bwd", "aabb", "search", "affine"};
+                                           "sample_encode", "composite_fwd", "composite_bwd", "aabb", "search", "affine",
+                                           "affine_moments", "affine_algebra"};
 
 PcnScope::PcnScope(int id_, cudaStream_t st_, double work, int nlaunch) : id(id_), st(st_), on(false) {
     g_launches.fetch_add(nlaunch, std::memory_order_relaxed);

@@ -104,18 +104,19 @@ def render_frame(nof_coarse_model, nof_fine_model, embedding_position, dataset_r
     G, S, F = plan.G, int(N_samples), int(N_samples) + int(N_importance)
     tc_c, tc_f = nof_coarse_model.mlp_precision() == 1, nof_fine_model.mlp_precision() == 1
     hr = rays.index_select(0, plan.head_rows)                        # (G,13): one row per physical ray
-    per_ray = F * (128 if tc_f else 256)
+    lazy_c, lazy_f = R._lazy(nof_coarse_model), R._lazy(nof_fine_model)      # closed-form engine: no encoding tensor at all
+    per_ray = F * (8 if lazy_f else 128 if tc_f else 256)
     B = max(1, min(G, FRAME_ENC_BYTES // per_ray))
     zf = torch.empty((G, F), dtype=torch.float32, device=dev)
     pf = torch.empty((G, F), dtype=torch.float32, device=dev)
     for g0 in range(0, G, B):
         h = hr[g0:g0 + B]
-        z, enc = ops.sample_encode_coarse(h, S, 0, 9, 10, 10, 11, False, 0.0, None, True, tc_c)
-        p = nof_coarse_model.forward_encoded(enc, chunk).view(-1, S)
+        z, enc = ops.sample_encode_coarse(h, S, 0, 9, 10, 10, 11, False, 0.0, None, not lazy_c, tc_c)
+        p = nof_coarse_model.forward_encoded(ops.LazyEnc(h, z) if lazy_c else enc, chunk).view(-1, S)
         del enc
         _, w, _, _, _ = ops.search_rows(p, z, h, 6, 7, 1e-10, depth_inference_method)     # the coarse weights (K5 arithmetic)
-        zf_b, encf = ops.sample_encode_fine(h, z, w, int(N_importance), None, True, True, tc_f)
-        pf_b = nof_fine_model.forward_encoded(encf, chunk).view(-1, F)
+        zf_b, encf = ops.sample_encode_fine(h, z, w, int(N_importance), None, True, not lazy_f, tc_f)
+        pf_b = nof_fine_model.forward_encoded(ops.LazyEnc(h, zf_b) if lazy_f else encf, chunk).view(-1, F)
         del encf
         if B >= G:
             zf, pf = zf_b, pf_b

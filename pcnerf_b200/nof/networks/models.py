@@ -189,6 +189,12 @@ class NOF(nn.Module):
                 if last == 1 or chunk == 1:
                     raise ValueError("Expected more than 1 value per channel when training, got input size [1, 256]")
                 return ops.AffineRaysFunction.apply(enc.rays, enc.z, chunk, self._buffers3(), *self.kernel_params())
+            if prec == 2 and not self.training and not torch.is_grad_enabled():
+                # eval mode (running statistics): alpha depends on the parameters only and is cached per parameter version
+                if not hasattr(self, "_eval_fold_cache"):
+                    object.__setattr__(self, "_eval_fold_cache", {})
+                alpha = ops.affine_eval_alpha(self.kernel_params(), self._buffers3(), self._eval_fold_cache)
+                return ops.affine_apply_rays(enc.rays, enc.z, alpha)
             enc = enc.materialise()
         want = torch.float16 if prec == 1 else torch.float32
         if enc.dtype != want:

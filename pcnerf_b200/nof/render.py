@@ -24,8 +24,9 @@ def _tc(model):
 
 
 def _lazy(model):
-    """Training pass of a closed-form (precision 2) model: K2 / K2' write depths only, the engine re-derives the encodings."""
-    return model.mlp_precision() == 2 and model.training
+    """Pass of a closed-form (precision 2) model in training mode, or in eval mode without autograd: K2 / K2' write depths
+    only, the engine re-derives the encodings from (rays, z)."""
+    return model.mlp_precision() == 2 and (model.training or not torch.is_grad_enabled())
 
 
 def _draw_u(n, Ni, device):
@@ -256,12 +257,13 @@ def _view_grouped(model, model_fine, rays, plan, N_samples, N_importance, chunk,
     rays = rays.contiguous()
     hr = rays.index_select(0, plan.head_rows)                       # (G,13) one row per physical ray
     G = plan.G
-    z, enc = ops.sample_encode_coarse(hr, N_samples, 0, 9, 10, 10, 11, False, 0.0, None, True, _tc(model))
-    p = model.forward_encoded(enc, chunk).view(G, N_samples)
+    lazy, lazy_f = _lazy(model), _lazy(model_fine)
+    z, enc = ops.sample_encode_coarse(hr, N_samples, 0, 9, 10, 10, 11, False, 0.0, None, not lazy, _tc(model))
+    p = model.forward_encoded(ops.LazyEnc(hr, z) if lazy else enc, chunk).view(G, N_samples)
     depth_c, w, op_c, peak, wsum = ops.search_rows(p, z, rays, 6, 7, 1e-10, method, row_ray=plan.row_ray)
     flag_c = ops.search_select(plan.other, peak, wsum)
-    zf, encf = ops.sample_encode_fine(hr, z, w, N_importance, None, True, True, _tc(model_fine))
-    pf = model_fine.forward_encoded(encf, chunk).view(G, N_samples + N_importance)
+    zf, encf = ops.sample_encode_fine(hr, z, w, N_importance, None, True, not lazy_f, _tc(model_fine))
+    pf = model_fine.forward_encoded(ops.LazyEnc(hr, zf) if lazy_f else encf, chunk).view(G, N_samples + N_importance)
     depth_f, wf, op_f, peak, wsum = ops.search_rows(pf, zf, rays, 6, 7, 1e-10, method, row_ray=plan.row_ray)
     flag_f = ops.search_select(plan.other, peak, wsum)
     rr = plan.row_ray.to(torch.int64)

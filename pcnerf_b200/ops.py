@@ -606,7 +606,8 @@ class AffineApplyFunction(torch.autograd.Function):
 class LazyEnc:
     """The (rows,64) encoding tensor of a sampling pass, NOT materialised: rows are (ray, depth) pairs and every kernel of the
     closed-form engine that needs a row's encoding re-derives it from rays[:, 0:6] and z (csrc/affine_rays.cu).  Produced by
-    nof/render.py for precision-2 models in training mode; `materialise()` gives the tensor K2 would have written."""
+    nof/render.py for precision-2 models (training passes, and eval-mode passes without autograd); `materialise()` gives the
+    tensor K2 would have written."""
 
     def __init__(self, rays, z):
         self.rays = _cuda_f32(rays, "rays")
@@ -680,6 +681,40 @@ class AffineRaysFunction(torch.autograd.Function):
                                                 _p(out), _p(gp), _p(work), work.numel(), _stream()))
         ctx.work = None
         return (None, None, None, None) + ret
+
+
+def affine_eval_alpha(params, buffers, cache):
+    """alpha (64,) f32 on the device: the eval-mode logit of the closed-form engine is alpha . (x, 1) (running statistics:
+    a function of the parameters alone).  Re-derived (17 small float64 kernels, pcnerf_affine_eval_alpha) only when a parameter
+    or a running statistic was written to since the last call -- same versioning as the folded weights of the tensor-core
+    engine (tensor version counters + note_param_write for library-side writes).  `cache`: a dict owned by the model."""
+    dev = params[0].device
+    ver = (_PARAM_GEN[0],) + tuple((t.data_ptr(), t._version) for t in params) + \
+        tuple((b.data_ptr(), b._version) for grp in buffers[:2] for b in grp)
+    alpha = cache.get("affine_alpha")
+    if alpha is None or alpha.device != dev:
+        if alpha is not None:
+            _SCRATCH_RETIRED.append((alpha, cache.get("affine_work")))     # a captured graph may still reference them
+        alpha = torch.empty(64, dtype=torch.float32, device=dev)
+        cache["affine_alpha"] = alpha
+        cache["affine_work"] = torch.empty(lib().pcnerf_affine_work_bytes(1), dtype=torch.uint8, device=dev)
+        cache["affine_ver"] = None
+    if cache.get("affine_ver") != ver:
+        P = _mlp_params(params, buffers, False, 2)
+        work = cache["affine_work"]
+        check(lib().pcnerf_affine_eval_alpha(ctypes.byref(P), _p(alpha), _p(work), work.numel(), _stream()))
+        cache["affine_ver"] = ver
+    return alpha
+
+
+def affine_apply_rays(rays, z, alpha):
+    """p (n S,) = sigmoid(alpha . (embed(o + d z), 1)) per (ray, depth) row, no encoding tensor (pcnerf_affine_apply_rays)."""
+    rays = _cuda_f32(rays, "rays")
+    z = _cuda_f32(z, "z")
+    n, S = z.shape
+    out = torch.empty(n * S, dtype=torch.float32, device=z.device)
+    check(lib().pcnerf_affine_apply_rays(_p(rays), rays.shape[1], n, _p(z), S, _p(alpha), _p(out), _stream()))
+    return out
 
 
 # -------------------------------------------------------------------------------------------- K4 composite + losses

@@ -202,9 +202,49 @@ def test_rays_engine_accumulates_into_existing_grads_and_rejects_eval():
                                    atol=1e-6 * float(g1[k].abs().max()) + 1e-12, err_msg=k)
     with pytest.raises(ValueError):
         mc.forward_encoded(ops.LazyEnc(rays[:1].to(dev()), z[:1, :1].to(dev())), 64)
-    # eval mode: the lazy rows are materialised and go through the running-statistics path
+    # eval mode without autograd: the rays form of the running-statistics path (test_rays_engine_eval_mode); with autograd
+    # enabled the lazy rows are materialised and take the encoded path
     mc.eval()
-    with torch.no_grad():
-        pe = mc.forward_encoded(lazy, 1024)
-        pm = mc.forward_encoded(lazy.materialise(), 1024)
+    pe = mc.forward_encoded(lazy, 1024)
+    pm = mc.forward_encoded(lazy.materialise(), 1024)
     assert torch.equal(pe, pm)
+
+
+@pytest.mark.parametrize("n,S", [(1, 1), (33, 64), (500, 192), (3000, 7)])
+def test_rays_engine_eval_mode(n, S):
+    """Eval mode (running statistics) on (ray, depth) rows -- pcnerf_affine_eval_alpha + pcnerf_affine_apply_rays -- against
+    the float32 oracle network on the materialised encodings and against the encoded form of the same engine; the cached
+    alpha follows torch-side and library-side parameter writes."""
+    from pcnerf_b200 import ops
+    from pcnerf_b200.optim import FlatAdam
+    rays, z = _ray_rows(n, S, 31 * n + S)
+    pts = (rays[:, None, :3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3)
+    enc = orc.embedding(pts)
+    mc, _, _ = make_nets(42, 43, True, "affine")
+    lazy = ops.LazyEnc(rays.to(dev()), z.to(dev()))
+    if n * S > 1:
+        mc.forward_encoded(lazy, 4096)                  # a training pass first: non-trivial running statistics
+    mc.eval()
+
+    def ref():
+        sd = {k: v.detach().cpu().clone() for k, v in mc.state_dict().items()}
+        return orc.nof_forward(sd, enc, False).reshape(-1).numpy()
+
+    with torch.no_grad():
+        p = mc.forward_encoded(lazy, 4096)
+        pm = mc.forward_encoded(lazy.materialise(), 4096)
+        assert p.shape == (n * S,)
+        np.testing.assert_allclose(p.cpu().numpy(), ref(), rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(p.cpu().numpy(), pm.cpu().numpy(), rtol=5e-6, atol=1e-7)
+        assert torch.equal(p, mc.forward_encoded(lazy, 77))          # cached alpha; `chunk` changes no eval-mode value
+        mc.layer2[0].weight.mul_(1.05)                               # torch-side in-place write
+        mc.layer1[1].running_var.mul_(1.3)
+        p2 = mc.forward_encoded(lazy, 4096)
+        assert not torch.equal(p2, p)
+        np.testing.assert_allclose(p2.cpu().numpy(), ref(), rtol=2e-5, atol=1e-7)
+        opt = FlatAdam(list(mc.parameters()), lr=1e-3, eps=1e-8, weight_decay=1e-3)
+        opt.bucket.flat.normal_(generator=torch.Generator(device=dev()).manual_seed(3))
+        opt.step()                                                   # library-side write (raw pointers)
+        p3 = mc.forward_encoded(lazy, 4096)
+        assert not torch.equal(p3, p2)
+        np.testing.assert_allclose(p3.cpu().numpy(), ref(), rtol=2e-5, atol=1e-7)

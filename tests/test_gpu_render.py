@@ -313,8 +313,13 @@ def test_fused_range_loss_equals_the_nof_loss_modules(use_child):
                      {k: p.grad.clone() for k, p in sys_.named_parameters()})
     for i in range(3):
         np.testing.assert_allclose(out[True][i], out[False][i], rtol=2e-6)
+    top = max(float(g.abs().max()) for g in out[False][3].values())
     for k, g in out[False][3].items():
         scale = float(g.abs().max())
+        if k.endswith(".bias") and k.split(".")[1] in ("layer1", "layer2") and not k.endswith("layer2.7.bias"):
+            # a Linear bias in front of a train-mode BatchNorm has an exactly zero gradient in exact arithmetic: both values
+            # are rounding noise (1e-10 here), to be measured against the gradients that are not
+            scale = top
         assert float((out[True][3][k] - g).abs().max()) <= 2e-5 * scale + 1e-12, k
     # micro-batched accumulation (BASELINE configs[3]) reproduces the one-pass gradient: 4 micro-batches of whole BN chunks
     sys_ = NOFSystem(hp)
