@@ -30,6 +30,7 @@
 #define AFR_FLUSH 4             // sub-tiles (= 160 rows per tile owner) accumulated in fp32 before the fold into fp64 (power of two)
 #define AFR_MOM_SMEM (2 * AFR_T * 64 * 4 + AFR_GROUPS * AFR_TILES * 64 * 4 + AFR_TILES * 64 * 8)     // dynamic shared memory of the moments kernel: two sub-tile buffers, fp32 scratch, fp64 accumulators
 #define AFR_SPLITS 6            // split-K factor of the weight-gradient GEMM (64 tiles x 6 = 384 blocks: one wave of 3 per SM)
+#define AFR_SPLITS_BATCHED 2    // ... of the batched launch over the seven layers of a pass (k_aff_wgrad_batched)
 
 struct RayRows {
     const float* rays;          // (n_rays, ld): origin in columns 0..2, direction in 3..5
@@ -349,16 +350,14 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
 // A(m, k) = A[m a_sm + k a_sk], B(k, n) = B[k b_sk + n b_sn]; *_KC: the operand is contiguous along k (else along m / n) --
 // only the lane -> element mapping of the tile loads depends on it.  M, N multiples of 32, K (per split) of 64.
 template <typename TA, bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(128) k_aff_dgemm(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
-                                                   const double* __restrict__ B, int64_t b_sk, int64_t b_sn,
-                                                   double* __restrict__ C, int64_t ldc, int64_t split_stride, int K,
-                                                   int k_per_split) {
+__device__ __forceinline__ void aff_dgemm_tile(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
+                                               const double* __restrict__ B, int64_t b_sk, int64_t b_sn,
+                                               double* __restrict__ out, int64_t ldc, int k_beg, int k_end) {
     // leading dimension 40: the four k rows of a fragment load start 0 / 8 / 0 / 8 (mod 16) eight-byte banks apart, so the 32
     // lanes of a fragment load touch every bank exactly twice (the minimum for 256 bytes)
     __shared__ double sm[4][2][16][40];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fk = lane & 3;
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-    const int k_beg = blockIdx.z * k_per_split, k_end = min(K, k_beg + k_per_split);
     const int kq = (k_end - k_beg) >> 2;                    // k steps of this warp: [k_beg + w kq, + kq)
     double (*As)[40] = sm[w][0];
     double (*Bs)[40] = sm[w][1];
@@ -405,12 +404,53 @@ __global__ void __launch_bounds__(128) k_aff_dgemm(const TA* __restrict__ A, int
         for (int u = 0; u < 4; ++u)
             *reinterpret_cast<double2*>(red + (w * 32 + 8 * t + fr) * 34 + 8 * u + 2 * fk) = make_double2(c[t][u][0], c[t][u][1]);
     __syncthreads();
-    double* out = C + (size_t)blockIdx.z * split_stride;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int e = tid + 128 * q, r = e >> 5, cc = e & 31;
         out[(int64_t)(m0 + r) * ldc + n0 + cc] = (red[r * 34 + cc] + red[(32 + r) * 34 + cc]) + (red[(64 + r) * 34 + cc] + red[(96 + r) * 34 + cc]);
     }
+}
+
+template <typename TA, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(128) k_aff_dgemm(const TA* __restrict__ A, int64_t a_sm, int64_t a_sk,
+                                                   const double* __restrict__ B, int64_t b_sk, int64_t b_sn,
+                                                   double* __restrict__ C, int64_t ldc, int64_t split_stride, int K,
+                                                   int k_per_split) {
+    const int k_beg = blockIdx.z * k_per_split;
+    aff_dgemm_tile<TA, A_KC, B_KC>(A, a_sm, a_sk, B, b_sk, b_sn, C + (size_t)blockIdx.z * split_stride, ldc, k_beg,
+                                   min(K, k_beg + k_per_split));
+}
+
+// The seven weight-gradient products of a backward pass in ONE launch: blockIdx.z = (layer - 1) * splits + split,
+//   part[layer - 1][split] (256 x 256) = sum over the split's chunks of G_layer Ab_{layer-1}^T     (K = nc 64 per layer)
+struct AffWgradBatch {
+    const double* G[7];          // dL/dA_l, l = 1..7   [256][nc][64]
+    const double* Ab[7];         // Ab_{l-1}
+};
+__global__ void __launch_bounds__(128) k_aff_wgrad_batched(AffWgradBatch b, int N, int splits, int k_per_split,
+                                                           double* __restrict__ part) {
+    const int li = blockIdx.z / splits, sp = blockIdx.z - li * splits, k_beg = sp * k_per_split;
+    const double *Gp = b.G[0], *Ap = b.Ab[0];              // (selects, not a dynamically indexed parameter array: no local copy)
+#pragma unroll
+    for (int i = 1; i < 7; ++i)
+        if (li == i) { Gp = b.G[i]; Ap = b.Ab[i]; }
+    aff_dgemm_tile<double, true, true>(Gp, N, 1, Ap, 1, N, part + (size_t)blockIdx.z * 65536, 256, k_beg,
+                                       min(N, k_beg + k_per_split));
+}
+
+// dW_l[i][k] += sum_splits part[l - 1][s][i][k] for the seven layers (grid (256, 7))
+struct AffWgradOut { float* dW[7]; int ld[7]; };
+__global__ void __launch_bounds__(256) k_aff_wgrad_reduce_batched(const double* __restrict__ part, int splits, AffWgradOut o) {
+    const int li = blockIdx.y, e = blockIdx.x * 256 + threadIdx.x;
+    const double* src = part + (size_t)li * splits * 65536 + e;
+    double s = 0.0;
+    for (int q = 0; q < splits; ++q) s += src[(size_t)q * 65536];
+    float* dW = o.dW[0];
+    int ld = o.ld[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i)
+        if (li == i) { dW = o.dW[i]; ld = o.ld[i]; }
+    dW[(e >> 8) * ld + (e & 255)] += (float)s;
 }
 
 // dW[i][k] += sum_splits part[s][i][k]   (256 x 256 block of a weight gradient with leading dimension ld)
@@ -502,6 +542,126 @@ __global__ void __launch_bounds__(256) k_aff_layer_fwd(AffLayer g) {
     }
 }
 
+// ---- one kernel per layer (the default; PCNERF_AFF_FUSED=0 restores the GEMM + per-layer kernel pairs above / below) ----
+// The chain is a sequence of small dependent kernels (4.2 GFLOP of float64 per fine pass spread over 62 launches of 5-25 us
+// each: launch, cold L2 loads and tail dominate), so each layer is ONE launch per direction: a block owns AFL_ROWS feature
+// rows of ONE chunk -- 32 x 64 elements, everything the BatchNorm algebra of a row needs -- computes its tile of the product
+// with the previous layer on the fp64 tensor pipe (warp w: the eight columns 8 w .. 8 w + 7, four 8 x 8 DMMA tiles; A
+// fragments from the block's W tile in shared memory, B fragments straight from L2 in fragment order) and applies the
+// per-row algebra of k_aff_layer_fwd / k_aff_layer_bwd to it.
+#define AFL_ROWS 32
+#define AFL_AS_LD 66            // tile row stride in doubles: the four rows a warp reads at once land in different banks
+#define AFL_WS_LD 260           // forward W tile [32][256] floats: row stride 260 -> A-fragment loads hit 32 different banks
+#define AFL_WT_LD 40            // backward W^T tile [256][32] floats: row stride 40 -> likewise
+#define AFL_SMEM_FWD (4096 * 8 + AFL_ROWS * AFL_AS_LD * 8 + 64 * 8 + AFL_ROWS * AFL_WS_LD * 4)
+#define AFL_SMEM_BWD (AFL_ROWS * AFL_AS_LD * 8 + 256 * AFL_WT_LD * 4)
+
+__device__ __forceinline__ double oct_sum(double v) {            // sum over the 8 lanes that share a row
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// grid (256 / AFL_ROWS, nc).  W: W_l + kOff_l (ld w_ld), Abp: Ab_{l-1} [256][nc][64] (both unused when g.init)
+__global__ void __launch_bounds__(256) k_aff_fwd_layer(AffLayer g, const float* __restrict__ W, int w_ld,
+                                                       const double* __restrict__ Abp) {
+    extern __shared__ __align__(16) unsigned char afl_raw[];
+    double* Cs = reinterpret_cast<double*>(afl_raw);             // [64][64]
+    double* As = Cs + 4096;                                      // [AFL_ROWS][AFL_AS_LD]
+    double* ms = As + AFL_ROWS * AFL_AS_LD;                      // [64]
+    float* Ws = reinterpret_cast<float*>(ms + 64);               // [AFL_ROWS][AFL_WS_LD]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fk = lane & 3;
+    const int c = blockIdx.y, row0 = blockIdx.x * AFL_ROWS, nc = g.nc;
+    const bool eval = g.rvar != nullptr;
+    if (!g.init) {
+#pragma unroll 8
+        for (int e = 0; e < AFL_ROWS; ++e) {
+            const int idx = tid + 256 * e, r = idx >> 8, k = idx & 255;
+            Ws[r * AFL_WS_LD + k] = W[(size_t)(row0 + r) * w_ld + k];
+        }
+    }
+    if (!eval) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Cs[tid + 256 * e] = g.C[(size_t)c * 4096 + tid + 256 * e];
+        if (tid < 64) ms[tid] = g.m[c * 64 + tid];
+    }
+    __syncthreads();
+    double acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+    if (!g.init) {
+        // eight B fragments are requested at a time and consumed by 32 DMMAs (measured: a register double buffer that ptxas
+        // flattens into just-in-time loads is 30 % SLOWER -- one exposed L2 latency per load instead of one per eight)
+        const size_t ks = (size_t)nc * 64;
+        const double* bp = Abp + (size_t)fk * ks + (size_t)c * 64 + 8 * w + fr;
+        const float* ap = Ws + fr * AFL_WS_LD + fk;
+#pragma unroll 1
+        for (int k0 = 0; k0 < 256; k0 += 32) {
+            double b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) b[u] = bp[(size_t)(k0 + 4 * u) * ks];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) dmma_884(acc[t][0], acc[t][1], (double)ap[8 * t * AFL_WS_LD + k0 + 4 * u], b[u]);
+        }
+    }
+    // A <- product (+ [Wx | 0]) + bias e_63^T
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = 8 * t + fr, j = 8 * w + 2 * fk + h;
+            double v = acc[t][h];
+            if (g.Wx && j < 63) v += (double)g.Wx[(size_t)(row0 + r) * g.wx_ld + j];
+            if (j == 63) v += (double)g.bias[row0 + r];
+            As[r * AFL_AS_LD + j] = v;
+        }
+    __syncthreads();
+    // per-row algebra: 8 lanes per row, lane q owns columns q, q + 8, ..., q + 56
+    const int lr = tid >> 3, q = tid & 7, row = row0 + lr;
+    const size_t idx = ((size_t)row * nc + c) * 64 + q;
+    double av[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) av[e] = As[lr * AFL_AS_LD + q + 8 * e];
+    if (eval) {
+        const double rr = 1.0 / sqrt((double)g.rvar[row] + g.eps), aa = (double)g.gamma[row] * rr;
+        const double sh = (double)g.beta[row] - aa * (double)g.rmean[row];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            g.A[idx + 8 * e] = av[e];
+            g.Ab[idx + 8 * e] = aa * av[e] + ((q + 8 * e) == 63 ? sh : 0.0);
+        }
+        return;
+    }
+    double ac[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ac[e] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < 64; ++k) {
+        const double ak = As[lr * AFL_AS_LD + k];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ac[e] = fma(ak, Cs[k * 64 + q + 8 * e], ac[e]);
+    }
+    double pv = 0.0, pm = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { pv = fma(ac[e], av[e], pv); pm = fma(av[e], ms[q + 8 * e], pm); }
+    pv = oct_sum(pv);
+    pm = oct_sum(pm);
+    const double var = pv > 0.0 ? pv : 0.0;
+    const double rr = 1.0 / sqrt(var + g.eps), aa = (double)g.gamma[row] * rr, sh = (double)g.beta[row] - aa * pm;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        g.A[idx + 8 * e] = av[e];
+        g.AC[idx + 8 * e] = ac[e];
+        g.Ab[idx + 8 * e] = aa * av[e] + ((q + 8 * e) == 63 ? sh : 0.0);
+    }
+    if (q == 0) {
+        const int o = c * 256 + row;
+        g.a[o] = aa; g.r[o] = rr; g.mean[o] = pm; g.var[o] = var;
+    }
+}
+
 // alpha[c][j] = sum_i w_out[i] Ab_7[i][c][j] (+ b_out at j = 63)
 __global__ void __launch_bounds__(256) k_aff_alpha(const double* __restrict__ Ab, const float* __restrict__ wo,
                                                    const float* __restrict__ bo, int nc, float* __restrict__ alpha) {
@@ -566,7 +726,9 @@ __global__ void __launch_bounds__(64) k_aff_head_bwd(const double* __restrict__ 
 }
 
 struct AffLayerBwd {
-    double* G;                              // in: dL/dAb_l, out: dL/dA_l   [256][nc][64]
+    double* G;                              // k_aff_layer_bwd: in dL/dAb_l, out dL/dA_l (in place)   [256][nc][64]
+    const double* Gin;                      // k_aff_bwd_layer: dL/dAb_l when it is not computed by the kernel (l = 7), else null
+    double* Gout;                           // k_aff_bwd_layer: dL/dA_l (kept per layer for the batched weight-gradient launch)
     const double *A, *AC;
     const double *a, *r, *mean, *var, *m;
     const float* gamma;
@@ -592,6 +754,101 @@ __global__ void __launch_bounds__(256) k_aff_layer_bwd(AffLayerBwd g) {
     for (int e = 0; e < 4; ++e)
         g.G[idx + 16 * e] = aa * gv[e] + 2.0 * vbar * g.AC[idx + 16 * e] + mbar * g.m[c * 64 + q + 16 * e];
     if (q == 0) { g.gpart[o] = abar * rr; g.bpart[o] = sbar; }
+}
+
+// Backward of layer l in one launch, grid (256 / AFL_ROWS, nc): the block's tile of dL/dAb_l = W'_{l+1}^T dL/dA_{l+1}
+// (Wn: W_{l+1} + kOff_{l+1}, ld wn_ld; Gn: dL/dA_{l+1}; l = 7: the tile is read from g.Gin instead), then the reverse of the
+// per-row algebra (k_aff_layer_bwd) -> g.Gout = dL/dA_l, g.gpart / g.bpart.
+__global__ void __launch_bounds__(256) k_aff_bwd_layer(AffLayerBwd g, const float* __restrict__ Wn, int wn_ld,
+                                                       const double* __restrict__ Gn) {
+    extern __shared__ __align__(16) unsigned char afl_raw[];
+    double* Gs = reinterpret_cast<double*>(afl_raw);             // [AFL_ROWS][AFL_AS_LD]
+    float* Wt = reinterpret_cast<float*>(Gs + AFL_ROWS * AFL_AS_LD);   // [256][AFL_WT_LD]: Wt[k][m] = W_{l+1}[k][kOff + row0 + m]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fk = lane & 3;
+    const int c = blockIdx.y, row0 = blockIdx.x * AFL_ROWS, nc = g.nc;
+    if (Gn) {
+#pragma unroll 8
+        for (int e = 0; e < 32; ++e) {
+            const int idx = tid + 256 * e, k = idx >> 5, mm = idx & 31;
+            Wt[k * AFL_WT_LD + mm] = Wn[(size_t)k * wn_ld + row0 + mm];
+        }
+        __syncthreads();
+        double acc[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+        const size_t ks = (size_t)nc * 64;
+        const double* bp = Gn + (size_t)fk * ks + (size_t)c * 64 + 8 * w + fr;
+        const float* ap = Wt + fk * AFL_WT_LD + fr;
+#pragma unroll 1
+        for (int k0 = 0; k0 < 256; k0 += 32) {
+            double b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) b[u] = bp[(size_t)(k0 + 4 * u) * ks];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) dmma_884(acc[t][0], acc[t][1], (double)ap[(k0 + 4 * u) * AFL_WT_LD + 8 * t], b[u]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            *reinterpret_cast<double2*>(Gs + (8 * t + fr) * AFL_AS_LD + 8 * w + 2 * fk) = make_double2(acc[t][0], acc[t][1]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + 256 * e, r = idx >> 6, j = idx & 63;
+            Gs[r * AFL_AS_LD + j] = g.Gin[((size_t)(row0 + r) * nc + c) * 64 + j];
+        }
+    }
+    __syncthreads();
+    const int lr = tid >> 3, q = tid & 7, row = row0 + lr;
+    const size_t idx = ((size_t)row * nc + c) * 64 + q;
+    double gv[8], av[8], dot = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { gv[e] = Gs[lr * AFL_AS_LD + q + 8 * e]; av[e] = g.A[idx + 8 * e]; dot = fma(gv[e], av[e], dot); }
+    dot = oct_sum(dot);
+    const double sbar = Gs[lr * AFL_AS_LD + 63];                 // dL/ds = column 63 of dL/dAb
+    const int o = c * 256 + row;
+    const double aa = g.a[o], rr = g.r[o];
+    const double abar = dot - sbar * g.mean[o];
+    const double mbar = -sbar * aa;
+    const double vbar = g.var[o] > 0.0 ? -0.5 * abar * (double)g.gamma[row] * rr * rr * rr : 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        g.Gout[idx + 8 * e] = aa * gv[e] + 2.0 * vbar * g.AC[idx + 8 * e] + mbar * g.m[c * 64 + q + 8 * e];
+    if (q == 0) { g.gpart[o] = abar * rr; g.bpart[o] = sbar; }
+}
+
+// the sums over chunks that end in parameter gradients, all eight layers in one launch: grid (256 (i), 8 (layer)), block 64 (j)
+struct AffColsumBatch {
+    const double* G[8];                     // dL/dA_l
+    const double *gpart[8], *bpart[8];      // [nc][256]
+    float *dgamma[8], *dbeta[8], *dbias[8];
+    float* dWx[8];                          // layers 0 and 4: the block that multiplies the encoding (else null)
+    int wx_ld[8];
+};
+__global__ void __launch_bounds__(64) k_aff_colsum_batched(AffColsumBatch b, int nc) {
+    const int i = blockIdx.x, l = blockIdx.y, j = threadIdx.x;
+    const double *G = b.G[0], *gp = b.gpart[0], *bp = b.bpart[0];
+    float *dg = b.dgamma[0], *dbt = b.dbeta[0], *dbs = b.dbias[0], *dWx = b.dWx[0];
+    int wx_ld = b.wx_ld[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+        if (l == q) {
+            G = b.G[q]; gp = b.gpart[q]; bp = b.bpart[q];
+            dg = b.dgamma[q]; dbt = b.dbeta[q]; dbs = b.dbias[q]; dWx = b.dWx[q]; wx_ld = b.wx_ld[q];
+        }
+    if (dWx || j == 63) {
+        double s = 0.0;
+        for (int c = 0; c < nc; ++c) s += G[((size_t)i * nc + c) * 64 + j];
+        if (j == 63) dbs[i] += (float)s;
+        else dWx[(size_t)i * wx_ld + j] += (float)s;
+    }
+    if (j < 2) {
+        const double* src = j == 0 ? gp : bp;
+        double s = 0.0;
+        for (int c = 0; c < nc; ++c) s += src[c * 256 + i];
+        (j == 0 ? dg : dbt)[i] += (float)s;
+    }
 }
 
 // grid 256 (i), block 64 (j): the sums over chunks that end in parameter gradients of layer l
@@ -622,6 +879,7 @@ namespace {
 
 struct Work {                 // offsets in doubles
     size_t part, shift, m, C, cnt, layer[8], small[8], G0, G1, dalpha, gpart, bpart, wsplit, alpha, total;
+    size_t Gl[8], gpl[8], bpl[8];      // fused backward: dL/dA_l and the per-chunk dgamma / dbeta terms of every layer
     size_t mat;               // 256 * nc * 64
 };
 
@@ -641,8 +899,9 @@ Work work_layout(int64_t nc) {
     w.dalpha = take(nc * 64);
     w.gpart = take(nc * 256);
     w.bpart = take(nc * 256);
-    w.wsplit = take((size_t)AFR_SPLITS * 65536);
+    w.wsplit = take((size_t)7 * AFR_SPLITS * 65536);
     w.alpha = take(nc * 32);              // nc x 64 floats
+    for (int l = 0; l < 8; ++l) { w.Gl[l] = take(w.mat); w.gpl[l] = take(nc * 256); w.bpl[l] = take(nc * 256); }
     w.total = o;
     return w;
 }
@@ -681,6 +940,23 @@ int parts_for(int64_t nc) {
     return (int)(p < 1 ? 1 : (p > AFR_PARTS ? AFR_PARTS : p));
 }
 
+bool aff_fused() {               // one kernel per layer and direction (default) or the GEMM + per-layer kernel pairs
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PCNERF_AFF_FUSED"); v = e ? (atoi(e) != 0) : 1; }
+    return v != 0;
+}
+
+int aff_attrs() {
+    static bool done = false;
+    if (!done) {
+        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, AFR_MOM_SMEM));
+        PCN_CUDA(cudaFuncSetAttribute(k_aff_fwd_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, AFL_SMEM_FWD));
+        PCN_CUDA(cudaFuncSetAttribute(k_aff_bwd_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, AFL_SMEM_BWD));
+        done = true;
+    }
+    return 0;
+}
+
 const int kLd[8] = {63, 256, 256, 256, 319, 256, 256, 256};       // leading dimension of W_l
 const int kOff[8] = {0, 0, 0, 0, 63, 0, 0, 0};                    // first column of the block that multiplies H_{l-1}
 
@@ -702,11 +978,9 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     double* base = (double*)work;
     const RayRows src{rays, ld, z, S};
     const int parts = parts_for(nc);
-    static bool attr_done = false;
-    if (!attr_done) {
-        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, AFR_MOM_SMEM));
-        attr_done = true;
-    }
+    rc = aff_attrs();
+    if (rc) return rc;
+    const bool fused = aff_fused();
     {
         // work: the FMAs of the upper-triangle outer products (36 tiles x 64 per row), 2 FLOP each
         PcnScope ps(PCN_K_AFFINE_MOMENTS, st, (double)rows * (AFR_TILES * 64) * 2.0, 3);
@@ -723,10 +997,10 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     AffRunning run;
     {
         // work: float64 FLOPs of the seven 256 x 256 x (nc 64) products and of A C (256 x 64 x 64 per layer and chunk)
-        PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 7.0 * 2.0 * 256 * 256 * N + 8.0 * 2.0 * 256 * 64 * N, 17);
+        PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 7.0 * 2.0 * 256 * 256 * N + 8.0 * 2.0 * 256 * 64 * N, fused ? 10 : 17);
         for (int l = 0; l < 8; ++l) {
             const LayerView v = layer_view(base, w, l, nc);
-            if (l > 0) {
+            if (l > 0 && !fused) {
                 const LayerView pv = layer_view(base, w, l - 1, nc);
                 k_aff_dgemm<float, true, false><<<dim3(N / 32, 8, 1), 128, 0, st>>>(P->W[l] + kOff[l], kLd[l], 1, pv.Ab, N, 1, v.A,
                                                                                     N, 0, 256, 256);
@@ -741,7 +1015,11 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
             g.bias = P->b[l]; g.gamma = P->gamma[l]; g.beta = P->beta[l];
             g.rmean = nullptr; g.rvar = nullptr;
             g.nc = (int)nc; g.eps = (double)P->eps;
-            k_aff_layer_fwd<<<dim3(16, (unsigned)nc), 256, 0, st>>>(g);
+            if (fused)
+                k_aff_fwd_layer<<<dim3(256 / AFL_ROWS, (unsigned)nc), 256, AFL_SMEM_FWD, st>>>(
+                    g, P->W[l] + kOff[l], kLd[l], l > 0 ? layer_view(base, w, l - 1, nc).Ab : nullptr);
+            else
+                k_aff_layer_fwd<<<dim3(16, (unsigned)nc), 256, 0, st>>>(g);
             PCN_LAUNCH_CHECK();
             run.rm[l] = P->running_mean[l]; run.rv[l] = P->running_var[l]; run.nbt[l] = P->num_batches_tracked[l];
             run.mean[l] = v.mean; run.var[l] = v.var;
@@ -769,10 +1047,13 @@ extern "C" int pcnerf_affine_eval_alpha(const pcnerf_mlp_params* P, float* alpha
     cudaStream_t st = (cudaStream_t)stream;
     const Work w = work_layout(1);
     double* base = (double*)work;
-    PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 7.0 * 2.0 * 256 * 256 * 64, 16);
+    int rc = aff_attrs();
+    if (rc) return rc;
+    const bool fused = aff_fused();
+    PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 7.0 * 2.0 * 256 * 256 * 64, fused ? 9 : 16);
     for (int l = 0; l < 8; ++l) {
         const LayerView v = layer_view(base, w, l, 1);
-        if (l > 0) {
+        if (l > 0 && !fused) {
             const LayerView pv = layer_view(base, w, l - 1, 1);
             k_aff_dgemm<float, true, false><<<dim3(2, 8, 1), 128, 0, st>>>(P->W[l] + kOff[l], kLd[l], 1, pv.Ab, 64, 1, v.A, 64, 0,
                                                                            256, 256);
@@ -787,7 +1068,11 @@ extern "C" int pcnerf_affine_eval_alpha(const pcnerf_mlp_params* P, float* alpha
         g.bias = P->b[l]; g.gamma = P->gamma[l]; g.beta = P->beta[l];
         g.rmean = P->running_mean[l]; g.rvar = P->running_var[l];
         g.nc = 1; g.eps = (double)P->eps;
-        k_aff_layer_fwd<<<dim3(16, 1), 256, 0, st>>>(g);
+        if (fused)
+            k_aff_fwd_layer<<<dim3(256 / AFL_ROWS, 1), 256, AFL_SMEM_FWD, st>>>(g, P->W[l] + kOff[l], kLd[l],
+                                                                                l > 0 ? layer_view(base, w, l - 1, 1).Ab : nullptr);
+        else
+            k_aff_layer_fwd<<<dim3(16, 1), 256, 0, st>>>(g);
         PCN_LAUNCH_CHECK();
     }
     k_aff_alpha<<<1, 256, 0, st>>>(layer_view(base, w, 7, 1).Ab, P->W[8], P->b[8], 1, alpha);
@@ -833,17 +1118,56 @@ extern "C" int pcnerf_affine_backward_rays(const pcnerf_mlp_params* P, const pcn
         k_affine_grad_finish<<<(unsigned)nc, 64, 0, st>>>(base + w.part, parts, base + w.dalpha);
         PCN_LAUNCH_CHECK();
     }
-    PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 14.0 * 2.0 * 256 * 256 * N, 45);       // two products per layer (dW, dAb)
+    const bool fused = aff_fused();
+    PcnScope ps(PCN_K_AFFINE_ALGEBRA, st, 14.0 * 2.0 * 256 * 256 * N, fused ? 12 : 45);       // two products per layer (dW, dAb)
     double* G = base + w.G0;
     double* Gn = base + w.G1;
     k_aff_head_bwd<<<256, 64, 0, st>>>(layer_view(base, w, 7, nc).Ab, base + w.dalpha, P->W[8], (int)nc, G, Gr->dW[8], Gr->db[8]);
     PCN_LAUNCH_CHECK();
     // chunks per split of the weight-gradient GEMM (K = nc * 64)
-    const int cps = (int)pcn_cdiv(nc, AFR_SPLITS), splits = (int)pcn_cdiv(nc, cps);
+    // (the batched launch covers seven layers: two splits already give 7 x 64 x 2 = 896 blocks = two waves of three per SM, and
+    // every warp runs 12 k steps instead of 4 at nc = 24)
+    static int spl_b = -1;
+    if (spl_b < 0) { const char* e = getenv("PCNERF_AFF_SPLITS"); spl_b = e ? atoi(e) : AFR_SPLITS_BATCHED; if (spl_b < 1 || spl_b > AFR_SPLITS) spl_b = AFR_SPLITS_BATCHED; }
+    const int cps = (int)pcn_cdiv(nc, fused ? spl_b : AFR_SPLITS), splits = (int)pcn_cdiv(nc, cps);
+    if (fused) {
+        rc = aff_attrs();
+        if (rc) return rc;
+        AffWgradBatch wb;
+        AffWgradOut wo;
+        AffColsumBatch cb;
+        for (int l = 7; l >= 0; --l) {
+            const LayerView v = layer_view(base, w, l, nc);
+            AffLayerBwd g;
+            g.G = nullptr; g.Gin = l == 7 ? G : nullptr; g.Gout = base + w.Gl[l];
+            g.A = v.A; g.AC = v.AC; g.a = v.a; g.r = v.r; g.mean = v.mean; g.var = v.var; g.m = base + w.m;
+            g.gamma = P->gamma[l]; g.gpart = base + w.gpl[l]; g.bpart = base + w.bpl[l]; g.nc = (int)nc;
+            k_aff_bwd_layer<<<dim3(256 / AFL_ROWS, (unsigned)nc), 256, AFL_SMEM_BWD, st>>>(
+                g, l < 7 ? P->W[l + 1] + kOff[l + 1] : nullptr, l < 7 ? kLd[l + 1] : 0, l < 7 ? base + w.Gl[l + 1] : nullptr);
+            PCN_LAUNCH_CHECK();
+            cb.G[l] = base + w.Gl[l]; cb.gpart[l] = base + w.gpl[l]; cb.bpart[l] = base + w.bpl[l];
+            cb.dgamma[l] = Gr->dgamma[l]; cb.dbeta[l] = Gr->dbeta[l]; cb.dbias[l] = Gr->db[l];
+            cb.dWx[l] = (l == 0 || l == 4) ? Gr->dW[l] : nullptr;
+            cb.wx_ld[l] = kLd[l];
+            if (l > 0) {
+                wb.G[l - 1] = base + w.Gl[l]; wb.Ab[l - 1] = layer_view(base, w, l - 1, nc).Ab;
+                wo.dW[l - 1] = Gr->dW[l] + kOff[l]; wo.ld[l - 1] = kLd[l];
+            }
+        }
+        // dW'_l += sum_chunks dL/dA_l Ab_{l-1}^T for l = 1..7, and the column sums of every layer
+        k_aff_wgrad_batched<<<dim3(8, 8, 7 * splits), 128, 0, st>>>(wb, N, splits, cps * 64, base + w.wsplit);
+        PCN_LAUNCH_CHECK();
+        k_aff_wgrad_reduce_batched<<<dim3(256, 7), 256, 0, st>>>(base + w.wsplit, splits, wo);
+        PCN_LAUNCH_CHECK();
+        k_aff_colsum_batched<<<dim3(256, 8), 64, 0, st>>>(cb, (int)nc);
+        PCN_LAUNCH_CHECK();
+        return 0;
+    }
     for (int l = 7; l >= 0; --l) {
         const LayerView v = layer_view(base, w, l, nc);
         AffLayerBwd g;
-        g.G = G; g.A = v.A; g.AC = v.AC; g.a = v.a; g.r = v.r; g.mean = v.mean; g.var = v.var; g.m = base + w.m;
+        g.G = G; g.Gin = nullptr; g.Gout = nullptr;
+        g.A = v.A; g.AC = v.AC; g.a = v.a; g.r = v.r; g.mean = v.mean; g.var = v.var; g.m = base + w.m;
         g.gamma = P->gamma[l]; g.gpart = base + w.gpart; g.bpart = base + w.bpart; g.nc = (int)nc;
         k_aff_layer_bwd<<<dim3(16, (unsigned)nc), 256, 0, st>>>(g);
         PCN_LAUNCH_CHECK();

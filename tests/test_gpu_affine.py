@@ -248,3 +248,17 @@ def test_rays_engine_eval_mode(n, S):
         p3 = mc.forward_encoded(lazy, 4096)
         assert not torch.equal(p3, p2)
         np.testing.assert_allclose(p3.cpu().numpy(), ref(), rtol=2e-5, atol=1e-7)
+
+
+def test_rays_engine_unfused_chain_in_a_subprocess():
+    """PCNERF_AFF_FUSED=0 (read once per process) selects the GEMM + per-layer kernel pairs the fused per-layer kernels replaced:
+    the same parity test must pass on that path too."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PCNERF_AFF_FUSED="0")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_affine.py"), "-k",
+                        "test_rays_engine_vs_oracle_and_encoded_engine or test_rays_engine_eval_mode"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
