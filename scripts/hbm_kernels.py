@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--Ni", type=int, default=256)
     ap.add_argument("--f16", type=int, default=1)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--flush", choices=["read", "write"], default="read",
+                    help="how the 126 MB L2 is emptied between launches: by READING a 256 MB buffer (clean lines) or by WRITING it "
+                         "(dirty lines: their write-back to HBM then runs during, and is charged to, the timed kernel)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -44,7 +47,14 @@ def main():
     rays[:, 12], rays[:, 13] = rays[:, 10], rays[:, 11]
     rays = rays.to(dev)
     esz = 128.0 if a.f16 else 256.0
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2, rewritten between launches
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2, read (or rewritten) between launches
+    flush32 = flush.view(torch.int32)
+
+    def l2_flush():
+        if a.flush == "write":
+            flush.zero_()
+        else:
+            flush32.sum()            # reads 256 MB: the L2 ends up full of clean, unrelated lines
 
     def timed(fn):
         for _ in range(2):
@@ -52,7 +62,7 @@ def main():
         torch.cuda.synchronize()
         tot = 0.0
         for _ in range(a.reps):
-            flush.zero_()
+            l2_flush()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -61,7 +71,7 @@ def main():
             tot += e0.elapsed_time(e1)
         return tot / a.reps
 
-    out = {"rays": n, "S": S, "Ni": Ni, "rows_f16": bool(a.f16), "peak_gbs": peak, "l2": "256 MB flush between launches",
+    out = {"rays": n, "S": S, "Ni": Ni, "rows_f16": bool(a.f16), "peak_gbs": peak, "l2": "256 MB %s between launches" % ("read (clean lines)" if a.flush == "read" else "written (dirty lines)"),
            "kernels": {}}
 
     def report(name, ms, nbytes):
@@ -97,7 +107,7 @@ def main():
         loss = o[1].sum() + o[2] + o[3]
         ops.profile(True)
         for _ in range(a.reps):
-            flush.zero_()
+            l2_flush()
             loss.backward(retain_graph=True)
         torch.cuda.synchronize()
         prof = ops.profile_read()
