@@ -18,6 +18,7 @@
 // Data-sized kernels: k_affine_moments_rays (second moments: the only O(rows x 64 x 64) work, upper triangle only),
 // k_affine_apply_rays, k_affine_grad_rays.  Test infrastructure compares against the torch formulation of the same algebra
 // (NOF._affine_coeffs) and the fp32 engine (tests/test_gpu_affine.py).
+#include <cstring>
 #include "common.cuh"
 #include "encode.cuh"
 
@@ -235,6 +236,257 @@ __global__ void __launch_bounds__(AFR_THREADS, 2) k_affine_moments_rays(RayRows 
         const int t_j = t_i + tt, el = e & 63;
         out[(t_i * 8 + (el >> 3)) * 64 + t_j * 8 + (el & 7)] = accs[e];
     }
+}
+
+// ---- the same sums on the legacy tensor path: mma.sync.m16n8k8 with 3 x TF32 operands ---------------------------------
+// Measured on a B200 (scripts/micro/mma_sync_rate.cu, profiles/r02_s2_mma_sync_rate.txt): register-fed mma.sync tf32 issues
+// 0.5 MMA per clock and SM = 512 FMA/clk, packed FFMA2 1.75 per clock = 112 FMA/clk (below the 128 of plain FFMA: the
+// packed form saves issue slots, not pipe cycles).  With every fp32 value split as x = hi + lo (hi = tf32(x), lo = tf32(x - hi):
+// 22 mantissa bits) and the products taken as lo hi + hi lo + hi hi (the dropped lo lo term is 2^-22 of the product) the
+// tensor path is worth 170 fp32-grade FMA per clock on a pipe of its own -- the encode work of the producer warps no
+// longer competes with the outer products for the FMA pipe.
+//   * the moment matrix is y^T y with M = N = the 64 columns and K = the rows: A(m, k) = y[k][m], B(k, n) = y[k][n] are the
+//     SAME shared-memory tile, and the A fragment of the 16 columns 16 mi .. is the pair of B fragments 2 mi, 2 mi + 1;
+//   * upper triangle in 16 x 8 tiles: (mi, nj) with nj >= 2 mi, 20 tiles in four sets of five, one per consumer warp, which
+//     owns them for every row: 20 accumulator registers and its own fp64 accumulators (no atomics), fragments of the next
+//     8-row step in flight while the 15 MMAs of the current one issue;
+//   * producers: warp p fills ring buffer p of four (sub-tiles p, p + 4, ...: 32 rows, one per lane): encode, split, 16 + 16
+//     STS.128 into the hi / lo tiles (row stride 72 words: the fragment loads of a warp hit 32 different banks).  A first
+//     form with two 64-row buffers, each filled by its own pair of warps, left ONE pair encoding at a time and was
+//     producer-latency-bound (1.55 ms per C2 step against 1.33 ms for the FFMA2 kernel);
+//   * measured (C2 closed-form step, same box, ms per step for the moment kernels): FFMA2 kernel 1.30; this kernel 1.55 (two
+//     64-row buffers), 1.70 (MMAs issued tile by tile behind asm volatile), 1.51 (A quads loaded instead of copied), 1.34
+//     (four tile sets, no atomics, fragments one step ahead).  Same parity, same speed: with the outer products off the FMA
+//     pipe the tensor pipe sits at ~30 % and BOTH kernels wait for their four producer warps per CTA (one row per thread
+//     at ~120 registers: 8 encoding warps per SM, where the stand-alone apply kernel encodes the same rows in 0.28 ms with
+//     64 warps per SM).  Opt-in (PCNERF_AFF_MOMENTS=tc) until the producers are restructured; FFMA2 stays the default.
+//   * fp32 accumulation over AMT_FLUSH sub-tiles (128 rows), then added into fp64 accumulators in shared memory.  The tensor core truncates its fp32 accumulator, so sums of like-signed products (the diagonal) come
+//     out low by ~1e-6 relative -- a common scaling of the covariance that BatchNorm's own normalisation absorbs layer by
+//     layer (parity gates in tests/test_gpu_affine.py are unchanged).
+#define AMT_T 32                // rows per sub-tile = one producer warp
+#define AMT_NBUF 4              // ring of sub-tile buffers, buffer p is filled by producer warp p
+#define AMT_LD 72               // row stride of the hi / lo tiles in 32-bit words
+#define AMT_TILE (AMT_T * AMT_LD)
+#define AMT_FLUSH 4             // sub-tiles (128 rows) between folds of a warp's fp32 accumulators into its fp64 ones (power of two)
+#define AMT_SMEM (AMT_NBUF * 2 * AMT_TILE * 4 + 4096 * 8)          // ring x (hi, lo) + accs [64][64] fp64 = 106,496 bytes
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// A fragment of 16 columns starting at p (= the lane's element of column block 2 mi, step row t4):
+// (y[t4][c], y[t4][c + 8], y[t4 + 4][c], y[t4 + 4][c + 8])
+__device__ __forceinline__ void amt_lds4(uint32_t (&a)[4], const uint32_t* p, uint32_t zero) {
+    // `zero` is a run-time 0 the compiler cannot fold: the address differs formally from the B fragments' and the loads stay
+    // (derived from the B registers, ptxas re-assembled the interleaved quads in front of almost every MMA: 2 IMAD.MOV per HMMA)
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(p) + zero;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a[0]) : "r"(sa));
+    asm volatile("ld.shared.b32 %0, [%1+32];" : "=r"(a[1]) : "r"(sa));
+    asm volatile("ld.shared.b32 %0, [%1+1152];" : "=r"(a[2]) : "r"(sa));          // + 4 rows = 4 * AMT_LD * 4 bytes
+    asm volatile("ld.shared.b32 %0, [%1+1184];" : "=r"(a[3]) : "r"(sa));
+}
+
+// The 20 tiles (mi, nj), nj >= 2 mi, in four sets of five, one per consumer warp (SET = warp index):
+//   0: mi 0, nj 0..4      1: mi 0, nj 5..7 + mi 3, nj 6..7      2: mi 1, nj 2..6      3: mi 1, nj 7 + mi 2, nj 4..7
+// A warp owns its tiles for ALL rows (four 8-row steps per sub-tile), so its fp64 accumulators are its own (no atomics).
+template <int SET> struct AmtSet;
+template <> struct AmtSet<0> { static constexpr int MA = 0, NA0 = 0, NA = 5, MB = 0, NB0 = 0, NB = 0; };
+template <> struct AmtSet<1> { static constexpr int MA = 0, NA0 = 5, NA = 3, MB = 3, NB0 = 6, NB = 2; };
+template <> struct AmtSet<2> { static constexpr int MA = 1, NA0 = 2, NA = 5, MB = 1, NB0 = 2, NB = 0; };
+template <> struct AmtSet<3> { static constexpr int MA = 1, NA0 = 7, NA = 1, MB = 2, NB0 = 4, NB = 4; };
+
+// fragments of one 8-row step: B pairs of the set's column blocks and the A quads of its (one or two) row blocks, hi and lo
+template <int SET>
+struct AmtFrag {
+    uint32_t bh[5][2], bl[5][2], ahA[4], alA[4], ahB[4], alB[4];
+    __device__ __forceinline__ void load(const uint32_t* __restrict__ h0, const uint32_t* __restrict__ l0, uint32_t zero) {
+        using S = AmtSet<SET>;
+#pragma unroll
+        for (int q = 0; q < S::NA; ++q) {
+            bh[q][0] = h0[8 * (S::NA0 + q)]; bh[q][1] = h0[4 * AMT_LD + 8 * (S::NA0 + q)];
+            bl[q][0] = l0[8 * (S::NA0 + q)]; bl[q][1] = l0[4 * AMT_LD + 8 * (S::NA0 + q)];
+        }
+#pragma unroll
+        for (int q = 0; q < S::NB; ++q) {
+            bh[S::NA + q][0] = h0[8 * (S::NB0 + q)]; bh[S::NA + q][1] = h0[4 * AMT_LD + 8 * (S::NB0 + q)];
+            bl[S::NA + q][0] = l0[8 * (S::NB0 + q)]; bl[S::NA + q][1] = l0[4 * AMT_LD + 8 * (S::NB0 + q)];
+        }
+        amt_lds4(ahA, h0 + 16 * S::MA, zero); amt_lds4(alA, l0 + 16 * S::MA, zero);
+        if (S::NB > 0) { amt_lds4(ahB, h0 + 16 * S::MB, zero); amt_lds4(alB, l0 + 16 * S::MB, zero); }
+    }
+    // the three products of a tile (lo hi, hi lo, hi hi: small terms first) as three passes over the five tiles
+    __device__ __forceinline__ void mma(float (&acc)[5][4]) const {
+        using S = AmtSet<SET>;
+#define AMT_PASS(AA_, AB_, B_)                                                                              \
+        do {                                                                                                \
+            _Pragma("unroll") for (int q = 0; q < S::NA; ++q)                                               \
+                mma_tf32(acc[q], AA_[0], AA_[1], AA_[2], AA_[3], B_[q][0], B_[q][1]);                       \
+            _Pragma("unroll") for (int q = 0; q < S::NB; ++q)                                               \
+                mma_tf32(acc[S::NA + q], AB_[0], AB_[1], AB_[2], AB_[3], B_[S::NA + q][0], B_[S::NA + q][1]); \
+        } while (0)
+        AMT_PASS(alA, alB, bh);
+        AMT_PASS(ahA, ahB, bl);
+        AMT_PASS(ahA, ahB, bh);
+#undef AMT_PASS
+    }
+};
+
+// one 32-row sub-tile (four steps) of tile set SET; the fragments of step ks + 1 are requested before the MMAs of step ks
+template <int SET>
+__device__ __forceinline__ void amt_consume(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, float (&acc)[5][4],
+                                            int g, int t4, uint32_t zero) {
+    const uint32_t* h0 = hi + t4 * AMT_LD + g;
+    const uint32_t* l0 = lo + t4 * AMT_LD + g;
+    AmtFrag<SET> f0, f1;
+    f0.load(h0, l0, zero);
+    f1.load(h0 + 8 * AMT_LD, l0 + 8 * AMT_LD, zero);
+    f0.mma(acc);
+    f0.load(h0 + 16 * AMT_LD, l0 + 16 * AMT_LD, zero);
+    f1.mma(acc);
+    f1.load(h0 + 24 * AMT_LD, l0 + 24 * AMT_LD, zero);
+    f0.mma(acc);
+    f1.mma(acc);
+}
+
+// (mi, nj) of accumulator tile e of tile set `set`
+__device__ __forceinline__ void amt_tile_of(int set, int e, int& mi, int& nj) {
+    switch (set) {
+        case 0: mi = 0; nj = e; break;
+        case 1: mi = e < 3 ? 0 : 3; nj = e < 3 ? 5 + e : 3 + e; break;
+        case 2: mi = 1; nj = 2 + e; break;
+        default: mi = e < 1 ? 1 : 2; nj = e < 1 ? 7 : 3 + e; break;
+    }
+}
+
+// named barriers 1 + b (FULL) / 5 + b (EMPTY) of ring buffer b: 32 producer threads + 128 consumer threads
+__device__ __forceinline__ void amt_full_sync(int b) {
+    switch (b) { case 0: bar_sync_id<1, 160>(); break; case 1: bar_sync_id<2, 160>(); break;
+                 case 2: bar_sync_id<3, 160>(); break; default: bar_sync_id<4, 160>(); }
+}
+__device__ __forceinline__ void amt_full_arrive(int b) {
+    switch (b) { case 0: bar_arrive_id<1, 160>(); break; case 1: bar_arrive_id<2, 160>(); break;
+                 case 2: bar_arrive_id<3, 160>(); break; default: bar_arrive_id<4, 160>(); }
+}
+__device__ __forceinline__ void amt_empty_sync(int b) {
+    switch (b) { case 0: bar_sync_id<5, 160>(); break; case 1: bar_sync_id<6, 160>(); break;
+                 case 2: bar_sync_id<7, 160>(); break; default: bar_sync_id<8, 160>(); }
+}
+__device__ __forceinline__ void amt_empty_arrive(int b) {
+    switch (b) { case 0: bar_arrive_id<5, 160>(); break; case 1: bar_arrive_id<6, 160>(); break;
+                 case 2: bar_arrive_id<7, 160>(); break; default: bar_arrive_id<8, 160>(); }
+}
+
+struct RowRaw { float z, o0, o1, o2, d0, d1, d2; };
+__device__ __forceinline__ RowRaw row_raw(const RayRows& s, int64_t r) {
+    const uint32_t ray = (uint32_t)r / (uint32_t)s.S;
+    const float* q = s.rays + (int64_t)ray * s.ld;
+    RowRaw v;
+    v.z = __ldg(s.z + r);
+    v.o0 = __ldg(q); v.o1 = __ldg(q + 1); v.o2 = __ldg(q + 2);
+    v.d0 = __ldg(q + 3); v.d1 = __ldg(q + 4); v.d2 = __ldg(q + 5);
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 2) k_affine_moments_rays_tc(RayRows src, int64_t rows, int64_t chunk,
+                                                                   double* __restrict__ part, double* __restrict__ shift_out) {
+    extern __shared__ __align__(16) uint32_t xt[];          // [AMT_NBUF][hi, lo][AMT_T][AMT_LD] | accs [64][64] fp64
+    __shared__ float shift[4];
+    double* accs = reinterpret_cast<double*>(xt + AMT_NBUF * 2 * AMT_TILE);
+    const int ci = blockIdx.y, pi = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    int64_t c_beg, r_beg, r_end;
+    part_range(rows, chunk, ci, pi, c_beg, r_beg, r_end);
+    if (tid == 0) ray_row_pos(src, c_beg, shift[0], shift[1], shift[2]);
+    for (int e = tid; e < 4096; e += 256) accs[e] = 0.0;
+    __syncthreads();
+    if (pi == 0 && tid < 64) shift_out[ci * 64 + tid] = tid < 3 ? (double)shift[tid] : 0.0;
+    const int nt = (int)((r_end - r_beg + AMT_T - 1) / AMT_T);
+    if (tid < 128) {
+        // producer warp p: sub-tiles p, p + 4, ... into ring buffer p, one row per lane; the raw ray / depth values of the
+        // NEXT sub-tile are requested before the current one is encoded
+        const int p = tid >> 5;
+        const float s0 = shift[0], s1 = shift[1], s2 = shift[2];
+        uint32_t* hi = xt + p * 2 * AMT_TILE + lane * AMT_LD;
+        uint32_t* lo = hi + AMT_TILE;
+        int64_t r = r_beg + (int64_t)p * AMT_T + lane;
+        RowRaw cur = {};
+        if (r < r_end) cur = row_raw(src, r);
+        for (int t = p; t < nt; t += AMT_NBUF, r += AMT_NBUF * AMT_T) {
+            const int64_t rn = r + AMT_NBUF * AMT_T;
+            RowRaw nxt = {};
+            if (rn < r_end) nxt = row_raw(src, rn);
+            float e[64];
+            if (r < r_end) {
+                const float x0 = __fadd_rn(cur.o0, __fmul_rn(cur.d0, cur.z)), x1 = __fadd_rn(cur.o1, __fmul_rn(cur.d1, cur.z)),
+                            x2 = __fadd_rn(cur.o2, __fmul_rn(cur.d2, cur.z));          // nof/render.py:458, as ray_row_pos
+                enc_visit_poly(x0, x1, x2, [&](int col, float v) { e[col] = v; });
+                e[0] -= s0; e[1] -= s1; e[2] -= s2;
+                e[63] = 1.f;
+            } else {
+#pragma unroll
+                for (int col = 0; col < 64; ++col) e[col] = 0.f;
+            }
+            if (t >= AMT_NBUF) amt_empty_sync(p);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    h[q] = to_tf32(e[4 * c + q]);
+                    l[q] = to_tf32(e[4 * c + q] - __uint_as_float(h[q]));
+                }
+                *reinterpret_cast<uint4*>(hi + 4 * c) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(lo + 4 * c) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            __threadfence_block();
+            amt_full_arrive(p);
+            cur = nxt;
+        }
+        return;
+    }
+    const int cw = (tid - 128) >> 5, g = lane >> 2, t4 = lane & 3;
+    const uint32_t zero = (gridDim.z - 1u) * 4u;             // 0 at run time (amt_lds4)
+    float acc[5][4];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
+    auto flush = [&]() {
+        // the warp's own 5 x 128 elements of accs: plain read-modify-write, 20 independent chains
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            int mi, nj;
+            amt_tile_of(cw, e, mi, nj);
+            double2* d = reinterpret_cast<double2*>(accs + (16 * mi + g) * 64 + 8 * nj + 2 * t4);
+            double2 v0 = d[0], v1 = d[8 * 32];
+            v0.x += (double)acc[e][0]; v0.y += (double)acc[e][1];
+            v1.x += (double)acc[e][2]; v1.y += (double)acc[e][3];
+            d[0] = v0; d[8 * 32] = v1;
+            acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
+        }
+    };
+    for (int t = 0; t < nt; ++t) {
+        const int b = t & (AMT_NBUF - 1);
+        amt_full_sync(b);
+        const uint32_t* hi = xt + b * 2 * AMT_TILE;
+        switch (cw) {
+            case 0: amt_consume<0>(hi, hi + AMT_TILE, acc, g, t4, zero); break;
+            case 1: amt_consume<1>(hi, hi + AMT_TILE, acc, g, t4, zero); break;
+            case 2: amt_consume<2>(hi, hi + AMT_TILE, acc, g, t4, zero); break;
+            default: amt_consume<3>(hi, hi + AMT_TILE, acc, g, t4, zero); break;
+        }
+        if (t + AMT_NBUF < nt) amt_empty_arrive(b);
+        if ((t & (AMT_FLUSH - 1)) == AMT_FLUSH - 1) flush();
+    }
+    if (nt & (AMT_FLUSH - 1)) flush();
+    bar_sync_id<9, 128>();
+    // every element of the 20 tiles (a superset of the 8 x 8 tiles k_affine_moments_reduce reads); the rest stays zero
+    double* out = part + ((size_t)ci * gridDim.x + pi) * 4096;
+    for (int e = tid - 128; e < 4096; e += 128) out[e] = accs[e];
 }
 
 // S[ci][e] = sum over the chunk's parts (upper-triangle tiles only; fixed order: deterministic)
@@ -946,10 +1198,17 @@ bool aff_fused() {               // one kernel per layer and direction (default)
     return v != 0;
 }
 
+bool aff_moments_tc() {          // second moments on packed fp32 FFMA2 (default) or on mma.sync 3 x TF32 (PCNERF_AFF_MOMENTS=tc)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PCNERF_AFF_MOMENTS"); v = (e && !strcmp(e, "tc")) ? 1 : 0; }
+    return v != 0;
+}
+
 int aff_attrs() {
     static bool done = false;
     if (!done) {
         PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, AFR_MOM_SMEM));
+        PCN_CUDA(cudaFuncSetAttribute(k_affine_moments_rays_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, AMT_SMEM));
         PCN_CUDA(cudaFuncSetAttribute(k_aff_fwd_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, AFL_SMEM_FWD));
         PCN_CUDA(cudaFuncSetAttribute(k_aff_bwd_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, AFL_SMEM_BWD));
         done = true;
@@ -984,8 +1243,12 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     {
         // work: the FMAs of the upper-triangle outer products (36 tiles x 64 per row), 2 FLOP each
         PcnScope ps(PCN_K_AFFINE_MOMENTS, st, (double)rows * (AFR_TILES * 64) * 2.0, 3);
-        k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, AFR_MOM_SMEM, st>>>(src, rows, chunk, base + w.part,
-                                                                                                base + w.shift);
+        if (aff_moments_tc())
+            k_affine_moments_rays_tc<<<dim3(parts, (unsigned)nc), 256, AMT_SMEM, st>>>(src, rows, chunk, base + w.part,
+                                                                                          base + w.shift);
+        else
+            k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, AFR_MOM_SMEM, st>>>(src, rows, chunk, base + w.part,
+                                                                                                    base + w.shift);
         PCN_LAUNCH_CHECK();
         k_affine_moments_reduce<<<dim3(16, (unsigned)nc), 256, 0, st>>>(base + w.part, parts, base + w.G0);    // (G0: free until backward)
         PCN_LAUNCH_CHECK();

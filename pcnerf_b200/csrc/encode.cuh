@@ -72,6 +72,13 @@ __device__ __forceinline__ void sincos_turn(int fr, float& sn, float& cs) {
     cs = __uint_as_float(__float_as_uint(b) ^ (((q + 1u) & 2u) << 30));
 }
 
+// |x| >= ENC_BIG, NaN, Inf (never in a real scene): sc[2 k], sc[2 k + 1] = sincosf(2^k x), what torch computes.  OUT OF LINE:
+// inlined, the thirty Payne-Hanek bodies made every kernel that re-derives encodings 3,700 - 5,400 SASS instructions long
+// (60 - 85 KB), and half of the stall samples of the moment kernels' producer warps were instruction-fetch stalls.
+static __device__ __noinline__ void enc_coord_slow(float x, float* sc) {
+    for (int k = 0; k < 10; ++k) sincosf((float)(1 << k) * x, sc + 2 * k, sc + 2 * k + 1);
+}
+
 template <int C, class F>
 __device__ __forceinline__ void enc_visit_coord_poly(float x, F&& f) {
     if (fabsf(x) < ENC_BIG) {
@@ -85,12 +92,12 @@ __device__ __forceinline__ void enc_visit_coord_poly(float x, F&& f) {
             f(6 + 6 * k + C, cs);
         }
     } else {
+        float sc[20];
+        enc_coord_slow(x, sc);
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
-            float sn, cs;
-            sincosf((float)(1 << k) * x, &sn, &cs);
-            f(3 + 6 * k + C, sn);
-            f(6 + 6 * k + C, cs);
+            f(3 + 6 * k + C, sc[2 * k]);
+            f(6 + 6 * k + C, sc[2 * k + 1]);
         }
     }
 }

@@ -250,13 +250,16 @@ def test_rays_engine_eval_mode(n, S):
         np.testing.assert_allclose(p3.cpu().numpy(), ref(), rtol=2e-5, atol=1e-7)
 
 
-def test_rays_engine_unfused_chain_in_a_subprocess():
-    """PCNERF_AFF_FUSED=0 (read once per process) selects the GEMM + per-layer kernel pairs the fused per-layer kernels replaced:
-    the same parity test must pass on that path too."""
+@pytest.mark.parametrize("var,val", [("PCNERF_AFF_FUSED", "0"), ("PCNERF_AFF_MOMENTS", "tc")])
+def test_rays_engine_alternative_kernels_in_a_subprocess(var, val):
+    """Switches read once per process: PCNERF_AFF_FUSED=0 selects the GEMM + per-layer kernel pairs the fused per-layer kernels
+    replaced, PCNERF_AFF_MOMENTS=tc the second-moment kernel on mma.sync with 3 x TF32 operands.  The same parity tests must
+    pass on those paths too."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, PCNERF_AFF_FUSED="0")
+    env = dict(os.environ)
+    env[var] = val
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_affine.py"), "-k",
                         "test_rays_engine_vs_oracle_and_encoded_engine or test_rays_engine_eval_mode"],
