@@ -610,18 +610,24 @@ def run_b200(a):
             # dominant kernel: the second-moment kernel is fp32 FMA work (rows x 2,304 FMA, upper triangle of x x^T), bounded
             # by the CUDA-core FMA pipe -- neither HBM (8 bytes per row are read) nor the tensor cores
             barrier()
+            clocks_f = ClockSampler(local)                # own clock samples: this step is not power-capped like the headline
+            clocks_f.start()
+            time.sleep(1.2)                               # nvidia-smi needs ~1 s to come up
+            t_f0 = time.time()
             ops.profile(True)
-            psteps = min(a.steps, 2)
+            psteps = 60                                   # ~0.25 s of eager steps: a few 100-ms clock samples under load
             for _ in range(psteps):
                 step(False)
             torch.cuda.synchronize()
             prof_f = ops.profile_read()
             ops.profile(False)
+            clk_f = clocks_f.stop(t_f0, time.time())
+            fast["clocks"] = clk_f
             fast["kernels"] = {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[1] / psteps}
                                for k, v in prof_f.items() if v[1]}
             m_ms, m_n, m_fl = prof_f.get("affine_moments", (0.0, 0, 0.0))
             a_ms, a_n, a_fl = prof_f.get("affine_algebra", (0.0, 0, 0.0))
-            sm_mhz = float((clk or {}).get("sm_mhz") or 0.0) or 1965.0
+            sm_mhz = float((clk_f or {}).get("sm_mhz") or 0.0) or float((clk_f or {}).get("sm_max_mhz") or 0.0) or 1965.0
             fma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
             if m_ms > 0:
                 tf = m_fl / (m_ms * 1e-3) / 1e12
