@@ -111,7 +111,7 @@ __device__ __forceinline__ void bar_arrive(int b) { if (b) bar_arrive_id<ID0 + 1
 // memory.
 __global__ void __launch_bounds__(AFR_THREADS, 2) k_affine_moments_rays(RayRows src, int64_t rows, int64_t chunk,
                                                                         double* __restrict__ part,
-                                                                        double* __restrict__ shift_out) {
+                                                                        double* __restrict__ shift_out, int dbg) {
     extern __shared__ __align__(16) float xs[];             // 2 x [AFR_T][64] | scratch [3][36][64] fp32 | acc [36][64] fp64
     __shared__ float shift[64];
     float* scratch = xs + 2 * AFR_T * 64;
@@ -139,7 +139,12 @@ __global__ void __launch_bounds__(AFR_THREADS, 2) k_affine_moments_rays(RayRows 
             const int64_t r = r_beg + (int64_t)t * AFR_T + tid;
             if (tid < AFR_T) {
                 float e[64];
-                if (r < r_end) {
+                if (r < r_end && dbg) {                  // timing experiment (PCNERF_AFF_DEBUG=1, wrong results): free producers
+                    float x0, x1, x2;
+                    ray_row_pos(src, r, x0, x1, x2);
+#pragma unroll
+                    for (int col = 0; col < 64; ++col) e[col] = x0 * (float)(col + 1);
+                } else if (r < r_end) {
                     float x0, x1, x2;
                     ray_row_pos(src, r, x0, x1, x2);
                     enc_visit_poly(x0, x1, x2, [&](int col, float v) { e[col] = v; });
@@ -256,10 +261,11 @@ __global__ void __launch_bounds__(AFR_THREADS, 2) k_affine_moments_rays(RayRows 
 //     producer-latency-bound (1.55 ms per C2 step against 1.33 ms for the FFMA2 kernel);
 //   * measured (C2 closed-form step, same box, ms per step for the moment kernels): FFMA2 kernel 1.30; this kernel 1.55 (two
 //     64-row buffers), 1.70 (MMAs issued tile by tile behind asm volatile), 1.51 (A quads loaded instead of copied), 1.34
-//     (four tile sets, no atomics, fragments one step ahead).  Same parity, same speed: with the outer products off the FMA
-//     pipe the tensor pipe sits at ~30 % and BOTH kernels wait for their four producer warps per CTA (one row per thread
-//     at ~120 registers: 8 encoding warps per SM, where the stand-alone apply kernel encodes the same rows in 0.28 ms with
-//     64 warps per SM).  Opt-in (PCNERF_AFF_MOMENTS=tc) until the producers are restructured; FFMA2 stays the default.
+//     (four tile sets, no atomics, fragments one step ahead).  Same parity, same speed -- and not because of the producers:
+//     with PCNERF_AFF_DEBUG=1 (producers write a cheap function of the position, results wrong) the FFMA2 kernel takes 1.14
+//     and this one 1.17 ms.  Both saturate the shared-memory pipe (26 - 35 wavefronts per row at one per clock and SM: here
+//     every element is loaded as a 4-byte fragment by 4.5 of the consumer warps and the hi / lo stores run at a two-way bank
+//     conflict); the tensor pipe sits at ~30 %.  Opt-in (PCNERF_AFF_MOMENTS=tc); FFMA2 stays the default.
 //   * fp32 accumulation over AMT_FLUSH sub-tiles (128 rows), then added into fp64 accumulators in shared memory.  The tensor core truncates its fp32 accumulator, so sums of like-signed products (the diagonal) come
 //     out low by ~1e-6 relative -- a common scaling of the covariance that BatchNorm's own normalisation absorbs layer by
 //     layer (parity gates in tests/test_gpu_affine.py are unchanged).
@@ -395,7 +401,8 @@ __device__ __forceinline__ RowRaw row_raw(const RayRows& s, int64_t r) {
 }
 
 __global__ void __launch_bounds__(256, 2) k_affine_moments_rays_tc(RayRows src, int64_t rows, int64_t chunk,
-                                                                   double* __restrict__ part, double* __restrict__ shift_out) {
+                                                                   double* __restrict__ part, double* __restrict__ shift_out,
+                                                                   int dbg) {
     extern __shared__ __align__(16) uint32_t xt[];          // [AMT_NBUF][hi, lo][AMT_T][AMT_LD] | accs [64][64] fp64
     __shared__ float shift[4];
     double* accs = reinterpret_cast<double*>(xt + AMT_NBUF * 2 * AMT_TILE);
@@ -422,7 +429,11 @@ __global__ void __launch_bounds__(256, 2) k_affine_moments_rays_tc(RayRows src, 
             RowRaw nxt = {};
             if (rn < r_end) nxt = row_raw(src, rn);
             float e[64];
-            if (r < r_end) {
+            if (r < r_end && dbg) {                      // timing experiment (PCNERF_AFF_DEBUG=1, wrong results): free producers
+                const float x0 = __fadd_rn(cur.o0, __fmul_rn(cur.d0, cur.z));
+#pragma unroll
+                for (int col = 0; col < 64; ++col) e[col] = x0 * (float)(col + 1);
+            } else if (r < r_end) {
                 const float x0 = __fadd_rn(cur.o0, __fmul_rn(cur.d0, cur.z)), x1 = __fadd_rn(cur.o1, __fmul_rn(cur.d1, cur.z)),
                             x2 = __fadd_rn(cur.o2, __fmul_rn(cur.d2, cur.z));          // nof/render.py:458, as ray_row_pos
                 enc_visit_poly(x0, x1, x2, [&](int col, float v) { e[col] = v; });
@@ -1243,12 +1254,14 @@ extern "C" int pcnerf_affine_forward_rays(const pcnerf_mlp_params* P, const floa
     {
         // work: the FMAs of the upper-triangle outer products (36 tiles x 64 per row), 2 FLOP each
         PcnScope ps(PCN_K_AFFINE_MOMENTS, st, (double)rows * (AFR_TILES * 64) * 2.0, 3);
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("PCNERF_AFF_DEBUG"); dbg = e ? atoi(e) : 0; }
         if (aff_moments_tc())
             k_affine_moments_rays_tc<<<dim3(parts, (unsigned)nc), 256, AMT_SMEM, st>>>(src, rows, chunk, base + w.part,
-                                                                                          base + w.shift);
+                                                                                          base + w.shift, dbg);
         else
             k_affine_moments_rays<<<dim3(parts, (unsigned)nc), AFR_THREADS, AFR_MOM_SMEM, st>>>(src, rows, chunk, base + w.part,
-                                                                                                    base + w.shift);
+                                                                                                    base + w.shift, dbg);
         PCN_LAUNCH_CHECK();
         k_affine_moments_reduce<<<dim3(16, (unsigned)nc), 256, 0, st>>>(base + w.part, parts, base + w.G0);    // (G0: free until backward)
         PCN_LAUNCH_CHECK();
