@@ -519,9 +519,11 @@ def run_b200(a):
         names = {"mlp_gemm_fwd": "mlp forward row GEMM (%s)" % ("k_tc_rowgemm2<FWD>: TMA + tcgen05.mma.cta_group::2 + TMEM, CTA pairs"
                                                                  if a.precision == "tc" else "k_gemm fp32"),
                  "mlp_gemm_dgrad": "mlp data-gradient row GEMM with the BN backward in its epilogue (%s)"
-                                   % ("k_tc_rowgemm<DGRAD>: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32"),
+                                   % ("k_tc_rowgemm2<DGRAD2>: TMA + tcgen05.mma.cta_group::2 + TMEM, CTA pairs, the H term of the "
+                                      "BN backward on the tensor core" if a.precision == "tc" else "k_gemm fp32"),
                  "mlp_gemm_wgrad": "mlp weight-gradient GEMM, split-K over the rows (%s)"
-                                   % ("k_tc_wgrad: TMA + tcgen05 + TMEM" if a.precision == "tc" else "k_gemm fp32")}
+                                   % ("k_tc_wgrad2: TMA + tcgen05.mma.cta_group::2 + TMEM, CTA pairs" if a.precision == "tc"
+                                      else "k_gemm fp32")}
         cls = {}
         for k, (ms_k, n_k, fl_k) in (("mlp_gemm_fwd", (f_ms, f_n, f_fl)), ("mlp_gemm_dgrad", (d_ms, d_n, d_fl)),
                                     ("mlp_gemm_wgrad", (w_ms, w_n, w_fl))):
@@ -545,7 +547,7 @@ def run_b200(a):
                 tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
                 if a.precision == "tc" and CHUNK == tr["rows"] and dom in tr:
                     traffic = tr[dom]["dram_bytes_read"] + tr[dom]["dram_bytes_write"]
-                    traffic_src = "static: one ncu --set full capture of this kernel (profiles/r02_traffic.json: %s), not measured in this run" % tr[dom]["source"]
+                    traffic_src = "static: one ncu --set full capture of %s (profiles/r02_traffic.json: %s), not measured in this run" % (tr[dom].get("kernel", "this kernel"), tr[dom]["source"])
             except (OSError, ValueError, KeyError):
                 pass
             c = cls[dom]
