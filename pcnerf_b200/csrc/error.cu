@@ -16,7 +16,7 @@ void pcn_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* pcnerf_last_error(void) { return g_err; }
-extern "C" int pcnerf_version(void) { return 103; }
+extern "C" int pcnerf_version(void) { return 104; }     // 104: pcnerf_affine_eval_alpha, pcnerf_affine_apply_rays
 
 // ---------------------------------------------------------------------------------------------------------------
 static std::atomic<long long> g_launches{0};
