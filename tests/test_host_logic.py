@@ -112,3 +112,25 @@ def test_hoisted_reciprocal_division_matches_ieee_division():
             q = Fraction(float(rn(q + r * rc)))            # fma(r, rc, q)
         bad += (np.float32(float(q)) != rn(A / D))
     assert bad == 0
+
+
+def test_closed_form_rows_are_lazy_only_where_the_engine_can_take_them():
+    """nof/render.py::_lazy decides when K2 / K2' write depths only and the closed-form engine re-derives the encodings
+    (csrc/affine_rays.cu): training passes of a precision-2 model, eval passes without autograd -- never for the layered
+    engines, and never for an eval pass that autograd records (those get the encoding tensor).  Host logic only: no kernel
+    runs; a CPU tensor must be refused by the row container like by every other op (no CPU fallback)."""
+    import pytest
+    import torch
+    from pcnerf_b200 import ops
+    from pcnerf_b200.nof import render
+    from pcnerf_b200.nof.networks import NOF_coarse
+    m = NOF_coarse()
+    for prec, train, grad, want in (("affine", True, True, True), ("affine", True, False, True), ("affine", False, False, True),
+                                    ("affine", False, True, False), ("tc", True, True, False), ("tc", False, False, False),
+                                    ("fp32", True, True, False), ("fp32", False, False, False)):
+        m.precision = prec
+        m.train(train)
+        with torch.set_grad_enabled(grad):
+            assert render._lazy(m) is want, (prec, train, grad)
+    with pytest.raises((ValueError, TypeError, RuntimeError)):
+        ops.LazyEnc(torch.zeros(4, 15), torch.zeros(4, 8))
